@@ -1,0 +1,80 @@
+"""ctypes binding of libfvt_b200.so — the only door between the Python host code and the sm_100a kernels.
+
+There is no CPU fallback: `load()` raises if the shared library is missing, and every compute entry point
+returns FVT_ERR_UNSUPPORTED_ARCH on a non-sm_100 device, which `check()` turns into an exception.
+"""
+import ctypes
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libfvt_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "fvt_b200.h")
+
+FVT_CONV_RELU = 1
+FVT_CONV_RESIDUAL = 2
+FVT_CONV_STATS = 4
+
+
+class FvtError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of `fvt_conv_desc` (include/fvt_b200.h)."""
+    _fields_ = [(k, ctypes.c_int32) for k in (
+        "n", "t", "h", "w", "cin", "cout", "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw", "flags", "block_n")]
+
+    def key(self):
+        return tuple(getattr(self, k) for k, _ in self._fields_)
+
+
+_lib = None
+
+
+def header_symbols():
+    """Names of every function declared in include/fvt_b200.h (used by the export test)."""
+    with open(HEADER_PATH) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fvt_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """Load the shared library (building it is `fastvideotagging_b200.build.build()`'s job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FvtError(
+            "libfvt_b200.so is not built (%s). Run `python -m fastvideotagging_b200.build` — there is no "
+            "CPU fallback for the R(2+1)D hot path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, fp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p
+    dp = ctypes.POINTER(ConvDesc)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    sigs = {
+        "fvt_version": (ctypes.c_int, []),
+        "fvt_last_error": (ctypes.c_char_p, []),
+        "fvt_device_check": (ctypes.c_int, [ctypes.c_int]),
+        "fvt_conv3d_out_shape": (ctypes.c_int, [dp, ip, ip, ip]),
+        "fvt_conv3d_block_n": (ctypes.c_int, [dp]),
+        "fvt_conv3d_packed_weight_elems": (ctypes.c_size_t, [dp]),
+        "fvt_pack_conv_weight": (ctypes.c_int, [dp, fp, i32, i32, vp, vp]),
+        "fvt_conv3d_fwd": (ctypes.c_int, [dp, vp, vp, fp, fp, vp, vp, fp, vp]),
+        "fvt_stem_unfold": (ctypes.c_int, [fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+        "fvt_pool_fc_fwd": (ctypes.c_int, [vp, i32, i32, i32, i32, fp, fp, i32, fp, fp, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status < 0:
+        msg = load().fvt_last_error()
+        raise FvtError("libfvt_b200 error %d: %s" % (status, msg.decode() if msg else "?"))
+    return status

@@ -1,0 +1,91 @@
+"""Tensor-level wrappers over the C ABI: torch is used for device memory and streams only."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, FVT_CONV_RELU, FVT_CONV_RESIDUAL, FVT_CONV_STATS, check
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.FvtError("%s must live on a CUDA device: the R(2+1)D hot path has no CPU fallback" % name)
+
+
+def conv_desc(n, t, h, w, cin, cout, kernel, stride=(1, 1, 1), pad=(0, 0, 0), flags=0, block_n=0):
+    return ConvDesc(n, t, h, w, cin, cout, kernel[0], kernel[1], kernel[2], stride[0], stride[1], stride[2],
+                    pad[0], pad[1], pad[2], flags, block_n)
+
+
+def conv_out_shape(desc):
+    lib = _lib.load()
+    a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    check(lib.fvt_conv3d_out_shape(ctypes.byref(desc), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def pack_conv_weight(desc, w_oidhw):
+    """fp32 (O, I, kT, kH, kW) device tensor -> packed bf16 weights for `desc` (zero padded)."""
+    lib = _lib.load()
+    require_cuda(w_oidhw, "weight")
+    w = w_oidhw.detach().to(torch.float32).contiguous()
+    elems = lib.fvt_conv3d_packed_weight_elems(ctypes.byref(desc))
+    if elems == 0:
+        check(-1)
+    out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
+    check(lib.fvt_pack_conv_weight(ctypes.byref(desc), _ptr(w), w.shape[0], w.shape[1], _ptr(out), _stream()))
+    return out
+
+
+def conv3d_fwd(desc, x, w_packed, scale=None, shift=None, residual=None, out=None, stats=None):
+    """x: (N, T, H, W, Cin) bf16 contiguous -> (N, To, Ho, Wo, Cout) bf16."""
+    lib = _lib.load()
+    require_cuda(x, "x")
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    assert tuple(x.shape) == (desc.n, desc.t, desc.h, desc.w, desc.cin), (tuple(x.shape), desc.key())
+    to, ho, wo = conv_out_shape(desc)
+    if out is None:
+        out = torch.empty((desc.n, to, ho, wo, desc.cout), dtype=torch.bfloat16, device=x.device)
+    check(lib.fvt_conv3d_fwd(ctypes.byref(desc), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(residual),
+                             _ptr(out), _ptr(stats), _stream()))
+    return out
+
+
+def stem_unfold(x_ncdhw, kw_taps=7, sw=2, pw=3, cu=32, out=None):
+    """(N, 3, T, H, W) fp32 -> (N, T, H, Wo, cu) bf16 with u[..., kw*3+ci] = x[n, ci, t, h, ow*sw-pw+kw]."""
+    lib = _lib.load()
+    require_cuda(x_ncdhw, "clips")
+    assert x_ncdhw.dtype == torch.float32 and x_ncdhw.is_contiguous() and x_ncdhw.shape[1] == 3
+    n, _, t, h, w = x_ncdhw.shape
+    wo = (w + 2 * pw - kw_taps) // sw + 1
+    if out is None:
+        out = torch.empty((n, t, h, wo, cu), dtype=torch.bfloat16, device=x_ncdhw.device)
+    check(lib.fvt_stem_unfold(_ptr(x_ncdhw), _ptr(out), n, t, h, w, kw_taps, sw, pw, cu, _stream()))
+    return out
+
+
+def pool_fc_fwd(x, c_real, weight, bias, want_pooled=False):
+    """x: (N, T, H, W, C) bf16 -> logits (N, num_class) fp32 [and pooled (N, c_real) fp32]."""
+    lib = _lib.load()
+    require_cuda(x, "x")
+    n = x.shape[0]
+    c = x.shape[-1]
+    positions = x.numel() // (n * c)
+    num_class = weight.shape[0] if weight is not None else 0
+    logits = torch.empty((n, num_class), dtype=torch.float32, device=x.device) if weight is not None else None
+    pooled = torch.empty((n, c_real), dtype=torch.float32, device=x.device) if want_pooled else None
+    check(lib.fvt_pool_fc_fwd(_ptr(x), n, positions, c, c_real, _ptr(weight), _ptr(bias), num_class, _ptr(pooled),
+                              _ptr(logits), _stream()))
+    return (logits, pooled) if want_pooled else logits

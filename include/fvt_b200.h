@@ -1,0 +1,94 @@
+/*
+ * fvt_b200.h — C ABI of the B200-native R(2+1)D hot path (libfvt_b200.so).
+ *
+ * The reference (bruceyang2012/FastVideoTagging) has no operator code of its own: every arithmetic step of
+ * model/R2Plus1.py, net.py and model/mlc_loss.py is an MXNet operator (cuDNN/cuBLAS/mshadow).  This header is the
+ * replacement boundary for exactly those operator calls; each entry point cites the reference call sites it
+ * stands in for.  Plain C: raw device pointers, sizes and a cudaStream_t (passed as void*).
+ *
+ * Conventions
+ *   - activations: NDHWC bf16, channel count stored padded to a multiple of 16 ("stored channels"); pad
+ *     channels hold zeros.
+ *   - every function is stream-ordered and allocates nothing; the caller owns all buffers.
+ *   - return value: 0 on success, negative fvt_status otherwise; fvt_last_error() gives a thread-local message.
+ *   - no CPU fallback: on a device that is not sm_100 the compute entry points return FVT_ERR_UNSUPPORTED_ARCH.
+ */
+#ifndef FVT_B200_H_
+#define FVT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum fvt_status {
+  FVT_OK = 0,
+  FVT_ERR_BAD_DESC = -1,
+  FVT_ERR_UNSUPPORTED_ARCH = -2,
+  FVT_ERR_MISALIGNED = -3,
+  FVT_ERR_WORKSPACE = -4,
+  FVT_ERR_CUDA = -5,
+  FVT_ERR_DRIVER = -6
+} fvt_status;
+
+/* epilogue / mode flags for fvt_conv_desc.flags */
+#define FVT_CONV_RELU 1      /* y = max(y, 0)                       (Activation 'relu', R2Plus1.py:33,60,81)   */
+#define FVT_CONV_RESIDUAL 2  /* y += residual before the ReLU       (nd.relu(y+x), R2Plus1.py:81; net.py:100)   */
+#define FVT_CONV_STATS 4     /* accumulate per-channel sum, sum^2 of the raw conv output (training BatchNorm) */
+
+/* One 3-D convolution (cross-correlation, no bias, dilation 1) — the parameters of nn.Conv3D / mx.sym.Convolution
+ * at R2Plus1.py:27-31,34-38,67-70,100-111 and net.py:40-42,49-51,95-96,122-131. */
+typedef struct fvt_conv_desc {
+  int32_t n, t, h, w;     /* input extent                                                   */
+  int32_t cin;            /* stored input channels (multiple of 16)                          */
+  int32_t cout;           /* stored output channels (multiple of 16)                         */
+  int32_t kt, kh, kw;     /* filter                                                         */
+  int32_t st, sh, sw;     /* stride                                                         */
+  int32_t pt, ph, pw;     /* symmetric zero padding                                         */
+  int32_t flags;          /* FVT_CONV_*                                                     */
+  int32_t block_n;        /* N tile of the implicit GEMM; 0 = library default               */
+} fvt_conv_desc;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int fvt_version(void);
+const char* fvt_last_error(void);
+/* 0 if `device` is an sm_100 part and the driver exposes the tensor-map encoders, else a negative status. */
+int fvt_device_check(int device);
+
+/* ---- convolution (K1) ----------------------------------------------------------------------------------- */
+/* Output extent floor((x + 2p - k)/s) + 1 per axis (MXNet convention). */
+int fvt_conv3d_out_shape(const fvt_conv_desc* d, int32_t* to, int32_t* ho, int32_t* wo);
+/* N tile the library will use for this descriptor (multiple of 16, <= 256). */
+int fvt_conv3d_block_n(const fvt_conv_desc* d);
+/* Number of bf16 elements of the packed weight buffer: rows(cout rounded up to whole N tiles) x kt*kh*kw*cin. */
+size_t fvt_conv3d_packed_weight_elems(const fvt_conv_desc* d);
+/* Pack fp32 weights in the reference layout (O, I, kT, kH, kW) (device pointer, cout_real x cin_real filters)
+ * into the K-major bf16 layout K1 consumes; rows/channels beyond the real counts are zero. */
+int fvt_pack_conv_weight(const fvt_conv_desc* d, const float* w_oidhw, int32_t cout_real, int32_t cin_real,
+                         void* w_packed, void* stream);
+/* y = epilogue(conv(x, w)):  acc*scale[c] + shift[c] (if scale != NULL)  (+ residual)  (ReLU)  -> bf16.
+ * stats (FVT_CONV_STATS): float[2*cout], sum then sum of squares of the bf16-rounded raw conv output,
+ * atomically accumulated — zero it first. */
+int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                   const float* shift, const void* residual, void* y, float* stats, void* stream);
+
+/* ---- stem input transform --------------------------------------------------------------------------------- */
+/* Clips in the reference layout NCDHW fp32 (data/data.py:46-47) with 3 channels -> W-unfolded NDHWC bf16
+ * u[n,t,h,ow, kw*3+ci] = x[n,ci,t,h, ow*sw - pw + kw] (zero outside), channels >= 3*kw_taps are zero.
+ * The 1x7x7/s(1,2,2) stem conv (R2Plus1.py:100-104, net.py:122-123) then runs on K1 as a (1,7,1)/s(1,2,1)
+ * conv over u with cin = cu. */
+int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+                    int32_t sw, int32_t pw, int32_t cu, void* stream);
+
+/* ---- head: global average pool + dense (A5) ------------------------------------------------------------------ */
+/* x: [n, positions, c] bf16 (NDHWC with T*H*W flattened); pooled (optional out): [n, c] fp32;
+ * logits[n, k] = sum_c pooled[n,c] * w[k,c] + b[k]   (AvgPool3D + Dense, R2Plus1.py:168-171,243-245). */
+int fvt_pool_fc_fwd(const void* x, int32_t n, int32_t positions, int32_t c, int32_t c_real, const float* w,
+                    const float* b, int32_t num_class, float* pooled, float* logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVT_B200_H_ */
