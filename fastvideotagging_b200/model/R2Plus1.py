@@ -1,0 +1,192 @@
+"""Host-side mirror of reference model/R2Plus1.py: the R(2+1)D block builder API on top of the sm_100a kernels.
+
+Same public names and argument meaning as the reference (`get_spatial_temporal_conv`, `R3DBlock`, `BLOCK_CONFIG`,
+`R2Plus2D`, `get_R2plus1d`); MXNet is not installable on this platform, so the containers are torch.nn.Modules
+(the "PyTorch extension" branch of the boundary) and tensors are torch CUDA tensors in the reference's NCDHW fp32
+layout.  All arithmetic happens in libfvt_b200.so; there is no eager/CPU fallback.
+"""
+import math
+import os
+
+import torch
+
+from .. import engine
+from ..engine import BLOCK_CONFIG, middle_filters  # noqa: F401  (BLOCK_CONFIG re-exported like the reference)
+
+BN_EPS_GLUON = 1e-5      # nn.BatchNorm() default used throughout model/R2Plus1.py
+BN_EPS_SYMBOL = 1e-3     # mx.sym.BatchNorm(eps=1e-3) in net.py
+BN_MOMENTUM = 0.9
+
+
+def xavier_uniform_(tensor, factor_type="avg", magnitude=3.0, generator=None):
+    """mx.init.Xavier (uniform): U(-s, s), s = sqrt(magnitude / factor), fan = channels * prod(kernel)
+    (train_simple_r3d.py:81 uses the defaults; train.py:88 uses factor_type='in', magnitude=2.34)."""
+    shape = tensor.shape
+    hw = 1
+    for s in shape[2:]:
+        hw *= s
+    fan_in, fan_out = shape[1] * hw, shape[0] * hw
+    factor = {"avg": (fan_in + fan_out) / 2.0, "in": fan_in, "out": fan_out}[factor_type]
+    s = math.sqrt(magnitude / factor)
+    with torch.no_grad():
+        tensor.uniform_(-s, s, generator=generator)
+    return tensor
+
+
+class R2Plus2D(torch.nn.Module):
+    """R(2+1)D-{10,16,18,26,34} (reference model/R2Plus1.py:93-254).
+
+    forward(x): x is (N, 3, T, H, W) fp32 on a CUDA device; returns (N, num_class) fp32 logits (no activation,
+    :171).  `final_temporal_kernel` / `final_spatial_kernel` are the AvgPool3D window and must cover the whole
+    conv5 map (T/8, H/16), as every reference caller arranges (train.py:39-40, R2Plus1.py:370).
+    """
+
+    def __init__(self, num_class, model_depth, final_spatial_kernel=7, final_temporal_kernel=2, with_bias=False,
+                 bn_eps=BN_EPS_GLUON):
+        super().__init__()
+        if with_bias:
+            raise NotImplementedError("with_bias=True is never used by the reference callers; conv bias is not built")
+        self.num_class = num_class
+        self.model_depth = model_depth
+        self.pool = (final_temporal_kernel, final_spatial_kernel, final_spatial_kernel)
+        self.bn_eps = bn_eps
+        pshapes, ashapes = engine.parameter_shapes(model_depth, num_class)
+        self._param_names = list(pshapes)
+        self._aux_names = list(ashapes)
+        for name, shape in pshapes.items():
+            if name.endswith("_gamma"):
+                init = torch.ones(shape)
+            elif name.endswith("_beta") or name.endswith("_bias"):
+                init = torch.zeros(shape)
+            else:
+                init = torch.zeros(shape)
+            self.register_parameter(name, torch.nn.Parameter(init))
+        for name, shape in ashapes.items():
+            self.register_buffer(name, torch.ones(shape) if name.endswith("_var") else torch.zeros(shape))
+        # name lists kept for load_from_sym_params compatibility (model/R2Plus1.py:174-227)
+        self.base_name = self.set_base_name()
+        self.dense0_name = ["final_fc_weight", "final_fc_bias"]
+        self._plans = {}
+        self._weights_version = 0
+
+    # ------------------------------------------------------------------ reference helpers
+    @staticmethod
+    def set_base_name():
+        return ["conv1_middle_weight",
+                "conv1_middle_spatbn_relu_gamma", "conv1_middle_spatbn_relu_beta",
+                "conv1_middle_spatbn_relu_moving_mean", "conv1_middle_spatbn_relu_moving_var",
+                "conv1_weight",
+                "conv1_spatbn_relu_gamma", "conv1_spatbn_relu_beta",
+                "conv1_spatbn_relu_moving_mean", "conv1_spatbn_relu_moving_var"]
+
+    @staticmethod
+    def add_comp_count_index(change_channels=False, downsampling=False, comp_index=-1, prefix=None):
+        names = []
+        for conv_idx in (1, 2):
+            names += ["comp_%d_conv_%d_middle_weight" % (comp_index, conv_idx)]
+            names += ["comp_%d_spatbn_%d_middle_%s" % (comp_index, conv_idx, s) for s in ("gamma", "beta", "moving_mean", "moving_var")]
+            names += ["comp_%d_conv_%d_weight" % (comp_index, conv_idx)]
+            names += ["comp_%d_spatbn_%d_%s" % (comp_index, conv_idx, s) for s in ("gamma", "beta", "moving_mean", "moving_var")]
+        if change_channels or downsampling:
+            names += ["shortcut_projection_%d_weight" % comp_index]
+            names += ["shortcut_projection_%d_spatbn_%s" % (comp_index, s) for s in ("gamma", "beta", "moving_mean", "moving_var")]
+        return names
+
+    # ------------------------------------------------------------------ gluon-style parameter protocol
+    def initialize(self, init=None, ctx=None, seed=None, factor_type="avg", magnitude=3.0):
+        """net.initialize(init.Xavier(), ctx) (train_simple_r3d.py:81): Xavier-uniform weights, gamma=1, beta=0,
+        running mean 0 / var 1, dense bias 0."""
+        device = ctx if ctx is not None else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if isinstance(device, (list, tuple)):
+            device = device[0]
+        if device is not None:
+            self.to(device)
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device=self.final_fc_weight.device)
+            gen.manual_seed(seed)
+        for name in self._param_names:
+            p = getattr(self, name)
+            if name.endswith("_weight"):
+                xavier_uniform_(p.data, factor_type, magnitude, gen)
+            elif name.endswith("_gamma"):
+                p.data.fill_(1.0)
+            else:
+                p.data.zero_()
+        for name in self._aux_names:
+            b = getattr(self, name)
+            b.fill_(1.0) if name.endswith("_var") else b.zero_()
+        self.invalidate()
+        return self
+
+    def collect_params(self):
+        return {n: getattr(self, n) for n in self._param_names + self._aux_names}
+
+    def load_param_dict(self, arrays, with_dense=True, strict=True):
+        """Load {symbol-API name: array-like}.  `arg:`/`aux:` prefixes of MXNet checkpoints are stripped
+        (model/R2Plus1.py:262-265)."""
+        clean = {k.split(":")[-1]: v for k, v in arrays.items()}
+        missing = []
+        with torch.no_grad():
+            for name in self._param_names + self._aux_names:
+                if name.startswith("final_fc") and not with_dense:
+                    continue
+                if name not in clean:
+                    missing.append(name)
+                    continue
+                dst = getattr(self, name)
+                src = torch.as_tensor(clean[name]).to(dst.device, dst.dtype)
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError("shape mismatch for %s: %s vs %s" % (name, tuple(src.shape), tuple(dst.shape)))
+                dst.copy_(src)
+        if strict and missing:
+            raise KeyError("missing parameters: %s" % missing[:5])
+        self.invalidate()
+        return missing
+
+    def save_parameters(self, filename):
+        torch.save({k: v.detach().cpu() for k, v in self.collect_params().items()}, filename)
+
+    def load_parameters(self, filename, ctx=None):
+        self.load_param_dict(torch.load(filename, map_location="cpu"))
+        if ctx is not None:
+            self.to(ctx[0] if isinstance(ctx, (list, tuple)) else ctx)
+
+    load_params = load_parameters   # deprecated gluon alias used at train_simple_r3d.py:92
+
+    def load_from_sym_params(self, f, ctx=None, with_dense=False):
+        """Reference model/R2Plus1.py:256-279: load a symbol-API checkpoint, skipping the dense layer unless asked."""
+        if not os.path.exists(f):
+            print("parameter file is not exist", f)
+            return
+        self.load_param_dict(torch.load(f, map_location="cpu"), with_dense=with_dense, strict=True)
+
+    def invalidate(self):
+        """Call after changing parameters outside of this module's own optimiser hooks."""
+        self._weights_version += 1
+        self._plans.clear()
+
+    # ------------------------------------------------------------------ forward
+    def _inference_plan(self, x):
+        key = (tuple(x.shape), x.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            n, _, t, h, w = x.shape
+            params = {k: getattr(self, k) for k in self._param_names}
+            aux = {k: getattr(self, k) for k in self._aux_names}
+            plan = engine.InferencePlan(params, aux, self.model_depth, self.num_class, self.pool, self.bn_eps,
+                                        n, t, h, w, x.device)
+            self._plans[key] = plan
+        return plan
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("R2Plus2D runs on sm_100a only: move the clip batch to a CUDA device (no CPU fallback)")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("training-mode forward is provided by fastvideotagging_b200.train (round 1: inference)")
+        return self._inference_plan(x).forward(x)
+
+    def extract_features(self, x):
+        """Reference :247-254 — the AvgPool3D output, shape (N, 512, 1, 1, 1)."""
+        _, pooled = self._inference_plan(x).forward(x, want_features=True)
+        return pooled.reshape(x.shape[0], 512, 1, 1, 1)

@@ -1,0 +1,2 @@
+"""Mirror of reference model/__init__.py:1-2 (the importable part of it)."""
+from .R2Plus1 import R2Plus2D, BLOCK_CONFIG  # noqa: F401

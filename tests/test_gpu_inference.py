@@ -1,0 +1,64 @@
+"""Parity of the eval-mode network (K1 + unfold + pool/fc through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import r2plus1d as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _clips(n, t, h, w, seed=123):
+    # synthetic clips U[0,1) as the reference's own timing loop uses (model/R2Plus1.py:372), seed from train_simple_r3d.py:27
+    return np.random.default_rng(seed).random((n, 3, t, h, w), dtype=np.float32)
+
+
+def _model(depth, num_class, pool, params, device, eps=orc.EPS_GLUON):
+    from fastvideotagging_b200.model import R2Plus2D
+    net = R2Plus2D(num_class, depth, final_spatial_kernel=pool[1], final_temporal_kernel=pool[0], bn_eps=eps)
+    net.to(device)
+    net.load_param_dict(params)
+    net.eval()
+    return net
+
+
+@pytest.mark.parametrize("depth,n,t,hw", [(18, 2, 8, 112), (34, 1, 16, 112), (18, 3, 8, 64)])
+def test_inference_logits_match_oracle(cuda_device, depth, n, t, hw):
+    pool = (t // 8, hw // 16, hw // 16)
+    params = orc.randomize_bn(orc.init_params(depth, 101, seed=0), seed=1)
+    x = _clips(n, t, hw, hw)
+    net = _model(depth, 101, pool, params, cuda_device)
+    with torch.no_grad():
+        got = net(torch.from_numpy(x).to(cuda_device)).float().cpu().numpy()
+    # oracle twice: (a) with bf16 storage emulated -> isolates kernel arithmetic, tight tolerance
+    #               (b) plain fp32 -> north-star tolerance rel 1e-2 on logits for the bf16 path
+    ref_q, _ = orc.Net(params, depth, pool, bf16_storage=True).forward(x)
+    ref_f, _ = orc.Net(params, depth, pool).forward(x)
+    ref_q, ref_f = ref_q.numpy(), ref_f.numpy()
+    scale = np.abs(ref_f).max()
+    assert np.abs(got - ref_q).max() <= 5e-3 * scale + 1e-4, (np.abs(got - ref_q).max(), scale)
+    assert np.abs(got - ref_f).max() <= 1e-2 * scale + 1e-4, (np.abs(got - ref_f).max(), scale)
+    # top-1 / top-5 predictions must match the oracle on every synthetic clip
+    assert (got.argmax(1) == ref_q.argmax(1)).all()
+    top5_g = np.argsort(-got, 1)[:, :5]
+    top5_r = np.argsort(-ref_q, 1)[:, :5]
+    for a, b in zip(top5_g, top5_r):
+        assert set(a.tolist()) == set(b.tolist()) or np.abs(np.sort(got)[:, -6:-4]).ptp() < 1e-3
+
+
+def test_extract_features_shape(cuda_device):
+    params = orc.init_params(18, 101, seed=0)
+    net = _model(18, 101, (1, 7, 7), params, cuda_device)
+    x = torch.from_numpy(_clips(1, 8, 112, 112)).to(cuda_device)
+    with torch.no_grad():
+        f = net.extract_features(x)
+    assert tuple(f.shape) == (1, 512, 1, 1, 1)
+    ref = orc.Net(params, 18, (1, 7, 7), bf16_storage=True).forward(x.cpu().numpy())[1]
+    assert torch.allclose(f.cpu(), ref.float(), rtol=2e-2, atol=2e-3)
+
+
+def test_cpu_tensor_is_rejected(cuda_device):
+    params = orc.init_params(18, 101, seed=0)
+    net = _model(18, 101, (1, 7, 7), params, cuda_device)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 8, 112, 112))
