@@ -102,6 +102,7 @@ static int validate_conv(const fvt_conv_desc* d) {
   if (d->n <= 0 || d->t <= 0 || d->h <= 0 || d->w <= 0) return set_error(FVT_ERR_BAD_DESC, "non-positive input extent");
   if (d->cin <= 0 || d->cin % 16) return set_error(FVT_ERR_BAD_DESC, "cin=%d must be a positive multiple of 16", d->cin);
   if (d->cout <= 0 || d->cout % 16) return set_error(FVT_ERR_BAD_DESC, "cout=%d must be a positive multiple of 16", d->cout);
+  if (d->cout > kMaxCout - 256) return set_error(FVT_ERR_BAD_DESC, "cout=%d exceeds the supported maximum %d", d->cout, kMaxCout - 256);
   if (d->kt < 1 || d->kh < 1 || d->kw < 1 || d->kt > 16 || d->kh > 16 || d->kw > 16) return set_error(FVT_ERR_BAD_DESC, "filter extent out of range");
   if (d->st < 1 || d->sh < 1 || d->sw < 1 || d->st > 8 || d->sh > 8 || d->sw > 8) return set_error(FVT_ERR_BAD_DESC, "stride must be in [1, 8]");
   if (d->pt < 0 || d->ph < 0 || d->pw < 0 || d->pt > 15 || d->ph > 15 || d->pw > 15) return set_error(FVT_ERR_BAD_DESC, "padding must be in [0, 15]");
@@ -275,12 +276,13 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   p.stats = stats;
 
   const int stage_bytes = kATileBytes + bn * kBlockK * 2;
-  const int budget = 227 * 1024 - 1024 - 4096;
+  const int kAuxBytes = 4096 + 2 * kMaxCout * 4;   // barriers + stats partials + staged scale/shift
+  const int budget = 227 * 1024 - 1024 - kAuxBytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(FVT_ERR_BAD_DESC, "tile does not fit shared memory");
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * stage_bytes + 4096;
+  const int smem_bytes = 1024 + stages * stage_bytes + kAuxBytes;
 
   CUtensorMap tmx, tmw;
   if (int e = encode_x_map(di, d, x, &tmx)) return e;

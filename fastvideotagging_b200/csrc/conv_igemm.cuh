@@ -10,7 +10,8 @@
 // * B operand: packed weights [Cout_pad, taps*Cin] (K-major), 2-D tiled TMA.
 // * MMA: tcgen05.mma cta_group::1 kind::f16, M=128, N=block_n (16..256), K=16 per instruction, fp32
 //   accumulators in TMEM (two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1).
-// * Warp roles (256 threads): warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warps4-7 epilogue.
+// * Warp roles (384 threads): warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warps4-11 epilogue
+//   (two warps per TMEM lane quadrant, alternate 16-column chunks, TMEM/residual loads software-pipelined).
 // * Epilogue: tcgen05.ld -> per-channel scale/shift (folded BatchNorm) -> (+ residual) -> ReLU -> bf16 store;
 //   optionally per-channel sum / sum-of-squares of the raw conv output for training-mode BatchNorm.
 //
@@ -23,7 +24,9 @@ namespace fvt {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;          // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
+constexpr int kEpilogueThreads = 256;
+constexpr int kMaxCout = 1536;             // per-channel scale/shift staged in shared memory
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KiB
 
@@ -83,6 +86,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
   float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);   // [2][256] per-CTA channel partials
+  float* affine_smem = stat_smem + 512;                          // [2][kMaxCout] scale, shift
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_x);
@@ -95,13 +99,20 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&acc_full_bar[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&acc_empty_bar[s]), 4);   // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&acc_empty_bar[s]), 8);   // one arrive per epilogue warp
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
     ptx::tmem_relinquish();
+  }
+  if (p.scale != nullptr) {
+    const int padded = p.num_n_tiles * p.block_n;
+    for (int i = threadIdx.x; i < padded; i += kConvThreads) {
+      affine_smem[i] = i < p.cout_store ? __ldg(p.scale + i) : 0.f;
+      affine_smem[kMaxCout + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -183,12 +194,18 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue (4 warps, 32 TMEM lanes each)
+    // ===================================================== epilogue (8 warps: 2 per TMEM lane quadrant)
+    // warp w reads TMEM lanes 32*(w%4).. ; the two warps of a quadrant take alternate 16-column chunks.
     const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;            // 0 or 1
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool do_stats = (p.flags & kConvStats) != 0;
-    const int et = threadIdx.x - 128;   // 0..127
+    const bool has_affine = p.scale != nullptr;
+    const bool has_res = (p.flags & kConvResidual) != 0;
+    const bool relu = (p.flags & kConvRelu) != 0;
+    const int et = threadIdx.x - 128;           // 0..255
+    const int n_chunks = p.block_n >> 4;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile - m_blk * p.num_n_tiles;
@@ -196,21 +213,42 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.m_total;
       if (do_stats) {
-        for (int i = et; i < 512; i += 128) stat_smem[i] = 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < 512; i += kEpilogueThreads) stat_smem[i] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       ptx::mbar_wait(ptx::smem_u32(&acc_full_bar[acc]), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
       __nv_bfloat16* yrow = p.y + static_cast<size_t>(row_ok ? row : 0) * p.cout_store;
-      const __nv_bfloat16* rrow =
-          (p.flags & kConvResidual) ? p.residual + static_cast<size_t>(row_ok ? row : 0) * p.cout_store : nullptr;
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(taddr + c, v);
+      const __nv_bfloat16* rrow = has_res ? p.residual + static_cast<size_t>(row_ok ? row : 0) * p.cout_store : nullptr;
+
+      // software pipeline: TMEM load + residual load of chunk i+1 are in flight while chunk i is processed
+      uint32_t v[16], vn[16];
+      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, rn0 = r0, rn1 = r0;
+      int ci = grp;
+      if (ci < n_chunks) {
+        ptx::tmem_ld_32x32b_x16(taddr + ci * 16, vn);
+        if (has_res && n0 + ci * 16 < p.cout_store) {
+          rn0 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + ci * 16));
+          rn1 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + ci * 16 + 8));
+        }
+      }
+      for (; ci < n_chunks; ci += 2) {
         ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = vn[i];
+        r0 = rn0; r1 = rn1;
+        const int c = ci * 16;
         const int ch0 = n0 + c;
-        if (ch0 >= p.cout_store) break;              // N tail (weights zero-padded to a whole tile)
+        const int cnext = ci + 2;
+        if (cnext < n_chunks) {
+          ptx::tmem_ld_32x32b_x16(taddr + cnext * 16, vn);
+          if (has_res && n0 + cnext * 16 < p.cout_store) {
+            rn0 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + cnext * 16));
+            rn1 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + cnext * 16 + 8));
+          }
+        }
+        if (ch0 >= p.cout_store) continue;           // N tail (weights zero-padded to a whole tile)
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
@@ -219,7 +257,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
           float s1[16], s2[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            // statistics of the value that is actually stored (bf16-rounded), rows beyond M contribute 0
+            // statistics of the value that is actually stored (bf16-rounded); rows beyond M contribute 0
             float r = row_ok ? __bfloat162float(__float2bfloat16_rn(f[i])) : 0.f;
             s1[i] = r; s2[i] = r * r;
           }
@@ -236,24 +274,28 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
               s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, bit);
             }
           }
-          // after bits 16,8,4,2 each lane holds 1 channel summed over 16 lanes; finish with bit 1
           s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
           s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
           if ((lane & 1) == 0) {
-            // channel index encoded by the halving path: bit16->8, bit8->4, bit4->2, bit2->1
             const int chl = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
             atomicAdd(&stat_smem[c + chl], s1[0]);
             atomicAdd(&stat_smem[256 + c + chl], s2[0]);
           }
         }
-        if (p.scale != nullptr) {
+        if (has_affine) {
+          const float4* sc4 = reinterpret_cast<const float4*>(affine_smem + ch0);
+          const float4* sh4 = reinterpret_cast<const float4*>(affine_smem + kMaxCout + ch0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], __ldg(p.scale + ch0 + i), __ldg(p.shift + ch0 + i));
+          for (int i = 0; i < 4; ++i) {
+            const float4 a = sc4[i], b = sh4[i];
+            f[4 * i + 0] = fmaf(f[4 * i + 0], a.x, b.x);
+            f[4 * i + 1] = fmaf(f[4 * i + 1], a.y, b.y);
+            f[4 * i + 2] = fmaf(f[4 * i + 2], a.z, b.z);
+            f[4 * i + 3] = fmaf(f[4 * i + 3], a.w, b.w);
+          }
         }
         if (row_ok) {
-          if (rrow != nullptr) {
-            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rrow + ch0));
-            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rrow + ch0 + 8));
+          if (has_res) {
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -261,7 +303,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
               f[2 * i + 1] += bf16_hi(rr[i]);
             }
           }
-          if (p.flags & kConvRelu) {
+          if (relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
           }
@@ -274,20 +316,20 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
           *reinterpret_cast<uint4*>(yrow + ch0 + 8) = o1;
         }
       }
-      // release the accumulator stage
+      // release the accumulator stage (all of this warp's TMEM reads have completed: wait::ld above)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty_bar[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < p.block_n; i += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < p.block_n; i += kEpilogueThreads) {
           if (n0 + i < p.cout_store) {
             atomicAdd(p.stats + n0 + i, stat_smem[i]);
             atomicAdd(p.stats + p.cout_store + n0 + i, stat_smem[256 + i]);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
   }
