@@ -64,6 +64,14 @@ def load():
         "fvt_conv3d_fwd": (ctypes.c_int, [dp, vp, vp, fp, fp, vp, vp, fp, vp]),
         "fvt_stem_unfold": (ctypes.c_int, [fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         "fvt_pool_fc_fwd": (ctypes.c_int, [vp, i32, i32, i32, i32, fp, fp, i32, fp, fp, vp]),
+        "fvt_loss_workspace_bytes": (ctypes.c_size_t, [i32]),
+        "fvt_lsep_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, fp, fp, vp, vp]),
+        "fvt_warp_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, i32, i32, ctypes.c_uint64, ctypes.c_uint64, fp, fp,
+                                            vp, fp, fp, vp, vp]),
+        "fvt_bce_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, fp, fp, vp]),
+        "fvt_softmax_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, fp, fp, vp]),
+        "fvt_philox4x32_10": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
+                                             ctypes.POINTER(ctypes.c_uint32)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -88,6 +88,34 @@ int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t
 int fvt_pool_fc_fwd(const void* x, int32_t n, int32_t positions, int32_t c, int32_t c_real, const float* w,
                     const float* b, int32_t num_class, float* pooled, float* logits, void* stream);
 
+/* ---- losses (K9-K11): forward and backward in one launch, gradients are d(loss)/d(pred) for head-gradient 1 ------ */
+/* Scratch for the loss kernels: (batch + 4) floats. */
+size_t fvt_loss_workspace_bytes(int32_t batch);
+/* LSEP.  mode 0 = LsepLoss.forward (model/mlc_loss.py:63-86) + its autodiff gradient;
+ *        mode 1 = LSEP_funcLoss exactly as written, row-index quirk and -1/loss backward included (:8-54).
+ * pred/target: [batch, num_class] fp32; loss: float[1]; grad: [batch, num_class]. */
+int fvt_lsep_fwd_bwd(const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t mode,
+                     float* loss, float* grad, void* workspace, void* stream);
+/* WARP.  mode 0 = WarpLoss.forward (:122-174), mode 1 = WARP_funcLoss (:177-233).
+ * Negative sampling (np.random.choice in the reference, :137,207) is replaced by the counter-based stream
+ * philox4x32_10(key=seed, counter=(sample_offset+row, class j, trial, 0)).x % n_neg over the ascending negative list.
+ * rank_in != NULL skips sampling and uses the given rank weights L[batch, num_class];
+ * rank_out / trials_out (optional) receive L and the number of draws per positive. */
+int fvt_warp_fwd_bwd(const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t label_size,
+                     int32_t max_trials, int32_t mode, uint64_t seed, uint64_t sample_offset, const float* rank_in,
+                     float* rank_out, int32_t* trials_out, float* loss, float* grad, void* workspace, void* stream);
+/* gluon SigmoidBinaryCrossEntropyLoss (train_simple_r3d.py:76,237): loss[batch] = mean over classes;
+ * grad (optional) = d(sum_b loss_b)/d(pred). */
+int fvt_bce_fwd_bwd(const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t from_sigmoid,
+                    float* loss, float* grad, void* stream);
+/* mode 0: gluon SoftmaxCrossEntropyLoss with sparse labels (train_simple_r3d.py:43): out = loss[batch];
+ * mode 1: mx.sym.SoftmaxOutput (net.py:167-169): out = probabilities [batch, num_class], label -1 ignored.
+ * label: float[batch] class indices; grad (optional) = softmax - onehot (un-normalised, as MXNet). */
+int fvt_softmax_fwd_bwd(const float* logits, const float* label, int32_t batch, int32_t num_class, int32_t mode,
+                        float* out, float* grad, void* stream);
+/* Host-side Philox4x32-10 block (same code the device uses) for known-answer tests. */
+int fvt_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif
