@@ -64,6 +64,16 @@ def load():
         "fvt_conv3d_fwd": (ctypes.c_int, [dp, vp, vp, fp, fp, vp, vp, fp, vp]),
         "fvt_stem_unfold": (ctypes.c_int, [fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         "fvt_pool_fc_fwd": (ctypes.c_int, [vp, i32, i32, i32, i32, fp, fp, i32, fp, fp, vp]),
+        "fvt_pack_conv_weight_dgrad": (ctypes.c_int, [dp, fp, i32, i32, vp, vp]),
+        "fvt_conv3d_wgrad": (ctypes.c_int, [dp, vp, vp, fp, i32, i32, vp]),
+        "fvt_zero_insert": (ctypes.c_int, [vp, vp] + [i32] * 11 + [vp]),
+        "fvt_bn_finalize": (ctypes.c_int, [fp, fp, fp, fp, fp, i32, i32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                           fp, fp, fp, fp, vp]),
+        "fvt_bn_apply": (ctypes.c_int, [vp, fp, fp, vp, fp, fp, vp, ctypes.c_int64, i32, i32, vp]),
+        "fvt_bn_backward": (ctypes.c_int, [vp, vp, vp, fp, fp, fp, fp, vp, vp, ctypes.c_int64, i32, i32, vp]),
+        "fvt_pool_fc_bwd": (ctypes.c_int, [fp, fp, fp, i32, i32, i32, i32, fp, fp, vp, i32, vp]),
+        "fvt_sgd_momentum_multi": (ctypes.c_int, [vp, vp, vp, i32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
+                                                  ctypes.c_float, vp]),
         "fvt_loss_workspace_bytes": (ctypes.c_size_t, [i32]),
         "fvt_lsep_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, fp, fp, vp, vp]),
         "fvt_warp_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, i32, i32, ctypes.c_uint64, ctypes.c_uint64, fp, fp,

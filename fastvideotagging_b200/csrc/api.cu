@@ -10,6 +10,7 @@
 
 #include "../../include/fvt_b200.h"
 #include "conv_igemm.cuh"
+#include "conv_wgrad.cuh"
 #include "host_common.h"
 
 namespace fvt {
@@ -135,8 +136,10 @@ static int pick_block_n(const fvt_conv_desc* d) {
 static int weight_rows(const fvt_conv_desc* d, int bn) { return (d->cout + bn - 1) / bn * bn; }
 
 // ------------------------------------------------------------------------------------------------ weight packing
+// dgrad = 1: pack the weights of the data-gradient convolution instead (input/output channels swapped, taps
+// reversed): out[ci][taps-1-tap][co] = w[co][ci][tap]; here rows index ci and the K axis runs over (tap, co).
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int taps,
-                                   int cin_store, int cout_real, int cin_real) {
+                                   int cin_store, int cout_real, int cin_real, int dgrad) {
   const size_t total = static_cast<size_t>(rows) * taps * cin_store;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -145,7 +148,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int tap = static_cast<int>(r % taps);
     const int o = static_cast<int>(r / taps);
     float v = 0.f;
-    if (o < cout_real && ci < cin_real) v = w[(static_cast<size_t>(o) * cin_real + ci) * taps + tap];
+    if (!dgrad) {
+      if (o < cout_real && ci < cin_real) v = w[(static_cast<size_t>(o) * cin_real + ci) * taps + tap];
+    } else {
+      // this conv: out channel o = forward ci, in channel ci = forward co; forward dims are (cin_real, cout_real)
+      if (o < cout_real && ci < cin_real) v = w[(static_cast<size_t>(ci) * cout_real + o) * taps + (taps - 1 - tap)];
+    }
     out[i] = __float2bfloat16_rn(v);
   }
 }
@@ -232,8 +240,27 @@ int fvt_pack_conv_weight(const fvt_conv_desc* d, const float* w_oidhw, int32_t c
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, rows, taps, d->cin,
-                                                              cout_real, cin_real);
+                                                              cout_real, cin_real, 0);
   return check_launch("pack_weight_kernel");
+}
+
+int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int32_t fwd_cout_real, int32_t fwd_cin_real,
+                               void* w_packed, void* stream) {
+  // `d` describes the data-gradient convolution: d->cin = stored forward Cout, d->cout = stored forward Cin.
+  if (int e = validate_conv(d)) return e;
+  if (fwd_cout_real <= 0 || fwd_cout_real > d->cin || fwd_cin_real <= 0 || fwd_cin_real > d->cout)
+    return set_error(FVT_ERR_BAD_DESC, "forward filter counts (%d, %d) exceed the dgrad descriptor (%d, %d)", fwd_cout_real, fwd_cin_real, d->cin, d->cout);
+  if (w_oidhw == nullptr || w_packed == nullptr) return set_error(FVT_ERR_BAD_DESC, "null weight pointer");
+  const int bn = pick_block_n(d);
+  const int rows = weight_rows(d, bn);
+  const int taps = d->kt * d->kh * d->kw;
+  const size_t total = (size_t)rows * taps * d->cin;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  // kernel view: rows o = forward ci (< fwd_cin_real), K channel ci = forward co (< fwd_cout_real)
+  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, rows, taps, d->cin,
+                                                              fwd_cin_real, fwd_cout_real, 1);
+  return check_launch("pack_weight_kernel(dgrad)");
 }
 
 int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
@@ -300,6 +327,98 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   const int grid = tiles < di->sm_count ? tiles : di->sm_count;
   conv_igemm_fwd_kernel<<<grid, kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p);
   return check_launch("conv_igemm_fwd_kernel");
+}
+
+
+int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
+                     int32_t cin_real, void* stream) {
+  if (int e = validate_conv(d)) return e;
+  if (x == nullptr || dy == nullptr || dw == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
+  if (cout_real <= 0 || cout_real > d->cout || cin_real <= 0 || cin_real > d->cin)
+    return set_error(FVT_ERR_BAD_DESC, "real filter counts exceed stored");
+  if (((uintptr_t)x | (uintptr_t)dy) & 15) return set_error(FVT_ERR_MISALIGNED, "tensor pointers must be 16-byte aligned");
+  int st = 0;
+  const DeviceInfo* di = current_device_info(&st);
+  if (di == nullptr) return st;
+  int to, ho, wo;
+  conv_out_shape(d, &to, &ho, &wo);
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_total = d->n * to * ho * wo;
+  p.to = to; p.ho = ho; p.wo = wo;
+  p.st = d->st; p.sh = d->sh; p.sw = d->sw;
+  p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
+  p.taps = d->kt * d->kh * d->kw;
+  p.cin_blocks = (d->cin + 63) / 64;
+  p.cin_real = cin_real; p.cout_real = cout_real;
+  p.dw = dw;
+  fvt_conv_desc tmp = *d;
+  tmp.block_n = 0;
+  if (d->cin % 64 != 0 && d->cout % 64 == 0) {
+    p.mode = 1;
+    p.m_groups = d->cout / 64;
+    tmp.cout = d->cin;                                  // N runs over the input channels of one tap
+  } else {
+    p.mode = 0;
+    p.m_groups = p.taps * p.cin_blocks;
+  }
+  p.n_tile = pick_block_n(&tmp);
+  p.n_tiles = (tmp.cout + p.n_tile - 1) / p.n_tile;
+  p.n_loads = (p.n_tile + 63) / 64;
+  p.m_tiles = (p.m_groups + 1) / 2;
+  p.kblocks_total = (p.m_total + kWgPix - 1) / kWgPix;
+  const int items = p.m_tiles * p.n_tiles * (p.mode == 1 ? p.taps : 1);
+  int splits = (2 * di->sm_count + items - 1) / items;
+  if (splits > p.kblocks_total) splits = p.kblocks_total;
+  if (splits < 1) splits = 1;
+  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
+  p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  const int stage_bytes = (2 + p.n_loads) * kSlabBytes;
+  int stages = (227 * 1024 - 2048) / stage_bytes;
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * stage_bytes + 1024;
+
+  // tensor maps: X as in the forward pass but 64 pixels per load; dY as a 1x1x1 "im2col" over the output tensor
+  CUtensorMap tmx, tmdy;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->t, (cuuint64_t)d->n};
+    const cuuint64_t strides[4] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w, (cuuint64_t)d->cin * 2 * d->w * d->h,
+                                   (cuuint64_t)d->cin * 2 * d->w * d->h * d->t};
+    const int lower[3] = {-d->pw, -d->ph, -d->pt};
+    const int upper[3] = {d->pw - (d->kw - 1), d->ph - (d->kh - 1), d->pt - (d->kt - 1)};
+    const cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->st, 1};
+    CUresult r = di->encode_im2col(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, lower, upper,
+                                   64, kWgPix, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeIm2col(x, wgrad) failed (CUresult %d)", (int)r);
+    if (di->driver_version <= 13010 && (size_t)d->cin * 2 * d->w * d->h * d->t * d->n < 131072) reinterpret_cast<uint64_t*>(&tmx)[1] &= ~(1ull << 21);
+  }
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)d->cout, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)to, (cuuint64_t)d->n};
+    const cuuint64_t strides[4] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * wo, (cuuint64_t)d->cout * 2 * wo * ho,
+                                   (cuuint64_t)d->cout * 2 * wo * ho * to};
+    const int zero3[3] = {0, 0, 0};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = di->encode_im2col(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides, zero3, zero3,
+                                   64, kWgPix, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeIm2col(dy, wgrad) failed (CUresult %d)", (int)r);
+    if (di->driver_version <= 13010 && (size_t)d->cout * 2 * wo * ho * to * d->n < 131072) reinterpret_cast<uint64_t*>(&tmdy)[1] &= ~(1ull << 21);
+  }
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_wgrad_kernel): %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const int grid = items * p.splits;
+  conv_wgrad_kernel<<<grid, kWgradThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmdy, p);
+  return check_launch("conv_wgrad_kernel");
 }
 
 }  // extern "C"

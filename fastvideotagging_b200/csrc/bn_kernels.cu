@@ -1,0 +1,378 @@
+// K5-K7, K12 and friends: the HBM-bound passes of a training step over NDHWC bf16 activations [rows, C].
+//
+//   K5  bn_finalize          per-channel (sum, sum^2) -> mean / biased var -> scale, shift, running-stat update
+//   K6  bn_apply             act = relu?( raw*scale + shift  [+ res  |  + res_raw*res_scale + res_shift] )
+//   K7a bn_bwd_reduce        dgamma, dbeta = sum_rows( dz * xhat ), sum_rows( dz ),  dz = dact * [mask > 0]
+//   K7b bn_bwd_apply         draw = gamma*inv_std * ( dz - dbeta/M - xhat*dgamma/M )   (and optionally dz itself)
+//       zero_insert          dY -> dY placed on the stride lattice of the conv input (dgrad of strided convs)
+//       pool_fc_bwd          dlogits -> dW_fc, db_fc, d(conv5 output)
+//   K12 sgd_momentum_multi   MXNet sgd_mom_update over a list of tensors in one launch
+//
+// Thread mapping for the [rows, C] passes: one thread owns 8 consecutive channels (one 16-byte vector) of a row;
+// consecutive threads walk the channel vectors of a row, then the next row, so every warp access is a run of
+// contiguous 16-byte vectors (fully coalesced).  A thread's channel group is fixed across its row loop
+// (blockDim.x is a multiple of C/8 ... enforced by the launcher), so per-channel parameters live in registers and the
+// reductions accumulate per thread, finish with a shared-memory fold and ONE atomic per channel per CTA.
+// MXNet semantics restated: reference model/R2Plus1.py:32,59,62,71 (nn.BatchNorm defaults), net.py:44-45 (eps=1e-3),
+// biased variance, running = momentum*running + (1-momentum)*batch.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/fvt_b200.h"
+#include "host_common.h"
+
+namespace fvt {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int c_store, int c_real, float inv_rows, float eps,
+                                   float momentum, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_store) return;
+  if (c >= c_real) {                      // pad channels: identity-zero so they stay exactly 0
+    scale[c] = 0.f; shift[c] = 0.f; mean_out[c] = 0.f; invstd_out[c] = 0.f;
+    return;
+  }
+  const double m = static_cast<double>(stats[c]) * inv_rows;
+  double v = static_cast<double>(stats[c_store + c]) * inv_rows - m * m;
+  if (v < 0.0) v = 0.0;
+  const float inv_std = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
+  const float g = gamma[c];
+  scale[c] = g * inv_std;
+  shift[c] = beta[c] - static_cast<float>(m) * g * inv_std;
+  mean_out[c] = static_cast<float>(m);
+  invstd_out[c] = inv_std;
+  if (running_mean != nullptr) {
+    running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * static_cast<float>(m);
+    running_var[c] = momentum * running_var[c] + (1.f - momentum) * static_cast<float>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K6
+// res_mode: 0 none, 1 add bf16 tensor `res`, 2 add res*res_scale + res_shift (projection shortcut's own BatchNorm)
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
+                const uint4* __restrict__ res, const float* __restrict__ res_scale, const float* __restrict__ res_shift,
+                uint4* __restrict__ out, size_t rows, int cvec, int res_mode, int relu) {
+  const int tpr = blockDim.x / cvec;                 // rows handled per CTA iteration
+  const int cv = threadIdx.x % cvec;
+  const int rsub = threadIdx.x / cvec;
+  if (rsub >= tpr) return;
+  float sc[8], sh[8], rs[8], rh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale[cv * 8 + i]; sh[i] = shift[cv * 8 + i];
+    rs[i] = res_mode == 2 ? res_scale[cv * 8 + i] : 1.f;
+    rh[i] = res_mode == 2 ? res_shift[cv * 8 + i] : 0.f;
+  }
+  for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
+    const size_t idx = r * cvec + cv;
+    float x[8], y[8];
+    unpack8(__ldg(raw + idx), x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = fmaf(x[i], sc[i], sh[i]);
+    if (res_mode) {
+      float q[8];
+      unpack8(__ldg(res + idx), q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] += fmaf(q[i], rs[i], rh[i]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+    }
+    out[idx] = pack8(y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K7a
+// sums[0..C) += sum dz*xhat (dgamma), sums[C..2C) += sum dz (dbeta);  xhat = (raw - mean)*inv_std
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums,
+                     size_t rows, int cvec, int c_store) {
+  extern __shared__ float sred[];                    // [blockDim.x][16] folded per channel vector
+  const int tpr = blockDim.x / cvec;
+  const int cv = threadIdx.x % cvec;
+  const int rsub = threadIdx.x / cvec;
+  float dg[8], db[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; mu[i] = mean[cv * 8 + i]; is[i] = invstd[cv * 8 + i]; }
+  if (rsub < tpr) {
+    for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
+      const size_t idx = r * cvec + cv;
+      float x[8], g[8];
+      unpack8(__ldg(raw + idx), x);
+      unpack8(__ldg(dact + idx), g);
+      if (mask != nullptr) {
+        float mk[8];
+        unpack8(__ldg(mask + idx), mk);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        db[i] += g[i];
+        dg[i] = fmaf(g[i], (x[i] - mu[i]) * is[i], dg[i]);
+      }
+    }
+  }
+  float* mine = sred + threadIdx.x * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = dg[i]; mine[8 + i] = db[i]; }
+  __syncthreads();
+  // fold the tpr row-subsets of each channel vector, then one atomic per channel per CTA
+  for (int o = threadIdx.x; o < cvec * 16; o += blockDim.x) {
+    const int v = o / 16, k = o % 16;
+    float s = 0.f;
+    for (int t = 0; t < tpr; ++t) s += sred[(t * cvec + v) * 16 + k];
+    const int ch = v * 8 + (k & 7);
+    atomicAdd(sums + (k < 8 ? 0 : c_store) + ch, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K7b
+// draw = gamma*inv_std*(dz - dbeta/M - xhat*dgamma/M); optionally also writes dz (masked dact) for the shortcut path.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ sums, uint4* __restrict__ draw, uint4* __restrict__ dz_out, size_t rows,
+                    int cvec, int c_store, int c_real, float inv_rows) {
+  const int tpr = blockDim.x / cvec;
+  const int cv = threadIdx.x % cvec;
+  const int rsub = threadIdx.x / cvec;
+  if (rsub >= tpr) return;
+  float mu[8], is[8], a[8], bq[8], cq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = cv * 8 + i;
+    mu[i] = mean[ch]; is[i] = invstd[ch];
+    const float g = ch < c_real ? gamma[ch] : 0.f;
+    a[i] = g * is[i];
+    bq[i] = sums[c_store + ch] * inv_rows;          // dbeta / M
+    cq[i] = sums[ch] * inv_rows;                    // dgamma / M
+  }
+  for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
+    const size_t idx = r * cvec + cv;
+    float x[8], g[8], o[8];
+    unpack8(__ldg(raw + idx), x);
+    unpack8(__ldg(dact + idx), g);
+    if (mask != nullptr) {
+      float mk[8];
+      unpack8(__ldg(mask + idx), mk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = a[i] * (g[i] - bq[i] - (x[i] - mu[i]) * is[i] * cq[i]);
+    draw[idx] = pack8(o);
+    if (dz_out != nullptr) dz_out[idx] = pack8(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ zero insert
+// up[n, to*st, ho*sh, wo*sw, :] = dy[n, to, ho, wo, :], zero elsewhere; up has the conv INPUT's spatial extent.
+__global__ void __launch_bounds__(256)
+zero_insert_kernel(const uint4* __restrict__ dy, uint4* __restrict__ up, int n, int t, int h, int w, int to, int ho,
+                   int wo, int st, int sh, int sw, int cvec) {
+  const size_t total = static_cast<size_t>(n) * t * h * w * cvec;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvec);
+    size_t r = i / cvec;
+    const int iw = static_cast<int>(r % w); r /= w;
+    const int ih = static_cast<int>(r % h); r /= h;
+    const int it = static_cast<int>(r % t);
+    const int in = static_cast<int>(r / t);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iw % sw == 0 && ih % sh == 0 && it % st == 0) {
+      const int ow = iw / sw, oh = ih / sh, ot = it / st;
+      if (ow < wo && oh < ho && ot < to)
+        v = __ldg(dy + (((static_cast<size_t>(in) * to + ot) * ho + oh) * wo + ow) * cvec + cv);
+    }
+    up[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ head backward
+// dlogits [n, K] fp32, pooled [n, C] fp32 (saved by the forward), w [K, C] fp32:
+//   dw[k, c] += sum_n dlogits[n,k]*pooled[n,c];  db[k] += sum_n dlogits[n,k];
+//   dx[n, p, c] = (sum_k dlogits[n,k]*w[k,c]) / positions      (bf16, broadcast over the pooled positions)
+__global__ void pool_fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled,
+                                   const float* __restrict__ w, int n, int num_class, int c, int positions,
+                                   float* __restrict__ dw, float* __restrict__ db, __nv_bfloat16* __restrict__ dx,
+                                   int c_store) {
+  // grid.x = n (dx part) + num_class (dw/db part)
+  if (blockIdx.x < n) {
+    const int in = blockIdx.x;
+    const float inv = 1.f / static_cast<float>(positions);
+    for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
+      float s = 0.f;
+      if (ch < c)
+        for (int k = 0; k < num_class; ++k) s = fmaf(dlogits[in * num_class + k], w[static_cast<size_t>(k) * c + ch], s);
+      const __nv_bfloat16 v = __float2bfloat16_rn(s * inv);
+      for (int p = 0; p < positions; ++p) dx[(static_cast<size_t>(in) * positions + p) * c_store + ch] = v;
+    }
+  } else {
+    const int k = blockIdx.x - n;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      float s = 0.f;
+      for (int in = 0; in < n; ++in) s = fmaf(dlogits[in * num_class + k], pooled[static_cast<size_t>(in) * c + ch], s);
+      dw[static_cast<size_t>(k) * c + ch] += s;
+    }
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int in = 0; in < n; ++in) s += dlogits[in * num_class + k];
+      db[k] += s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K12
+// MXNet sgd_mom_update on a list of tensors: g' = rescale*g + wd*w; mom = momentum*mom - lr*g'; w += mom
+// (gluon.Trainer 'sgd', train_simple_r3d.py:95-97,124).  One launch for the whole list: the descriptor table lives
+// in device memory; CTA b processes chunk b of the concatenated index space.
+struct SgdTensor { float* w; const float* g; float* mom; unsigned long long numel; float wd; float lr_mult; };
+
+__global__ void __launch_bounds__(256)
+sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tensors, const unsigned int* __restrict__ chunk_tensor,
+                          const unsigned int* __restrict__ chunk_offset, float lr, float momentum, float rescale,
+                          unsigned int chunk_elems) {
+  const SgdTensor t = tensors[chunk_tensor[blockIdx.x]];
+  const unsigned long long start = static_cast<unsigned long long>(chunk_offset[blockIdx.x]) * chunk_elems;
+  unsigned long long end = start + chunk_elems;
+  if (end > t.numel) end = t.numel;
+  const float lrt = lr * t.lr_mult;
+  for (unsigned long long i = start + threadIdx.x; i < end; i += blockDim.x) {
+    const float w = t.w[i];
+    const float gp = fmaf(rescale, t.g[i], t.wd * w);
+    const float m = momentum * t.mom[i] - lrt * gp;
+    t.mom[i] = m;
+    t.w[i] = w + m;
+  }
+}
+
+static int rows_launch(size_t rows, int cvec, int* blocks, int* threads) {
+  // blockDim multiple of cvec (thread -> fixed channel vector), <= 256 threads when possible
+  int tpr = 256 / cvec;
+  if (tpr < 1) tpr = 1;
+  *threads = tpr * cvec;
+  if (*threads > 1024) return -1;
+  size_t b = (rows + tpr - 1) / tpr;
+  const size_t cap = 148 * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  *blocks = static_cast<int>(b);
+  return 0;
+}
+
+}  // namespace fvt
+
+using namespace fvt;
+
+extern "C" {
+
+int fvt_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, int32_t c_store, int32_t c_real, int64_t rows, float eps, float momentum,
+                    float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  if (!stats || !gamma || !beta || !scale || !shift || !mean || !invstd) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  if (c_store <= 0 || c_real <= 0 || c_real > c_store || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_finalize extent");
+  int st = 0;
+  if (current_device_info(&st) == nullptr) return st;
+  bn_finalize_kernel<<<(c_store + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      stats, gamma, beta, running_mean, running_var, c_store, c_real, 1.0f / static_cast<float>(rows), eps, momentum,
+      scale, shift, mean, invstd);
+  return check_launch("bn_finalize_kernel");
+}
+
+int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const void* res, const float* res_scale,
+                 const float* res_shift, void* out, int64_t rows, int32_t c_store, int32_t relu, void* stream) {
+  if (!raw || !scale || !shift || !out) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  if (c_store <= 0 || c_store % 8 || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_apply extent");
+  if ((res_scale == nullptr) != (res_shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "res_scale/res_shift must come together");
+  int st = 0;
+  if (current_device_info(&st) == nullptr) return st;
+  int blocks, threads;
+  if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
+  const int res_mode = res == nullptr ? 0 : (res_scale ? 2 : 1);
+  bn_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((const uint4*)raw, scale, shift, (const uint4*)res, res_scale,
+                                                                res_shift, (uint4*)out, rows, c_store / 8, res_mode, relu);
+  return check_launch("bn_apply_kernel");
+}
+
+int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const float* mean, const float* invstd,
+                    const float* gamma, float* sums, void* draw, void* dz_out, int64_t rows, int32_t c_store,
+                    int32_t c_real, void* stream) {
+  if (!raw || !dact || !mean || !invstd || !gamma || !sums || !draw) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  if (c_store <= 0 || c_store % 8 || rows <= 0 || c_real > c_store) return set_error(FVT_ERR_BAD_DESC, "bad bn_backward extent");
+  int st = 0;
+  if (current_device_info(&st) == nullptr) return st;
+  int blocks, threads;
+  if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c_store, (cudaStream_t)stream);
+  bn_bwd_reduce_kernel<<<blocks, threads, threads * 16 * sizeof(float), (cudaStream_t)stream>>>(
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, sums, rows, c_store / 8, c_store);
+  if (int e = check_launch("bn_bwd_reduce_kernel")) return e;
+  bn_bwd_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, sums, (uint4*)draw, (uint4*)dz_out,
+      rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows));
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+int fvt_zero_insert(const void* dy, void* up, int32_t n, int32_t t, int32_t h, int32_t w, int32_t to, int32_t ho,
+                    int32_t wo, int32_t st_, int32_t sh, int32_t sw, int32_t c_store, void* stream) {
+  if (!dy || !up) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  if (c_store <= 0 || c_store % 8) return set_error(FVT_ERR_BAD_DESC, "bad channel count");
+  int st = 0;
+  if (current_device_info(&st) == nullptr) return st;
+  const size_t total = static_cast<size_t>(n) * t * h * w * (c_store / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  zero_insert_kernel<<<static_cast<int>(blocks), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)up, n, t, h, w, to, ho,
+                                                                                 wo, st_, sh, sw, c_store / 8);
+  return check_launch("zero_insert_kernel");
+}
+
+int fvt_pool_fc_bwd(const float* dlogits, const float* pooled, const float* w, int32_t n, int32_t num_class,
+                    int32_t c, int32_t positions, float* dw, float* db, void* dx, int32_t c_store, void* stream) {
+  if (!dlogits || !pooled || !w || !dw || !db || !dx) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  int st = 0;
+  if (current_device_info(&st) == nullptr) return st;
+  pool_fc_bwd_kernel<<<n + num_class, 256, 0, (cudaStream_t)stream>>>(dlogits, pooled, w, n, num_class, c, positions, dw, db,
+                                                                      (__nv_bfloat16*)dx, c_store);
+  return check_launch("pool_fc_bwd_kernel");
+}
+
+int fvt_sgd_momentum_multi(const void* tensor_table, const uint32_t* chunk_tensor, const uint32_t* chunk_offset,
+                           int32_t num_chunks, uint32_t chunk_elems, float lr, float momentum, float rescale,
+                           void* stream) {
+  if (!tensor_table || !chunk_tensor || !chunk_offset || num_chunks <= 0) return set_error(FVT_ERR_BAD_DESC, "bad sgd table");
+  int st = 0;
+  if (current_device_info(&st) == nullptr) return st;
+  sgd_momentum_multi_kernel<<<num_chunks, 256, 0, (cudaStream_t)stream>>>((const SgdTensor*)tensor_table, chunk_tensor,
+                                                                          chunk_offset, lr, momentum, rescale, chunk_elems);
+  return check_launch("sgd_momentum_multi_kernel");
+}
+
+}  // extern "C"

@@ -89,3 +89,74 @@ def pool_fc_fwd(x, c_real, weight, bias, want_pooled=False):
     check(lib.fvt_pool_fc_fwd(_ptr(x), n, positions, c, c_real, _ptr(weight), _ptr(bias), num_class, _ptr(pooled),
                               _ptr(logits), _stream()))
     return (logits, pooled) if want_pooled else logits
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training ops
+# ---------------------------------------------------------------------------------------------------------------------
+def dgrad_desc(fwd, block_n=0, flags=0):
+    """Descriptor of the stride-1 convolution that computes the data gradient of `fwd` from dY (for strided `fwd`,
+    dY must first be zero-inserted onto the input lattice, see zero_insert): channels swapped, padding k-1-p."""
+    return ConvDesc(fwd.n, fwd.t, fwd.h, fwd.w, fwd.cout, fwd.cin, fwd.kt, fwd.kh, fwd.kw, 1, 1, 1,
+                    fwd.kt - 1 - fwd.pt, fwd.kh - 1 - fwd.ph, fwd.kw - 1 - fwd.pw, flags, block_n)
+
+
+def pack_conv_weight_dgrad(ddesc, w_oidhw):
+    lib = _lib.load()
+    w = w_oidhw.detach().to(torch.float32).contiguous()
+    elems = lib.fvt_conv3d_packed_weight_elems(ctypes.byref(ddesc))
+    out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
+    check(lib.fvt_pack_conv_weight_dgrad(ctypes.byref(ddesc), _ptr(w), w.shape[0], w.shape[1], _ptr(out), _stream()))
+    return out
+
+
+def zero_insert(dy, fwd, out=None):
+    """dy: (N, To, Ho, Wo, C) -> (N, T, H, W, C) with dy on the stride lattice of `fwd`'s input."""
+    lib = _lib.load()
+    n, to, ho, wo, c = dy.shape
+    if out is None:
+        out = torch.empty((n, fwd.t, fwd.h, fwd.w, c), dtype=torch.bfloat16, device=dy.device)
+    check(lib.fvt_zero_insert(_ptr(dy), _ptr(out), n, fwd.t, fwd.h, fwd.w, to, ho, wo, fwd.st, fwd.sh, fwd.sw, c, _stream()))
+    return out
+
+
+def conv3d_wgrad(fwd, x, dy, dw, cout_real, cin_real):
+    """dw (fp32, (cout_real, cin_real, kT, kH, kW)) += wgrad(x, dy)."""
+    lib = _lib.load()
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    check(lib.fvt_conv3d_wgrad(ctypes.byref(fwd), _ptr(x), _ptr(dy), _ptr(dw), cout_real, cin_real, _stream()))
+    return dw
+
+
+def bn_finalize(stats, gamma, beta, running_mean, running_var, c_store, rows, eps, momentum, scale, shift, mean, invstd):
+    lib = _lib.load()
+    check(lib.fvt_bn_finalize(_ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), c_store,
+                              gamma.numel(), rows, eps, momentum, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _stream()))
+
+
+def bn_apply(raw, scale, shift, out, relu, res=None, res_scale=None, res_shift=None):
+    lib = _lib.load()
+    c = raw.shape[-1]
+    rows = raw.numel() // c
+    check(lib.fvt_bn_apply(_ptr(raw), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out),
+                           rows, c, int(relu), _stream()))
+    return out
+
+
+def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None):
+    lib = _lib.load()
+    c = raw.shape[-1]
+    rows = raw.numel() // c
+    check(lib.fvt_bn_backward(_ptr(raw), _ptr(dact), _ptr(mask), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums),
+                              _ptr(draw), _ptr(dz_out), rows, c, gamma.numel(), _stream()))
+    return draw
+
+
+def pool_fc_bwd(dlogits, pooled, weight, dw, db, dx):
+    lib = _lib.load()
+    n, k = dlogits.shape
+    c = pooled.shape[1]
+    c_store = dx.shape[-1]
+    positions = dx.numel() // (n * c_store)
+    check(lib.fvt_pool_fc_bwd(_ptr(dlogits), _ptr(pooled), _ptr(weight), n, k, c, positions, _ptr(dw), _ptr(db), _ptr(dx),
+                              c_store, _stream()))

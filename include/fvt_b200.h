@@ -88,6 +88,50 @@ int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t
 int fvt_pool_fc_fwd(const void* x, int32_t n, int32_t positions, int32_t c, int32_t c_real, const float* w,
                     const float* b, int32_t num_class, float* pooled, float* logits, void* stream);
 
+/* ---- training: convolution gradients (K2, K3) ----------------------------------------------------------------- */
+/* Data gradient of a STRIDE-1 convolution is itself a convolution (K1) of dY with the channel-transposed, tap-reversed
+ * filter and padding k-1-p.  `d` describes that convolution (d->cin = stored forward Cout, d->cout = stored forward
+ * Cin); this packs the forward weights (O, I, kT, kH, kW) for it.  Strided convolutions go through fvt_zero_insert
+ * first.  (cuDNN backward-data in the reference.) */
+int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int32_t fwd_cout_real, int32_t fwd_cin_real,
+                               void* w_packed, void* stream);
+/* dw[(co*cin_real + ci)*taps + tap] += sum over output pixels of dy[pixel, co] * x[pixel + tap, ci]  — fp32, the
+ * reference's (O, I, kT, kH, kW) layout, accumulated with atomics (zero it first).  `d` is the FORWARD descriptor;
+ * x: stored input activation, dy: gradient w.r.t. the raw conv output, both NDHWC bf16.  (cuDNN backward-filter.) */
+int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
+                     int32_t cin_real, void* stream);
+/* up[n, to*st, ho*sh, wo*sw, :] = dy[n, to, ho, wo, :], zero elsewhere (up has the conv input's T,H,W). */
+int fvt_zero_insert(const void* dy, void* up, int32_t n, int32_t t, int32_t h, int32_t w, int32_t to, int32_t ho,
+                    int32_t wo, int32_t st, int32_t sh, int32_t sw, int32_t c_store, void* stream);
+
+/* ---- training: BatchNorm (K5-K7), MXNet semantics (A4) ---------------------------------------------------------- */
+/* stats = [sum(c_store), sum^2(c_store)] from fvt_conv3d_fwd(FVT_CONV_STATS) over `rows` pixels ->
+ * mean, inv_std = 1/sqrt(biased_var + eps), scale = gamma*inv_std, shift = beta - mean*scale;
+ * running = momentum*running + (1-momentum)*batch (biased variance) when running_mean != NULL. */
+int fvt_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, int32_t c_store, int32_t c_real, int64_t rows, float eps, float momentum,
+                    float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* out = relu?( raw*scale + shift [+ res | + res*res_scale + res_shift] ), [rows, c_store] bf16. */
+int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const void* res, const float* res_scale,
+                 const float* res_shift, void* out, int64_t rows, int32_t c_store, int32_t relu, void* stream);
+/* dz = dact * [mask > 0] (mask == NULL: dz = dact);  sums = [dgamma(c_store), dbeta(c_store)] (overwritten);
+ * draw = gamma*inv_std*(dz - dbeta/rows - xhat*dgamma/rows);  dz_out (optional) receives dz. */
+int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const float* mean, const float* invstd,
+                    const float* gamma, float* sums, void* draw, void* dz_out, int64_t rows, int32_t c_store,
+                    int32_t c_real, void* stream);
+
+/* ---- training: head backward, optimiser ----------------------------------------------------------------------- */
+/* dw[k,c] += sum_n dlogits[n,k]*pooled[n,c]; db[k] += sum_n dlogits[n,k]; dx[n,p,c] = (dlogits[n,:] . w[:,c]) / positions. */
+int fvt_pool_fc_bwd(const float* dlogits, const float* pooled, const float* w, int32_t n, int32_t num_class,
+                    int32_t c, int32_t positions, float* dw, float* db, void* dx, int32_t c_store, void* stream);
+/* MXNet sgd_mom_update over a tensor list in one launch (gluon.Trainer 'sgd', train_simple_r3d.py:95-97,124):
+ * g' = rescale*g + wd*w; mom = momentum*mom - lr*lr_mult*g'; w += mom.
+ * tensor_table: device array of {float* w; const float* g; float* mom; uint64 numel; float wd; float lr_mult};
+ * chunk_tensor/chunk_offset: device arrays, one entry per CTA: tensor index and chunk index inside it. */
+int fvt_sgd_momentum_multi(const void* tensor_table, const uint32_t* chunk_tensor, const uint32_t* chunk_offset,
+                           int32_t num_chunks, uint32_t chunk_elems, float lr, float momentum, float rescale,
+                           void* stream);
+
 /* ---- losses (K9-K11): forward and backward in one launch, gradients are d(loss)/d(pred) for head-gradient 1 ------ */
 /* Scratch for the loss kernels: (batch + 4) floats. */
 size_t fvt_loss_workspace_bytes(int32_t batch);
