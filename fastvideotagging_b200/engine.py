@@ -214,3 +214,284 @@ class InferencePlan:
             ops.conv3d_fwd(L.desc, self._view(L.src), L.w_packed, L.scale, L.shift,
                            self._view(L.res) if L.res is not None else None, out=self._view(L.dst))
         return ops.pool_fc_fwd(self._view(self.final), 512, self.fc_w, self.fc_b, want_pooled=want_features)
+
+
+# =====================================================================================================================
+# training
+# =====================================================================================================================
+class FlatParams:
+    """All trainable tensors in ONE fp32 buffer (plus same-shaped gradient and momentum buffers).
+
+    Layout, in forward order: conv weight (O, I, kT, kH, kW) | gamma padded to c_store | beta padded to c_store | ...
+    | final_fc_weight | final_fc_bias.  BatchNorm gamma/beta are stored padded so the BN-backward kernel can write
+    [dgamma | dbeta] straight into the gradient buffer; the user-visible parameters are views of the first c entries.
+    A contiguous gradient buffer is what makes the NCCL all-reduce bucketing copy-free (slices of one tensor) and the
+    SGD step a single launch.
+    """
+
+    def __init__(self, model_depth, num_class, device):
+        self.slots = {}                 # name -> (offset, numel, shape)
+        off = 0
+        pshapes, _ = parameter_shapes(model_depth, num_class)
+        for name, shape in pshapes.items():
+            numel = 1
+            for s in shape:
+                numel *= s
+            store = pad16(shape[0]) if (name.endswith("_gamma") or name.endswith("_beta")) else numel
+            off = (off + 3) // 4 * 4                                  # 16-byte aligned slots
+            self.slots[name] = (off, numel, tuple(shape), store)
+            off += store
+        self.total = (off + 3) // 4 * 4
+        self.w = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.g = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.m = torch.zeros(self.total, dtype=torch.float32, device=device)
+
+    def view(self, buf, name):
+        off, numel, shape, _ = self.slots[name]
+        return buf[off:off + numel].view(shape)
+
+    def padded(self, buf, name):
+        off, _, _, store = self.slots[name]
+        return buf[off:off + store]
+
+
+class _TLayer:
+    __slots__ = ("spec", "fwd", "dgr", "w_name", "cin_real", "cout_real", "cin_s", "cout_s", "rows", "in_shape",
+                 "out_shape", "src", "raw", "act", "stats", "scale", "shift", "mean", "invstd", "wp", "wpd", "w_eq",
+                 "strided", "need_dgrad")
+
+
+class TrainPlan:
+    """Shape-specialised training step: forward with batch-statistics BatchNorm (reference semantics inside
+    autograd.record(), model/R2Plus1.py:73-82 + A4) and the full backward pass, on the C-ABI kernels.
+
+    forward:   per conv  K1(+stats) -> K5 finalize -> K6 apply(+residual)(+ReLU)
+    backward:  per conv  K7 (reduce + apply) -> K3 wgrad -> K1 dgrad (zero-insert first when strided)
+    """
+
+    def __init__(self, flat, aux, model_depth, num_class, pool, eps, n, t, h, w, device, momentum=0.9):
+        self.flat, self.aux = flat, aux
+        self.device = device
+        self.eps, self.momentum = eps, momentum
+        self.n, self.t, self.h, self.w = n, t, h, w
+        self.num_class = num_class
+        self.bufs = {}
+        self.layers = {}
+        self.blocks = []
+        self.grad_hook = None            # callable(lo, hi): gradient slice [lo, hi) of flat.g is final
+        self.weights_version = -1
+
+        def buf(name, shape, dtype=torch.bfloat16):
+            tns = torch.empty(shape, dtype=dtype, device=device)
+            self.bufs[name] = tns
+            return tns
+
+        def make(spec, in_shape, src_name, kernel=None, stride=None, pad=None, cin_store=None, need_dgrad=True):
+            L = _TLayer()
+            L.spec = spec
+            k, s, p = kernel or spec.kernel, stride or spec.stride, pad or spec.pad
+            L.cin_real, L.cout_real = spec.cin, spec.cout
+            L.cin_s, L.cout_s = cin_store or pad16(spec.cin), pad16(spec.cout)
+            nn_, tt, hh, ww = in_shape[:4]
+            L.fwd = ops.conv_desc(nn_, tt, hh, ww, L.cin_s, L.cout_s, k, s, p, ops.FVT_CONV_STATS)
+            to, ho, wo = ops.conv_out_shape(L.fwd)
+            L.in_shape = (nn_, tt, hh, ww, L.cin_s)
+            L.out_shape = (nn_, to, ho, wo, L.cout_s)
+            L.rows = nn_ * to * ho * wo
+            L.strided = tuple(s) != (1, 1, 1)
+            L.need_dgrad = need_dgrad
+            L.dgr = ops.dgrad_desc(L.fwd) if need_dgrad else None
+            L.w_name = spec.name + "_weight"
+            L.src = src_name
+            L.raw = buf(spec.name + ":raw", L.out_shape)
+            L.act = buf(spec.name + ":act", L.out_shape)
+            L.stats = buf(spec.name + ":stats", (2 * L.cout_s,), torch.float32)
+            for nm in ("scale", "shift", "mean", "invstd"):
+                setattr(L, nm, buf(spec.name + ":" + nm, (L.cout_s,), torch.float32))
+            L.wp = L.wpd = L.w_eq = None
+            self.layers[spec.name] = L
+            return L
+
+        s_sp, s_tm = stem_specs()
+        wo_unf = (w + 2 * 3 - 7) // 2 + 1
+        self.unfold = buf("unfold", (n, t, h, wo_unf, STEM_UNFOLD_CH))
+        self.stem0 = make(s_sp, (n, t, h, wo_unf), "unfold", kernel=(1, 7, 1), stride=(1, 2, 1), pad=(0, 3, 0),
+                          cin_store=STEM_UNFOLD_CH, need_dgrad=False)
+        self.stem0.cin_real = 21
+        self.stem1 = make(s_tm, self.stem0.out_shape, s_sp.name + ":act")
+        cur_name, cur_shape = s_tm.name + ":act", self.stem1.out_shape
+        max_elems = max(self.stem0.raw.numel(), self.stem1.raw.numel())
+        for comp, cin, cout, down in network_blocks(model_depth):
+            main, short = block_specs(comp, cin, cout, down)
+            a = make(main[0], cur_shape, cur_name)
+            b = make(main[1], a.out_shape, main[0].name + ":act")
+            c = make(main[2], b.out_shape, main[1].name + ":act")
+            d = make(main[3], c.out_shape, main[2].name + ":act")
+            sc = make(short, cur_shape, cur_name) if short is not None else None
+            self.blocks.append((comp, cur_name, cur_shape, a, b, c, d, sc))
+            cur_name, cur_shape = main[3].name + ":act", d.out_shape     # block output lives in d.act
+            for L in (a, b, c, d):
+                max_elems = max(max_elems, L.raw.numel(), L.in_shape[0] * L.in_shape[1] * L.in_shape[2] * L.in_shape[3] * L.in_shape[4])
+        self.final_name, self.final_shape = cur_name, cur_shape
+        tp, hp, wp = cur_shape[1] - pool[0] + 1, cur_shape[2] - pool[1] + 1, cur_shape[3] - pool[2] + 1
+        if (tp, hp, wp) != (1, 1, 1):
+            raise ValueError("AvgPool3D%s over a %s map leaves %s: only a global pool is supported" % (pool, cur_shape[1:4], (tp, hp, wp)))
+        # backward scratch: two activation-gradient ping-pong buffers, one raw-gradient buffer, the masked block
+        # gradient, the shortcut gradient and the zero-insert staging area
+        up_elems = 1
+        for L in self.layers.values():
+            if L.strided and L.need_dgrad:
+                up_elems = max(up_elems, L.fwd.n * L.fwd.t * L.fwd.h * L.fwd.w * L.cout_s)
+        for nm in ("gA", "gB", "draw", "gmask", "gshort", "draw_s"):
+            buf(nm, (max_elems,))
+        buf("up", (up_elems,))
+        self.pooled = None
+        self.launches_fwd = self.launches_bwd = 0
+
+    # ------------------------------------------------------------------ weights
+    def _w(self, L):
+        return self.flat.view(self.flat.w, L.w_name)
+
+    def refresh_weights(self, version):
+        """Re-pack bf16 operand copies of the fp32 master weights (forward and data-gradient layouts)."""
+        if version == self.weights_version:
+            return
+        for L in self.layers.values():
+            w = self._w(L)
+            if L is self.stem0:
+                w = stem_equivalent_weight(w)
+            L.wp = ops.pack_conv_weight(L.fwd, w)
+            if L.need_dgrad:
+                L.wpd = ops.pack_conv_weight_dgrad(L.dgr, w)
+        self.weights_version = version
+
+    # ------------------------------------------------------------------ forward
+    def _bn_names(self, L):
+        return L.spec.bn + "_gamma", L.spec.bn + "_beta", L.spec.bn + "_moving_mean", L.spec.bn + "_moving_var"
+
+    def _conv_bn(self, L, src):
+        gname, bname, mname, vname = self._bn_names(L)
+        L.stats.zero_()
+        ops.conv3d_fwd(L.fwd, src, L.wp, out=L.raw, stats=L.stats)
+        ops.bn_finalize(L.stats, self.flat.view(self.flat.w, gname), self.flat.view(self.flat.w, bname),
+                        self.aux[mname], self.aux[vname], L.cout_s, L.rows, self.eps, self.momentum,
+                        L.scale, L.shift, L.mean, L.invstd)
+
+    def forward(self, x):
+        assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w)
+        ops.stem_unfold(x.contiguous(), out=self.unfold)
+        B = self.bufs
+        for L in (self.stem0, self.stem1):
+            self._conv_bn(L, B[L.src])
+            ops.bn_apply(L.raw, L.scale, L.shift, L.act, True)
+        for comp, xin_name, xin_shape, a, b, c, d, sc in self.blocks:
+            xin = B[xin_name]
+            for L in (a, b, c):
+                self._conv_bn(L, B[L.src])
+                ops.bn_apply(L.raw, L.scale, L.shift, L.act, True)
+            self._conv_bn(d, B[d.src])
+            if sc is not None:
+                self._conv_bn(sc, xin)
+                ops.bn_apply(d.raw, d.scale, d.shift, d.act, True, res=sc.raw, res_scale=sc.scale, res_shift=sc.shift)
+            else:
+                ops.bn_apply(d.raw, d.scale, d.shift, d.act, True, res=xin)
+        logits, self.pooled = ops.pool_fc_fwd(B[self.final_name], 512, self.flat.view(self.flat.w, "final_fc_weight"),
+                                              self.flat.view(self.flat.w, "final_fc_bias"), want_pooled=True)
+        return logits
+
+    # ------------------------------------------------------------------ backward
+    def _view(self, name, shape):
+        numel = 1
+        for s in shape:
+            numel *= s
+        return self.bufs[name][:numel].view(shape)
+
+    def _ready(self, *names):
+        if self.grad_hook is None:
+            return
+        lo = min(self.flat.slots[n][0] for n in names)
+        hi = max(self.flat.slots[n][0] + self.flat.slots[n][3] for n in names)
+        self.grad_hook(lo, hi)
+
+    def _bn_bwd(self, L, dact, mask, draw, dz_out=None):
+        gname, bname, _, _ = self._bn_names(L)
+        sums = self.flat.padded(self.flat.g, gname)           # [dgamma(c_store) | dbeta(c_store)] adjacent slots
+        off_g, off_b = self.flat.slots[gname][0], self.flat.slots[bname][0]
+        assert off_b == off_g + L.cout_s, "gamma/beta slots must be adjacent"
+        sums2 = self.flat.g[off_g:off_g + 2 * L.cout_s]
+        ops.bn_backward(L.raw, dact, mask, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, dz_out)
+
+    def _wgrad(self, L, x_in, draw):
+        if L is self.stem0:
+            dweq = torch.zeros((45, 21, 1, 7, 1), dtype=torch.float32, device=self.device)
+            ops.conv3d_wgrad(L.fwd, x_in, draw, dweq, 45, 21)
+            # dW[o, ci, 0, kh, kw] = dW_eq[o, kw*3+ci, 0, kh, 0]
+            self.flat.view(self.flat.g, L.w_name).add_(dweq.reshape(45, 7, 3, 1, 7).permute(0, 2, 3, 4, 1))
+        else:
+            ops.conv3d_wgrad(L.fwd, x_in, draw, self.flat.view(self.flat.g, L.w_name), L.cout_real, L.cin_real)
+
+    def _dgrad(self, L, draw, out, residual=None):
+        src = draw
+        if L.strided:
+            src = ops.zero_insert(draw, L.fwd, out=self._view("up", (L.fwd.n, L.fwd.t, L.fwd.h, L.fwd.w, L.cout_s)))
+        d = L.dgr
+        if residual is not None:
+            d = ops.ConvDesc(*d.key())
+            d.flags = ops.FVT_CONV_RESIDUAL
+        ops.conv3d_fwd(d, src, L.wpd, residual=residual, out=out)
+        return out
+
+    def backward(self, dlogits):
+        """dlogits: (N, num_class) fp32.  Accumulates into flat.g (zeroed by the caller at step start)."""
+        B = self.bufs
+        fl = self.flat
+        final = B[self.final_name]
+        g_cur = self._view("gA", self.final_shape)
+        ops.pool_fc_bwd(dlogits.contiguous(), self.pooled, fl.view(fl.w, "final_fc_weight"), fl.view(fl.g, "final_fc_weight"),
+                        fl.view(fl.g, "final_fc_bias"), g_cur)
+        self._ready("final_fc_weight", "final_fc_bias")
+        cur_key = "gA"
+        for comp, xin_name, xin_shape, a, b, c, d, sc in reversed(self.blocks):
+            xin = B[xin_name]
+            other = "gB" if cur_key == "gA" else "gA"
+            gmask = self._view("gmask", d.out_shape)
+            draw_d = self._view("draw", d.out_shape)
+            self._bn_bwd(d, g_cur, d.act, draw_d, dz_out=gmask)           # out = relu(bn2 + shortcut): mask by out > 0
+            if sc is not None:
+                draw_s = self._view("draw_s", sc.out_shape)
+                self._bn_bwd(sc, gmask, None, draw_s)
+                self._wgrad(sc, xin, draw_s)
+                gshort = self._dgrad(sc, draw_s, self._view("gshort", xin_shape))
+            else:
+                gshort = gmask
+            self._wgrad(d, c.act, draw_d)
+            gc = self._dgrad(d, draw_d, self._view(other, c.out_shape))
+            draw_c = self._view("draw", c.out_shape)
+            self._bn_bwd(c, gc, c.act, draw_c)
+            self._wgrad(c, b.act, draw_c)
+            gb = self._dgrad(c, draw_c, self._view(cur_key, b.out_shape))
+            draw_b = self._view("draw", b.out_shape)
+            self._bn_bwd(b, gb, b.act, draw_b)
+            self._wgrad(b, a.act, draw_b)
+            ga = self._dgrad(b, draw_b, self._view(other, a.out_shape))
+            draw_a = self._view("draw", a.out_shape)
+            self._bn_bwd(a, ga, a.act, draw_a)
+            self._wgrad(a, xin, draw_a)
+            g_cur = self._dgrad(a, draw_a, self._view(cur_key, xin_shape), residual=gshort)
+            names = []
+            for L in (a, b, c, d) + ((sc,) if sc is not None else ()):
+                names += [L.w_name, L.spec.bn + "_gamma", L.spec.bn + "_beta"]
+            self._ready(*names)
+        # stem
+        other = "gB" if cur_key == "gA" else "gA"
+        draw1 = self._view("draw", self.stem1.out_shape)
+        self._bn_bwd(self.stem1, g_cur, self.stem1.act, draw1)
+        self._wgrad(self.stem1, self.stem0.act, draw1)
+        g0 = self._dgrad(self.stem1, draw1, self._view(other, self.stem0.out_shape))
+        draw0 = self._view("draw", self.stem0.out_shape)
+        self._bn_bwd(self.stem0, g0, self.stem0.act, draw0)
+        self._wgrad(self.stem0, self.unfold, draw0)
+        names = []
+        for L in (self.stem0, self.stem1):
+            names += [L.w_name, L.spec.bn + "_gamma", L.spec.bn + "_beta"]
+        self._ready(*names)

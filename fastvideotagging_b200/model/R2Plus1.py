@@ -33,6 +33,24 @@ def xavier_uniform_(tensor, factor_type="avg", magnitude=3.0, generator=None):
     return tensor
 
 
+class _TrainStep(torch.autograd.Function):
+    """One training-mode forward/backward of the whole network on the C-ABI kernels.  Parameter gradients are written
+    into the flat gradient buffer (the .grad views of the parameters), not returned through autograd."""
+
+    @staticmethod
+    def forward(ctx, x, net, anchor):
+        plan = net._train_plan(x)
+        plan.refresh_weights(net._weights_version)
+        net._flat.g.zero_()                      # grad_req='write': every backward overwrites
+        ctx.plan = plan
+        return plan.forward(x)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.plan.backward(dlogits.float())
+        return None, None, None
+
+
 class R2Plus2D(torch.nn.Module):
     """R(2+1)D-{10,16,18,26,34} (reference model/R2Plus1.py:93-254).
 
@@ -67,7 +85,12 @@ class R2Plus2D(torch.nn.Module):
         self.base_name = self.set_base_name()
         self.dense0_name = ["final_fc_weight", "final_fc_bias"]
         self._plans = {}
+        self._train_plans = {}
         self._weights_version = 0
+        self._flat = None
+        self._trainer = None
+        self._grad_anchor = None
+        self.bn_momentum = BN_MOMENTUM
 
     # ------------------------------------------------------------------ reference helpers
     @staticmethod
@@ -166,6 +189,51 @@ class R2Plus2D(torch.nn.Module):
         self._weights_version += 1
         self._plans.clear()
 
+    def _weights_changed(self):
+        """Optimiser hook: bf16 operand copies are re-packed lazily, folded-BN inference plans are dropped."""
+        self._weights_version += 1
+        self._plans.clear()
+
+    def _attach_trainer(self, trainer):
+        self._trainer = trainer
+        for plan in self._train_plans.values():
+            plan.grad_hook = trainer.on_grads_ready
+
+    def _ensure_flat(self, device):
+        """Move every trainable tensor into one flat fp32 buffer (engine.FlatParams); the nn.Parameters become views
+        of it and their .grad views of the flat gradient buffer."""
+        if self._flat is not None and self._flat.w.device == device:
+            return self._flat
+        flat = engine.FlatParams(self.model_depth, self.num_class, device)
+        with torch.no_grad():
+            for name in self._param_names:
+                p = getattr(self, name)
+                flat.view(flat.w, name).copy_(p.data.to(device))
+                p.data = flat.view(flat.w, name)
+                p.grad = flat.view(flat.g, name)
+        for name in self._aux_names:
+            b = getattr(self, name)
+            if b.device != device:
+                setattr(self, name, b.to(device))
+        self._flat = flat
+        self._grad_anchor = torch.zeros(1, device=device, requires_grad=True)
+        self._train_plans.clear()
+        return flat
+
+    def _train_plan(self, x):
+        flat = self._ensure_flat(x.device)
+        key = (tuple(x.shape), x.device.index)
+        plan = self._train_plans.get(key)
+        if plan is None:
+            n, _, t, h, w = x.shape
+            aux = {k: getattr(self, k) for k in self._aux_names}
+            plan = engine.TrainPlan(flat, aux, self.model_depth, self.num_class, self.pool, self.bn_eps, n, t, h, w,
+                                    x.device, momentum=self.bn_momentum)
+            if self._trainer is not None:
+                plan.grad_hook = self._trainer.on_grads_ready
+            self._train_plans[key] = plan
+        return plan
+
     # ------------------------------------------------------------------ forward
     def _inference_plan(self, x):
         key = (tuple(x.shape), x.device.index)
@@ -183,8 +251,13 @@ class R2Plus2D(torch.nn.Module):
         if not x.is_cuda:
             raise RuntimeError("R2Plus2D runs on sm_100a only: move the clip batch to a CUDA device (no CPU fallback)")
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("training-mode forward is provided by fastvideotagging_b200.train (round 1: inference)")
+            # inside autograd.record() in the reference: batch-statistics BatchNorm, gradients on backward()
+            return _TrainStep.apply(x, self, self._ensure_anchor(x.device))
         return self._inference_plan(x).forward(x)
+
+    def _ensure_anchor(self, device):
+        self._ensure_flat(device)
+        return self._grad_anchor
 
     def extract_features(self, x):
         """Reference :247-254 — the AvgPool3D output, shape (N, 512, 1, 1, 1)."""

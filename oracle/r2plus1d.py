@@ -410,7 +410,11 @@ class Net:
                 layers = block_layers(item["comp"], item["cin"], item["cout"], item["downsampling"])
                 main = [dict(l) for l in layers if not l.get("shortcut")]
                 main[-1]["last_in_block"] = True
-                short = [l for l in layers if l.get("shortcut")]
+                short = [dict(l) for l in layers if l.get("shortcut")]
+                if short and train:
+                    # training path: the projection's BatchNorm is applied inside the fused residual kernel in fp32
+                    # (no bf16 round trip); the eval path stores the folded shortcut in bf16.
+                    short[-1]["last_in_block"] = True
                 y = self._run(main, x, train, taps)
                 sc = self._run(short, x, train, taps) if short else x
                 x = self._q(torch.relu(y + sc))

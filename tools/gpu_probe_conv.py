@@ -8,7 +8,6 @@ from fastvideotagging_b200 import ops, _lib
 
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
-print("device", torch.cuda.get_device_name(0), "check", _lib.load().fvt_device_check(0), flush=True)
 
 def ref_conv(x_ndhwc, w, stride, pad):
     x = x_ndhwc.float().permute(0, 4, 1, 2, 3).contiguous()
@@ -74,7 +73,7 @@ def run_case(name, n, t, h, w, cin, cout, k, s, p, relu=False, res=False, affine
         print("   bad fraction %.4f; bad rows(first) %s" % (bad.float().mean().item(), sorted(set(bad.nonzero()[:, 3].tolist()))[:10]))
     return ok
 
-cases = [
+CASES = [
     # name, n,t,h,w, cin,cout, k, s, p
     ("1x1x1 64->64 tiny", 1, 2, 8, 8, 64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
     ("1x1x1 64->64 M=128", 1, 2, 8, 8, 64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
@@ -90,20 +89,26 @@ cases = [
     ("3x3x3 96->128", 1, 4, 14, 14, 96, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     ("1x3x3 256->576 big", 4, 8, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
 ]
-allok = True
-for c in cases:
+def main():
+    print("device", torch.cuda.get_device_name(0), "check", _lib.load().fvt_device_check(0), flush=True)
+    allok = True
+    for c in CASES:
+        try:
+            allok &= run_case(*c)
+        except Exception as e:
+            print("%-28s EXC %r" % (c[0], e), flush=True)
+            allok = False
+            break
     try:
-        allok &= run_case(*c)
+        allok &= run_case("epilogue affine+res+relu", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, True)
+        allok &= run_case("epilogue stats", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, False, False, True)
+        allok &= run_case("block_n=64 on 144", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), block_n=64)
+        allok &= run_case("multi-tile persistent", 8, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, True, True)
     except Exception as e:
-        print("%-28s EXC %r" % (c[0], e), flush=True)
-        allok = False
-        break
-try:
-    allok &= run_case("epilogue affine+res+relu", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, True)
-    allok &= run_case("epilogue stats", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, False, False, True)
-    allok &= run_case("block_n=64 on 144", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), block_n=64)
-    allok &= run_case("multi-tile persistent", 8, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, True, True)
-except Exception as e:
-    print("EXC", repr(e)); allok = False
-print("ALL OK" if allok else "SOME FAILED")
-sys.exit(0 if allok else 1)
+        print("EXC", repr(e)); allok = False
+    print("ALL OK" if allok else "SOME FAILED")
+    sys.exit(0 if allok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,10 +9,9 @@ from oracle import r2plus1d as orc
 
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
-allok = True
+STATE = {"ok": True}
 
 def conv_case(name, n, t, h, w, cin, cout, k, s, p):
-    global allok
     cin_s, cout_s = ops.pad16(cin), ops.pad16(cout)
     x = (torch.randn(n, t, h, w, cin_s) * 0.5); x[..., cin:] = 0; x = x.to(torch.bfloat16)
     wt = torch.randn(cout, cin, *k) * (1.0 / (cin * k[0] * k[1] * k[2]) ** 0.5)
@@ -43,9 +42,10 @@ def conv_case(name, n, t, h, w, cin, cout, k, s, p):
     e2 = (dxc - dx_ref).abs().max().item(); sc2 = dx_ref.abs().max().item()
     okd = e2 <= 1.5e-2 * sc2 + 1e-3 and float(dx.float().cpu()[..., cin:].abs().max()) == 0.0 if cin_s > cin else e2 <= 1.5e-2 * sc2 + 1e-3
     print("%-26s wgrad err %.4f/%.3f %s | dgrad err %.4f/%.3f %s" % (name, e, sc, "OK" if okw else "FAIL", e2, sc2, "OK" if okd else "FAIL"), flush=True)
-    allok &= okw and okd
+    STATE["ok"] &= bool(okw and okd)
+    return bool(okw and okd)
 
-cases = [
+CONV_CASES = [
     ("1x3x3 64->144", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ("3x1x1 144->64", 2, 4, 14, 14, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
     ("1x3x3 s2 64->230", 2, 4, 28, 28, 64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
@@ -59,15 +59,8 @@ cases = [
     ("3x1x1 45->64 stem", 1, 4, 28, 28, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
     ("1x3x3 64->144 big", 4, 8, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
 ]
-for c in cases:
-    try:
-        conv_case(*c)
-    except Exception as ex:
-        print("%-26s EXC %r" % (c[0], ex), flush=True); allok = False
-
 # ---- BatchNorm forward (stats from K1 epilogue -> finalize -> apply) and backward
 def bn_case(rows_shape, c, relu, with_mask):
-    global allok
     cs = ops.pad16(c)
     n, t, h, w = rows_shape
     rows = n * t * h * w
@@ -105,13 +98,27 @@ def bn_case(rows_shape, c, relu, with_mask):
     e4 = max(np.abs(sums[:c].cpu().numpy() - dg).max() / (np.abs(dg).max() + 1e-9), np.abs(sums[cs:cs + c].cpu().numpy() - db).max() / (np.abs(db).max() + 1e-9))
     ok = e1 < 3e-2 and e2 < 1e-4 and e3 < 1.5e-2 and e4 < 2e-3
     print("bn rows=%d c=%d relu=%d mask=%d: apply err %.4f running err %.2e dx rel %.4f dgamma/dbeta rel %.2e %s" % (rows, c, relu, with_mask, e1, e2, e3, e4, "OK" if ok else "FAIL"), flush=True)
-    allok &= ok
+    STATE["ok"] &= bool(ok)
+    return bool(ok)
 
-for shp, c, relu, m in (((2, 4, 14, 14), 144, True, True), ((2, 4, 14, 14), 64, False, False), ((1, 2, 7, 7), 1152, True, True),
-                        ((2, 8, 28, 28), 230, True, True), ((1, 4, 28, 28), 45, True, True)):
-    try:
-        bn_case(shp, c, relu, m)
-    except Exception as ex:
-        print("bn EXC %r" % (ex,), flush=True); allok = False
-print("ALL OK" if allok else "SOME FAILED")
-sys.exit(0 if allok else 1)
+BN_CASES = [((2, 4, 14, 14), 144, True, True), ((2, 4, 14, 14), 64, False, False), ((1, 2, 7, 7), 1152, True, True),
+            ((2, 8, 28, 28), 230, True, True), ((1, 4, 28, 28), 45, True, True)]
+
+def main():
+    for c in CONV_CASES:
+        try:
+            conv_case(*c)
+        except Exception as ex:
+            print("%-26s EXC %r" % (c[0], ex), flush=True); STATE["ok"] = False
+
+    for shp, c, relu, m in BN_CASES:
+        try:
+            bn_case(shp, c, relu, m)
+        except Exception as ex:
+            print("bn EXC %r" % (ex,), flush=True); STATE["ok"] = False
+    print("ALL OK" if STATE["ok"] else "SOME FAILED")
+    sys.exit(0 if STATE["ok"] else 1)
+
+
+if __name__ == "__main__":
+    main()
