@@ -19,6 +19,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GFLOP_PER_CLIP_FWD = 304.711020544      # 2*M*N*K over unpadded conv dims, R34 32x112^2 (oracle.conv_flops)
+GFLOP_PER_CLIP_TRAIN = 912.8            # fwd + dgrad + wgrad, minus the stem dgrad
+TRAIN_BATCH_PER_GPU = 4                 # BASELINE configs[2]
 MODEL_DEPTH, NUM_CLASS, T, HW = 34, 101, 32, 112
 BATCH_PER_GPU = 48
 
@@ -160,6 +162,7 @@ def run_ours(args, rank, world, local_rank):
 
     with torch.no_grad():
         plan = net._inference_plan(x_dev)
+        n_launches = plan.launches
         # ---------------- device-resident throughput ("value")
         for _ in range(max(args.warmup, 3)):
             logits = net(x_dev)
@@ -235,11 +238,45 @@ def run_ours(args, rank, world, local_rank):
                 fl = 2.0 * m * L.spec.cout * kk
                 rows.append((L.spec.name, m, L.spec.cout, kk, t, fl / t / 1e9))
 
+    # ---------------- training step (BASELINE configs[2]): fwd + bwd + BCE + NCCL all-reduce + fused SGD
+    train = None
+    if not args.no_train:
+        from fastvideotagging_b200.model import SigmoidBinaryCrossEntropyLoss
+        from fastvideotagging_b200.trainer import Trainer
+        tb = TRAIN_BATCH_PER_GPU
+        net.train()
+        trainer = Trainer(net, "sgd", {"learning_rate": 1e-4, "momentum": 0.9, "wd": 1e-4}, kvstore="device")
+        xt = torch.from_numpy(synthetic_clips(tb, seed=7 + rank)).to(dev)
+        lab = (torch.rand(tb, NUM_CLASS, device=dev) < 0.03).float()
+        lab[:, 0] = 1
+        crit = SigmoidBinaryCrossEntropyLoss()
+
+        def train_step():
+            loss = crit(net(xt), lab).mean()
+            loss.backward()
+            trainer.step(tb * world)
+            return loss
+
+        for _ in range(3):
+            train_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            last = train_step()
+        b.record()
+        barrier()
+        ms_train = a.elapsed_time(b)
+        tplan = list(net._train_plans.values())[0]
+        train = {"ms": ms_train, "loss": float(last.item()), "batch": tb}
+
     # max over ranks
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device=dev)
+        tt = torch.tensor([ms, ms_e2e, train["ms"] if train else 0.0], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = tt[0].item(), tt[1].item()
+        if train:
+            train["ms"] = tt[2].item()
 
     if rank == 0:
         clips = batch * world * args.steps
@@ -267,9 +304,17 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                     "d2h_bytes_per_step": batch * NUM_CLASS * 4 * world, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": plan.launches * args.steps,
+            "gpu_launches": n_launches * args.steps,
             "clocks": clocks,
         }
+        if train:
+            tv = train["batch"] * world * args.steps / (train["ms"] / 1e3)
+            line["train"] = {"metric": "r2plus1d34_32x112_train_clips_per_s", "value": tv, "unit": "clips/s",
+                             "ms_per_step": train["ms"] / args.steps, "final_loss": train["loss"],
+                             "config": "BASELINE configs[2]: fwd+bwd, BCE head, batch %d/GPU, SGD-momentum, %s" % (
+                                 train["batch"], "NCCL all-reduce bucketed+overlapped" if world > 1 else "single GPU"),
+                             "gflop_per_clip": GFLOP_PER_CLIP_TRAIN,
+                             "frac_of_tensor_peak": tv * GFLOP_PER_CLIP_TRAIN / 1e3 / world / peaks["tflops"]}
         print(json.dumps(line), flush=True)
         if args.layer_table:
             with open(args.layer_table, "w") as fh:
@@ -288,6 +333,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--layer-table", default=None, help="write per-layer K1 times (csv)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

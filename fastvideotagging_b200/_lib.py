@@ -57,6 +57,7 @@ def load():
         "fvt_version": (ctypes.c_int, []),
         "fvt_last_error": (ctypes.c_char_p, []),
         "fvt_device_check": (ctypes.c_int, [ctypes.c_int]),
+        "fvt_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
         "fvt_conv3d_out_shape": (ctypes.c_int, [dp, ip, ip, ip]),
         "fvt_conv3d_block_n": (ctypes.c_int, [dp]),
         "fvt_conv3d_packed_weight_elems": (ctypes.c_size_t, [dp]),

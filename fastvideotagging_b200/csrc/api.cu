@@ -11,6 +11,7 @@
 #include "../../include/fvt_b200.h"
 #include "conv_igemm.cuh"
 #include "conv_wgrad.cuh"
+#include "conv_slab.cuh"
 #include "host_common.h"
 
 namespace fvt {
@@ -44,6 +45,7 @@ struct DeviceInfo {
   EncodeIm2colFn encode_im2col = nullptr;
 };
 static DeviceInfo g_dev[16];
+static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
 static int resolve_driver(DeviceInfo& di) {
@@ -196,7 +198,12 @@ using namespace fvt;
 
 extern "C" {
 
-int fvt_version(void) { return 100; }
+int fvt_version(void) { return 101; }
+
+int fvt_set_option(const char* name, int value) {
+  if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
+  return set_error(FVT_ERR_BAD_DESC, "unknown option");
+}
 
 const char* fvt_last_error(void) { return g_err; }
 
@@ -281,6 +288,74 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   const int bn = pick_block_n(d);
   const int rows = weight_rows(d, bn);
   const int taps = d->kt * d->kh * d->kw;
+
+  // ---- K1s: stride-1 'same' spatial convs with <= 128 input channels load each input row once (conv_slab.cuh)
+  if (!g_disable_slab && d->kt == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && (d->kh > 1 || d->kw > 1) &&
+      2 * d->ph == d->kh - 1 && 2 * d->pw == d->kw - 1 && d->cin % 64 == 0 && d->cin <= 128 && d->w + 2 * d->pw <= 128) {
+    SlabParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.frames = d->n * d->t; sp.h = d->h; sp.w = d->w; sp.wp = d->w + 2 * d->pw;
+    sp.ph = d->ph; sp.pw = d->pw; sp.kh = d->kh; sp.kw = d->kw;
+    sp.r_out = 128 / sp.wp;
+    if (sp.r_out > d->h) sp.r_out = d->h;
+    sp.r_in = sp.r_out + d->kh - 1;
+    sp.tiles_per_frame = (d->h + sp.r_out - 1) / sp.r_out;
+    const double useful = (double)d->h * d->w / ((double)sp.tiles_per_frame * 128.0);
+    sp.cin_blocks = d->cin / 64; sp.cin_k16 = d->cin / 16;
+    sp.n_tile = bn; sp.num_n_tiles = rows / bn;
+    const int slot_rows = (128 + (d->kh - 1) * sp.wp + d->kw - 1 + 7) / 8 * 8;
+    sp.slab_slot_bytes = slot_rows * 128;
+    sp.slab_tx_bytes = sp.wp * sp.r_in * 128;
+    const int stage_bytes = sp.cin_blocks * sp.slab_slot_bytes;
+    const int b_slab = bn * 128;
+    const int b_all = taps * sp.cin_blocks;
+    const bool want_stats = (d->flags & FVT_CONV_STATS) != 0;
+    const int aux = (512 + 2 * rows * 4 + (want_stats ? 2 * bn * 4 : 0) + 255) / 256 * 256;
+    const int kSmemMax = 227 * 1024;
+    bool ok = useful >= 0.6 && sp.r_in * sp.wp <= slot_rows && sp.r_in <= 256;
+    if (ok) {
+      if (sp.num_n_tiles == 1 && b_all <= kSlabMaxBRing && b_all * b_slab + 2 * stage_bytes + aux <= kSmemMax) {
+        sp.b_stationary = 1;
+        sp.b_ring = b_all;
+        sp.stages = (kSmemMax - aux - b_all * b_slab) / stage_bytes;
+      } else {
+        sp.b_stationary = 0;
+        sp.stages = 2;
+        sp.b_ring = (kSmemMax - aux - 2 * stage_bytes) / b_slab;
+        if (sp.b_ring > kSlabMaxBRing) sp.b_ring = kSlabMaxBRing;
+        if (sp.b_ring < 4) ok = false;
+      }
+      if (sp.stages > kSlabMaxStages) sp.stages = kSlabMaxStages;
+    }
+    if (ok) {
+      sp.cout_store = d->cout; sp.flags = d->flags;
+      sp.scale = scale; sp.shift = shift; sp.residual = (const __nv_bfloat16*)residual;
+      sp.y = (__nv_bfloat16*)y; sp.stats = stats;
+      const int smem_bytes = sp.b_ring * b_slab + sp.stages * stage_bytes + aux;
+      CUtensorMap tmx, tmw;
+      const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)sp.frames};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w, (cuuint64_t)d->cin * 2 * d->w * d->h};
+      const cuuint32_t box[4] = {64, (cuuint32_t)sp.wp, (cuuint32_t)sp.r_in, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(slab x) failed (CUresult %d)", (int)r);
+      if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
+      static bool attr_set_s[16] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr_set_s[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_slab_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_fwd_kernel): %s", cudaGetErrorString(e));
+        attr_set_s[dev] = true;
+      }
+      const int m_tiles = sp.frames * sp.tiles_per_frame;
+      const int grid = m_tiles < di->sm_count ? m_tiles : di->sm_count;
+      conv_slab_fwd_kernel<<<grid, kSlabThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
+      return check_launch("conv_slab_fwd_kernel");
+    }
+  }
 
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));

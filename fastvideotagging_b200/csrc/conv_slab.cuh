@@ -1,0 +1,269 @@
+// K1s — "slab" variant of the implicit-GEMM forward kernel for stride-1 spatial convolutions (1 x kh x kw, the 1x3x3
+// convs that carry 74 % of the R(2+1)D FLOPs).
+//
+// K1 fetches one im2col tile per filter tap, i.e. reads every input pixel kh*kw times from L2; with the small channel
+// counts of conv2_x/conv3_x that makes the layer L2->SM-bandwidth-bound (ncu: 11.8 GB of L2 reads for 2.0 GB of HBM
+// traffic).  Here each CTA loads a *slab* of R_in whole padded image rows ONCE with a tiled TMA box
+// [64 ch, W+2*pw, R_in rows] (the out-of-bounds halo is zero-filled by TMA), and every filter tap (dh, dw) is the SAME
+// slab addressed through a shared-memory descriptor whose start is shifted by (dh*(W+2pw) + dw) rows: with 128-byte
+// swizzling the UMMA address generator swizzles on absolute smem address bits, so any 128-byte-aligned start inside a
+// TMA-written slab is a valid K-major operand (verified in tools/experiments/shifted_desc.cu).
+//
+// GEMM rows of a tile = R_out consecutive padded image rows (positions m' = hl*Wp + w', Wp = W + 2pw); the 2pw junk
+// columns per row and the rows beyond R_out*Wp are computed but never stored.  Weights: when all kh*kw*cin_blocks
+// [n_tile x 64] slabs fit next to two input slabs they are loaded once and stay resident for the CTA's lifetime
+// ("stationary"); otherwise they stream through a ring.
+//
+// Warp roles (384 threads): warp0 slab producer, warp1 MMA issuer, warp2 TMEM allocator, warp3 weight producer,
+// warps 4-11 epilogue (shared with K1: epilogue.cuh).
+#pragma once
+#include "ptx.cuh"
+#include "epilogue.cuh"
+
+namespace fvt {
+
+constexpr int kSlabThreads = 384;
+constexpr int kSlabMaxStages = 4;
+constexpr int kSlabMaxBRing = 24;
+
+struct SlabParams {
+  int frames;              // N*T
+  int h, w;                // image extent (output extent is the same: stride 1, 'same' padding)
+  int wp;                  // padded row pitch W + 2*pw
+  int ph, pw, kh, kw;
+  int r_out, r_in;         // output rows per tile, slab rows loaded per tile
+  int tiles_per_frame;
+  int cin_blocks, cin_k16; // 64-channel blocks / 16-channel MMA steps of the input
+  int n_tile, num_n_tiles;
+  int slab_slot_bytes;     // per 64-channel block, multiple of 1024
+  int slab_tx_bytes;       // bytes one slab TMA load delivers (wp * r_in * 128)
+  int stages;              // slab stages
+  int b_ring;              // weight ring slots
+  int b_stationary;
+  int cout_store, flags;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  float* stats;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kSlabThreads, 1)
+conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                     const SlabParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();      // swizzle atoms need a 1024-byte aligned carve-up
+
+  const int taps = p.kh * p.kw;
+  const int b_slab_bytes = p.n_tile * 128;
+  const int stage_bytes = p.cin_blocks * p.slab_slot_bytes;
+  uint8_t* smem_b = smem;                                              // [b_ring][n_tile x 64]
+  uint8_t* smem_a = smem + p.b_ring * b_slab_bytes;                    // [stages][cin_blocks][slot]
+  uint8_t* aux = smem_a + p.stages * stage_bytes;
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(aux);             // [kSlabMaxStages]
+  uint64_t* slab_empty = slab_full + kSlabMaxStages;
+  uint64_t* b_full = slab_empty + kSlabMaxStages;                      // [kSlabMaxBRing]
+  uint64_t* b_empty = b_full + kSlabMaxBRing;
+  uint64_t* acc_full = b_empty + kSlabMaxBRing;                        // [2]
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* affine_smem = reinterpret_cast<float*>(tmem_slot + 4);        // scale[n_total], shift[n_total]
+  const int n_total = p.n_tile * p.num_n_tiles;
+  float* stat_smem = affine_smem + 2 * n_total;                        // [2][n_tile] (only touched with kConvStats)
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_x);
+    ptx::prefetch_tensormap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&slab_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&slab_empty[s]), 1);
+    }
+    for (int s = 0; s < p.b_ring; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&b_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&b_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&acc_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&acc_empty[s]), 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+    ptx::tmem_relinquish();
+  }
+  if (p.scale != nullptr) {
+    for (int i = threadIdx.x; i < n_total; i += kSlabThreads) {
+      affine_smem[i] = i < p.cout_store ? __ldg(p.scale + i) : 0.f;
+      affine_smem[n_total + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m_tiles = p.frames * p.tiles_per_frame;
+  const int b_per_ntile = taps * p.cin_blocks;
+
+  if (warp == 0) {
+    // ===================================================== input slab producer (warp-uniform, elected lane issues)
+    {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+        const int frame = mt / p.tiles_per_frame;
+        const int h0 = (mt - frame * p.tiles_per_frame) * p.r_out;
+        ptx::mbar_wait(ptx::smem_u32(&slab_empty[stage]), phase ^ 1);
+        const uint32_t fb = ptx::smem_u32(&slab_full[stage]);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(fb, p.cin_blocks * p.slab_tx_bytes);
+          for (int cb = 0; cb < p.cin_blocks; ++cb)
+            tma_load_4d(ptx::smem_u32(smem_a + stage * stage_bytes + cb * p.slab_slot_bytes), &tmap_x, fb,
+                        cb * 64, -p.pw, h0 - p.ph, frame);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================== weight producer
+    {
+      int slot = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+        if (p.b_stationary && !first) break;
+        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+          for (int j = 0; j < b_per_ntile; ++j) {
+            ptx::mbar_wait(ptx::smem_u32(&b_empty[slot]), phase ^ 1);
+            const uint32_t fb = ptx::smem_u32(&b_full[slot]);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(fb, b_slab_bytes);
+              ptx::tma_load_2d(ptx::smem_u32(smem_b + slot * b_slab_bytes), &tmap_w, fb, j * 64, nt * p.n_tile);
+            }
+            __syncwarp();
+            if (++slot == p.b_ring) { slot = 0; phase ^= 1; }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (warp-uniform loop, elected lane issues)
+    {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.n_tile, 0, 0);
+      int stage = 0, slot = 0, acc = 0;
+      uint32_t phase = 0, bphase = 0, acc_phase = 0;
+      bool first = true;
+      for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+        ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
+        ptx::tc_fence_after();
+        const uint32_t a_base = ptx::smem_u32(smem_a + stage * stage_bytes);
+        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+          ptx::mbar_wait(ptx::smem_u32(&acc_empty[acc]), acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          uint32_t row_off = 0;
+          int dw = 0;
+          for (int tap = 0; tap < taps; ++tap) {
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+              if (!p.b_stationary || first) {
+                ptx::mbar_wait(ptx::smem_u32(&b_full[slot]), bphase);
+                ptx::tc_fence_after();
+              }
+              int k16 = p.cin_k16 - cb * 4;
+              if (k16 > 4) k16 = 4;
+              const uint64_t a_desc = ptx::make_sw128_desc(a_base + cb * p.slab_slot_bytes + row_off, 16, 1024);
+              const uint64_t b_desc = ptx::make_sw128_desc(ptx::smem_u32(smem_b + slot * b_slab_bytes), 16, 1024);
+              if (ptx::elect_one()) {
+                ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (tap | cb) != 0);
+                if (k16 > 1) ptx::umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
+                if (k16 > 2) ptx::umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
+                if (k16 > 3) ptx::umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
+                if (!p.b_stationary) ptx::umma_commit(ptx::smem_u32(&b_empty[slot]));
+              }
+              __syncwarp();
+              if (++slot == p.b_ring) { slot = 0; bphase ^= 1; }
+            }
+            // next tap: one column to the right, or first column of the next padded row
+            if (++dw == p.kw) { dw = 0; row_off += static_cast<uint32_t>(p.wp - p.kw + 1) * 128u; }
+            else row_off += 128u;
+          }
+          if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&acc_full[acc]));
+          __syncwarp();
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (p.b_stationary) { slot = 0; first = false; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&slab_empty[stage]));
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128;
+    const bool do_stats = (p.flags & kConvStats) != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    EpilogueArgs ea;
+    ea.block_n = p.n_tile; ea.cout_store = p.cout_store; ea.flags = p.flags;
+    ea.scale_smem = p.scale != nullptr ? affine_smem : nullptr; ea.shift_smem = affine_smem + n_total;
+    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem; ea.stat_stride = p.n_tile;
+    const int r = q * 32 + lane;                 // GEMM row = padded position m' inside the tile
+    const int hl = r / p.wp, wl = r - hl * p.wp;
+    for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+      const int frame = mt / p.tiles_per_frame;
+      const int h0 = (mt - frame * p.tiles_per_frame) * p.r_out;
+      const bool ok = hl < p.r_out && wl < p.w && (h0 + hl) < p.h;
+      const long long out_row = ok ? (static_cast<long long>(frame) * p.h + h0 + hl) * p.w + wl : -1ll;
+      for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+        const int n0 = nt * p.n_tile;
+        if (do_stats) {
+          for (int i = et; i < 2 * p.n_tile; i += 256) stat_smem[i] = 0.f;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        ptx::mbar_wait(ptx::smem_u32(&acc_full[acc]), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+        epilogue_chunks(ea, taddr, n0, out_row, grp, lane);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (do_stats) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int i = et; i < p.n_tile; i += 256) {
+            if (n0 + i < p.cout_store) {
+              atomicAdd(p.stats + n0 + i, stat_smem[i]);
+              atomicAdd(p.stats + p.cout_store + n0 + i, stat_smem[p.n_tile + i]);
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fvt

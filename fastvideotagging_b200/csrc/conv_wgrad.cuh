@@ -93,7 +93,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (m_valid_groups + p.n_loads) * kSlabBytes;
@@ -106,8 +106,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int cw = ow * p.sw - p.pw, ch = oh * p.sh - p.ph, cd = ot * p.st - p.pt;
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-        ptx::mbar_arrive_expect_tx(fb, tx_bytes);
         uint8_t* base = smem + stage * stage_bytes;
+        if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(fb, tx_bytes);
         // ---- M side
         for (int g = 0; g < m_valid_groups; ++g) {
           const uint32_t dst = ptx::smem_u32(base + g * kSlabBytes);
@@ -131,11 +132,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             ptx::tma_load_im2col_5d(dst, &tmap_x, fb, c0, cw, ch, cd, on, (uint16_t)dw_, (uint16_t)dh_, (uint16_t)dt_);
           }
         }
+        }
+        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.n_tile, 1, 1);    // both operands MN-major
       int stage = 0;
       uint32_t phase = 0;
@@ -147,15 +150,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // MN-major SW128: LBO = distance between 64-channel groups (one slab), SBO = 8 pixel rows = 1024 B
         const uint64_t a_desc = ptx::make_sw128_desc(a_addr, kSlabBytes, 1024);
         const uint64_t b_desc = ptx::make_sw128_desc(b_addr, kSlabBytes, 1024);
-#pragma unroll
-        for (int k = 0; k < kWgPix / 16; ++k) {
+        if (ptx::elect_one()) {
           // 16 pixels = 2 swizzle atoms = 2048 B along K  ->  +128 in the (addr >> 4) field
-          ptx::umma_bf16_ss(tmem_base, a_desc + 128 * k, b_desc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          ptx::umma_bf16_ss(tmem_base, a_desc, b_desc, idesc, kb > kb0 ? 1u : 0u);
+          ptx::umma_bf16_ss(tmem_base, a_desc + 128, b_desc + 128, idesc, 1u);
+          ptx::umma_bf16_ss(tmem_base, a_desc + 256, b_desc + 256, idesc, 1u);
+          ptx::umma_bf16_ss(tmem_base, a_desc + 384, b_desc + 384, idesc, 1u);
+          ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
         }
-        ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
+        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(ptx::smem_u32(acc_bar));
+      if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(acc_bar));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int q = warp & 3;

@@ -1,0 +1,144 @@
+// Shared epilogue of the tcgen05 convolution kernels: TMEM accumulator tile -> registers -> (per-channel statistics)
+// -> scale/shift (folded BatchNorm) -> (+ residual) -> (ReLU) -> bf16 rows of Y.
+// One call handles this warp's 32 accumulator rows (TMEM lanes) for the 16-column chunks grp, grp+2, grp+4, ...;
+// TMEM and residual loads of chunk i+1 are in flight while chunk i is processed.
+#pragma once
+#include "ptx.cuh"
+
+namespace fvt {
+
+enum ConvFlags : int {
+  kConvRelu = 1,
+  kConvResidual = 2,
+  kConvStats = 4,
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+struct EpilogueArgs {
+  int block_n;                      // accumulator columns of this tile
+  int cout_store;                   // channel pitch of Y / residual
+  int flags;                        // ConvFlags
+  const float* scale_smem;          // staged per-channel scale (indexed by absolute channel) or nullptr
+  const float* shift_smem;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  float* stat_smem;                 // [2][stat_stride] per-CTA partial sums (kConvStats)
+  int stat_stride;
+};
+
+// taddr: TMEM address of (this warp's first lane, column 0 of the tile); n0: first absolute channel of the tile;
+// out_row: row of Y this thread's accumulator row maps to, or < 0 when the row is padding / out of range.
+__device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t taddr, int n0, long long out_row,
+                                                int grp, int lane) {
+  const bool do_stats = (p.flags & kConvStats) != 0;
+  const bool has_affine = p.scale_smem != nullptr;
+  const bool has_res = (p.flags & kConvResidual) != 0;
+  const bool relu = (p.flags & kConvRelu) != 0;
+  const bool row_ok = out_row >= 0;
+  const int n_chunks = p.block_n >> 4;
+  float* stat_smem = p.stat_smem;
+  __nv_bfloat16* yrow = p.y + static_cast<size_t>(row_ok ? out_row : 0) * p.cout_store;
+  const __nv_bfloat16* rrow = has_res ? p.residual + static_cast<size_t>(row_ok ? out_row : 0) * p.cout_store : nullptr;
+  // software pipeline: TMEM load + residual load of chunk i+1 are in flight while chunk i is processed
+  uint32_t v[16], vn[16];
+  uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, rn0 = r0, rn1 = r0;
+  int ci = grp;
+  if (ci < n_chunks) {
+    ptx::tmem_ld_32x32b_x16(taddr + ci * 16, vn);
+    if (has_res && n0 + ci * 16 < p.cout_store) {
+      rn0 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + ci * 16));
+      rn1 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + ci * 16 + 8));
+    }
+  }
+  for (; ci < n_chunks; ci += 2) {
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = vn[i];
+    r0 = rn0; r1 = rn1;
+    const int c = ci * 16;
+    const int ch0 = n0 + c;
+    const int cnext = ci + 2;
+    if (cnext < n_chunks) {
+      ptx::tmem_ld_32x32b_x16(taddr + cnext * 16, vn);
+      if (has_res && n0 + cnext * 16 < p.cout_store) {
+        rn0 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + cnext * 16));
+        rn1 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + cnext * 16 + 8));
+      }
+    }
+    if (ch0 >= p.cout_store) continue;           // N tail (weights zero-padded to a whole tile)
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    if (do_stats) {
+      // per-channel sum / sum^2 over this warp's 32 rows: recursive-halving butterfly, 16 values -> 1 per lane pair
+      float s1[16], s2[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        // statistics of the value that is actually stored (bf16-rounded); rows beyond M contribute 0
+        float r = row_ok ? __bfloat162float(__float2bfloat16_rn(f[i])) : 0.f;
+        s1[i] = r; s2[i] = r * r;
+      }
+#pragma unroll
+      for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send1 = upper ? s1[i] : s1[i + half];
+          const float keep1 = upper ? s1[i + half] : s1[i];
+          const float send2 = upper ? s2[i] : s2[i + half];
+          const float keep2 = upper ? s2[i + half] : s2[i];
+          s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, bit);
+          s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, bit);
+        }
+      }
+      s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+      s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+      if ((lane & 1) == 0) {
+        const int chl = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+        atomicAdd(&stat_smem[c + chl], s1[0]);
+        atomicAdd(&stat_smem[p.stat_stride + c + chl], s2[0]);
+      }
+    }
+    if (has_affine) {
+      const float4* sc4 = reinterpret_cast<const float4*>(p.scale_smem + ch0);
+      const float4* sh4 = reinterpret_cast<const float4*>(p.shift_smem + ch0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = sc4[i], b = sh4[i];
+        f[4 * i + 0] = fmaf(f[4 * i + 0], a.x, b.x);
+        f[4 * i + 1] = fmaf(f[4 * i + 1], a.y, b.y);
+        f[4 * i + 2] = fmaf(f[4 * i + 2], a.z, b.z);
+        f[4 * i + 3] = fmaf(f[4 * i + 3], a.w, b.w);
+      }
+    }
+    if (row_ok) {
+      if (has_res) {
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[2 * i] += bf16_lo(rr[i]);
+          f[2 * i + 1] += bf16_hi(rr[i]);
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      uint4 o0, o1;
+      o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+      o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+      o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+      o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+      *reinterpret_cast<uint4*>(yrow + ch0) = o0;
+      *reinterpret_cast<uint4*>(yrow + ch0 + 8) = o1;
+    }
+  }
+}
+
+}  // namespace fvt

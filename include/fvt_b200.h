@@ -56,6 +56,8 @@ int fvt_version(void);
 const char* fvt_last_error(void);
 /* 0 if `device` is an sm_100 part and the driver exposes the tensor-map encoders, else a negative status. */
 int fvt_device_check(int device);
+/* Tuning/debug switches. "disable_slab" = 1 routes every convolution through the generic im2col kernel (K1). */
+int fvt_set_option(const char* name, int value);
 
 /* ---- convolution (K1) ----------------------------------------------------------------------------------- */
 /* Output extent floor((x + 2p - k)/s) + 1 per axis (MXNet convention). */

@@ -17,7 +17,7 @@ def _probe_train():
     return gpu_probe_train
 
 
-@pytest.mark.parametrize("idx", range(13))
+@pytest.mark.parametrize("idx", range(16))
 def test_conv_forward_shapes(cuda_device, idx):
     m = _probe_conv()
     assert m.run_case(*m.CASES[idx])
@@ -31,6 +31,27 @@ def test_conv_forward_epilogues(cuda_device):
     assert m.run_case("block_n=64", *base, block_n=64)
     assert m.run_case("multi-tile persistent", 8, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, True, True)
     assert m.run_case("ragged M tail", 1, 3, 7, 9, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, False, True, True)
+
+
+def test_slab_and_im2col_kernels_agree(cuda_device, lib):
+    """K1s (slab) and K1 (im2col) are two schedules of the same convolution: identical inputs -> results equal up to
+    fp32 summation order (<= 1 bf16 ulp)."""
+    import torch
+    from fastvideotagging_b200 import ops
+    torch.manual_seed(3)
+    x = (torch.randn(2, 4, 28, 28, 64) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = torch.randn(144, 64, 1, 3, 3, device=cuda_device) / 24.0
+    d = ops.conv_desc(2, 4, 28, 28, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), ops.FVT_CONV_RELU)
+    wp = ops.pack_conv_weight(d, w)
+    y_slab = ops.conv3d_fwd(d, x, wp)
+    assert lib.fvt_set_option(b"disable_slab", 1) == 0
+    try:
+        y_gen = ops.conv3d_fwd(d, x, wp)
+    finally:
+        lib.fvt_set_option(b"disable_slab", 0)
+    torch.cuda.synchronize()
+    diff = (y_slab.float() - y_gen.float()).abs().max().item()
+    assert diff <= 2 ** -7 * y_gen.float().abs().max().item()
 
 
 @pytest.mark.parametrize("idx", range(12))

@@ -88,6 +88,9 @@ CASES = [
     ("3x1x1 45->64 stem", 1, 4, 56, 56, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
     ("3x3x3 96->128", 1, 4, 14, 14, 96, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     ("1x3x3 256->576 big", 4, 8, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 64->144 56x56 slab", 2, 8, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 128->288 28x28 slab", 2, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 64->64 odd 13x9", 1, 3, 13, 9, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
 ]
 def main():
     print("device", torch.cuda.get_device_name(0), "check", _lib.load().fvt_device_check(0), flush=True)
