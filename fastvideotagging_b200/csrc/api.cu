@@ -12,6 +12,7 @@
 #include "conv_igemm.cuh"
 #include "conv_wgrad.cuh"
 #include "conv_slab.cuh"
+#include "conv_wgrad_slab.cuh"
 #include "host_common.h"
 
 namespace fvt {
@@ -45,6 +46,8 @@ struct DeviceInfo {
   EncodeIm2colFn encode_im2col = nullptr;
 };
 static DeviceInfo g_dev[16];
+static int g_disable_bstat = 0;  // fvt_set_option("disable_b_stationary", 1): K1 always streams the weights
+static int g_disable_wgrad_slab = 0;   // fvt_set_option("disable_wgrad_slab", 1): K3 (im2col) for every weight gradient
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -138,25 +141,59 @@ static int pick_block_n(const fvt_conv_desc* d) {
 static int weight_rows(const fvt_conv_desc* d, int bn) { return (d->cout + bn - 1) / bn * bn; }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// dgrad = 1: pack the weights of the data-gradient convolution instead (input/output channels swapped, taps
-// reversed): out[ci][taps-1-tap][co] = w[co][ci][tap]; here rows index ci and the K axis runs over (tap, co).
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int taps,
-                                   int cin_store, int cout_real, int cin_real, int dgrad) {
-  const size_t total = static_cast<size_t>(rows) * taps * cin_store;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int ci = static_cast<int>(i % cin_store);
-    const size_t r = i / cin_store;
-    const int tap = static_cast<int>(r % taps);
-    const int o = static_cast<int>(r / taps);
+// fp32 (O, I, taps) master weights -> bf16 K-major operand layout out[row][tap][k] (k = stored input channels).
+// Both kernels stage a tile in shared memory so that global reads AND writes are runs of contiguous bytes (the naive
+// gather reads with a stride of taps*4 B, or cin*taps*4 B for the data-gradient layout, and ran 8x off HBM speed).
+//
+// forward layout: out[o][tap][ci] = w[o][ci][tap].  One CTA per output row o: the row (cin_real*taps floats) is
+// contiguous in w; it is read once, permuted in shared memory and written as taps runs of cin_store bf16.
+__global__ void __launch_bounds__(256)
+pack_weight_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int cin_store,
+                       int cout_real, int cin_real) {
+  extern __shared__ float srow[];                       // [cin_real * taps]
+  const int o = blockIdx.x;
+  const int len = cin_real * taps;
+  const bool live = o < cout_real;
+  if (live) {
+    const float* src = w + static_cast<size_t>(o) * len;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) srow[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = out + static_cast<size_t>(o) * taps * cin_store;
+  const int total = taps * cin_store;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int tap = i / cin_store, ci = i - tap * cin_store;
+    const float v = (live && ci < cin_real) ? srow[ci * taps + tap] : 0.f;
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// data-gradient layout: out[r][taps-1-tap][k] = w[k][r][tap]  (r = forward input channel, k = forward output channel).
+// One CTA per (8 rows r, 64 channels k): reads 64 runs of 8*taps contiguous floats, writes 8*taps runs of 64 bf16.
+constexpr int kPackR = 8, kPackK = 64;
+__global__ void __launch_bounds__(256)
+pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int taps, int k_store,
+                         int fwd_cin_real, int fwd_cout_real) {
+  extern __shared__ float stile[];                      // [kPackK][kPackR * taps + 1]
+  const int r0 = blockIdx.x * kPackR;
+  const int k0 = blockIdx.y * kPackK;
+  const int run = kPackR * taps;
+  const int pitch = run + 1;
+  for (int i = threadIdx.x; i < kPackK * run; i += blockDim.x) {
+    const int kk = i / run, j = i - kk * run;           // j = rr * taps + tap
+    const int rr = j / taps;
+    const int k = k0 + kk, r = r0 + rr;
     float v = 0.f;
-    if (!dgrad) {
-      if (o < cout_real && ci < cin_real) v = w[(static_cast<size_t>(o) * cin_real + ci) * taps + tap];
-    } else {
-      // this conv: out channel o = forward ci, in channel ci = forward co; forward dims are (cin_real, cout_real)
-      if (o < cout_real && ci < cin_real) v = w[(static_cast<size_t>(ci) * cout_real + o) * taps + (taps - 1 - tap)];
-    }
-    out[i] = __float2bfloat16_rn(v);
+    if (k < fwd_cout_real && r < fwd_cin_real) v = __ldg(w + (static_cast<size_t>(k) * fwd_cin_real + r0) * taps + j);
+    stile[kk * pitch + j] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < run * kPackK; i += blockDim.x) {
+    const int j = i / kPackK, kk = i - j * kPackK;
+    const int rr = j / taps, tap = j - rr * taps;
+    const int r = r0 + rr, k = k0 + kk;
+    if (r < rows && k < k_store)
+      out[(static_cast<size_t>(r) * taps + (taps - 1 - tap)) * k_store + k] = __float2bfloat16_rn(stile[kk * pitch + j]);
   }
 }
 
@@ -192,6 +229,133 @@ static int encode_w_map(const DeviceInfo* di, const void* w, int k_total, int ro
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ K3s launch
+// Returns 1 when the slab weight-gradient kernel took the call, 0 when the shape is not eligible, < 0 on error.
+static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
+                          int cout_real, int cin_real, cudaStream_t stream) {
+  if (g_disable_wgrad_slab) return 0;
+  if (!(d->kt == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && (d->kh > 1 || d->kw > 1) &&
+        2 * d->ph == d->kh - 1 && 2 * d->pw == d->kw - 1 && d->cin % 64 == 0 && d->w + 2 * d->pw <= 128))
+    return 0;
+  WgradSlabParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = d->n * d->t; p.h = d->h; p.w = d->w; p.wp = d->w + 2 * d->pw;
+  p.ph = d->ph; p.pw = d->pw; p.kh = d->kh; p.kw = d->kw;
+  p.r_out = 128 / p.wp;
+  if (p.r_out > d->h) p.r_out = d->h;
+  p.r_in = p.r_out + d->kh - 1;
+  p.tiles_per_frame = (d->h + p.r_out - 1) / p.r_out;
+  p.num_tiles = p.frames * p.tiles_per_frame;
+  p.ksteps = (p.r_out * p.wp + 15) / 16;
+  p.taps = d->kh * d->kw;
+  p.cin_blocks = d->cin / 64;
+  p.groups = p.taps * p.cin_blocks;
+  const int slot_rows = (128 + (d->kh - 1) * p.wp + d->kw - 1 + 7) / 8 * 8;
+  if (p.r_in * p.wp > slot_rows || p.r_in > 256) return 0;
+  p.slab_slot_bytes = slot_rows * 128;
+  p.slab_tx_bytes = p.wp * p.r_in * 128;
+  p.dy_tx_bytes = p.wp * p.r_out * 128;
+  const double useful = (double)d->h * d->w / ((double)p.tiles_per_frame * 16.0 * p.ksteps);
+  if (useful < 0.45) return 0;
+  const int kSmemMax = 227 * 1024, kAux = 1024;
+  const int mt_total = (p.groups + 1) / 2;
+
+  // ---- pick (N tile, M tiles per CTA): minimise the estimated time of the slowest CTA
+  double best = 1e30;
+  int best_nt = 0, best_mt = 0;
+  for (int nt = 1; nt <= 8; ++nt) {
+    const int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
+    if (n_tile > 256) continue;
+    if (nt > 1 && n_tile * (nt - 1) >= d->cout) continue;       // an empty last tile
+    const int acc_stride = (n_tile + 31) / 32 * 32;
+    const int n_blocks = (n_tile + 63) / 64;
+    int mt_max = 512 / acc_stride;
+    if (mt_max > kWgsMaxMt) mt_max = kWgsMaxMt;
+    for (int mt = 1; mt <= mt_max && mt <= mt_total; ++mt) {
+      const int m_chunks = (mt_total + mt - 1) / mt;
+      int ncb_max = 1;
+      for (int c = 0; c < m_chunks; ++c) {
+        const int g_lo = c * 2 * mt;
+        int g_hi = g_lo + 2 * mt; if (g_hi > p.groups) g_hi = p.groups;
+        const int span = (g_hi - 1) / p.taps - g_lo / p.taps + 1;
+        if (span > ncb_max) ncb_max = span;
+      }
+      const int stage_bytes = ncb_max * p.slab_slot_bytes + n_blocks * 128 * 128;
+      if (2 * stage_bytes + kAux > kSmemMax) continue;
+      const int items = m_chunks * nt;
+      int splits = di->sm_count / items;
+      if (splits < 1) splits = 1;
+      if (splits > p.num_tiles) splits = p.num_tiles;
+      const int tps = (p.num_tiles + splits - 1) / splits;
+      const double mma_clk = (double)mt * p.ksteps * (n_tile / 2.0);
+      const double bytes = (double)ncb_max * p.slab_tx_bytes + (double)p.dy_tx_bytes * n_tile / 64.0;
+      const double per_tile = mma_clk > bytes / 64.0 ? mma_clk : bytes / 64.0;
+      const int waves = (items * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
+      const double epi = (double)mt * n_tile * 40.0;            // atomics of one accumulator block
+      const double est = waves * (tps * per_tile + epi + 3000.0);
+      if (est < best) { best = est; best_nt = nt; best_mt = mt; }
+    }
+  }
+  if (best_nt == 0) return 0;
+  p.n_tiles = best_nt;
+  p.n_tile = ((d->cout + best_nt - 1) / best_nt + 15) / 16 * 16;
+  p.acc_stride = (p.n_tile + 31) / 32 * 32;
+  p.n_blocks = (p.n_tile + 63) / 64;
+  p.mt_per_cta = best_mt;
+  p.m_chunks = (mt_total + best_mt - 1) / best_mt;
+  p.ncb_max = 1;
+  for (int c = 0; c < p.m_chunks; ++c) {
+    const int g_lo = c * 2 * best_mt;
+    int g_hi = g_lo + 2 * best_mt; if (g_hi > p.groups) g_hi = p.groups;
+    const int span = (g_hi - 1) / p.taps - g_lo / p.taps + 1;
+    if (span > p.ncb_max) p.ncb_max = span;
+  }
+  p.stage_bytes = p.ncb_max * p.slab_slot_bytes + p.n_blocks * 128 * 128;
+  p.stages = (kSmemMax - kAux) / p.stage_bytes;
+  if (p.stages > kWgsMaxStages) p.stages = kWgsMaxStages;
+  const int items = p.m_chunks * p.n_tiles;
+  int splits = di->sm_count / items;
+  if (splits < 1) splits = 1;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
+  p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.cin_real = cin_real; p.cout_real = cout_real;
+  p.dw = dw;
+
+  CUtensorMap tmx, tmdy;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)p.frames};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w, (cuuint64_t)d->cin * 2 * d->w * d->h};
+    const cuuint32_t box[4] = {64, (cuuint32_t)p.wp, (cuuint32_t)p.r_in, 1};
+    CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad slab x) failed (CUresult %d)", (int)r);
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)p.frames};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * d->w, (cuuint64_t)d->cout * 2 * d->w * d->h};
+    const cuuint32_t box[4] = {64, (cuuint32_t)p.wp, (cuuint32_t)p.r_out, 1};
+    CUresult r = di->encode_tiled(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad slab dy) failed (CUresult %d)", (int)r);
+  }
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_wgrad_slab_kernel): %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const int smem_bytes = p.stages * p.stage_bytes + kAux;
+  conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
+  if (int e = check_launch("conv_wgrad_slab_kernel")) return e;
+  return 1;
+}
+
 }  // namespace fvt
 
 using namespace fvt;
@@ -202,6 +366,8 @@ int fvt_version(void) { return 101; }
 
 int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
+  if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
+  if (name != nullptr && strcmp(name, "disable_wgrad_slab") == 0) { g_disable_wgrad_slab = value; return 0; }
   return set_error(FVT_ERR_BAD_DESC, "unknown option");
 }
 
@@ -243,12 +409,18 @@ int fvt_pack_conv_weight(const fvt_conv_desc* d, const float* w_oidhw, int32_t c
   const int bn = pick_block_n(d);
   const int rows = weight_rows(d, bn);
   const int taps = d->kt * d->kh * d->kw;
-  const size_t total = (size_t)rows * taps * d->cin;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4096) blocks = 4096;
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, rows, taps, d->cin,
-                                                              cout_real, cin_real, 0);
-  return check_launch("pack_weight_kernel");
+  const size_t smem = sizeof(float) * (size_t)cin_real * taps;
+  if (smem > 96 * 1024) return set_error(FVT_ERR_BAD_DESC, "filter row too long to pack (%zu bytes)", smem);
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaFuncSetAttribute(pack_weight_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set[dev] = true;
+  }
+  pack_weight_fwd_kernel<<<rows, 256, smem, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, taps, d->cin,
+                                                                    cout_real, cin_real);
+  return check_launch("pack_weight_fwd_kernel");
 }
 
 int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int32_t fwd_cout_real, int32_t fwd_cin_real,
@@ -261,13 +433,20 @@ int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int
   const int bn = pick_block_n(d);
   const int rows = weight_rows(d, bn);
   const int taps = d->kt * d->kh * d->kw;
-  const size_t total = (size_t)rows * taps * d->cin;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4096) blocks = 4096;
-  // kernel view: rows o = forward ci (< fwd_cin_real), K channel ci = forward co (< fwd_cout_real)
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, rows, taps, d->cin,
-                                                              fwd_cin_real, fwd_cout_real, 1);
-  return check_launch("pack_weight_kernel(dgrad)");
+  // kernel view: rows r = forward ci (< fwd_cin_real), K channel k = forward co (< fwd_cout_real)
+  const dim3 grid((rows + kPackR - 1) / kPackR, (d->cin + kPackK - 1) / kPackK);
+  const size_t smem = sizeof(float) * kPackK * (kPackR * taps + 1);
+  if (smem > 96 * 1024) return set_error(FVT_ERR_BAD_DESC, "filter has too many taps to pack (%d)", taps);
+  static bool attr_set_d[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set_d[dev]) {
+    cudaFuncSetAttribute(pack_weight_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set_d[dev] = true;
+  }
+  pack_weight_dgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, rows, taps, d->cin,
+                                                                      fwd_cin_real, fwd_cout_real);
+  return check_launch("pack_weight_dgrad_kernel");
 }
 
 int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
@@ -291,7 +470,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
 
   // ---- K1s: stride-1 'same' spatial convs with <= 128 input channels load each input row once (conv_slab.cuh)
   if (!g_disable_slab && d->kt == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && (d->kh > 1 || d->kw > 1) &&
-      2 * d->ph == d->kh - 1 && 2 * d->pw == d->kw - 1 && d->cin % 64 == 0 && d->cin <= 128 && d->w + 2 * d->pw <= 128) {
+      2 * d->ph == d->kh - 1 && 2 * d->pw == d->kw - 1 && d->cin <= 192 && d->w + 2 * d->pw <= 128) {
     SlabParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.frames = d->n * d->t; sp.h = d->h; sp.w = d->w; sp.wp = d->w + 2 * d->pw;
@@ -301,7 +480,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     sp.r_in = sp.r_out + d->kh - 1;
     sp.tiles_per_frame = (d->h + sp.r_out - 1) / sp.r_out;
     const double useful = (double)d->h * d->w / ((double)sp.tiles_per_frame * 128.0);
-    sp.cin_blocks = d->cin / 64; sp.cin_k16 = d->cin / 16;
+    sp.k_per_tap = d->cin; sp.cin_blocks = (d->cin + 63) / 64; sp.cin_k16 = d->cin / 16;   // a partial last block is zero-filled by TMA (channel OOB)
     sp.n_tile = bn; sp.num_n_tiles = rows / bn;
     const int slot_rows = (128 + (d->kh - 1) * sp.wp + d->kw - 1 + 7) / 8 * 8;
     sp.slab_slot_bytes = slot_rows * 128;
@@ -377,14 +556,24 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   p.y = (__nv_bfloat16*)y;
   p.stats = stats;
 
-  const int stage_bytes = kATileBytes + bn * kBlockK * 2;
+  const int b_tile_bytes = bn * kBlockK * 2;
+  int stage_bytes = kATileBytes + b_tile_bytes;
   const int kAuxBytes = 4096 + 2 * kMaxCout * 4;   // barriers + stats partials + staged scale/shift
   const int budget = 227 * 1024 - 1024 - kAuxBytes;
-  int stages = budget / stage_bytes;
+  // Small filters (one N tile, all taps*cin_blocks weight tiles + >= 4 A stages fit): keep the weights resident in
+  // shared memory for the CTA's lifetime instead of re-fetching them from L2 with every 128-pixel tile.
+  const int b_all_bytes = taps * p.cin_blocks * b_tile_bytes;
+  int b_region = 0;
+  if (!g_disable_bstat && p.num_n_tiles == 1 && p.num_m_tiles > di->sm_count && b_all_bytes + 4 * kATileBytes <= budget) {
+    p.b_stationary = 1;
+    b_region = b_all_bytes;
+    stage_bytes = kATileBytes;
+  }
+  int stages = (budget - b_region) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(FVT_ERR_BAD_DESC, "tile does not fit shared memory");
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * stage_bytes + kAuxBytes;
+  const int smem_bytes = 1024 + b_region + stages * stage_bytes + kAuxBytes;
 
   CUtensorMap tmx, tmw;
   if (int e = encode_x_map(di, d, x, &tmx)) return e;
@@ -415,6 +604,10 @@ int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, floa
   int st = 0;
   const DeviceInfo* di = current_device_info(&st);
   if (di == nullptr) return st;
+  {
+    const int r = try_wgrad_slab(di, d, x, dy, dw, cout_real, cin_real, (cudaStream_t)stream);
+    if (r != 0) return r < 0 ? r : 0;
+  }
   int to, ho, wo;
   conv_out_shape(d, &to, &ho, &wo);
 

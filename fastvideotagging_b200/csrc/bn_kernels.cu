@@ -110,15 +110,21 @@ bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, 
 // sums[0..C) += sum dz*xhat (dgamma), sums[C..2C) += sum dz (dbeta);  xhat = (raw - mean)*inv_std
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
-                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums,
-                     size_t rows, int cvec, int c_store) {
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
+                     float* __restrict__ sums, size_t rows, int cvec, int c_store) {
   extern __shared__ float sred[];                    // [blockDim.x][16] folded per channel vector
   const int tpr = blockDim.x / cvec;
   const int cv = threadIdx.x % cvec;
   const int rsub = threadIdx.x / cvec;
-  float dg[8], db[8], mu[8], is[8];
+  float dg[8], db[8], mu[8], is[8], rsc[8], rsh[8];
+  const bool self_mask = relu_scale != nullptr;       // ReLU mask recomputed from raw: [raw*scale + shift > 0]
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; mu[i] = mean[cv * 8 + i]; is[i] = invstd[cv * 8 + i]; }
+  for (int i = 0; i < 8; ++i) {
+    dg[i] = 0.f; db[i] = 0.f; mu[i] = mean[cv * 8 + i]; is[i] = invstd[cv * 8 + i];
+    rsc[i] = self_mask ? relu_scale[cv * 8 + i] : 0.f;
+    rsh[i] = self_mask ? relu_shift[cv * 8 + i] : 1.f;
+  }
   if (rsub < tpr) {
     for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
       const size_t idx = r * cvec + cv;
@@ -130,6 +136,9 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ da
         unpack8(__ldg(mask + idx), mk);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
+      } else if (self_mask) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -157,17 +166,21 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ da
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
                     const float* __restrict__ sums, uint4* __restrict__ draw, uint4* __restrict__ dz_out, size_t rows,
                     int cvec, int c_store, int c_real, float inv_rows) {
   const int tpr = blockDim.x / cvec;
   const int cv = threadIdx.x % cvec;
   const int rsub = threadIdx.x / cvec;
   if (rsub >= tpr) return;
-  float mu[8], is[8], a[8], bq[8], cq[8];
+  float mu[8], is[8], a[8], bq[8], cq[8], rsc[8], rsh[8];
+  const bool self_mask = relu_scale != nullptr;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int ch = cv * 8 + i;
     mu[i] = mean[ch]; is[i] = invstd[ch];
+    rsc[i] = self_mask ? relu_scale[ch] : 0.f;
+    rsh[i] = self_mask ? relu_shift[ch] : 1.f;
     const float g = ch < c_real ? gamma[ch] : 0.f;
     a[i] = g * is[i];
     bq[i] = sums[c_store + ch] * inv_rows;          // dbeta / M
@@ -183,6 +196,9 @@ bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dac
       unpack8(__ldg(mask + idx), mk);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
+    } else if (self_mask) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = a[i] * (g[i] - bq[i] - (x[i] - mu[i]) * is[i] * cq[i]);
@@ -322,8 +338,10 @@ int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const 
 }
 
 int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const float* mean, const float* invstd,
-                    const float* gamma, float* sums, void* draw, void* dz_out, int64_t rows, int32_t c_store,
-                    int32_t c_real, void* stream) {
+                    const float* gamma, const float* relu_scale, const float* relu_shift, float* sums, void* draw,
+                    void* dz_out, int64_t rows, int32_t c_store, int32_t c_real, void* stream) {
+  if ((relu_scale == nullptr) != (relu_shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "relu_scale/relu_shift must come together");
+  if (mask != nullptr && relu_scale != nullptr) return set_error(FVT_ERR_BAD_DESC, "give either a mask tensor or relu_scale/relu_shift");
   if (!raw || !dact || !mean || !invstd || !gamma || !sums || !draw) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   if (c_store <= 0 || c_store % 8 || rows <= 0 || c_real > c_store) return set_error(FVT_ERR_BAD_DESC, "bad bn_backward extent");
   int st = 0;
@@ -332,10 +350,12 @@ int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const f
   if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c_store, (cudaStream_t)stream);
   bn_bwd_reduce_kernel<<<blocks, threads, threads * 16 * sizeof(float), (cudaStream_t)stream>>>(
-      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, sums, rows, c_store / 8, c_store);
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, relu_scale, relu_shift, sums, rows, c_store / 8,
+      c_store);
   if (int e = check_launch("bn_bwd_reduce_kernel")) return e;
   bn_bwd_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, sums, (uint4*)draw, (uint4*)dz_out,
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, relu_scale, relu_shift, sums,
+      (uint4*)draw, (uint4*)dz_out,
       rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows));
   return check_launch("bn_bwd_apply_kernel");
 }

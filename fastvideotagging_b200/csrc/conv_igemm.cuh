@@ -45,6 +45,7 @@ struct ConvKernelParams {
   int cout_store;         // channel pitch of Y / residual (elements)
   int flags;
   int stages;
+  int b_stationary;       // 1: all taps*cin_blocks weight tiles are loaded once and stay in shared memory
   const float* scale;     // [cout_store] or nullptr (identity)
   const float* shift;     // [cout_store] or nullptr
   const __nv_bfloat16* residual;
@@ -64,15 +65,21 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const int b_tile_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = kATileBytes + b_tile_bytes;
+  const int taps = p.kt * p.kh * p.kw;
+  const int k_blocks = taps * p.cin_blocks;
+  // stationary weights: [k_blocks][block_n x 64] ahead of the A ring, whose stages then hold the A tile only
+  const int b_region_bytes = p.b_stationary ? k_blocks * b_tile_bytes : 0;
+  const int stage_bytes = p.b_stationary ? kATileBytes : kATileBytes + b_tile_bytes;
 
-  uint8_t* smem_tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint8_t* smem_b = smem;
+  uint8_t* smem_tiles = smem + b_region_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_tiles + stages * stage_bytes);
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + kMaxStages;         // [stages]
   uint64_t* acc_full_bar = bars + 2 * kMaxStages;  // [2]
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+  uint64_t* b_full_bar = acc_empty_bar + 2;        // [1] stationary weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full_bar + 2);   // keeps the float4 arrays below 16-byte aligned
   float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);   // [2][256] per-CTA channel partials
   float* affine_smem = stat_smem + 512;                          // [2][kMaxCout] scale, shift
 
@@ -89,6 +96,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       ptx::mbar_init(ptx::smem_u32(&acc_full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&acc_empty_bar[s]), 8);   // one arrive per epilogue warp
     }
+    ptx::mbar_init(ptx::smem_u32(b_full_bar), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -108,12 +116,21 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int taps = p.kt * p.kh * p.kw;
-  const int k_blocks = taps * p.cin_blocks;
 
   if (warp == 0) {
     // ===================================================== TMA producer (warp-uniform loop, elected lane issues)
     {
+      if (p.b_stationary && blockIdx.x < num_tiles) {
+        const uint32_t bb = ptx::smem_u32(b_full_bar);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bb, b_region_bytes);
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+            ptx::tma_load_2d(ptx::smem_u32(smem_b + kb * b_tile_bytes), &tmap_w, bb, tap * p.k_per_tap + cb * kBlockK, 0);
+          }
+        }
+        __syncwarp();
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -141,8 +158,9 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   ptx::tma_load_im2col_5d(ptx::smem_u32(a_dst), &tmap_x, fb, cb * kBlockK, cw, ch, cd, on,
                                           static_cast<uint16_t>(dw), static_cast<uint16_t>(dh),
                                           static_cast<uint16_t>(dt));
-                  ptx::tma_load_2d(ptx::smem_u32(a_dst + kATileBytes), &tmap_w, fb,
-                                   tap * p.k_per_tap + cb * kBlockK, n0);
+                  if (!p.b_stationary)
+                    ptx::tma_load_2d(ptx::smem_u32(a_dst + kATileBytes), &tmap_w, fb,
+                                     tap * p.k_per_tap + cb * kBlockK, n0);
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -163,6 +181,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.b_stationary && blockIdx.x < num_tiles) ptx::mbar_wait(ptx::smem_u32(b_full_bar), 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(ptx::smem_u32(&acc_empty_bar[acc]), acc_phase ^ 1);
         ptx::tc_fence_after();
@@ -175,7 +194,8 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem_tiles + stage * stage_bytes);
           const uint64_t a_desc = ptx::make_sw128_desc(a_addr, 16, 1024);
-          const uint64_t b_desc = ptx::make_sw128_desc(a_addr + kATileBytes, 16, 1024);
+          const uint64_t b_desc = ptx::make_sw128_desc(
+              p.b_stationary ? ptx::smem_u32(smem_b + kb * b_tile_bytes) : a_addr + kATileBytes, 16, 1024);
           if (ptx::elect_one()) {
             // +32 bytes (16 bf16) along K inside the swizzle atom == +2 in the (addr >> 4) field
             ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, kb != 0);

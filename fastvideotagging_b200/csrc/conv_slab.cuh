@@ -34,6 +34,7 @@ struct SlabParams {
   int r_out, r_in;         // output rows per tile, slab rows loaded per tile
   int tiles_per_frame;
   int cin_blocks, cin_k16; // 64-channel blocks / 16-channel MMA steps of the input
+  int k_per_tap;           // K elements per filter tap in the packed weights (= stored Cin)
   int n_tile, num_n_tiles;
   int slab_slot_bytes;     // per 64-channel block, multiple of 1024
   int slab_tx_bytes;       // bytes one slab TMA load delivers (wp * r_in * 128)
@@ -151,7 +152,8 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const uint32_t fb = ptx::smem_u32(&b_full[slot]);
             if (ptx::elect_one()) {
               ptx::mbar_arrive_expect_tx(fb, b_slab_bytes);
-              ptx::tma_load_2d(ptx::smem_u32(smem_b + slot * b_slab_bytes), &tmap_w, fb, j * 64, nt * p.n_tile);
+              const int tap = j / p.cin_blocks, cb = j - tap * p.cin_blocks;
+              ptx::tma_load_2d(ptx::smem_u32(smem_b + slot * b_slab_bytes), &tmap_w, fb, tap * p.k_per_tap + cb * 64, nt * p.n_tile);
             }
             __syncwarp();
             if (++slot == p.b_ring) { slot = 0; phase ^= 1; }

@@ -1,0 +1,204 @@
+// K3s — "slab" weight gradient for stride-1 'same' spatial convolutions (1 x kh x kw), the layers that carry two thirds
+// of the weight-gradient FLOPs of R(2+1)D:
+//
+//     dW[co, ci, tap] += sum over output positions p of  dY[p, co] * X[p + shift(tap), ci]
+//
+// K3 (conv_wgrad.cuh) fetches one im2col slab of X per filter tap and owns one 128-row accumulator, so it re-reads X
+// kh*kw times and dY once per M tile from L2 (measured 7x off the tensor roofline on conv2_x).  Here a CTA
+//   * loads, per pixel tile, each X slab ONCE as R_in whole zero-padded image rows (tiled TMA, halo by OOB fill — the
+//     same geometry as the forward slab kernel, conv_slab.cuh) plus the matching dY tile in padded-row indexing
+//     (box [64 ch, W+2pw, R_out]: the 2pw junk columns and rows beyond H come back as zeros, so they add nothing);
+//   * treats both as MN-major UMMA operands (GEMM-K = positions).  A filter tap is the SAME slab addressed through a
+//     descriptor shifted by (dh*(W+2pw)+dw) rows, and ONE M=128 instruction covers TWO (tap, 64-channel) groups: the
+//     descriptor's leading-dimension byte offset is simply the distance between the two shifted views
+//     (tools/experiments/mn_stack.cu verifies this on hardware);
+//   * keeps up to 512 TMEM columns of fp32 accumulators (several 128-row M tiles x one N tile) for its whole pixel
+//     range, so X and dY are read once per CTA and the epilogue runs once: atomics into the fp32 (O, I, kT, kH, kW)
+//     gradient (pixel splits of the same block meet there).
+//
+// Warp roles (192 threads): warp0 TMA producer, warp1 MMA issuer (+ TMEM alloc), warps 2-5 epilogue.
+// Replaces cuDNN backward-filter for the Conv3D(1,3,3) layers at reference model/R2Plus1.py:27-31, net.py:40-42.
+#pragma once
+#include "ptx.cuh"
+#include "conv_slab.cuh"
+
+namespace fvt {
+
+constexpr int kWgsThreads = 192;
+constexpr int kWgsMaxStages = 4;
+constexpr int kWgsMaxMt = 5;            // 128-row accumulator tiles per CTA
+
+struct WgradSlabParams {
+  int frames, h, w, wp;
+  int ph, pw, kh, kw;
+  int r_out, r_in, tiles_per_frame, num_tiles;
+  int ksteps;                 // 16-position MMA steps per pixel tile (= ceil(r_out*wp / 16))
+  int taps, cin_blocks, groups;   // groups = cin_blocks * taps, ordered cb-major: g = cb*taps + tap
+  int mt_per_cta, m_chunks;
+  int n_tile, n_tiles, n_blocks, acc_stride;
+  int ncb_max;                // X slabs per stage
+  int slab_slot_bytes, slab_tx_bytes, dy_tx_bytes;
+  int stage_bytes, stages;
+  int splits, tiles_per_split;
+  int cin_real, cout_real;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(kWgsThreads, 1)
+conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                       const WgradSlabParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+
+  uint8_t* aux = smem + p.stages * p.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);          // [kWgsMaxStages]
+  uint64_t* empty_bar = full_bar + kWgsMaxStages;
+  uint64_t* acc_bar = empty_bar + kWgsMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  // ---- work item: (pixel split, M chunk, N tile)
+  int item = blockIdx.x;
+  const int nt = item % p.n_tiles;     item /= p.n_tiles;
+  const int chunk = item % p.m_chunks; item /= p.m_chunks;
+  const int split = item;
+  const int g_lo = chunk * 2 * p.mt_per_cta;
+  int g_hi = g_lo + 2 * p.mt_per_cta;
+  if (g_hi > p.groups) g_hi = p.groups;
+  const int mt_count = (g_hi - g_lo + 1) >> 1;
+  const int cb_lo = g_lo / p.taps;
+  const int cb_hi = (g_hi - 1) / p.taps;
+  const int ncb = cb_hi - cb_lo + 1;
+  const int tile0 = split * p.tiles_per_split;
+  int tile1 = tile0 + p.tiles_per_split;
+  if (tile1 > p.num_tiles) tile1 = p.num_tiles;
+
+  // Zero the operand stages once: TMA only ever writes the boxes, so the slab tails (rows past R_in*Wp that shifted
+  // taps reach) and the dY rows past R_out*Wp stay zero and contribute nothing (stale NaN bit patterns would).
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = p.stages * p.stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += kWgsThreads) z[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_x);
+    ptx::prefetch_tensormap(&tmap_dy);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(acc_bar), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int dy_off = p.ncb_max * p.slab_slot_bytes;      // dY blocks follow the X slabs inside a stage
+
+  if (warp == 0) {
+    // ===================================================== producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx = ncb * p.slab_tx_bytes + p.n_blocks * p.dy_tx_bytes;
+    for (int tile = tile0; tile < tile1; ++tile) {
+      const int frame = tile / p.tiles_per_frame;
+      const int h0 = (tile - frame * p.tiles_per_frame) * p.r_out;
+      ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+      const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+      const uint32_t base = ptx::smem_u32(smem + stage * p.stage_bytes);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(fb, tx);
+        for (int c = 0; c < ncb; ++c)
+          tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, -p.pw, h0 - p.ph, frame);
+        for (int j = 0; j < p.n_blocks; ++j)
+          tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, 0, h0, frame);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (warp-uniform control flow, elected lane issues)
+    const uint32_t idesc = ptx::make_idesc_bf16(128, p.n_tile, 1, 1);
+    // per M tile: byte offset of its first group inside a stage and the distance to its second group
+    uint32_t a_off[kWgsMaxMt], a_lbo[kWgsMaxMt];
+#pragma unroll
+    for (int i = 0; i < kWgsMaxMt; ++i) {
+      a_off[i] = 0; a_lbo[i] = 0;
+      if (i < mt_count) {
+        const int ga = g_lo + 2 * i;
+        const int gb = ga + 1 < g_hi ? ga + 1 : ga;          // odd tail: second half duplicates the first, ignored later
+        const int cba = ga / p.taps, tapa = ga - cba * p.taps;
+        const int cbb = gb / p.taps, tapb = gb - cbb * p.taps;
+        const uint32_t oa = (cba - cb_lo) * p.slab_slot_bytes + ((tapa / p.kw) * p.wp + tapa % p.kw) * 128;
+        const uint32_t ob = (cbb - cb_lo) * p.slab_slot_bytes + ((tapb / p.kw) * p.wp + tapb % p.kw) * 128;
+        a_off[i] = oa;
+        a_lbo[i] = ob - oa;
+      }
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < tile1; ++tile) {
+      ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+      ptx::tc_fence_after();
+      const uint32_t base = ptx::smem_u32(smem + stage * p.stage_bytes);
+      const uint64_t b_desc = ptx::make_sw128_desc(base + dy_off, 128 * 128, 1024);
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int i = 0; i < kWgsMaxMt; ++i) {
+          if (i < mt_count) {
+            const uint64_t a_desc = ptx::make_sw128_desc(base + a_off[i], a_lbo[i], 1024);
+            const uint32_t d_tmem = tmem_base + i * p.acc_stride;
+            for (int ks = 0; ks < p.ksteps; ++ks)      // 16 positions = 2048 B along K -> +128 in the (addr >> 4) field
+              ptx::umma_bf16_ss(d_tmem, a_desc + 128 * ks, b_desc + 128 * ks, idesc, (tile > tile0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(acc_bar));
+    __syncwarp();
+  } else if (tile1 > tile0) {
+    // ===================================================== epilogue (warps 2-5 own TMEM lane quadrants warp % 4)
+    const int q = warp & 3;
+    ptx::mbar_wait(ptx::smem_u32(acc_bar), 0);
+    ptx::tc_fence_after();
+    const int r = q * 32 + lane;
+    for (int i = 0; i < mt_count; ++i) {
+      const int g = g_lo + 2 * i + (r >> 6);
+      const int cb = g / p.taps, tap = g - cb * p.taps;
+      const int ci = cb * 64 + (r & 63);
+      const bool row_ok = g < g_hi && ci < p.cin_real;
+      const uint32_t taddr = tmem_base + i * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c = 0; c < p.n_tile; c += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(taddr + c, v);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = nt * p.n_tile + c + j;
+            if (co < p.cout_real)
+              atomicAdd(p.dw + (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fvt

@@ -8,6 +8,8 @@ The layer list is generated here from the same formulas the reference uses (mid-
 parameter names are the symbol-API names (net.py:42-51,80,96-98,123-132,166) that the reference's own
 `load_from_sym_params` (model/R2Plus1.py:256-279) maps Gluon parameters onto.
 """
+import os
+
 import torch
 
 from . import ops
@@ -305,7 +307,7 @@ class TrainPlan:
             L.src = src_name
             L.raw = buf(spec.name + ":raw", L.out_shape)
             L.act = buf(spec.name + ":act", L.out_shape)
-            L.stats = buf(spec.name + ":stats", (2 * L.cout_s,), torch.float32)
+            L.stats = None                     # view of self.stats_all, assigned once every layer is known
             for nm in ("scale", "shift", "mean", "invstd"):
                 setattr(L, nm, buf(spec.name + ":" + nm, (L.cout_s,), torch.float32))
             L.wp = L.wpd = L.w_eq = None
@@ -333,6 +335,12 @@ class TrainPlan:
             for L in (a, b, c, d):
                 max_elems = max(max_elems, L.raw.numel(), L.in_shape[0] * L.in_shape[1] * L.in_shape[2] * L.in_shape[3] * L.in_shape[4])
         self.final_name, self.final_shape = cur_name, cur_shape
+        # per-channel (sum, sum^2) accumulators of every conv in ONE buffer: a single memset per step
+        self.stats_all = torch.zeros(sum(2 * L.cout_s for L in self.layers.values()), dtype=torch.float32, device=device)
+        off = 0
+        for L in self.layers.values():
+            L.stats = self.stats_all[off:off + 2 * L.cout_s]
+            off += 2 * L.cout_s
         tp, hp, wp = cur_shape[1] - pool[0] + 1, cur_shape[2] - pool[1] + 1, cur_shape[3] - pool[2] + 1
         if (tp, hp, wp) != (1, 1, 1):
             raise ValueError("AvgPool3D%s over a %s map leaves %s: only a global pool is supported" % (pool, cur_shape[1:4], (tp, hp, wp)))
@@ -347,6 +355,15 @@ class TrainPlan:
         buf("up", (up_elems,))
         self.pooled = None
         self.launches_fwd = self.launches_bwd = 0
+        # CUDA graphs: the ~700 launches of a step are captured once (forward graph, backward graph) and replayed, so
+        # the step is not paced by Python/ctypes launch overhead.  FVT_CUDA_GRAPHS=0 runs every launch eagerly.
+        self.use_graphs = os.environ.get("FVT_CUDA_GRAPHS", "1") != "0"
+        self.x_static = torch.empty((n, 3, t, h, w), dtype=torch.float32, device=device)
+        self.dlogits_static = torch.empty((n, num_class), dtype=torch.float32, device=device)
+        self._fwd_graph = self._bwd_graph = None
+        self._logits_static = None
+        self._warm_fwd = self._warm_bwd = 0
+        self.finish_hook = None          # callable(): wait for gradient reductions launched by grad_hook
 
     # ------------------------------------------------------------------ weights
     def _w(self, L):
@@ -360,9 +377,9 @@ class TrainPlan:
             w = self._w(L)
             if L is self.stem0:
                 w = stem_equivalent_weight(w)
-            L.wp = ops.pack_conv_weight(L.fwd, w)
+            L.wp = ops.pack_conv_weight(L.fwd, w, out=L.wp)               # packed buffers are allocated once
             if L.need_dgrad:
-                L.wpd = ops.pack_conv_weight_dgrad(L.dgr, w)
+                L.wpd = ops.pack_conv_weight_dgrad(L.dgr, w, out=L.wpd)
         self.weights_version = version
 
     # ------------------------------------------------------------------ forward
@@ -371,15 +388,39 @@ class TrainPlan:
 
     def _conv_bn(self, L, src):
         gname, bname, mname, vname = self._bn_names(L)
-        L.stats.zero_()
         ops.conv3d_fwd(L.fwd, src, L.wp, out=L.raw, stats=L.stats)
         ops.bn_finalize(L.stats, self.flat.view(self.flat.w, gname), self.flat.view(self.flat.w, bname),
                         self.aux[mname], self.aux[vname], L.cout_s, L.rows, self.eps, self.momentum,
                         L.scale, L.shift, L.mean, L.invstd)
 
-    def forward(self, x):
+    def forward(self, x, weights_version):
+        """Training-mode forward: re-pack bf16 operand copies if the weights changed, zero the gradient buffer
+        (grad_req='write'), run the network.  Returns fp32 logits (N, num_class)."""
         assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w)
-        ops.stem_unfold(x.contiguous(), out=self.unfold)
+        if not self.use_graphs:
+            self.refresh_weights(weights_version)
+            self.flat.g.zero_()
+            return self._forward_body(x.contiguous())
+        self.x_static.copy_(x)
+        if self._fwd_graph is None:
+            if self._warm_fwd < 1:                      # first call: eager (one-time initialisation inside the library)
+                self._warm_fwd += 1
+                self.refresh_weights(weights_version)
+                self.flat.g.zero_()
+                return self._forward_body(self.x_static)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.weights_version = -1               # the graph always re-packs: weights change every step
+                self.refresh_weights(0)
+                self.flat.g.zero_()
+                self._logits_static = self._forward_body(self.x_static)
+            self._fwd_graph = graph
+        self._fwd_graph.replay()
+        return self._logits_static.clone()
+
+    def _forward_body(self, x):
+        self.stats_all.zero_()
+        ops.stem_unfold(x, out=self.unfold)
         B = self.bufs
         for L in (self.stem0, self.stem1):
             self._conv_bn(L, B[L.src])
@@ -419,7 +460,11 @@ class TrainPlan:
         off_g, off_b = self.flat.slots[gname][0], self.flat.slots[bname][0]
         assert off_b == off_g + L.cout_s, "gamma/beta slots must be adjacent"
         sums2 = self.flat.g[off_g:off_g + 2 * L.cout_s]
-        ops.bn_backward(L.raw, dact, mask, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, dz_out)
+        if mask is True:          # ReLU directly after this BatchNorm: recompute the mask from raw (one read less)
+            ops.bn_backward(L.raw, dact, None, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, dz_out,
+                            relu_scale=L.scale, relu_shift=L.shift)
+        else:
+            ops.bn_backward(L.raw, dact, mask, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, dz_out)
 
     def _wgrad(self, L, x_in, draw):
         if L is self.stem0:
@@ -442,12 +487,28 @@ class TrainPlan:
         return out
 
     def backward(self, dlogits):
-        """dlogits: (N, num_class) fp32.  Accumulates into flat.g (zeroed by the caller at step start)."""
+        """dlogits: (N, num_class) fp32.  Accumulates into flat.g (zeroed by forward())."""
+        if not self.use_graphs:
+            return self._backward_body(dlogits.contiguous())
+        self.dlogits_static.copy_(dlogits)
+        if self._bwd_graph is None:
+            if self._warm_bwd < 1:
+                self._warm_bwd += 1
+                return self._backward_body(self.dlogits_static)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._backward_body(self.dlogits_static)
+                if self.finish_hook is not None:        # gradient all-reduces launched during capture join here
+                    self.finish_hook()
+            self._bwd_graph = graph
+        self._bwd_graph.replay()
+
+    def _backward_body(self, dlogits):
         B = self.bufs
         fl = self.flat
         final = B[self.final_name]
         g_cur = self._view("gA", self.final_shape)
-        ops.pool_fc_bwd(dlogits.contiguous(), self.pooled, fl.view(fl.w, "final_fc_weight"), fl.view(fl.g, "final_fc_weight"),
+        ops.pool_fc_bwd(dlogits, self.pooled, fl.view(fl.w, "final_fc_weight"), fl.view(fl.g, "final_fc_weight"),
                         fl.view(fl.g, "final_fc_bias"), g_cur)
         self._ready("final_fc_weight", "final_fc_bias")
         cur_key = "gA"
@@ -467,15 +528,15 @@ class TrainPlan:
             self._wgrad(d, c.act, draw_d)
             gc = self._dgrad(d, draw_d, self._view(other, c.out_shape))
             draw_c = self._view("draw", c.out_shape)
-            self._bn_bwd(c, gc, c.act, draw_c)
+            self._bn_bwd(c, gc, True, draw_c)
             self._wgrad(c, b.act, draw_c)
             gb = self._dgrad(c, draw_c, self._view(cur_key, b.out_shape))
             draw_b = self._view("draw", b.out_shape)
-            self._bn_bwd(b, gb, b.act, draw_b)
+            self._bn_bwd(b, gb, True, draw_b)
             self._wgrad(b, a.act, draw_b)
             ga = self._dgrad(b, draw_b, self._view(other, a.out_shape))
             draw_a = self._view("draw", a.out_shape)
-            self._bn_bwd(a, ga, a.act, draw_a)
+            self._bn_bwd(a, ga, True, draw_a)
             self._wgrad(a, xin, draw_a)
             g_cur = self._dgrad(a, draw_a, self._view(cur_key, xin_shape), residual=gshort)
             names = []
@@ -485,11 +546,11 @@ class TrainPlan:
         # stem
         other = "gB" if cur_key == "gA" else "gA"
         draw1 = self._view("draw", self.stem1.out_shape)
-        self._bn_bwd(self.stem1, g_cur, self.stem1.act, draw1)
+        self._bn_bwd(self.stem1, g_cur, True, draw1)
         self._wgrad(self.stem1, self.stem0.act, draw1)
         g0 = self._dgrad(self.stem1, draw1, self._view(other, self.stem0.out_shape))
         draw0 = self._view("draw", self.stem0.out_shape)
-        self._bn_bwd(self.stem0, g0, self.stem0.act, draw0)
+        self._bn_bwd(self.stem0, g0, True, draw0)
         self._wgrad(self.stem0, self.unfold, draw0)
         names = []
         for L in (self.stem0, self.stem1):

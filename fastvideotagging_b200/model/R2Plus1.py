@@ -40,10 +40,8 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, net, anchor):
         plan = net._train_plan(x)
-        plan.refresh_weights(net._weights_version)
-        net._flat.g.zero_()                      # grad_req='write': every backward overwrites
         ctx.plan = plan
-        return plan.forward(x)
+        return plan.forward(x, net._weights_version)      # also zeroes the gradient buffer (grad_req='write')
 
     @staticmethod
     def backward(ctx, dlogits):
@@ -198,6 +196,7 @@ class R2Plus2D(torch.nn.Module):
         self._trainer = trainer
         for plan in self._train_plans.values():
             plan.grad_hook = trainer.on_grads_ready
+            plan.finish_hook = trainer.allreduce_grads
 
     def _ensure_flat(self, device):
         """Move every trainable tensor into one flat fp32 buffer (engine.FlatParams); the nn.Parameters become views
@@ -231,6 +230,7 @@ class R2Plus2D(torch.nn.Module):
                                     x.device, momentum=self.bn_momentum)
             if self._trainer is not None:
                 plan.grad_hook = self._trainer.on_grads_ready
+                plan.finish_hook = self._trainer.allreduce_grads
             self._train_plans[key] = plan
         return plan
 

@@ -36,7 +36,7 @@ def conv_out_shape(desc):
     return a.value, b.value, c.value
 
 
-def pack_conv_weight(desc, w_oidhw):
+def pack_conv_weight(desc, w_oidhw, out=None):
     """fp32 (O, I, kT, kH, kW) device tensor -> packed bf16 weights for `desc` (zero padded)."""
     lib = _lib.load()
     require_cuda(w_oidhw, "weight")
@@ -44,7 +44,9 @@ def pack_conv_weight(desc, w_oidhw):
     elems = lib.fvt_conv3d_packed_weight_elems(ctypes.byref(desc))
     if elems == 0:
         check(-1)
-    out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
+    if out is None:
+        out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
+    assert out.numel() == elems and out.dtype == torch.bfloat16
     check(lib.fvt_pack_conv_weight(ctypes.byref(desc), _ptr(w), w.shape[0], w.shape[1], _ptr(out), _stream()))
     return out
 
@@ -101,11 +103,13 @@ def dgrad_desc(fwd, block_n=0, flags=0):
                     fwd.kt - 1 - fwd.pt, fwd.kh - 1 - fwd.ph, fwd.kw - 1 - fwd.pw, flags, block_n)
 
 
-def pack_conv_weight_dgrad(ddesc, w_oidhw):
+def pack_conv_weight_dgrad(ddesc, w_oidhw, out=None):
     lib = _lib.load()
     w = w_oidhw.detach().to(torch.float32).contiguous()
     elems = lib.fvt_conv3d_packed_weight_elems(ctypes.byref(ddesc))
-    out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
+    if out is None:
+        out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
+    assert out.numel() == elems and out.dtype == torch.bfloat16
     check(lib.fvt_pack_conv_weight_dgrad(ctypes.byref(ddesc), _ptr(w), w.shape[0], w.shape[1], _ptr(out), _stream()))
     return out
 
@@ -143,12 +147,15 @@ def bn_apply(raw, scale, shift, out, relu, res=None, res_scale=None, res_shift=N
     return out
 
 
-def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None):
+def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None, relu_scale=None, relu_shift=None):
+    """mask: tensor whose sign gates the gradient (ReLU after a residual add), or None; relu_scale/relu_shift: the
+    forward scale/shift of this BatchNorm when the ReLU follows it directly (mask recomputed from raw)."""
     lib = _lib.load()
     c = raw.shape[-1]
     rows = raw.numel() // c
-    check(lib.fvt_bn_backward(_ptr(raw), _ptr(dact), _ptr(mask), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums),
-                              _ptr(draw), _ptr(dz_out), rows, c, gamma.numel(), _stream()))
+    check(lib.fvt_bn_backward(_ptr(raw), _ptr(dact), _ptr(mask), _ptr(mean), _ptr(invstd), _ptr(gamma),
+                              _ptr(relu_scale), _ptr(relu_shift), _ptr(sums), _ptr(draw), _ptr(dz_out), rows, c,
+                              gamma.numel(), _stream()))
     return draw
 
 

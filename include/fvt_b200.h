@@ -56,7 +56,9 @@ int fvt_version(void);
 const char* fvt_last_error(void);
 /* 0 if `device` is an sm_100 part and the driver exposes the tensor-map encoders, else a negative status. */
 int fvt_device_check(int device);
-/* Tuning/debug switches. "disable_slab" = 1 routes every convolution through the generic im2col kernel (K1). */
+/* Tuning/debug switches (A/B runs and tests): "disable_slab" = 1 routes every convolution through the generic im2col
+ * kernel (K1); "disable_b_stationary" = 1 makes K1 stream its weights; "disable_wgrad_slab" = 1 routes every weight
+ * gradient through the im2col kernel (K3). */
 int fvt_set_option(const char* name, int value);
 
 /* ---- convolution (K1) ----------------------------------------------------------------------------------- */
@@ -116,11 +118,15 @@ int fvt_bn_finalize(const float* stats, const float* gamma, const float* beta, f
 /* out = relu?( raw*scale + shift [+ res | + res*res_scale + res_shift] ), [rows, c_store] bf16. */
 int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const void* res, const float* res_scale,
                  const float* res_shift, void* out, int64_t rows, int32_t c_store, int32_t relu, void* stream);
-/* dz = dact * [mask > 0] (mask == NULL: dz = dact);  sums = [dgamma(c_store), dbeta(c_store)] (overwritten);
+/* dz = dact * [mask > 0]  (mask tensor given: the ReLU sits after a residual add, R2Plus1.py:81),
+ *    = dact * [raw*relu_scale + relu_shift > 0]  (relu_scale/relu_shift = the forward scale/shift of this BatchNorm:
+ *      the ReLU directly follows it, R2Plus1.py:33,60 — the mask is recomputed from raw, saving one tensor read),
+ *    = dact  (neither given);
+ * sums = [dgamma(c_store), dbeta(c_store)] (overwritten);
  * draw = gamma*inv_std*(dz - dbeta/rows - xhat*dgamma/rows);  dz_out (optional) receives dz. */
 int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const float* mean, const float* invstd,
-                    const float* gamma, float* sums, void* draw, void* dz_out, int64_t rows, int32_t c_store,
-                    int32_t c_real, void* stream);
+                    const float* gamma, const float* relu_scale, const float* relu_shift, float* sums, void* draw,
+                    void* dz_out, int64_t rows, int32_t c_store, int32_t c_real, void* stream);
 
 /* ---- training: head backward, optimiser ----------------------------------------------------------------------- */
 /* dw[k,c] += sum_n dlogits[n,k]*pooled[n,c]; db[k] += sum_n dlogits[n,k]; dx[n,p,c] = (dlogits[n,:] . w[:,c]) / positions. */

@@ -17,7 +17,7 @@ def _probe_train():
     return gpu_probe_train
 
 
-@pytest.mark.parametrize("idx", range(16))
+@pytest.mark.parametrize("idx", range(19))
 def test_conv_forward_shapes(cuda_device, idx):
     m = _probe_conv()
     assert m.run_case(*m.CASES[idx])
@@ -54,7 +54,48 @@ def test_slab_and_im2col_kernels_agree(cuda_device, lib):
     assert diff <= 2 ** -7 * y_gen.float().abs().max().item()
 
 
-@pytest.mark.parametrize("idx", range(12))
+def test_stationary_and_streamed_weights_agree(cuda_device, lib):
+    """K1 with the filter resident in shared memory vs. streamed per tile: same MMAs in the same order -> bit-identical."""
+    import torch
+    from fastvideotagging_b200 import ops
+    torch.manual_seed(4)
+    x = (torch.randn(2, 8, 56, 56, 144) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = torch.randn(64, 144, 3, 1, 1, device=cuda_device) / 20.0
+    d = ops.conv_desc(2, 8, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU)
+    wp = ops.pack_conv_weight(d, w)
+    y_stat = ops.conv3d_fwd(d, x, wp)
+    assert lib.fvt_set_option(b"disable_b_stationary", 1) == 0
+    try:
+        y_str = ops.conv3d_fwd(d, x, wp)
+    finally:
+        lib.fvt_set_option(b"disable_b_stationary", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(y_stat, y_str)
+
+
+def test_wgrad_slab_and_im2col_kernels_agree(cuda_device, lib):
+    """K3s (slab, stacked taps) and K3 (im2col) compute the same weight gradient up to fp32 summation order."""
+    import torch
+    from fastvideotagging_b200 import ops
+    torch.manual_seed(5)
+    for (n, t, h, w_, cin, cout) in ((2, 4, 56, 56, 64, 144), (2, 4, 28, 28, 128, 288), (1, 2, 7, 7, 512, 1152)):
+        x = (torch.randn(n, t, h, w_, cin) * 0.5).to(torch.bfloat16).to(cuda_device)
+        dy = (torch.randn(n, t, h, w_, cout) * 0.5).to(torch.bfloat16).to(cuda_device)
+        d = ops.conv_desc(n, t, h, w_, cin, cout, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+        dw_slab = torch.zeros(cout, cin, 1, 3, 3, device=cuda_device)
+        ops.conv3d_wgrad(d, x, dy, dw_slab, cout, cin)
+        assert lib.fvt_set_option(b"disable_wgrad_slab", 1) == 0
+        try:
+            dw_gen = torch.zeros_like(dw_slab)
+            ops.conv3d_wgrad(d, x, dy, dw_gen, cout, cin)
+        finally:
+            lib.fvt_set_option(b"disable_wgrad_slab", 0)
+        torch.cuda.synchronize()
+        scale = dw_gen.abs().max().item()
+        assert (dw_slab - dw_gen).abs().max().item() <= 2e-4 * scale + 1e-4, (h, cin, cout)
+
+
+@pytest.mark.parametrize("idx", range(16))
 def test_conv_wgrad_dgrad(cuda_device, idx):
     m = _probe_train()
     assert m.conv_case(*m.CONV_CASES[idx])

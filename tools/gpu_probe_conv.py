@@ -91,6 +91,9 @@ CASES = [
     ("1x3x3 64->144 56x56 slab", 2, 8, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ("1x3x3 128->288 28x28 slab", 2, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ("1x3x3 64->64 odd 13x9", 1, 3, 13, 9, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 144->64 56x56 slab", 2, 4, 56, 56, 144, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 176->96 28x28 slab", 1, 4, 28, 28, 176, 96, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("3x1x1 144->64 56x56 B-stat", 2, 8, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
 ]
 def main():
     print("device", torch.cuda.get_device_name(0), "check", _lib.load().fvt_device_check(0), flush=True)

@@ -58,6 +58,10 @@ CONV_CASES = [
     ("stem-eq 1x7x1 21->45", 1, 2, 56, 28, 21, 45, (1, 7, 1), (1, 2, 1), (0, 3, 0)),
     ("3x1x1 45->64 stem", 1, 4, 28, 28, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
     ("1x3x3 64->144 big", 4, 8, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 128->288 28x28", 2, 4, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 256->576 14x14", 2, 4, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 64->64 odd 13x9", 1, 3, 13, 9, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("1x3x3 192->80 odd 11x17", 2, 2, 11, 17, 192, 80, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
 ]
 # ---- BatchNorm forward (stats from K1 epilogue -> finalize -> apply) and backward
 def bn_case(rows_shape, c, relu, with_mask):
@@ -97,6 +101,18 @@ def bn_case(rows_shape, c, relu, with_mask):
     e3 = np.abs(dxa - dx).max() / (np.abs(dx).max() + 1e-9)
     e4 = max(np.abs(sums[:c].cpu().numpy() - dg).max() / (np.abs(dg).max() + 1e-9), np.abs(sums[cs:cs + c].cpu().numpy() - db).max() / (np.abs(db).max() + 1e-9))
     ok = e1 < 3e-2 and e2 < 1e-4 and e3 < 1.5e-2 and e4 < 2e-3
+    if with_mask and relu:
+        # the ReLU directly follows this BatchNorm: mask recomputed from raw must give the same result as mask = act
+        sums_b = torch.empty(2 * cs, device=dev); draw_b = torch.empty_like(rawd)
+        ops.bn_backward(rawd, dact.to(dev), None, mean_d, inv_d, gd, sums_b, draw_b, relu_scale=scale, relu_shift=shift)
+        torch.cuda.synchronize()
+        # (cross-CTA atomics make the channel sums order-dependent in the last bits, so compare with a tolerance)
+        dsum = (sums_b - sums).abs().max().item() / (sums.abs().max().item() + 1e-9)
+        ddraw = (draw_b.float() - draw.float()).abs().max().item() / (draw.float().abs().max().item() + 1e-9)
+        same = dsum < 1e-5 and ddraw < 2 ** -7
+        if not same:
+            print("   self-mask variant differs from mask=act: sums rel %.3g draw rel %.3g" % (dsum, ddraw))
+        ok = ok and same
     print("bn rows=%d c=%d relu=%d mask=%d: apply err %.4f running err %.2e dx rel %.4f dgamma/dbeta rel %.2e %s" % (rows, c, relu, with_mask, e1, e2, e3, e4, "OK" if ok else "FAIL"), flush=True)
     STATE["ok"] &= bool(ok)
     return bool(ok)
