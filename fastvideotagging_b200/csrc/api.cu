@@ -13,6 +13,7 @@
 #include "conv_wgrad.cuh"
 #include "conv_slab.cuh"
 #include "conv_wgrad_slab.cuh"
+#include "conv_frame_ring.cuh"
 #include "host_common.h"
 
 namespace fvt {
@@ -48,6 +49,11 @@ struct DeviceInfo {
 static DeviceInfo g_dev[16];
 static int g_disable_bstat = 0;  // fvt_set_option("disable_b_stationary", 1): K1 always streams the weights
 static int g_disable_wgrad_slab = 0;   // fvt_set_option("disable_wgrad_slab", 1): K3 (im2col) for every weight gradient
+static int g_debug_flags = 0;    // fvt_set_option("debug_flags", bits): OR-ed into the conv kernels' flags (experiments)
+static int g_slab_box_rows = 0;  // fvt_set_option("slab_box_rows", r): rows per slab TMA box (0 = whole slab in one box)
+static int g_slab_prefetch = 2;  // fvt_set_option("slab_prefetch", d): L2 prefetch distance in tiles (0 = off)
+static int g_ring_prefetch = 4;  // fvt_set_option("ring_prefetch", f): K1t L2 prefetch distance in frames (0 = off)
+static int g_disable_ring = 0;   // fvt_set_option("disable_frame_ring", 1): temporal convs go through K1 (im2col)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -367,6 +373,11 @@ int fvt_version(void) { return 101; }
 int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
+  if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
+  if (name != nullptr && strcmp(name, "disable_frame_ring") == 0) { g_disable_ring = value; return 0; }
+  if (name != nullptr && strcmp(name, "slab_box_rows") == 0) { g_slab_box_rows = value; return 0; }
+  if (name != nullptr && strcmp(name, "slab_prefetch") == 0) { g_slab_prefetch = value; return 0; }
+  if (name != nullptr && strcmp(name, "debug_flags") == 0) { g_debug_flags = value & (kDbgNoStore | kDbgNoEpilogue); return 0; }
   if (name != nullptr && strcmp(name, "disable_wgrad_slab") == 0) { g_disable_wgrad_slab = value; return 0; }
   return set_error(FVT_ERR_BAD_DESC, "unknown option");
 }
@@ -456,8 +467,8 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   if ((scale == nullptr) != (shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "scale and shift must be given together");
   if ((d->flags & FVT_CONV_RESIDUAL) && residual == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_RESIDUAL without a residual tensor");
   if ((d->flags & FVT_CONV_STATS) && stats == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_STATS without a stats buffer");
-  if (((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)y | (uintptr_t)residual) & 15)
-    return set_error(FVT_ERR_MISALIGNED, "tensor pointers must be 16-byte aligned");
+  if (((uintptr_t)x | (uintptr_t)w_packed) & 15) return set_error(FVT_ERR_MISALIGNED, "x / w_packed must be 16-byte aligned");
+  if (((uintptr_t)y | (uintptr_t)residual) & 31) return set_error(FVT_ERR_MISALIGNED, "y / residual must be 32-byte aligned (256-bit epilogue accesses)");
   int st = 0;
   const DeviceInfo* di = current_device_info(&st);
   if (di == nullptr) return st;
@@ -507,14 +518,17 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       if (sp.stages > kSlabMaxStages) sp.stages = kSlabMaxStages;
     }
     if (ok) {
-      sp.cout_store = d->cout; sp.flags = d->flags;
+      sp.cout_store = d->cout; sp.flags = d->flags | g_debug_flags;
       sp.scale = scale; sp.shift = shift; sp.residual = (const __nv_bfloat16*)residual;
       sp.y = (__nv_bfloat16*)y; sp.stats = stats;
       const int smem_bytes = sp.b_ring * b_slab + sp.stages * stage_bytes + aux;
       CUtensorMap tmx, tmw;
       const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)sp.frames};
       const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w, (cuuint64_t)d->cin * 2 * d->w * d->h};
-      const cuuint32_t box[4] = {64, (cuuint32_t)sp.wp, (cuuint32_t)sp.r_in, 1};
+      sp.box_rows = sp.r_in;
+      if (g_slab_box_rows > 0 && g_slab_box_rows < sp.r_in && sp.r_in % g_slab_box_rows == 0) sp.box_rows = g_slab_box_rows;
+      sp.prefetch_dist = g_slab_prefetch > 0 ? g_slab_prefetch : 0;
+      const cuuint32_t box[4] = {64, (cuuint32_t)sp.wp, (cuuint32_t)sp.box_rows, 1};
       const cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -536,6 +550,64 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     }
   }
 
+  // ---- K1t: stride-1 temporal convs whose whole filter fits in shared memory walk a 128-pixel block through time and
+  //      load every input frame block once (conv_frame_ring.cuh)
+  if (!g_disable_ring && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 &&
+      d->ph == 0 && d->pw == 0 && 2 * d->pt == d->kt - 1 && rows == bn && d->h * d->w >= 128) {
+    FrameRingParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.n = d->n; rp.t = d->t; rp.hw = d->h * d->w;
+    rp.blocks_per_frame = (rp.hw + 127) / 128;
+    rp.kt = d->kt; rp.pt = d->pt;
+    rp.cin_blocks = (d->cin + 63) / 64; rp.cin_k16 = d->cin / 16; rp.k_per_tap = d->cin;
+    rp.n_tile = bn;
+    const int kSmemMax = 227 * 1024;
+    const int aux = (320 + 16 * bn + 255) / 256 * 256;
+    const int w_bytes = d->kt * rp.cin_blocks * bn * 128;
+    int slots = (kSmemMax - aux - w_bytes) / kRingBlockBytes;
+    if (slots > kRingMaxSlots) slots = kRingMaxSlots;
+    const double useful = (double)rp.hw / (rp.blocks_per_frame * 128.0);
+    // Measured (tools/gpu_ring_ab.py): the ring wins when it is deep (one 64-channel block per frame, >= 4 spare slots:
+    // 4.6 vs 3.8 TB/s on 64 -> 64) and loses to K1's 8-stage pipeline when only the kt resident frames fit (144 -> 64).
+    if (w_bytes + aux < kSmemMax && rp.cin_blocks == 1 && bn <= 64 && slots >= d->kt + 4 && useful >= 0.6) {
+      rp.slots = slots;
+      rp.prefetch_frames = g_ring_prefetch;
+      // split the T axis so that there are >= 2 work items per SM (each item re-reads kt-1 halo frames)
+      int chunks = 1;
+      while (chunks * 2 <= d->t && d->t % (chunks * 2) == 0 && d->n * rp.blocks_per_frame * chunks < 2 * di->sm_count &&
+             d->t / (chunks * 2) >= 4)
+        chunks *= 2;
+      rp.chunks_per_clip = chunks;
+      rp.t_chunk = d->t / chunks;
+      rp.num_items = d->n * chunks * rp.blocks_per_frame;
+      rp.cout_store = d->cout; rp.flags = d->flags | g_debug_flags;
+      rp.scale = scale; rp.shift = shift; rp.residual = (const __nv_bfloat16*)residual;
+      rp.y = (__nv_bfloat16*)y; rp.stats = stats;
+      CUtensorMap tmx, tmw;
+      const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)rp.hw, (cuuint64_t)d->t, (cuuint64_t)d->n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * rp.hw, (cuuint64_t)d->cin * 2 * rp.hw * d->t};
+      const cuuint32_t box[4] = {64, 128, 1, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(frame ring x) failed (CUresult %d)", (int)r);
+      if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
+      static bool attr_set_r[16] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr_set_r[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_frame_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_frame_ring_kernel): %s", cudaGetErrorString(e));
+        attr_set_r[dev] = true;
+      }
+      const int smem_bytes = w_bytes + slots * kRingBlockBytes + aux;
+      const int grid = rp.num_items < di->sm_count ? rp.num_items : di->sm_count;
+      conv_frame_ring_kernel<<<grid, kRingThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, rp);
+      return check_launch("conv_frame_ring_kernel");
+    }
+  }
+
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
   p.m_total = d->n * to * ho * wo;
@@ -550,7 +622,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   p.num_m_tiles = (p.m_total + kBlockM - 1) / kBlockM;
   p.num_n_tiles = rows / bn;
   p.cout_store = d->cout;
-  p.flags = d->flags;
+  p.flags = d->flags | g_debug_flags;
   p.scale = scale; p.shift = shift;
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;

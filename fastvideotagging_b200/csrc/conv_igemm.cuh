@@ -176,9 +176,20 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // registers); one elected lane issues the tcgen05 instructions.  A thread-divergent issuer (if lane == 0 around the
     // loop) makes the compiler wrap every UTCHMMA in an ELECT/BRA.U.ANY serialisation loop and costs ~230 clk per MMA.
     {
+      // The issue loop runs on ONE thread: every instruction of bookkeeping per k-block is ~6 clk of serial latency, so
+      // descriptors advance by precomputed steps and barrier addresses are plain adds.
       const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      const uint32_t tiles_u32 = ptx::smem_u32(smem_tiles);
+      const uint32_t full_u32 = ptx::smem_u32(full_bar), empty_u32 = ptx::smem_u32(empty_bar);
+      const uint64_t a_desc_s0 = ptx::make_sw128_desc(tiles_u32, 16, 1024);
+      const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
+      const uint64_t b_stat0 = ptx::make_sw128_desc(ptx::smem_u32(smem_b), 16, 1024);
+      const uint32_t b_step = static_cast<uint32_t>(b_tile_bytes) >> 4;
+      const uint32_t b_in_stage = p.b_stationary ? 0u : static_cast<uint32_t>(kATileBytes >> 4);
+      const int last_k16 = p.cin_k16 - (p.cin_blocks - 1) * (kBlockK / 16);   // MMAs of the last channel block of a tap
       int stage = 0;
       uint32_t phase = 0;
+      uint64_t a_desc = a_desc_s0;
       int acc = 0;
       uint32_t acc_phase = 0;
       if (p.b_stationary && blockIdx.x < num_tiles) ptx::mbar_wait(ptx::smem_u32(b_full_bar), 0);
@@ -187,26 +198,24 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         int cb = 0;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          int k16 = p.cin_k16 - cb * (kBlockK / 16);
-          if (k16 > kBlockK / 16) k16 = kBlockK / 16;
-          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+        uint64_t b_stat = b_stat0;
+        for (int kb = 0; kb < k_blocks; ++kb, b_stat += b_step) {
+          const int k16 = (cb == p.cin_blocks - 1) ? last_k16 : kBlockK / 16;
+          ptx::mbar_wait(full_u32 + stage * 8, phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_tiles + stage * stage_bytes);
-          const uint64_t a_desc = ptx::make_sw128_desc(a_addr, 16, 1024);
-          const uint64_t b_desc = ptx::make_sw128_desc(
-              p.b_stationary ? ptx::smem_u32(smem_b + kb * b_tile_bytes) : a_addr + kATileBytes, 16, 1024);
+          const uint64_t b_desc = p.b_stationary ? b_stat : a_desc + b_in_stage;
           if (ptx::elect_one()) {
             // +32 bytes (16 bf16) along K inside the swizzle atom == +2 in the (addr >> 4) field
             ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, kb != 0);
             if (k16 > 1) ptx::umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
             if (k16 > 2) ptx::umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
             if (k16 > 3) ptx::umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
-            ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
+            ptx::umma_commit(empty_u32 + stage * 8);
           }
           __syncwarp();
           if (++cb == p.cin_blocks) cb = 0;
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          a_desc += stage_step;
+          if (++stage == stages) { stage = 0; phase ^= 1; a_desc = a_desc_s0; }
         }
         if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&acc_full_bar[acc]));
         __syncwarp();

@@ -41,6 +41,8 @@ struct SlabParams {
   int stages;              // slab stages
   int b_ring;              // weight ring slots
   int b_stationary;
+  int box_rows;            // image rows per TMA box (r_in: one box per slab block; smaller: several boxes per block)
+  int prefetch_dist;       // > 0: L2-prefetch the slab of the tile `prefetch_dist` iterations ahead
   int cout_store, flags;
   const float* scale;
   const float* shift;
@@ -54,6 +56,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// L2 prefetch of a 4-D box (no shared-memory destination, no barrier): warms L2 for a slab this CTA loads a few tiles later.
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(kSlabThreads, 1)
@@ -131,8 +140,19 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(fb, p.cin_blocks * p.slab_tx_bytes);
           for (int cb = 0; cb < p.cin_blocks; ++cb)
-            tma_load_4d(ptx::smem_u32(smem_a + stage * stage_bytes + cb * p.slab_slot_bytes), &tmap_x, fb,
-                        cb * 64, -p.pw, h0 - p.ph, frame);
+            for (int r = 0; r < p.r_in; r += p.box_rows)
+              tma_load_4d(ptx::smem_u32(smem_a + stage * stage_bytes + cb * p.slab_slot_bytes + r * p.wp * 128), &tmap_x,
+                          fb, cb * 64, -p.pw, h0 - p.ph + r, frame);
+          if (p.prefetch_dist > 0) {
+            const int mt2 = mt + p.prefetch_dist * gridDim.x;
+            if (mt2 < num_m_tiles) {
+              const int frame2 = mt2 / p.tiles_per_frame;
+              const int h2 = (mt2 - frame2 * p.tiles_per_frame) * p.r_out;
+              for (int cb = 0; cb < p.cin_blocks; ++cb)
+                for (int r = 0; r < p.r_in; r += p.box_rows)
+                  tma_prefetch_4d(&tmap_x, cb * 64, -p.pw, h2 - p.ph + r, frame2);
+            }
+          }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -173,6 +193,46 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
         ptx::tc_fence_after();
         const uint32_t a_base = ptx::smem_u32(smem_a + stage * stage_bytes);
+        if (p.b_stationary) {
+          // ---- lean issue path: the whole filter is resident, so a tile's MMAs need no barrier in between and are
+          // issued as ONE straight run by the elected lane (descriptor = base + precomputed offset).  The issue loop
+          // runs on a single thread: with ~100 instructions of bookkeeping per filter tap it, not the tensor pipe,
+          // paced the kernel (ncu: 480 clk per 4 MMAs against a 288 clk floor).
+          if (first) {
+            for (int j = 0; j < b_per_ntile; ++j) ptx::mbar_wait(ptx::smem_u32(&b_full[j]), 0);
+            first = false;
+          }
+          ptx::mbar_wait(ptx::smem_u32(&acc_empty[acc]), acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          const uint64_t a_desc0 = ptx::make_sw128_desc(a_base, 16, 1024);
+          const uint64_t b_desc0 = ptx::make_sw128_desc(ptx::smem_u32(smem_b), 16, 1024);
+          const uint32_t a_cb_step = static_cast<uint32_t>(p.slab_slot_bytes) >> 4;
+          const uint32_t b_step = static_cast<uint32_t>(b_slab_bytes) >> 4;
+          const uint32_t a_row_step = static_cast<uint32_t>(p.wp) * 8u;        // one padded image row, in 16-byte units
+          if (ptx::elect_one()) {
+            uint32_t acc_flag = 0;
+            uint64_t b_desc = b_desc0;
+            uint64_t a_row = a_desc0;
+            for (int dh = 0; dh < p.kh; ++dh, a_row += a_row_step) {
+              uint64_t a_tap = a_row;
+              for (int dw = 0; dw < p.kw; ++dw, a_tap += 8) {
+                uint64_t a_desc = a_tap;
+                int k16 = p.cin_k16;
+                for (int cb = 0; cb < p.cin_blocks; ++cb, a_desc += a_cb_step, b_desc += b_step, k16 -= 4) {
+                  ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc_flag);
+                  acc_flag = 1;
+                  if (k16 > 1) ptx::umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
+                  if (k16 > 2) ptx::umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
+                  if (k16 > 3) ptx::umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
+                }
+              }
+            }
+            ptx::umma_commit(ptx::smem_u32(&acc_full[acc]));
+          }
+          __syncwarp();
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        } else
         for (int nt = 0; nt < p.num_n_tiles; ++nt) {
           ptx::mbar_wait(ptx::smem_u32(&acc_empty[acc]), acc_phase ^ 1);
           ptx::tc_fence_after();

@@ -11,6 +11,8 @@ enum ConvFlags : int {
   kConvRelu = 1,
   kConvResidual = 2,
   kConvStats = 4,
+  kDbgNoStore = 256,     // experiments only (fvt_set_option("debug_flags")): skip the global stores
+  kDbgNoEpilogue = 512,  // experiments only: epilogue does the barrier handshakes but touches no data
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -41,35 +43,30 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
   const bool has_res = (p.flags & kConvResidual) != 0;
   const bool relu = (p.flags & kConvRelu) != 0;
   const bool row_ok = out_row >= 0;
-  const int n_chunks = p.block_n >> 4;
+  const int n_chunks = (p.flags & kDbgNoEpilogue) ? 0 : (p.block_n >> 4);
   float* stat_smem = p.stat_smem;
   __nv_bfloat16* yrow = p.y + static_cast<size_t>(row_ok ? out_row : 0) * p.cout_store;
   const __nv_bfloat16* rrow = has_res ? p.residual + static_cast<size_t>(row_ok ? out_row : 0) * p.cout_store : nullptr;
   // software pipeline: TMEM load + residual load of chunk i+1 are in flight while chunk i is processed
   uint32_t v[16], vn[16];
-  uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, rn0 = r0, rn1 = r0;
+  uint32_t rr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int ci = grp;
   if (ci < n_chunks) {
     ptx::tmem_ld_32x32b_x16(taddr + ci * 16, vn);
-    if (has_res && n0 + ci * 16 < p.cout_store) {
-      rn0 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + ci * 16));
-      rn1 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + ci * 16 + 8));
-    }
+    if (has_res && n0 + ci * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + ci * 16, rn);
   }
   for (; ci < n_chunks; ci += 2) {
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = vn[i];
-    r0 = rn0; r1 = rn1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rr[i] = rn[i];
     const int c = ci * 16;
     const int ch0 = n0 + c;
     const int cnext = ci + 2;
     if (cnext < n_chunks) {
       ptx::tmem_ld_32x32b_x16(taddr + cnext * 16, vn);
-      if (has_res && n0 + cnext * 16 < p.cout_store) {
-        rn0 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + cnext * 16));
-        rn1 = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + cnext * 16 + 8));
-      }
+      if (has_res && n0 + cnext * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + cnext * 16, rn);
     }
     if (ch0 >= p.cout_store) continue;           // N tail (weights zero-padded to a whole tile)
     float f[16];
@@ -117,9 +114,8 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
         f[4 * i + 3] = fmaf(f[4 * i + 3], a.w, b.w);
       }
     }
-    if (row_ok) {
+    if (row_ok && !(p.flags & kDbgNoStore)) {
       if (has_res) {
-        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           f[2 * i] += bf16_lo(rr[i]);
@@ -130,13 +126,10 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
       }
-      uint4 o0, o1;
-      o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-      o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-      o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-      o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-      *reinterpret_cast<uint4*>(yrow + ch0) = o0;
-      *reinterpret_cast<uint4*>(yrow + ch0 + 8) = o1;
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      ptx::st_global_256(yrow + ch0, o);          // one full 32-byte sector per thread
     }
   }
 }

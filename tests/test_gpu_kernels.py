@@ -73,6 +73,35 @@ def test_stationary_and_streamed_weights_agree(cuda_device, lib):
     assert torch.equal(y_stat, y_str)
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 56, 56, 64, 64), (1, 16, 28, 28, 64, 48), (3, 5, 14, 14, 48, 64), (1, 32, 20, 13, 32, 64), (2, 8, 56, 56, 144, 64)])
+def test_frame_ring_and_im2col_kernels_agree(cuda_device, lib, shape):
+    """K1t (frame ring: every frame block loaded once, taps = ring slots) and K1 (im2col) are two schedules of the same
+    3x1x1 convolution (with residual + ReLU + statistics): equal up to fp32 summation order."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w_, cin, cout = shape
+    torch.manual_seed(6)
+    x = (torch.randn(n, t, h, w_, cin) * 0.5).to(torch.bfloat16).to(cuda_device)
+    res = (torch.randn(n, t, h, w_, cout) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = torch.randn(cout, cin, 3, 1, 1, device=cuda_device) / (3 * cin) ** 0.5
+    sc = (torch.rand(cout, device=cuda_device) + 0.5)
+    sh = torch.randn(cout, device=cuda_device) * 0.1
+    d = ops.conv_desc(n, t, h, w_, cin, cout, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL | ops.FVT_CONV_STATS)
+    wp = ops.pack_conv_weight(d, w)
+    st_ring = torch.zeros(2 * cout, device=cuda_device)
+    y_ring = ops.conv3d_fwd(d, x, wp, sc, sh, res, stats=st_ring)
+    assert lib.fvt_set_option(b"disable_frame_ring", 1) == 0
+    try:
+        st_gen = torch.zeros(2 * cout, device=cuda_device)
+        y_gen = ops.conv3d_fwd(d, x, wp, sc, sh, res, stats=st_gen)
+    finally:
+        lib.fvt_set_option(b"disable_frame_ring", 0)
+    torch.cuda.synchronize()
+    scale = y_gen.float().abs().max().item()
+    assert (y_ring.float() - y_gen.float()).abs().max().item() <= 2 ** -7 * scale
+    assert (st_ring - st_gen).abs().max().item() <= 1e-3 * st_gen.abs().max().item()
+
+
 def test_wgrad_slab_and_im2col_kernels_agree(cuda_device, lib):
     """K3s (slab, stacked taps) and K3 (im2col) compute the same weight gradient up to fp32 summation order."""
     import torch
