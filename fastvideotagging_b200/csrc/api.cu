@@ -54,6 +54,7 @@ static int g_slab_box_rows = 0;  // fvt_set_option("slab_box_rows", r): rows per
 static int g_slab_prefetch = 2;  // fvt_set_option("slab_prefetch", d): L2 prefetch distance in tiles (0 = off)
 static int g_ring_prefetch = 4;  // fvt_set_option("ring_prefetch", f): K1t L2 prefetch distance in frames (0 = off)
 static int g_disable_ring = 0;   // fvt_set_option("disable_frame_ring", 1): temporal convs go through K1 (im2col)
+static int g_slab_single_stage = 1;   // fvt_set_option("slab_single_stage", 0): keep two input stages even with a shallow weight ring
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -375,6 +376,7 @@ int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
   if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
   if (name != nullptr && strcmp(name, "disable_frame_ring") == 0) { g_disable_ring = value; return 0; }
+  if (name != nullptr && strcmp(name, "slab_single_stage") == 0) { g_slab_single_stage = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_box_rows") == 0) { g_slab_box_rows = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_prefetch") == 0) { g_slab_prefetch = value; return 0; }
   if (name != nullptr && strcmp(name, "debug_flags") == 0) { g_debug_flags = value & (kDbgNoStore | kDbgNoEpilogue); return 0; }
@@ -512,6 +514,13 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
         sp.b_stationary = 0;
         sp.stages = 2;
         sp.b_ring = (kSmemMax - aux - 2 * stage_bytes) / b_slab;
+        // A weight slab is consumed in <= 4 MMAs (256-300 clk) but takes > 1000 clk to arrive: a shallow weight ring
+        // starves the tensor pipe (measured on the 144 -> 64 data-gradient conv).  Trade the second input stage for
+        // ring depth when the ring would be shallower than 5 slabs.
+        if (sp.b_ring < 5 && g_slab_single_stage) {
+          sp.stages = 1;
+          sp.b_ring = (kSmemMax - aux - stage_bytes) / b_slab;
+        }
         if (sp.b_ring > kSlabMaxBRing) sp.b_ring = kSlabMaxBRing;
         if (sp.b_ring < 4) ok = false;
       }

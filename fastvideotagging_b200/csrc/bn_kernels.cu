@@ -24,6 +24,8 @@
 
 namespace fvt {
 
+constexpr int kUnroll = 4;      // rows per thread per loop iteration in the [rows, C] passes
+
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -86,23 +88,36 @@ bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, 
     rs[i] = res_mode == 2 ? res_scale[cv * 8 + i] : 1.f;
     rh[i] = res_mode == 2 ? res_shift[cv * 8 + i] : 0.f;
   }
-  for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
-    const size_t idx = r * cvec + cv;
-    float x[8], y[8];
-    unpack8(__ldg(raw + idx), x);
+  // kUnroll rows per thread per iteration: all loads are issued before the first use (bytes in flight per thread)
+  const size_t rstep = static_cast<size_t>(gridDim.x) * tpr;
+  for (size_t r0 = static_cast<size_t>(blockIdx.x) * tpr + rsub; r0 < rows; r0 += rstep * kUnroll) {
+    uint4 vx[kUnroll], vq[kUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = fmaf(x[i], sc[i], sh[i]);
-    if (res_mode) {
-      float q[8];
-      unpack8(__ldg(res + idx), q);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] += fmaf(q[i], rs[i], rh[i]);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t r = r0 + u * rstep;
+      vx[u] = r < rows ? __ldg(raw + r * cvec + cv) : make_uint4(0, 0, 0, 0);
+      vq[u] = (res_mode && r < rows) ? __ldg(res + r * cvec + cv) : make_uint4(0, 0, 0, 0);
     }
-    if (relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t r = r0 + u * rstep;
+      if (r >= rows) break;
+      float x[8], y[8];
+      unpack8(vx[u], x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaf(x[i], sc[i], sh[i]);
+      if (res_mode) {
+        float q[8];
+        unpack8(vq[u], q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] += fmaf(q[i], rs[i], rh[i]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      out[r * cvec + cv] = pack8(y);
     }
-    out[idx] = pack8(y);
   }
 }
 
@@ -126,24 +141,36 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ da
     rsh[i] = self_mask ? relu_shift[cv * 8 + i] : 1.f;
   }
   if (rsub < tpr) {
-    for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
-      const size_t idx = r * cvec + cv;
-      float x[8], g[8];
-      unpack8(__ldg(raw + idx), x);
-      unpack8(__ldg(dact + idx), g);
-      if (mask != nullptr) {
-        float mk[8];
-        unpack8(__ldg(mask + idx), mk);
+    const size_t rstep = static_cast<size_t>(gridDim.x) * tpr;
+    for (size_t r0 = static_cast<size_t>(blockIdx.x) * tpr + rsub; r0 < rows; r0 += rstep * kUnroll) {
+      uint4 vx[kUnroll], vg[kUnroll], vm[kUnroll];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
-      } else if (self_mask) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
+      for (int u = 0; u < kUnroll; ++u) {
+        const size_t r = r0 + u * rstep;
+        const bool ok = r < rows;
+        vx[u] = ok ? __ldg(raw + r * cvec + cv) : make_uint4(0, 0, 0, 0);
+        vg[u] = ok ? __ldg(dact + r * cvec + cv) : make_uint4(0, 0, 0, 0);     // zero gradient: contributes nothing
+        vm[u] = (ok && mask != nullptr) ? __ldg(mask + r * cvec + cv) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        db[i] += g[i];
-        dg[i] = fmaf(g[i], (x[i] - mu[i]) * is[i], dg[i]);
+      for (int u = 0; u < kUnroll; ++u) {
+        float x[8], g[8];
+        unpack8(vx[u], x);
+        unpack8(vg[u], g);
+        if (mask != nullptr) {
+          float mk[8];
+          unpack8(vm[u], mk);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
+        } else if (self_mask) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          db[i] += g[i];
+          dg[i] = fmaf(g[i], (x[i] - mu[i]) * is[i], dg[i]);
+        }
       }
     }
   }
@@ -186,24 +213,39 @@ bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dac
     bq[i] = sums[c_store + ch] * inv_rows;          // dbeta / M
     cq[i] = sums[ch] * inv_rows;                    // dgamma / M
   }
-  for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
-    const size_t idx = r * cvec + cv;
-    float x[8], g[8], o[8];
-    unpack8(__ldg(raw + idx), x);
-    unpack8(__ldg(dact + idx), g);
-    if (mask != nullptr) {
-      float mk[8];
-      unpack8(__ldg(mask + idx), mk);
+  const size_t rstep = static_cast<size_t>(gridDim.x) * tpr;
+  for (size_t r0 = static_cast<size_t>(blockIdx.x) * tpr + rsub; r0 < rows; r0 += rstep * kUnroll) {
+    uint4 vx[kUnroll], vg[kUnroll], vm[kUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
-    } else if (self_mask) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t r = r0 + u * rstep;
+      const bool ok = r < rows;
+      vx[u] = ok ? __ldg(raw + r * cvec + cv) : make_uint4(0, 0, 0, 0);
+      vg[u] = ok ? __ldg(dact + r * cvec + cv) : make_uint4(0, 0, 0, 0);
+      vm[u] = (ok && mask != nullptr) ? __ldg(mask + r * cvec + cv) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = a[i] * (g[i] - bq[i] - (x[i] - mu[i]) * is[i] * cq[i]);
-    draw[idx] = pack8(o);
-    if (dz_out != nullptr) dz_out[idx] = pack8(g);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t r = r0 + u * rstep;
+      if (r >= rows) break;
+      const size_t idx = r * cvec + cv;
+      float x[8], g[8], o[8];
+      unpack8(vx[u], x);
+      unpack8(vg[u], g);
+      if (mask != nullptr) {
+        float mk[8];
+        unpack8(vm[u], mk);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
+      } else if (self_mask) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = a[i] * (g[i] - bq[i] - (x[i] - mu[i]) * is[i] * cq[i]);
+      draw[idx] = pack8(o);
+      if (dz_out != nullptr) dz_out[idx] = pack8(g);
+    }
   }
 }
 
@@ -295,7 +337,7 @@ static int rows_launch(size_t rows, int cvec, int* blocks, int* threads) {
   if (tpr < 1) tpr = 1;
   *threads = tpr * cvec;
   if (*threads > 1024) return -1;
-  size_t b = (rows + tpr - 1) / tpr;
+  size_t b = (rows + static_cast<size_t>(tpr) * kUnroll - 1) / (static_cast<size_t>(tpr) * kUnroll);
   const size_t cap = 148 * 8;
   if (b > cap) b = cap;
   if (b < 1) b = 1;

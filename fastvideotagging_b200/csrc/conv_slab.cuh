@@ -166,17 +166,22 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       bool first = true;
       for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
         if (p.b_stationary && !first) break;
+        // lean loop (single issuing thread): no divisions, the K coordinate of the weight slab advances incrementally
+        const uint32_t bfull_u32 = ptx::smem_u32(b_full), bempty_u32 = ptx::smem_u32(b_empty);
+        const uint32_t smem_b_u32 = ptx::smem_u32(smem_b);
         for (int nt = 0; nt < p.num_n_tiles; ++nt) {
-          for (int j = 0; j < b_per_ntile; ++j) {
-            ptx::mbar_wait(ptx::smem_u32(&b_empty[slot]), phase ^ 1);
-            const uint32_t fb = ptx::smem_u32(&b_full[slot]);
-            if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(fb, b_slab_bytes);
-              const int tap = j / p.cin_blocks, cb = j - tap * p.cin_blocks;
-              ptx::tma_load_2d(ptx::smem_u32(smem_b + slot * b_slab_bytes), &tmap_w, fb, tap * p.k_per_tap + cb * 64, nt * p.n_tile);
+          const int n0 = nt * p.n_tile;
+          int k_tap = 0;
+          for (int tap = 0; tap < taps; ++tap, k_tap += p.k_per_tap) {
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+              ptx::mbar_wait(bempty_u32 + slot * 8, phase ^ 1);
+              if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(bfull_u32 + slot * 8, b_slab_bytes);
+                ptx::tma_load_2d(smem_b_u32 + slot * b_slab_bytes, &tmap_w, bfull_u32 + slot * 8, k_tap + cb * 64, n0);
+              }
+              __syncwarp();
+              if (++slot == p.b_ring) { slot = 0; phase ^= 1; }
             }
-            __syncwarp();
-            if (++slot == p.b_ring) { slot = 0; phase ^= 1; }
           }
         }
         first = false;
@@ -232,41 +237,47 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           }
           __syncwarp();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        } else
-        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
-          ptx::mbar_wait(ptx::smem_u32(&acc_empty[acc]), acc_phase ^ 1);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * 256;
-          uint32_t row_off = 0;
-          int dw = 0;
-          for (int tap = 0; tap < taps; ++tap) {
-            for (int cb = 0; cb < p.cin_blocks; ++cb) {
-              if (!p.b_stationary || first) {
-                ptx::mbar_wait(ptx::smem_u32(&b_full[slot]), bphase);
-                ptx::tc_fence_after();
+        } else {
+          // ---- streamed filter: one barrier per [n_tile x 64] weight slab; same lean bookkeeping (descriptors advance
+          // by precomputed steps, barrier addresses are base + slot * 8)
+          const uint64_t a_desc0 = ptx::make_sw128_desc(a_base, 16, 1024);
+          const uint64_t b_desc_s0 = ptx::make_sw128_desc(ptx::smem_u32(smem_b), 16, 1024);
+          const uint32_t a_cb_step = static_cast<uint32_t>(p.slab_slot_bytes) >> 4;
+          const uint32_t b_step = static_cast<uint32_t>(b_slab_bytes) >> 4;
+          const uint32_t a_row_step = static_cast<uint32_t>(p.wp) * 8u;
+          const uint32_t bfull_u32 = ptx::smem_u32(b_full), bempty_u32 = ptx::smem_u32(b_empty);
+          for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+            ptx::mbar_wait(ptx::smem_u32(&acc_empty[acc]), acc_phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            uint32_t acc_flag = 0;
+            uint64_t a_row = a_desc0;
+            for (int dh = 0; dh < p.kh; ++dh, a_row += a_row_step) {
+              uint64_t a_tap = a_row;
+              for (int dw = 0; dw < p.kw; ++dw, a_tap += 8) {
+                uint64_t a_desc = a_tap;
+                int k16 = p.cin_k16;
+                for (int cb = 0; cb < p.cin_blocks; ++cb, a_desc += a_cb_step, k16 -= 4) {
+                  ptx::mbar_wait(bfull_u32 + slot * 8, bphase);
+                  ptx::tc_fence_after();
+                  const uint64_t b_desc = b_desc_s0 + static_cast<uint32_t>(slot) * b_step;
+                  if (ptx::elect_one()) {
+                    ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc_flag);
+                    if (k16 > 1) ptx::umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
+                    if (k16 > 2) ptx::umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
+                    if (k16 > 3) ptx::umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
+                    ptx::umma_commit(bempty_u32 + slot * 8);
+                  }
+                  __syncwarp();
+                  acc_flag = 1;
+                  if (++slot == p.b_ring) { slot = 0; bphase ^= 1; }
+                }
               }
-              int k16 = p.cin_k16 - cb * 4;
-              if (k16 > 4) k16 = 4;
-              const uint64_t a_desc = ptx::make_sw128_desc(a_base + cb * p.slab_slot_bytes + row_off, 16, 1024);
-              const uint64_t b_desc = ptx::make_sw128_desc(ptx::smem_u32(smem_b + slot * b_slab_bytes), 16, 1024);
-              if (ptx::elect_one()) {
-                ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (tap | cb) != 0);
-                if (k16 > 1) ptx::umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
-                if (k16 > 2) ptx::umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
-                if (k16 > 3) ptx::umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
-                if (!p.b_stationary) ptx::umma_commit(ptx::smem_u32(&b_empty[slot]));
-              }
-              __syncwarp();
-              if (++slot == p.b_ring) { slot = 0; bphase ^= 1; }
             }
-            // next tap: one column to the right, or first column of the next padded row
-            if (++dw == p.kw) { dw = 0; row_off += static_cast<uint32_t>(p.wp - p.kw + 1) * 128u; }
-            else row_off += 128u;
+            if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&acc_full[acc]));
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           }
-          if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&acc_full[acc]));
-          __syncwarp();
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          if (p.b_stationary) { slot = 0; first = false; }
         }
         if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&slab_empty[stage]));
         __syncwarp();
