@@ -283,6 +283,26 @@ def run_ours(args, rank, world, local_rank):
         value = clips / (ms / 1e3)
         e2e = clips / (ms_e2e / 1e3)
         conv_tflops = batch * GFLOP_PER_CLIP_FWD / k1_ms if k1_ms > 0 else None     # GFLOP / ms = TFLOP/s
+        # dominant kernel: conv_slab_fwd_kernel on the six conv2_x 1x3x3 (64 -> 144) layers — one launch each, the largest
+        # single share of the step.  achieved = algorithmic 2*M*N*K of one launch / its mean CUDA-event duration.
+        dom = [r for r in rows if r[0].startswith(("comp_0_", "comp_1_", "comp_2_")) and r[0].endswith("_middle")]
+        dom_ms = sum(r[4] for r in dom) / max(len(dom), 1)
+        dom_flop = 2.0 * dom[0][1] * dom[0][2] * dom[0][3] if dom else 0.0
+        dom_tflops = dom_flop / dom_ms / 1e9 if dom else None
+        # DRAM bytes of that launch from `ncu --set full` (profiles/r01j_ncu_slab_conv2x_inference.txt, batch 48):
+        # 617 MB read + 1335 MB written = the algorithmic bytes (input once + output once), i.e. no wasted re-reads
+        traffic = 1.952e9 * batch / 48.0
+        roofline = {"bound": "tensor", "achieved": dom_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": (dom_tflops / peaks["tflops"]) if dom_tflops else None, "traffic": traffic,
+                    "kernel": "conv_slab_fwd_kernel, conv2_x 1x3x3 64->144 (6 launches/step, %.0f%% of the step); "
+                              "algorithmic 2MNK = %.1f GFLOP/launch, mean CUDA-event time %.3f ms" % (
+                                  100.0 * dom_ms * len(dom) / (ms / args.steps), dom_flop / 1e9, dom_ms),
+                    "peak_source": peaks["source"] + " bf16_tflops_sustained (cuBLAS 8192^3 back to back, power-capped clocks)",
+                    "all_conv_kernels": {"launches_per_step": len(rows), "achieved": conv_tflops,
+                                         "frac": (conv_tflops / peaks["tflops"]) if conv_tflops else None,
+                                         "note": "69 conv launches (conv_igemm_fwd / conv_slab_fwd / conv_frame_ring), "
+                                                 "304.7 GFLOP/clip algorithmic / summed CUDA-event time"},
+                    "step_frac_of_peak": value * GFLOP_PER_CLIP_FWD / 1e3 / world / peaks["tflops"]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, _, threads = cpu_reference_rate(2, 5, 1)
@@ -296,11 +316,7 @@ def run_ours(args, rank, world, local_rank):
                        "global_batch": batch * world, "parallelism": "replicas x%d (batch-sharded, no collective)" % world,
                        "l2": "activations per layer (0.4-1.4 GB) exceed the 126 MB L2; no explicit flush",
                        "gflop_per_clip": GFLOP_PER_CLIP_FWD},
-            "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": (conv_tflops / peaks["tflops"]) if conv_tflops else None, "traffic": None,
-                         "kernel": "conv_igemm_fwd_kernel (69 launches/step, algorithmic 2MNK flops / summed CUDA-event time)",
-                         "peak_source": peaks["source"] + " bf16_tflops_sustained",
-                         "step_frac_of_peak": value * GFLOP_PER_CLIP_FWD / 1e3 / world / peaks["tflops"]},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                     "d2h_bytes_per_step": batch * NUM_CLASS * 4 * world, "ms_per_step": ms_e2e / args.steps},
