@@ -134,6 +134,13 @@ def run_reference(args, rank, world):
 
 
 def run_ours(args, rank, world, local_rank):
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) are sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     from fastvideotagging_b200 import build
@@ -142,8 +149,14 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line (no NCCL version banner)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    def note(msg):
+        if os.environ.get("FVT_BENCH_VERBOSE"):
+            sys.stderr.write("[bench rank %d] %s\n" % (rank, msg))
+            sys.stderr.flush()
 
     peaks = load_peaks()
     batch = args.batch
@@ -167,6 +180,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(max(args.warmup, 3)):
             logits = net(x_dev)
         barrier()
+        note("inference warm-up done")
         sampler = ClockSampler(local_rank)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -206,6 +220,7 @@ def run_ours(args, rank, world, local_rank):
                 out_host.copy_(lg, non_blocking=True)
             main.synchronize()
 
+        note("device-resident timing done")
         e2e_loop(2)
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
@@ -257,8 +272,11 @@ def run_ours(args, rank, world, local_rank):
             trainer.step(tb * world)
             return loss
 
-        for _ in range(3):
+        note("inference done, training warm-up")
+        for i in range(3):
             train_step()
+            torch.cuda.synchronize()
+            note("train warm-up step %d done" % i)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -331,14 +349,32 @@ def run_ours(args, rank, world, local_rank):
                                  train["batch"], "NCCL all-reduce bucketed+overlapped" if world > 1 else "single GPU"),
                              "gflop_per_clip": GFLOP_PER_CLIP_TRAIN,
                              "frac_of_tensor_peak": tv * GFLOP_PER_CLIP_TRAIN / 1e3 / world / peaks["tflops"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
         if args.layer_table:
             with open(args.layer_table, "w") as fh:
                 fh.write("layer,M,N,K,ms,GFLOP/s\n")
                 for r in rows:
                     fh.write("%s,%d,%d,%d,%.4f,%.0f\n" % r)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down in dependency order: CUDA graphs that captured NCCL kernels first, then the communicator.  A
+        # communicator destroyed while such graphs are alive can block forever, so the teardown also has a watchdog.
+        sys.stdout.flush()
+        net._train_plans.clear()
+        net._plans.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        done = threading.Event()
+
+        def _destroy():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+
+        threading.Thread(target=_destroy, daemon=True).start()
+        if not done.wait(20.0):
+            os._exit(0)
 
 
 def main():
