@@ -236,6 +236,92 @@ static int encode_w_map(const DeviceInfo* di, const void* w, int k_total, int ro
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ K3s temporal launch
+// kt x 1 x 1 stride-1 convs: same kernel, temporal mode (see WgradSlabParams).  Returns 1 / 0 / < 0 like try_wgrad_slab.
+static int try_wgrad_temporal(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
+                              int cout_real, int cin_real, cudaStream_t stream) {
+  if (g_disable_wgrad_slab) return 0;
+  if (!(d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 && d->ph == 0 &&
+        d->pw == 0 && 2 * d->pt == d->kt - 1))
+    return 0;
+  const int hw = d->h * d->w;
+  if (hw < 96) return 0;                                   // a 128-position tile would be mostly padding
+  WgradSlabParams p;
+  memset(&p, 0, sizeof(p));
+  p.temporal = 1;
+  p.hw = hw; p.t_frames = d->t; p.kt = d->kt; p.pt = d->pt;
+  p.blocks_per_frame = (hw + 127) / 128;
+  p.num_tiles = d->n * d->t * p.blocks_per_frame;
+  p.tiles_per_frame = 1; p.r_out = 1;                      // unused by the temporal producer
+  p.ksteps = 8;
+  p.taps = d->kt; p.kw = 1; p.kh = 1; p.wp = 0;
+  p.cin_blocks = (d->cin + 63) / 64;
+  p.groups = p.cin_blocks;
+  p.slab_slot_bytes = 128 * 128;
+  p.slab_tx_bytes = 128 * 128;
+  p.dy_tx_bytes = 128 * 128;
+  const int kSmemMax = 227 * 1024, kAux = 1024;
+  // N tile: whole Cout when it fits 256 columns, else equal parts; M tiles per CTA limited by 512 TMEM columns
+  int nt = (d->cout + 255) / 256;
+  int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
+  int acc_stride = (n_tile + 31) / 32 * 32;
+  int mt = 512 / acc_stride;
+  if (mt > kWgsMaxMt) mt = kWgsMaxMt;
+  const int mt_total = (p.cin_blocks + 1) / 2;
+  if (mt > mt_total) mt = mt_total;
+  // keep >= 2 stages in shared memory
+  while (mt > 1 && 2 * ((2 * mt) * p.slab_slot_bytes + ((n_tile + 63) / 64) * 128 * 128) + kAux > kSmemMax) --mt;
+  p.n_tiles = nt; p.n_tile = n_tile; p.acc_stride = acc_stride; p.n_blocks = (n_tile + 63) / 64;
+  p.mt_per_cta = mt;
+  p.chunks_per_tap = (mt_total + mt - 1) / mt;
+  p.m_chunks = p.chunks_per_tap * d->kt;
+  p.ncb_max = 2 * mt < p.cin_blocks ? 2 * mt : p.cin_blocks;
+  p.stage_bytes = p.ncb_max * p.slab_slot_bytes + p.n_blocks * 128 * 128;
+  p.stages = (kSmemMax - kAux) / p.stage_bytes;
+  if (p.stages < 2) return 0;
+  if (p.stages > kWgsMaxStages) p.stages = kWgsMaxStages;
+  const int items = p.m_chunks * p.n_tiles;
+  int splits = di->sm_count / items;
+  if (splits < 1) splits = 1;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
+  p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.cin_real = cin_real; p.cout_real = cout_real;
+  p.dw = dw;
+
+  CUtensorMap tmx, tmdy;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint32_t box[4] = {64, 128, 1, 1};
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)hw, (cuuint64_t)d->t, (cuuint64_t)d->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * hw, (cuuint64_t)d->cin * 2 * hw * d->t};
+    CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad temporal x) failed (CUresult %d)", (int)r);
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)hw, (cuuint64_t)d->t, (cuuint64_t)d->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * hw, (cuuint64_t)d->cout * 2 * hw * d->t};
+    CUresult r = di->encode_tiled(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad temporal dy) failed (CUresult %d)", (int)r);
+  }
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_wgrad_slab_kernel): %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const int smem_bytes = p.stages * p.stage_bytes + kAux;
+  conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
+  if (int e = check_launch("conv_wgrad_slab_kernel(temporal)")) return e;
+  return 1;
+}
+
 // ------------------------------------------------------------------------------------------------ K3s launch
 // Returns 1 when the slab weight-gradient kernel took the call, 0 when the shape is not eligible, < 0 on error.
 static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
@@ -686,7 +772,8 @@ int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, floa
   const DeviceInfo* di = current_device_info(&st);
   if (di == nullptr) return st;
   {
-    const int r = try_wgrad_slab(di, d, x, dy, dw, cout_real, cin_real, (cudaStream_t)stream);
+    int r = try_wgrad_slab(di, d, x, dy, dw, cout_real, cin_real, (cudaStream_t)stream);
+    if (r == 0) r = try_wgrad_temporal(di, d, x, dy, dw, cout_real, cin_real, (cudaStream_t)stream);
     if (r != 0) return r < 0 ? r : 0;
   }
   int to, ho, wo;

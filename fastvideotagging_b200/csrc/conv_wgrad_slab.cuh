@@ -41,6 +41,10 @@ struct WgradSlabParams {
   int stage_bytes, stages;
   int splits, tiles_per_split;
   int cin_real, cout_real;
+  // temporal mode (kt x 1 x 1 convs): a pixel tile = 128 positions of one output frame; a CTA's M chunk = (tap, range of
+  // 64-channel blocks); the tap's input frame blocks are plain [128 x 64] TMA boxes (no shifted views: shift = 0)
+  int temporal;
+  int hw, t_frames, blocks_per_frame, kt, pt, chunks_per_tap;
   float* dw;
 };
 
@@ -63,12 +67,15 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const int nt = item % p.n_tiles;     item /= p.n_tiles;
   const int chunk = item % p.m_chunks; item /= p.m_chunks;
   const int split = item;
-  const int g_lo = chunk * 2 * p.mt_per_cta;
+  // spatial: groups g = cb*taps + tap over the whole filter;  temporal: this CTA's tap is fixed, groups = channel blocks
+  const int tap_t = p.temporal ? chunk / p.chunks_per_tap : 0;
+  const int n_groups = p.temporal ? p.cin_blocks : p.groups;
+  const int g_lo = (p.temporal ? chunk - tap_t * p.chunks_per_tap : chunk) * 2 * p.mt_per_cta;
   int g_hi = g_lo + 2 * p.mt_per_cta;
-  if (g_hi > p.groups) g_hi = p.groups;
+  if (g_hi > n_groups) g_hi = n_groups;
   const int mt_count = (g_hi - g_lo + 1) >> 1;
-  const int cb_lo = g_lo / p.taps;
-  const int cb_hi = (g_hi - 1) / p.taps;
+  const int cb_lo = p.temporal ? g_lo : g_lo / p.taps;
+  const int cb_hi = p.temporal ? g_hi - 1 : (g_hi - 1) / p.taps;
   const int ncb = cb_hi - cb_lo + 1;
   const int tile0 = split * p.tiles_per_split;
   int tile1 = tile0 + p.tiles_per_split;
@@ -115,10 +122,22 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       const uint32_t base = ptx::smem_u32(smem + stage * p.stage_bytes);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(fb, tx);
-        for (int c = 0; c < ncb; ++c)
-          tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, -p.pw, h0 - p.ph, frame);
-        for (int j = 0; j < p.n_blocks; ++j)
-          tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, 0, h0, frame);
+        if (!p.temporal) {
+          for (int c = 0; c < ncb; ++c)
+            tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, -p.pw, h0 - p.ph, frame);
+          for (int j = 0; j < p.n_blocks; ++j)
+            tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, 0, h0, frame);
+        } else {
+          // tile -> (clip n, output frame t, 128-position block b); maps are {C, H*W, T, N}; frames outside [0, T) and
+          // positions beyond H*W come back as zeros
+          const int b = tile % p.blocks_per_frame;
+          const int nt_ = tile / p.blocks_per_frame;
+          const int t = nt_ % p.t_frames, n = nt_ / p.t_frames;
+          for (int c = 0; c < ncb; ++c)
+            tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, b * 128, t + tap_t - p.pt, n);
+          for (int j = 0; j < p.n_blocks; ++j)
+            tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, b * 128, t, n);
+        }
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -134,10 +153,16 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       if (i < mt_count) {
         const int ga = g_lo + 2 * i;
         const int gb = ga + 1 < g_hi ? ga + 1 : ga;          // odd tail: second half duplicates the first, ignored later
-        const int cba = ga / p.taps, tapa = ga - cba * p.taps;
-        const int cbb = gb / p.taps, tapb = gb - cbb * p.taps;
-        const uint32_t oa = (cba - cb_lo) * p.slab_slot_bytes + ((tapa / p.kw) * p.wp + tapa % p.kw) * 128;
-        const uint32_t ob = (cbb - cb_lo) * p.slab_slot_bytes + ((tapb / p.kw) * p.wp + tapb % p.kw) * 128;
+        uint32_t oa, ob;
+        if (p.temporal) {
+          oa = (ga - cb_lo) * p.slab_slot_bytes;
+          ob = (gb - cb_lo) * p.slab_slot_bytes;
+        } else {
+          const int cba = ga / p.taps, tapa = ga - cba * p.taps;
+          const int cbb = gb / p.taps, tapb = gb - cbb * p.taps;
+          oa = (cba - cb_lo) * p.slab_slot_bytes + ((tapa / p.kw) * p.wp + tapa % p.kw) * 128;
+          ob = (cbb - cb_lo) * p.slab_slot_bytes + ((tapb / p.kw) * p.wp + tapb % p.kw) * 128;
+        }
         a_off[i] = oa;
         a_lbo[i] = ob - oa;
       }
@@ -174,7 +199,8 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int r = q * 32 + lane;
     for (int i = 0; i < mt_count; ++i) {
       const int g = g_lo + 2 * i + (r >> 6);
-      const int cb = g / p.taps, tap = g - cb * p.taps;
+      const int cb = p.temporal ? g : g / p.taps;
+      const int tap = p.temporal ? tap_t : g - cb * p.taps;
       const int ci = cb * 64 + (r & 63);
       const bool row_ok = g < g_hi && ci < p.cin_real;
       const uint32_t taddr = tmem_base + i * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);

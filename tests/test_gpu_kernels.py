@@ -124,6 +124,30 @@ def test_wgrad_slab_and_im2col_kernels_agree(cuda_device, lib):
         assert (dw_slab - dw_gen).abs().max().item() <= 2e-4 * scale + 1e-4, (h, cin, cout)
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 56, 56, 144, 64), (2, 6, 28, 28, 288, 128), (1, 4, 14, 14, 576, 256), (3, 5, 20, 13, 48, 64)])
+def test_wgrad_temporal_slab_and_im2col_kernels_agree(cuda_device, lib, shape):
+    """K3s in temporal mode (one tap per CTA, channel blocks stacked in M) vs K3 (im2col) on 3x1x1 convs."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w_, cin, cout = shape
+    torch.manual_seed(7)
+    x = (torch.randn(n, t, h, w_, cin) * 0.5).to(torch.bfloat16).to(cuda_device)
+    dy = (torch.randn(n, t, h, w_, cout) * 0.5).to(torch.bfloat16).to(cuda_device)
+    d = ops.conv_desc(n, t, h, w_, cin, cout, (3, 1, 1), (1, 1, 1), (1, 0, 0))
+    cin_r = cin - 3 if cin == 48 else cin                     # stem-like: 45 real channels in 48 stored
+    dw_slab = torch.zeros(cout, cin_r, 3, 1, 1, device=cuda_device)
+    ops.conv3d_wgrad(d, x, dy, dw_slab, cout, cin_r)
+    assert lib.fvt_set_option(b"disable_wgrad_slab", 1) == 0
+    try:
+        dw_gen = torch.zeros_like(dw_slab)
+        ops.conv3d_wgrad(d, x, dy, dw_gen, cout, cin_r)
+    finally:
+        lib.fvt_set_option(b"disable_wgrad_slab", 0)
+    torch.cuda.synchronize()
+    scale = dw_gen.abs().max().item()
+    assert (dw_slab - dw_gen).abs().max().item() <= 2e-4 * scale + 1e-4
+
+
 @pytest.mark.parametrize("idx", range(16))
 def test_conv_wgrad_dgrad(cuda_device, idx):
     m = _probe_train()
