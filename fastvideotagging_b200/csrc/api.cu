@@ -14,6 +14,7 @@
 #include "conv_slab.cuh"
 #include "conv_wgrad_slab.cuh"
 #include "conv_frame_ring.cuh"
+#include "conv_temporal_is.cuh"
 #include "host_common.h"
 
 namespace fvt {
@@ -55,6 +56,7 @@ static int g_slab_prefetch = 2;  // fvt_set_option("slab_prefetch", d): L2 prefe
 static int g_ring_prefetch = 4;  // fvt_set_option("ring_prefetch", f): K1t L2 prefetch distance in frames (0 = off)
 static int g_disable_ring = 0;   // fvt_set_option("disable_frame_ring", 1): temporal convs go through K1 (im2col)
 static int g_slab_single_stage = 1;   // fvt_set_option("slab_single_stage", 0): keep two input stages even with a shallow weight ring
+static int g_disable_tis = 0;    // fvt_set_option("disable_temporal_is", 1): no input-stationary temporal kernel (K1i)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -463,6 +465,7 @@ int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
   if (name != nullptr && strcmp(name, "disable_frame_ring") == 0) { g_disable_ring = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_single_stage") == 0) { g_slab_single_stage = value; return 0; }
+  if (name != nullptr && strcmp(name, "disable_temporal_is") == 0) { g_disable_tis = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_box_rows") == 0) { g_slab_box_rows = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_prefetch") == 0) { g_slab_prefetch = value; return 0; }
   if (name != nullptr && strcmp(name, "debug_flags") == 0) { g_debug_flags = value & (kDbgNoStore | kDbgNoEpilogue); return 0; }
@@ -642,6 +645,63 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       const int grid = m_tiles < di->sm_count ? m_tiles : di->sm_count;
       conv_slab_fwd_kernel<<<grid, kSlabThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
       return check_launch("conv_slab_fwd_kernel");
+    }
+  }
+
+  // ---- K1i: stride-1 temporal convs with several channel blocks whose filter fits in shared memory: input-stationary
+  //      (each input frame block is loaded once, multiplied by all kt taps into rotating TMEM accumulators)
+  if (!g_disable_tis && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 &&
+      d->ph == 0 && d->pw == 0 && 2 * d->pt == d->kt - 1 && rows == bn && d->h * d->w >= 128 && d->cin > 64) {
+    TemporalIsParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.n = d->n; tp.t = d->t; tp.hw = d->h * d->w;
+    tp.blocks_per_frame = (tp.hw + 127) / 128;
+    tp.kt = d->kt; tp.pt = d->pt;
+    tp.cin_blocks = (d->cin + 63) / 64; tp.cin_k16 = d->cin / 16; tp.k_per_tap = d->cin;
+    tp.n_tile = bn;
+    tp.acc_slots = 512 / bn;
+    if (tp.acc_slots > kTisMaxAcc) tp.acc_slots = kTisMaxAcc;
+    const int kSmemMax = 227 * 1024;
+    const int aux = (512 + 16 * bn + 255) / 256 * 256;
+    const int w_bytes = d->kt * tp.cin_blocks * bn * 128;
+    const int stage_bytes = tp.cin_blocks * 128 * 128;
+    int stages = (kSmemMax - aux - w_bytes) / stage_bytes;
+    if (stages > kTisMaxStages) stages = kTisMaxStages;
+    const double useful = (double)tp.hw / (tp.blocks_per_frame * 128.0);
+    if (w_bytes + aux < kSmemMax && stages >= 3 && tp.acc_slots >= d->kt + 1 && useful >= 0.6) {
+      tp.stages = stages;
+      int chunks = 1;
+      while (chunks * 2 <= d->t && d->t % (chunks * 2) == 0 && d->n * tp.blocks_per_frame * chunks < 2 * di->sm_count &&
+             d->t / (chunks * 2) >= 4)
+        chunks *= 2;
+      tp.chunks_per_clip = chunks;
+      tp.t_chunk = d->t / chunks;
+      tp.num_items = d->n * chunks * tp.blocks_per_frame;
+      tp.cout_store = d->cout; tp.flags = d->flags | g_debug_flags;
+      tp.scale = scale; tp.shift = shift; tp.residual = (const __nv_bfloat16*)residual;
+      tp.y = (__nv_bfloat16*)y; tp.stats = stats;
+      CUtensorMap tmx, tmw;
+      const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)tp.hw, (cuuint64_t)d->t, (cuuint64_t)d->n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * tp.hw, (cuuint64_t)d->cin * 2 * tp.hw * d->t};
+      const cuuint32_t box[4] = {64, 128, 1, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(temporal-is x) failed (CUresult %d)", (int)r);
+      if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
+      static bool attr_set_t[16] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr_set_t[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_temporal_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_temporal_is_kernel): %s", cudaGetErrorString(e));
+        attr_set_t[dev] = true;
+      }
+      const int smem_bytes = w_bytes + stages * stage_bytes + aux;
+      const int grid = tp.num_items < di->sm_count ? tp.num_items : di->sm_count;
+      conv_temporal_is_kernel<<<grid, kTisThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, tp);
+      return check_launch("conv_temporal_is_kernel");
     }
   }
 

@@ -229,6 +229,7 @@ conv_frame_ring_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
           for (int i = et; i < 2 * p.n_tile; i += 256) stat_smem[i] = 0.f;
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+        epilogue_prefetch_residual(ea, 0, out_row, grp);
         ptx::mbar_wait(ptx::smem_u32(&acc_full[acc]), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);

@@ -242,6 +242,11 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         for (int i = et; i < 512; i += kEpilogueThreads) stat_smem[i] = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      {
+        EpilogueArgs pre;
+        pre.block_n = p.block_n; pre.cout_store = p.cout_store; pre.flags = p.flags; pre.residual = p.residual;
+        epilogue_prefetch_residual(pre, n0, row_ok ? static_cast<long long>(row) : -1ll, grp);
+      }
       ptx::mbar_wait(ptx::smem_u32(&acc_full_bar[acc]), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);

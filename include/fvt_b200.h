@@ -57,7 +57,7 @@ const char* fvt_last_error(void);
 /* 0 if `device` is an sm_100 part and the driver exposes the tensor-map encoders, else a negative status. */
 int fvt_device_check(int device);
 /* Tuning/debug switches (A/B runs and tests): "disable_slab" = 1 routes every convolution through the generic im2col
- * kernel (K1); "disable_frame_ring" = 1 does the same for the temporal convs only; "disable_b_stationary" = 1 makes K1
+ * kernel (K1); "disable_frame_ring" / "disable_temporal_is" = 1 do the same for the temporal kernels (K1t / K1i) only; "disable_b_stationary" = 1 makes K1
  * stream its weights; "disable_wgrad_slab" = 1 routes every weight gradient through the im2col kernel (K3);
  * "slab_prefetch" / "slab_box_rows" / "debug_flags" are load-path and epilogue experiments (tools/gpu_*_ab.py). */
 int fvt_set_option(const char* name, int value);

@@ -73,10 +73,12 @@ def test_stationary_and_streamed_weights_agree(cuda_device, lib):
     assert torch.equal(y_stat, y_str)
 
 
-@pytest.mark.parametrize("shape", [(2, 8, 56, 56, 64, 64), (1, 16, 28, 28, 64, 48), (3, 5, 14, 14, 48, 64), (1, 32, 20, 13, 32, 64), (2, 8, 56, 56, 144, 64)])
+@pytest.mark.parametrize("shape", [(2, 8, 56, 56, 64, 64), (1, 16, 28, 28, 64, 48), (3, 5, 14, 14, 48, 64), (1, 32, 20, 13, 32, 64),
+                                   (2, 8, 56, 56, 144, 64), (3, 4, 28, 28, 144, 64), (1, 32, 20, 13, 128, 64), (5, 3, 14, 14, 96, 128),
+                                   (2, 1, 28, 28, 144, 64), (2, 2, 28, 28, 80, 48)])
 def test_frame_ring_and_im2col_kernels_agree(cuda_device, lib, shape):
-    """K1t (frame ring: every frame block loaded once, taps = ring slots) and K1 (im2col) are two schedules of the same
-    3x1x1 convolution (with residual + ReLU + statistics): equal up to fp32 summation order."""
+    """K1t (frame ring, one channel block) / K1i (input-stationary, several channel blocks) and K1 (im2col) are
+    schedules of the same 3x1x1 convolution (with residual + ReLU + statistics): equal up to fp32 summation order."""
     import torch
     from fastvideotagging_b200 import ops
     n, t, h, w_, cin, cout = shape
@@ -90,12 +92,13 @@ def test_frame_ring_and_im2col_kernels_agree(cuda_device, lib, shape):
     wp = ops.pack_conv_weight(d, w)
     st_ring = torch.zeros(2 * cout, device=cuda_device)
     y_ring = ops.conv3d_fwd(d, x, wp, sc, sh, res, stats=st_ring)
-    assert lib.fvt_set_option(b"disable_frame_ring", 1) == 0
+    assert lib.fvt_set_option(b"disable_frame_ring", 1) == 0 and lib.fvt_set_option(b"disable_temporal_is", 1) == 0
     try:
         st_gen = torch.zeros(2 * cout, device=cuda_device)
         y_gen = ops.conv3d_fwd(d, x, wp, sc, sh, res, stats=st_gen)
     finally:
         lib.fvt_set_option(b"disable_frame_ring", 0)
+        lib.fvt_set_option(b"disable_temporal_is", 0)
     torch.cuda.synchronize()
     scale = y_gen.float().abs().max().item()
     assert (y_ring.float() - y_gen.float()).abs().max().item() <= 2 ** -7 * scale
