@@ -57,6 +57,7 @@ static int g_ring_prefetch = 4;  // fvt_set_option("ring_prefetch", f): K1t L2 p
 static int g_disable_ring = 0;   // fvt_set_option("disable_frame_ring", 1): temporal convs go through K1 (im2col)
 static int g_slab_single_stage = 1;   // fvt_set_option("slab_single_stage", 0): keep two input stages even with a shallow weight ring
 static int g_disable_tis = 0;    // fvt_set_option("disable_temporal_is", 1): no input-stationary temporal kernel (K1i)
+static int g_disable_splitk = 0; // fvt_set_option("disable_split_k", 1): K1 never splits the reduction
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -466,6 +467,7 @@ int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_frame_ring") == 0) { g_disable_ring = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_single_stage") == 0) { g_slab_single_stage = value; return 0; }
   if (name != nullptr && strcmp(name, "disable_temporal_is") == 0) { g_disable_tis = value; return 0; }
+  if (name != nullptr && strcmp(name, "disable_split_k") == 0) { g_disable_splitk = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_box_rows") == 0) { g_slab_box_rows = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_prefetch") == 0) { g_slab_prefetch = value; return 0; }
   if (name != nullptr && strcmp(name, "debug_flags") == 0) { g_debug_flags = value & (kDbgNoStore | kDbgNoEpilogue); return 0; }
@@ -552,7 +554,8 @@ int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int
 }
 
 int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
-                   const float* shift, const void* residual, void* y, float* stats, void* stream) {
+                   const float* shift, const void* residual, void* y, float* stats, void* workspace,
+                   size_t workspace_bytes, void* stream) {
   if (int e = validate_conv(d)) return e;
   if (x == nullptr || w_packed == nullptr || y == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if ((scale == nullptr) != (shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "scale and shift must be given together");
@@ -802,6 +805,27 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   p.stages = stages;
   const int smem_bytes = 1024 + b_region + stages * stage_bytes + kAuxBytes;
 
+  // split-K: a small-M convolution (conv4_x/conv5_x at a few clips per GPU) has fewer tiles than SMs and a long
+  // reduction; splitting K over several CTAs fills the machine.  Needs the caller's zeroed fp32 workspace.
+  p.k_splits = 1;
+  p.kb_per_split = taps * p.cin_blocks;
+  {
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int k_blocks = taps * p.cin_blocks;
+    const size_t need = (size_t)p.m_total * d->cout * sizeof(float);
+    if (!g_disable_splitk && !p.b_stationary && workspace != nullptr && workspace_bytes >= need && ((uintptr_t)workspace & 15) == 0 &&
+        2 * tiles <= di->sm_count && k_blocks >= 8) {
+      int splits = di->sm_count / tiles;
+      if (splits > k_blocks / 4) splits = k_blocks / 4;
+      if (splits > 8) splits = 8;
+      if (splits >= 2) {
+        p.kb_per_split = (k_blocks + splits - 1) / splits;
+        p.k_splits = (k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+        p.ws = (float*)workspace;
+      }
+    }
+  }
+
   CUtensorMap tmx, tmw;
   if (int e = encode_x_map(di, d, x, &tmx)) return e;
   if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
@@ -814,10 +838,14 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_fwd_kernel): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < di->sm_count ? tiles : di->sm_count;
   conv_igemm_fwd_kernel<<<grid, kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p);
-  return check_launch("conv_igemm_fwd_kernel");
+  if (int e = check_launch("conv_igemm_fwd_kernel")) return e;
+  if (p.k_splits > 1)
+    return launch_splitk_finalize(p.ws, scale, shift, (d->flags & FVT_CONV_RESIDUAL) ? residual : nullptr, y, (d->flags & FVT_CONV_STATS) ? stats : nullptr,
+                                  (size_t)p.m_total, d->cout, (d->flags & FVT_CONV_RELU) ? 1 : 0, (cudaStream_t)stream);
+  return 0;
 }
 
 

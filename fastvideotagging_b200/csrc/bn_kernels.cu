@@ -331,6 +331,68 @@ sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tensors, const unsigned 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ split-K finalize
+// ws [rows, C] fp32 holds the summed partial tiles of a split-K convolution (conv_igemm.cuh).  This pass is the
+// convolution's epilogue: y = bf16( relu?( ws*scale + shift  + residual ) ), optional per-channel (sum, sum^2) of the
+// bf16-rounded raw output for training BatchNorm; it also writes zeros back so the workspace is clean for the next call.
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(float4* __restrict__ ws, const float* __restrict__ scale, const float* __restrict__ shift,
+                       const uint4* __restrict__ res, uint4* __restrict__ y, float* __restrict__ stats, size_t rows, int cvec,
+                       int c_store, int relu) {
+  extern __shared__ float sred[];                    // [blockDim.x][16] (statistics only)
+  const int tpr = blockDim.x / cvec;
+  const int cv = threadIdx.x % cvec;
+  const int rsub = threadIdx.x / cvec;
+  float sc[8], sh[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale != nullptr ? scale[cv * 8 + i] : 1.f;
+    sh[i] = shift != nullptr ? shift[cv * 8 + i] : 0.f;
+    s1[i] = 0.f; s2[i] = 0.f;
+  }
+  if (rsub < tpr) {
+    for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
+      const size_t idx = r * cvec + cv;
+      const float4 a = ws[2 * idx], b = ws[2 * idx + 1];
+      ws[2 * idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ws[2 * idx + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      if (stats != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float q = __bfloat162float(__float2bfloat16_rn(v[i]));
+          s1[i] += q; s2[i] = fmaf(q, q, s2[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+      if (res != nullptr) {
+        float q[8];
+        unpack8(__ldg(res + idx), q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += q[i];
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      y[idx] = pack8(v);
+    }
+  }
+  if (stats != nullptr) {
+    float* mine = sred + threadIdx.x * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mine[i] = s1[i]; mine[8 + i] = s2[i]; }
+    __syncthreads();
+    for (int o = threadIdx.x; o < cvec * 16; o += blockDim.x) {
+      const int v = o / 16, k = o % 16;
+      float s = 0.f;
+      for (int t = 0; t < tpr; ++t) s += sred[(t * cvec + v) * 16 + k];
+      atomicAdd(stats + (k < 8 ? 0 : c_store) + v * 8 + (k & 7), s);
+    }
+  }
+}
+
 static int rows_launch(size_t rows, int cvec, int* blocks, int* threads) {
   // blockDim multiple of cvec (thread -> fixed channel vector), <= 256 threads when possible
   int tpr = 256 / cvec;
@@ -343,6 +405,18 @@ static int rows_launch(size_t rows, int cvec, int* blocks, int* threads) {
   if (b < 1) b = 1;
   *blocks = static_cast<int>(b);
   return 0;
+}
+
+int launch_splitk_finalize(float* ws, const float* scale, const float* shift, const void* residual, void* y, float* stats,
+                           size_t rows, int c_store, int relu, cudaStream_t stream) {
+  int blocks, threads;
+  if (c_store % 8 || rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "split-K finalize: bad channel count");
+  // one row per thread per iteration here: rows_launch sized the grid for kUnroll rows per iteration
+  size_t b = (rows + (threads / (c_store / 8)) - 1) / (threads / (c_store / 8));
+  if (b > 148 * 8) b = 148 * 8;
+  splitk_finalize_kernel<<<static_cast<int>(b), threads, stats ? threads * 16 * sizeof(float) : 0, stream>>>(
+      reinterpret_cast<float4*>(ws), scale, shift, (const uint4*)residual, (uint4*)y, stats, rows, c_store / 8, c_store, relu);
+  return check_launch("splitk_finalize_kernel");
 }
 
 }  // namespace fvt

@@ -45,6 +45,9 @@ struct ConvKernelParams {
   int cout_store;         // channel pitch of Y / residual (elements)
   int flags;
   int stages;
+  int k_splits;           // > 1: split-K — item = (tile, split); partial sums are added into `ws` (fp32), no epilogue math
+  int kb_per_split;
+  float* ws;              // [m_total][cout_store] fp32, zero on entry (split-K only)
   int b_stationary;       // 1: all taps*cin_blocks weight tiles are loaded once and stay in shared memory
   const float* scale;     // [cout_store] or nullptr (identity)
   const float* shift;     // [cout_store] or nullptr
@@ -115,7 +118,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;     // work items (tile x K split)
 
   if (warp == 0) {
     // ===================================================== TMA producer (warp-uniform loop, elected lane issues)
@@ -133,7 +136,9 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / p.k_splits;
+        const int split = item - tile * p.k_splits;
         const int m_blk = tile / p.num_n_tiles;
         const int n_blk = tile - m_blk * p.num_n_tiles;
         int m0 = m_blk * kBlockM;
@@ -145,27 +150,28 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int ch = oh * p.sh - p.ph;
         const int cd = ot * p.st - p.pt;
         const int n0 = n_blk * p.block_n;
-        for (int dt = 0; dt < p.kt; ++dt) {
-          for (int dh = 0; dh < p.kh; ++dh) {
-            for (int dw = 0; dw < p.kw; ++dw) {
-              const int tap = (dt * p.kh + dh) * p.kw + dw;
-              for (int cb = 0; cb < p.cin_blocks; ++cb) {
-                ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
-                const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-                uint8_t* a_dst = smem_tiles + stage * stage_bytes;
-                if (ptx::elect_one()) {
-                  ptx::mbar_arrive_expect_tx(fb, stage_bytes);
-                  ptx::tma_load_im2col_5d(ptx::smem_u32(a_dst), &tmap_x, fb, cb * kBlockK, cw, ch, cd, on,
-                                          static_cast<uint16_t>(dw), static_cast<uint16_t>(dh),
-                                          static_cast<uint16_t>(dt));
-                  if (!p.b_stationary)
-                    ptx::tma_load_2d(ptx::smem_u32(a_dst + kATileBytes), &tmap_w, fb,
-                                     tap * p.k_per_tap + cb * kBlockK, n0);
-                }
-                __syncwarp();
-                if (++stage == stages) { stage = 0; phase ^= 1; }
-              }
-            }
+        // this item's k-block range [kb0, kb1) and the filter position of kb0
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = kb0 + p.kb_per_split < k_blocks ? kb0 + p.kb_per_split : k_blocks;
+        int cb = kb0 % p.cin_blocks;
+        int tap = kb0 / p.cin_blocks;
+        int dw = tap % p.kw, dh = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+          uint8_t* a_dst = smem_tiles + stage * stage_bytes;
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+            ptx::tma_load_im2col_5d(ptx::smem_u32(a_dst), &tmap_x, fb, cb * kBlockK, cw, ch, cd, on,
+                                    static_cast<uint16_t>(dw), static_cast<uint16_t>(dh), static_cast<uint16_t>(dt));
+            if (!p.b_stationary)
+              ptx::tma_load_2d(ptx::smem_u32(a_dst + kATileBytes), &tmap_w, fb, tap * p.k_per_tap + cb * kBlockK, n0);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++cb == p.cin_blocks) {
+            cb = 0; ++tap;
+            if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
           }
         }
       }
@@ -193,20 +199,23 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       int acc = 0;
       uint32_t acc_phase = 0;
       if (p.b_stationary && blockIdx.x < num_tiles) ptx::mbar_wait(ptx::smem_u32(b_full_bar), 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
         ptx::mbar_wait(ptx::smem_u32(&acc_empty_bar[acc]), acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        int cb = 0;
-        uint64_t b_stat = b_stat0;
-        for (int kb = 0; kb < k_blocks; ++kb, b_stat += b_step) {
+        const int split = item % p.k_splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = kb0 + p.kb_per_split < k_blocks ? kb0 + p.kb_per_split : k_blocks;
+        int cb = kb0 % p.cin_blocks;
+        uint64_t b_stat = b_stat0 + static_cast<uint32_t>(kb0) * b_step;
+        for (int kb = kb0; kb < kb1; ++kb, b_stat += b_step) {
           const int k16 = (cb == p.cin_blocks - 1) ? last_k16 : kBlockK / 16;
           ptx::mbar_wait(full_u32 + stage * 8, phase);
           ptx::tc_fence_after();
           const uint64_t b_desc = p.b_stationary ? b_stat : a_desc + b_in_stage;
           if (ptx::elect_one()) {
             // +32 bytes (16 bf16) along K inside the swizzle atom == +2 in the (addr >> 4) field
-            ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, kb != 0);
+            ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, kb != kb0);
             if (k16 > 1) ptx::umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
             if (k16 > 2) ptx::umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
             if (k16 > 3) ptx::umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
@@ -232,12 +241,38 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     const bool do_stats = (p.flags & kConvStats) != 0;
     const bool has_affine = p.scale != nullptr;
     const int et = threadIdx.x - 128;           // 0..255
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int tile = item / p.k_splits;
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile - m_blk * p.num_n_tiles;
       const int n0 = n_blk * p.block_n;
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.m_total;
+      if (p.k_splits > 1) {
+        // split-K: add this item's fp32 partial tile into the workspace (vector reductions, 16 bytes each); the
+        // epilogue math runs in splitk_finalize_kernel once all splits have landed
+        ptx::mbar_wait(ptx::smem_u32(&acc_full_bar[acc]), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+        float* wrow = p.ws + static_cast<size_t>(row_ok ? row : 0) * p.cout_store + n0;
+        for (int c = grp * 16; c < p.block_n; c += 32) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(taddr + c, v);
+          ptx::tmem_ld_wait();
+          if (row_ok && n0 + c < p.cout_store) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c + 4 * i), "f"(__uint_as_float(v[4 * i])),
+                           "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
+                           : "memory");
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty_bar[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       if (do_stats) {
         for (int i = et; i < 512; i += kEpilogueThreads) stat_smem[i] = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -14,5 +14,8 @@ int check_launch(const char* what);
 const DeviceInfo* current_device_info(int* status);
 const DeviceInfo* device_info(int device, int* status);
 int sm_count_of(const DeviceInfo* di);
+// Epilogue pass of a split-K convolution (bn_kernels.cu): ws fp32 -> y bf16 (+ stats), leaves ws zeroed.
+int launch_splitk_finalize(float* ws, const float* scale, const float* shift, const void* residual, void* y, float* stats,
+                           size_t rows, int c_store, int relu, cudaStream_t stream);
 
 }  // namespace fvt

@@ -51,6 +51,21 @@ def pack_conv_weight(desc, w_oidhw, out=None):
     return out
 
 
+_WORKSPACE = {}
+WORKSPACE_BYTES = 64 << 20
+
+
+def workspace(device):
+    """Per-device zeroed fp32 scratch handed to fvt_conv3d_fwd (split-K of small-M convolutions).  The library keeps it
+    zeroed, so it is allocated and cleared exactly once."""
+    key = (device.type, device.index)
+    ws = _WORKSPACE.get(key)
+    if ws is None:
+        ws = torch.zeros(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
+        _WORKSPACE[key] = ws
+    return ws
+
+
 def conv3d_fwd(desc, x, w_packed, scale=None, shift=None, residual=None, out=None, stats=None):
     """x: (N, T, H, W, Cin) bf16 contiguous -> (N, To, Ho, Wo, Cout) bf16."""
     lib = _lib.load()
@@ -60,8 +75,9 @@ def conv3d_fwd(desc, x, w_packed, scale=None, shift=None, residual=None, out=Non
     to, ho, wo = conv_out_shape(desc)
     if out is None:
         out = torch.empty((desc.n, to, ho, wo, desc.cout), dtype=torch.bfloat16, device=x.device)
+    ws = workspace(x.device)
     check(lib.fvt_conv3d_fwd(ctypes.byref(desc), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(residual),
-                             _ptr(out), _ptr(stats), _stream()))
+                             _ptr(out), _ptr(stats), _ptr(ws), ws.numel() * 4, _stream()))
     return out
 
 

@@ -59,7 +59,7 @@ int fvt_device_check(int device);
 /* Tuning/debug switches (A/B runs and tests): "disable_slab" = 1 routes every convolution through the generic im2col
  * kernel (K1); "disable_frame_ring" / "disable_temporal_is" = 1 do the same for the temporal kernels (K1t / K1i) only; "disable_b_stationary" = 1 makes K1
  * stream its weights; "disable_wgrad_slab" = 1 routes every weight gradient through the im2col kernel (K3);
- * "slab_prefetch" / "slab_box_rows" / "debug_flags" are load-path and epilogue experiments (tools/gpu_*_ab.py). */
+ * "disable_split_k" = 1 keeps small-M convolutions single-pass; "slab_prefetch" / "slab_box_rows" / "debug_flags" are load-path and epilogue experiments (tools/gpu_*_ab.py). */
 int fvt_set_option(const char* name, int value);
 
 /* ---- convolution (K1) ----------------------------------------------------------------------------------- */
@@ -75,9 +75,13 @@ int fvt_pack_conv_weight(const fvt_conv_desc* d, const float* w_oidhw, int32_t c
                          void* w_packed, void* stream);
 /* y = epilogue(conv(x, w)):  acc*scale[c] + shift[c] (if scale != NULL)  (+ residual)  (ReLU)  -> bf16.
  * stats (FVT_CONV_STATS): float[2*cout], sum then sum of squares of the bf16-rounded raw conv output,
- * atomically accumulated — zero it first. */
+ * atomically accumulated — zero it first.
+ * workspace (optional, may be NULL): caller-owned fp32 scratch of workspace_bytes, ALL ZERO on entry and left all zero
+ * on return.  With >= M*cout*4 bytes it lets small-M convolutions (fewer output tiles than SMs) split their reduction
+ * over several CTAs (split-K + one finalize pass); without it every convolution runs single-pass. */
 int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
-                   const float* shift, const void* residual, void* y, float* stats, void* stream);
+                   const float* shift, const void* residual, void* y, float* stats, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* ---- stem input transform --------------------------------------------------------------------------------- */
 /* Clips in the reference layout NCDHW fp32 (data/data.py:46-47) with 3 channels -> W-unfolded NDHWC bf16

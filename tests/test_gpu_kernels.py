@@ -105,6 +105,41 @@ def test_frame_ring_and_im2col_kernels_agree(cuda_device, lib, shape):
     assert (st_ring - st_gen).abs().max().item() <= 1e-3 * st_gen.abs().max().item()
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 7, 7, 512, 1152, (1, 3, 3), (0, 1, 1)), (4, 4, 7, 7, 1152, 512, (3, 1, 1), (1, 0, 0)),
+                                   (1, 8, 14, 14, 576, 256, (3, 1, 1), (1, 0, 0)), (1, 3, 5, 9, 256, 80, (1, 3, 3), (0, 1, 1))])
+def test_split_k_matches_single_pass(cuda_device, lib, shape):
+    """Small-M convolutions split their reduction over several CTAs (fp32 partials in the caller's workspace + one
+    finalize pass).  Same result as the single-pass kernel up to fp32 summation order, for both epilogue flavours; the
+    workspace is left zeroed."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w_, cin, cout, k, pad = shape
+    torch.manual_seed(8)
+    x = (torch.randn(n, t, h, w_, cin) * 0.5).to(torch.bfloat16).to(cuda_device)
+    res = (torch.randn(n, t, h, w_, cout) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = torch.randn(cout, cin, *k, device=cuda_device) / (cin * k[0] * k[1] * k[2]) ** 0.5
+    sc = torch.rand(cout, device=cuda_device) + 0.5
+    sh = torch.randn(cout, device=cuda_device) * 0.1
+    outs = {}
+    for split in (1, 0):
+        assert lib.fvt_set_option(b"disable_split_k", 0 if split else 1) == 0
+        try:
+            d1 = ops.conv_desc(n, t, h, w_, cin, cout, k, (1, 1, 1), pad, ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+            wp = ops.pack_conv_weight(d1, w)
+            y1 = ops.conv3d_fwd(d1, x, wp, sc, sh, res)
+            d2 = ops.conv_desc(n, t, h, w_, cin, cout, k, (1, 1, 1), pad, ops.FVT_CONV_STATS)
+            st = torch.zeros(2 * cout, device=cuda_device)
+            y2 = ops.conv3d_fwd(d2, x, wp, stats=st)
+            torch.cuda.synchronize()
+            outs[split] = (y1.float(), y2.float(), st.clone())
+        finally:
+            lib.fvt_set_option(b"disable_split_k", 0)
+    assert float(ops.workspace(cuda_device).abs().max()) == 0.0
+    for a, b in zip(outs[1][:2], outs[0][:2]):
+        assert (a - b).abs().max().item() <= 2 ** -7 * b.abs().max().item()
+    assert (outs[1][2] - outs[0][2]).abs().max().item() <= 2e-3 * outs[0][2].abs().max().item()
+
+
 def test_wgrad_slab_and_im2col_kernels_agree(cuda_device, lib):
     """K3s (slab, stacked taps) and K3 (im2col) compute the same weight gradient up to fp32 summation order."""
     import torch
