@@ -75,6 +75,12 @@ def load():
         "fvt_pool_fc_bwd": (ctypes.c_int, [fp, fp, fp, i32, i32, i32, i32, fp, fp, vp, i32, vp]),
         "fvt_sgd_momentum_multi": (ctypes.c_int, [vp, vp, vp, i32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                                   ctypes.c_float, vp]),
+        "fvt_clip_stats_u8": (ctypes.c_int, [vp, ctypes.c_int64, vp, vp]),
+        "fvt_clip_normalize_u8": (ctypes.c_int, [vp, vp, fp, i32, i32, i32, i32, ctypes.c_float,
+                                                 ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]),
+        "fvt_softmax_accumulate": (ctypes.c_int, [fp, fp, i32, i32, vp]),
+        "fvt_argmax_correct": (ctypes.c_int, [fp, vp, i32, i32, vp, vp, vp]),
+        "fvt_topk_iou": (ctypes.c_int, [fp, fp, i32, i32, i32, vp, vp, vp]),
         "fvt_loss_workspace_bytes": (ctypes.c_size_t, [i32]),
         "fvt_lsep_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, fp, fp, vp, vp]),
         "fvt_warp_fwd_bwd": (ctypes.c_int, [fp, fp, i32, i32, i32, i32, i32, ctypes.c_uint64, ctypes.c_uint64, fp, fp,

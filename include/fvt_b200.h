@@ -170,6 +170,25 @@ int fvt_bce_fwd_bwd(const float* pred, const float* target, int32_t batch, int32
  * label: float[batch] class indices; grad (optional) = softmax - onehot (un-normalised, as MXNet). */
 int fvt_softmax_fwd_bwd(const float* logits, const float* label, int32_t batch, int32_t num_class, int32_t mode,
                         float* out, float* grad, void* stream);
+/* ---- rows next to the hot path ----------------------------------------------------------------- */
+/* N2, clip pre-processing (videos_reader.py:69-76,93-97; data/ucf101.py:124-128).
+ * clips_nthwc: decoded uint8 frames (N, T, H, W, 3).  fvt_clip_stats_u8: sums6 = [sum x (3 channels), sum x^2 (3)] over all
+ * `pixels` = N*T*H*W pixels (exact integers; overwritten).  fvt_clip_normalize_u8:
+ * out[n, c, t, h, w] = (clips[n, t, h, w', c]*scale - mean[c]) * inv_std[c] in the reference's NCDHW fp32 layout, with
+ * w' = W-1-w for clips whose flip[n] != 0 (flip may be NULL).  mean / inv_std are HOST arrays of 3 floats. */
+int fvt_clip_stats_u8(const uint8_t* clips_nthwc, int64_t pixels, uint64_t* sums6, void* stream);
+int fvt_clip_normalize_u8(const uint8_t* clips_nthwc, const uint8_t* flip, float* out_ncdhw, int32_t n, int32_t t, int32_t h,
+                          int32_t w, float scale, const float mean[3], const float inv_std[3], void* stream);
+/* N3, evaluation tail.  acc[rows, C] += softmax(logits[rows, C]) (validation.py:49-51);
+ * pred[row] = argmax acc[row] (first maximum), *correct += number of rows with pred == labels (validation.py:61-63). */
+int fvt_softmax_accumulate(const float* logits, float* acc, int32_t rows, int32_t num_class, void* stream);
+int fvt_argmax_correct(const float* acc, const int32_t* labels, int32_t rows, int32_t num_class, int32_t* pred,
+                       uint64_t* correct, void* stream);
+/* Top-k IoU counts (train_simple_r3d.py:169-193): per row the k largest scores in `argsort()[:, ::-1]` order (ties: larger
+ * index first), labels = {j : target > 0.1}; inter[k-1] += |top_k & labels|, uni[k-1] += |top_k | labels|, k = 1..k_max <= 4.
+ * The caller zeroes inter / uni and adds the reference's 1e-4 offsets when forming the ratio. */
+int fvt_topk_iou(const float* scores, const float* target, int32_t rows, int32_t num_class, int32_t k_max, uint64_t* inter,
+                 uint64_t* uni, void* stream);
 /* Host-side Philox4x32-10 block (same code the device uses) for known-answer tests. */
 int fvt_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 
