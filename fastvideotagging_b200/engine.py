@@ -350,7 +350,7 @@ class TrainPlan:
         for L in self.layers.values():
             if L.strided and L.need_dgrad:
                 up_elems = max(up_elems, L.fwd.n * L.fwd.t * L.fwd.h * L.fwd.w * L.cout_s)
-        for nm in ("gA", "gB", "draw", "gmask", "gshort", "draw_s"):
+        for nm in ("gA", "gB", "draw0", "draw1", "draw2", "gmask", "gshort", "draw_s"):
             buf(nm, (max_elems,))
         buf("up", (up_elems,))
         self.pooled = None
@@ -364,23 +364,59 @@ class TrainPlan:
         self._logits_static = None
         self._warm_fwd = self._warm_bwd = 0
         self.finish_hook = None          # callable(): wait for gradient reductions launched by grad_hook
+        # Second stream (a parallel branch of the captured graphs): weight re-packing runs beside the first forward
+        # layers, and every weight gradient runs beside the data-gradient chain it does not feed.  At batch 4 the
+        # conv4_x / conv5_x launches fill 14-49 of the 148 SMs, so the two branches genuinely overlap.
+        self.side = torch.cuda.Stream(device=device) if os.environ.get("FVT_SIDE_STREAM", "1") != "0" else None
+        self._packed_ev = {}
+        self._busy = {}                  # scratch buffer name -> event recorded after its last reader on the side stream
+        self._draw_i = 0
 
     # ------------------------------------------------------------------ weights
     def _w(self, L):
         return self.flat.view(self.flat.w, L.w_name)
 
     def refresh_weights(self, version):
-        """Re-pack bf16 operand copies of the fp32 master weights (forward and data-gradient layouts)."""
+        """Re-pack bf16 operand copies of the fp32 master weights (forward and data-gradient layouts).  With the side
+        stream the packing launches form a branch parallel to the forward pass: forward-layout copies in layer order
+        (each conv waits for its own copy only, `_wait_packed`), then the data-gradient copies, joined by
+        `_join_side()` at the end of the forward pass."""
+        self._packed_ev = {}
         if version == self.weights_version:
             return
-        for L in self.layers.values():
-            w = self._w(L)
-            if L is self.stem0:
-                w = stem_equivalent_weight(w)
-            L.wp = ops.pack_conv_weight(L.fwd, w, out=L.wp)               # packed buffers are allocated once
-            if L.need_dgrad:
-                L.wpd = ops.pack_conv_weight_dgrad(L.dgr, w, out=L.wpd)
+        main = torch.cuda.current_stream(self.device)
+        if self.side is None:
+            for L in self.layers.values():
+                w = self._w(L)
+                if L is self.stem0:
+                    w = stem_equivalent_weight(w)
+                L.wp = ops.pack_conv_weight(L.fwd, w, out=L.wp)               # packed buffers are allocated once
+                if L.need_dgrad:
+                    L.wpd = ops.pack_conv_weight_dgrad(L.dgr, w, out=L.wpd)
+        else:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                for L in self.layers.values():
+                    w = self._w(L)
+                    if L is self.stem0:
+                        w = stem_equivalent_weight(w)
+                    L.wp = ops.pack_conv_weight(L.fwd, w, out=L.wp)
+                    ev = torch.cuda.Event()
+                    ev.record(self.side)
+                    self._packed_ev[L.spec.name] = ev
+                for L in reversed(list(self.layers.values())):
+                    if L.need_dgrad:
+                        L.wpd = ops.pack_conv_weight_dgrad(L.dgr, self._w(L), out=L.wpd)
         self.weights_version = version
+
+    def _wait_packed(self, L):
+        ev = self._packed_ev.pop(L.spec.name, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _join_side(self):
+        if self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
 
     # ------------------------------------------------------------------ forward
     def _bn_names(self, L):
@@ -388,6 +424,7 @@ class TrainPlan:
 
     def _conv_bn(self, L, src):
         gname, bname, mname, vname = self._bn_names(L)
+        self._wait_packed(L)
         ops.conv3d_fwd(L.fwd, src, L.wp, out=L.raw, stats=L.stats)
         ops.bn_finalize(L.stats, self.flat.view(self.flat.w, gname), self.flat.view(self.flat.w, bname),
                         self.aux[mname], self.aux[vname], L.cout_s, L.rows, self.eps, self.momentum,
@@ -400,20 +437,25 @@ class TrainPlan:
         if not self.use_graphs:
             self.refresh_weights(weights_version)
             self.flat.g.zero_()
-            return self._forward_body(x.contiguous())
+            out = self._forward_body(x.contiguous())
+            self._join_side()
+            return out
         self.x_static.copy_(x)
         if self._fwd_graph is None:
             if self._warm_fwd < 1:                      # first call: eager (one-time initialisation inside the library)
                 self._warm_fwd += 1
                 self.refresh_weights(weights_version)
                 self.flat.g.zero_()
-                return self._forward_body(self.x_static)
+                out = self._forward_body(self.x_static)
+                self._join_side()
+                return out
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.weights_version = -1               # the graph always re-packs: weights change every step
                 self.refresh_weights(0)
                 self.flat.g.zero_()
                 self._logits_static = self._forward_body(self.x_static)
+                self._join_side()
             self._fwd_graph = graph
         self._fwd_graph.replay()
         return self._logits_static.clone()
@@ -466,7 +508,32 @@ class TrainPlan:
         else:
             ops.bn_backward(L.raw, dact, mask, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, dz_out)
 
+    def _draw(self, shape, key=None):
+        """Next raw-gradient scratch buffer (three rotate, so a weight gradient still reading one on the side stream
+        never sees it overwritten); waits for that buffer's last side-stream reader."""
+        if key is None:
+            key = "draw%d" % self._draw_i
+            self._draw_i = (self._draw_i + 1) % 3
+        ev = self._busy.pop(key, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        v = self._view(key, shape)
+        v._fvt_key = key
+        return v
+
     def _wgrad(self, L, x_in, draw):
+        """Weight gradient of L; on the side stream when there is one (it feeds nothing but the gradient buffer)."""
+        if self.side is None:
+            return self._wgrad_now(L, x_in, draw)
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._wgrad_now(L, x_in, draw)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self._busy[draw._fvt_key] = ev
+
+    def _wgrad_now(self, L, x_in, draw):
         if L is self.stem0:
             dweq = torch.zeros((45, 21, 1, 7, 1), dtype=torch.float32, device=self.device)
             ops.conv3d_wgrad(L.fwd, x_in, draw, dweq, 45, 21)
@@ -516,10 +583,10 @@ class TrainPlan:
             xin = B[xin_name]
             other = "gB" if cur_key == "gA" else "gA"
             gmask = self._view("gmask", d.out_shape)
-            draw_d = self._view("draw", d.out_shape)
+            draw_d = self._draw(d.out_shape)
             self._bn_bwd(d, g_cur, d.act, draw_d, dz_out=gmask)           # out = relu(bn2 + shortcut): mask by out > 0
             if sc is not None:
-                draw_s = self._view("draw_s", sc.out_shape)
+                draw_s = self._draw(sc.out_shape, key="draw_s")
                 self._bn_bwd(sc, gmask, None, draw_s)
                 self._wgrad(sc, xin, draw_s)
                 gshort = self._dgrad(sc, draw_s, self._view("gshort", xin_shape))
@@ -527,32 +594,36 @@ class TrainPlan:
                 gshort = gmask
             self._wgrad(d, c.act, draw_d)
             gc = self._dgrad(d, draw_d, self._view(other, c.out_shape))
-            draw_c = self._view("draw", c.out_shape)
+            draw_c = self._draw(c.out_shape)
             self._bn_bwd(c, gc, True, draw_c)
             self._wgrad(c, b.act, draw_c)
             gb = self._dgrad(c, draw_c, self._view(cur_key, b.out_shape))
-            draw_b = self._view("draw", b.out_shape)
+            draw_b = self._draw(b.out_shape)
             self._bn_bwd(b, gb, True, draw_b)
             self._wgrad(b, a.act, draw_b)
             ga = self._dgrad(b, draw_b, self._view(other, a.out_shape))
-            draw_a = self._view("draw", a.out_shape)
+            draw_a = self._draw(a.out_shape)
             self._bn_bwd(a, ga, True, draw_a)
             self._wgrad(a, xin, draw_a)
             g_cur = self._dgrad(a, draw_a, self._view(cur_key, xin_shape), residual=gshort)
             names = []
             for L in (a, b, c, d) + ((sc,) if sc is not None else ()):
                 names += [L.w_name, L.spec.bn + "_gamma", L.spec.bn + "_beta"]
+            if self.grad_hook is not None:
+                self._join_side()                 # the block's weight gradients must be final before they are reduced
             self._ready(*names)
         # stem
         other = "gB" if cur_key == "gA" else "gA"
-        draw1 = self._view("draw", self.stem1.out_shape)
+        draw1 = self._draw(self.stem1.out_shape)
         self._bn_bwd(self.stem1, g_cur, True, draw1)
         self._wgrad(self.stem1, self.stem0.act, draw1)
         g0 = self._dgrad(self.stem1, draw1, self._view(other, self.stem0.out_shape))
-        draw0 = self._view("draw", self.stem0.out_shape)
+        draw0 = self._draw(self.stem0.out_shape)
         self._bn_bwd(self.stem0, g0, True, draw0)
         self._wgrad(self.stem0, self.unfold, draw0)
         names = []
         for L in (self.stem0, self.stem1):
             names += [L.w_name, L.spec.bn + "_gamma", L.spec.bn + "_beta"]
+        self._join_side()
+        self._busy.clear()
         self._ready(*names)
