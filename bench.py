@@ -23,6 +23,7 @@ GFLOP_PER_CLIP_TRAIN = 912.8            # fwd + dgrad + wgrad, minus the stem dg
 TRAIN_BATCH_PER_GPU = 4                 # BASELINE configs[2]
 MODEL_DEPTH, NUM_CLASS, T, HW = 34, 101, 32, 112
 BATCH_PER_GPU = 48
+C4_BATCH_PER_GPU, C4_T, C4_NUM_CLASS = 16, 16, 63     # BASELINE configs[3] (Meitu shape, train_simple_r3d.py:336,341)
 
 
 def load_peaks():
@@ -288,13 +289,60 @@ def run_ours(args, rank, world, local_rank):
         tplan = list(net._train_plans.values())[0]
         train = {"ms": ms_train, "loss": float(last.item()), "batch": tb}
 
+    # ---------------- BASELINE configs[3]: 63-tag multi-label heads (LSEP, WARP), Meitu-shape clips 16x112x112,
+    # batch 16/GPU, same fwd + bwd + all-reduce + SGD step with the ranking loss kernels in the loop
+    c4 = None
+    if not args.no_train and not args.no_c4:
+        from fastvideotagging_b200.model import LsepLoss, WarpLoss
+        from fastvideotagging_b200.trainer import Trainer
+        from oracle import r2plus1d as orc
+        cb, ct, cc = C4_BATCH_PER_GPU, C4_T, C4_NUM_CLASS
+        net4 = R2Plus2D(cc, MODEL_DEPTH, final_spatial_kernel=HW // 16, final_temporal_kernel=ct // 8).to(dev)
+        net4.load_param_dict(orc.randomize_bn(orc.init_params(MODEL_DEPTH, cc, seed=0), seed=1))
+        net4.train()
+        trainer4 = Trainer(net4, "sgd", {"learning_rate": 1e-4, "momentum": 0.9, "wd": 1e-4}, kvstore="device")
+        import numpy as np
+        rng = np.random.default_rng(11 + rank)
+        x4 = torch.from_numpy(rng.random((cb, 3, ct, HW, HW), dtype=np.float32)).to(dev)
+        lab4 = np.zeros((cb, cc), np.float32)
+        for r in range(cb):                                   # 1-4 tags per clip, every row keeps negatives
+            lab4[r, rng.choice(cc, size=int(rng.integers(1, 5)), replace=False)] = 1
+        lab4 = torch.from_numpy(lab4).to(dev)
+        c4 = {"batch": cb}
+        for tag, crit4 in (("lsep", LsepLoss()), ("warp", WarpLoss(auto_advance=False))):
+            state = {"i": 0}
+
+            def c4_step():
+                if tag == "warp":                              # global sample index: ranks independent of the GPU count
+                    crit4.sample_offset = (state["i"] * world + rank) * cb
+                state["i"] += 1
+                loss = crit4(net4(x4), lab4).sum()
+                loss.backward()
+                trainer4.step(cb * world)
+                return loss
+
+            for _ in range(3):
+                c4_step()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                last4 = c4_step()
+            b.record()
+            barrier()
+            c4[tag] = {"ms": a.elapsed_time(b), "loss": float(last4.item())}
+        note("configs[3] done")
+
     # max over ranks
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e, train["ms"] if train else 0.0], device=dev)
+        tt = torch.tensor([ms, ms_e2e, train["ms"] if train else 0.0, c4["lsep"]["ms"] if c4 else 0.0,
+                           c4["warp"]["ms"] if c4 else 0.0], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = tt[0].item(), tt[1].item()
         if train:
             train["ms"] = tt[2].item()
+        if c4:
+            c4["lsep"]["ms"], c4["warp"]["ms"] = tt[3].item(), tt[4].item()
 
     if rank == 0:
         clips = batch * world * args.steps
@@ -349,6 +397,15 @@ def run_ours(args, rank, world, local_rank):
                                  train["batch"], "NCCL all-reduce bucketed+overlapped" if world > 1 else "single GPU"),
                              "gflop_per_clip": GFLOP_PER_CLIP_TRAIN,
                              "frac_of_tensor_peak": tv * GFLOP_PER_CLIP_TRAIN / 1e3 / world / peaks["tflops"]}
+        if c4:
+            line["train_multilabel"] = {
+                "config": "BASELINE configs[3]: R(2+1)D-34, 63 tags, 16x112x112 clips, batch %d/GPU, fwd+bwd+SGD" % c4["batch"],
+                "gflop_per_clip": GFLOP_PER_CLIP_TRAIN / 2}
+            for tag in ("lsep", "warp"):
+                v = c4["batch"] * world * args.steps / (c4[tag]["ms"] / 1e3)
+                line["train_multilabel"][tag] = {
+                    "value": v, "unit": "clips/s", "ms_per_step": c4[tag]["ms"] / args.steps, "final_loss": c4[tag]["loss"],
+                    "frac_of_tensor_peak": v * GFLOP_PER_CLIP_TRAIN / 2 / 1e3 / world / peaks["tflops"]}
         emit(line)
         if args.layer_table:
             with open(args.layer_table, "w") as fh:
@@ -361,6 +418,8 @@ def run_ours(args, rank, world, local_rank):
         sys.stdout.flush()
         net._train_plans.clear()
         net._plans.clear()
+        if c4:
+            net4._train_plans.clear()
         import gc
         gc.collect()
         torch.cuda.synchronize()
@@ -386,6 +445,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] (LSEP/WARP, batch 16) training measurement")
     ap.add_argument("--layer-table", default=None, help="write per-layer K1 times (csv)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -7,10 +7,11 @@ layout.  All arithmetic happens in libfvt_b200.so; there is no eager/CPU fallbac
 """
 import math
 import os
+import pickle
 
 import torch
 
-from .. import engine
+from .. import engine, params_io
 from ..engine import BLOCK_CONFIG, middle_filters  # noqa: F401  (BLOCK_CONFIG re-exported like the reference)
 
 BN_EPS_GLUON = 1e-5      # nn.BatchNorm() default used throughout model/R2Plus1.py
@@ -166,21 +167,42 @@ class R2Plus2D(torch.nn.Module):
         return missing
 
     def save_parameters(self, filename):
-        torch.save({k: v.detach().cpu() for k, v in self.collect_params().items()}, filename)
+        """gluon `save_parameters` (train_simple_r3d.py:137): an MXNet NDArray-dict file keyed by the symbol-API names."""
+        params_io.nd_save(filename, {k: v.detach().float().cpu().numpy() for k, v in self.collect_params().items()})
 
-    def load_parameters(self, filename, ctx=None):
-        self.load_param_dict(torch.load(filename, map_location="cpu"))
+    def load_parameters(self, filename, ctx=None, allow_missing=False):
+        """gluon `load_parameters` / deprecated `load_params` (train_simple_r3d.py:92,225).  Reads an MXNet NDArray file
+        (plain, or `arg:`/`aux:`-prefixed as written by `do_checkpoint`) or a torch-saved dict."""
+        self.load_param_dict(params_io.load_any(filename), strict=not allow_missing)
         if ctx is not None:
             self.to(ctx[0] if isinstance(ctx, (list, tuple)) else ctx)
 
     load_params = load_parameters   # deprecated gluon alias used at train_simple_r3d.py:92
 
     def load_from_sym_params(self, f, ctx=None, with_dense=False):
-        """Reference model/R2Plus1.py:256-279: load a symbol-API checkpoint, skipping the dense layer unless asked."""
+        """Reference model/R2Plus1.py:256-279: load a symbol-API checkpoint (`prefix-0001.params`), skipping the dense
+        layer unless asked."""
         if not os.path.exists(f):
             print("parameter file is not exist", f)
             return
-        self.load_param_dict(torch.load(f, map_location="cpu"), with_dense=with_dense, strict=True)
+        self.load_param_dict(params_io.load_any(f), with_dense=with_dense, strict=True)
+
+    def load_from_caffe2_pickle(self, f):
+        """Reference model/R2Plus1.py:285-290 opens the Caffe2 R(2+1)D pickle and stops (an unfinished stub); the mapping
+        it was heading for is the one `utils.load_from_caffe2_pkl` applies (utils.py:21-33), used here.  The Kinetics
+        head (`last_out_L400_*`) has no counterpart and the dense layer keeps its initialisation, exactly the
+        "not loaded / not used" outcome the reference logs (r2plus1d_output/log.txt:41-47)."""
+        if not os.path.exists(f):
+            print("parameter file is not exist", f)
+            return None
+        with open(f, "rb") as fh:
+            blobs = pickle.load(fh, encoding="latin1")["blobs"]
+        args_loaded, auxs_loaded = params_io.caffe2_blobs_to_params(blobs)
+        merged = dict(args_loaded)
+        merged.update(auxs_loaded)
+        own = set(self._param_names + self._aux_names)
+        missing = self.load_param_dict({k: v for k, v in merged.items() if k in own}, with_dense=False, strict=False)
+        return {"not_loaded": [m for m in missing], "not_used": sorted(k for k in merged if k not in own)}
 
     def invalidate(self):
         """Call after changing parameters outside of this module's own optimiser hooks."""

@@ -62,3 +62,34 @@ def test_cpu_tensor_is_rejected(cuda_device):
     net = _model(18, 101, (1, 7, 7), params, cuda_device)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 8, 112, 112))
+
+
+def test_full_size_batch48_properties(cuda_device):
+    """BASELINE configs[1] at its full size (R34, 48 clips of 32x112x112) — too big for the oracle as a whole, so the
+    size-independent properties of the path are checked instead: (1) eval-mode logits of a clip do not depend on what
+    else is in the batch (batch 48 vs the same clips run in batches of 1 and 5; the kernels have no cross-clip
+    reduction); (2) permuting the batch permutes the logits; (3) two clips
+    of the batch agree with the oracle at the inference tolerance; (4) every logit is finite."""
+    depth, n, t, hw = 34, 48, 32, 112
+    pool = (t // 8, hw // 16, hw // 16)
+    params = orc.randomize_bn(orc.init_params(depth, 101, seed=0), seed=1)
+    x = _clips(n, t, hw, hw)
+    net = _model(depth, 101, pool, params, cuda_device)
+    xd = torch.from_numpy(x).to(cuda_device)
+    with torch.no_grad():
+        full = net(xd).float().cpu().numpy()
+        one = net(xd[7:8].contiguous()).float().cpu().numpy()
+        five = net(xd[20:25].contiguous()).float().cpu().numpy()
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(0))
+        permuted = net(xd[perm.to(cuda_device)].contiguous()).float().cpu().numpy()
+    assert np.isfinite(full).all()
+    scale_f = np.abs(full).max()
+    # split-K of the small-M layers is chosen per batch size, so the accumulation order may differ between batch sizes
+    assert np.abs(one[0] - full[7]).max() <= 3e-3 * scale_f
+    assert np.abs(five - full[20:25]).max() <= 3e-3 * scale_f
+    assert np.array_equal(permuted, full[perm.numpy()])          # same launches, same per-pixel accumulation order
+    ref, _ = orc.Net(params, depth, pool, bf16_storage=True).forward(x[[7, 41]])
+    ref = ref.numpy()
+    scale = np.abs(ref).max()
+    assert np.abs(full[[7, 41]] - ref).max() <= 5e-3 * scale + 1e-4
+    assert (full[[7, 41]].argmax(1) == ref.argmax(1)).all()

@@ -147,3 +147,41 @@ def test_loss_decreases_over_a_few_steps(cuda_device):
         trainer.step(4)
         losses.append(loss.item())
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_full_size_backward_is_linear_in_the_head_gradient(cuda_device):
+    """BASELINE configs[2] at its full size (R34, 4 clips of 32x112x112): the oracle cannot run it in seconds, so the
+    size-independent property is used — for a fixed forward pass the whole backward (69 BN backwards, dgrads, wgrads,
+    residual joins) is a linear map of dlogits: grad(2 * d) == 2 * grad(d) (a power of two, so the bf16 intermediates scale exactly), and grad(d1 + d2) == grad(d1) + grad(d2)
+    up to fp32 atomics order and the bf16 rounding of the intermediate gradients."""
+    from fastvideotagging_b200.model import SigmoidBinaryCrossEntropyLoss
+    net, params, x, pool = _setup(34, 4, 32, 112, 101, cuda_device)
+    xd = torch.from_numpy(x).to(cuda_device)
+    lab = torch.zeros(4, 101, device=cuda_device)
+    lab[:, 3] = 1
+    loss = SigmoidBinaryCrossEntropyLoss()(net(xd), lab).mean()
+    loss.backward()
+    plan = list(net._train_plans.values())[0]
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    d1 = (torch.randn(4, 101, generator=gen) * 1e-2).to(cuda_device)
+    d2 = (torch.randn(4, 101, generator=gen) * 1e-2).to(cuda_device)
+
+    def grads(d):
+        plan.flat.g.zero_()
+        plan._backward_body(d.contiguous())
+        torch.cuda.synchronize()
+        return plan.flat.g.clone()
+
+    g1, g2, g12, g1s = grads(d1), grads(d2), grads(d1 + d2), grads(2.0 * d1)
+    assert torch.isfinite(g12).all()
+    # compare per parameter tensor, relative to that tensor's magnitude
+    worst_scale = worst_add = 0.0
+    for name, (off, numel, shape, store) in plan.flat.slots.items():
+        sl = slice(off, off + numel)
+        ref = g1[sl].abs().max().item() + 1e-20
+        worst_scale = max(worst_scale, (g1s[sl] - 2.0 * g1[sl]).abs().max().item() / (2.0 * ref))
+        ref12 = g12[sl].abs().max().item() + 1e-20
+        worst_add = max(worst_add, (g12[sl] - g1[sl] - g2[sl]).abs().max().item() / ref12)
+    print("linearity: scale %.3e additivity %.3e" % (worst_scale, worst_add))
+    assert worst_scale < 1e-2, worst_scale      # only the fp32 atomics order differs between the two runs
+    assert worst_add < 8e-2, worst_add          # plus independent bf16 roundings of ~70 chained gradient tensors
