@@ -208,13 +208,15 @@ class InferencePlan:
             numel *= s
         return self.bufs[key][:numel].view(shape)
 
-    def forward(self, x, want_features=False):
+    def forward(self, x, want_features=False, want_map=False):
         """x: (N, 3, T, H, W) fp32 CUDA -> logits (N, num_class) fp32 [, pooled features (N, 512)]."""
         assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w), (tuple(x.shape), (self.n, 3, self.t, self.h, self.w))
         ops.stem_unfold(x.contiguous(), out=self._view(self.unfold))
         for L in self.layers:
             ops.conv3d_fwd(L.desc, self._view(L.src), L.w_packed, L.scale, L.shift,
                            self._view(L.res) if L.res is not None else None, out=self._view(L.dst))
+        if want_map:                   # conv5_x output (N, T/8, H/16, W/16, 512) bf16 for heads other than pool + Dense
+            return self._view(self.final).clone()
         return ops.pool_fc_fwd(self._view(self.final), 512, self.fc_w, self.fc_b, want_pooled=want_features)
 
 

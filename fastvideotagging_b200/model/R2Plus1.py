@@ -281,6 +281,13 @@ class R2Plus2D(torch.nn.Module):
         self._ensure_flat(device)
         return self._grad_anchor
 
+    def conv5_features(self, x):
+        """conv5_x output in the kernels' layout, (N, T/8, H/16, W/16, 512) bf16 — the input of the multi-task heads
+        (reference multi_taskR3d.py:246-251 runs the same trunk)."""
+        if not x.is_cuda:
+            raise RuntimeError("R2Plus2D runs on sm_100a only: move the clip batch to a CUDA device (no CPU fallback)")
+        return self._inference_plan(x).forward(x, want_map=True)
+
     def extract_features(self, x):
         """Reference :247-254 — the AvgPool3D output, shape (N, 512, 1, 1, 1)."""
         _, pooled = self._inference_plan(x).forward(x, want_features=True)

@@ -43,16 +43,16 @@ def to_ncdhw(y, c):
 
 
 class Conv3D(torch.nn.Module):
-    """nn.Conv3D(channels, kernel_size, strides, padding, use_bias=False) on K1 (no bias: every reference call site
-    passes use_bias=False, R2Plus1.py:31,38,70)."""
+    """nn.Conv3D(channels, kernel_size, strides, padding, use_bias=False) on K1.  The trunk never has a bias
+    (R2Plus1.py:31,38,70 pass use_bias=False); the multi-task heads use gluon's default use_bias=True
+    (multi_taskR3d.py:171,179), supported in eval mode by folding the bias into the epilogue's shift."""
 
     def __init__(self, in_channels, channels, kernel_size, strides=(1, 1, 1), padding=(0, 0, 0), use_bias=False):
         super().__init__()
-        if use_bias:
-            raise NotImplementedError("use_bias=True is never used by the reference callers")
         self.in_channels, self.channels = in_channels, channels
         self.kernel, self.strides, self.padding = tuple(kernel_size), tuple(strides), tuple(padding)
         self.weight = torch.nn.Parameter(_xavier((channels, in_channels) + self.kernel))
+        self.bias = torch.nn.Parameter(torch.zeros(channels)) if use_bias else None
 
     def run(self, x, bn=None, relu=False, residual=None, training=False):
         """x: NDHWC bf16.  bn: BatchNorm module applied to the conv output (folded in eval mode)."""
@@ -60,12 +60,32 @@ class Conv3D(torch.nn.Module):
         cout_s = pad16(self.channels)
         flags = (FVT_CONV_RELU if relu else 0) | (FVT_CONV_RESIDUAL if residual is not None else 0)
         if bn is None or not training:
+            # eval mode: packed bf16 weights and the folded (scale, shift) are cached until a parameter changes
+            ver = (self.weight._version, self.weight.data_ptr(), None if self.bias is None else self.bias._version,
+                   None if bn is None else (bn.gamma._version, bn.beta._version, bn.running_mean._version,
+                                            bn.running_var._version, bn.gamma.data_ptr()), cs, flags, (n, t, h, w))
+            hit = getattr(self, "_eval_cache", None)
+            if hit is not None and hit[0] == ver:
+                d, wp, scale, shift = hit[1]
+                return ops.conv3d_fwd(d, x, wp, scale, shift, residual)
             d = ops.conv_desc(n, t, h, w, cs, cout_s, self.kernel, self.strides, self.padding, flags)
             wp = ops.pack_conv_weight(d, self.weight)
             scale = shift = None
             if bn is not None:
                 scale, shift = bn.folded(cout_s)
+            if self.bias is not None:                  # BN(conv + b) = scale * conv + (shift + scale * b)
+                b = torch.zeros(cout_s, dtype=torch.float32, device=x.device)
+                b[: self.channels] = self.bias.detach().float()
+                if scale is None:
+                    scale = torch.zeros(cout_s, dtype=torch.float32, device=x.device)
+                    scale[: self.channels] = 1.0
+                    shift = b
+                else:
+                    shift = shift + scale * b
+            self._eval_cache = (ver, (d, wp, scale, shift))
             return ops.conv3d_fwd(d, x, wp, scale, shift, residual)
+        if self.bias is not None:
+            raise NotImplementedError("training-mode Conv3D with a bias: train through R2Plus2D (bias-free trunk)")
         # training mode: batch statistics (biased variance), running-stat update with the MXNet convention
         d = ops.conv_desc(n, t, h, w, cs, cout_s, self.kernel, self.strides, self.padding, FVT_CONV_STATS)
         wp = ops.pack_conv_weight(d, self.weight)

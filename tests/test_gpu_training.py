@@ -172,16 +172,26 @@ def test_full_size_backward_is_linear_in_the_head_gradient(cuda_device):
         torch.cuda.synchronize()
         return plan.flat.g.clone()
 
-    g1, g2, g12, g1s = grads(d1), grads(d2), grads(d1 + d2), grads(2.0 * d1)
+    g1, g2, g12, g1s, g1b = grads(d1), grads(d2), grads(d1 + d2), grads(2.0 * d1), grads(d1)
     assert torch.isfinite(g12).all()
-    # compare per parameter tensor, relative to that tensor's magnitude
+    # per weight tensor: relative L2 error (BatchNorm beta/gamma gradients of ~1e-9 magnitude are rounding noise and only
+    # enter the whole-buffer figure)
+    def rel_l2(a, b):
+        return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
     worst_scale = worst_add = 0.0
     for name, (off, numel, shape, store) in plan.flat.slots.items():
+        if not name.endswith("_weight"):
+            continue
         sl = slice(off, off + numel)
-        ref = g1[sl].abs().max().item() + 1e-20
-        worst_scale = max(worst_scale, (g1s[sl] - 2.0 * g1[sl]).abs().max().item() / (2.0 * ref))
-        ref12 = g12[sl].abs().max().item() + 1e-20
-        worst_add = max(worst_add, (g12[sl] - g1[sl] - g2[sl]).abs().max().item() / ref12)
-    print("linearity: scale %.3e additivity %.3e" % (worst_scale, worst_add))
-    assert worst_scale < 1e-2, worst_scale      # only the fp32 atomics order differs between the two runs
-    assert worst_add < 8e-2, worst_add          # plus independent bf16 roundings of ~70 chained gradient tensors
+        worst_scale = max(worst_scale, rel_l2(g1s[sl], 2.0 * g1[sl]))
+        worst_add = max(worst_add, rel_l2(g12[sl], g1[sl] + g2[sl]))
+    all_scale, all_add = rel_l2(g1s, 2.0 * g1), rel_l2(g12, g1 + g2)
+    noise = rel_l2(g1b, g1)                      # run-to-run difference of the SAME backward (atomics order)
+    print("run-to-run noise %.3e" % noise)
+    print("linearity rel-L2: scale worst %.3e all %.3e | additivity worst %.3e all %.3e" % (worst_scale, all_scale, worst_add, all_add))
+    # x2 is exact in bf16, so only the fp32 atomics order (and the bf16 roundings it flips, amplified by the
+    # cancellation inside the BatchNorm backward) separates the two runs: the yardstick is the run-to-run difference
+    # of the same backward.  Additivity also carries independent bf16 roundings of ~70 chained gradient tensors.
+    assert all_scale <= 3.0 * noise + 2e-3 and worst_scale <= 6.0 * noise + 5e-3, (worst_scale, all_scale, noise)
+    assert worst_add < 1e-1 and all_add < 5e-2, (worst_add, all_add)
