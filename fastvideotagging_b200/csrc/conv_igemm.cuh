@@ -113,6 +113,11 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       affine_smem[kMaxCout + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
     }
   }
+  // Training forward (statistics, no folded affine): the per-channel sums of ALL tiles of this CTA accumulate in the
+  // otherwise unused affine area and reach global memory once, after the tile loop (no per-tile barriers/atomics).
+  const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr && p.k_splits == 1;
+  if (acc_stats)
+    for (int i = threadIdx.x; i < 2 * kMaxCout; i += kConvThreads) affine_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -273,7 +278,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      if (do_stats) {
+      if (do_stats && !acc_stats) {
         for (int i = et; i < 512; i += kEpilogueThreads) stat_smem[i] = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -289,7 +294,8 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         EpilogueArgs ea;
         ea.block_n = p.block_n; ea.cout_store = p.cout_store; ea.flags = p.flags;
         ea.scale_smem = has_affine ? affine_smem : nullptr; ea.shift_smem = affine_smem + kMaxCout;
-        ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem; ea.stat_stride = 256;
+        ea.residual = p.residual; ea.y = p.y;
+        ea.stat_smem = acc_stats ? affine_smem + n0 : stat_smem; ea.stat_stride = acc_stats ? kMaxCout : 256;
         epilogue_chunks(ea, taddr, n0, row_ok ? static_cast<long long>(row) : -1ll, grp, lane);
       }
       // release the accumulator stage (all of this warp's TMEM reads have completed: wait::ld above)
@@ -297,7 +303,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty_bar[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (do_stats) {
+      if (do_stats && !acc_stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = et; i < p.block_n; i += kEpilogueThreads) {
           if (n0 + i < p.cout_store) {
@@ -306,6 +312,13 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    }
+    if (acc_stats && blockIdx.x < num_tiles) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < p.cout_store; i += kEpilogueThreads) {
+        atomicAdd(p.stats + i, affine_smem[i]);
+        atomicAdd(p.stats + p.cout_store + i, affine_smem[kMaxCout + i]);
       }
     }
   }

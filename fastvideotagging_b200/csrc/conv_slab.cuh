@@ -119,6 +119,11 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       affine_smem[n_total + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
     }
   }
+  // training forward (statistics, no folded affine): sums of all tiles of this CTA accumulate in the unused affine area
+  // [2][n_total] and are flushed to global memory once after the tile loop
+  const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr;
+  if (acc_stats)
+    for (int i = threadIdx.x; i < 2 * n_total; i += kSlabThreads) affine_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -305,10 +310,11 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const long long out_row = ok ? (static_cast<long long>(frame) * p.h + h0 + hl) * p.w + wl : -1ll;
       for (int nt = 0; nt < p.num_n_tiles; ++nt) {
         const int n0 = nt * p.n_tile;
-        if (do_stats) {
+        if (do_stats && !acc_stats) {
           for (int i = et; i < 2 * p.n_tile; i += 256) stat_smem[i] = 0.f;
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+        if (acc_stats) { ea.stat_smem = affine_smem + n0; ea.stat_stride = n_total; }
         epilogue_prefetch_residual(ea, n0, out_row, grp);
         ptx::mbar_wait(ptx::smem_u32(&acc_full[acc]), acc_phase);
         ptx::tc_fence_after();
@@ -318,7 +324,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (do_stats) {
+        if (do_stats && !acc_stats) {
           asm volatile("bar.sync 1, 256;" ::: "memory");
           for (int i = et; i < p.n_tile; i += 256) {
             if (n0 + i < p.cout_store) {
@@ -328,6 +334,13 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+      }
+    }
+    if (acc_stats && static_cast<int>(blockIdx.x) < num_m_tiles) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < n_total && i < p.cout_store; i += 256) {
+        atomicAdd(p.stats + i, affine_smem[i]);
+        atomicAdd(p.stats + p.cout_store + i, affine_smem[n_total + i]);
       }
     }
   }

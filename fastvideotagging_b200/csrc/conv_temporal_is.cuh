@@ -92,6 +92,9 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       affine_smem[p.n_tile + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
     }
   }
+  // per-channel statistics accumulate in shared memory over ALL tiles of this CTA; one flush after the tile loop
+  if (p.flags & kConvStats)
+    for (int i = threadIdx.x; i < 2 * p.n_tile; i += blockDim.x) stat_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -214,10 +217,6 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       for (int lo = 0; lo < p.t_chunk; ++lo) {
         const int tt = chunk * p.t_chunk + lo;
         const long long out_row = pos < p.hw ? (static_cast<long long>(n) * p.t + tt) * p.hw + pos : -1ll;
-        if (do_stats) {
-          for (int i = et; i < 2 * p.n_tile; i += 256) stat_smem[i] = 0.f;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
         epilogue_prefetch_residual(ea, 0, out_row, grp);
         ptx::mbar_wait(ptx::smem_u32(&acc_full[slot]), par);
         ptx::tc_fence_after();
@@ -227,22 +226,18 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty[slot]));
         if (++slot == p.acc_slots) { slot = 0; par ^= 1u; }
-        if (do_stats) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          for (int i = et; i < p.n_tile; i += 256) {
-            if (i < p.cout_store) {
-              atomicAdd(p.stats + i, stat_smem[i]);
-              atomicAdd(p.stats + p.cout_store + i, stat_smem[p.n_tile + i]);
-            }
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
       }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if ((p.flags & kConvStats) && static_cast<int>(blockIdx.x) < p.num_items) {
+    for (int i = threadIdx.x; i < p.n_tile && i < p.cout_store; i += blockDim.x) {
+      atomicAdd(p.stats + i, stat_smem[i]);
+      atomicAdd(p.stats + p.cout_store + i, stat_smem[p.n_tile + i]);
+    }
+  }
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
