@@ -71,110 +71,149 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
   }
 }
 
-// ------------------------------------------------------------------------------------------------ K6
+// ------------------------------------------------------------------------------------------------ K6 / K7
+// The [rows, C] passes are HBM-bound, so what matters is bytes in flight per SM.  The first version kept every
+// per-channel constant of a thread's 8 channels in registers (92-141 registers per thread -> 1-2 CTAs per SM, 12-24 %
+// of the warp slots, 38-50 % of DRAM bandwidth in ncu).  Here the constants sit in shared memory (computed once per
+// CTA) and are read two channels at a time inside the compute phase, which brings the kernels to <= 64 registers
+// (4 CTAs of 256 threads per SM) with 4 rows x 2-3 16-byte loads in flight per thread.
+struct Words { uint32_t w[4]; };
+__device__ __forceinline__ Words ld_words(const uint4* p) {
+  const uint4 v = __ldg(p);
+  Words r; r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  return r;
+}
+__device__ __forceinline__ uint4 to_uint4(const Words& a) { return make_uint4(a.w[0], a.w[1], a.w[2], a.w[3]); }
+__device__ __forceinline__ float lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 // res_mode: 0 none, 1 add bf16 tensor `res`, 2 add res*res_scale + res_shift (projection shortcut's own BatchNorm)
-__global__ void __launch_bounds__(256)
+template <int kResMode>
+__global__ void __launch_bounds__(256, 4)
 bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                 const uint4* __restrict__ res, const float* __restrict__ res_scale, const float* __restrict__ res_shift,
-                uint4* __restrict__ out, size_t rows, int cvec, int res_mode, int relu) {
+                uint4* __restrict__ out, size_t rows, int cvec, int relu) {
+  extern __shared__ float cst[];                     // [4][C]: scale, shift, res_scale, res_shift
+  const int c_store = cvec * 8;
+  for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
+    cst[ch] = scale[ch];
+    cst[c_store + ch] = shift[ch];
+    if (kResMode == 2) { cst[2 * c_store + ch] = res_scale[ch]; cst[3 * c_store + ch] = res_shift[ch]; }
+  }
+  __syncthreads();
   const int tpr = blockDim.x / cvec;                 // rows handled per CTA iteration
   const int cv = threadIdx.x % cvec;
   const int rsub = threadIdx.x / cvec;
   if (rsub >= tpr) return;
-  float sc[8], sh[8], rs[8], rh[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    sc[i] = scale[cv * 8 + i]; sh[i] = shift[cv * 8 + i];
-    rs[i] = res_mode == 2 ? res_scale[cv * 8 + i] : 1.f;
-    rh[i] = res_mode == 2 ? res_shift[cv * 8 + i] : 0.f;
-  }
-  // kUnroll rows per thread per iteration: all loads are issued before the first use (bytes in flight per thread)
+  const float2* sc2 = reinterpret_cast<const float2*>(cst) + cv * 4;
+  const float2* sh2 = reinterpret_cast<const float2*>(cst + c_store) + cv * 4;
+  const float2* rs2 = reinterpret_cast<const float2*>(cst + 2 * c_store) + cv * 4;
+  const float2* rh2 = reinterpret_cast<const float2*>(cst + 3 * c_store) + cv * 4;
+  const float lo_clamp = relu ? 0.f : -INFINITY;
   const size_t rstep = static_cast<size_t>(gridDim.x) * tpr;
   for (size_t r0 = static_cast<size_t>(blockIdx.x) * tpr + rsub; r0 < rows; r0 += rstep * kUnroll) {
-    uint4 vx[kUnroll], vq[kUnroll];
+    Words vx[kUnroll], vq[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t r = r0 + u * rstep;
-      vx[u] = r < rows ? __ldg(raw + r * cvec + cv) : make_uint4(0, 0, 0, 0);
-      vq[u] = (res_mode && r < rows) ? __ldg(res + r * cvec + cv) : make_uint4(0, 0, 0, 0);
+      if (r < rows) {
+        vx[u] = ld_words(raw + r * cvec + cv);
+        if (kResMode) vq[u] = ld_words(res + r * cvec + cv);
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float2 sc = sc2[w], sh = sh2[w];
+      float2 rs = make_float2(1.f, 1.f), rh = make_float2(0.f, 0.f);
+      if (kResMode == 2) { rs = rs2[w]; rh = rh2[w]; }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float y0 = fmaf(lo_f(vx[u].w[w]), sc.x, sh.x), y1 = fmaf(hi_f(vx[u].w[w]), sc.y, sh.y);
+        if (kResMode) {
+          y0 += fmaf(lo_f(vq[u].w[w]), rs.x, rh.x);
+          y1 += fmaf(hi_f(vq[u].w[w]), rs.y, rh.y);
+        }
+        vx[u].w[w] = pack2(fmaxf(y0, lo_clamp), fmaxf(y1, lo_clamp));
+      }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t r = r0 + u * rstep;
-      if (r >= rows) break;
-      float x[8], y[8];
-      unpack8(vx[u], x);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaf(x[i], sc[i], sh[i]);
-      if (res_mode) {
-        float q[8];
-        unpack8(vq[u], q);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] += fmaf(q[i], rs[i], rh[i]);
-      }
-      if (relu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
-      }
-      out[r * cvec + cv] = pack8(y);
+      if (r < rows) out[r * cvec + cv] = to_uint4(vx[u]);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ K7a
 // sums[0..C) += sum dz*xhat (dgamma), sums[C..2C) += sum dz (dbeta);  xhat = (raw - mean)*inv_std
-__global__ void __launch_bounds__(256)
+// kMask: 0 no mask, 1 mask tensor (dz = dact * [mask > 0]), 2 ReLU mask recomputed from raw: [raw*scale + shift > 0]
+template <int kMask>
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
                      float* __restrict__ sums, size_t rows, int cvec, int c_store) {
-  extern __shared__ float sred[];                    // [blockDim.x][16] folded per channel vector
+  extern __shared__ float sred[];                    // [3][C] constants, then [blockDim.x][16] fold area
+  float* cst = sred;
+  float* fold = sred + 3 * c_store;
+  for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
+    cst[ch] = mean[ch];
+    if (kMask == 2) { cst[c_store + ch] = relu_scale[ch]; cst[2 * c_store + ch] = relu_shift[ch]; }
+  }
+  __syncthreads();
   const int tpr = blockDim.x / cvec;
   const int cv = threadIdx.x % cvec;
   const int rsub = threadIdx.x / cvec;
-  float dg[8], db[8], mu[8], is[8], rsc[8], rsh[8];
-  const bool self_mask = relu_scale != nullptr;       // ReLU mask recomputed from raw: [raw*scale + shift > 0]
+  float dg[8], db[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    dg[i] = 0.f; db[i] = 0.f; mu[i] = mean[cv * 8 + i]; is[i] = invstd[cv * 8 + i];
-    rsc[i] = self_mask ? relu_scale[cv * 8 + i] : 0.f;
-    rsh[i] = self_mask ? relu_shift[cv * 8 + i] : 1.f;
-  }
+  for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; }
   if (rsub < tpr) {
+    const float2* mu2 = reinterpret_cast<const float2*>(cst) + cv * 4;
+    const float2* rs2 = reinterpret_cast<const float2*>(cst + c_store) + cv * 4;
+    const float2* rh2 = reinterpret_cast<const float2*>(cst + 2 * c_store) + cv * 4;
     const size_t rstep = static_cast<size_t>(gridDim.x) * tpr;
     for (size_t r0 = static_cast<size_t>(blockIdx.x) * tpr + rsub; r0 < rows; r0 += rstep * kUnroll) {
-      uint4 vx[kUnroll], vg[kUnroll], vm[kUnroll];
+      Words vx[kUnroll], vg[kUnroll], vm[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const size_t r = r0 + u * rstep;
-        const bool ok = r < rows;
-        vx[u] = ok ? __ldg(raw + r * cvec + cv) : make_uint4(0, 0, 0, 0);
-        vg[u] = ok ? __ldg(dact + r * cvec + cv) : make_uint4(0, 0, 0, 0);     // zero gradient: contributes nothing
-        vm[u] = (ok && mask != nullptr) ? __ldg(mask + r * cvec + cv) : make_uint4(0, 0, 0, 0);
+        if (r < rows) {
+          vx[u] = ld_words(raw + r * cvec + cv);
+          vg[u] = ld_words(dact + r * cvec + cv);
+          if (kMask == 1) vm[u] = ld_words(mask + r * cvec + cv);
+        } else {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { vx[u].w[w] = 0u; vg[u].w[w] = 0u; vm[u].w[w] = 0u; }   // zero gradient: adds nothing
+        }
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        float x[8], g[8];
-        unpack8(vx[u], x);
-        unpack8(vg[u], g);
-        if (mask != nullptr) {
-          float mk[8];
-          unpack8(vm[u], mk);
+      for (int w = 0; w < 4; ++w) {
+        const float2 mu = mu2[w];
+        float2 rs = make_float2(0.f, 0.f), rh = make_float2(1.f, 1.f);
+        if (kMask == 2) { rs = rs2[w]; rh = rh2[w]; }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
-        } else if (self_mask) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          db[i] += g[i];
-          dg[i] = fmaf(g[i], (x[i] - mu[i]) * is[i], dg[i]);
+        for (int u = 0; u < kUnroll; ++u) {
+          const float x0 = lo_f(vx[u].w[w]), x1 = hi_f(vx[u].w[w]);
+          float g0 = lo_f(vg[u].w[w]), g1 = hi_f(vg[u].w[w]);
+          if (kMask == 1) {
+            g0 = lo_f(vm[u].w[w]) > 0.f ? g0 : 0.f;
+            g1 = hi_f(vm[u].w[w]) > 0.f ? g1 : 0.f;
+          } else if (kMask == 2) {
+            g0 = fmaf(x0, rs.x, rh.x) > 0.f ? g0 : 0.f;
+            g1 = fmaf(x1, rs.y, rh.y) > 0.f ? g1 : 0.f;
+          }
+          db[2 * w] += g0; db[2 * w + 1] += g1;
+          dg[2 * w] = fmaf(g0, x0 - mu.x, dg[2 * w]);
+          dg[2 * w + 1] = fmaf(g1, x1 - mu.y, dg[2 * w + 1]);
         }
       }
     }
   }
-  float* mine = sred + threadIdx.x * 16;
+  float* mine = fold + threadIdx.x * 16;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mine[i] = dg[i]; mine[8 + i] = db[i]; }
   __syncthreads();
@@ -182,69 +221,86 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ da
   for (int o = threadIdx.x; o < cvec * 16; o += blockDim.x) {
     const int v = o / 16, k = o % 16;
     float s = 0.f;
-    for (int t = 0; t < tpr; ++t) s += sred[(t * cvec + v) * 16 + k];
+    for (int t = 0; t < tpr; ++t) s += fold[(t * cvec + v) * 16 + k];
     const int ch = v * 8 + (k & 7);
+    if (k < 8) s *= invstd[ch];                      // sum dz*(x - mean) -> sum dz*xhat
     atomicAdd(sums + (k < 8 ? 0 : c_store) + ch, s);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ K7b
 // draw = gamma*inv_std*(dz - dbeta/M - xhat*dgamma/M); optionally also writes dz (masked dact) for the shortcut path.
-__global__ void __launch_bounds__(256)
+template <int kMask, bool kDz>
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
                     const float* __restrict__ sums, uint4* __restrict__ draw, uint4* __restrict__ dz_out, size_t rows,
                     int cvec, int c_store, int c_real, float inv_rows) {
+  extern __shared__ float cst[];      // [6][C]: a = gamma*inv_std, a*dbeta/M, a*inv_std*dgamma/M, mean, relu scale, relu shift
+  for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
+    const float is = invstd[ch];
+    const float a = (ch < c_real ? gamma[ch] : 0.f) * is;
+    cst[ch] = a;
+    cst[c_store + ch] = a * sums[c_store + ch] * inv_rows;
+    cst[2 * c_store + ch] = a * is * sums[ch] * inv_rows;
+    cst[3 * c_store + ch] = mean[ch];
+    if (kMask == 2) { cst[4 * c_store + ch] = relu_scale[ch]; cst[5 * c_store + ch] = relu_shift[ch]; }
+  }
+  __syncthreads();
   const int tpr = blockDim.x / cvec;
   const int cv = threadIdx.x % cvec;
   const int rsub = threadIdx.x / cvec;
   if (rsub >= tpr) return;
-  float mu[8], is[8], a[8], bq[8], cq[8], rsc[8], rsh[8];
-  const bool self_mask = relu_scale != nullptr;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int ch = cv * 8 + i;
-    mu[i] = mean[ch]; is[i] = invstd[ch];
-    rsc[i] = self_mask ? relu_scale[ch] : 0.f;
-    rsh[i] = self_mask ? relu_shift[ch] : 1.f;
-    const float g = ch < c_real ? gamma[ch] : 0.f;
-    a[i] = g * is[i];
-    bq[i] = sums[c_store + ch] * inv_rows;          // dbeta / M
-    cq[i] = sums[ch] * inv_rows;                    // dgamma / M
-  }
+  const float2* a2 = reinterpret_cast<const float2*>(cst) + cv * 4;
+  const float2* b2 = reinterpret_cast<const float2*>(cst + c_store) + cv * 4;
+  const float2* c2 = reinterpret_cast<const float2*>(cst + 2 * c_store) + cv * 4;
+  const float2* mu2 = reinterpret_cast<const float2*>(cst + 3 * c_store) + cv * 4;
+  const float2* rs2 = reinterpret_cast<const float2*>(cst + 4 * c_store) + cv * 4;
+  const float2* rh2 = reinterpret_cast<const float2*>(cst + 5 * c_store) + cv * 4;
   const size_t rstep = static_cast<size_t>(gridDim.x) * tpr;
   for (size_t r0 = static_cast<size_t>(blockIdx.x) * tpr + rsub; r0 < rows; r0 += rstep * kUnroll) {
-    uint4 vx[kUnroll], vg[kUnroll], vm[kUnroll];
+    Words vx[kUnroll], vg[kUnroll], vm[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t r = r0 + u * rstep;
-      const bool ok = r < rows;
-      vx[u] = ok ? __ldg(raw + r * cvec + cv) : make_uint4(0, 0, 0, 0);
-      vg[u] = ok ? __ldg(dact + r * cvec + cv) : make_uint4(0, 0, 0, 0);
-      vm[u] = (ok && mask != nullptr) ? __ldg(mask + r * cvec + cv) : make_uint4(0, 0, 0, 0);
+      if (r < rows) {
+        vx[u] = ld_words(raw + r * cvec + cv);
+        vg[u] = ld_words(dact + r * cvec + cv);
+        if (kMask == 1) vm[u] = ld_words(mask + r * cvec + cv);
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float2 a = a2[w], ab = b2[w], ac = c2[w], mu = mu2[w];
+      float2 rs = make_float2(0.f, 0.f), rh = make_float2(1.f, 1.f);
+      if (kMask == 2) { rs = rs2[w]; rh = rh2[w]; }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const float x0 = lo_f(vx[u].w[w]), x1 = hi_f(vx[u].w[w]);
+        float g0 = lo_f(vg[u].w[w]), g1 = hi_f(vg[u].w[w]);
+        if (kMask == 1) {
+          g0 = lo_f(vm[u].w[w]) > 0.f ? g0 : 0.f;
+          g1 = hi_f(vm[u].w[w]) > 0.f ? g1 : 0.f;
+        } else if (kMask == 2) {
+          g0 = fmaf(x0, rs.x, rh.x) > 0.f ? g0 : 0.f;
+          g1 = fmaf(x1, rs.y, rh.y) > 0.f ? g1 : 0.f;
+        }
+        // a*(g - dbeta/M - xhat*dgamma/M) with the per-channel products folded into ab, ac
+        const float o0 = fmaf(a.x, g0, -ab.x) - (x0 - mu.x) * ac.x;
+        const float o1 = fmaf(a.y, g1, -ab.y) - (x1 - mu.y) * ac.y;
+        vx[u].w[w] = pack2(o0, o1);
+        if (kDz) vg[u].w[w] = pack2(g0, g1);
+      }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t r = r0 + u * rstep;
-      if (r >= rows) break;
-      const size_t idx = r * cvec + cv;
-      float x[8], g[8], o[8];
-      unpack8(vx[u], x);
-      unpack8(vg[u], g);
-      if (mask != nullptr) {
-        float mk[8];
-        unpack8(vm[u], mk);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = mk[i] > 0.f ? g[i] : 0.f;
-      } else if (self_mask) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = fmaf(x[i], rsc[i], rsh[i]) > 0.f ? g[i] : 0.f;
+      if (r < rows) {
+        const size_t idx = r * cvec + cv;
+        draw[idx] = to_uint4(vx[u]);
+        if (kDz) dz_out[idx] = to_uint4(vg[u]);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = a[i] * (g[i] - bq[i] - (x[i] - mu[i]) * is[i] * cq[i]);
-      draw[idx] = pack8(o);
-      if (dz_out != nullptr) dz_out[idx] = pack8(g);
     }
   }
 }
@@ -448,8 +504,11 @@ int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const 
   int blocks, threads;
   if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
   const int res_mode = res == nullptr ? 0 : (res_scale ? 2 : 1);
-  bn_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((const uint4*)raw, scale, shift, (const uint4*)res, res_scale,
-                                                                res_shift, (uint4*)out, rows, c_store / 8, res_mode, relu);
+  const size_t smem = sizeof(float) * 4 * c_store;
+#define FVT_BN_APPLY(M) bn_apply_kernel<M><<<blocks, threads, smem, (cudaStream_t)stream>>>( \
+      (const uint4*)raw, scale, shift, (const uint4*)res, res_scale, res_shift, (uint4*)out, rows, c_store / 8, relu)
+  if (res_mode == 0) FVT_BN_APPLY(0); else if (res_mode == 1) FVT_BN_APPLY(1); else FVT_BN_APPLY(2);
+#undef FVT_BN_APPLY
   return check_launch("bn_apply_kernel");
 }
 
@@ -465,14 +524,23 @@ int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const f
   int blocks, threads;
   if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c_store, (cudaStream_t)stream);
-  bn_bwd_reduce_kernel<<<blocks, threads, threads * 16 * sizeof(float), (cudaStream_t)stream>>>(
-      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, relu_scale, relu_shift, sums, rows, c_store / 8,
-      c_store);
+  const int mask_mode = mask != nullptr ? 1 : (relu_scale != nullptr ? 2 : 0);
+  const size_t smem_r = sizeof(float) * (3 * c_store + threads * 16);
+#define FVT_BN_RED(M) bn_bwd_reduce_kernel<M><<<blocks, threads, smem_r, (cudaStream_t)stream>>>( \
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, relu_scale, relu_shift, sums, rows, c_store / 8, c_store)
+  if (mask_mode == 0) FVT_BN_RED(0); else if (mask_mode == 1) FVT_BN_RED(1); else FVT_BN_RED(2);
+#undef FVT_BN_RED
   if (int e = check_launch("bn_bwd_reduce_kernel")) return e;
-  bn_bwd_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, relu_scale, relu_shift, sums,
-      (uint4*)draw, (uint4*)dz_out,
-      rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows));
+  const size_t smem_a = sizeof(float) * 6 * c_store;
+#define FVT_BN_APP(M, D) bn_bwd_apply_kernel<M, D><<<blocks, threads, smem_a, (cudaStream_t)stream>>>( \
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, relu_scale, relu_shift, sums, \
+      (uint4*)draw, (uint4*)dz_out, rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows))
+  if (dz_out != nullptr) {
+    if (mask_mode == 0) FVT_BN_APP(0, true); else if (mask_mode == 1) FVT_BN_APP(1, true); else FVT_BN_APP(2, true);
+  } else {
+    if (mask_mode == 0) FVT_BN_APP(0, false); else if (mask_mode == 1) FVT_BN_APP(1, false); else FVT_BN_APP(2, false);
+  }
+#undef FVT_BN_APP
   return check_launch("bn_bwd_apply_kernel");
 }
 
