@@ -71,6 +71,8 @@ def load():
         "fvt_bn_finalize": (ctypes.c_int, [fp, fp, fp, fp, fp, i32, i32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                            fp, fp, fp, fp, vp]),
         "fvt_bn_apply": (ctypes.c_int, [vp, fp, fp, vp, fp, fp, vp, ctypes.c_int64, i32, i32, vp]),
+        "fvt_bn_finalize_apply": (ctypes.c_int, [fp, fp, fp, fp, fp, i32, i32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                                 fp, fp, fp, fp, vp, vp, fp, fp, vp, i32, vp]),
         "fvt_bn_backward": (ctypes.c_int, [vp, vp, vp, fp, fp, fp, fp, fp, fp, vp, vp, ctypes.c_int64, i32, i32, vp]),
         "fvt_pool_fc_bwd": (ctypes.c_int, [fp, fp, fp, i32, i32, i32, i32, fp, fp, vp, i32, vp]),
         "fvt_sgd_momentum_multi": (ctypes.c_int, [vp, vp, vp, i32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/fvt_b200.h"
 #include "host_common.h"
@@ -92,16 +93,49 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // res_mode: 0 none, 1 add bf16 tensor `res`, 2 add res*res_scale + res_shift (projection shortcut's own BatchNorm)
+// Fused K5: when `fin.stats` is set, every CTA derives (scale, shift) from the accumulated (sum, sum^2) itself — the
+// same arithmetic as bn_finalize_kernel — and CTA 0 also publishes scale/shift/mean/inv_std for the backward pass and
+// updates the running statistics, so the forward pass needs no separate finalize launch.
+struct BnFinalizeArgs {
+  const float* stats; const float* gamma; const float* beta;
+  float* running_mean; float* running_var;
+  float* scale_out; float* shift_out; float* mean_out; float* invstd_out;
+  int c_real; float inv_rows, eps, momentum;
+};
+
 template <int kResMode>
 __global__ void __launch_bounds__(256, 4)
 bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                 const uint4* __restrict__ res, const float* __restrict__ res_scale, const float* __restrict__ res_shift,
-                uint4* __restrict__ out, size_t rows, int cvec, int relu) {
+                uint4* __restrict__ out, size_t rows, int cvec, int relu, const BnFinalizeArgs fin) {
   extern __shared__ float cst[];                     // [4][C]: scale, shift, res_scale, res_shift
   const int c_store = cvec * 8;
   for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
-    cst[ch] = scale[ch];
-    cst[c_store + ch] = shift[ch];
+    if (fin.stats != nullptr) {
+      float sc = 0.f, sh = 0.f, mf = 0.f, inv_std = 0.f, vf = 0.f;
+      if (ch < fin.c_real) {                         // pad channels: identity-zero so they stay exactly 0
+        const double m = static_cast<double>(fin.stats[ch]) * fin.inv_rows;
+        double v = static_cast<double>(fin.stats[c_store + ch]) * fin.inv_rows - m * m;
+        if (v < 0.0) v = 0.0;
+        inv_std = static_cast<float>(1.0 / sqrt(v + static_cast<double>(fin.eps)));
+        const float g = fin.gamma[ch];
+        mf = static_cast<float>(m); vf = static_cast<float>(v);
+        sc = g * inv_std;
+        sh = fin.beta[ch] - mf * g * inv_std;
+      }
+      cst[ch] = sc;
+      cst[c_store + ch] = sh;
+      if (blockIdx.x == 0) {
+        fin.scale_out[ch] = sc; fin.shift_out[ch] = sh; fin.mean_out[ch] = mf; fin.invstd_out[ch] = inv_std;
+        if (fin.running_mean != nullptr && ch < fin.c_real) {
+          fin.running_mean[ch] = fin.momentum * fin.running_mean[ch] + (1.f - fin.momentum) * mf;
+          fin.running_var[ch] = fin.momentum * fin.running_var[ch] + (1.f - fin.momentum) * vf;
+        }
+      }
+    } else {
+      cst[ch] = scale[ch];
+      cst[c_store + ch] = shift[ch];
+    }
     if (kResMode == 2) { cst[2 * c_store + ch] = res_scale[ch]; cst[3 * c_store + ch] = res_shift[ch]; }
   }
   __syncthreads();
@@ -479,6 +513,18 @@ int launch_splitk_finalize(float* ws, const float* scale, const float* shift, co
 
 using namespace fvt;
 
+static int launch_bn_apply(const void* raw, const float* scale, const float* shift, const void* res, const float* res_scale,
+                           const float* res_shift, void* out, int64_t rows, int c_store, int relu, const BnFinalizeArgs& fin,
+                           int blocks, int threads, cudaStream_t stream) {
+  const int res_mode = res == nullptr ? 0 : (res_scale ? 2 : 1);
+  const size_t smem = sizeof(float) * 4 * c_store;
+#define FVT_BN_APPLY(M) bn_apply_kernel<M><<<blocks, threads, smem, stream>>>( \
+      (const uint4*)raw, scale, shift, (const uint4*)res, res_scale, res_shift, (uint4*)out, rows, c_store / 8, relu, fin)
+  if (res_mode == 0) FVT_BN_APPLY(0); else if (res_mode == 1) FVT_BN_APPLY(1); else FVT_BN_APPLY(2);
+#undef FVT_BN_APPLY
+  return check_launch("bn_apply_kernel");
+}
+
 extern "C" {
 
 int fvt_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
@@ -503,13 +549,30 @@ int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const 
   if (current_device_info(&st) == nullptr) return st;
   int blocks, threads;
   if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
-  const int res_mode = res == nullptr ? 0 : (res_scale ? 2 : 1);
-  const size_t smem = sizeof(float) * 4 * c_store;
-#define FVT_BN_APPLY(M) bn_apply_kernel<M><<<blocks, threads, smem, (cudaStream_t)stream>>>( \
-      (const uint4*)raw, scale, shift, (const uint4*)res, res_scale, res_shift, (uint4*)out, rows, c_store / 8, relu)
-  if (res_mode == 0) FVT_BN_APPLY(0); else if (res_mode == 1) FVT_BN_APPLY(1); else FVT_BN_APPLY(2);
-#undef FVT_BN_APPLY
-  return check_launch("bn_apply_kernel");
+  BnFinalizeArgs fin;
+  memset(&fin, 0, sizeof(fin));
+  return launch_bn_apply(raw, scale, shift, res, res_scale, res_shift, out, rows, c_store, relu, fin, blocks, threads,
+                         (cudaStream_t)stream);
+}
+
+int fvt_bn_finalize_apply(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, int32_t c_store, int32_t c_real, int64_t rows, float eps, float momentum,
+                          float* scale, float* shift, float* mean, float* invstd, const void* raw, const void* res,
+                          const float* res_scale, const float* res_shift, void* out, int32_t relu, void* stream) {
+  if (!stats || !gamma || !beta || !scale || !shift || !mean || !invstd || !raw || !out) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  if (c_store <= 0 || c_store % 8 || c_real <= 0 || c_real > c_store || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_finalize_apply extent");
+  if ((res_scale == nullptr) != (res_shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "res_scale/res_shift must come together");
+  if ((running_mean == nullptr) != (running_var == nullptr)) return set_error(FVT_ERR_BAD_DESC, "running_mean/running_var must come together");
+  int st = 0;
+  if (current_device_info(&st) == nullptr) return st;
+  int blocks, threads;
+  if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
+  BnFinalizeArgs fin;
+  fin.stats = stats; fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
+  fin.scale_out = scale; fin.shift_out = shift; fin.mean_out = mean; fin.invstd_out = invstd;
+  fin.c_real = c_real; fin.inv_rows = 1.0f / static_cast<float>(rows); fin.eps = eps; fin.momentum = momentum;
+  return launch_bn_apply(raw, nullptr, nullptr, res, res_scale, res_shift, out, rows, c_store, relu, fin, blocks, threads,
+                         (cudaStream_t)stream);
 }
 
 int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const float* mean, const float* invstd,

@@ -424,13 +424,20 @@ class TrainPlan:
     def _bn_names(self, L):
         return L.spec.bn + "_gamma", L.spec.bn + "_beta", L.spec.bn + "_moving_mean", L.spec.bn + "_moving_var"
 
-    def _conv_bn(self, L, src):
+    def _conv_bn(self, L, src, apply=None):
+        """conv (+ per-channel statistics) -> BatchNorm.  apply=None: finalize only (projection shortcut, whose affine is
+        applied inside the block's last fused pass); apply=dict(relu, res, res_scale, res_shift): finalize + apply in
+        one launch."""
         gname, bname, mname, vname = self._bn_names(L)
         self._wait_packed(L)
         ops.conv3d_fwd(L.fwd, src, L.wp, out=L.raw, stats=L.stats)
-        ops.bn_finalize(L.stats, self.flat.view(self.flat.w, gname), self.flat.view(self.flat.w, bname),
-                        self.aux[mname], self.aux[vname], L.cout_s, L.rows, self.eps, self.momentum,
-                        L.scale, L.shift, L.mean, L.invstd)
+        args = (L.stats, self.flat.view(self.flat.w, gname), self.flat.view(self.flat.w, bname),
+                self.aux[mname], self.aux[vname], L.cout_s, L.rows, self.eps, self.momentum,
+                L.scale, L.shift, L.mean, L.invstd)
+        if apply is None:
+            ops.bn_finalize(*args)
+        else:
+            ops.bn_finalize_apply(*args, L.raw, L.act, True, **apply)
 
     def forward(self, x, weights_version):
         """Training-mode forward: re-pack bf16 operand copies if the weights changed, zero the gradient buffer
@@ -467,19 +474,16 @@ class TrainPlan:
         ops.stem_unfold(x, out=self.unfold)
         B = self.bufs
         for L in (self.stem0, self.stem1):
-            self._conv_bn(L, B[L.src])
-            ops.bn_apply(L.raw, L.scale, L.shift, L.act, True)
+            self._conv_bn(L, B[L.src], apply={})
         for comp, xin_name, xin_shape, a, b, c, d, sc in self.blocks:
             xin = B[xin_name]
             for L in (a, b, c):
-                self._conv_bn(L, B[L.src])
-                ops.bn_apply(L.raw, L.scale, L.shift, L.act, True)
-            self._conv_bn(d, B[d.src])
+                self._conv_bn(L, B[L.src], apply={})
             if sc is not None:
                 self._conv_bn(sc, xin)
-                ops.bn_apply(d.raw, d.scale, d.shift, d.act, True, res=sc.raw, res_scale=sc.scale, res_shift=sc.shift)
+                self._conv_bn(d, B[d.src], apply=dict(res=sc.raw, res_scale=sc.scale, res_shift=sc.shift))
             else:
-                ops.bn_apply(d.raw, d.scale, d.shift, d.act, True, res=xin)
+                self._conv_bn(d, B[d.src], apply=dict(res=xin))
         logits, self.pooled = ops.pool_fc_fwd(B[self.final_name], 512, self.flat.view(self.flat.w, "final_fc_weight"),
                                               self.flat.view(self.flat.w, "final_fc_bias"), want_pooled=True)
         return logits

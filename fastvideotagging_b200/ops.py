@@ -163,6 +163,16 @@ def bn_apply(raw, scale, shift, out, relu, res=None, res_scale=None, res_shift=N
     return out
 
 
+def bn_finalize_apply(stats, gamma, beta, running_mean, running_var, c_store, rows, eps, momentum, scale, shift, mean, invstd,
+                      raw, out, relu, res=None, res_scale=None, res_shift=None):
+    """bn_finalize + bn_apply in one launch (training forward)."""
+    lib = _lib.load()
+    check(lib.fvt_bn_finalize_apply(_ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), c_store,
+                                    gamma.numel(), rows, eps, momentum, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                    _ptr(raw), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out), int(relu), _stream()))
+    return out
+
+
 def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None, relu_scale=None, relu_shift=None):
     """mask: tensor whose sign gates the gradient (ReLU after a residual add), or None; relu_scale/relu_shift: the
     forward scale/shift of this BatchNorm when the ReLU follows it directly (mask recomputed from raw)."""

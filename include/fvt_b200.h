@@ -123,6 +123,13 @@ int fvt_bn_finalize(const float* stats, const float* gamma, const float* beta, f
 /* out = relu?( raw*scale + shift [+ res | + res*res_scale + res_shift] ), [rows, c_store] bf16. */
 int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const void* res, const float* res_scale,
                  const float* res_shift, void* out, int64_t rows, int32_t c_store, int32_t relu, void* stream);
+/* fvt_bn_finalize followed by fvt_bn_apply in ONE launch (the training forward's per-layer pair): every CTA derives
+ * scale/shift from `stats` itself; scale/shift/mean/invstd and the running statistics are written once, as by
+ * fvt_bn_finalize.  Replaces nn.BatchNorm + Activation('relu') at reference model/R2Plus1.py:32-33,59-60,62,81. */
+int fvt_bn_finalize_apply(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, int32_t c_store, int32_t c_real, int64_t rows, float eps, float momentum,
+                          float* scale, float* shift, float* mean, float* invstd, const void* raw, const void* res,
+                          const float* res_scale, const float* res_shift, void* out, int32_t relu, void* stream);
 /* dz = dact * [mask > 0]  (mask tensor given: the ReLU sits after a residual add, R2Plus1.py:81),
  *    = dact * [raw*relu_scale + relu_shift > 0]  (relu_scale/relu_shift = the forward scale/shift of this BatchNorm:
  *      the ReLU directly follows it, R2Plus1.py:33,60 — the mask is recomputed from raw, saving one tensor read),

@@ -196,3 +196,43 @@ def test_conv_wgrad_dgrad(cuda_device, idx):
 def test_batchnorm_forward_backward(cuda_device, idx):
     m = _probe_train()
     assert m.bn_case(*m.BN_CASES[idx])
+
+
+@pytest.mark.parametrize("rows,c_real,res_mode", [(4096, 144, 0), (1000, 64, 1), (777, 230, 2), (50176, 288, 0)])
+def test_bn_finalize_apply_matches_the_two_pass_form(cuda_device, lib, rows, c_real, res_mode):
+    """fvt_bn_finalize_apply (one launch) == fvt_bn_finalize + fvt_bn_apply, bit for bit: outputs, scale/shift/mean/invstd
+    and the running statistics (MXNet momentum convention)."""
+    import torch
+    from fastvideotagging_b200 import ops
+    gen = torch.Generator().manual_seed(rows + c_real)
+    cs = ops.pad16(c_real)
+    raw = torch.zeros(rows, cs)
+    raw[:, :c_real] = torch.randn(rows, c_real, generator=gen) * 2 + 0.5
+    raw = raw.to(torch.bfloat16).to(cuda_device)
+    rf = raw.float()
+    stats = torch.cat([rf.sum(0), (rf * rf).sum(0)]).contiguous()
+    gamma = (0.5 + torch.rand(c_real, generator=gen)).to(cuda_device)
+    beta = torch.randn(c_real, generator=gen).to(cuda_device)
+    res = torch.randn(rows, cs, generator=gen).to(torch.bfloat16).to(cuda_device) if res_mode else None
+    rs = torch.rand(cs, generator=gen).to(cuda_device) if res_mode == 2 else None
+    rh = torch.randn(cs, generator=gen).to(cuda_device) if res_mode == 2 else None
+
+    def fresh():
+        return (torch.full((c_real,), 0.25, device=cuda_device), torch.full((c_real,), 1.5, device=cuda_device),
+                [torch.empty(cs, device=cuda_device) for _ in range(4)], torch.empty_like(raw))
+
+    rm1, rv1, o1, y1 = fresh()
+    ops.bn_finalize(stats, gamma, beta, rm1, rv1, cs, rows, 1e-5, 0.9, *o1)
+    ops.bn_apply(raw, o1[0], o1[1], y1, True, res=res, res_scale=rs, res_shift=rh)
+    rm2, rv2, o2, y2 = fresh()
+    ops.bn_finalize_apply(stats, gamma, beta, rm2, rv2, cs, rows, 1e-5, 0.9, *o2, raw, y2, True, res=res, res_scale=rs, res_shift=rh)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)
+    assert torch.equal(rm1, rm2) and torch.equal(rv1, rv2)
+    # and against the definition (biased variance, reference semantics A4)
+    mean = rf[:, :c_real].double().mean(0)
+    var = rf[:, :c_real].double().var(0, unbiased=False)
+    assert torch.allclose(o2[2][:c_real].double().cpu(), mean.cpu(), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(rv2.double().cpu(), (0.9 * 1.5 + 0.1 * var).cpu(), rtol=1e-4, atol=1e-4)
