@@ -58,6 +58,8 @@ static int g_disable_ring = 0;   // fvt_set_option("disable_frame_ring", 1): tem
 static int g_slab_single_stage = 1;   // fvt_set_option("slab_single_stage", 0): keep two input stages even with a shallow weight ring
 static int g_disable_tis = 0;    // fvt_set_option("disable_temporal_is", 1): no input-stationary temporal kernel (K1i)
 static int g_disable_splitk = 0; // fvt_set_option("disable_split_k", 1): K1 never splits the reduction
+static int g_slab_epi_warps = 8;   // fvt_set_option("slab_epi_warps", 8|16): epilogue warps of the slab kernel.  16 measured SLOWER
+                                   // (conv2_x 1x3x3 at batch 48: 756 -> 996 us): the stores are request-throughput-bound, not latency-bound
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -462,6 +464,7 @@ int fvt_version(void) { return 101; }
 
 int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
+  if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
   if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
   if (name != nullptr && strcmp(name, "disable_frame_ring") == 0) { g_disable_ring = value; return 0; }
@@ -640,13 +643,18 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       int dev = 0;
       cudaGetDevice(&dev);
       if (!attr_set_s[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_slab_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        cudaError_t e = cudaFuncSetAttribute(conv_slab_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(conv_slab_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
         if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_fwd_kernel): %s", cudaGetErrorString(e));
         attr_set_s[dev] = true;
       }
       const int m_tiles = sp.frames * sp.tiles_per_frame;
       const int grid = m_tiles < di->sm_count ? m_tiles : di->sm_count;
-      conv_slab_fwd_kernel<<<grid, kSlabThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
+      if (g_slab_epi_warps == 16)
+        conv_slab_fwd_kernel<16><<<grid, kSlabThreadsWide, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
+      else
+        conv_slab_fwd_kernel<8><<<grid, kSlabThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
       return check_launch("conv_slab_fwd_kernel");
     }
   }

@@ -22,7 +22,8 @@
 
 namespace fvt {
 
-constexpr int kSlabThreads = 384;
+constexpr int kSlabThreads = 384;          // 4 control warps + 8 epilogue warps
+constexpr int kSlabThreadsWide = 640;      // 4 control warps + 16 epilogue warps (narrow-N layers are paced by the epilogue)
 constexpr int kSlabMaxStages = 4;
 constexpr int kSlabMaxBRing = 24;
 
@@ -65,9 +66,12 @@ __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1
                : "memory");
 }
 
-__global__ void __launch_bounds__(kSlabThreads, 1)
+template <int kEpiWarps>
+__global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1)
 conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const SlabParams p) {
+  constexpr int kThreads = 128 + 32 * kEpiWarps;
+  constexpr int kEpiThreads = 32 * kEpiWarps;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,7 +109,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&acc_empty[s]), 8);
+      ptx::mbar_init(ptx::smem_u32(&acc_empty[s]), kEpiWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -114,7 +118,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     ptx::tmem_relinquish();
   }
   if (p.scale != nullptr) {
-    for (int i = threadIdx.x; i < n_total; i += kSlabThreads) {
+    for (int i = threadIdx.x; i < n_total; i += kThreads) {
       affine_smem[i] = i < p.cout_store ? __ldg(p.scale + i) : 0.f;
       affine_smem[n_total + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
     }
@@ -123,7 +127,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   // [2][n_total] and are flushed to global memory once after the tile loop
   const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 2 * n_total; i += kSlabThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * n_total; i += kThreads) affine_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -298,6 +302,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     EpilogueArgs ea;
+    ea.ngrp = kEpiWarps / 4;
     ea.block_n = p.n_tile; ea.cout_store = p.cout_store; ea.flags = p.flags;
     ea.scale_smem = p.scale != nullptr ? affine_smem : nullptr; ea.shift_smem = affine_smem + n_total;
     ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem; ea.stat_stride = p.n_tile;
@@ -311,8 +316,8 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       for (int nt = 0; nt < p.num_n_tiles; ++nt) {
         const int n0 = nt * p.n_tile;
         if (do_stats && !acc_stats) {
-          for (int i = et; i < 2 * p.n_tile; i += 256) stat_smem[i] = 0.f;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int i = et; i < 2 * p.n_tile; i += kEpiThreads) stat_smem[i] = 0.f;
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
         if (acc_stats) { ea.stat_smem = affine_smem + n0; ea.stat_stride = n_total; }
         epilogue_prefetch_residual(ea, n0, out_row, grp);
@@ -325,20 +330,20 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         if (do_stats && !acc_stats) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          for (int i = et; i < p.n_tile; i += 256) {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          for (int i = et; i < p.n_tile; i += kEpiThreads) {
             if (n0 + i < p.cout_store) {
               atomicAdd(p.stats + n0 + i, stat_smem[i]);
               atomicAdd(p.stats + p.cout_store + n0 + i, stat_smem[p.n_tile + i]);
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
       }
     }
     if (acc_stats && static_cast<int>(blockIdx.x) < num_m_tiles) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < n_total && i < p.cout_store; i += 256) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      for (int i = et; i < n_total && i < p.cout_store; i += kEpiThreads) {
         atomicAdd(p.stats + i, affine_smem[i]);
         atomicAdd(p.stats + p.cout_store + i, affine_smem[n_total + i]);
       }

@@ -32,6 +32,7 @@ struct EpilogueArgs {
   __nv_bfloat16* y;
   float* stat_smem;                 // [2][stat_stride] per-CTA partial sums (kConvStats)
   int stat_stride;
+  int ngrp = 2;                     // epilogue warps per TMEM lane quadrant: warp `grp` takes chunks grp, grp+ngrp, ...
 };
 
 // Issued BEFORE waiting for the accumulator: pulls this thread's residual row segments into L2 so that the residual
@@ -40,7 +41,7 @@ struct EpilogueArgs {
 __device__ __forceinline__ void epilogue_prefetch_residual(const EpilogueArgs& p, int n0, long long out_row, int grp) {
   if (!(p.flags & kConvResidual) || out_row < 0) return;
   const __nv_bfloat16* rrow = p.residual + static_cast<size_t>(out_row) * p.cout_store + n0;
-  for (int c = grp * 16; c < p.block_n && n0 + c < p.cout_store; c += 32)
+  for (int c = grp * 16; c < p.block_n && n0 + c < p.cout_store; c += 16 * p.ngrp)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + c));
 }
 
@@ -65,7 +66,8 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
     ptx::tmem_ld_32x32b_x16(taddr + ci * 16, vn);
     if (has_res && n0 + ci * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + ci * 16, rn);
   }
-  for (; ci < n_chunks; ci += 2) {
+  const int ngrp = p.ngrp;
+  for (; ci < n_chunks; ci += ngrp) {
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = vn[i];
@@ -73,7 +75,7 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
     for (int i = 0; i < 8; ++i) rr[i] = rn[i];
     const int c = ci * 16;
     const int ch0 = n0 + c;
-    const int cnext = ci + 2;
+    const int cnext = ci + ngrp;
     if (cnext < n_chunks) {
       ptx::tmem_ld_32x32b_x16(taddr + cnext * 16, vn);
       if (has_res && n0 + cnext * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + cnext * 16, rn);

@@ -6,6 +6,9 @@ import torch
 from fastvideotagging_b200 import ops, _lib
 lib = _lib.load()
 dev = torch.device("cuda:0")
+for kv in os.environ.get("FVT_DBG_OPTS", "").split(","):
+    if kv:
+        k_, v_ = kv.split("="); assert lib.fvt_set_option(k_.encode(), int(v_)) == 0
 CASES = [
     ("conv2 spatial 64->144 b48", 48, 32, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1), False),
     ("conv2 temporal 144->64 b48", 48, 32, 56, 56, 144, 64, (3, 1, 1), (1, 0, 0), False),
@@ -14,6 +17,8 @@ CASES = [
     ("conv3 temporal 288->128 b48", 48, 16, 28, 28, 288, 128, (3, 1, 1), (1, 0, 0), False),
     ("conv2 dgrad-spatial 144->64 b4", 4, 32, 56, 56, 144, 64, (1, 3, 3), (0, 1, 1), False),
     ("conv2 spatial 64->144 b4", 4, 32, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1), False),
+    ("conv3 spatial 128->288 b4", 4, 16, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1), False),
+    ("conv3 dgrad-spatial 288->128 b4", 4, 16, 28, 28, 288, 128, (1, 3, 3), (0, 1, 1), False),
 ]
 def timeit(fn, reps=5):
     fn(); torch.cuda.synchronize()
