@@ -38,7 +38,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -371,9 +371,10 @@ def run_ours(args, rank, world, local_rank):
                     "step_frac_of_peak": value * GFLOP_PER_CLIP_FWD / 1e3 / world / peaks["tflops"]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, _, threads = cpu_reference_rate(2, 5, 1)
+            rate, _, threads = cpu_reference_rate(2, 15, 1)
             cpu = {"value": rate, "unit": "clips/s", "cores": threads, "kind": "port",
-                   "sample": "10 clips (5 steps x 2), R34 32x112x112 fp32, oracle torch-CPU restatement"}
+                   "sample": "30 clips (15 steps x 2) of the same workload, R34 32x112x112 fp32, oracle torch-CPU restatement "
+                             "of model/R2Plus1.py (MXNet itself is not installable), all host threads"}
         line = {
             "metric": "r2plus1d34_32x112_inference_clips_per_s", "value": value, "unit": "clips/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
