@@ -14,6 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "fvt_b200.h")
 FVT_CONV_RELU = 1
 FVT_CONV_RESIDUAL = 2
 FVT_CONV_STATS = 4
+FVT_CONV_W_OHWI = 8
 
 
 class FvtError(RuntimeError):

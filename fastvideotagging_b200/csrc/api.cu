@@ -60,6 +60,7 @@ static int g_disable_tis = 0;    // fvt_set_option("disable_temporal_is", 1): no
 static int g_disable_splitk = 0; // fvt_set_option("disable_split_k", 1): K1 never splits the reduction
 static int g_slab_epi_warps = 8;   // fvt_set_option("slab_epi_warps", 8|16): epilogue warps of the slab kernel.  16 measured SLOWER
                                    // (conv2_x 1x3x3 at batch 48: 756 -> 996 us): the stores are request-throughput-bound, not latency-bound
+static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -161,7 +162,7 @@ static int weight_rows(const fvt_conv_desc* d, int bn) { return (d->cout + bn - 
 // contiguous in w; it is read once, permuted in shared memory and written as taps runs of cin_store bf16.
 __global__ void __launch_bounds__(256)
 pack_weight_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int cin_store,
-                       int cout_real, int cin_real) {
+                       int cout_real, int cin_real, int ohwi) {
   extern __shared__ float srow[];                       // [cin_real * taps]
   const int o = blockIdx.x;
   const int len = cin_real * taps;
@@ -175,7 +176,8 @@ pack_weight_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ 
   const int total = taps * cin_store;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int tap = i / cin_store, ci = i - tap * cin_store;
-    const float v = (live && ci < cin_real) ? srow[ci * taps + tap] : 0.f;
+    // source row layout: (I, taps) for the reference's (O, I, kT, kH, kW); (taps, I) with FVT_CONV_W_OHWI
+    const float v = (live && ci < cin_real) ? srow[ohwi ? tap * cin_real + ci : ci * taps + tap] : 0.f;
     dst[i] = __float2bfloat16_rn(v);
   }
 }
@@ -185,7 +187,7 @@ pack_weight_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ 
 constexpr int kPackR = 8, kPackK = 64;
 __global__ void __launch_bounds__(256)
 pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int taps, int k_store,
-                         int fwd_cin_real, int fwd_cout_real) {
+                         int fwd_cin_real, int fwd_cout_real, int ohwi) {
   extern __shared__ float stile[];                      // [kPackK][kPackR * taps + 1]
   const int r0 = blockIdx.x * kPackR;
   const int k0 = blockIdx.y * kPackK;
@@ -196,7 +198,9 @@ pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict_
     const int rr = j / taps;
     const int k = k0 + kk, r = r0 + rr;
     float v = 0.f;
-    if (k < fwd_cout_real && r < fwd_cin_real) v = __ldg(w + (static_cast<size_t>(k) * fwd_cin_real + r0) * taps + j);
+    if (k < fwd_cout_real && r < fwd_cin_real)
+      v = ohwi ? __ldg(w + (static_cast<size_t>(k) * taps + (j - rr * taps)) * fwd_cin_real + r)
+               : __ldg(w + (static_cast<size_t>(k) * fwd_cin_real + r0) * taps + j);
     stile[kk * pitch + j] = v;
   }
   __syncthreads();
@@ -292,7 +296,7 @@ static int try_wgrad_temporal(const DeviceInfo* di, const fvt_conv_desc* d, cons
   p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
   p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw;
+  p.dw = dw; p.dbg_no_atomics = g_wgrad_no_atomics; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
 
   CUtensorMap tmx, tmdy;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -418,7 +422,7 @@ static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const vo
   p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
   p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw;
+  p.dw = dw; p.dbg_no_atomics = g_wgrad_no_atomics; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
 
   CUtensorMap tmx, tmdy;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -464,6 +468,7 @@ int fvt_version(void) { return 101; }
 
 int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
+  if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
   if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
@@ -526,7 +531,7 @@ int fvt_pack_conv_weight(const fvt_conv_desc* d, const float* w_oidhw, int32_t c
     attr_set[dev] = true;
   }
   pack_weight_fwd_kernel<<<rows, 256, smem, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, taps, d->cin,
-                                                                    cout_real, cin_real);
+                                                                    cout_real, cin_real, (d->flags & FVT_CONV_W_OHWI) ? 1 : 0);
   return check_launch("pack_weight_fwd_kernel");
 }
 
@@ -552,7 +557,8 @@ int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int
     attr_set_d[dev] = true;
   }
   pack_weight_dgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, rows, taps, d->cin,
-                                                                      fwd_cin_real, fwd_cout_real);
+                                                                      fwd_cin_real, fwd_cout_real,
+                                                                      (d->flags & FVT_CONV_W_OHWI) ? 1 : 0);
   return check_launch("pack_weight_dgrad_kernel");
 }
 
@@ -885,7 +891,7 @@ int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, floa
   p.taps = d->kt * d->kh * d->kw;
   p.cin_blocks = (d->cin + 63) / 64;
   p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw;
+  p.dw = dw; p.dbg_no_atomics = g_wgrad_no_atomics; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
   fvt_conv_desc tmp = *d;
   tmp.block_n = 0;
   if (d->cin % 64 != 0 && d->cout % 64 == 0) {

@@ -92,7 +92,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), p.b_stationary ? 1 : 2);   // streamed weights: A and B producers arrive
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -154,7 +154,6 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int cw = ow * p.sw - p.pw;
         const int ch = oh * p.sh - p.ph;
         const int cd = ot * p.st - p.pt;
-        const int n0 = n_blk * p.block_n;
         // this item's k-block range [kb0, kb1) and the filter position of kb0
         const int kb0 = split * p.kb_per_split;
         const int kb1 = kb0 + p.kb_per_split < k_blocks ? kb0 + p.kb_per_split : k_blocks;
@@ -166,11 +165,9 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
           const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
           uint8_t* a_dst = smem_tiles + stage * stage_bytes;
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+            ptx::mbar_arrive_expect_tx(fb, kATileBytes);
             ptx::tma_load_im2col_5d(ptx::smem_u32(a_dst), &tmap_x, fb, cb * kBlockK, cw, ch, cd, on,
                                     static_cast<uint16_t>(dw), static_cast<uint16_t>(dh), static_cast<uint16_t>(dt));
-            if (!p.b_stationary)
-              ptx::tma_load_2d(ptx::smem_u32(a_dst + kATileBytes), &tmap_w, fb, tap * p.k_per_tap + cb * kBlockK, n0);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -178,6 +175,39 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
             cb = 0; ++tap;
             if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
           }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================== weight-tile producer (streamed weights only)
+    // A single issuing thread sustains one TMA per ~275 clk (profiles/r01_tma_rate_microbench.log), so with the input
+    // and the weight tile on one thread the mid-size layers (N <= 256: MMA work per k-block < 550 clk) were paced by the
+    // producer (conv3_x 288->128 temporal: 7900 clk per tile against 3840 clk of MMAs).  The weight tiles therefore come
+    // from their own warp; both producers arrive on the stage's full barrier.
+    if (!p.b_stationary) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_u32 = ptx::smem_u32(full_bar), empty_u32 = ptx::smem_u32(empty_bar);
+      const uint32_t b_dst0 = ptx::smem_u32(smem_tiles) + kATileBytes;
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / p.k_splits;
+        const int split = item - tile * p.k_splits;
+        const int n0 = (tile % p.num_n_tiles) * p.block_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = kb0 + p.kb_per_split < k_blocks ? kb0 + p.kb_per_split : k_blocks;
+        int cb = kb0 % p.cin_blocks;
+        int tap = kb0 / p.cin_blocks;
+        int kcoord = tap * p.k_per_tap + cb * kBlockK;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(empty_u32 + stage * 8, phase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(full_u32 + stage * 8, b_tile_bytes);
+            ptx::tma_load_2d(b_dst0 + stage * stage_bytes, &tmap_w, full_u32 + stage * 8, kcoord, n0);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          kcoord += kBlockK;
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; kcoord = tap * p.k_per_tap; }
         }
       }
     }

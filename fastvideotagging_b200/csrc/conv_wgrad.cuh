@@ -40,6 +40,8 @@ struct WgradParams {
   int cin_real, cout_real;
   int stages;
   float* dw;
+  int w_ohwi;            // dw layout (O, taps, I) instead of (O, I, taps)
+  int dbg_no_atomics;    // experiments only: epilogue reads TMEM, adds nothing
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -187,16 +189,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         uint32_t v[16];
         ptx::tmem_ld_32x32b_x16(taddr + c, v);
         ptx::tmem_ld_wait();
-        if (row_ok) {
+        const int nbase = nt * p.n_tile + c;
+        if (row_ok && !p.dbg_no_atomics && p.mode == 1 && p.w_ohwi && (p.cin_real & 3) == 0 && nbase + 16 <= p.cin_real) {
+          // (O, taps, I) layout, input channels along N: this thread's 16 columns are 16 consecutive floats
+          float* dst = p.dw + (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + nbase;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(__uint_as_float(v[4 * i])),
+                         "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
+                         : "memory");
+        } else if (row_ok && !p.dbg_no_atomics) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int nidx = nt * p.n_tile + c + j;
+            const int nidx = nbase + j;
             if (p.mode == 0) {
               if (nidx < p.cout_real)
-                atomicAdd(p.dw + (static_cast<size_t>(nidx) * p.cin_real + ci) * p.taps + tap, __uint_as_float(v[j]));
+                atomicAdd(p.dw + (p.w_ohwi ? (static_cast<size_t>(nidx) * p.taps + tap) * p.cin_real + ci
+                                           : (static_cast<size_t>(nidx) * p.cin_real + ci) * p.taps + tap), __uint_as_float(v[j]));
             } else {
               if (nidx < p.cin_real)
-                atomicAdd(p.dw + (static_cast<size_t>(co) * p.cin_real + nidx) * p.taps + tap, __uint_as_float(v[j]));
+                atomicAdd(p.dw + (p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + nidx
+                                           : (static_cast<size_t>(co) * p.cin_real + nidx) * p.taps + tap), __uint_as_float(v[j]));
             }
           }
         }

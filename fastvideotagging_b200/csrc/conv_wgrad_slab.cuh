@@ -46,6 +46,8 @@ struct WgradSlabParams {
   int temporal;
   int hw, t_frames, blocks_per_frame, kt, pt, chunks_per_tap;
   float* dw;
+  int w_ohwi;                  // dw layout (O, taps, I) instead of (O, I, taps)
+  int dbg_no_atomics;          // experiments only (fvt_set_option("wgrad_no_atomics")): epilogue reads TMEM, adds nothing
 };
 
 __global__ void __launch_bounds__(kWgsThreads, 1)
@@ -208,12 +210,13 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         uint32_t v[16];
         ptx::tmem_ld_32x32b_x16(taddr + c, v);
         ptx::tmem_ld_wait();
-        if (row_ok) {
+        if (row_ok && !p.dbg_no_atomics) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = nt * p.n_tile + c + j;
             if (co < p.cout_real)
-              atomicAdd(p.dw + (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap, __uint_as_float(v[j]));
+              atomicAdd(p.dw + (p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + ci
+                                         : (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap), __uint_as_float(v[j]));
           }
         }
       }

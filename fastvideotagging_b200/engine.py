@@ -251,8 +251,20 @@ class FlatParams:
         self.m = torch.zeros(self.total, dtype=torch.float32, device=device)
 
     def view(self, buf, name):
+        """The tensor in the reference's shape.  Conv weights are STORED (O, kT, kH, kW, I) — input channels innermost, so
+        the weight-gradient kernels add 32 consecutive floats per warp (FVT_CONV_W_OHWI) — and returned as a permuted
+        (O, I, kT, kH, kW) view; everything else is stored as shaped."""
         off, numel, shape, _ = self.slots[name]
+        if len(shape) == 5:
+            o, i, kt, kh, kw = shape
+            return buf[off:off + numel].view(o, kt, kh, kw, i).permute(0, 4, 1, 2, 3)
         return buf[off:off + numel].view(shape)
+
+    def raw(self, buf, name):
+        """Contiguous storage of a conv weight: (O, kT, kH, kW, I)."""
+        off, numel, shape, _ = self.slots[name]
+        o, i, kt, kh, kw = shape
+        return buf[off:off + numel].view(o, kt, kh, kw, i)
 
     def padded(self, buf, name):
         off, _, _, store = self.slots[name]
@@ -373,10 +385,22 @@ class TrainPlan:
         self._packed_ev = {}
         self._busy = {}                  # scratch buffer name -> event recorded after its last reader on the side stream
         self._draw_i = 0
+        # timing experiments only (tools/gpu_train_ablate.py): FVT_SKIP=wgrad,dgrad,bnbwd leaves those launches out, which
+        # shows each family's marginal cost inside the replayed graph (results are garbage then)
+        self._skip = set(filter(None, os.environ.get("FVT_SKIP", "").split(",")))
 
     # ------------------------------------------------------------------ weights
     def _w(self, L):
         return self.flat.view(self.flat.w, L.w_name)
+
+    def _w_raw(self, L):
+        return self.flat.raw(self.flat.w, L.w_name)
+
+    def _pack_fwd(self, L):
+        if L is self.stem0:       # the stem filter is re-expressed over the W-unfolded input (a tiny tensor: torch ops)
+            L.wp = ops.pack_conv_weight(L.fwd, stem_equivalent_weight(self._w(L)), out=L.wp)
+        else:
+            L.wp = ops.pack_conv_weight(L.fwd, self._w_raw(L), out=L.wp, ohwi=True)
 
     def refresh_weights(self, version):
         """Re-pack bf16 operand copies of the fp32 master weights (forward and data-gradient layouts).  With the side
@@ -389,26 +413,20 @@ class TrainPlan:
         main = torch.cuda.current_stream(self.device)
         if self.side is None:
             for L in self.layers.values():
-                w = self._w(L)
-                if L is self.stem0:
-                    w = stem_equivalent_weight(w)
-                L.wp = ops.pack_conv_weight(L.fwd, w, out=L.wp)               # packed buffers are allocated once
+                self._pack_fwd(L)                                             # packed buffers are allocated once
                 if L.need_dgrad:
-                    L.wpd = ops.pack_conv_weight_dgrad(L.dgr, w, out=L.wpd)
+                    L.wpd = ops.pack_conv_weight_dgrad(L.dgr, self._w_raw(L), out=L.wpd, ohwi=True)
         else:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 for L in self.layers.values():
-                    w = self._w(L)
-                    if L is self.stem0:
-                        w = stem_equivalent_weight(w)
-                    L.wp = ops.pack_conv_weight(L.fwd, w, out=L.wp)
+                    self._pack_fwd(L)
                     ev = torch.cuda.Event()
                     ev.record(self.side)
                     self._packed_ev[L.spec.name] = ev
                 for L in reversed(list(self.layers.values())):
                     if L.need_dgrad:
-                        L.wpd = ops.pack_conv_weight_dgrad(L.dgr, self._w(L), out=L.wpd)
+                        L.wpd = ops.pack_conv_weight_dgrad(L.dgr, self._w_raw(L), out=L.wpd, ohwi=True)
         self.weights_version = version
 
     def _wait_packed(self, L):
@@ -503,6 +521,8 @@ class TrainPlan:
         self.grad_hook(lo, hi)
 
     def _bn_bwd(self, L, dact, mask, draw, dz_out=None):
+        if "bnbwd" in self._skip:
+            return
         gname, bname, _, _ = self._bn_names(L)
         sums = self.flat.padded(self.flat.g, gname)           # [dgamma(c_store) | dbeta(c_store)] adjacent slots
         off_g, off_b = self.flat.slots[gname][0], self.flat.slots[bname][0]
@@ -540,15 +560,19 @@ class TrainPlan:
         self._busy[draw._fvt_key] = ev
 
     def _wgrad_now(self, L, x_in, draw):
+        if "wgrad" in self._skip:
+            return
         if L is self.stem0:
             dweq = torch.zeros((45, 21, 1, 7, 1), dtype=torch.float32, device=self.device)
             ops.conv3d_wgrad(L.fwd, x_in, draw, dweq, 45, 21)
             # dW[o, ci, 0, kh, kw] = dW_eq[o, kw*3+ci, 0, kh, 0]
             self.flat.view(self.flat.g, L.w_name).add_(dweq.reshape(45, 7, 3, 1, 7).permute(0, 2, 3, 4, 1))
         else:
-            ops.conv3d_wgrad(L.fwd, x_in, draw, self.flat.view(self.flat.g, L.w_name), L.cout_real, L.cin_real)
+            ops.conv3d_wgrad(L.fwd, x_in, draw, self.flat.raw(self.flat.g, L.w_name), L.cout_real, L.cin_real, ohwi=True)
 
     def _dgrad(self, L, draw, out, residual=None):
+        if "dgrad" in self._skip:
+            return out
         src = draw
         if L.strided:
             src = ops.zero_insert(draw, L.fwd, out=self._view("up", (L.fwd.n, L.fwd.t, L.fwd.h, L.fwd.w, L.cout_s)))

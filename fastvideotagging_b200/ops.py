@@ -4,7 +4,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, FVT_CONV_RELU, FVT_CONV_RESIDUAL, FVT_CONV_STATS, check
+from ._lib import ConvDesc, FVT_CONV_RELU, FVT_CONV_RESIDUAL, FVT_CONV_STATS, FVT_CONV_W_OHWI, check
 
 
 def pad16(c):
@@ -36,8 +36,15 @@ def conv_out_shape(desc):
     return a.value, b.value, c.value
 
 
-def pack_conv_weight(desc, w_oidhw, out=None):
-    """fp32 (O, I, kT, kH, kW) device tensor -> packed bf16 weights for `desc` (zero padded)."""
+def _with_ohwi(desc):
+    d = ConvDesc(*desc.key())
+    d.flags |= FVT_CONV_W_OHWI
+    return d
+
+
+def pack_conv_weight(desc, w_oidhw, out=None, ohwi=False):
+    """fp32 (O, I, kT, kH, kW) device tensor -> packed bf16 weights for `desc` (zero padded).  ohwi=True: the tensor
+    is the (O, kT, kH, kW, I) storage used by engine.FlatParams (FVT_CONV_W_OHWI)."""
     lib = _lib.load()
     require_cuda(w_oidhw, "weight")
     w = w_oidhw.detach().to(torch.float32).contiguous()
@@ -47,7 +54,9 @@ def pack_conv_weight(desc, w_oidhw, out=None):
     if out is None:
         out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
     assert out.numel() == elems and out.dtype == torch.bfloat16
-    check(lib.fvt_pack_conv_weight(ctypes.byref(desc), _ptr(w), w.shape[0], w.shape[1], _ptr(out), _stream()))
+    d = _with_ohwi(desc) if ohwi else desc
+    cout, cin = (w.shape[0], w.shape[4]) if ohwi else (w.shape[0], w.shape[1])
+    check(lib.fvt_pack_conv_weight(ctypes.byref(d), _ptr(w), cout, cin, _ptr(out), _stream()))
     return out
 
 
@@ -119,14 +128,16 @@ def dgrad_desc(fwd, block_n=0, flags=0):
                     fwd.kt - 1 - fwd.pt, fwd.kh - 1 - fwd.ph, fwd.kw - 1 - fwd.pw, flags, block_n)
 
 
-def pack_conv_weight_dgrad(ddesc, w_oidhw, out=None):
+def pack_conv_weight_dgrad(ddesc, w_oidhw, out=None, ohwi=False):
     lib = _lib.load()
     w = w_oidhw.detach().to(torch.float32).contiguous()
     elems = lib.fvt_conv3d_packed_weight_elems(ctypes.byref(ddesc))
     if out is None:
         out = torch.empty(elems, dtype=torch.bfloat16, device=w.device)
     assert out.numel() == elems and out.dtype == torch.bfloat16
-    check(lib.fvt_pack_conv_weight_dgrad(ctypes.byref(ddesc), _ptr(w), w.shape[0], w.shape[1], _ptr(out), _stream()))
+    d = _with_ohwi(ddesc) if ohwi else ddesc
+    cout, cin = (w.shape[0], w.shape[4]) if ohwi else (w.shape[0], w.shape[1])
+    check(lib.fvt_pack_conv_weight_dgrad(ctypes.byref(d), _ptr(w), cout, cin, _ptr(out), _stream()))
     return out
 
 
@@ -140,11 +151,12 @@ def zero_insert(dy, fwd, out=None):
     return out
 
 
-def conv3d_wgrad(fwd, x, dy, dw, cout_real, cin_real):
-    """dw (fp32, (cout_real, cin_real, kT, kH, kW)) += wgrad(x, dy)."""
+def conv3d_wgrad(fwd, x, dy, dw, cout_real, cin_real, ohwi=False):
+    """dw (fp32, (cout_real, cin_real, kT, kH, kW); ohwi=True: (cout_real, kT, kH, kW, cin_real)) += wgrad(x, dy)."""
     lib = _lib.load()
     assert dw.dtype == torch.float32 and dw.is_contiguous()
-    check(lib.fvt_conv3d_wgrad(ctypes.byref(fwd), _ptr(x), _ptr(dy), _ptr(dw), cout_real, cin_real, _stream()))
+    d = _with_ohwi(fwd) if ohwi else fwd
+    check(lib.fvt_conv3d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), cout_real, cin_real, _stream()))
     return dw
 
 

@@ -37,6 +37,10 @@ typedef enum fvt_status {
 #define FVT_CONV_RELU 1      /* y = max(y, 0)                       (Activation 'relu', R2Plus1.py:33,60,81)   */
 #define FVT_CONV_RESIDUAL 2  /* y += residual before the ReLU       (nd.relu(y+x), R2Plus1.py:81; net.py:100)   */
 #define FVT_CONV_STATS 4     /* accumulate per-channel sum, sum^2 of the raw conv output (training BatchNorm) */
+#define FVT_CONV_W_OHWI 8    /* fvt_pack_conv_weight[_dgrad] / fvt_conv3d_wgrad only: the fp32 weight (gradient) tensor is
+                              * laid out (O, kT, kH, kW, I) instead of the reference's (O, I, kT, kH, kW).  With input
+                              * channels innermost a warp of the weight-gradient epilogue adds 32 consecutive floats
+                              * (one coalesced reduction) instead of 32 scattered ones.                           */
 
 /* One 3-D convolution (cross-correlation, no bias, dilation 1) — the parameters of nn.Conv3D / mx.sym.Convolution
  * at R2Plus1.py:27-31,34-38,67-70,100-111 and net.py:40-42,49-51,95-96,122-131. */

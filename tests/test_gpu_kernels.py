@@ -236,3 +236,40 @@ def test_bn_finalize_apply_matches_the_two_pass_form(cuda_device, lib, rows, c_r
     var = rf[:, :c_real].double().var(0, unbiased=False)
     assert torch.allclose(o2[2][:c_real].double().cpu(), mean.cpu(), rtol=1e-4, atol=1e-4)
     assert torch.allclose(rv2.double().cpu(), (0.9 * 1.5 + 0.1 * var).cpu(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+                                   (2, 4, 14, 14, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+                                   (2, 4, 28, 28, 64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+                                   (2, 8, 14, 14, 230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+                                   (1, 4, 56, 56, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+                                   (2, 4, 7, 7, 512, 1152, (1, 3, 3), (1, 1, 1), (0, 1, 1))])
+def test_channels_last_weight_layout_matches_reference_layout(cuda_device, lib, shape):
+    """FVT_CONV_W_OHWI: packing from, and weight gradients into, (O, kT, kH, kW, I) storage give the same numbers as the
+    reference's (O, I, kT, kH, kW) layout (packing bit for bit; gradients up to the fp32 atomics order)."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w, cin, cout, k, s, p = shape
+    gen = torch.Generator().manual_seed(cin * 7 + cout)
+    cin_s, cout_s = ops.pad16(cin), ops.pad16(cout)
+    wt = (torch.randn(cout, cin, *k, generator=gen) / (cin * k[0] * k[1] * k[2]) ** 0.5).to(cuda_device)
+    wt_ohwi = wt.permute(0, 2, 3, 4, 1).contiguous()
+    fwd = ops.conv_desc(n, t, h, w, cin_s, cout_s, k, s, p, 0)
+    assert torch.equal(ops.pack_conv_weight(fwd, wt), ops.pack_conv_weight(fwd, wt_ohwi, ohwi=True))
+    dgr = ops.dgrad_desc(fwd)
+    assert torch.equal(ops.pack_conv_weight_dgrad(dgr, wt), ops.pack_conv_weight_dgrad(dgr, wt_ohwi, ohwi=True))
+    x = torch.zeros(n, t, h, w, cin_s)
+    x[..., :cin] = torch.randn(n, t, h, w, cin, generator=gen)
+    x = x.to(torch.bfloat16).to(cuda_device)
+    to, ho, wo = ops.conv_out_shape(fwd)
+    dy = torch.zeros(n, to, ho, wo, cout_s)
+    dy[..., :cout] = torch.randn(n, to, ho, wo, cout, generator=gen)
+    dy = dy.to(torch.bfloat16).to(cuda_device)
+    dw_a = torch.zeros(cout, cin, *k, device=cuda_device)
+    dw_b = torch.zeros(cout, *k, cin, device=cuda_device)
+    ops.conv3d_wgrad(fwd, x, dy, dw_a, cout, cin)
+    ops.conv3d_wgrad(fwd, x, dy, dw_b, cout, cin, ohwi=True)
+    torch.cuda.synchronize()
+    ref = dw_a.permute(0, 2, 3, 4, 1)
+    assert (dw_b - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-6
+    assert dw_b.abs().max().item() > 0

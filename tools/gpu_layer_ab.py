@@ -15,6 +15,10 @@ CASES = [
     ("conv2 temporal+res b48", 48, 32, 56, 56, 144, 64, (3, 1, 1), (1, 0, 0), True),
     ("conv3 spatial 128->288 b48", 48, 16, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1), False),
     ("conv3 temporal 288->128 b48", 48, 16, 28, 28, 288, 128, (3, 1, 1), (1, 0, 0), False),
+    ("conv3 temporal 256->128 b48 (aligned)", 48, 16, 28, 28, 256, 128, (3, 1, 1), (1, 0, 0), False),
+    ("conv3 temporal 320->128 b48 (aligned)", 48, 16, 28, 28, 320, 128, (3, 1, 1), (1, 0, 0), False),
+    ("conv3 temporal 288->128 b48 +res", 48, 16, 28, 28, 288, 128, (3, 1, 1), (1, 0, 0), True),
+    ("conv4 temporal 576->256 b48", 48, 8, 14, 14, 576, 256, (3, 1, 1), (1, 0, 0), False),
     ("conv2 dgrad-spatial 144->64 b4", 4, 32, 56, 56, 144, 64, (1, 3, 3), (0, 1, 1), False),
     ("conv2 spatial 64->144 b4", 4, 32, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1), False),
     ("conv3 spatial 128->288 b4", 4, 16, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1), False),
