@@ -14,9 +14,11 @@ namespace fvt {
 // Reads are coalesced across the warp (adjacent ow -> addresses sw apart, overlapping taps hit L1);
 // writes are fully coalesced (cu*2 contiguous bytes per thread, consecutive threads consecutive pixels).
 // ---------------------------------------------------------------------------------------------------------
+// hpair != 0: the unfolded rows 2*h2 and 2*h2+1 are interleaved per pixel, u2[n,t,h2,ow, (h&1)*CU + k] = u[n,t,h,ow,k]
+// (h even), so the stride-2 walk of the stem conv over H becomes a stride-1 walk over h2 with 2*CU channels.
 template <int CU>
 __global__ void stem_unfold_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ u, int n, int t, int h,
-                                   int w, int wo, int kw_taps, int sw, int pw) {
+                                   int w, int wo, int kw_taps, int sw, int pw, int hpair) {
   const size_t total = static_cast<size_t>(n) * t * h * wo;
   const size_t plane = static_cast<size_t>(h) * w;           // one (n, c, t) frame
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -40,7 +42,9 @@ __global__ void stem_unfold_kernel(const float* __restrict__ x, __nv_bfloat16* _
         }
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(u + i * CU);
+    size_t o = i;
+    if (hpair) o = ((((static_cast<size_t>(in) * t + it) * (h >> 1) + (ih >> 1)) * wo + ow) << 1) + (ih & 1);
+    uint4* dst = reinterpret_cast<uint4*>(u + o * CU);
     const uint4* src = reinterpret_cast<const uint4*>(vals);
 #pragma unroll
     for (int k = 0; k < CU / 8; ++k) dst[k] = src[k];
@@ -85,12 +89,13 @@ using namespace fvt;
 
 extern "C" {
 
-int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
-                    int32_t sw, int32_t pw, int32_t cu, void* stream) {
+static int stem_unfold_launch(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+                              int32_t sw, int32_t pw, int32_t cu, int hpair, void* stream) {
   if (x_ncdhw == nullptr || u == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (n <= 0 || t <= 0 || h <= 0 || w <= 0 || kw_taps <= 0 || sw <= 0 || pw < 0)
     return set_error(FVT_ERR_BAD_DESC, "bad stem unfold extent");
   if (cu != 32 || kw_taps * 3 > cu) return set_error(FVT_ERR_BAD_DESC, "stem unfold supports cu=32 with 3*kw_taps <= 32");
+  if (hpair && (h & 1)) return set_error(FVT_ERR_BAD_DESC, "row-paired stem unfold needs an even height (got %d)", h);
   int st = 0;
   if (current_device_info(&st) == nullptr) return st;
   const int wo = (w + 2 * pw - kw_taps) / sw + 1;
@@ -98,8 +103,18 @@ int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   stem_unfold_kernel<32><<<static_cast<int>(blocks), 256, 0, (cudaStream_t)stream>>>(
-      x_ncdhw, (__nv_bfloat16*)u, n, t, h, w, wo, kw_taps, sw, pw);
+      x_ncdhw, (__nv_bfloat16*)u, n, t, h, w, wo, kw_taps, sw, pw, hpair);
   return check_launch("stem_unfold_kernel");
+}
+
+int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+                    int32_t sw, int32_t pw, int32_t cu, void* stream) {
+  return stem_unfold_launch(x_ncdhw, u, n, t, h, w, kw_taps, sw, pw, cu, 0, stream);
+}
+
+int fvt_stem_unfold_hpair(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+                          int32_t sw, int32_t pw, int32_t cu, void* stream) {
+  return stem_unfold_launch(x_ncdhw, u, n, t, h, w, kw_taps, sw, pw, cu, 1, stream);
 }
 
 int fvt_pool_fc_fwd(const void* x, int32_t n, int32_t positions, int32_t c, int32_t c_real, const float* w,

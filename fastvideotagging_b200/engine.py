@@ -119,6 +119,50 @@ def stem_equivalent_weight(w):
     return w.permute(0, 4, 1, 2, 3).reshape(o, kw * ci, kt, kh, 1).contiguous()
 
 
+class StemGeometry:
+    """How the 1x7x7 / s(1,2,2) stem conv (reference model/R2Plus1.py:100-104) is laid onto the conv kernels.
+
+    hpair (even H): the clip is W-unfolded with rows 2*h2, 2*h2+1 side by side in 64 channels (ops.stem_unfold_hpair) and
+    the conv becomes a stride-1 (1,5,1) conv, pad (0,2,0), over h2 — eligible for the slab kernels, which read every
+    input row once (the (1,7,1)/s(1,2,1) form re-reads the unfolded input 7 times from L2: 0.65 -> 0.2 ms at batch 48).
+      w2[o, par*32 + kw*3+ci, 0, kh2, 0] = w[o, ci, 0, kh = 2*kh2 + par - 1, kw]    (zero where kh is outside 0..6)
+    otherwise: the (1,7,1)/s(1,2,1) conv over the 32-channel unfold."""
+
+    def __init__(self, h):
+        self.hpair = (h % 2 == 0) and os.environ.get("FVT_STEM_HPAIR", "1") != "0"
+        if self.hpair:
+            self.cin_store, self.kernel, self.stride, self.pad, self.cin_real = 64, (1, 5, 1), (1, 1, 1), (0, 2, 0), 64
+        else:
+            self.cin_store, self.kernel, self.stride, self.pad, self.cin_real = STEM_UNFOLD_CH, (1, 7, 1), (1, 2, 1), (0, 3, 0), 21
+
+    def unfold_shape(self, n, t, h, w):
+        wo = (w + 2 * 3 - 7) // 2 + 1
+        return (n, t, h // 2, wo, 64) if self.hpair else (n, t, h, wo, STEM_UNFOLD_CH)
+
+    def unfold(self, x, out):
+        return ops.stem_unfold_hpair(x, out=out) if self.hpair else ops.stem_unfold(x, out=out)
+
+    def weight(self, w):
+        """(45, 3, 1, 7, 7) -> the equivalent filter over the unfolded input, reference (O, I, kT, kH, kW) layout."""
+        if not self.hpair:
+            return stem_equivalent_weight(w)
+        o = w.shape[0]
+        wp = torch.nn.functional.pad(w[:, :, 0], (0, 0, 1, 2))                 # (o, 3, kh' = kh+1 in 0..9, 7)
+        wp = wp.reshape(o, 3, 5, 2, 7).permute(0, 3, 4, 1, 2).reshape(o, 2, 21, 5)      # [o, par, kw*3+ci, kh2]
+        out = torch.zeros((o, 2, 32, 5), dtype=w.dtype, device=w.device)
+        out[:, :, :21] = wp
+        return out.reshape(o, 64, 1, 5, 1).contiguous()
+
+    def weight_grad(self, dweq):
+        """Inverse map for the gradient: equivalent-filter gradient -> (45, 3, 1, 7, 7)."""
+        o = dweq.shape[0]
+        if not self.hpair:
+            return dweq.reshape(o, 7, 3, 1, 7).permute(0, 2, 3, 4, 1)         # dW[o, ci, 0, kh, kw] = dW_eq[o, kw*3+ci, 0, kh, 0]
+        g = dweq.reshape(o, 2, 32, 5)[:, :, :21].reshape(o, 2, 7, 3, 5)       # [o, par, kw, ci, kh2]
+        g = g.permute(0, 3, 4, 1, 2).reshape(o, 3, 10, 7)[:, :, 1:8]          # [o, ci, kh, kw]
+        return g.unsqueeze(2)
+
+
 class _Layer:
     __slots__ = ("spec", "desc", "w_packed", "scale", "shift", "out_shape", "src", "dst", "res")
 
@@ -170,11 +214,12 @@ class InferencePlan:
 
         # ---- stem: unfold + (1,7,1)/s(1,2,1) conv on K1, then the 3x1x1 temporal conv
         s_sp, s_tm = stem_specs()
-        wo_unf = (w + 2 * 3 - 7) // 2 + 1
-        self.unfold = new_buf("unfold", (n, t, h, wo_unf, STEM_UNFOLD_CH))
-        cur, shp = add_layer(s_sp, (n, t, h, wo_unf), self.unfold, "mid", None,
-                             w_override=stem_equivalent_weight(params["conv1_middle_weight"].detach()),
-                             kernel=(1, 7, 1), stride=(1, 2, 1), pad=(0, 3, 0), cin_store=STEM_UNFOLD_CH)
+        self.stem = StemGeometry(h)
+        ushape = self.stem.unfold_shape(n, t, h, w)
+        self.unfold = new_buf("unfold", ushape)
+        cur, shp = add_layer(s_sp, ushape[:4], self.unfold, "mid", None,
+                             w_override=self.stem.weight(params["conv1_middle_weight"].detach()),
+                             kernel=self.stem.kernel, stride=self.stem.stride, pad=self.stem.pad, cin_store=self.stem.cin_store)
         cur, shp = add_layer(s_tm, shp, cur, "x0", None)
         # ---- residual blocks; block input alternates between x0/x1, intermediates reuse mid / y / sc
         flip = 0
@@ -211,7 +256,7 @@ class InferencePlan:
     def forward(self, x, want_features=False, want_map=False):
         """x: (N, 3, T, H, W) fp32 CUDA -> logits (N, num_class) fp32 [, pooled features (N, 512)]."""
         assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w), (tuple(x.shape), (self.n, 3, self.t, self.h, self.w))
-        ops.stem_unfold(x.contiguous(), out=self._view(self.unfold))
+        self.stem.unfold(x.contiguous(), self._view(self.unfold))
         for L in self.layers:
             ops.conv3d_fwd(L.desc, self._view(L.src), L.w_packed, L.scale, L.shift,
                            self._view(L.res) if L.res is not None else None, out=self._view(L.dst))
@@ -329,11 +374,12 @@ class TrainPlan:
             return L
 
         s_sp, s_tm = stem_specs()
-        wo_unf = (w + 2 * 3 - 7) // 2 + 1
-        self.unfold = buf("unfold", (n, t, h, wo_unf, STEM_UNFOLD_CH))
-        self.stem0 = make(s_sp, (n, t, h, wo_unf), "unfold", kernel=(1, 7, 1), stride=(1, 2, 1), pad=(0, 3, 0),
-                          cin_store=STEM_UNFOLD_CH, need_dgrad=False)
-        self.stem0.cin_real = 21
+        self.stem = StemGeometry(h)
+        ushape = self.stem.unfold_shape(n, t, h, w)
+        self.unfold = buf("unfold", ushape)
+        self.stem0 = make(s_sp, ushape[:4], "unfold", kernel=self.stem.kernel, stride=self.stem.stride, pad=self.stem.pad,
+                          cin_store=self.stem.cin_store, need_dgrad=False)
+        self.stem0.cin_real = self.stem.cin_real
         self.stem1 = make(s_tm, self.stem0.out_shape, s_sp.name + ":act")
         cur_name, cur_shape = s_tm.name + ":act", self.stem1.out_shape
         max_elems = max(self.stem0.raw.numel(), self.stem1.raw.numel())
@@ -398,7 +444,7 @@ class TrainPlan:
 
     def _pack_fwd(self, L):
         if L is self.stem0:       # the stem filter is re-expressed over the W-unfolded input (a tiny tensor: torch ops)
-            L.wp = ops.pack_conv_weight(L.fwd, stem_equivalent_weight(self._w(L)), out=L.wp)
+            L.wp = ops.pack_conv_weight(L.fwd, self.stem.weight(self._w(L)), out=L.wp)
         else:
             L.wp = ops.pack_conv_weight(L.fwd, self._w_raw(L), out=L.wp, ohwi=True)
 
@@ -489,7 +535,7 @@ class TrainPlan:
 
     def _forward_body(self, x):
         self.stats_all.zero_()
-        ops.stem_unfold(x, out=self.unfold)
+        self.stem.unfold(x, self.unfold)
         B = self.bufs
         for L in (self.stem0, self.stem1):
             self._conv_bn(L, B[L.src], apply={})
@@ -563,10 +609,10 @@ class TrainPlan:
         if "wgrad" in self._skip:
             return
         if L is self.stem0:
-            dweq = torch.zeros((45, 21, 1, 7, 1), dtype=torch.float32, device=self.device)
-            ops.conv3d_wgrad(L.fwd, x_in, draw, dweq, 45, 21)
-            # dW[o, ci, 0, kh, kw] = dW_eq[o, kw*3+ci, 0, kh, 0]
-            self.flat.view(self.flat.g, L.w_name).add_(dweq.reshape(45, 7, 3, 1, 7).permute(0, 2, 3, 4, 1))
+            k = self.stem.kernel
+            dweq = torch.zeros((45, self.stem.cin_real, k[0], k[1], k[2]), dtype=torch.float32, device=self.device)
+            ops.conv3d_wgrad(L.fwd, x_in, draw, dweq, 45, self.stem.cin_real)
+            self.flat.view(self.flat.g, L.w_name).add_(self.stem.weight_grad(dweq))
         else:
             ops.conv3d_wgrad(L.fwd, x_in, draw, self.flat.raw(self.flat.g, L.w_name), L.cout_real, L.cin_real, ohwi=True)
 

@@ -103,6 +103,19 @@ def stem_unfold(x_ncdhw, kw_taps=7, sw=2, pw=3, cu=32, out=None):
     return out
 
 
+def stem_unfold_hpair(x_ncdhw, kw_taps=7, sw=2, pw=3, cu=32, out=None):
+    """(N, 3, T, H, W) fp32, H even -> (N, T, H/2, Wo, 2*cu) bf16 with u2[..., (h&1)*cu + kw*3+ci] = x[n, ci, t, h, ow*sw-pw+kw]."""
+    lib = _lib.load()
+    require_cuda(x_ncdhw, "clips")
+    assert x_ncdhw.dtype == torch.float32 and x_ncdhw.is_contiguous() and x_ncdhw.shape[1] == 3
+    n, _, t, h, w = x_ncdhw.shape
+    wo = (w + 2 * pw - kw_taps) // sw + 1
+    if out is None:
+        out = torch.empty((n, t, h // 2, wo, 2 * cu), dtype=torch.bfloat16, device=x_ncdhw.device)
+    check(lib.fvt_stem_unfold_hpair(_ptr(x_ncdhw), _ptr(out), n, t, h, w, kw_taps, sw, pw, cu, _stream()))
+    return out
+
+
 def pool_fc_fwd(x, c_real, weight, bias, want_pooled=False):
     """x: (N, T, H, W, C) bf16 -> logits (N, num_class) fp32 [and pooled (N, c_real) fp32]."""
     lib = _lib.load()

@@ -94,6 +94,12 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
  * conv over u with cin = cu. */
 int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
                     int32_t sw, int32_t pw, int32_t cu, void* stream);
+/* Row-paired variant (h even): u2[n,t,h/2,ow, (h&1)*cu + kw*3+ci] — rows 2*h2 and 2*h2+1 side by side in 2*cu channels.
+ * The stem's stride-2 walk over H is then a STRIDE-1 (1,5,1) conv over h2 with pad (0,2,0) (w2[o, par*cu+kw*3+ci, kh2] =
+ * w[o, ci, kh = 2*kh2+par-1, kw], zero where kh is outside 0..6), which the slab kernel runs reading every input row
+ * once instead of 7 times (same reference call sites as fvt_stem_unfold). */
+int fvt_stem_unfold_hpair(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+                          int32_t sw, int32_t pw, int32_t cu, void* stream);
 
 /* ---- head: global average pool + dense (A5) ------------------------------------------------------------------ */
 /* x: [n, positions, c] bf16 (NDHWC with T*H*W flattened); pooled (optional out): [n, c] fp32;

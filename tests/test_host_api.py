@@ -61,3 +61,41 @@ def test_blocks_refuse_cpu_tensors():
     from fastvideotagging_b200.model import R3DBlock
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         R3DBlock(64, 64, comp_index=0)(torch.zeros(1, 64, 2, 8, 8))
+
+
+def test_row_paired_stem_geometry_is_the_same_convolution():
+    """engine.StemGeometry (CPU, torch only): the stride-1 (1,5,1) conv over the row-paired W-unfolded clip with the
+    re-expressed filter equals the reference's Conv3D(45,(1,7,7),s(1,2,2),p(0,3,3)) (model/R2Plus1.py:100-104), and
+    weight_grad is the adjoint of weight (so gradients map back exactly)."""
+    import torch
+    import torch.nn.functional as F
+    from fastvideotagging_b200.engine import StemGeometry
+    gen = torch.Generator().manual_seed(0)
+    n, t, h, w = 2, 3, 16, 20
+    x = torch.randn(n, 3, t, h, w, generator=gen, dtype=torch.float64)
+    wt = torch.randn(45, 3, 1, 7, 7, generator=gen, dtype=torch.float64)
+    ref = F.conv3d(x, wt, stride=(1, 2, 2), padding=(0, 3, 3))
+    for hpair in (True, False):
+        geo = StemGeometry(h if hpair else h + 1)
+        assert geo.hpair == hpair
+        wo = (w + 6 - 7) // 2 + 1
+        xp = F.pad(x, (3, 3))
+        # W-unfold by definition: u[n,t,h,ow,kw*3+ci] = x[n,ci,t,h,2*ow-3+kw]
+        u = torch.stack([xp[..., 2 * ow:2 * ow + 7] for ow in range(wo)], dim=-2)       # (n,3,t,h,wo,7)
+        u = u.permute(0, 2, 3, 4, 5, 1).reshape(n, t, h, wo, 21)
+        if hpair:
+            u32 = torch.zeros(n, t, h, wo, 32, dtype=x.dtype)
+            u32[..., :21] = u
+            u2 = u32.reshape(n, t, h // 2, 2, wo, 32).permute(0, 1, 2, 4, 3, 5).reshape(n, t, h // 2, wo, 64)
+            inp, cin = u2, 64
+        else:
+            inp, cin = u, 21
+        weq = geo.weight(wt)
+        assert tuple(weq.shape) == (45, cin, *geo.kernel)
+        got = F.conv3d(inp.permute(0, 4, 1, 2, 3), weq, stride=geo.stride, padding=geo.pad)
+        assert got.shape == ref.shape
+        assert torch.allclose(got, ref, atol=1e-10)
+        g = torch.randn(weq.shape, generator=gen, dtype=torch.float64)
+        lhs = (weq * g).sum()
+        rhs = (wt * geo.weight_grad(g)).sum()
+        assert abs(lhs.item() - rhs.item()) < 1e-9 * max(1.0, abs(lhs.item()))
