@@ -66,6 +66,8 @@ def load():
         "fvt_conv3d_fwd": (ctypes.c_int, [dp, vp, vp, fp, fp, vp, vp, fp, vp, ctypes.c_size_t, vp]),
         "fvt_stem_unfold": (ctypes.c_int, [fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         "fvt_stem_unfold_hpair": (ctypes.c_int, [fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+        "fvt_conv3d_fwd_f32": (ctypes.c_int, [dp, fp, fp, fp, fp, fp, fp, vp]),
+        "fvt_pool_fc_fwd_f32": (ctypes.c_int, [fp, i32, i32, i32, fp, fp, i32, fp, fp, vp]),
         "fvt_pool_fc_fwd": (ctypes.c_int, [vp, i32, i32, i32, i32, fp, fp, i32, fp, fp, vp]),
         "fvt_pack_conv_weight_dgrad": (ctypes.c_int, [dp, fp, i32, i32, vp, vp]),
         "fvt_conv3d_wgrad": (ctypes.c_int, [dp, vp, vp, fp, i32, i32, vp]),

@@ -265,6 +265,76 @@ class InferencePlan:
         return ops.pool_fc_fwd(self._view(self.final), 512, self.fc_w, self.fc_b, want_pooled=want_features)
 
 
+class InferencePlanF32:
+    """Eval-mode forward in plain fp32 (north-star "fp32 path", BASELINE configs[0]): the same layer plan on
+    ops.conv3d_fwd_f32 / pool_fc_fwd_f32, activations NDHWC fp32 with the real channel counts.  Verification-grade speed
+    (CUDA cores); it pins the layer semantics against an fp32 reference at 1e-4, which bf16 storage cannot."""
+
+    def __init__(self, params, aux, model_depth, num_class, pool, eps, n, t, h, w, device):
+        self.n, self.t, self.h, self.w = n, t, h, w
+        self.pool = pool
+        self.layers = []
+
+        def add_layer(spec, in_shape, res):
+            flags = (FVT_CONV_RELU if (spec.relu or res) else 0) | (FVT_CONV_RESIDUAL if res else 0)
+            nn_, tt, hh, ww = in_shape[:4]
+            d = ops.conv_desc(nn_, tt, hh, ww, spec.cin, spec.cout, spec.kernel, spec.stride, spec.pad, flags)
+            wt = params[spec.name + "_weight"].detach().float().permute(2, 3, 4, 1, 0).contiguous()      # (kT,kH,kW,I,O)
+            g, b = params[spec.bn + "_gamma"].detach().float(), params[spec.bn + "_beta"].detach().float()
+            m, v = aux[spec.bn + "_moving_mean"].float(), aux[spec.bn + "_moving_var"].float()
+            scale = (g / torch.sqrt(v + eps)).contiguous()
+            shift = (b - m * scale).contiguous()
+            to, ho, wo = ((tt + 2 * spec.pad[0] - spec.kernel[0]) // spec.stride[0] + 1,
+                          (hh + 2 * spec.pad[1] - spec.kernel[1]) // spec.stride[1] + 1,
+                          (ww + 2 * spec.pad[2] - spec.kernel[2]) // spec.stride[2] + 1)
+            self.layers.append((d, wt, scale, shift))
+            return (nn_, to, ho, wo, spec.cout)
+
+        s_sp, s_tm = stem_specs()
+        shp = add_layer(s_sp, (n, t, h, w), False)
+        shp = add_layer(s_tm, shp, False)
+        self.blocks = []
+        for comp, cin, cout, down in network_blocks(model_depth):
+            main, short = block_specs(comp, cin, cout, down)
+            first = len(self.layers)
+            x_shape = shp
+            sa = add_layer(main[0], x_shape, False)
+            sb = add_layer(main[1], sa, False)
+            sc_ = add_layer(main[2], sb, False)
+            has_short = short is not None
+            if has_short:
+                add_layer(short, x_shape, False)
+            shp = add_layer(main[3], sc_, True)
+            self.blocks.append((first, has_short))
+        tp, hp, wp = shp[1] - pool[0] + 1, shp[2] - pool[1] + 1, shp[3] - pool[2] + 1
+        if (tp, hp, wp) != (1, 1, 1):
+            raise ValueError("AvgPool3D%s over a %s map leaves %s: only a global pool is supported" % (pool, shp[1:4], (tp, hp, wp)))
+        self.fc_w = params["final_fc_weight"].detach().float().contiguous()
+        self.fc_b = params["final_fc_bias"].detach().float().contiguous()
+        self.launches = len(self.layers) + 1
+
+    def _run(self, idx, x, res=None):
+        d, wt, scale, shift = self.layers[idx]
+        return ops.conv3d_fwd_f32(d, x, wt, scale, shift, res)
+
+    def forward(self, x, want_features=False, want_map=False):
+        assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w)
+        cur = x.float().permute(0, 2, 3, 4, 1).contiguous()              # NCDHW -> NDHWC (layout only)
+        cur = self._run(1, self._run(0, cur))
+        for first, has_short in self.blocks:
+            a = self._run(first, cur)
+            b = self._run(first + 1, a)
+            c = self._run(first + 2, b)
+            if has_short:
+                res = self._run(first + 3, cur)
+                cur = self._run(first + 4, c, res)
+            else:
+                cur = self._run(first + 3, c, cur)
+        if want_map:
+            return cur
+        return ops.pool_fc_fwd_f32(cur, self.fc_w, self.fc_b, want_pooled=want_features)
+
+
 # =====================================================================================================================
 # training
 # =====================================================================================================================

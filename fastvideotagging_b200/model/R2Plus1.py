@@ -54,15 +54,19 @@ class R2Plus2D(torch.nn.Module):
     """R(2+1)D-{10,16,18,26,34} (reference model/R2Plus1.py:93-254).
 
     forward(x): x is (N, 3, T, H, W) fp32 on a CUDA device; returns (N, num_class) fp32 logits (no activation,
-    :171).  `final_temporal_kernel` / `final_spatial_kernel` are the AvgPool3D window and must cover the whole
+    :171).  precision='fp32' runs eval-mode forwards on the plain-fp32 kernels (the reference's own number type; slow,
+    for checking against fp32 references at 1e-4); training always uses the bf16-storage tcgen05 path.  `final_temporal_kernel` / `final_spatial_kernel` are the AvgPool3D window and must cover the whole
     conv5 map (T/8, H/16), as every reference caller arranges (train.py:39-40, R2Plus1.py:370).
     """
 
     def __init__(self, num_class, model_depth, final_spatial_kernel=7, final_temporal_kernel=2, with_bias=False,
-                 bn_eps=BN_EPS_GLUON):
+                 bn_eps=BN_EPS_GLUON, precision="bf16"):
         super().__init__()
         if with_bias:
             raise NotImplementedError("with_bias=True is never used by the reference callers; conv bias is not built")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (tcgen05 kernels, the fast path) or 'fp32' (CUDA-core inference path)")
+        self.precision = precision
         self.num_class = num_class
         self.model_depth = model_depth
         self.pool = (final_temporal_kernel, final_spatial_kernel, final_spatial_kernel)
@@ -264,8 +268,8 @@ class R2Plus2D(torch.nn.Module):
             n, _, t, h, w = x.shape
             params = {k: getattr(self, k) for k in self._param_names}
             aux = {k: getattr(self, k) for k in self._aux_names}
-            plan = engine.InferencePlan(params, aux, self.model_depth, self.num_class, self.pool, self.bn_eps,
-                                        n, t, h, w, x.device)
+            cls = engine.InferencePlanF32 if self.precision == "fp32" else engine.InferencePlan
+            plan = cls(params, aux, self.model_depth, self.num_class, self.pool, self.bn_eps, n, t, h, w, x.device)
             self._plans[key] = plan
         return plan
 

@@ -218,3 +218,31 @@ def pool_fc_bwd(dlogits, pooled, weight, dw, db, dx):
     positions = dx.numel() // (n * c_store)
     check(lib.fvt_pool_fc_bwd(_ptr(dlogits), _ptr(pooled), _ptr(weight), n, k, c, positions, _ptr(dw), _ptr(db), _ptr(dx),
                               c_store, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ fp32 path
+def conv3d_fwd_f32(desc, x, w_thwio, scale=None, shift=None, residual=None, out=None):
+    """fp32 NDHWC conv (+ folded BN / residual / ReLU per desc.flags) on the CUDA cores; weights (kT, kH, kW, I, O)."""
+    lib = _lib.load()
+    require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.is_contiguous() and w_thwio.dtype == torch.float32 and w_thwio.is_contiguous()
+    to, ho, wo = ((desc.t + 2 * desc.pt - desc.kt) // desc.st + 1, (desc.h + 2 * desc.ph - desc.kh) // desc.sh + 1,
+                  (desc.w + 2 * desc.pw - desc.kw) // desc.sw + 1)
+    if out is None:
+        out = torch.empty((desc.n, to, ho, wo, desc.cout), dtype=torch.float32, device=x.device)
+    check(lib.fvt_conv3d_fwd_f32(ctypes.byref(desc), _ptr(x), _ptr(w_thwio), _ptr(scale), _ptr(shift), _ptr(residual),
+                                 _ptr(out), _stream()))
+    return out
+
+
+def pool_fc_fwd_f32(x, weight, bias, want_pooled=False):
+    """x: (N, T, H, W, C) fp32 -> logits (N, num_class) fp32 [and pooled (N, C)]."""
+    lib = _lib.load()
+    require_cuda(x, "x")
+    n, c = x.shape[0], x.shape[-1]
+    positions = x.numel() // (n * c)
+    logits = torch.empty((n, weight.shape[0]), dtype=torch.float32, device=x.device)
+    pooled = torch.empty((n, c), dtype=torch.float32, device=x.device) if want_pooled else None
+    check(lib.fvt_pool_fc_fwd_f32(_ptr(x), n, positions, c, _ptr(weight), _ptr(bias), weight.shape[0], _ptr(pooled),
+                                  _ptr(logits), _stream()))
+    return (logits, pooled) if want_pooled else logits

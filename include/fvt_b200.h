@@ -101,6 +101,16 @@ int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t
 int fvt_stem_unfold_hpair(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
                           int32_t sw, int32_t pw, int32_t cu, void* stream);
 
+/* ---- fp32 path (inference only) --------------------------------------------------------------------------------
+ * The same convolution + folded-BatchNorm / residual / ReLU epilogue in plain fp32 on the CUDA cores: activations NDHWC
+ * fp32 with the REAL channel counts (no padding rule), weights (kT, kH, kW, I, O) fp32.  desc.flags: FVT_CONV_RELU,
+ * FVT_CONV_RESIDUAL.  It exists to check the layer semantics against an fp32 reference at rel 1e-4 (north-star "fp32
+ * path", BASELINE configs[0]: the reference's own fp32 CPU-runnable case); the bf16 tcgen05 kernels are the fast path. */
+int fvt_conv3d_fwd_f32(const fvt_conv_desc* desc, const float* x, const float* w_thwio, const float* scale,
+                       const float* shift, const float* residual, float* y, void* stream);
+int fvt_pool_fc_fwd_f32(const float* x, int32_t n, int32_t positions, int32_t c, const float* w, const float* b,
+                        int32_t num_class, float* pooled, float* logits, void* stream);
+
 /* ---- head: global average pool + dense (A5) ------------------------------------------------------------------ */
 /* x: [n, positions, c] bf16 (NDHWC with T*H*W flattened); pooled (optional out): [n, c] fp32;
  * logits[n, k] = sum_c pooled[n,c] * w[k,c] + b[k]   (AvgPool3D + Dense, R2Plus1.py:168-171,243-245). */

@@ -93,3 +93,57 @@ def test_full_size_batch48_properties(cuda_device):
     scale = np.abs(ref).max()
     assert np.abs(full[[7, 41]] - ref).max() <= 5e-3 * scale + 1e-4
     assert (full[[7, 41]].argmax(1) == ref.argmax(1)).all()
+
+
+def test_fp32_path_baseline_config0(cuda_device):
+    """BASELINE configs[0] — the reference's own fp32 case: R(2+1)D-18 forward, batch 2, 8x112x112 clips, 101 classes,
+    random init — through the fp32 path (fvt_conv3d_fwd_f32 / fvt_pool_fc_fwd_f32).  North-star tolerance for the fp32
+    path: logits within rel 1e-4 of the reference (here the oracle's fp32 restatement), identical top-1 / top-5."""
+    from fastvideotagging_b200.model import R2Plus2D
+    depth, n, t, hw = 18, 2, 8, 112
+    pool = (1, 7, 7)
+    params = orc.randomize_bn(orc.init_params(depth, 101, seed=0), seed=1)
+    x = _clips(n, t, hw, hw)
+    net = R2Plus2D(101, depth, final_spatial_kernel=7, final_temporal_kernel=1, precision="fp32").to(cuda_device)
+    net.load_param_dict(params)
+    net.eval()
+    with torch.no_grad():
+        got = net(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+        feat = net.extract_features(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    ref, pooled = orc.Net(params, depth, pool).forward(x)
+    ref64, _ = orc.Net(params, depth, pool, dtype=torch.float64).forward(x)
+    ref, ref64 = ref.numpy(), ref64.numpy()
+    scale = np.abs(ref64).max()
+    assert np.abs(got - ref64).max() <= 1e-4 * scale, (np.abs(got - ref64).max(), scale)
+    assert np.abs(got - ref).max() <= 1e-4 * scale
+    assert (got.argmax(1) == ref64.argmax(1)).all()
+    assert (np.argsort(-got, 1)[:, :5] == np.argsort(-ref64, 1)[:, :5]).all()
+    assert feat.shape == (n, 512, 1, 1, 1)
+    assert np.abs(feat.reshape(n, 512) - pooled.numpy().reshape(n, 512)).max() <= 1e-4 * np.abs(pooled.numpy()).max()
+
+
+def test_fp32_conv_kernel_against_torch(cuda_device):
+    """fvt_conv3d_fwd_f32 on odd shapes (strides, pads, channel counts that are not multiples of anything) with the
+    affine + residual + ReLU epilogue, against torch's fp64 conv."""
+    import torch.nn.functional as F
+    from fastvideotagging_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    for (n, t, h, w, cin, cout, k, s, p) in [(2, 5, 9, 11, 3, 45, (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+                                             (1, 6, 7, 7, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+                                             (2, 4, 10, 10, 64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+                                             (1, 8, 6, 6, 230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+                                             (3, 4, 8, 8, 64, 128, (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+                                             (1, 4, 6, 6, 37, 33, (3, 3, 3), (1, 1, 1), (1, 1, 1))]:
+        x = torch.randn(n, cin, t, h, w, generator=gen)
+        wt = torch.randn(cout, cin, *k, generator=gen) / (cin * k[0] * k[1] * k[2]) ** 0.5
+        sc, sh = 0.5 + torch.rand(cout, generator=gen), torch.randn(cout, generator=gen)
+        ref = F.conv3d(x.double(), wt.double(), stride=s, padding=p)
+        res = torch.randn(ref.shape, generator=gen)
+        ref = torch.relu(ref * sc.double().view(1, -1, 1, 1, 1) + sh.double().view(1, -1, 1, 1, 1) + res.double())
+        d = ops.conv_desc(n, t, h, w, cin, cout, k, s, p, ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+        got = ops.conv3d_fwd_f32(d, x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device),
+                                 wt.permute(2, 3, 4, 1, 0).contiguous().to(cuda_device), sc.to(cuda_device), sh.to(cuda_device),
+                                 res.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
+        got = got.permute(0, 4, 1, 2, 3).cpu().double()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-6, (k, s)
