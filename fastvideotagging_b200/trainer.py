@@ -110,3 +110,72 @@ class Trainer:
                                               _CHUNK, ctypes.c_float(self._lr), ctypes.c_float(self.momentum),
                                               ctypes.c_float(1.0 / float(batch_size)), _stream()))
         net._weights_changed()
+
+
+# ------------------------------------------------------------------------------------------------ LR schedules
+class FactorScheduler:
+    """`mx.lr_scheduler.FactorScheduler(step, factor)` as used at reference train.py:75-77: the rate is multiplied by
+    `factor` every `step` updates (MXNet semantics: applied once `num_update` EXCEEDS count + step; floor
+    `stop_factor_lr`).  Third-party MXNet behaviour, restated."""
+
+    def __init__(self, step, factor=1.0, stop_factor_lr=1e-8, base_lr=0.01):
+        if step < 1:
+            raise ValueError("Schedule step must be greater or equal than 1 round")
+        if factor > 1.0:
+            raise ValueError("Factor must be no more than 1 to make lr reduce")
+        self.step, self.factor, self.stop_factor_lr, self.base_lr = step, factor, stop_factor_lr, base_lr
+        self.count = 0
+
+    def __call__(self, num_update):
+        while num_update > self.count + self.step:
+            self.count += self.step
+            self.base_lr *= self.factor
+            if self.base_lr < self.stop_factor_lr:
+                self.base_lr = self.stop_factor_lr
+        return self.base_lr
+
+
+class MultiFactorScheduler:
+    """`mx.lr_scheduler.MultiFactorScheduler(step=[...], factor)` — reference train_simple_r3d.py:99-100, evaluated once
+    per EPOCH there (`trainer.set_learning_rate(lr_sch(epoch))`, :106): the rate is multiplied by `factor` each time
+    `num_update` exceeds the next entry of `step`."""
+
+    def __init__(self, step, factor=1.0, base_lr=0.01):
+        if not isinstance(step, (list, tuple)) or len(step) < 1:
+            raise ValueError("step must be a non-empty list")
+        for i, s in enumerate(step):
+            if i != 0 and step[i] <= step[i - 1]:
+                raise ValueError("Schedule step must be an increasing integer list")
+            if s < 1:
+                raise ValueError("Schedule step must be greater or equal than 1 round")
+        if factor > 1.0:
+            raise ValueError("Factor must be no more than 1 to make lr reduce")
+        self.step, self.factor, self.base_lr = list(step), factor, base_lr
+        self.cur_step_ind, self.count = 0, 0
+
+    def __call__(self, num_update):
+        while self.cur_step_ind <= len(self.step) - 1:
+            if num_update > self.step[self.cur_step_ind]:
+                self.count = self.step[self.cur_step_ind]
+                self.cur_step_ind += 1
+                self.base_lr *= self.factor
+            else:
+                return self.base_lr
+        return self.base_lr
+
+
+def split_and_load(data, ctx_list, batch_axis=0, even_split=True):
+    """`gluon.utils.split_and_load` (reference train_simple_r3d.py:110-111): slice a batch along `batch_axis` into one
+    piece per device.  With one process per GPU `ctx_list` normally has one entry."""
+    n = len(ctx_list)
+    size = data.shape[batch_axis]
+    if even_split and size % n != 0:
+        raise ValueError("data with shape %s cannot be evenly split into %d slices along axis %d" % (tuple(data.shape), n, batch_axis))
+    step = size // n
+    out = []
+    for i, ctx in enumerate(ctx_list):
+        lo = i * step
+        hi = size if i == n - 1 else (i + 1) * step
+        piece = data.narrow(batch_axis, lo, hi - lo)
+        out.append(piece.to(ctx) if ctx is not None else piece)
+    return out

@@ -99,3 +99,24 @@ def test_row_paired_stem_geometry_is_the_same_convolution():
         lhs = (weq * g).sum()
         rhs = (wt * geo.weight_grad(g)).sum()
         assert abs(lhs.item() - rhs.item()) < 1e-9 * max(1.0, abs(lhs.item()))
+
+
+def test_lr_schedulers_follow_mxnet_semantics():
+    """FactorScheduler / MultiFactorScheduler as the reference drives them (train.py:75-77; train_simple_r3d.py:99-106,
+    per epoch with steps "2,5,10")."""
+    from fastvideotagging_b200.trainer import FactorScheduler, MultiFactorScheduler, split_and_load
+    import numpy as np
+    import torch
+    s = MultiFactorScheduler([2, 5, 10], 0.1)
+    s.base_lr = 1e-2
+    got = [s(e) for e in range(13)]
+    exp = [1e-2] * 3 + [1e-3] * 3 + [1e-4] * 5 + [1e-5] * 2          # the factor applies once the epoch EXCEEDS a step
+    assert np.allclose(got, exp, rtol=1e-12)
+    f = FactorScheduler(step=4, factor=0.5, base_lr=1.0)
+    assert [f(i) for i in (0, 4, 5, 8, 9, 13)] == [1.0, 1.0, 0.5, 0.5, 0.25, 0.125]
+    with pytest.raises(ValueError):
+        MultiFactorScheduler([5, 2], 0.1)
+    parts = split_and_load(torch.arange(12).reshape(6, 2), [None, None, None])
+    assert [p.shape[0] for p in parts] == [2, 2, 2] and parts[2][0, 0].item() == 8
+    with pytest.raises(ValueError):
+        split_and_load(torch.zeros(5, 2), [None, None])
