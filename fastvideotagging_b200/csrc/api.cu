@@ -57,6 +57,10 @@ static int g_ring_prefetch = 4;  // fvt_set_option("ring_prefetch", f): K1t L2 p
 static int g_disable_ring = 0;   // fvt_set_option("disable_frame_ring", 1): temporal convs go through K1 (im2col)
 static int g_slab_single_stage = 1;   // fvt_set_option("slab_single_stage", 0): keep two input stages even with a shallow weight ring
 static int g_disable_tis = 0;    // fvt_set_option("disable_temporal_is", 1): no input-stationary temporal kernel (K1i)
+static int g_disable_tis_tma_store = 1;  // fvt_set_option("disable_tis_tma_store", 0) turns the TMA-store epilogue of K1i ON.  Measured
+                                         // SLOWER than the register stores it replaces (conv2_x 144->64 at batch 48: 399 -> 422 us,
+                                         // with residual 562 -> 641 us): the staging tiles cost a pipeline stage (main loop 357 ->
+                                         // 394 us) and the two 256-thread barriers per tile serialise the eight epilogue warps
 static int g_disable_splitk = 0; // fvt_set_option("disable_split_k", 1): K1 never splits the reduction
 static int g_slab_epi_warps = 8;   // fvt_set_option("slab_epi_warps", 8|16): epilogue warps of the slab kernel.  16 measured SLOWER
                                    // (conv2_x 1x3x3 at batch 48: 756 -> 996 us): the stores are request-throughput-bound, not latency-bound
@@ -468,6 +472,7 @@ int fvt_version(void) { return 101; }
 
 int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
+  if (name != nullptr && strcmp(name, "disable_tis_tma_store") == 0) { g_disable_tis_tma_store = value; return 0; }
   if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
@@ -682,10 +687,15 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     const int aux = (512 + 16 * bn + 255) / 256 * 256;
     const int w_bytes = d->kt * tp.cin_blocks * bn * 128;
     const int stage_bytes = tp.cin_blocks * 128 * 128;
-    int stages = (kSmemMax - aux - w_bytes) / stage_bytes;
+    // TMA-store epilogue for one-row-is-one-line outputs (64 channels): two [128 x 128 B] staging tiles, paid for with
+    // one pipeline stage (a stage is released as soon as its frame's MMAs are issued, two are enough to stream)
+    tp.tma_store = (!g_disable_tis_tma_store && bn == 64 && d->cout == 64 &&
+                    w_bytes + aux + 2 * kTisOutTileBytes + 2 * stage_bytes <= kSmemMax) ? 1 : 0;
+    const int out_bytes = tp.tma_store ? 2 * kTisOutTileBytes : 0;
+    int stages = (kSmemMax - aux - w_bytes - out_bytes) / stage_bytes;
     if (stages > kTisMaxStages) stages = kTisMaxStages;
     const double useful = (double)tp.hw / (tp.blocks_per_frame * 128.0);
-    if (w_bytes + aux < kSmemMax && stages >= 3 && tp.acc_slots >= d->kt + 1 && useful >= 0.6) {
+    if (w_bytes + aux < kSmemMax && stages >= (tp.tma_store ? 2 : 3) && tp.acc_slots >= d->kt + 1 && useful >= 0.6) {
       tp.stages = stages;
       int chunks = 1;
       while (chunks * 2 <= d->t && d->t % (chunks * 2) == 0 && d->n * tp.blocks_per_frame * chunks < 2 * di->sm_count &&
@@ -707,6 +717,15 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(temporal-is x) failed (CUresult %d)", (int)r);
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
+      CUtensorMap tmy = tmx;                               // placeholder when the TMA-store epilogue is off
+      if (tp.tma_store) {
+        const cuuint64_t ydims[4] = {(cuuint64_t)d->cout, (cuuint64_t)tp.hw, (cuuint64_t)d->t, (cuuint64_t)d->n};
+        const cuuint64_t ystrides[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * tp.hw, (cuuint64_t)d->cout * 2 * tp.hw * d->t};
+        CUresult ry = di->encode_tiled(&tmy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, ydims, ystrides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (ry != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(temporal-is y) failed (CUresult %d)", (int)ry);
+      }
       static bool attr_set_t[16] = {false};
       int dev = 0;
       cudaGetDevice(&dev);
@@ -715,9 +734,9 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
         if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_temporal_is_kernel): %s", cudaGetErrorString(e));
         attr_set_t[dev] = true;
       }
-      const int smem_bytes = w_bytes + stages * stage_bytes + aux;
+      const int smem_bytes = w_bytes + stages * stage_bytes + out_bytes + aux;
       const int grid = tp.num_items < di->sm_count ? tp.num_items : di->sm_count;
-      conv_temporal_is_kernel<<<grid, kTisThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, tp);
+      conv_temporal_is_kernel<<<grid, kTisThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, tmy, tp);
       return check_launch("conv_temporal_is_kernel");
     }
   }

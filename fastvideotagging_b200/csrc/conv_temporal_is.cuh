@@ -35,6 +35,7 @@ struct TemporalIsParams {
   int acc_slots;              // S: output accumulators rotating through TMEM
   int stages;
   int cout_store, flags;
+  int tma_store;              // 1: output tiles leave through shared memory + TMA (n_tile == cout_store == 64)
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
@@ -42,9 +43,11 @@ struct TemporalIsParams {
   float* stats;
 };
 
+constexpr int kTisOutTileBytes = 128 * 128;     // [128 positions x 64 channels] bf16 staging tile (TMA-store epilogue)
+
 __global__ void __launch_bounds__(kTisThreads, 1)
 conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                        const TemporalIsParams p) {
+                        const __grid_constant__ CUtensorMap tmap_y, const TemporalIsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -56,7 +59,8 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   const int stage_bytes = CB * (128 * 128);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + w_bytes;
-  uint8_t* aux = smem_a + p.stages * stage_bytes;
+  uint8_t* smem_o = smem_a + p.stages * stage_bytes;           // [2][kTisOutTileBytes] when p.tma_store
+  uint8_t* aux = smem_o + (p.tma_store ? 2 * kTisOutTileBytes : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);       // [kTisMaxStages]
   uint64_t* empty_bar = full_bar + kTisMaxStages;
   uint64_t* acc_full = empty_bar + kTisMaxStages;              // [kTisMaxAcc]
@@ -69,6 +73,7 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_x);
     ptx::prefetch_tensormap(&tmap_w);
+    if (p.tma_store) ptx::prefetch_tensormap(&tmap_y);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -208,6 +213,7 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     ea.scale_smem = p.scale != nullptr ? affine_smem : nullptr; ea.shift_smem = affine_smem + p.n_tile;
     ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem; ea.stat_stride = p.n_tile;
     const int r = q * 32 + lane;
+    int obuf = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int b = item % p.blocks_per_frame;
       const int rest = item / p.blocks_per_frame;
@@ -217,6 +223,13 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       for (int lo = 0; lo < p.t_chunk; ++lo) {
         const int tt = chunk * p.t_chunk + lo;
         const long long out_row = pos < p.hw ? (static_cast<long long>(n) * p.t + tt) * p.hw + pos : -1ll;
+        if (p.tma_store) {
+          // the TMA store that read this staging buffer two tiles ago must have finished reading it
+          if (et == 0) ptx::tma_store_wait_read<1>();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          ea.stage_smem = ptx::smem_u32(smem_o + obuf * kTisOutTileBytes);
+          ea.stage_row = r;
+        }
         epilogue_prefetch_residual(ea, 0, out_row, grp);
         ptx::mbar_wait(ptx::smem_u32(&acc_full[slot]), par);
         ptx::tc_fence_after();
@@ -226,8 +239,18 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty[slot]));
         if (++slot == p.acc_slots) { slot = 0; par ^= 1u; }
+        if (p.tma_store) {
+          ptx::fence_proxy_async_smem();                 // generic-proxy writes -> visible to the TMA (async proxy)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            ptx::tma_store_4d(&tmap_y, ea.stage_smem, 0, b * 128, tt, n);     // positions >= H*W are clipped by the map
+            ptx::tma_store_commit();
+          }
+          obuf ^= 1;
+        }
       }
     }
+    if (p.tma_store && et == 0) ptx::tma_store_wait<0>();
   }
 
   ptx::tc_fence_before();

@@ -33,6 +33,11 @@ struct EpilogueArgs {
   float* stat_smem;                 // [2][stat_stride] per-CTA partial sums (kConvStats)
   int stat_stride;
   int ngrp = 2;                     // epilogue warps per TMEM lane quadrant: warp `grp` takes chunks grp, grp+ngrp, ...
+  // TMA-store epilogue (N tile == 64 channels == one 128-byte row): instead of 32-byte global stores from every thread
+  // (32 different lines per warp instruction: the L2 request path, not HBM, paces the narrow-N layers) the bf16 row
+  // segments go into a 128B-swizzled [128 x 128 B] shared-memory tile that one thread hands to the TMA unit.
+  uint32_t stage_smem = 0;          // shared-memory address of this tile's staging buffer (0: store to global)
+  int stage_row = 0;                // this thread's row inside the tile
 };
 
 // Issued BEFORE waiting for the accumulator: pulls this thread's residual row segments into L2 so that the residual
@@ -126,7 +131,7 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
         f[4 * i + 3] = fmaf(f[4 * i + 3], a.w, b.w);
       }
     }
-    if (row_ok && !(p.flags & kDbgNoStore)) {
+    if ((row_ok || p.stage_smem != 0u) && !(p.flags & kDbgNoStore)) {
       if (has_res) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -141,7 +146,15 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
       uint32_t o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-      ptx::st_global_256(yrow + ch0, o);          // one full 32-byte sector per thread
+      if (p.stage_smem != 0u) {
+        // chunk ci covers the 16-byte units 2ci, 2ci+1 of the row; SWIZZLE_128B stores unit j at j ^ (row & 7)
+        const uint32_t rowb = p.stage_smem + static_cast<uint32_t>(p.stage_row) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(p.stage_row) & 7u;
+        ptx::st_shared_128(rowb + (((2u * ci) ^ sw) << 4), o[0], o[1], o[2], o[3]);
+        ptx::st_shared_128(rowb + (((2u * ci + 1u) ^ sw) << 4), o[4], o[5], o[6], o[7]);
+      } else {
+        ptx::st_global_256(yrow + ch0, o);          // one full 32-byte sector per thread
+      }
     }
   }
 }

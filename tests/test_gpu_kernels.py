@@ -273,3 +273,28 @@ def test_channels_last_weight_layout_matches_reference_layout(cuda_device, lib, 
     ref = dw_a.permute(0, 2, 3, 4, 1)
     assert (dw_b - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-6
     assert dw_b.abs().max().item() > 0
+
+
+def test_temporal_is_tma_store_epilogue_matches_register_stores(cuda_device, lib):
+    """K1i's optional TMA-store epilogue (off by default: measured slower) writes bit-identical outputs, including the
+    clipped partial position block (14*14 = 196 positions) and the residual + ReLU + affine epilogue."""
+    import torch
+    from fastvideotagging_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    for (n, t, h, w) in [(2, 6, 14, 14), (1, 4, 56, 56)]:
+        x = (torch.randn(n, t, h, w, 144, generator=gen) * 0.5).to(torch.bfloat16).to(cuda_device)
+        wt = (torch.randn(64, 144, 3, 1, 1, generator=gen) / 432 ** 0.5).to(cuda_device)
+        res = torch.randn(n, t, h, w, 64, generator=gen).to(torch.bfloat16).to(cuda_device)
+        sc = (0.5 + torch.rand(64, generator=gen)).to(cuda_device)
+        sh = torch.randn(64, generator=gen).to(cuda_device)
+        d = ops.conv_desc(n, t, h, w, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+        wp = ops.pack_conv_weight(d, wt)
+        a = ops.conv3d_fwd(d, x, wp, sc, sh, res).clone()
+        assert lib.fvt_set_option(b"disable_tis_tma_store", 0) == 0
+        try:
+            b = ops.conv3d_fwd(d, x, wp, sc, sh, res).clone()
+        finally:
+            lib.fvt_set_option(b"disable_tis_tma_store", 1)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        assert a.float().abs().max().item() > 0
