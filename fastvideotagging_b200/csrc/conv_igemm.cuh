@@ -326,6 +326,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         ea.scale_smem = has_affine ? affine_smem : nullptr; ea.shift_smem = affine_smem + kMaxCout;
         ea.residual = p.residual; ea.y = p.y;
         ea.stat_smem = acc_stats ? affine_smem + n0 : stat_smem; ea.stat_stride = acc_stats ? kMaxCout : 256;
+        ea.stat_mask = stat_mask_below(static_cast<long long>(m_blk) * kBlockM + q * 32, lane, p.m_total);
         epilogue_chunks(ea, taddr, n0, row_ok ? static_cast<long long>(row) : -1ll, grp, lane);
       }
       // release the accumulator stage (all of this warp's TMEM reads have completed: wait::ld above)

@@ -308,10 +308,27 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem; ea.stat_stride = p.n_tile;
     const int r = q * 32 + lane;                 // GEMM row = padded position m' inside the tile
     const int hl = r / p.wp, wl = r - hl * p.wp;
+    // rows whose statistics this thread gathers (16x256b fragment: q*32 + lane/4 + 8j): tile-invariant (hl, wl)
+    int shl[4];
+    uint32_t smask_static = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rj = q * 32 + (lane >> 2) + 8 * j;
+      shl[j] = rj / p.wp;
+      const int swl = rj - shl[j] * p.wp;
+      if (shl[j] < p.r_out && swl < p.w) smask_static |= 1u << j;
+    }
     for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
       const int frame = mt / p.tiles_per_frame;
       const int h0 = (mt - frame * p.tiles_per_frame) * p.r_out;
       const bool ok = hl < p.r_out && wl < p.w && (h0 + hl) < p.h;
+      {
+        uint32_t m = smask_static;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (h0 + shl[j] >= p.h) m &= ~(1u << j);
+        ea.stat_mask = m;
+      }
       const long long out_row = ok ? (static_cast<long long>(frame) * p.h + h0 + hl) * p.w + wl : -1ll;
       for (int nt = 0; nt < p.num_n_tiles; ++nt) {
         const int n0 = nt * p.n_tile;

@@ -220,6 +220,7 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int chunk = rest % p.chunks_per_clip;
       const int n = rest / p.chunks_per_clip;
       const int pos = b * 128 + r;
+      ea.stat_mask = stat_mask_below(static_cast<long long>(b) * 128 + q * 32, lane, p.hw);
       for (int lo = 0; lo < p.t_chunk; ++lo) {
         const int tt = chunk * p.t_chunk + lo;
         const long long out_row = pos < p.hw ? (static_cast<long long>(n) * p.t + tt) * p.hw + pos : -1ll;

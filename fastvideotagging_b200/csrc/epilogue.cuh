@@ -38,7 +38,17 @@ struct EpilogueArgs {
   // segments go into a 128B-swizzled [128 x 128 B] shared-memory tile that one thread hands to the TMA unit.
   uint32_t stage_smem = 0;          // shared-memory address of this tile's staging buffer (0: store to global)
   int stage_row = 0;                // this thread's row inside the tile
+  // kConvStats: bit j set <=> row (lane/4) + 8*j of this warp's 32 accumulator rows is a real output pixel
+  uint32_t stat_mask = 0xFu;
 };
+
+// Row-validity mask for the statistics of this warp's rows base + (lane/4) + 8*j, j = 0..3, against a row limit.
+__device__ __forceinline__ uint32_t stat_mask_below(long long base_row, int lane, long long limit) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m |= (base_row + (lane >> 2) + 8 * j < limit) ? (1u << j) : 0u;
+  return m;
+}
 
 // Issued BEFORE waiting for the accumulator: pulls this thread's residual row segments into L2 so that the residual
 // loads of the epilogue proper do not expose DRAM latency (the epilogue of the residual convs was the bottleneck:
@@ -52,9 +62,9 @@ __device__ __forceinline__ void epilogue_prefetch_residual(const EpilogueArgs& p
 
 // taddr: TMEM address of (this warp's first lane, column 0 of the tile); n0: first absolute channel of the tile;
 // out_row: row of Y this thread's accumulator row maps to, or < 0 when the row is padding / out of range.
-__device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t taddr, int n0, long long out_row,
-                                                int grp, int lane) {
-  const bool do_stats = (p.flags & kConvStats) != 0;
+template <bool do_stats>
+__device__ __forceinline__ void epilogue_chunks_impl(const EpilogueArgs& p, uint32_t taddr, int n0, long long out_row,
+                                                     int grp, int lane) {
   const bool has_affine = p.scale_smem != nullptr;
   const bool has_res = (p.flags & kConvResidual) != 0;
   const bool relu = (p.flags & kConvRelu) != 0;
@@ -65,10 +75,15 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
   const __nv_bfloat16* rrow = has_res ? p.residual + static_cast<size_t>(row_ok ? out_row : 0) * p.cout_store : nullptr;
   // software pipeline: TMEM load + residual load of chunk i+1 are in flight while chunk i is processed
   uint32_t v[16], vn[16];
+  uint32_t sa[8], sb[8], san[8], sbn[8];          // statistics fragments (16x256b shape: 4 rows x 4 columns per thread)
   uint32_t rr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int ci = grp;
   if (ci < n_chunks) {
     ptx::tmem_ld_32x32b_x16(taddr + ci * 16, vn);
+    if (do_stats) {
+      ptx::tmem_ld_16x256b_x2(taddr + ci * 16, san);
+      ptx::tmem_ld_16x256b_x2(taddr + (16u << 16) + ci * 16, sbn);
+    }
     if (has_res && n0 + ci * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + ci * 16, rn);
   }
   const int ngrp = p.ngrp;
@@ -78,11 +93,19 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
     for (int i = 0; i < 16; ++i) v[i] = vn[i];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rr[i] = rn[i];
+    if (do_stats) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sa[i] = san[i]; sb[i] = sbn[i]; }
+    }
     const int c = ci * 16;
     const int ch0 = n0 + c;
     const int cnext = ci + ngrp;
     if (cnext < n_chunks) {
       ptx::tmem_ld_32x32b_x16(taddr + cnext * 16, vn);
+      if (do_stats) {
+        ptx::tmem_ld_16x256b_x2(taddr + cnext * 16, san);
+        ptx::tmem_ld_16x256b_x2(taddr + (16u << 16) + cnext * 16, sbn);
+      }
       if (has_res && n0 + cnext * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + cnext * 16, rn);
     }
     if (ch0 >= p.cout_store) continue;           // N tail (weights zero-padded to a whole tile)
@@ -90,34 +113,54 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
     if (do_stats) {
-      // per-channel sum / sum^2 over this warp's 32 rows: recursive-halving butterfly, 16 values -> 1 per lane pair
-      float s1[16], s2[16];
+      // Per-channel sum / sum^2 over this warp's 32 rows.  The accumulator chunk is read a second time in the 16x256b
+      // shape, where a thread holds FOUR rows (lane/4 + 8j) of four columns (2*(lane%4) + {0, 1, 8, 9}): the rows are
+      // added locally and only the 8 row-groups (lane bits 2..4) remain to be combined — 7 shuffles per chunk for both
+      // quantities instead of 32 with one row per thread.  Statistics are those of the value actually stored
+      // (bf16-rounded); rows beyond the tensor contribute 0 (p.stat_mask).
+      float a8[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        // statistics of the value that is actually stored (bf16-rounded); rows beyond M contribute 0
-        float r = row_ok ? __bfloat162float(__float2bfloat16_rn(f[i])) : 0.f;
-        s1[i] = r; s2[i] = r * r;
+      for (int k = 0; k < 4; ++k) {                 // column k of this thread: registers (k&1) + 4*(k>>1) [+2 for row +8]
+        const int reg = (k & 1) + 4 * (k >> 1);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {               // row j: fragment (sa: rows 0..15, sb: rows 16..31), register +2 for +8
+          const uint32_t raw = (j < 2 ? sa : sb)[reg + 2 * (j & 1)];
+          float r = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw)));
+          r = ((p.stat_mask >> j) & 1u) ? r : 0.f;
+          s1 += r; s2 = fmaf(r, r, s2);
+        }
+        a8[k] = s1; a8[4 + k] = s2;
       }
+      // recursive halving over lane bits 4, 3, 2: 8 -> 4 -> 2 -> 1 values
+      {
+        const bool up = (lane & 16) != 0;
 #pragma unroll
-      for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-        const bool upper = (lane & bit) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-          const float send1 = upper ? s1[i] : s1[i + half];
-          const float keep1 = upper ? s1[i + half] : s1[i];
-          const float send2 = upper ? s2[i] : s2[i + half];
-          const float keep2 = upper ? s2[i + half] : s2[i];
-          s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, bit);
-          s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, bit);
+        for (int i = 0; i < 4; ++i) {
+          const float send = up ? a8[i] : a8[i + 4];
+          const float keep = up ? a8[i + 4] : a8[i];
+          a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
       }
-      s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
-      s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
-      if ((lane & 1) == 0) {
-        const int chl = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-        atomicAdd(&stat_smem[c + chl], s1[0]);
-        atomicAdd(&stat_smem[p.stat_stride + c + chl], s2[0]);
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = up ? a8[i] : a8[i + 2];
+          const float keep = up ? a8[i + 2] : a8[i];
+          a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
       }
+      {
+        const bool up = (lane & 4) != 0;
+        const float send = up ? a8[0] : a8[1];
+        const float keep = up ? a8[1] : a8[0];
+        a8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      // lane bit 4: quantity (sum / sum^2); bits 3,2: which of this thread's four columns; bits 1,0: column pair
+      const int kcol = ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+      const int col = 2 * (lane & 3) + (kcol & 1) + ((kcol & 2) ? 8 : 0);
+      atomicAdd(&stat_smem[((lane & 16) ? p.stat_stride : 0) + c + col], a8[0]);
     }
     if (has_affine) {
       const float4* sc4 = reinterpret_cast<const float4*>(p.scale_smem + ch0);
@@ -157,6 +200,14 @@ __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t 
       }
     }
   }
+}
+
+// Two instantiations: the statistics variant (training forward) carries the extra TMEM fragments and shuffles; the
+// inference variant must not pay for them in registers or scheduling.
+__device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t taddr, int n0, long long out_row,
+                                                int grp, int lane) {
+  if (p.flags & kConvStats) epilogue_chunks_impl<true>(p, taddr, n0, out_row, grp, lane);
+  else epilogue_chunks_impl<false>(p, taddr, n0, out_row, grp, lane);
 }
 
 }  // namespace fvt

@@ -155,6 +155,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bits, twice (16 columns): thread t receives rows (t/4) and (t/4)+8 of the 16-lane window, columns
+// 2*(t%4), +1 (registers 0,1 / 2,3) and 8 + 2*(t%4), +1 (registers 4,5 / 6,7) — measured layout,
+// profiles/r01_tmem_ld_16x256b_layout.log.  Four rows x four columns per thread after two calls (lane offsets 0, 16):
+// column sums then need 3 butterfly steps instead of 5.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- 256-bit global access (sm_100: LDG/STG.256)
