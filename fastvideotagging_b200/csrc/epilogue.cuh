@@ -120,17 +120,20 @@ __device__ __forceinline__ void epilogue_chunks_impl(const EpilogueArgs& p, uint
       // (bf16-rounded); rows beyond the tensor contribute 0 (p.stat_mask).
       float a8[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {                 // column k of this thread: registers (k&1) + 4*(k>>1) [+2 for row +8]
-        const int reg = (k & 1) + 4 * (k >> 1);
-        float s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < 8; ++i) a8[i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {               // row j: fragment (sa: rows 0..15, sb: rows 16..31), register +2 for +8
-          const uint32_t raw = (j < 2 ? sa : sb)[reg + 2 * (j & 1)];
-          float r = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw)));
-          r = ((p.stat_mask >> j) & 1u) ? r : 0.f;
-          s1 += r; s2 = fmaf(r, r, s2);
+      for (int j = 0; j < 4; ++j) {                 // row j: fragment (sa: rows 0..15, sb: rows 16..31), registers +2 for +8
+        const bool live = ((p.stat_mask >> j) & 1u) != 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {               // column pair h: registers 4h, 4h+1 (columns 2*(lane%4) + 8h, +1)
+          const int reg = 4 * h + 2 * (j & 1);
+          const uint32_t* frag = j < 2 ? sa : sb;
+          // one packed conversion rounds both columns to bf16 (the stored values); unpack = shift / mask
+          const uint32_t pk = pack_bf16x2(__uint_as_float(frag[reg]), __uint_as_float(frag[reg + 1]));
+          const float r0 = live ? bf16_lo(pk) : 0.f, r1 = live ? bf16_hi(pk) : 0.f;
+          a8[2 * h] += r0;     a8[4 + 2 * h] = fmaf(r0, r0, a8[4 + 2 * h]);
+          a8[2 * h + 1] += r1; a8[5 + 2 * h] = fmaf(r1, r1, a8[5 + 2 * h]);
         }
-        a8[k] = s1; a8[4 + k] = s2;
       }
       // recursive halving over lane bits 4, 3, 2: 8 -> 4 -> 2 -> 1 values
       {
