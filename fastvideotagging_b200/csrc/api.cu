@@ -64,6 +64,10 @@ static int g_disable_tis_tma_store = 1;  // fvt_set_option("disable_tis_tma_stor
 static int g_disable_splitk = 0; // fvt_set_option("disable_split_k", 1): K1 never splits the reduction
 static int g_slab_epi_warps = 8;   // fvt_set_option("slab_epi_warps", 8|16): epilogue warps of the slab kernel.  16 measured SLOWER
                                    // (conv2_x 1x3x3 at batch 48: 756 -> 996 us): the stores are request-throughput-bound, not latency-bound
+static int g_wgrad_atomic_rate = 0;    // fvt_set_option("wgrad_atomic_rate", r): fp32 reductions per clock assumed by the K3s tiling
+                                       // heuristic as a launch-wide flush cost.  0 = ignore it (default): with r = 150 the
+                                       // heuristic picks fewer pixel splits and the step's weight gradients get SLOWER
+                                       // (3.74 -> 4.06 ms; conv2_x 116 -> 157 us) — the flush overlaps other CTAs' MMAs
 static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
@@ -398,7 +402,13 @@ static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const vo
       const double per_tile = mma_clk > bytes / 64.0 ? mma_clk : bytes / 64.0;
       const int waves = (items * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
       const double epi = (double)mt * n_tile * 40.0;            // atomics of one accumulator block
-      const double est = waves * (tps * per_tile + epi + 3000.0);
+      // every CTA of the launch flushes mt*128*n_tile fp32 reductions, and the L2 atomic units retire only ~150 of them per
+      // clock GPU-wide (measured: the 69 weight gradients of a step take 3.9 ms with, 2.6 ms without the reductions), so
+      // the flush is a launch-wide cost that grows with the number of pixel splits
+      const double ctas = (double)items * ((p.num_tiles + tps - 1) / tps);
+      const double glob = g_wgrad_atomic_rate > 0 ? ctas * mt * 128.0 * n_tile / (double)g_wgrad_atomic_rate : 0.0;
+      const double flush = waves * epi > glob ? waves * epi : glob;
+      const double est = waves * (tps * per_tile + 3000.0) + flush;
       if (est < best) { best = est; best_nt = nt; best_mt = mt; }
     }
   }
@@ -473,6 +483,7 @@ int fvt_version(void) { return 101; }
 int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
   if (name != nullptr && strcmp(name, "disable_tis_tma_store") == 0) { g_disable_tis_tma_store = value; return 0; }
+  if (name != nullptr && strcmp(name, "wgrad_atomic_rate") == 0) { g_wgrad_atomic_rate = value; return 0; }
   if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
