@@ -627,6 +627,13 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
         sp.b_stationary = 1;
         sp.b_ring = b_all;
         sp.stages = (kSmemMax - aux - b_all * b_slab) / stage_bytes;
+      } else if (g_slab_single_stage && sp.num_n_tiles == 1 && b_all <= kSlabMaxBRing &&
+                 b_all * b_slab + stage_bytes + aux <= kSmemMax) {
+        // the filter fits beside ONE input stage: resident weights + L2-prefetched single-stage input beats re-streaming
+        // the whole filter for every tile
+        sp.b_stationary = 1;
+        sp.b_ring = b_all;
+        sp.stages = 1;
       } else {
         sp.b_stationary = 0;
         sp.stages = 2;

@@ -20,6 +20,8 @@ CASES = [
     ("conv3 temporal 288->128 b48 +res", 48, 16, 28, 28, 288, 128, (3, 1, 1), (1, 0, 0), True),
     ("conv4 temporal 576->256 b48", 48, 8, 14, 14, 576, 256, (3, 1, 1), (1, 0, 0), False),
     ("conv2 dgrad-spatial 144->64 b4", 4, 32, 56, 56, 144, 64, (1, 3, 3), (0, 1, 1), False),
+    ("dgrad-part 128->64 1x3x3 b4", 4, 32, 56, 56, 128, 64, (1, 3, 3), (0, 1, 1), False),
+    ("dgrad-part 16->64 1x3x3 +res b4", 4, 32, 56, 56, 16, 64, (1, 3, 3), (0, 1, 1), True),
     ("conv2 spatial 64->144 b4", 4, 32, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1), False),
     ("conv3 spatial 128->288 b4", 4, 16, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1), False),
     ("conv3 dgrad-spatial 288->128 b4", 4, 16, 28, 28, 288, 128, (1, 3, 3), (0, 1, 1), False),
