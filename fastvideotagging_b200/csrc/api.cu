@@ -12,6 +12,7 @@
 #include "conv_igemm.cuh"
 #include "conv_wgrad.cuh"
 #include "conv_slab.cuh"
+#include "conv_slab_pair.cuh"
 #include "conv_wgrad_slab.cuh"
 #include "conv_frame_ring.cuh"
 #include "conv_temporal_is.cuh"
@@ -69,6 +70,8 @@ static int g_wgrad_atomic_rate = 0;    // fvt_set_option("wgrad_atomic_rate", r)
                                        // heuristic picks fewer pixel splits and the step's weight gradients get SLOWER
                                        // (3.74 -> 4.06 ms; conv2_x 116 -> 157 us) — the flush overlaps other CTAs' MMAs
 static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
+static int g_slab_pair = 0;      // fvt_set_option("slab_pair", 0|1|2): CTA-pair slab kernel (cta_group::2) for stationary-filter layers;
+                                 // 2 = pair kernel with register stores instead of the staged TMA store (A/B runs)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
 
@@ -485,6 +488,7 @@ int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "disable_tis_tma_store") == 0) { g_disable_tis_tma_store = value; return 0; }
   if (name != nullptr && strcmp(name, "wgrad_atomic_rate") == 0) { g_wgrad_atomic_rate = value; return 0; }
   if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
+  if (name != nullptr && strcmp(name, "slab_pair") == 0) { g_slab_pair = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
   if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
@@ -668,6 +672,62 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(slab x) failed (CUresult %d)", (int)r);
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
+      // ---- K1s2: the same convolution on a CTA pair (tcgen05.mma.cta_group::2) when the filter is stationary: each CTA
+      //      holds half of the filter rows, which frees shared memory for the staged TMA-store epilogue
+      if (g_slab_pair && sp.b_stationary && sp.num_n_tiles == 1 && bn % 16 == 0 && sp.box_rows == sp.r_in &&
+          !(want_stats && scale != nullptr) && di->sm_count % 2 == 0) {
+        SlabPairParams pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.s = sp;
+        pp.n_half = bn / 2;
+        const int num_m_tiles = sp.frames * sp.tiles_per_frame;
+        pp.num_pairs = (num_m_tiles + 1) / 2;
+        pp.tma_store = (g_slab_pair == 1 && bn == d->cout) ? 1 : 0;
+        pp.out_tile_bytes = (sp.r_out * d->w * d->cout * 2 + 1023) / 1024 * 1024;
+        const int aux2 = (512 + 8 * bn + 255) / 256 * 256;
+        const int b_bytes = (b_all * pp.n_half * 128 + 1023) / 1024 * 1024;
+        const int out_bytes = pp.tma_store ? 2 * pp.out_tile_bytes : 0;
+        int stages2 = (kSmemMax - aux2 - b_bytes - out_bytes) / stage_bytes;
+        if (stages2 > kPairMaxStages) stages2 = kPairMaxStages;
+        if (stages2 >= 2) {
+          pp.s.stages = stages2;
+          pp.s.b_ring = b_all;
+          CUtensorMap tmw2, tmy = tmx;
+          if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, pp.n_half, &tmw2)) return e;
+          if (pp.tma_store) {
+            const cuuint64_t ydims[4] = {(cuuint64_t)d->cout, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)sp.frames};
+            const cuuint64_t ystr[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * d->w, (cuuint64_t)d->cout * 2 * d->w * d->h};
+            const cuuint32_t ybox[4] = {(cuuint32_t)d->cout, (cuuint32_t)d->w, (cuuint32_t)sp.r_out, 1};
+            CUresult ry = di->encode_tiled(&tmy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, ydims, ystr, ybox, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ry != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(slab pair y) failed (CUresult %d)", (int)ry);
+          }
+          static bool attr_set_p[16] = {false};
+          int devp = 0;
+          cudaGetDevice(&devp);
+          if (!attr_set_p[devp]) {
+            cudaError_t e = cudaFuncSetAttribute(conv_slab_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+            if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_pair_kernel): %s", cudaGetErrorString(e));
+            attr_set_p[devp] = true;
+          }
+          const int smem2 = b_bytes + stages2 * stage_bytes + out_bytes + aux2;
+          int clusters = pp.num_pairs < di->sm_count / 2 ? pp.num_pairs : di->sm_count / 2;
+          cudaLaunchConfig_t cfg;
+          memset(&cfg, 0, sizeof(cfg));
+          cfg.gridDim = dim3(2 * clusters);
+          cfg.blockDim = dim3(kPairThreads);
+          cfg.dynamicSmemBytes = smem2;
+          cfg.stream = (cudaStream_t)stream;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          cudaError_t le = cudaLaunchKernelEx(&cfg, conv_slab_pair_kernel, tmx, tmw2, tmy, pp);
+          if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "conv_slab_pair_kernel launch: %s", cudaGetErrorString(le));
+          return check_launch("conv_slab_pair_kernel");
+        }
+      }
       static bool attr_set_s[16] = {false};
       int dev = 0;
       cudaGetDevice(&dev);

@@ -37,7 +37,9 @@ struct EpilogueArgs {
   // (32 different lines per warp instruction: the L2 request path, not HBM, paces the narrow-N layers) the bf16 row
   // segments go into a 128B-swizzled [128 x 128 B] shared-memory tile that one thread hands to the TMA unit.
   uint32_t stage_smem = 0;          // shared-memory address of this tile's staging buffer (0: store to global)
-  int stage_row = 0;                // this thread's row inside the tile
+  int stage_row = 0;                // this thread's row inside the staging tile (< 0: padding row, nothing staged)
+  int stage_pitch = 128;            // bytes per staged row
+  int stage_swizzle = 1;            // 1: 128-byte rows, SWIZZLE_128B (unit j at j ^ (row & 7)); 0: dense rows, no swizzle
   // kConvStats: bit j set <=> row (lane/4) + 8*j of this warp's 32 accumulator rows is a real output pixel
   uint32_t stat_mask = 0xFu;
 };
@@ -193,11 +195,13 @@ __device__ __forceinline__ void epilogue_chunks_impl(const EpilogueArgs& p, uint
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
       if (p.stage_smem != 0u) {
-        // chunk ci covers the 16-byte units 2ci, 2ci+1 of the row; SWIZZLE_128B stores unit j at j ^ (row & 7)
-        const uint32_t rowb = p.stage_smem + static_cast<uint32_t>(p.stage_row) * 128u;
-        const uint32_t sw = static_cast<uint32_t>(p.stage_row) & 7u;
-        ptx::st_shared_128(rowb + (((2u * ci) ^ sw) << 4), o[0], o[1], o[2], o[3]);
-        ptx::st_shared_128(rowb + (((2u * ci + 1u) ^ sw) << 4), o[4], o[5], o[6], o[7]);
+        if (p.stage_row >= 0) {
+          // chunk ci covers the 16-byte units 2ci, 2ci+1 of the row; SWIZZLE_128B stores unit j at j ^ (row & 7)
+          const uint32_t rowb = p.stage_smem + static_cast<uint32_t>(p.stage_row) * static_cast<uint32_t>(p.stage_pitch);
+          const uint32_t sw = p.stage_swizzle ? (static_cast<uint32_t>(p.stage_row) & 7u) : 0u;
+          ptx::st_shared_128(rowb + (((2u * ci) ^ sw) << 4), o[0], o[1], o[2], o[3]);
+          ptx::st_shared_128(rowb + (((2u * ci + 1u) ^ sw) << 4), o[4], o[5], o[6], o[7]);
+        }
       } else {
         ptx::st_global_256(yrow + ch0, o);          // one full 32-byte sector per thread
       }

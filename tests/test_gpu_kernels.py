@@ -298,3 +298,47 @@ def test_temporal_is_tma_store_epilogue_matches_register_stores(cuda_device, lib
         torch.cuda.synchronize()
         assert torch.equal(a, b)
         assert a.float().abs().max().item() > 0
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1)),      # conv2_x 1x3x3
+                                   (1, 3, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1)),      # odd number of tiles: one dummy tile
+                                   (1, 2, 14, 14, 64, 144, (1, 3, 3), (0, 1, 1)),      # tiles with a clipped bottom row
+                                   (2, 3, 56, 56, 64, 48, (1, 5, 1), (0, 2, 0))])      # the row-paired stem conv
+def test_cta_pair_slab_kernel_matches_single_cta(cuda_device, lib, shape):
+    """K1s2 (tcgen05.mma.cta_group::2 over a CTA pair, staged TMA store) == K1s on one CTA, bit for bit: plain, with the
+    affine + residual + ReLU epilogue, and with BatchNorm statistics."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w, cin, cout, k, p = shape
+    gen = torch.Generator().manual_seed(n * 100 + h)
+    x = (torch.randn(n, t, h, w, cin, generator=gen) * 0.5).to(torch.bfloat16).to(cuda_device)
+    wt = (torch.randn(cout, cin, *k, generator=gen) / (cin * k[1] * k[2]) ** 0.5).to(cuda_device)
+    res = torch.randn(n, t, h, w, cout, generator=gen).to(torch.bfloat16).to(cuda_device)
+    sc = (0.5 + torch.rand(cout, generator=gen)).to(cuda_device)
+    sh = torch.randn(cout, generator=gen).to(cuda_device)
+    d_plain = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, 0)
+    d_full = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+    d_stat = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, ops.FVT_CONV_STATS)
+    wp = ops.pack_conv_weight(d_plain, wt)
+
+    def run_all():
+        a = ops.conv3d_fwd(d_plain, x, wp).clone()
+        b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
+        st = torch.zeros(2 * cout, device=cuda_device)
+        c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
+        torch.cuda.synchronize()
+        return a, b, c, st.clone()
+
+    out = {}
+    try:
+        for mode in (0, 1, 2):
+            assert lib.fvt_set_option(b"slab_pair", mode) == 0
+            out[mode] = run_all()
+    finally:
+        lib.fvt_set_option(b"slab_pair", 0)
+    for mode in (1, 2):
+        for i in range(3):
+            assert torch.equal(out[0][i], out[mode][i]), (mode, i)
+        ref = out[0][3]
+        assert (out[mode][3] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-3     # fp32 atomics order
+    assert out[0][0].float().abs().max().item() > 0
