@@ -64,6 +64,8 @@ def load():
         "fvt_conv3d_packed_weight_elems": (ctypes.c_size_t, [dp]),
         "fvt_pack_conv_weight": (ctypes.c_int, [dp, fp, i32, i32, vp, vp]),
         "fvt_conv3d_fwd": (ctypes.c_int, [dp, vp, vp, fp, fp, vp, vp, fp, vp, ctypes.c_size_t, vp]),
+        "fvt_unit2p1_supported": (ctypes.c_int, [dp, dp]),
+        "fvt_unit2p1_fwd": (ctypes.c_int, [dp, dp, vp, vp, fp, fp, vp, fp, fp, vp, vp, vp]),
         "fvt_stem_unfold": (ctypes.c_int, [fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         "fvt_stem_unfold_hpair": (ctypes.c_int, [fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         "fvt_conv3d_fwd_f32": (ctypes.c_int, [dp, fp, fp, fp, fp, fp, fp, vp]),

@@ -13,6 +13,7 @@
 #include "conv_wgrad.cuh"
 #include "conv_slab.cuh"
 #include "conv_slab_pair.cuh"
+#include "conv_unit_fused.cuh"
 #include "conv_wgrad_slab.cuh"
 #include "conv_frame_ring.cuh"
 #include "conv_temporal_is.cuh"
@@ -959,6 +960,122 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ K2f: fused (2+1)D unit
+// Geometry of the fused unit for a (spatial, temporal) descriptor pair; returns 0 and fills *up / *smem_bytes when the
+// pair is eligible, a negative status (error text set) otherwise.
+static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt_conv_desc* dt, UnitFusedParams* up, int* smem_bytes) {
+  if (int e = validate_conv(ds)) return e;
+  if (int e = validate_conv(dt)) return e;
+  const bool spatial_ok = ds->kt == 1 && ds->kh == 3 && ds->kw == 3 && ds->st == 1 && ds->sh == 1 && ds->sw == 1 &&
+                          ds->pt == 0 && ds->ph == 1 && ds->pw == 1 && ds->cin == 64;
+  const bool temporal_ok = dt->kt == 3 && dt->kh == 1 && dt->kw == 1 && dt->st == 1 && dt->sh == 1 && dt->sw == 1 &&
+                           dt->pt == 1 && dt->ph == 0 && dt->pw == 0 && dt->cin == ds->cout && dt->cout == 64;
+  if (!spatial_ok || !temporal_ok)
+    return set_error(FVT_ERR_BAD_DESC, "fused unit needs a stride-1 1x3x3 conv (64 -> mid, pad 0,1,1) followed by a stride-1 3x1x1 conv (mid -> 64, pad 1,0,0)");
+  if (ds->n != dt->n || ds->t != dt->t || ds->h != dt->h || ds->w != dt->w)
+    return set_error(FVT_ERR_BAD_DESC, "fused unit: the two convolutions must share N, T, H, W");
+  const int n_mid = ds->cout;
+  if (n_mid > 144 || pick_block_n(ds) != n_mid || pick_block_n(dt) != 64)
+    return set_error(FVT_ERR_BAD_DESC, "fused unit: mid=%d must be <= 144 with single-tile packed filters", n_mid);
+  if (di->sm_count % 2) return set_error(FVT_ERR_BAD_DESC, "fused unit needs an even SM count (CTA pairs)");
+  UnitFusedParams u;
+  memset(&u, 0, sizeof(u));
+  u.clips = ds->n; u.t = ds->t; u.h = ds->h; u.w = ds->w; u.wp = ds->w + 2;
+  if (u.wp > 128) return set_error(FVT_ERR_BAD_DESC, "fused unit: W + 2 = %d exceeds one 128-row tile", u.wp);
+  u.r_out = 128 / u.wp;
+  if (u.r_out > ds->h) u.r_out = ds->h;
+  u.r_in = u.r_out + 2;
+  u.tiles_per_frame = (ds->h + u.r_out - 1) / u.r_out;
+  u.pairs_per_frame = (u.tiles_per_frame + 1) / 2;
+  u.num_units = u.clips * u.pairs_per_frame;
+  const double useful = (double)ds->h * ds->w / ((double)2 * u.pairs_per_frame * 128.0);
+  if (useful < 0.5) return set_error(FVT_ERR_BAD_DESC, "fused unit: %dx%d frames fill only %.0f %% of the tiles", ds->h, ds->w, 100 * useful);
+  const int slot_rows = (128 + 2 * u.wp + 2 + 7) / 8 * 8;
+  if (u.r_in * u.wp > slot_rows) return set_error(FVT_ERR_BAD_DESC, "fused unit: slab does not fit its slot");
+  u.slab_slot_bytes = (slot_rows * 128 + 1023) / 1024 * 1024;
+  u.slab_tx_bytes = u.wp * u.r_in * 128;
+  u.n_mid = n_mid; u.n_out = 64;
+  u.mid_blocks = (n_mid + 63) / 64; u.mid_k16 = n_mid / 16;
+  const int b_bytes = 9 * (n_mid / 2) * 128 + (3 * u.mid_blocks * 32 * 128 + 1023) / 1024 * 1024;
+  const int aux = (512 + (2 * n_mid + 2 * 64) * 4 + 255) / 256 * 256;
+  const int kSmemMax = 227 * 1024;
+  u.stages = (kSmemMax - aux - b_bytes) / u.slab_slot_bytes;
+  if (u.stages > kUnitMaxStages) u.stages = kUnitMaxStages;
+  if (u.stages < 2) return set_error(FVT_ERR_BAD_DESC, "fused unit: filters leave no room for two input stages");
+  *smem_bytes = b_bytes + u.stages * u.slab_slot_bytes + aux;
+  *up = u;
+  return 0;
+}
+
+int fvt_unit2p1_supported(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal) {
+  int st = 0;
+  const DeviceInfo* di = current_device_info(&st);
+  if (di == nullptr) return st;
+  UnitFusedParams u;
+  int smem = 0;
+  return plan_unit2p1(di, d_spatial, d_temporal, &u, &smem) == 0 ? 1 : 0;
+}
+
+int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal, const void* x,
+                    const void* w_spatial_packed, const float* scale_mid, const float* shift_mid,
+                    const void* w_temporal_packed, const float* scale_out, const float* shift_out,
+                    const void* residual, void* y, void* stream) {
+  int st = 0;
+  const DeviceInfo* di = current_device_info(&st);
+  if (di == nullptr) return st;
+  UnitFusedParams u;
+  int smem_bytes = 0;
+  if (int e = plan_unit2p1(di, d_spatial, d_temporal, &u, &smem_bytes)) return e;
+  if (x == nullptr || w_spatial_packed == nullptr || w_temporal_packed == nullptr || y == nullptr)
+    return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
+  if (scale_mid == nullptr || shift_mid == nullptr || scale_out == nullptr || shift_out == nullptr)
+    return set_error(FVT_ERR_BAD_DESC, "fused unit needs the folded BatchNorm scale/shift of both convolutions");
+  const bool has_res = (d_temporal->flags & FVT_CONV_RESIDUAL) != 0;
+  if (has_res && residual == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_RESIDUAL without a residual tensor");
+  if (((uintptr_t)x | (uintptr_t)w_spatial_packed | (uintptr_t)w_temporal_packed) & 15)
+    return set_error(FVT_ERR_MISALIGNED, "x / packed weights must be 16-byte aligned");
+  if (((uintptr_t)y | (uintptr_t)residual) & 31) return set_error(FVT_ERR_MISALIGNED, "y / residual must be 32-byte aligned (256-bit epilogue accesses)");
+  u.flags = (has_res ? kConvResidual : 0) | g_debug_flags;
+  u.scale_mid = scale_mid; u.shift_mid = shift_mid; u.scale_out = scale_out; u.shift_out = shift_out;
+  u.residual = (const __nv_bfloat16*)residual; u.y = (__nv_bfloat16*)y;
+
+  CUtensorMap tmx, tmws, tmwt;
+  const int frames = u.clips * u.t;
+  const cuuint64_t dims[4] = {64, (cuuint64_t)u.w, (cuuint64_t)u.h, (cuuint64_t)frames};
+  const cuuint64_t strides[3] = {128, (cuuint64_t)128 * u.w, (cuuint64_t)128 * u.w * u.h};
+  const cuuint32_t box[4] = {64, (cuuint32_t)u.wp, (cuuint32_t)u.r_in, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(fused unit x) failed (CUresult %d)", (int)r);
+  if (int e = encode_w_map(di, w_spatial_packed, 9 * 64, u.n_mid, u.n_mid / 2, &tmws)) return e;
+  if (int e = encode_w_map(di, w_temporal_packed, 3 * u.n_mid, 64, 32, &tmwt)) return e;
+
+  static bool attr_set_u[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set_u[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(unit2p1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(unit2p1_fused_kernel): %s", cudaGetErrorString(e));
+    attr_set_u[dev] = true;
+  }
+  int clusters = u.num_units < di->sm_count / 2 ? u.num_units : di->sm_count / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kUnitThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, unit2p1_fused_kernel, tmx, tmws, tmwt, u);
+  if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "unit2p1_fused_kernel launch: %s", cudaGetErrorString(le));
+  return check_launch("unit2p1_fused_kernel");
+}
 
 int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
                      int32_t cin_real, void* stream) {

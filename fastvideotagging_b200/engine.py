@@ -244,7 +244,15 @@ class InferencePlan:
             raise ValueError("AvgPool3D%s over a %s map leaves %s: only a global pool (1x1x1 output) is supported; "
                              "pass final_temporal_kernel = T/8 and final_spatial_kernel = H/16 as the reference callers do"
                              % (pool, shp[1:4], (tp, hp, wp)))
-        self.launches = 1 + len(self.layers) + 1
+        # ---- K2f: a stride-1 64 -> mid -> 64 unit (conv2_x) runs as ONE launch with `mid` kept in tensor memory
+        self.fused = {}
+        if os.environ.get("FVT_FUSED_UNIT", "1") != "0":
+            for i in range(len(self.layers) - 1):
+                a, b = self.layers[i], self.layers[i + 1]
+                if (a.spec.role == "spatial" and b.spec.role in ("temporal", "temporal_out") and b.src == a.dst
+                        and a.res is None and (i - 1) not in self.fused and ops.unit2p1_supported(a.desc, b.desc)):
+                    self.fused[i] = b
+        self.launches = 1 + len(self.layers) - len(self.fused) + 1
 
     def _view(self, ref):
         key, shape = ref
@@ -257,7 +265,17 @@ class InferencePlan:
         """x: (N, 3, T, H, W) fp32 CUDA -> logits (N, num_class) fp32 [, pooled features (N, 512)]."""
         assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w), (tuple(x.shape), (self.n, 3, self.t, self.h, self.w))
         self.stem.unfold(x.contiguous(), self._view(self.unfold))
-        for L in self.layers:
+        skip = False
+        for i, L in enumerate(self.layers):
+            if skip:
+                skip = False
+                continue
+            B = self.fused.get(i)
+            if B is not None:
+                ops.unit2p1_fwd(L.desc, B.desc, self._view(L.src), L.w_packed, L.scale, L.shift, B.w_packed, B.scale, B.shift,
+                                self._view(B.res) if B.res is not None else None, out=self._view(B.dst))
+                skip = True
+                continue
             ops.conv3d_fwd(L.desc, self._view(L.src), L.w_packed, L.scale, L.shift,
                            self._view(L.res) if L.res is not None else None, out=self._view(L.dst))
         if want_map:                   # conv5_x output (N, T/8, H/16, W/16, 512) bf16 for heads other than pool + Dense

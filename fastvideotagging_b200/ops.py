@@ -90,6 +90,29 @@ def conv3d_fwd(desc, x, w_packed, scale=None, shift=None, residual=None, out=Non
     return out
 
 
+def unit2p1_supported(d_spatial, d_temporal):
+    """True when the (1x3x3, 3x1x1) descriptor pair can run as ONE fused launch (fvt_unit2p1_fwd) on this device."""
+    lib = _lib.load()
+    return check(lib.fvt_unit2p1_supported(ctypes.byref(d_spatial), ctypes.byref(d_temporal))) == 1
+
+
+def unit2p1_fwd(d_spatial, d_temporal, x, w_spatial, scale_mid, shift_mid, w_temporal, scale_out, shift_out,
+                residual=None, out=None):
+    """The factorised unit + the BatchNorm/ReLU(/residual) around it in one launch (eval mode):
+    x (N, T, H, W, 64) bf16 -> relu(bn(conv3x1x1(relu(bn(conv1x3x3(x))))) [+ residual]) (N, T, H, W, 64) bf16."""
+    lib = _lib.load()
+    require_cuda(x, "x")
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    assert tuple(x.shape) == (d_spatial.n, d_spatial.t, d_spatial.h, d_spatial.w, d_spatial.cin), (tuple(x.shape), d_spatial.key())
+    if out is None:
+        out = torch.empty((d_temporal.n, d_temporal.t, d_temporal.h, d_temporal.w, d_temporal.cout), dtype=torch.bfloat16,
+                          device=x.device)
+    check(lib.fvt_unit2p1_fwd(ctypes.byref(d_spatial), ctypes.byref(d_temporal), _ptr(x), _ptr(w_spatial), _ptr(scale_mid),
+                              _ptr(shift_mid), _ptr(w_temporal), _ptr(scale_out), _ptr(shift_out), _ptr(residual),
+                              _ptr(out), _stream()))
+    return out
+
+
 def stem_unfold(x_ncdhw, kw_taps=7, sw=2, pw=3, cu=32, out=None):
     """(N, 3, T, H, W) fp32 -> (N, T, H, Wo, cu) bf16 with u[..., kw*3+ci] = x[n, ci, t, h, ow*sw-pw+kw]."""
     lib = _lib.load()

@@ -87,6 +87,21 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
                    const float* shift, const void* residual, void* y, float* stats, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ---- fused (2+1)D unit (K2f, inference) ------------------------------------------------------------------------
+ * y = relu( bn_out( conv3x1x1( relu( bn_mid( conv1x3x3(x) ) ) ) ) [+ residual] ) in ONE launch: the factorised unit
+ * get_spatial_temporal_conv (model/R2Plus1.py:19-40, net.py:31-52) plus the BatchNorm/ReLU/add that R3DBlock wraps
+ * around it (model/R2Plus1.py:59-62,76-81), eval mode.  d_spatial: 1x3x3, stride 1, pad (0,1,1), cin = 64, cout = mid
+ * (stored, <= 144); d_temporal: 3x1x1, stride 1, pad (1,0,0), cin = mid, cout = 64, same N/T/H/W; FVT_CONV_RESIDUAL in
+ * d_temporal->flags adds `residual` before the final ReLU.  Weights are the buffers fvt_pack_conv_weight makes for the
+ * two descriptors; scale/shift are the folded BatchNorm constants (mid: d_spatial->cout floats, out: 64 floats).
+ * The mid tensor stays in tensor memory.  fvt_unit2p1_supported returns 1 when the pair of descriptors is eligible on
+ * the current device, 0 when the caller must use two fvt_conv3d_fwd calls. */
+int fvt_unit2p1_supported(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal);
+int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal, const void* x,
+                    const void* w_spatial_packed, const float* scale_mid, const float* shift_mid,
+                    const void* w_temporal_packed, const float* scale_out, const float* shift_out,
+                    const void* residual, void* y, void* stream);
+
 /* ---- stem input transform --------------------------------------------------------------------------------- */
 /* Clips in the reference layout NCDHW fp32 (data/data.py:46-47) with 3 channels -> W-unfolded NDHWC bf16
  * u[n,t,h,ow, kw*3+ci] = x[n,ci,t,h, ow*sw - pw + kw] (zero outside), channels >= 3*kw_taps are zero.

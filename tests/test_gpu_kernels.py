@@ -342,3 +342,75 @@ def test_cta_pair_slab_kernel_matches_single_cta(cuda_device, lib, shape):
         ref = out[0][3]
         assert (out[mode][3] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-3     # fp32 atomics order
     assert out[0][0].float().abs().max().item() > 0
+
+
+def _unit_case(device, n, t, h, w, mid, seed, residual):
+    import torch
+    from fastvideotagging_b200 import ops
+    gen = torch.Generator().manual_seed(seed)
+    x = (torch.randn(n, t, h, w, 64, generator=gen) * 0.5).to(torch.bfloat16).to(device)
+    w_s = (torch.randn(mid, 64, 1, 3, 3, generator=gen) / 24.0).to(device)
+    w_t = (torch.randn(64, mid, 3, 1, 1, generator=gen) / (3 * mid) ** 0.5).to(device)
+    sc_m = (0.5 + torch.rand(mid, generator=gen)).to(device)
+    sh_m = (0.3 * torch.randn(mid, generator=gen)).to(device)
+    sc_o = (0.5 + torch.rand(64, generator=gen)).to(device)
+    sh_o = (0.3 * torch.randn(64, generator=gen)).to(device)
+    res = torch.randn(n, t, h, w, 64, generator=gen).to(torch.bfloat16).to(device) if residual else None
+    d_s = ops.conv_desc(n, t, h, w, 64, mid, (1, 3, 3), (1, 1, 1), (0, 1, 1), ops.FVT_CONV_RELU)
+    d_t = ops.conv_desc(n, t, h, w, mid, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0),
+                        ops.FVT_CONV_RELU | (ops.FVT_CONV_RESIDUAL if residual else 0))
+    wp_s, wp_t = ops.pack_conv_weight(d_s, w_s), ops.pack_conv_weight(d_t, w_t)
+    return x, w_s, w_t, sc_m, sh_m, sc_o, sh_o, res, d_s, d_t, wp_s, wp_t
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 56, 56, 144, True),      # conv2_x, second unit of a block (residual)
+                                   (1, 6, 56, 56, 144, False),     # conv2_x, first unit; more frames than P / D ring slots
+                                   (1, 1, 56, 56, 144, False),     # one frame: only the centre temporal tap
+                                   (3, 2, 28, 28, 144, True),      # 7 row tiles per frame: the last pair has a dummy tile
+                                   (2, 3, 14, 14, 144, True),      # second tile clipped at the bottom edge
+                                   (1, 5, 56, 56, 96, True),       # another mid width (two 64-channel blocks, 6 K steps)
+                                   (20, 3, 56, 56, 144, True)])    # more units than CTA pairs: several clips per cluster
+def test_fused_unit_matches_two_launches(cuda_device, lib, shape):
+    """K2f (one launch, mid in tensor memory, cta_group::2, A operand from TMEM) == spatial conv launch + temporal conv
+    launch on identical inputs: the bf16 rounding of mid is the same, so results differ by fp32 summation order only
+    (<= 1 bf16 ulp per element); and both agree with a torch fp32 evaluation at the bf16 tolerance (1e-2 of max)."""
+    import torch
+    import torch.nn.functional as F
+    from fastvideotagging_b200 import ops
+    n, t, h, w, mid, residual = shape
+    x, w_s, w_t, sc_m, sh_m, sc_o, sh_o, res, d_s, d_t, wp_s, wp_t = _unit_case(cuda_device, n, t, h, w, mid, n * 10 + t, residual)
+    assert ops.unit2p1_supported(d_s, d_t)
+    y_mid = ops.conv3d_fwd(d_s, x, wp_s, sc_m, sh_m)
+    y_two = ops.conv3d_fwd(d_t, y_mid, wp_t, sc_o, sh_o, res)
+    y_fused = torch.full_like(y_two, float("nan"))
+    ops.unit2p1_fwd(d_s, d_t, x, wp_s, sc_m, sh_m, wp_t, sc_o, sh_o, res, out=y_fused)
+    torch.cuda.synchronize()
+    a, b = y_fused.float(), y_two.float()
+    assert torch.isfinite(a).all()
+    tol = 2 ** -7 * b.abs() + 2 ** -7 * 1e-2 * b.abs().max()
+    assert ((a - b).abs() <= tol).all(), ((a - b).abs().max().item(), b.abs().max().item())
+    assert (a != b).float().mean().item() < 0.02
+    # torch fp32 evaluation from the same bf16 inputs / bf16-rounded weights, mid rounded to bf16 as both paths store it
+    xf = x.float().permute(0, 4, 1, 2, 3)
+    m = F.conv3d(xf, w_s.to(torch.bfloat16).float(), padding=(0, 1, 1))
+    m = torch.relu(m * sc_m.view(1, -1, 1, 1, 1) + sh_m.view(1, -1, 1, 1, 1)).to(torch.bfloat16).float()
+    o = F.conv3d(m, w_t.to(torch.bfloat16).float(), padding=(1, 0, 0)) * sc_o.view(1, -1, 1, 1, 1) + sh_o.view(1, -1, 1, 1, 1)
+    if res is not None:
+        o = o + res.float().permute(0, 4, 1, 2, 3)
+    o = torch.relu(o).permute(0, 2, 3, 4, 1)
+    assert (a - o).abs().max().item() <= 1e-2 * o.abs().max().item()
+    assert a.abs().max().item() > 0
+
+
+def test_fused_unit_rejects_other_geometries(cuda_device, lib):
+    """Strided / wider units are not eligible: the caller keeps the two-launch path (no silent approximation)."""
+    from fastvideotagging_b200 import ops, _lib
+    d_s = ops.conv_desc(1, 4, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), ops.FVT_CONV_RELU)
+    d_t = ops.conv_desc(1, 4, 28, 28, 288, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU)
+    assert not ops.unit2p1_supported(d_s, d_t)
+    d_s2 = ops.conv_desc(1, 4, 56, 56, 64, 144, (1, 3, 3), (1, 2, 2), (0, 1, 1), ops.FVT_CONV_RELU)
+    d_t2 = ops.conv_desc(1, 4, 28, 28, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU)
+    assert not ops.unit2p1_supported(d_s2, d_t2)
+    import ctypes
+    with pytest.raises(_lib.FvtError):          # the C entry point itself refuses (bad descriptor pair), nothing is launched
+        _lib.check(lib.fvt_unit2p1_fwd(ctypes.byref(d_s), ctypes.byref(d_t), *([None] * 10)))
