@@ -989,6 +989,7 @@ static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt
   u.tiles_per_frame = (ds->h + u.r_out - 1) / u.r_out;
   u.pairs_per_frame = (u.tiles_per_frame + 1) / 2;
   u.num_units = u.clips * u.pairs_per_frame;
+  u.total_steps = (long long)u.num_units * u.t;
   const double useful = (double)ds->h * ds->w / ((double)2 * u.pairs_per_frame * 128.0);
   if (useful < 0.5) return set_error(FVT_ERR_BAD_DESC, "fused unit: %dx%d frames fill only %.0f %% of the tiles", ds->h, ds->w, 100 * useful);
   const int slot_rows = (128 + 2 * u.wp + 2 + 7) / 8 * 8;
@@ -1061,7 +1062,9 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
     if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(unit2p1_fused_kernel): %s", cudaGetErrorString(e));
     attr_set_u[dev] = true;
   }
-  int clusters = u.num_units < di->sm_count / 2 ? u.num_units : di->sm_count / 2;
+  // every cluster takes an equal share of the output frames; tiny problems keep whole units (a split costs a halo frame per side)
+  int clusters = di->sm_count / 2;
+  if (u.total_steps < 8ll * clusters) clusters = u.num_units < clusters ? u.num_units : clusters;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);

@@ -14,15 +14,17 @@
 //             of its operands are converted BEFORE frame t's spatial MMAs are issued: the tensor pipe has 27 queued
 //             temporal MMAs to run while the convert warps turn S(t) into P[t % 4], and S is free again by the time
 //             they retire.  Frames outside the clip are zero padding = skipped taps.
-//   output    4 warps per CTA: D -> scale/shift (+ residual) -> ReLU -> 128-byte rows of Y (shared epilogue); the drain
-//             overlaps the next frame's spatial MMAs.
+//   output    8 warps per CTA: D -> registers, accumulator handed back at once, then scale/shift (+ residual) -> ReLU
+//             -> 64-byte row segments of Y; the drain overlaps the next frame's spatial MMAs.
 // Both filters are stationary, half of their N rows per CTA (83 KB + 36 KB), next to three input-slab stages.
 // TMEM columns: S [0, mid) | P0..P3 [mid, 3*mid) | D [448, 512).
 //
 // Pair protocol as in conv_slab_pair.cuh (own slab per CTA, relay warp, multicast commits); additionally the convert
 // and output warps of BOTH CTAs arrive on the leader's p_full / d_empty barriers.
-// Warp roles per CTA (512 threads): warp0 slab producer, warp1 MMA issuer (leader) / relay (peer), warp2 TMEM allocator,
-// warp3 filter producer, warps 4-11 convert, warps 12-15 output.
+// Work split: the clusters share the num_units * T output frames evenly; a cluster that starts or ends inside a unit
+// recomputes one halo frame of the spatial conv on that side (< 1 % extra work, no tail wave).
+// Warp roles per CTA (640 threads): warp0 slab producer, warp1 MMA issuer (leader) / relay (peer), warp2 TMEM allocator,
+// warp3 filter producer, warps 4-11 convert, warps 12-19 output (32 rows x 32 columns each).
 #pragma once
 #include "ptx.cuh"
 #include "epilogue.cuh"
@@ -31,7 +33,7 @@
 
 namespace fvt {
 
-constexpr int kUnitThreads = 512;
+constexpr int kUnitThreads = 640;
 constexpr int kUnitMaxStages = 4;
 constexpr int kUnitDCol0 = 448;            // first TMEM column of the output accumulator (64 columns)
 constexpr int kUnitPSlots = 4;             // converted mid frames resident in TMEM
@@ -43,6 +45,7 @@ struct UnitFusedParams {
   int tiles_per_frame;       // row tiles per frame
   int pairs_per_frame;       // ceil(tiles_per_frame / 2): tile 2*pair + rank belongs to CTA `rank`
   int num_units;             // clips * pairs_per_frame
+  long long total_steps;     // num_units * t output frames, shared evenly by the clusters
   int slab_slot_bytes, slab_tx_bytes, stages;
   int n_mid, n_out;          // stored channels of mid (multiple of 16, <= 144) and of the output (64)
   int mid_blocks, mid_k16;   // 64-channel blocks / 16-channel MMA steps of mid
@@ -70,6 +73,29 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A cluster's share [g, g1) of the global output-frame sequence (unit-major), cut into per-unit segments.
+struct Segments {
+  long long g, g1;
+  int t;
+  __device__ __forceinline__ Segments(long long total, int frames_per_unit) : t(frames_per_unit) {
+    const long long c = pair::cluster_id_x(), n = pair::nclusters_x();
+    g = total * c / n;
+    g1 = total * (c + 1) / n;
+  }
+  // next segment: unit u, output frames [tb, te), spatial (mid) frames [fs0, fs1) = the outputs' frames plus the halo inside the clip
+  __device__ __forceinline__ bool next(int& u, int& tb, int& te, int& fs0, int& fs1) {
+    if (g >= g1) return false;
+    u = static_cast<int>(g / t);
+    const long long base = static_cast<long long>(u) * t;
+    tb = static_cast<int>(g - base);
+    const long long end = g1 < base + t ? g1 : base + t;
+    te = static_cast<int>(end - base);
+    g = end;
+    fs0 = tb > 0 ? tb - 1 : 0;
+    fs1 = te < t ? te + 1 : t;
+    return true;
+  }
+};
 }  // namespace unit
 
 __global__ void __launch_bounds__(kUnitThreads, 1)
@@ -98,7 +124,7 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   uint64_t* s_full = peer_b_full + 1;                                  // [1] multicast commit: spatial accumulator complete
   uint64_t* p_full = s_full + 1;                                       // [1] leader: 16 convert warps (S drained, P written)
   uint64_t* d_full = p_full + 1;                                       // [1] multicast commit: output accumulator complete
-  uint64_t* d_empty = d_full + 1;                                      // [1] leader: 8 output warps
+  uint64_t* d_empty = d_full + 1;                                      // [1] leader: 16 output warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
   float* aff_mid = reinterpret_cast<float*>(tmem_slot + 4);            // scale[n_mid], shift[n_mid]
   float* aff_out = aff_mid + 2 * p.n_mid;                              // scale[n_out], shift[n_out]
@@ -119,7 +145,7 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     ptx::mbar_init(ptx::smem_u32(s_full), 1);
     ptx::mbar_init(ptx::smem_u32(p_full), 16);
     ptx::mbar_init(ptx::smem_u32(d_full), 1);
-    ptx::mbar_init(ptx::smem_u32(d_empty), 8);
+    ptx::mbar_init(ptx::smem_u32(d_empty), 16);
     ptx::fence_mbar_init();
   }
   if (warp == 2) pair::tmem_alloc2(ptx::smem_u32(tmem_slot), 512);
@@ -139,19 +165,18 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const uint32_t p_cols = static_cast<uint32_t>(p.n_mid) >> 1;        // TMEM columns of one bf16 mid frame
   const uint32_t p_col0 = static_cast<uint32_t>(p.n_mid);
 
-  const int unit0 = static_cast<int>(pair::cluster_id_x());
-  const int unit_step = static_cast<int>(pair::nclusters_x());
-  const bool has_work = unit0 < p.num_units;
+  const bool has_work = unit::Segments(p.total_steps, p.t).g < unit::Segments(p.total_steps, p.t).g1;
+  int u, tb, te, fs0, fs1;
 
   if (warp == 0) {
     // ===================================================== input slab producer: own row tile, every frame of the clip
     int stage = 0;
     uint32_t phase = 0;
-    for (int u = unit0; u < p.num_units; u += unit_step) {
+    for (unit::Segments sg(p.total_steps, p.t); sg.next(u, tb, te, fs0, fs1);) {
       const int clip = u / p.pairs_per_frame;
       const int tile = 2 * (u - clip * p.pairs_per_frame) + static_cast<int>(rank);
-      const int h0 = tile * p.r_out;            // a dummy tile (odd tiles_per_frame) starts beyond H: the slab is all zero fill
-      for (int t = 0; t < p.t; ++t) {
+      const int h0 = tile * p.r_out;            // a dummy tile (odd tiles_per_frame) starts beyond H: its rows are never stored
+      for (int t = fs0; t < fs1; ++t) {
         ptx::mbar_wait(ptx::smem_u32(&slab_empty[stage]), phase ^ 1);
         const uint32_t fb = ptx::smem_u32(&slab_full[stage]);
         if (ptx::elect_one()) {
@@ -187,8 +212,8 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int u = unit0; u < p.num_units; u += unit_step) {
-      for (int t = 0; t < p.t; ++t) {
+    for (unit::Segments sg(p.total_steps, p.t); sg.next(u, tb, te, fs0, fs1);) {
+      for (int t = fs0; t < fs1; ++t) {
         ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
         if (ptx::elect_one()) pair::remote_arrive(pair::map_to_rank(ptx::smem_u32(&peer_full[stage]), 0));
         __syncwarp();
@@ -213,9 +238,9 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       pair::wait_cluster(ptx::smem_u32(peer_b_full), 0);
     }
     const uint32_t d_tmem = tmem_base + kUnitDCol0;
-    for (int u = unit0; u < p.num_units; u += unit_step) {
-      for (int tp = 0; tp < p.t + 2; ++tp) {
-        if (tp < p.t) {
+    for (unit::Segments sg(p.total_steps, p.t); sg.next(u, tb, te, fs0, fs1);) {
+      for (int tp = fs0; tp < fs1 + 2; ++tp) {
+        if (tp < fs1) {
           // ---- spatial conv of frame tp into S (S is free: the p_full wait of the previous frame covered its drain)
           ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
           pair::wait_cluster(ptx::smem_u32(&peer_full[stage]), phase);
@@ -243,7 +268,7 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         const int o = tp - 2;                                          // output frame whose three mid frames are all converted
-        if (o >= 0) {
+        if (o >= tb && o < te) {
           pair::wait_cluster(ptx::smem_u32(d_empty), (go & 1u) ^ 1u);   // the output warps of both CTAs drained frame o-1
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
@@ -269,7 +294,7 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           __syncwarp();
           ++go;
         }
-        if (tp < p.t) {
+        if (tp < fs1) {
           pair::wait_cluster(ptx::smem_u32(p_full), p_phase);           // frame tp: S drained, P[tp % 4] written (both CTAs)
           p_phase ^= 1;
           ptx::tc_fence_after();
@@ -284,8 +309,8 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const uint32_t p_full_leader = pair::map_to_rank(ptx::smem_u32(p_full), 0);
     const int n_chunks = p.n_mid >> 4;
     uint32_t s_phase = 0;
-    for (int u = unit0; u < p.num_units; u += unit_step) {
-      for (int t = 0; t < p.t; ++t) {
+    for (unit::Segments sg(p.total_steps, p.t); sg.next(u, tb, te, fs0, fs1);) {
+      for (int t = fs0; t < fs1; ++t) {
         ptx::mbar_wait(ptx::smem_u32(s_full), s_phase);
         s_phase ^= 1;
         ptx::tc_fence_after();
@@ -322,33 +347,67 @@ unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
     }
   } else if (warp >= 12) {
-    // ===================================================== output: D -> BN (+ residual) -> ReLU -> Y, own 128 rows
+    // ===================================================== output: D -> BN (+ residual) -> ReLU -> Y; 32 rows x 32 columns per warp
     const int q = warp & 3;
-    EpilogueArgs ea;
-    ea.ngrp = 1;
-    ea.block_n = p.n_out; ea.cout_store = p.n_out; ea.flags = kConvRelu | (p.flags & (kConvResidual | kDbgNoStore | kDbgNoEpilogue));
-    ea.scale_smem = aff_out; ea.shift_smem = aff_out + p.n_out;
-    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = nullptr; ea.stat_stride = 0;
+    const int c0 = ((warp - 12) >> 2) * 32;      // this warp's first output channel
+    const bool has_res = (p.flags & kConvResidual) != 0;
+    const bool no_data = (p.flags & kDbgNoEpilogue) != 0, no_store = (p.flags & kDbgNoStore) != 0;
     const int r = q * 32 + lane;                 // GEMM row = padded position inside the tile
     const int hl = r / p.wp, wl = r - hl * p.wp;
     const uint32_t d_empty_leader = pair::map_to_rank(ptx::smem_u32(d_empty), 0);
+    const uint32_t taddr = tmem_base + kUnitDCol0 + c0 + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t go = 0;
-    for (int u = unit0; u < p.num_units; u += unit_step) {
+    for (unit::Segments sg(p.total_steps, p.t); sg.next(u, tb, te, fs0, fs1);) {
       const int clip = u / p.pairs_per_frame;
       const int tile = 2 * (u - clip * p.pairs_per_frame) + static_cast<int>(rank);
       const int h0 = tile * p.r_out;
       const bool ok = tile < p.tiles_per_frame && hl < p.r_out && wl < p.w && (h0 + hl) < p.h;
-      for (int t = 0; t < p.t; ++t) {
-        const long long out_row = ok ? (static_cast<long long>(clip * p.t + t) * p.h + h0 + hl) * p.w + wl : -1ll;
-        epilogue_prefetch_residual(ea, 0, out_row, 0);
+      for (int t = tb; t < te; ++t, ++go) {
+        const size_t off = ok ? (((static_cast<size_t>(clip) * p.t + t) * p.h + h0 + hl) * p.w + wl) * p.n_out + c0 : 0;
+        uint32_t rr[2][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rr[0][i] = rr[1][i] = 0u;
+        if (has_res && ok && !no_data) {           // the residual does not depend on the accumulator: in flight before the wait
+          ptx::ld_global_nc_256(p.residual + off, rr[0]);
+          ptx::ld_global_nc_256(p.residual + off + 16, rr[1]);
+        }
         ptx::mbar_wait(ptx::smem_u32(d_full), go & 1u);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + kUnitDCol0 + (static_cast<uint32_t>(q * 32) << 16);
-        epilogue_chunks_impl<false>(ea, taddr, 0, out_row, 0, lane);
+        uint32_t v[2][16];
+        if (!no_data) {
+          ptx::tmem_ld_32x32b_x16(taddr, v[0]);
+          ptx::tmem_ld_32x32b_x16(taddr + 16, v[1]);
+          ptx::tmem_ld_wait();
+        }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) pair::remote_arrive(d_empty_leader);
-        ++go;
+        if (lane == 0) pair::remote_arrive(d_empty_leader);       // the accumulator is in registers: hand it back before the math
+        if (no_data || !ok) continue;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4* sc4 = reinterpret_cast<const float4*>(aff_out + c0 + 16 * c);
+          const float4* sh4 = reinterpret_cast<const float4*>(aff_out + p.n_out + c0 + 16 * c);
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 a = sc4[i], b = sh4[i];
+            f[4 * i + 0] = fmaf(__uint_as_float(v[c][4 * i + 0]), a.x, b.x);
+            f[4 * i + 1] = fmaf(__uint_as_float(v[c][4 * i + 1]), a.y, b.y);
+            f[4 * i + 2] = fmaf(__uint_as_float(v[c][4 * i + 2]), a.z, b.z);
+            f[4 * i + 3] = fmaf(__uint_as_float(v[c][4 * i + 3]), a.w, b.w);
+          }
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += bf16_lo(rr[c][i]);
+              f[2 * i + 1] += bf16_hi(rr[c][i]);
+            }
+          }
+          uint32_t o8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = pack_bf16x2(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
+          if (!no_store) ptx::st_global_256(p.y + off + 16 * c, o8);
+        }
       }
     }
   }
