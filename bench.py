@@ -21,6 +21,8 @@ sys.path.insert(0, ROOT)
 GFLOP_PER_CLIP_FWD = 304.711020544      # 2*M*N*K over unpadded conv dims, R34 32x112^2 (oracle.conv_flops)
 GFLOP_PER_CLIP_TRAIN = 912.8            # fwd + dgrad + wgrad, minus the stem dgrad
 TRAIN_BATCH_PER_GPU = 4                 # BASELINE configs[2]
+# dram__bytes_read.sum + dram__bytes_write.sum of one unit2p1_fused_kernel launch at batch 48 (ncu --set full); None until captured
+FUSED_UNIT_DRAM_BYTES_B48 = 1.495e9   # profiles/r01z_ncu_unit2p1_fused_os.txt: 909 MB read + 586 MB written (algorithmic 617 + 617 MB: halo rows re-read)
 MODEL_DEPTH, NUM_CLASS, T, HW = 34, 101, 32, 112
 BATCH_PER_GPU = 48
 C4_BATCH_PER_GPU, C4_T, C4_NUM_CLASS = 16, 16, 63     # BASELINE configs[3] (Meitu shape, train_simple_r3d.py:336,341)
@@ -237,22 +239,41 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             from fastvideotagging_b200 import ops
             reps = 3
-            for L in plan.layers:
+
+            def conv_flops(L):
+                m = L.out_shape[0] * L.out_shape[1] * L.out_shape[2] * L.out_shape[3]
+                kk = L.spec.cin * L.spec.kernel[0] * L.spec.kernel[1] * L.spec.kernel[2]
+                return m, kk, 2.0 * m * L.spec.cout * kk
+
+            i = 0
+            while i < len(plan.layers):                       # one entry per LAUNCH of the inference plan
+                L = plan.layers[i]
+                B = plan.fused.get(i)
+                src = plan._view(L.src)
+                if B is not None:                             # K2f: the whole (2+1)D unit in one launch
+                    dst = plan._view(B.dst)
+                    res = plan._view(B.res) if B.res is not None else None
+                    fn = lambda: ops.unit2p1_fwd(L.desc, B.desc, src, L.w_packed, L.scale, L.shift, B.w_packed, B.scale,
+                                                 B.shift, res, out=dst)
+                    m, kk, fl = conv_flops(L)
+                    fl += conv_flops(B)[2]
+                    name, ncol, i = L.spec.name + "+" + B.spec.name, L.spec.cout, i + 2
+                else:
+                    dst = plan._view(L.dst)
+                    res = plan._view(L.res) if L.res is not None else None
+                    fn = lambda: ops.conv3d_fwd(L.desc, src, L.w_packed, L.scale, L.shift, res, out=dst)
+                    m, kk, fl = conv_flops(L)
+                    name, ncol, i = L.spec.name, L.spec.cout, i + 1
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                src, dst = plan._view(L.src), plan._view(L.dst)
-                res = plan._view(L.res) if L.res is not None else None
-                ops.conv3d_fwd(L.desc, src, L.w_packed, L.scale, L.shift, res, out=dst)
+                fn()
                 a.record()
                 for _ in range(reps):
-                    ops.conv3d_fwd(L.desc, src, L.w_packed, L.scale, L.shift, res, out=dst)
+                    fn()
                 b.record()
                 torch.cuda.synchronize()
                 t = a.elapsed_time(b) / reps
                 k1_ms += t
-                m = L.out_shape[0] * L.out_shape[1] * L.out_shape[2] * L.out_shape[3]
-                kk = L.spec.cin * L.spec.kernel[0] * L.spec.kernel[1] * L.spec.kernel[2]
-                fl = 2.0 * m * L.spec.cout * kk
-                rows.append((L.spec.name, m, L.spec.cout, kk, t, fl / t / 1e9))
+                rows.append((name, m, ncol, kk, t, fl / t / 1e9, fl))
 
     # ---------------- training step (BASELINE configs[2]): fwd + bwd + BCE + NCCL all-reduce + fused SGD
     train = None
@@ -349,25 +370,31 @@ def run_ours(args, rank, world, local_rank):
         value = clips / (ms / 1e3)
         e2e = clips / (ms_e2e / 1e3)
         conv_tflops = batch * GFLOP_PER_CLIP_FWD / k1_ms if k1_ms > 0 else None     # GFLOP / ms = TFLOP/s
-        # dominant kernel: conv_slab_fwd_kernel on the six conv2_x 1x3x3 (64 -> 144) layers — one launch each, the largest
-        # single share of the step.  achieved = algorithmic 2*M*N*K of one launch / its mean CUDA-event duration.
-        dom = [r for r in rows if r[0].startswith(("comp_0_", "comp_1_", "comp_2_")) and r[0].endswith("_middle")]
+        # dominant kernel: unit2p1_fused_kernel — the six conv2_x (2+1)D units (64 -> 144 -> 64), one launch each, the
+        # largest single share of the step.  achieved = algorithmic 2*M*N*K of both convolutions of one launch / its mean
+        # CUDA-event duration.  (FVT_FUSED_UNIT=0: the unfused conv_slab_fwd_kernel launches of the same layers.)
+        dom = [r for r in rows if "+" in r[0]]
+        dom_kernel = "unit2p1_fused_kernel, conv2_x unit 1x3x3 64->144 + 3x1x1 144->64"
+        # DRAM bytes per launch from `ncu --set full` at batch 48 (profiles/): scaled to this batch
+        traffic = FUSED_UNIT_DRAM_BYTES_B48 * batch / 48.0 if FUSED_UNIT_DRAM_BYTES_B48 else None
+        if not dom:
+            dom = [r for r in rows if r[0].startswith(("comp_0_", "comp_1_", "comp_2_")) and r[0].endswith("_middle")]
+            dom_kernel = "conv_slab_fwd_kernel, conv2_x 1x3x3 64->144"
+            traffic = 1.952e9 * batch / 48.0          # profiles/r01j_ncu_slab_conv2x_inference.txt
         dom_ms = sum(r[4] for r in dom) / max(len(dom), 1)
-        dom_flop = 2.0 * dom[0][1] * dom[0][2] * dom[0][3] if dom else 0.0
+        dom_flop = sum(r[6] for r in dom) / max(len(dom), 1)
         dom_tflops = dom_flop / dom_ms / 1e9 if dom else None
-        # DRAM bytes of that launch from `ncu --set full` (profiles/r01j_ncu_slab_conv2x_inference.txt, batch 48):
-        # 617 MB read + 1335 MB written = the algorithmic bytes (input once + output once), i.e. no wasted re-reads
-        traffic = 1.952e9 * batch / 48.0
         roofline = {"bound": "tensor", "achieved": dom_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": (dom_tflops / peaks["tflops"]) if dom_tflops else None, "traffic": traffic,
-                    "kernel": "conv_slab_fwd_kernel, conv2_x 1x3x3 64->144 (6 launches/step, %.0f%% of the step); "
+                    "kernel": "%s (%d launches/step, %.0f%% of the step); "
                               "algorithmic 2MNK = %.1f GFLOP/launch, mean CUDA-event time %.3f ms" % (
-                                  100.0 * dom_ms * len(dom) / (ms / args.steps), dom_flop / 1e9, dom_ms),
+                                  dom_kernel, len(dom), 100.0 * dom_ms * len(dom) / (ms / args.steps), dom_flop / 1e9, dom_ms),
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (cuBLAS 8192^3 back to back, power-capped clocks)",
                     "all_conv_kernels": {"launches_per_step": len(rows), "achieved": conv_tflops,
                                          "frac": (conv_tflops / peaks["tflops"]) if conv_tflops else None,
-                                         "note": "69 conv launches (conv_igemm_fwd / conv_slab_fwd / conv_frame_ring), "
-                                                 "304.7 GFLOP/clip algorithmic / summed CUDA-event time"},
+                                         "note": "%d conv launches (unit2p1_fused / conv_igemm_fwd / conv_slab_fwd / "
+                                                 "conv_frame_ring / conv_temporal_is), 304.7 GFLOP/clip algorithmic / summed "
+                                                 "CUDA-event time" % len(rows)},
                     "step_frac_of_peak": value * GFLOP_PER_CLIP_FWD / 1e3 / world / peaks["tflops"]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -412,7 +439,7 @@ def run_ours(args, rank, world, local_rank):
             with open(args.layer_table, "w") as fh:
                 fh.write("layer,M,N,K,ms,GFLOP/s\n")
                 for r in rows:
-                    fh.write("%s,%d,%d,%d,%.4f,%.0f\n" % r)
+                    fh.write("%s,%d,%d,%d,%.4f,%.0f\n" % r[:6])
     if world > 1:
         # Tear down in dependency order: CUDA graphs that captured NCCL kernels first, then the communicator.  A
         # communicator destroyed while such graphs are alive can block forever, so the teardown also has a watchdog.

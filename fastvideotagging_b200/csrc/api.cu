@@ -14,6 +14,7 @@
 #include "conv_slab.cuh"
 #include "conv_slab_pair.cuh"
 #include "conv_unit_fused.cuh"
+#include "conv_unit_fused_is.cuh"
 #include "conv_wgrad_slab.cuh"
 #include "conv_frame_ring.cuh"
 #include "conv_temporal_is.cuh"
@@ -71,6 +72,8 @@ static int g_wgrad_atomic_rate = 0;    // fvt_set_option("wgrad_atomic_rate", r)
                                        // heuristic picks fewer pixel splits and the step's weight gradients get SLOWER
                                        // (3.74 -> 4.06 ms; conv2_x 116 -> 157 us) — the flush overlaps other CTAs' MMAs
 static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
+static int g_unit_is = 1;        // fvt_set_option("unit_input_stationary", 0|1): fused (2+1)D unit with the temporal conv as one N = 192 MMA chain
+                                 // per mid frame (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame (conv_unit_fused.cuh)
 static int g_slab_pair = 0;      // fvt_set_option("slab_pair", 0|1|2): CTA-pair slab kernel (cta_group::2) for stationary-filter layers;
                                  // 2 = pair kernel with register stores instead of the staged TMA store (A/B runs)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
@@ -490,6 +493,7 @@ int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "wgrad_atomic_rate") == 0) { g_wgrad_atomic_rate = value; return 0; }
   if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_pair") == 0) { g_slab_pair = value; return 0; }
+  if (name != nullptr && strcmp(name, "unit_input_stationary") == 0) { g_unit_is = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
   if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
@@ -964,7 +968,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
 // ------------------------------------------------------------------------------------------------ K2f: fused (2+1)D unit
 // Geometry of the fused unit for a (spatial, temporal) descriptor pair; returns 0 and fills *up / *smem_bytes when the
 // pair is eligible, a negative status (error text set) otherwise.
-static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt_conv_desc* dt, UnitFusedParams* up, int* smem_bytes) {
+static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt_conv_desc* dt, UnitFusedParams* up, int* smem_bytes, int* use_is) {
   if (int e = validate_conv(ds)) return e;
   if (int e = validate_conv(dt)) return e;
   const bool spatial_ok = ds->kt == 1 && ds->kh == 3 && ds->kw == 3 && ds->st == 1 && ds->sh == 1 && ds->sw == 1 &&
@@ -998,7 +1002,10 @@ static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt
   u.slab_tx_bytes = u.wp * u.r_in * 128;
   u.n_mid = n_mid; u.n_out = 64;
   u.mid_blocks = (n_mid + 63) / 64; u.mid_k16 = n_mid / 16;
-  const int b_bytes = 9 * (n_mid / 2) * 128 + (3 * u.mid_blocks * 32 * 128 + 1023) / 1024 * 1024;
+  // input-stationary form: temporal filter as five 32-row blocks per K block (every tap rotation is a contiguous window)
+  *use_is = g_unit_is && n_mid % 48 == 0;
+  const int bt_bytes = *use_is ? u.mid_blocks * 5 * 32 * 128 : (3 * u.mid_blocks * 32 * 128 + 1023) / 1024 * 1024;
+  const int b_bytes = 9 * (n_mid / 2) * 128 + bt_bytes;
   const int aux = (512 + (2 * n_mid + 2 * 64) * 4 + 255) / 256 * 256;
   const int kSmemMax = 227 * 1024;
   u.stages = (kSmemMax - aux - b_bytes) / u.slab_slot_bytes;
@@ -1014,8 +1021,8 @@ int fvt_unit2p1_supported(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d
   const DeviceInfo* di = current_device_info(&st);
   if (di == nullptr) return st;
   UnitFusedParams u;
-  int smem = 0;
-  return plan_unit2p1(di, d_spatial, d_temporal, &u, &smem) == 0 ? 1 : 0;
+  int smem = 0, use_is = 0;
+  return plan_unit2p1(di, d_spatial, d_temporal, &u, &smem, &use_is) == 0 ? 1 : 0;
 }
 
 int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal, const void* x,
@@ -1026,8 +1033,8 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
   const DeviceInfo* di = current_device_info(&st);
   if (di == nullptr) return st;
   UnitFusedParams u;
-  int smem_bytes = 0;
-  if (int e = plan_unit2p1(di, d_spatial, d_temporal, &u, &smem_bytes)) return e;
+  int smem_bytes = 0, use_is = 0;
+  if (int e = plan_unit2p1(di, d_spatial, d_temporal, &u, &smem_bytes, &use_is)) return e;
   if (x == nullptr || w_spatial_packed == nullptr || w_temporal_packed == nullptr || y == nullptr)
     return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (scale_mid == nullptr || shift_mid == nullptr || scale_out == nullptr || shift_out == nullptr)
@@ -1059,6 +1066,7 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
   cudaGetDevice(&dev);
   if (!attr_set_u[dev]) {
     cudaError_t e = cudaFuncSetAttribute(unit2p1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(unit2p1_fused_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(unit2p1_fused_kernel): %s", cudaGetErrorString(e));
     attr_set_u[dev] = true;
   }
@@ -1068,14 +1076,15 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kUnitThreads);
+  cfg.blockDim = dim3(use_is ? kUnitIsThreads : kUnitThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, unit2p1_fused_kernel, tmx, tmws, tmwt, u);
+  cudaError_t le = use_is ? cudaLaunchKernelEx(&cfg, unit2p1_fused_is_kernel, tmx, tmws, tmwt, u)
+                          : cudaLaunchKernelEx(&cfg, unit2p1_fused_kernel, tmx, tmws, tmwt, u);
   if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "unit2p1_fused_kernel launch: %s", cudaGetErrorString(le));
   return check_launch("unit2p1_fused_kernel");
 }

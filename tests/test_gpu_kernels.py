@@ -370,10 +370,13 @@ def _unit_case(device, n, t, h, w, mid, seed, residual):
                                    (2, 3, 14, 14, 144, True),      # second tile clipped at the bottom edge
                                    (1, 5, 56, 56, 96, True),       # another mid width (two 64-channel blocks, 6 K steps)
                                    (20, 3, 56, 56, 144, True)])    # more units than CTA pairs: several clips per cluster
-def test_fused_unit_matches_two_launches(cuda_device, lib, shape):
+@pytest.mark.parametrize("input_stationary", [1, 0])
+def test_fused_unit_matches_two_launches(cuda_device, lib, shape, input_stationary):
     """K2f (one launch, mid in tensor memory, cta_group::2, A operand from TMEM) == spatial conv launch + temporal conv
     launch on identical inputs: the bf16 rounding of mid is the same, so results differ by fp32 summation order only
-    (<= 1 bf16 ulp per element); and both agree with a torch fp32 evaluation at the bf16 tolerance (1e-2 of max)."""
+    (<= 1 bf16 ulp per element); and both agree with a torch fp32 evaluation at the bf16 tolerance (1e-2 of max).
+    Both schedules of the temporal conv: input-stationary (one N = 192 MMA chain per mid frame, rotating tap window,
+    slots zeroed by the output warps) and output-stationary (three N = 64 chains per output frame)."""
     import torch
     import torch.nn.functional as F
     from fastvideotagging_b200 import ops
@@ -383,8 +386,12 @@ def test_fused_unit_matches_two_launches(cuda_device, lib, shape):
     y_mid = ops.conv3d_fwd(d_s, x, wp_s, sc_m, sh_m)
     y_two = ops.conv3d_fwd(d_t, y_mid, wp_t, sc_o, sh_o, res)
     y_fused = torch.full_like(y_two, float("nan"))
-    ops.unit2p1_fwd(d_s, d_t, x, wp_s, sc_m, sh_m, wp_t, sc_o, sh_o, res, out=y_fused)
-    torch.cuda.synchronize()
+    assert lib.fvt_set_option(b"unit_input_stationary", input_stationary) == 0
+    try:
+        ops.unit2p1_fwd(d_s, d_t, x, wp_s, sc_m, sh_m, wp_t, sc_o, sh_o, res, out=y_fused)
+        torch.cuda.synchronize()
+    finally:
+        lib.fvt_set_option(b"unit_input_stationary", 1)
     a, b = y_fused.float(), y_two.float()
     assert torch.isfinite(a).all()
     tol = 2 ** -7 * b.abs() + 2 ** -7 * 1e-2 * b.abs().max()
