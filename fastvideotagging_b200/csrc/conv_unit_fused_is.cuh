@@ -27,6 +27,15 @@
 
 namespace fvt {
 
+// 4-D tiled load whose completion bytes are counted on a barrier of EITHER CTA of the pair (.cta_group::2): both CTAs' slabs
+// signal the leader's barrier directly, so the MMA warp waits once per frame and no relay warp is needed.
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 constexpr int kUnitIsThreads = 768;
 constexpr int kUnitIsDCol0 = 320;          // first TMEM column of the 192-column accumulator window
 
@@ -48,8 +57,8 @@ unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   uint8_t* smem_bt = smem_bs + kTaps * bs_slab;                        // [mid_blocks][5][32 x 64]
   uint8_t* smem_a = smem_bt + p.mid_blocks * bt_cb_bytes;               // [stages][slot]
   uint8_t* aux = smem_a + p.stages * p.slab_slot_bytes;
-  uint64_t* slab_full = reinterpret_cast<uint64_t*>(aux);             // [kUnitMaxStages] local TMA completion
-  uint64_t* peer_full = slab_full + kUnitMaxStages;                    // [kUnitMaxStages] leader: the peer's slab has landed
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(aux);             // [kUnitMaxStages] leader: both CTAs' slabs have landed
+  uint64_t* peer_full = slab_full + kUnitMaxStages;                    // [kUnitMaxStages] (unused)
   uint64_t* slab_empty = peer_full + kUnitMaxStages;                   // [kUnitMaxStages] multicast commit
   uint64_t* b_full = slab_empty + kUnitMaxStages;                      // [1] local filter halves landed
   uint64_t* peer_b_full = b_full + 1;                                  // [1] leader: the peer's filter halves landed
@@ -113,10 +122,10 @@ unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int h0 = tile * p.r_out;            // a dummy tile (odd tiles_per_frame) starts beyond H: its rows are never stored
       for (int t = fs0; t < fs1; ++t) {
         ptx::mbar_wait(ptx::smem_u32(&slab_empty[stage]), phase ^ 1);
-        const uint32_t fb = ptx::smem_u32(&slab_full[stage]);
+        const uint32_t fb = pair::map_to_rank(ptx::smem_u32(&slab_full[stage]), 0);      // the LEADER's barrier counts both slabs
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(fb, p.slab_tx_bytes);
-          tma_load_4d(ptx::smem_u32(smem_a + stage * p.slab_slot_bytes), &tmap_x, fb, 0, -1, h0 - 1, clip * p.t + t);
+          if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&slab_full[stage]), 2 * p.slab_tx_bytes);
+          tma_load_4d_pair(ptx::smem_u32(smem_a + stage * p.slab_slot_bytes), &tmap_x, fb, 0, -1, h0 - 1, clip * p.t + t);
           if (t + p.stages < fs1) tma_prefetch_4d(&tmap_x, 0, -1, h0 - 1, clip * p.t + t + p.stages);     // warm L2 for the load after next
         }
         __syncwarp();
@@ -142,21 +151,11 @@ unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       __syncwarp();
     }
   } else if (warp == 1 && !leader) {
-    // ===================================================== relay (peer CTA): forward local TMA completions to the leader
+    // ===================================================== relay (peer CTA): forward the filter's TMA completion to the leader
     if (has_work) {
       ptx::mbar_wait(ptx::smem_u32(b_full), 0);
       if (ptx::elect_one()) pair::remote_arrive(pair::map_to_rank(ptx::smem_u32(peer_b_full), 0));
       __syncwarp();
-    }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (unit::Segments sg(p.total_steps, p.t); sg.next(u, tb, te, fs0, fs1);) {
-      for (int t = fs0; t < fs1; ++t) {
-        ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
-        if (ptx::elect_one()) pair::remote_arrive(pair::map_to_rank(ptx::smem_u32(&peer_full[stage]), 0));
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA): M = 256 over the pair
@@ -182,8 +181,7 @@ unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       for (int tp = fs0; tp <= fs1; ++tp) {
         if (tp < fs1) {
           // ---- spatial conv of frame tp into S, as soon as the previous frame's S sits in the convert warps' registers
-          ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
-          pair::wait_cluster(ptx::smem_u32(&peer_full[stage]), phase);
+          pair::wait_cluster(ptx::smem_u32(&slab_full[stage]), phase);
           if (gf > 0) pair::wait_cluster(ptx::smem_u32(s_empty), (gf - 1u) & 1u);
           ++gf;
           ptx::tc_fence_after();
