@@ -74,6 +74,7 @@ static int g_wgrad_atomic_rate = 0;    // fvt_set_option("wgrad_atomic_rate", r)
 static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
 static int g_unit_is = 1;        // fvt_set_option("unit_input_stationary", 0|1): fused (2+1)D unit with the temporal conv as one N = 192 MMA chain
                                  // per mid frame (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame (conv_unit_fused.cuh)
+static int g_slab_pair_auto = 1; // fvt_set_option("slab_pair_auto", 0|1): CTA-pair slab kernel when the filter fits two SMs but not one
 static int g_slab_pair = 0;      // fvt_set_option("slab_pair", 0|1|2): CTA-pair slab kernel (cta_group::2) for stationary-filter layers;
                                  // 2 = pair kernel with register stores instead of the staged TMA store (A/B runs)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
@@ -493,6 +494,7 @@ int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "wgrad_atomic_rate") == 0) { g_wgrad_atomic_rate = value; return 0; }
   if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_pair") == 0) { g_slab_pair = value; return 0; }
+  if (name != nullptr && strcmp(name, "slab_pair_auto") == 0) { g_slab_pair_auto = value; return 0; }
   if (name != nullptr && strcmp(name, "unit_input_stationary") == 0) { g_unit_is = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
@@ -679,20 +681,26 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
       // ---- K1s2: the same convolution on a CTA pair (tcgen05.mma.cta_group::2) when the filter is stationary: each CTA
       //      holds half of the filter rows, which frees shared memory for the staged TMA-store epilogue
-      if (g_slab_pair && sp.b_stationary && sp.num_n_tiles == 1 && bn % 16 == 0 && sp.box_rows == sp.r_in &&
-          !(want_stats && scale != nullptr) && di->sm_count % 2 == 0) {
+      //      Default ("slab_pair_auto") for the layers whose filter does not fit one SM but fits two (conv3_x 128 -> 288 with
+      //      one N tile per cluster, conv2_x data gradient 144 -> 64); "slab_pair" forces it for single-SM-stationary layers.
+      const bool pair_shape_ok = bn % 16 == 0 && sp.box_rows == sp.r_in && !(want_stats && scale != nullptr) &&
+                                 di->sm_count % 2 == 0 && (di->sm_count / 2) % sp.num_n_tiles == 0;
+      const bool pair_forced = g_slab_pair && sp.b_stationary && sp.num_n_tiles == 1;
+      const bool pair_auto = g_slab_pair_auto && !sp.b_stationary;
+      if (pair_shape_ok && (pair_forced || pair_auto)) {
         SlabPairParams pp;
         memset(&pp, 0, sizeof(pp));
         pp.s = sp;
         pp.n_half = bn / 2;
+        pp.n_tiles = sp.num_n_tiles;
         const int num_m_tiles = sp.frames * sp.tiles_per_frame;
         pp.num_pairs = (num_m_tiles + 1) / 2;
-        pp.tma_store = (g_slab_pair == 1 && bn == d->cout) ? 1 : 0;
+        pp.tma_store = (pair_forced && g_slab_pair == 1 && bn == d->cout) ? 1 : 0;
         pp.out_tile_bytes = (sp.r_out * d->w * d->cout * 2 + 1023) / 1024 * 1024;
-        const int aux2 = (512 + 8 * bn + 255) / 256 * 256;
+        const int aux2 = (512 + 8 * rows + 255) / 256 * 256;
         const int b_bytes = (b_all * pp.n_half * 128 + 1023) / 1024 * 1024;
         const int out_bytes = pp.tma_store ? 2 * pp.out_tile_bytes : 0;
-        int stages2 = (kSmemMax - aux2 - b_bytes - out_bytes) / stage_bytes;
+        int stages2 = (kSmemMax - aux2 - b_bytes - out_bytes) / sp.slab_slot_bytes;      // ring slots of one 64-channel block
         if (stages2 > kPairMaxStages) stages2 = kPairMaxStages;
         if (stages2 >= 2) {
           pp.s.stages = stages2;
@@ -716,8 +724,9 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
             if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_pair_kernel): %s", cudaGetErrorString(e));
             attr_set_p[devp] = true;
           }
-          const int smem2 = b_bytes + stages2 * stage_bytes + out_bytes + aux2;
-          int clusters = pp.num_pairs < di->sm_count / 2 ? pp.num_pairs : di->sm_count / 2;
+          const int smem2 = b_bytes + stages2 * sp.slab_slot_bytes + out_bytes + aux2;
+          int clusters = di->sm_count / 2;                                                // a multiple of n_tiles (checked above)
+          if (pp.num_pairs * pp.n_tiles < clusters) clusters = pp.num_pairs * pp.n_tiles;
           cudaLaunchConfig_t cfg;
           memset(&cfg, 0, sizeof(cfg));
           cfg.gridDim = dim3(2 * clusters);

@@ -17,6 +17,16 @@
 //     CTAs' slab_empty / acc_full barriers (same shared-memory offsets);
 //   * both CTAs' epilogue warps drain their own TMEM rows and arrive (locally / remotely) on the LEADER's acc_empty.
 //
+// Two generalisations make the pair the default schedule for the layers whose filter does NOT fit one SM but does fit
+// two (conv3_x 1x3x3 128 -> 288: 663 KB streamed per 128-row tile by K1s, the smem fill rate paces it; conv2_x 1x3x3
+// data gradient 144 -> 64: 221 KB):
+//   * N tiles: a cluster keeps ONE N tile (n_tile columns) of the filter for its lifetime, cluster c works on N tile
+//     c mod n_tiles and on every (clusters / n_tiles)-th tile pair; the input tile is read once per N tile (L2);
+//   * the input ring is per 64-channel BLOCK, not per tile: the MMAs run channel-block-major, a block slot is released
+//     as soon as its nine taps are issued, so two slots overlap loads and MMAs even when only one tile's slab fits.
+// Both CTAs' slab loads count on the LEADER's barrier (cp.async.bulk.tensor .cta_group::2), so the MMA warp waits once
+// per block and only the one-time filter load needs the relay.
+//
 // Warp roles per CTA (384 threads): warp0 slab producer, warp1 MMA issuer (leader) / relay (peer), warp2 TMEM
 // allocator, warp3 filter producer, warps 4-11 epilogue.
 // Replaces cuDNN convolution calls for Conv3D(k=(1,3,3)) at reference model/R2Plus1.py:27-31,100-104, net.py:40-42.
@@ -28,7 +38,7 @@
 namespace fvt {
 
 constexpr int kPairThreads = 384;
-constexpr int kPairMaxStages = 4;
+constexpr int kPairMaxStages = 6;          // input ring slots (one 64-channel block each)
 
 struct SlabPairParams {
   SlabParams s;               // geometry as in conv_slab.cuh (n_tile = full N, b_ring = taps * cin_blocks)
@@ -36,6 +46,7 @@ struct SlabPairParams {
   int num_pairs;              // ceil(num_m_tiles / 2): tile 2*pair + rank belongs to CTA `rank` of the cluster
   int out_tile_bytes;         // r_out * w * cout_store * 2 rounded up to 128
   int tma_store;              // 1: staged TMA store (needs n_tile == cout_store), 0: register stores
+  int n_tiles;                // N tiles of n_tile columns; a cluster works on N tile (cluster id mod n_tiles) only
 };
 
 namespace pair {
@@ -107,6 +118,13 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
   ptx::tma_store_4d(tmap, src, c0, c1, c2, c3);
 }
+// 4-D tiled load whose completion bytes are counted on a barrier of EITHER CTA of the pair (.cta_group::2)
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 }  // namespace pair
 
 __global__ void __launch_bounds__(kPairThreads, 1)
@@ -123,13 +141,13 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const int taps = p.kh * p.kw;
   const int b_slab_bytes = pp.n_half * 128;
   const int b_all = taps * p.cin_blocks;
-  const int stage_bytes = p.cin_blocks * p.slab_slot_bytes;
+  const int stage_bytes = p.slab_slot_bytes;                           // one ring slot = one 64-channel block of one tile
   uint8_t* smem_b = smem;                                              // [b_all][n_half x 64]
-  uint8_t* smem_a = smem + ((b_all * b_slab_bytes + 1023) & ~1023);    // [stages][cin_blocks][slot]
+  uint8_t* smem_a = smem + ((b_all * b_slab_bytes + 1023) & ~1023);    // [stages][slot]
   uint8_t* smem_o = smem_a + p.stages * stage_bytes;                   // [2][out_tile_bytes] (tma_store)
   uint8_t* aux = smem_o + (pp.tma_store ? 2 * pp.out_tile_bytes : 0);
-  uint64_t* slab_full = reinterpret_cast<uint64_t*>(aux);             // [kPairMaxStages] local TMA completion
-  uint64_t* peer_full = slab_full + kPairMaxStages;                    // [kPairMaxStages] leader: the peer's slab has landed
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(aux);             // [kPairMaxStages] leader: both CTAs' blocks have landed
+  uint64_t* peer_full = slab_full + kPairMaxStages;                    // [kPairMaxStages] (unused)
   uint64_t* slab_empty = peer_full + kPairMaxStages;                   // [kPairMaxStages] multicast commit
   uint64_t* b_full = slab_empty + kPairMaxStages;                      // [1] local filter half landed
   uint64_t* peer_b_full = b_full + 1;                                  // [1] leader: the peer's filter half landed
@@ -137,7 +155,7 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   uint64_t* acc_empty = acc_full + 2;                                  // [2] leader: 16 epilogue warps (8 local + 8 remote)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* affine_smem = reinterpret_cast<float*>(tmem_slot + 4);        // scale[n_tile], shift[n_tile] / statistics
-  const int n_total = p.n_tile;
+  const int n_total = p.n_tile * pp.n_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_x);
@@ -175,35 +193,37 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_m_tiles = p.frames * p.tiles_per_frame;
-  const int pair0 = static_cast<int>(pair::cluster_id_x());
-  const int pair_step = static_cast<int>(pair::nclusters_x());
+  const int nt = static_cast<int>(pair::cluster_id_x()) % pp.n_tiles;            // this cluster's N tile
+  const int n0 = nt * p.n_tile;
+  const int pair0 = static_cast<int>(pair::cluster_id_x()) / pp.n_tiles;
+  const int pair_step = static_cast<int>(pair::nclusters_x()) / pp.n_tiles;      // the host launches a multiple of n_tiles clusters
 
   if (warp == 0) {
-    // ===================================================== input slab producer (own tile; out-of-range tiles zero-fill)
+    // ===================================================== input slab producer (own tile, block by block; out-of-range tiles zero-fill)
     int stage = 0;
     uint32_t phase = 0;
     for (int pr = pair0; pr < pp.num_pairs; pr += pair_step) {
       const int mt = 2 * pr + static_cast<int>(rank);
       const int frame = mt / p.tiles_per_frame;
       const int h0 = (mt - frame * p.tiles_per_frame) * p.r_out;
-      ptx::mbar_wait(ptx::smem_u32(&slab_empty[stage]), phase ^ 1);
-      const uint32_t fb = ptx::smem_u32(&slab_full[stage]);
-      if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(fb, p.cin_blocks * p.slab_tx_bytes);
-        for (int cb = 0; cb < p.cin_blocks; ++cb)
-          tma_load_4d(ptx::smem_u32(smem_a + stage * stage_bytes + cb * p.slab_slot_bytes), &tmap_x, fb, cb * 64, -p.pw,
-                      h0 - p.ph, frame);
-        if (p.prefetch_dist > 0) {
-          const int mt2 = mt + 2 * p.prefetch_dist * pair_step;
-          if (mt2 < num_m_tiles) {
-            const int frame2 = mt2 / p.tiles_per_frame;
-            const int h2 = (mt2 - frame2 * p.tiles_per_frame) * p.r_out;
-            for (int cb = 0; cb < p.cin_blocks; ++cb) tma_prefetch_4d(&tmap_x, cb * 64, -p.pw, h2 - p.ph, frame2);
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        ptx::mbar_wait(ptx::smem_u32(&slab_empty[stage]), phase ^ 1);
+        const uint32_t fb = pair::map_to_rank(ptx::smem_u32(&slab_full[stage]), 0);       // the LEADER's barrier counts both blocks
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&slab_full[stage]), 2 * p.slab_tx_bytes);
+          pair::tma_load_4d_2sm(ptx::smem_u32(smem_a + stage * stage_bytes), &tmap_x, fb, cb * 64, -p.pw, h0 - p.ph, frame);
+          if (p.prefetch_dist > 0) {
+            const int mt2 = mt + 2 * p.prefetch_dist * pair_step;
+            if (mt2 < num_m_tiles) {
+              const int frame2 = mt2 / p.tiles_per_frame;
+              const int h2 = (mt2 - frame2 * p.tiles_per_frame) * p.r_out;
+              tma_prefetch_4d(&tmap_x, cb * 64, -p.pw, h2 - p.ph, frame2);
+            }
           }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 3) {
     // ===================================================== filter producer: this CTA's half of the N rows, once
@@ -215,24 +235,16 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         for (int tap = 0; tap < taps; ++tap)
           for (int cb = 0; cb < p.cin_blocks; ++cb, ++j)
             ptx::tma_load_2d(ptx::smem_u32(smem_b + j * b_slab_bytes), &tmap_w, bb, tap * p.k_per_tap + cb * 64,
-                             static_cast<int>(rank) * pp.n_half);
+                             n0 + static_cast<int>(rank) * pp.n_half);
       }
       __syncwarp();
     }
   } else if (warp == 1 && !leader) {
-    // ===================================================== relay (peer CTA): forward local TMA completions to the leader
+    // ===================================================== relay (peer CTA): forward the filter's TMA completion to the leader
     if (pair0 < pp.num_pairs) {
       ptx::mbar_wait(ptx::smem_u32(b_full), 0);
       if (ptx::elect_one()) pair::remote_arrive(pair::map_to_rank(ptx::smem_u32(peer_b_full), 0));
       __syncwarp();
-    }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int pr = pair0; pr < pp.num_pairs; pr += pair_step) {
-      ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
-      if (ptx::elect_one()) pair::remote_arrive(pair::map_to_rank(ptx::smem_u32(&peer_full[stage]), 0));
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA): M = 256 over the pair
@@ -240,47 +252,46 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     bool first = true;
+    const uint64_t b_desc0 = ptx::make_sw128_desc(ptx::smem_u32(smem_b), 16, 1024);
+    const uint32_t b_step = static_cast<uint32_t>(b_slab_bytes) >> 4;
+    const uint32_t b_tap_step = b_step * static_cast<uint32_t>(p.cin_blocks);
+    const uint32_t a_row_step = static_cast<uint32_t>(p.wp) * 8u;
     for (int pr = pair0; pr < pp.num_pairs; pr += pair_step) {
-      ptx::mbar_wait(ptx::smem_u32(&slab_full[stage]), phase);
-      pair::wait_cluster(ptx::smem_u32(&peer_full[stage]), phase);
       if (first) {
         ptx::mbar_wait(ptx::smem_u32(b_full), 0);
         pair::wait_cluster(ptx::smem_u32(peer_b_full), 0);
         first = false;
       }
       pair::wait_cluster(ptx::smem_u32(&acc_empty[acc]), acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t a_base = ptx::smem_u32(smem_a + stage * stage_bytes);
       const uint32_t d_tmem = tmem_base + acc * 256;
-      const uint64_t a_desc0 = ptx::make_sw128_desc(a_base, 16, 1024);
-      const uint64_t b_desc0 = ptx::make_sw128_desc(ptx::smem_u32(smem_b), 16, 1024);
-      const uint32_t a_cb_step = static_cast<uint32_t>(p.slab_slot_bytes) >> 4;
-      const uint32_t b_step = static_cast<uint32_t>(b_slab_bytes) >> 4;
-      const uint32_t a_row_step = static_cast<uint32_t>(p.wp) * 8u;
-      if (ptx::elect_one()) {
-        uint32_t acc_flag = 0;
-        uint64_t b_desc = b_desc0;
-        uint64_t a_row = a_desc0;
-        for (int dh = 0; dh < p.kh; ++dh, a_row += a_row_step) {
-          uint64_t a_tap = a_row;
-          for (int dw = 0; dw < p.kw; ++dw, a_tap += 8) {
-            uint64_t a_desc = a_tap;
-            int k16 = p.cin_k16;
-            for (int cb = 0; cb < p.cin_blocks; ++cb, a_desc += a_cb_step, b_desc += b_step, k16 -= 4) {
-              pair::umma2_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc_flag);
+      uint32_t acc_flag = 0;
+      int k16 = p.cin_k16;
+      for (int cb = 0; cb < p.cin_blocks; ++cb, k16 -= 4) {
+        // ---- channel-block-major: the nine taps of one 64-channel block, then the block's ring slot is free again
+        pair::wait_cluster(ptx::smem_u32(&slab_full[stage]), phase);
+        ptx::tc_fence_after();
+        const uint64_t a_desc0 = ptx::make_sw128_desc(ptx::smem_u32(smem_a + stage * stage_bytes), 16, 1024);
+        if (ptx::elect_one()) {
+          uint64_t b_desc = b_desc0 + static_cast<uint32_t>(cb) * b_step;
+          uint64_t a_row = a_desc0;
+          for (int dh = 0; dh < p.kh; ++dh, a_row += a_row_step) {
+            uint64_t a_tap = a_row;
+            for (int dw = 0; dw < p.kw; ++dw, a_tap += 8, b_desc += b_tap_step) {
+              pair::umma2_bf16_ss(d_tmem, a_tap, b_desc, idesc, acc_flag);
+              if (k16 > 1) pair::umma2_bf16_ss(d_tmem, a_tap + 2, b_desc + 2, idesc, 1);
+              if (k16 > 2) pair::umma2_bf16_ss(d_tmem, a_tap + 4, b_desc + 4, idesc, 1);
+              if (k16 > 3) pair::umma2_bf16_ss(d_tmem, a_tap + 6, b_desc + 6, idesc, 1);
               acc_flag = 1;
-              if (k16 > 1) pair::umma2_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
-              if (k16 > 2) pair::umma2_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
-              if (k16 > 3) pair::umma2_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
             }
           }
+          if (cb == p.cin_blocks - 1) pair::umma2_commit_both(ptx::smem_u32(&acc_full[acc]));
+          pair::umma2_commit_both(ptx::smem_u32(&slab_empty[stage]));
         }
-        pair::umma2_commit_both(ptx::smem_u32(&acc_full[acc]));
-        pair::umma2_commit_both(ptx::smem_u32(&slab_empty[stage]));
+        __syncwarp();
+        acc_flag = 1;
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (own 128 accumulator rows)
@@ -292,7 +303,7 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     EpilogueArgs ea;
     ea.block_n = p.n_tile; ea.cout_store = p.cout_store; ea.flags = p.flags;
     ea.scale_smem = p.scale != nullptr ? affine_smem : nullptr; ea.shift_smem = affine_smem + n_total;
-    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = affine_smem; ea.stat_stride = n_total;
+    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = affine_smem + n0; ea.stat_stride = n_total;
     const int r = q * 32 + lane;                 // GEMM row = padded position inside the tile
     const int hl = r / p.wp, wl = r - hl * p.wp;
     int shl[4];
@@ -328,11 +339,11 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         ea.stage_pitch = p.cout_store * 2;
         ea.stage_swizzle = 0;
       }
-      epilogue_prefetch_residual(ea, 0, out_row, grp);
+      epilogue_prefetch_residual(ea, n0, out_row, grp);
       ptx::mbar_wait(ptx::smem_u32(&acc_full[acc]), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_chunks(ea, taddr, 0, out_row, grp, lane);
+      epilogue_chunks(ea, taddr, n0, out_row, grp, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) pair::remote_arrive(acc_empty_leader0 + acc * 8);      // the leader owns the accumulator hand-back
@@ -350,7 +361,7 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (pp.tma_store && et == 0) ptx::tma_store_wait<0>();
     if (acc_stats && pair0 < pp.num_pairs) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < n_total && i < p.cout_store; i += 256) {
+      for (int i = n0 + et; i < n0 + p.n_tile && i < p.cout_store; i += 256) {
         atomicAdd(p.stats + i, affine_smem[i]);
         atomicAdd(p.stats + p.cout_store + i, affine_smem[n_total + i]);
       }

@@ -421,3 +421,51 @@ def test_fused_unit_rejects_other_geometries(cuda_device, lib):
     import ctypes
     with pytest.raises(_lib.FvtError):          # the C entry point itself refuses (bad descriptor pair), nothing is launched
         _lib.check(lib.fvt_unit2p1_fwd(ctypes.byref(d_s), ctypes.byref(d_t), *([None] * 10)))
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1)),     # conv3_x 1x3x3: two N tiles, two channel blocks
+                                   (1, 3, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1)),     # odd number of row tiles (21): a dummy tile
+                                   (2, 3, 56, 56, 144, 64, (1, 3, 3), (0, 1, 1)),      # conv2_x data-gradient shape: 2.25 channel blocks
+                                   (1, 2, 14, 14, 128, 288, (1, 3, 3), (0, 1, 1)),     # clipped bottom rows
+                                   (40, 4, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1))])   # more tile pairs than clusters
+def test_cta_pair_auto_matches_streamed_single_cta(cuda_device, lib, shape):
+    """Layers whose filter fits two SMs but not one run on the CTA-pair kernel by default (one N tile per cluster, input ring
+    per channel block).  Same convolution as the single-CTA streamed-filter slab kernel; the channel-block-major MMA order
+    changes the fp32 summation order only (<= 1 bf16 ulp): plain, affine + residual + ReLU, and BatchNorm statistics."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w, cin, cout, k, p = shape
+    gen = torch.Generator().manual_seed(n * 100 + h + cin)
+    x = (torch.randn(n, t, h, w, cin, generator=gen) * 0.5).to(torch.bfloat16).to(cuda_device)
+    wt = (torch.randn(cout, cin, *k, generator=gen) / (cin * k[1] * k[2]) ** 0.5).to(cuda_device)
+    res = torch.randn(n, t, h, w, cout, generator=gen).to(torch.bfloat16).to(cuda_device)
+    sc = (0.5 + torch.rand(cout, generator=gen)).to(cuda_device)
+    sh = torch.randn(cout, generator=gen).to(cuda_device)
+    d_plain = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, 0)
+    d_full = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+    d_stat = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, ops.FVT_CONV_STATS)
+    wp = ops.pack_conv_weight(d_plain, wt)
+
+    def run_all():
+        a = ops.conv3d_fwd(d_plain, x, wp).clone()
+        b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
+        st = torch.zeros(2 * cout, device=cuda_device)
+        c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
+        torch.cuda.synchronize()
+        return a, b, c, st.clone()
+
+    out = {}
+    try:
+        for mode in (0, 1):
+            assert lib.fvt_set_option(b"slab_pair_auto", mode) == 0
+            out[mode] = run_all()
+    finally:
+        lib.fvt_set_option(b"slab_pair_auto", 1)
+    for i in range(3):
+        a, b = out[1][i].float(), out[0][i].float()
+        assert torch.isfinite(a).all()
+        tol = 2 ** -7 * b.abs() + 2 ** -7 * 1e-2 * b.abs().max()
+        assert ((a - b).abs() <= tol).all(), (i, (a - b).abs().max().item(), b.abs().max().item())
+    ref = out[0][3]
+    assert (out[1][3] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+    assert out[0][0].float().abs().max().item() > 0

@@ -1,0 +1,46 @@
+"""CTA-pair slab kernel (one N tile per cluster, block-granular input ring) against the single-CTA streamed-filter slab kernel
+on the layers that pick it by default."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fastvideotagging_b200 import ops, _lib
+lib = _lib.load()
+dev = torch.device("cuda:0")
+CASES = [
+    ("conv3 spatial 128->288 b48", 48, 16, 28, 28, 128, 288, 0),
+    ("conv3 spatial 128->288 b4 stats", 4, 16, 28, 28, 128, 288, 1),
+    ("conv2 dgrad 144->64 b4", 4, 32, 56, 56, 144, 64, 0),
+    ("conv2 dgrad 144->64 b16 T16", 16, 16, 56, 56, 144, 64, 0),
+]
+
+
+def timeit(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e3
+
+
+for name, n, t, h, w, cin, cout, stats in CASES:
+    x = (torch.randn(n, t, h, w, cin, device=dev) * 0.5).to(torch.bfloat16)
+    wt = torch.randn(cout, cin, 1, 3, 3, device=dev) / (cin * 9) ** 0.5
+    sc, sh = 0.5 + torch.rand(cout, device=dev), torch.randn(cout, device=dev)
+    d = ops.conv_desc(n, t, h, w, cin, cout, (1, 3, 3), (1, 1, 1), (0, 1, 1), ops.FVT_CONV_STATS if stats else ops.FVT_CONV_RELU)
+    wp = ops.pack_conv_weight(d, wt)
+    y = torch.empty(n, t, h, w, cout, device=dev, dtype=torch.bfloat16)
+    st = torch.zeros(2 * cout, device=dev)
+    gflop = 2.0 * n * t * h * w * cout * cin * 9 / 1e9
+    line = "%-34s" % name
+    for mode in (0, 1):
+        lib.fvt_set_option(b"slab_pair_auto", mode)
+        fn = (lambda: ops.conv3d_fwd(d, x, wp, out=y, stats=st)) if stats else (lambda: ops.conv3d_fwd(d, x, wp, sc, sh, out=y))
+        us = timeit(fn)
+        line += " | %s %7.1f us (%5.0f TF/s)" % ("pair  " if mode else "single", us, gflop / us * 1e3)
+        for dl, bits in (("no-epi", 512),):
+            lib.fvt_set_option(b"debug_flags", bits)
+            line += " %s %7.1f" % (dl, timeit(fn))
+            lib.fvt_set_option(b"debug_flags", 0)
+    lib.fvt_set_option(b"slab_pair_auto", 1)
+    print(line, flush=True)
