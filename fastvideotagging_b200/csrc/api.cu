@@ -74,7 +74,7 @@ static int g_wgrad_atomic_rate = 0;    // fvt_set_option("wgrad_atomic_rate", r)
 static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
 static int g_unit_is = 1;        // fvt_set_option("unit_input_stationary", 0|1): fused (2+1)D unit with the temporal conv as one N = 192 MMA chain
                                  // per mid frame (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame (conv_unit_fused.cuh)
-static int g_slab_pair_auto = 1; // fvt_set_option("slab_pair_auto", 0|1): CTA-pair slab kernel when the filter fits two SMs but not one
+static int g_slab_pair_auto = 1; // fvt_set_option("slab_pair_auto", 0|1|2): CTA-pair slab kernel when the filter fits two SMs but not one (2: also for small problems)
 static int g_slab_pair = 0;      // fvt_set_option("slab_pair", 0|1|2): CTA-pair slab kernel (cta_group::2) for stationary-filter layers;
                                  // 2 = pair kernel with register stores instead of the staged TMA store (A/B runs)
 static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
@@ -693,6 +693,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
         pp.s = sp;
         pp.n_half = bn / 2;
         pp.n_tiles = sp.num_n_tiles;
+        pp.w_chunks = 1; pp.w_tile = d->w;
         const int num_m_tiles = sp.frames * sp.tiles_per_frame;
         pp.num_pairs = (num_m_tiles + 1) / 2;
         pp.tma_store = (pair_forced && g_slab_pair == 1 && bn == d->cout) ? 1 : 0;
@@ -759,6 +760,92 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       else
         conv_slab_fwd_kernel<8><<<grid, kSlabThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
       return check_launch("conv_slab_fwd_kernel");
+    }
+  }
+
+  // ---- K1s2 (temporal): stride-1 kt x 1 x 1 convs whose filter fits two SMs but not one (conv3_x 288 -> 128 and its data
+  //      gradient) on the CTA-pair slab kernel: image rows = frames, image columns = H*W positions, 16 frames x 8 positions per
+  //      tile (taps = shifted descriptors, frames outside the clip = TMA zero fill), filter stationary, one N tile per cluster
+  if (g_slab_pair_auto && !g_disable_slab && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 &&
+      d->sw == 1 && d->ph == 0 && d->pw == 0 && 2 * d->pt == d->kt - 1 && d->cin > 64 && bn % 16 == 0 &&
+      di->sm_count % 2 == 0 && (di->sm_count / 2) % (rows / bn) == 0 && !((d->flags & FVT_CONV_STATS) && scale != nullptr)) {
+    const int kSmemMax = 227 * 1024;
+    const int cin_blocks = (d->cin + 63) / 64;
+    // would K1i (single SM, every input frame read exactly once) take it?  then leave it there
+    const bool tis_fits = rows == bn && d->h * d->w >= 128 &&
+                          d->kt * cin_blocks * bn * 128 + (512 + 16 * bn + 255) / 256 * 256 + 3 * cin_blocks * 128 * 128 <= kSmemMax;
+    int r_out = 16;
+    while (r_out > d->t) r_out >>= 1;
+    SlabParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.frames = d->n; sp.h = d->t; sp.w = d->h * d->w;
+    sp.ph = d->pt; sp.pw = 0; sp.kh = d->kt; sp.kw = 1;
+    sp.r_out = r_out; sp.r_in = r_out + d->kt - 1;
+    const int w_tile = 128 / r_out;
+    sp.wp = w_tile;
+    const int row_tiles = (d->t + r_out - 1) / r_out, w_chunks = (sp.w + w_tile - 1) / w_tile;
+    sp.tiles_per_frame = row_tiles * w_chunks;
+    sp.k_per_tap = d->cin; sp.cin_blocks = cin_blocks; sp.cin_k16 = d->cin / 16;
+    sp.n_tile = bn; sp.num_n_tiles = rows / bn;
+    const int slot_rows = (sp.r_in * sp.wp + 7) / 8 * 8;
+    sp.slab_slot_bytes = (slot_rows * 128 + 1023) / 1024 * 1024;
+    sp.slab_tx_bytes = sp.wp * sp.r_in * 128;
+    sp.box_rows = sp.r_in;
+    sp.prefetch_dist = g_slab_prefetch > 0 ? g_slab_prefetch : 0;
+    sp.cout_store = d->cout; sp.flags = d->flags | g_debug_flags;
+    sp.scale = scale; sp.shift = shift; sp.residual = (const __nv_bfloat16*)residual;
+    sp.y = (__nv_bfloat16*)y; sp.stats = stats;
+    const int b_all = d->kt * cin_blocks;
+    const int b_bytes = (b_all * (bn / 2) * 128 + 1023) / 1024 * 1024;
+    const int aux2 = (512 + 8 * rows + 255) / 256 * 256;
+    int stages2 = (kSmemMax - aux2 - b_bytes) / sp.slab_slot_bytes;
+    if (stages2 > kPairMaxStages) stages2 = kPairMaxStages;
+    const double useful = (double)d->t * sp.w / ((double)row_tiles * r_out * w_chunks * w_tile);
+    // a cluster loads its filter half once (0.1 MB per CTA) and tiles come in whole rounds of the 74 clusters: below ~6 rounds
+    // the generic kernel is as fast or faster (measured at batch 4: 24.0 vs 24.2 us, data gradient 24.9 vs 27.7 us)
+    const long long pair_items = ((long long)sp.frames * sp.tiles_per_frame + 1) / 2 * sp.num_n_tiles;
+    if (!tis_fits && b_bytes + aux2 < kSmemMax && stages2 >= 3 && sp.w >= w_tile && useful >= 0.6 &&
+        (pair_items >= 6ll * (di->sm_count / 2) || g_slab_pair_auto == 2)) {
+      sp.stages = stages2; sp.b_ring = b_all;
+      SlabPairParams pp;
+      memset(&pp, 0, sizeof(pp));
+      pp.s = sp;
+      pp.n_half = bn / 2; pp.n_tiles = sp.num_n_tiles;
+      pp.w_chunks = w_chunks; pp.w_tile = w_tile;
+      pp.num_pairs = (sp.frames * sp.tiles_per_frame + 1) / 2;
+      CUtensorMap tmx, tmw2;
+      const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)sp.w, (cuuint64_t)d->t, (cuuint64_t)d->n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * sp.w, (cuuint64_t)d->cin * 2 * sp.w * d->t};
+      const cuuint32_t box[4] = {64, (cuuint32_t)w_tile, (cuuint32_t)sp.r_in, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(temporal pair x) failed (CUresult %d)", (int)r);
+      if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, pp.n_half, &tmw2)) return e;
+      static bool attr_set_tp[16] = {false};
+      int devp = 0;
+      cudaGetDevice(&devp);
+      if (!attr_set_tp[devp]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_slab_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_pair_kernel): %s", cudaGetErrorString(e));
+        attr_set_tp[devp] = true;
+      }
+      int clusters = di->sm_count / 2;
+      if (pp.num_pairs * pp.n_tiles < clusters) clusters = pp.num_pairs * pp.n_tiles;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * clusters);
+      cfg.blockDim = dim3(kPairThreads);
+      cfg.dynamicSmemBytes = b_bytes + stages2 * sp.slab_slot_bytes + aux2;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, conv_slab_pair_kernel, tmx, tmw2, tmx, pp);
+      if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "conv_slab_pair_kernel(temporal) launch: %s", cudaGetErrorString(le));
+      return check_launch("conv_slab_pair_kernel(temporal)");
     }
   }
 

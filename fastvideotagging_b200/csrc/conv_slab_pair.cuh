@@ -22,6 +22,9 @@
 // data gradient 144 -> 64: 221 KB):
 //   * N tiles: a cluster keeps ONE N tile (n_tile columns) of the filter for its lifetime, cluster c works on N tile
 //     c mod n_tiles and on every (clusters / n_tiles)-th tile pair; the input tile is read once per N tile (L2);
+//   * column chunks: a tile may be r_out rows x w_tile columns of a wide image, which is how the stride-1 kt x 1 x 1
+//     TEMPORAL convs whose filter fits two SMs (conv3_x 288 -> 128 and its data gradient) run here: image rows = frames,
+//     image columns = the H*W positions, 16 frames x 8 positions per tile, zero frames by TMA out-of-bounds fill;
 //   * the input ring is per 64-channel BLOCK, not per tile: the MMAs run channel-block-major, a block slot is released
 //     as soon as its nine taps are issued, so two slots overlap loads and MMAs even when only one tile's slab fits.
 // Both CTAs' slab loads count on the LEADER's barrier (cp.async.bulk.tensor .cta_group::2), so the MMA warp waits once
@@ -47,6 +50,9 @@ struct SlabPairParams {
   int out_tile_bytes;         // r_out * w * cout_store * 2 rounded up to 128
   int tma_store;              // 1: staged TMA store (needs n_tile == cout_store), 0: register stores
   int n_tiles;                // N tiles of n_tile columns; a cluster works on N tile (cluster id mod n_tiles) only
+  int w_chunks, w_tile;       // column chunks per row tile and their width (1, s.w for whole-row tiles).  With chunks
+                              // (kw = 1, pw = 0, s.wp = w_tile) a tile is r_out rows x w_tile columns: a kt x 1 x 1 temporal
+                              // conv runs here as a (kh = kt, kw = 1) conv over the image [H' = T] x [W' = H*W]
 };
 
 namespace pair {
@@ -205,19 +211,22 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int pr = pair0; pr < pp.num_pairs; pr += pair_step) {
       const int mt = 2 * pr + static_cast<int>(rank);
       const int frame = mt / p.tiles_per_frame;
-      const int h0 = (mt - frame * p.tiles_per_frame) * p.r_out;
+      const int rem = mt - frame * p.tiles_per_frame;
+      const int rt = rem / pp.w_chunks;
+      const int h0 = rt * p.r_out, w0 = (rem - rt * pp.w_chunks) * pp.w_tile;
       for (int cb = 0; cb < p.cin_blocks; ++cb) {
         ptx::mbar_wait(ptx::smem_u32(&slab_empty[stage]), phase ^ 1);
         const uint32_t fb = pair::map_to_rank(ptx::smem_u32(&slab_full[stage]), 0);       // the LEADER's barrier counts both blocks
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&slab_full[stage]), 2 * p.slab_tx_bytes);
-          pair::tma_load_4d_2sm(ptx::smem_u32(smem_a + stage * stage_bytes), &tmap_x, fb, cb * 64, -p.pw, h0 - p.ph, frame);
+          pair::tma_load_4d_2sm(ptx::smem_u32(smem_a + stage * stage_bytes), &tmap_x, fb, cb * 64, w0 - p.pw, h0 - p.ph, frame);
           if (p.prefetch_dist > 0) {
             const int mt2 = mt + 2 * p.prefetch_dist * pair_step;
             if (mt2 < num_m_tiles) {
               const int frame2 = mt2 / p.tiles_per_frame;
-              const int h2 = (mt2 - frame2 * p.tiles_per_frame) * p.r_out;
-              tma_prefetch_4d(&tmap_x, cb * 64, -p.pw, h2 - p.ph, frame2);
+              const int rem2 = mt2 - frame2 * p.tiles_per_frame;
+              const int rt2 = rem2 / pp.w_chunks;
+              tma_prefetch_4d(&tmap_x, cb * 64, (rem2 - rt2 * pp.w_chunks) * pp.w_tile - p.pw, rt2 * p.r_out - p.ph, frame2);
             }
           }
         }
@@ -306,36 +315,38 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     ea.residual = p.residual; ea.y = p.y; ea.stat_smem = affine_smem + n0; ea.stat_stride = n_total;
     const int r = q * 32 + lane;                 // GEMM row = padded position inside the tile
     const int hl = r / p.wp, wl = r - hl * p.wp;
-    int shl[4];
+    int shl[4], swl[4];
     uint32_t smask_static = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int rj = q * 32 + (lane >> 2) + 8 * j;
       shl[j] = rj / p.wp;
-      const int swl = rj - shl[j] * p.wp;
-      if (shl[j] < p.r_out && swl < p.w) smask_static |= 1u << j;
+      swl[j] = rj - shl[j] * p.wp;
+      if (shl[j] < p.r_out && swl[j] < pp.w_tile) smask_static |= 1u << j;
     }
     const uint32_t acc_empty_leader0 = pair::map_to_rank(ptx::smem_u32(&acc_empty[0]), 0);
     int obuf = 0;
     for (int pr = pair0; pr < pp.num_pairs; pr += pair_step) {
       const int mt = 2 * pr + static_cast<int>(rank);
       const int frame = mt / p.tiles_per_frame;
-      const int h0 = (mt - frame * p.tiles_per_frame) * p.r_out;
+      const int rem = mt - frame * p.tiles_per_frame;
+      const int rt = rem / pp.w_chunks;
+      const int h0 = rt * p.r_out, w0 = (rem - rt * pp.w_chunks) * pp.w_tile;
       const bool in_range = mt < num_m_tiles;
-      const bool ok = in_range && hl < p.r_out && wl < p.w && (h0 + hl) < p.h;
-      const long long out_row = ok ? (static_cast<long long>(frame) * p.h + h0 + hl) * p.w + wl : -1ll;
+      const bool ok = in_range && hl < p.r_out && wl < pp.w_tile && (h0 + hl) < p.h && (w0 + wl) < p.w;
+      const long long out_row = ok ? (static_cast<long long>(frame) * p.h + h0 + hl) * p.w + w0 + wl : -1ll;
       {
         uint32_t m = in_range ? smask_static : 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (h0 + shl[j] >= p.h) m &= ~(1u << j);
+          if (h0 + shl[j] >= p.h || w0 + swl[j] >= p.w) m &= ~(1u << j);
         ea.stat_mask = m;
       }
       if (pp.tma_store) {
         if (et == 0) ptx::tma_store_wait_read<1>();      // the store that read this staging buffer two tiles ago is done
         asm volatile("bar.sync 1, 256;" ::: "memory");
         ea.stage_smem = ptx::smem_u32(smem_o + obuf * pp.out_tile_bytes);
-        ea.stage_row = (hl < p.r_out && wl < p.w) ? hl * p.w + wl : -1;
+        ea.stage_row = (hl < p.r_out && wl < p.w) ? hl * p.w + wl : -1;       // staged store: whole-row tiles only (w_chunks == 1)
         ea.stage_pitch = p.cout_store * 2;
         ea.stage_swizzle = 0;
       }

@@ -469,3 +469,53 @@ def test_cta_pair_auto_matches_streamed_single_cta(cuda_device, lib, shape):
     ref = out[0][3]
     assert (out[1][3] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
     assert out[0][0].float().abs().max().item() > 0
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 28, 28, 288, 128),      # conv3_x 3x1x1: 4.5 channel blocks, whole clip per tile
+                                   (2, 16, 28, 28, 128, 288),      # its data gradient: two N tiles
+                                   (3, 8, 14, 14, 288, 128),       # 8 frames x 16 positions per tile, ragged last column chunk
+                                   (2, 5, 7, 9, 288, 128),         # 4 frames x 32 positions, clipped frame tile and column chunk
+                                   (1, 32, 28, 28, 288, 128),      # two frame tiles per clip: temporal halo crosses tiles
+                                   (30, 16, 28, 28, 288, 128)])    # more tile pairs than clusters
+def test_cta_pair_temporal_matches_im2col(cuda_device, lib, shape):
+    """Stride-1 3x1x1 convs whose filter fits two SMs but not one run on the CTA-pair slab kernel (frames as image rows, H*W
+    positions as image columns).  Same convolution as the generic im2col kernel K1: results equal up to fp32 summation
+    order (<= 1 bf16 ulp): plain, affine + residual + ReLU, and BatchNorm statistics."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w, cin, cout = shape
+    gen = torch.Generator().manual_seed(n * 100 + t + cin)
+    x = (torch.randn(n, t, h, w, cin, generator=gen) * 0.5).to(torch.bfloat16).to(cuda_device)
+    wt = (torch.randn(cout, cin, 3, 1, 1, generator=gen) / (cin * 3) ** 0.5).to(cuda_device)
+    res = torch.randn(n, t, h, w, cout, generator=gen).to(torch.bfloat16).to(cuda_device)
+    sc = (0.5 + torch.rand(cout, generator=gen)).to(cuda_device)
+    sh = torch.randn(cout, generator=gen).to(cuda_device)
+    k, p = (3, 1, 1), (1, 0, 0)
+    d_plain = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, 0)
+    d_full = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+    d_stat = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, ops.FVT_CONV_STATS)
+    wp = ops.pack_conv_weight(d_plain, wt)
+
+    def run_all():
+        a = ops.conv3d_fwd(d_plain, x, wp).clone()
+        b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
+        st = torch.zeros(2 * cout, device=cuda_device)
+        c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
+        torch.cuda.synchronize()
+        return a, b, c, st.clone()
+
+    out = {}
+    try:
+        for mode in (0, 2):                      # 2: the pair kernel even below the problem size where it pays off
+            assert lib.fvt_set_option(b"slab_pair_auto", mode) == 0
+            out[mode] = run_all()
+    finally:
+        lib.fvt_set_option(b"slab_pair_auto", 1)
+    for i in range(3):
+        a, b = out[2][i].float(), out[0][i].float()
+        assert torch.isfinite(a).all()
+        tol = 2 ** -7 * b.abs() + 2 ** -7 * 1e-2 * b.abs().max()
+        assert ((a - b).abs() <= tol).all(), (i, (a - b).abs().max().item(), b.abs().max().item())
+    ref = out[0][3]
+    assert (out[2][3] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+    assert out[0][0].float().abs().max().item() > 0

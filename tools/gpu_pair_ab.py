@@ -11,6 +11,10 @@ CASES = [
     ("conv3 spatial 128->288 b4 stats", 4, 16, 28, 28, 128, 288, 1),
     ("conv2 dgrad 144->64 b4", 4, 32, 56, 56, 144, 64, 0),
     ("conv2 dgrad 144->64 b16 T16", 16, 16, 56, 56, 144, 64, 0),
+    ("conv3 temporal 288->128 b48", 48, 16, 28, 28, 288, 128, 0, (3, 1, 1), (1, 0, 0)),
+    ("conv3 temporal 288->128 b4 stats", 4, 16, 28, 28, 288, 128, 1, (3, 1, 1), (1, 0, 0)),
+    ("conv3 t-dgrad 128->288 b4", 4, 16, 28, 28, 128, 288, 0, (3, 1, 1), (1, 0, 0)),
+    ("conv3 temporal 288->128 b16 T8", 16, 8, 28, 28, 288, 128, 0, (3, 1, 1), (1, 0, 0)),
 ]
 
 
@@ -23,15 +27,18 @@ def timeit(fn, reps=5):
     return a.elapsed_time(b) / reps * 1e3
 
 
-for name, n, t, h, w, cin, cout, stats in CASES:
+for case in CASES:
+    name, n, t, h, w, cin, cout, stats = case[:8]
+    kern, pad = (case[8], case[9]) if len(case) > 8 else ((1, 3, 3), (0, 1, 1))
     x = (torch.randn(n, t, h, w, cin, device=dev) * 0.5).to(torch.bfloat16)
-    wt = torch.randn(cout, cin, 1, 3, 3, device=dev) / (cin * 9) ** 0.5
+    taps = kern[0] * kern[1] * kern[2]
+    wt = torch.randn(cout, cin, *kern, device=dev) / (cin * taps) ** 0.5
     sc, sh = 0.5 + torch.rand(cout, device=dev), torch.randn(cout, device=dev)
-    d = ops.conv_desc(n, t, h, w, cin, cout, (1, 3, 3), (1, 1, 1), (0, 1, 1), ops.FVT_CONV_STATS if stats else ops.FVT_CONV_RELU)
+    d = ops.conv_desc(n, t, h, w, cin, cout, kern, (1, 1, 1), pad, ops.FVT_CONV_STATS if stats else ops.FVT_CONV_RELU)
     wp = ops.pack_conv_weight(d, wt)
     y = torch.empty(n, t, h, w, cout, device=dev, dtype=torch.bfloat16)
     st = torch.zeros(2 * cout, device=dev)
-    gflop = 2.0 * n * t * h * w * cout * cin * 9 / 1e9
+    gflop = 2.0 * n * t * h * w * cout * cin * taps / 1e9
     line = "%-34s" % name
     for mode in (0, 1):
         lib.fvt_set_option(b"slab_pair_auto", mode)
