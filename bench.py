@@ -373,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
         # dominant kernel: unit2p1_fused_kernel — the six conv2_x (2+1)D units (64 -> 144 -> 64), one launch each, the
         # largest single share of the step.  achieved = algorithmic 2*M*N*K of both convolutions of one launch / its mean
         # CUDA-event duration.  (FVT_FUSED_UNIT=0: the unfused conv_slab_fwd_kernel launches of the same layers.)
-        dom = [r for r in rows if "+" in r[0]]
+        dom = [r for r in rows if "+" in r[0] and r[0].startswith("comp_")]
         dom_kernel = "unit2p1_fused_kernel, conv2_x unit 1x3x3 64->144 + 3x1x1 144->64"
         # DRAM bytes per launch from `ncu --set full` at batch 48 (profiles/): scaled to this batch
         traffic = FUSED_UNIT_DRAM_BYTES_B48 * batch / 48.0 if FUSED_UNIT_DRAM_BYTES_B48 else None

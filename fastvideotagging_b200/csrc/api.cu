@@ -1067,12 +1067,13 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
 static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt_conv_desc* dt, UnitFusedParams* up, int* smem_bytes, int* use_is) {
   if (int e = validate_conv(ds)) return e;
   if (int e = validate_conv(dt)) return e;
-  const bool spatial_ok = ds->kt == 1 && ds->kh == 3 && ds->kw == 3 && ds->st == 1 && ds->sh == 1 && ds->sw == 1 &&
-                          ds->pt == 0 && ds->ph == 1 && ds->pw == 1 && ds->cin == 64;
+  const bool spatial_ok = ds->kt == 1 && (ds->kh & 1) && (ds->kw & 1) && ds->kh * ds->kw > 1 && ds->kh <= 7 && ds->kw <= 7 &&
+                          ds->st == 1 && ds->sh == 1 && ds->sw == 1 && ds->pt == 0 && 2 * ds->ph == ds->kh - 1 &&
+                          2 * ds->pw == ds->kw - 1 && ds->cin == 64;
   const bool temporal_ok = dt->kt == 3 && dt->kh == 1 && dt->kw == 1 && dt->st == 1 && dt->sh == 1 && dt->sw == 1 &&
                            dt->pt == 1 && dt->ph == 0 && dt->pw == 0 && dt->cin == ds->cout && dt->cout == 64;
   if (!spatial_ok || !temporal_ok)
-    return set_error(FVT_ERR_BAD_DESC, "fused unit needs a stride-1 1x3x3 conv (64 -> mid, pad 0,1,1) followed by a stride-1 3x1x1 conv (mid -> 64, pad 1,0,0)");
+    return set_error(FVT_ERR_BAD_DESC, "fused unit needs a stride-1 'same' 1 x kh x kw conv (64 -> mid) followed by a stride-1 3x1x1 conv (mid -> 64, pad 1,0,0)");
   if (ds->n != dt->n || ds->t != dt->t || ds->h != dt->h || ds->w != dt->w)
     return set_error(FVT_ERR_BAD_DESC, "fused unit: the two convolutions must share N, T, H, W");
   const int n_mid = ds->cout;
@@ -1081,18 +1082,19 @@ static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt
   if (di->sm_count % 2) return set_error(FVT_ERR_BAD_DESC, "fused unit needs an even SM count (CTA pairs)");
   UnitFusedParams u;
   memset(&u, 0, sizeof(u));
-  u.clips = ds->n; u.t = ds->t; u.h = ds->h; u.w = ds->w; u.wp = ds->w + 2;
-  if (u.wp > 128) return set_error(FVT_ERR_BAD_DESC, "fused unit: W + 2 = %d exceeds one 128-row tile", u.wp);
+  u.clips = ds->n; u.t = ds->t; u.h = ds->h; u.w = ds->w; u.wp = ds->w + 2 * ds->pw;
+  u.kh = ds->kh; u.kw = ds->kw; u.ph = ds->ph; u.pw = ds->pw;
+  if (u.wp > 128) return set_error(FVT_ERR_BAD_DESC, "fused unit: padded row of %d positions exceeds one 128-row tile", u.wp);
   u.r_out = 128 / u.wp;
   if (u.r_out > ds->h) u.r_out = ds->h;
-  u.r_in = u.r_out + 2;
+  u.r_in = u.r_out + ds->kh - 1;
   u.tiles_per_frame = (ds->h + u.r_out - 1) / u.r_out;
   u.pairs_per_frame = (u.tiles_per_frame + 1) / 2;
   u.num_units = u.clips * u.pairs_per_frame;
   u.total_steps = (long long)u.num_units * u.t;
   const double useful = (double)ds->h * ds->w / ((double)2 * u.pairs_per_frame * 128.0);
   if (useful < 0.5) return set_error(FVT_ERR_BAD_DESC, "fused unit: %dx%d frames fill only %.0f %% of the tiles", ds->h, ds->w, 100 * useful);
-  const int slot_rows = (128 + 2 * u.wp + 2 + 7) / 8 * 8;
+  const int slot_rows = (128 + (ds->kh - 1) * u.wp + ds->kw - 1 + 7) / 8 * 8;
   if (u.r_in * u.wp > slot_rows) return set_error(FVT_ERR_BAD_DESC, "fused unit: slab does not fit its slot");
   u.slab_slot_bytes = (slot_rows * 128 + 1023) / 1024 * 1024;
   u.slab_tx_bytes = u.wp * u.r_in * 128;
@@ -1100,8 +1102,11 @@ static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt
   u.mid_blocks = (n_mid + 63) / 64; u.mid_k16 = n_mid / 16;
   // input-stationary form: temporal filter as five 32-row blocks per K block (every tap rotation is a contiguous window)
   *use_is = g_unit_is && n_mid % 48 == 0;
+  const int s_taps = ds->kh * ds->kw;
+  if (!*use_is && s_taps != 9) return set_error(FVT_ERR_BAD_DESC, "fused unit: only the input-stationary form (mid a multiple of 48) handles filters other than 3x3");
   const int bt_bytes = *use_is ? u.mid_blocks * 5 * 32 * 128 : (3 * u.mid_blocks * 32 * 128 + 1023) / 1024 * 1024;
-  const int b_bytes = 9 * (n_mid / 2) * 128 + bt_bytes;
+  const int b_bytes = (s_taps * (n_mid / 2) * 128 + 1023) / 1024 * 1024 + bt_bytes;
+  if ((s_taps * (n_mid / 2) * 128) % 1024) return set_error(FVT_ERR_BAD_DESC, "fused unit: spatial filter half is not a whole number of swizzle atoms");
   const int aux = (512 + (2 * n_mid + 2 * 64) * 4 + 255) / 256 * 256;
   const int kSmemMax = 227 * 1024;
   u.stages = (kSmemMax - aux - b_bytes) / u.slab_slot_bytes;
@@ -1154,7 +1159,7 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(fused unit x) failed (CUresult %d)", (int)r);
-  if (int e = encode_w_map(di, w_spatial_packed, 9 * 64, u.n_mid, u.n_mid / 2, &tmws)) return e;
+  if (int e = encode_w_map(di, w_spatial_packed, u.kh * u.kw * 64, u.n_mid, u.n_mid / 2, &tmws)) return e;
   if (int e = encode_w_map(di, w_temporal_packed, 3 * u.n_mid, 64, 32, &tmwt)) return e;
 
   static bool attr_set_u[16] = {false};

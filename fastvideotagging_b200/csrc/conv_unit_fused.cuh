@@ -40,7 +40,8 @@ constexpr int kUnitPSlots = 4;             // converted mid frames resident in T
 
 struct UnitFusedParams {
   int clips, t;              // clips, frames per clip
-  int h, w, wp;              // image extent, padded row pitch W + 2
+  int h, w, wp;              // image extent, padded row pitch W + 2 pw
+  int kh, kw, ph, pw;        // spatial filter extent and its 'same' padding (the output-stationary kernel handles 3 x 3 only)
   int r_out, r_in;           // output rows per tile, slab rows loaded per tile
   int tiles_per_frame;       // row tiles per frame
   int pairs_per_frame;       // ceil(tiles_per_frame / 2): tile 2*pair + rank belongs to CTA `rank`

@@ -49,7 +49,8 @@ unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   const uint32_t rank = pair::ctarank();
   const bool leader = rank == 0;
 
-  constexpr int kTaps = 9, kBtBlocks = 5, kBtBlockBytes = 32 * 128;
+  constexpr int kBtBlocks = 5, kBtBlockBytes = 32 * 128;
+  const int kTaps = p.kh * p.kw;
   const int n_mid_half = p.n_mid >> 1;
   const int bs_slab = n_mid_half * 128;                                // one spatial tap, this CTA's filter rows
   const int bt_cb_bytes = kBtBlocks * kBtBlockBytes;                    // one 64-channel K block: [W2 W1 W0 W2 W1] x 32 rows
@@ -125,8 +126,8 @@ unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         const uint32_t fb = pair::map_to_rank(ptx::smem_u32(&slab_full[stage]), 0);      // the LEADER's barrier counts both slabs
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&slab_full[stage]), 2 * p.slab_tx_bytes);
-          tma_load_4d_pair(ptx::smem_u32(smem_a + stage * p.slab_slot_bytes), &tmap_x, fb, 0, -1, h0 - 1, clip * p.t + t);
-          if (t + p.stages < fs1) tma_prefetch_4d(&tmap_x, 0, -1, h0 - 1, clip * p.t + t + p.stages);     // warm L2 for the load after next
+          tma_load_4d_pair(ptx::smem_u32(smem_a + stage * p.slab_slot_bytes), &tmap_x, fb, 0, -p.pw, h0 - p.ph, clip * p.t + t);
+          if (t + p.stages < fs1) tma_prefetch_4d(&tmap_x, 0, -p.pw, h0 - p.ph, clip * p.t + t + p.stages);     // warm L2 for the load after next
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -190,10 +191,9 @@ unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             uint32_t acc_flag = 0;
             uint64_t b_desc = bs_desc0;
             uint64_t a_row = a_desc0;
-            for (int dh = 0; dh < 3; ++dh, a_row += a_row_step) {
+            for (int dh = 0; dh < p.kh; ++dh, a_row += a_row_step) {
               uint64_t a_tap = a_row;
-#pragma unroll
-              for (int dw = 0; dw < 3; ++dw, a_tap += 8, b_desc += bs_step) {
+              for (int dw = 0; dw < p.kw; ++dw, a_tap += 8, b_desc += bs_step) {
                 pair::umma2_bf16_ss(tmem_base, a_tap, b_desc, idesc_s, acc_flag);
                 acc_flag = 1;
                 pair::umma2_bf16_ss(tmem_base, a_tap + 2, b_desc + 2, idesc_s, 1);

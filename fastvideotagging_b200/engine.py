@@ -244,12 +244,13 @@ class InferencePlan:
             raise ValueError("AvgPool3D%s over a %s map leaves %s: only a global pool (1x1x1 output) is supported; "
                              "pass final_temporal_kernel = T/8 and final_spatial_kernel = H/16 as the reference callers do"
                              % (pool, shp[1:4], (tp, hp, wp)))
-        # ---- K2f: a stride-1 64 -> mid -> 64 unit (conv2_x) runs as ONE launch with `mid` kept in tensor memory
+        # ---- K2f: a stride-1 64 -> mid -> 64 unit (conv2_x, and the row-paired stem: (1,5,1) conv 64 -> 48 + 3x1x1 48 -> 64)
+        #      runs as ONE launch with `mid` kept in tensor memory
         self.fused = {}
         if os.environ.get("FVT_FUSED_UNIT", "1") != "0":
             for i in range(len(self.layers) - 1):
                 a, b = self.layers[i], self.layers[i + 1]
-                if (a.spec.role == "spatial" and b.spec.role in ("temporal", "temporal_out") and b.src == a.dst
+                if (a.spec.role in ("spatial", "stem_spatial") and b.spec.role in ("temporal", "temporal_out", "stem_temporal") and b.src == a.dst
                         and a.res is None and (i - 1) not in self.fused and ops.unit2p1_supported(a.desc, b.desc)):
                     self.fused[i] = b
         self.launches = 1 + len(self.layers) - len(self.fused) + 1

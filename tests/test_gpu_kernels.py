@@ -344,19 +344,19 @@ def test_cta_pair_slab_kernel_matches_single_cta(cuda_device, lib, shape):
     assert out[0][0].float().abs().max().item() > 0
 
 
-def _unit_case(device, n, t, h, w, mid, seed, residual):
+def _unit_case(device, n, t, h, w, mid, seed, residual, kernel=(1, 3, 3)):
     import torch
     from fastvideotagging_b200 import ops
     gen = torch.Generator().manual_seed(seed)
     x = (torch.randn(n, t, h, w, 64, generator=gen) * 0.5).to(torch.bfloat16).to(device)
-    w_s = (torch.randn(mid, 64, 1, 3, 3, generator=gen) / 24.0).to(device)
+    w_s = (torch.randn(mid, 64, *kernel, generator=gen) / (64 * kernel[1] * kernel[2]) ** 0.5).to(device)
     w_t = (torch.randn(64, mid, 3, 1, 1, generator=gen) / (3 * mid) ** 0.5).to(device)
     sc_m = (0.5 + torch.rand(mid, generator=gen)).to(device)
     sh_m = (0.3 * torch.randn(mid, generator=gen)).to(device)
     sc_o = (0.5 + torch.rand(64, generator=gen)).to(device)
     sh_o = (0.3 * torch.randn(64, generator=gen)).to(device)
     res = torch.randn(n, t, h, w, 64, generator=gen).to(torch.bfloat16).to(device) if residual else None
-    d_s = ops.conv_desc(n, t, h, w, 64, mid, (1, 3, 3), (1, 1, 1), (0, 1, 1), ops.FVT_CONV_RELU)
+    d_s = ops.conv_desc(n, t, h, w, 64, mid, kernel, (1, 1, 1), (0, kernel[1] // 2, kernel[2] // 2), ops.FVT_CONV_RELU)
     d_t = ops.conv_desc(n, t, h, w, mid, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0),
                         ops.FVT_CONV_RELU | (ops.FVT_CONV_RESIDUAL if residual else 0))
     wp_s, wp_t = ops.pack_conv_weight(d_s, w_s), ops.pack_conv_weight(d_t, w_t)
@@ -369,7 +369,9 @@ def _unit_case(device, n, t, h, w, mid, seed, residual):
                                    (3, 2, 28, 28, 144, True),      # 7 row tiles per frame: the last pair has a dummy tile
                                    (2, 3, 14, 14, 144, True),      # second tile clipped at the bottom edge
                                    (1, 5, 56, 56, 96, True),       # another mid width (two 64-channel blocks, 6 K steps)
-                                   (20, 3, 56, 56, 144, True)])    # more units than CTA pairs: several clips per cluster
+                                   (20, 3, 56, 56, 144, True),     # more units than CTA pairs: several clips per cluster
+                                   (2, 5, 56, 56, 48, False, (1, 5, 1)),     # the row-paired stem: (1,5,1) conv 64 -> 48, then 48 -> 64
+                                   (1, 4, 28, 28, 48, True, (1, 1, 3))])     # another filter shape
 @pytest.mark.parametrize("input_stationary", [1, 0])
 def test_fused_unit_matches_two_launches(cuda_device, lib, shape, input_stationary):
     """K2f (one launch, mid in tensor memory, cta_group::2, A operand from TMEM) == spatial conv launch + temporal conv
@@ -380,8 +382,11 @@ def test_fused_unit_matches_two_launches(cuda_device, lib, shape, input_stationa
     import torch
     import torch.nn.functional as F
     from fastvideotagging_b200 import ops
-    n, t, h, w, mid, residual = shape
-    x, w_s, w_t, sc_m, sh_m, sc_o, sh_o, res, d_s, d_t, wp_s, wp_t = _unit_case(cuda_device, n, t, h, w, mid, n * 10 + t, residual)
+    n, t, h, w, mid, residual = shape[:6]
+    kernel = shape[6] if len(shape) > 6 else (1, 3, 3)
+    if kernel != (1, 3, 3) and not input_stationary:
+        pytest.skip("the output-stationary form handles 3x3 filters only")
+    x, w_s, w_t, sc_m, sh_m, sc_o, sh_o, res, d_s, d_t, wp_s, wp_t = _unit_case(cuda_device, n, t, h, w, mid, n * 10 + t, residual, kernel)
     assert ops.unit2p1_supported(d_s, d_t)
     y_mid = ops.conv3d_fwd(d_s, x, wp_s, sc_m, sh_m)
     y_two = ops.conv3d_fwd(d_t, y_mid, wp_t, sc_o, sh_o, res)
@@ -399,7 +404,7 @@ def test_fused_unit_matches_two_launches(cuda_device, lib, shape, input_stationa
     assert (a != b).float().mean().item() < 0.02
     # torch fp32 evaluation from the same bf16 inputs / bf16-rounded weights, mid rounded to bf16 as both paths store it
     xf = x.float().permute(0, 4, 1, 2, 3)
-    m = F.conv3d(xf, w_s.to(torch.bfloat16).float(), padding=(0, 1, 1))
+    m = F.conv3d(xf, w_s.to(torch.bfloat16).float(), padding=(0, kernel[1] // 2, kernel[2] // 2))
     m = torch.relu(m * sc_m.view(1, -1, 1, 1, 1) + sh_m.view(1, -1, 1, 1, 1)).to(torch.bfloat16).float()
     o = F.conv3d(m, w_t.to(torch.bfloat16).float(), padding=(1, 0, 0)) * sc_o.view(1, -1, 1, 1, 1) + sh_o.view(1, -1, 1, 1, 1)
     if res is not None:
