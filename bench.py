@@ -22,7 +22,7 @@ GFLOP_PER_CLIP_FWD = 304.711020544      # 2*M*N*K over unpadded conv dims, R34 3
 GFLOP_PER_CLIP_TRAIN = 912.8            # fwd + dgrad + wgrad, minus the stem dgrad
 TRAIN_BATCH_PER_GPU = 4                 # BASELINE configs[2]
 # dram__bytes_read.sum + dram__bytes_write.sum of one unit2p1_fused_kernel launch at batch 48 (ncu --set full); None until captured
-FUSED_UNIT_DRAM_BYTES_B48 = 1.495e9   # profiles/r01z_ncu_unit2p1_fused_os.txt: 909 MB read + 586 MB written (algorithmic 617 + 617 MB: halo rows re-read)
+FUSED_UNIT_DRAM_BYTES_B48 = 1.521e9   # profiles/r01z_ncu_unit2p1_fused_is.txt: 923 MB read + 598 MB written (algorithmic 617 + 617 MB: halo rows re-read)
 MODEL_DEPTH, NUM_CLASS, T, HW = 34, 101, 32, 112
 BATCH_PER_GPU = 48
 C4_BATCH_PER_GPU, C4_T, C4_NUM_CLASS = 16, 16, 63     # BASELINE configs[3] (Meitu shape, train_simple_r3d.py:336,341)
