@@ -63,7 +63,10 @@ int fvt_device_check(int device);
 /* Tuning/debug switches (A/B runs and tests): "disable_slab" = 1 routes every convolution through the generic im2col
  * kernel (K1); "disable_frame_ring" / "disable_temporal_is" = 1 do the same for the temporal kernels (K1t / K1i) only; "disable_b_stationary" = 1 makes K1
  * stream its weights; "disable_wgrad_slab" = 1 routes every weight gradient through the im2col kernel (K3);
- * "disable_split_k" = 1 keeps small-M convolutions single-pass; "slab_prefetch" / "slab_box_rows" / "debug_flags" are load-path and epilogue experiments (tools/gpu_*_ab.py). */
+ * "disable_split_k" = 1 keeps small-M convolutions single-pass; "slab_prefetch" / "slab_box_rows" / "debug_flags" are load-path and epilogue experiments (tools/gpu_*_ab.py);
+ * "slab_pair_auto" = 0 keeps the layers whose filter fits two SMs but not one off the CTA-pair kernel (2: pair even for small problems),
+ * "slab_pair" = 1|2 forces the pair kernel for single-SM-stationary layers (1: staged TMA store), "unit_input_stationary" = 0 selects the
+ * output-stationary form of the fused (2+1)D unit. */
 int fvt_set_option(const char* name, int value);
 
 /* ---- convolution (K1) ----------------------------------------------------------------------------------- */

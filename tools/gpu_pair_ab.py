@@ -51,3 +51,28 @@ for case in CASES:
             lib.fvt_set_option(b"debug_flags", 0)
     lib.fvt_set_option(b"slab_pair_auto", 1)
     print(line, flush=True)
+
+# ---- layers whose filter is stationary on ONE SM (conv2_x 1x3x3 64 -> 144, the row-paired stem): single CTA vs forced pair
+print("== forced pair (fvt_set_option slab_pair) on single-SM-stationary layers")
+for name, n, t, cin, cout, kern, pad in (("conv2 spatial 64->144 b48", 48, 32, 64, 144, (1, 3, 3), (0, 1, 1)),
+                                         ("conv2 spatial 64->144 b4", 4, 32, 64, 144, (1, 3, 3), (0, 1, 1)),
+                                         ("conv2 spatial 64->144 b16 T16", 16, 16, 64, 144, (1, 3, 3), (0, 1, 1)),
+                                         ("conv2 dgrad(t) 64->144... stem 64->48 b4", 4, 32, 64, 48, (1, 5, 1), (0, 2, 0))):
+    h = w = 56
+    x = (torch.randn(n, t, h, w, cin, device=dev) * 0.5).to(torch.bfloat16)
+    taps = kern[1] * kern[2]
+    wt = torch.randn(cout, cin, *kern, device=dev) / (cin * taps) ** 0.5
+    sc, sh = 0.5 + torch.rand(cout, device=dev), torch.randn(cout, device=dev)
+    d_inf = ops.conv_desc(n, t, h, w, cin, cout, kern, (1, 1, 1), pad, ops.FVT_CONV_RELU)
+    d_trn = ops.conv_desc(n, t, h, w, cin, cout, kern, (1, 1, 1), pad, ops.FVT_CONV_STATS)
+    wp = ops.pack_conv_weight(d_inf, wt)
+    y = torch.empty(n, t, h, w, cout, device=dev, dtype=torch.bfloat16)
+    st = torch.zeros(2 * cout, device=dev)
+    line = "%-40s" % name
+    for mode in (0, 2, 1):
+        lib.fvt_set_option(b"slab_pair", mode)
+        a = timeit(lambda: ops.conv3d_fwd(d_inf, x, wp, sc, sh, out=y))
+        b = timeit(lambda: ops.conv3d_fwd(d_trn, x, wp, out=y, stats=st))
+        line += " | pair=%d inference %7.1f train(stats) %7.1f" % (mode, a, b)
+    lib.fvt_set_option(b"slab_pair", 0)
+    print(line, flush=True)
