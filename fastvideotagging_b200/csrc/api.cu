@@ -13,6 +13,7 @@
 #include "conv_wgrad.cuh"
 #include "conv_slab.cuh"
 #include "conv_slab_pair.cuh"
+#include "conv_igemm_pair.cuh"
 #include "conv_unit_fused.cuh"
 #include "conv_unit_fused_is.cuh"
 #include "conv_wgrad_slab.cuh"
@@ -74,6 +75,7 @@ static int g_wgrad_atomic_rate = 0;    // fvt_set_option("wgrad_atomic_rate", r)
 static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
 static int g_unit_is = 1;        // fvt_set_option("unit_input_stationary", 0|1): fused (2+1)D unit with the temporal conv as one N = 192 MMA chain
                                  // per mid frame (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame (conv_unit_fused.cuh)
+static int g_igemm_pair = 1;     // fvt_set_option("igemm_pair", 0|1): generic im2col convolution on CTA pairs (K1p) for the wide streamed-weight layers
 static int g_slab_pair_auto = 1; // fvt_set_option("slab_pair_auto", 0|1|2): CTA-pair slab kernel when the filter fits two SMs but not one (2: also for small problems)
 static int g_slab_pair = 0;      // fvt_set_option("slab_pair", 0|1|2): CTA-pair slab kernel (cta_group::2) for stationary-filter layers;
                                  // 2 = pair kernel with register stores instead of the staged TMA store (A/B runs)
@@ -495,6 +497,7 @@ int fvt_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_pair") == 0) { g_slab_pair = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_pair_auto") == 0) { g_slab_pair_auto = value; return 0; }
+  if (name != nullptr && strcmp(name, "igemm_pair") == 0) { g_igemm_pair = value; return 0; }
   if (name != nullptr && strcmp(name, "unit_input_stationary") == 0) { g_unit_is = value; return 0; }
   if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
   if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
@@ -1040,6 +1043,46 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
 
   CUtensorMap tmx, tmw;
   if (int e = encode_x_map(di, d, x, &tmx)) return e;
+
+  // ---- K1p: streamed-weight layers with at least a few rounds of tile pairs run on CTA pairs (cta_group::2, M = 256):
+  //      each CTA loads its own im2col tile and HALF of the weight tile, which takes 30-40 % off the per-SM smem fill
+  {
+    const int n_half = bn / 2;
+    const int stage2 = kATileBytes + (n_half * kBlockK * 2 + 1023) / 1024 * 1024;
+    int stages2 = budget / stage2;
+    if (stages2 > kMaxStages) stages2 = kMaxStages;
+    const long long items = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const bool stats_with_affine = (d->flags & FVT_CONV_STATS) && scale != nullptr;
+    if (g_igemm_pair && !p.b_stationary && p.k_splits == 1 && bn >= 128 && di->sm_count % 2 == 0 && stages2 >= 3 &&
+        !stats_with_affine && (items >= 3ll * (di->sm_count / 2) || g_igemm_pair == 2)) {
+      ConvKernelParams pp = p;
+      pp.stages = stages2;
+      if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, n_half, &tmw)) return e;
+      static bool attr_set_ip[16] = {false};
+      int devp = 0;
+      cudaGetDevice(&devp);
+      if (!attr_set_ip[devp]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_pair_kernel): %s", cudaGetErrorString(e));
+        attr_set_ip[devp] = true;
+      }
+      int clusters = di->sm_count / 2;
+      if (items < clusters) clusters = (int)items;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * clusters);
+      cfg.blockDim = dim3(kConvThreads);
+      cfg.dynamicSmemBytes = stages2 * stage2 + kAuxBytes;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel, tmx, tmw, pp);
+      if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "conv_igemm_pair_kernel launch: %s", cudaGetErrorString(le));
+      return check_launch("conv_igemm_pair_kernel");
+    }
+  }
   if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
 
   static bool attr_set[16] = {false};

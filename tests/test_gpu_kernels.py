@@ -524,3 +524,51 @@ def test_cta_pair_temporal_matches_im2col(cuda_device, lib, shape):
     ref = out[0][3]
     assert (out[2][3] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
     assert out[0][0].float().abs().max().item() > 0
+
+
+@pytest.mark.parametrize("shape", [(4, 8, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1)),      # conv4_x 1x3x3: three N tiles
+                                   (4, 8, 14, 14, 576, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # conv4_x 3x1x1
+                                   (3, 4, 7, 7, 512, 1152, (1, 3, 3), (1, 1, 1), (0, 1, 1)),       # conv5_x: 5 tiles (odd: dummy tile), ragged rows
+                                   (2, 8, 28, 28, 128, 464, (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # strided first conv of conv4_x
+                                   (2, 8, 14, 14, 464, 256, (3, 1, 1), (2, 1, 1), (1, 0, 0)),      # strided temporal conv
+                                   (24, 8, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1))])    # more items than clusters
+def test_cta_pair_im2col_matches_single_cta(cuda_device, lib, shape):
+    """K1p (generic im2col convolution on CTA pairs, cta_group::2, half of the weight tile per CTA) == K1 on one CTA:
+    same MMAs in the same order -> bit-identical outputs (plain, affine + residual + ReLU), statistics up to atomics order."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w, cin, cout, k, s, p = shape
+    gen = torch.Generator().manual_seed(n * 100 + h + cin)
+    x = (torch.randn(n, t, h, w, cin, generator=gen) * 0.5).to(torch.bfloat16).to(cuda_device)
+    wt = (torch.randn(cout, cin, *k, generator=gen) / (cin * k[0] * k[1] * k[2]) ** 0.5).to(cuda_device)
+    d_plain = ops.conv_desc(n, t, h, w, cin, cout, k, s, p, 0)
+    to, ho, wo = ops.conv_out_shape(d_plain)
+    res = torch.randn(n, to, ho, wo, cout, generator=gen).to(torch.bfloat16).to(cuda_device)
+    sc = (0.5 + torch.rand(cout, generator=gen)).to(cuda_device)
+    sh = torch.randn(cout, generator=gen).to(cuda_device)
+    d_full = ops.conv_desc(n, t, h, w, cin, cout, k, s, p, ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+    d_stat = ops.conv_desc(n, t, h, w, cin, cout, k, s, p, ops.FVT_CONV_STATS)
+    wp = ops.pack_conv_weight(d_plain, wt)
+
+    def run_all():
+        a = ops.conv3d_fwd(d_plain, x, wp).clone()
+        b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
+        st = torch.zeros(2 * cout, device=cuda_device)
+        c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
+        torch.cuda.synchronize()
+        return a, b, c, st.clone()
+
+    out = {}
+    try:
+        assert lib.fvt_set_option(b"disable_split_k", 1) == 0          # same single-pass reduction on both sides
+        for mode in (0, 2):                                              # 2: the pair kernel whatever the problem size
+            assert lib.fvt_set_option(b"igemm_pair", mode) == 0
+            out[mode] = run_all()
+    finally:
+        lib.fvt_set_option(b"igemm_pair", 1)
+        lib.fvt_set_option(b"disable_split_k", 0)
+    for i in range(3):
+        assert torch.equal(out[0][i], out[2][i]), i
+    ref = out[0][3]
+    assert (out[2][3] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-3
+    assert out[0][0].float().abs().max().item() > 0

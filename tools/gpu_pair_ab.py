@@ -52,6 +52,32 @@ for case in CASES:
     lib.fvt_set_option(b"slab_pair_auto", 1)
     print(line, flush=True)
 
+# ---- K1p: generic im2col convolution on CTA pairs (wide streamed-weight layers)
+print("== K1p (fvt_set_option igemm_pair) on the conv4_x / conv5_x layers")
+for name, n, t, hh, cin, cout, kern, strd, pad in (("conv4 spatial 256->576 b48", 48, 8, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+                                                  ("conv4 temporal 576->256 b48", 48, 8, 14, 576, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+                                                  ("conv5 spatial 512->1152 b48", 48, 4, 7, 512, 1152, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+                                                  ("conv5 temporal 1152->512 b48", 48, 4, 7, 1152, 512, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+                                                  ("conv4 first spatial 128->464 s2 b48", 48, 16, 28, 128, 464, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+                                                  ("conv3 first temporal 240->128 s2 b48", 48, 32, 28, 240, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+                                                  ("conv4 spatial 256->576 b16 T16", 16, 4, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1))):
+    x = (torch.randn(n, t, hh, hh, cin, device=dev) * 0.5).to(torch.bfloat16)
+    taps = kern[0] * kern[1] * kern[2]
+    wt = torch.randn(cout, cin, *kern, device=dev) / (cin * taps) ** 0.5
+    sc, sh = 0.5 + torch.rand(cout, device=dev), torch.randn(cout, device=dev)
+    d = ops.conv_desc(n, t, hh, hh, cin, cout, kern, strd, pad, ops.FVT_CONV_RELU)
+    to, ho, wo = ops.conv_out_shape(d)
+    wp = ops.pack_conv_weight(d, wt)
+    y = torch.empty(n, to, ho, wo, cout, device=dev, dtype=torch.bfloat16)
+    gflop = 2.0 * n * to * ho * wo * cout * cin * taps / 1e9
+    line = "%-38s" % name
+    for mode in (0, 2):
+        lib.fvt_set_option(b"igemm_pair", mode)
+        us = timeit(lambda: ops.conv3d_fwd(d, x, wp, sc, sh, out=y))
+        line += " | %s %7.1f us (%5.0f TF/s)" % ("pair  " if mode else "single", us, gflop / us * 1e3)
+    lib.fvt_set_option(b"igemm_pair", 1)
+    print(line, flush=True)
+
 # ---- layers whose filter is stationary on ONE SM (conv2_x 1x3x3 64 -> 144, the row-paired stem): single CTA vs forced pair
 print("== forced pair (fvt_set_option slab_pair) on single-SM-stationary layers")
 for name, n, t, cin, cout, kern, pad in (("conv2 spatial 64->144 b48", 48, 32, 64, 144, (1, 3, 3), (0, 1, 1)),
