@@ -65,6 +65,7 @@ int fvt_device_check(int device);
  * stream its weights; "disable_wgrad_slab" = 1 routes every weight gradient through the im2col kernel (K3);
  * "disable_split_k" = 1 keeps small-M convolutions single-pass; "slab_prefetch" / "slab_box_rows" / "debug_flags" are load-path and epilogue experiments (tools/gpu_*_ab.py);
  * "slab_pair_auto" = 0 keeps the layers whose filter fits two SMs but not one off the CTA-pair kernel (2: pair even for small problems),
+ * "igemm_pair" = 0 keeps the generic im2col convolution on single CTAs (2: pairs even for small problems),
  * "slab_pair" = 1|2 forces the pair kernel for single-SM-stationary layers (1: staged TMA store), "unit_input_stationary" = 0 selects the
  * output-stationary form of the fused (2+1)D unit. */
 int fvt_set_option(const char* name, int value);
