@@ -73,6 +73,7 @@ def load():
         "fvt_pool_fc_fwd": (ctypes.c_int, [vp, i32, i32, i32, i32, fp, fp, i32, fp, fp, vp]),
         "fvt_pack_conv_weight_dgrad": (ctypes.c_int, [dp, fp, i32, i32, vp, vp]),
         "fvt_conv3d_wgrad": (ctypes.c_int, [dp, vp, vp, fp, i32, i32, vp]),
+        "fvt_set_wgrad_workspace": (ctypes.c_int, [vp, ctypes.c_size_t]),
         "fvt_zero_insert": (ctypes.c_int, [vp, vp] + [i32] * 11 + [vp]),
         "fvt_bn_finalize": (ctypes.c_int, [fp, fp, fp, fp, fp, i32, i32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                            fp, fp, fp, fp, vp]),

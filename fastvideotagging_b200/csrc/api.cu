@@ -263,6 +263,58 @@ static int encode_w_map(const DeviceInfo* di, const void* w, int k_total, int ro
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad workspace reduction
+static float* g_wgrad_ws[16] = {nullptr};      // fvt_set_wgrad_workspace: caller-owned scratch per device
+static size_t g_wgrad_ws_bytes[16] = {0};
+
+// dw[i] += sum over the pixel splits of ws[split][i]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long elems, int splits) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  if ((elems & 3) == 0) {
+    const long long n4 = elems >> 2;
+    const float4* w4 = reinterpret_cast<const float4*>(ws);
+    float4* d4 = reinterpret_cast<float4*>(dw);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 a = d4[i];
+      for (int k = 0; k < splits; ++k) {
+        const float4 b = __ldg(w4 + k * n4 + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      d4[i] = a;
+    }
+  } else {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) {
+      float a = dw[i];
+      for (int k = 0; k < splits; ++k) a += __ldg(ws + k * elems + i);
+      dw[i] = a;
+    }
+  }
+}
+
+// Chooses the workspace path for a K3s launch: fills p->ws / p->ws_split_stride when the registered scratch holds
+// `splits` dW-shaped slices.  Returns the slice size in elements (0: atomics).
+static long long wgrad_pick_workspace(WgradSlabParams* p, const float* dw, int cout_real, int cin_real) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const long long elems = (long long)cout_real * cin_real * p->taps;
+  if (dev < 0 || dev >= 16 || g_wgrad_ws[dev] == nullptr || p->splits < 2 || g_wgrad_no_atomics) return 0;
+  if ((size_t)p->splits * (size_t)elems * sizeof(float) > g_wgrad_ws_bytes[dev]) return 0;
+  if ((((uintptr_t)dw) & 15) != 0) return 0;
+  p->ws = g_wgrad_ws[dev];
+  p->ws_split_stride = elems;
+  return elems;
+}
+
+static int wgrad_reduce(const WgradSlabParams& p, long long elems, cudaStream_t stream) {
+  long long work = (elems & 3) == 0 ? elems >> 2 : elems;
+  int blocks = (int)((work + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, p.dw, elems, p.splits);
+  return check_launch("wgrad_reduce_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------ K3s temporal launch
 // kt x 1 x 1 stride-1 convs: same kernel, temporal mode (see WgradSlabParams).  Returns 1 / 0 / < 0 like try_wgrad_slab.
 static int try_wgrad_temporal(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
@@ -344,8 +396,11 @@ static int try_wgrad_temporal(const DeviceInfo* di, const fvt_conv_desc* d, cons
     attr_set[dev] = true;
   }
   const int smem_bytes = p.stages * p.stage_bytes + kAux;
+  const long long ws_elems = wgrad_pick_workspace(&p, dw, cout_real, cin_real);
   conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
   if (int e = check_launch("conv_wgrad_slab_kernel(temporal)")) return e;
+  if (ws_elems > 0)
+    if (int e = wgrad_reduce(p, ws_elems, stream)) return e;
   return 1;
 }
 
@@ -477,8 +532,11 @@ static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const vo
     attr_set[dev] = true;
   }
   const int smem_bytes = p.stages * p.stage_bytes + kAux;
+  const long long ws_elems = wgrad_pick_workspace(&p, dw, cout_real, cin_real);
   conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
   if (int e = check_launch("conv_wgrad_slab_kernel")) return e;
+  if (ws_elems > 0)
+    if (int e = wgrad_reduce(p, ws_elems, stream)) return e;
   return 1;
 }
 
@@ -519,6 +577,15 @@ int fvt_device_check(int device) {
   int st = 0;
   device_info(device, &st);
   return st;
+}
+
+int fvt_set_wgrad_workspace(void* ws, size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return set_error(FVT_ERR_CUDA, "no current CUDA device");
+  if (ws != nullptr && (((uintptr_t)ws) & 15)) return set_error(FVT_ERR_MISALIGNED, "weight-gradient workspace must be 16-byte aligned");
+  g_wgrad_ws[dev] = (float*)ws;
+  g_wgrad_ws_bytes[dev] = ws != nullptr ? bytes : 0;
+  return 0;
 }
 
 int fvt_conv3d_out_shape(const fvt_conv_desc* d, int32_t* to, int32_t* ho, int32_t* wo) {

@@ -48,6 +48,10 @@ struct WgradSlabParams {
   float* dw;
   int w_ohwi;                  // dw layout (O, taps, I) instead of (O, I, taps)
   int dbg_no_atomics;          // experiments only (fvt_set_option("wgrad_no_atomics")): epilogue reads TMEM, adds nothing
+  // Workspace reduction (fvt_set_wgrad_workspace): every pixel split STORES its partial gradient into its own dW-shaped
+  // slice ws[split][...] (full 128-byte lines, no read-modify-write in L2) and one reduce pass adds the slices into dw.
+  float* ws;                   // nullptr: fp32 atomics straight into dw
+  long long ws_split_stride;   // elements of one slice (= cout_real * cin_real * taps)
 };
 
 __global__ void __launch_bounds__(kWgsThreads, 1)
@@ -211,12 +215,16 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         ptx::tmem_ld_32x32b_x16(taddr + c, v);
         ptx::tmem_ld_wait();
         if (row_ok && !p.dbg_no_atomics) {
+          float* slice = p.ws != nullptr ? p.ws + static_cast<size_t>(split) * p.ws_split_stride : nullptr;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = nt * p.n_tile + c + j;
-            if (co < p.cout_real)
-              atomicAdd(p.dw + (p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + ci
-                                         : (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap), __uint_as_float(v[j]));
+            if (co < p.cout_real) {
+              const size_t idx = p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + ci
+                                          : (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap;
+              if (slice != nullptr) slice[idx] = __uint_as_float(v[j]);       // a warp writes 32 consecutive floats (OHWI)
+              else atomicAdd(p.dw + idx, __uint_as_float(v[j]));
+            }
           }
         }
       }

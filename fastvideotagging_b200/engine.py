@@ -453,6 +453,11 @@ class TrainPlan:
         self.device = device
         self.eps, self.momentum = eps, momentum
         self.n, self.t, self.h, self.w = n, t, h, w
+        # FVT_WGRAD_WS=1: the pixel splits of a slab weight gradient are reduced through a scratch buffer (plain stores +
+        # one reduce pass, fixed order -> bit-reproducible gradients) instead of fp32 atomics.  Measured no faster inside
+        # the step (11.68 vs 11.53 ms: the atomics overlap the data-gradient chain on the side stream), so off by default.
+        # All weight gradients run on ONE stream, so one buffer per device is enough.
+        self._wgrad_ws = ops.wgrad_workspace(device, enable=os.environ.get("FVT_WGRAD_WS", "0") == "1")
         self.num_class = num_class
         self.bufs = {}
         self.layers = {}

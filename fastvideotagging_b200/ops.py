@@ -157,6 +157,27 @@ def pool_fc_fwd(x, c_real, weight, bias, want_pooled=False):
 # ---------------------------------------------------------------------------------------------------------------------
 # training ops
 # ---------------------------------------------------------------------------------------------------------------------
+_WGRAD_WS = {}
+WGRAD_WS_BYTES = 160 << 20
+
+
+def wgrad_workspace(device, enable=True):
+    """Registers (once per device) the scratch the slab weight-gradient kernels reduce their pixel splits through
+    (fvt_set_wgrad_workspace) — plain stores + one reduce pass instead of fp32 atomics.  enable=False withdraws it."""
+    lib = _lib.load()
+    key = (device.type, device.index)
+    with torch.cuda.device(device):
+        if not enable:
+            check(lib.fvt_set_wgrad_workspace(None, 0))
+            return None
+        ws = _WGRAD_WS.get(key)
+        if ws is None:
+            ws = torch.empty(WGRAD_WS_BYTES // 4, dtype=torch.float32, device=device)
+            _WGRAD_WS[key] = ws
+        check(lib.fvt_set_wgrad_workspace(_ptr(ws), ws.numel() * 4))
+    return ws
+
+
 def dgrad_desc(fwd, block_n=0, flags=0):
     """Descriptor of the stride-1 convolution that computes the data gradient of `fwd` from dY (for strided `fwd`,
     dY must first be zero-inserted onto the input lattice, see zero_insert): channels swapped, padding k-1-p."""

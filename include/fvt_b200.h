@@ -148,6 +148,12 @@ int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int
  * x: stored input activation, dy: gradient w.r.t. the raw conv output, both NDHWC bf16.  (cuDNN backward-filter.) */
 int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
                      int32_t cin_real, void* stream);
+/* Optional caller-owned fp32 scratch for the current device (NULL / 0 to withdraw it; it must stay valid until then).
+ * With it the slab weight-gradient kernels (stride-1 1xkhxkw and ktx1x1 convs) no longer meet in dw with fp32 atomics:
+ * every pixel split stores its partial gradient into its own dW-shaped slice and one reduce pass adds the slices into dw
+ * (same sums in a fixed order: deterministic).  Used when splits * cout_real * cin_real * taps * 4 bytes fit; launches
+ * that use it must be stream-ordered with respect to each other (one workspace). */
+int fvt_set_wgrad_workspace(void* ws, size_t bytes);
 /* up[n, to*st, ho*sh, wo*sw, :] = dy[n, to, ho, wo, :], zero elsewhere (up has the conv input's T,H,W). */
 int fvt_zero_insert(const void* dy, void* up, int32_t n, int32_t t, int32_t h, int32_t w, int32_t to, int32_t ho,
                     int32_t wo, int32_t st, int32_t sh, int32_t sw, int32_t c_store, void* stream);

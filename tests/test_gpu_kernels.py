@@ -572,3 +572,41 @@ def test_cta_pair_im2col_matches_single_cta(cuda_device, lib, shape):
     ref = out[0][3]
     assert (out[2][3] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-3
     assert out[0][0].float().abs().max().item() > 0
+
+
+@pytest.mark.parametrize("shape", [(4, 8, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1)),      # conv2_x 1x3x3
+                                   (2, 8, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1)),     # conv3_x 1x3x3
+                                   (2, 8, 56, 56, 144, 64, (3, 1, 1), (1, 0, 0)),      # conv2_x 3x1x1 (temporal mode)
+                                   (2, 4, 28, 28, 288, 128, (3, 1, 1), (1, 0, 0))])    # conv3_x 3x1x1
+def test_wgrad_workspace_reduction_matches_atomics(cuda_device, lib, shape):
+    """Slab weight gradients with the pixel splits reduced through the workspace (plain stores + one reduce pass,
+    fvt_set_wgrad_workspace) == the same kernel with fp32 atomics into dw, up to fp32 summation order; the workspace
+    form is deterministic (two runs bit-identical) and accumulates into dw like the atomics do."""
+    import torch
+    from fastvideotagging_b200 import ops
+    n, t, h, w, cin, cout, k, p = shape
+    gen = torch.Generator().manual_seed(cin + cout)
+    x = (torch.randn(n, t, h, w, cin, generator=gen) * 0.5).to(torch.bfloat16).to(cuda_device)
+    dy = (torch.randn(n, t, h, w, cout, generator=gen) * 0.1).to(torch.bfloat16).to(cuda_device)
+    d = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, 0)
+    taps = k[0] * k[1] * k[2]
+
+    def run(ws_on, base):
+        ops.wgrad_workspace(cuda_device, enable=ws_on)
+        dw = torch.full((cout, taps, cin), base, dtype=torch.float32, device=cuda_device)
+        ops.conv3d_wgrad(d, x, dy, dw, cout, cin, ohwi=True)
+        torch.cuda.synchronize()
+        return dw
+
+    try:
+        ref = run(False, 0.0)
+        a = run(True, 0.0)
+        b = run(True, 0.0)
+        c = run(True, 1.5)                   # accumulates on top of what dw holds
+    finally:
+        ops.wgrad_workspace(cuda_device, enable=True)
+    assert torch.equal(a, b)
+    scale = ref.abs().max().item()
+    assert scale > 0
+    assert (a - ref).abs().max().item() <= 1e-5 * scale + 1e-6
+    assert (c - 1.5 - a).abs().max().item() <= 1e-5 * scale + 1e-5
