@@ -15,6 +15,22 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.fvt_version() >= 100
 
 
+def test_ctypes_signatures_match_the_header(lib):
+    """Every function the header declares is bound in _lib.load() with as many ctypes arguments as the C declaration has
+    parameters (a drifted binding would pass garbage pointers to a kernel launch instead of failing here)."""
+    import re
+    with open(_lib.HEADER_PATH) as fh:
+        text = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
+    decls = re.findall(r"\b(fvt_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) >= 15
+    for name, params in decls:
+        params = params.strip()
+        n_c = 0 if params in ("", "void") else len([q for q in params.split(",") if q.strip()])
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, "%s is exported but has no ctypes signature in _lib.load()" % name
+        assert len(fn.argtypes) == n_c, (name, len(fn.argtypes), n_c)
+
+
 def test_conv_descriptor_validation_and_shapes(lib):
     d = ops.conv_desc(2, 8, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))
     assert ops.conv_out_shape(d) == (8, 56, 56)
