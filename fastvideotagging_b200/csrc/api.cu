@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <new>
 #include <unordered_map>
 
 #include "../../include/fvt_b200.h"
@@ -19,6 +20,7 @@
 #include "conv_wgrad_slab.cuh"
 #include "conv_frame_ring.cuh"
 #include "conv_temporal_is.cuh"
+#include "det_sum.cuh"
 #include "host_common.h"
 
 namespace fvt {
@@ -52,35 +54,55 @@ struct DeviceInfo {
   EncodeIm2colFn encode_im2col = nullptr;
 };
 static DeviceInfo g_dev[16];
-static int g_disable_bstat = 0;  // fvt_set_option("disable_b_stationary", 1): K1 always streams the weights
-static int g_disable_wgrad_slab = 0;   // fvt_set_option("disable_wgrad_slab", 1): K3 (im2col) for every weight gradient
-static int g_debug_flags = 0;    // fvt_set_option("debug_flags", bits): OR-ed into the conv kernels' flags (experiments)
-static int g_slab_box_rows = 0;  // fvt_set_option("slab_box_rows", r): rows per slab TMA box (0 = whole slab in one box)
-static int g_slab_prefetch = 2;  // fvt_set_option("slab_prefetch", d): L2 prefetch distance in tiles (0 = off)
-static int g_ring_prefetch = 4;  // fvt_set_option("ring_prefetch", f): K1t L2 prefetch distance in frames (0 = off)
-static int g_disable_ring = 0;   // fvt_set_option("disable_frame_ring", 1): temporal convs go through K1 (im2col)
-static int g_slab_single_stage = 1;   // fvt_set_option("slab_single_stage", 0): keep two input stages even with a shallow weight ring
-static int g_disable_tis = 0;    // fvt_set_option("disable_temporal_is", 1): no input-stationary temporal kernel (K1i)
-static int g_disable_tis_tma_store = 1;  // fvt_set_option("disable_tis_tma_store", 0) turns the TMA-store epilogue of K1i ON.  Measured
-                                         // SLOWER than the register stores it replaces (conv2_x 144->64 at batch 48: 399 -> 422 us,
-                                         // with residual 562 -> 641 us): the staging tiles cost a pipeline stage (main loop 357 ->
-                                         // 394 us) and the two 256-thread barriers per tile serialise the eight epilogue warps
-static int g_disable_splitk = 0; // fvt_set_option("disable_split_k", 1): K1 never splits the reduction
-static int g_slab_epi_warps = 8;   // fvt_set_option("slab_epi_warps", 8|16): epilogue warps of the slab kernel.  16 measured SLOWER
-                                   // (conv2_x 1x3x3 at batch 48: 756 -> 996 us): the stores are request-throughput-bound, not latency-bound
-static int g_wgrad_atomic_rate = 0;    // fvt_set_option("wgrad_atomic_rate", r): fp32 reductions per clock assumed by the K3s tiling
-                                       // heuristic as a launch-wide flush cost.  0 = ignore it (default): with r = 150 the
-                                       // heuristic picks fewer pixel splits and the step's weight gradients get SLOWER
-                                       // (3.74 -> 4.06 ms; conv2_x 116 -> 157 us) — the flush overlaps other CTAs' MMAs
-static int g_wgrad_no_atomics = 0;   // fvt_set_option("wgrad_no_atomics", 1): experiments only (timing without the epilogue atomics)
-static int g_unit_is = 1;        // fvt_set_option("unit_input_stationary", 0|1): fused (2+1)D unit with the temporal conv as one N = 192 MMA chain
-                                 // per mid frame (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame (conv_unit_fused.cuh)
-static int g_igemm_pair = 1;     // fvt_set_option("igemm_pair", 0|1): generic im2col convolution on CTA pairs (K1p) for the wide streamed-weight layers
-static int g_slab_pair_auto = 1; // fvt_set_option("slab_pair_auto", 0|1|2): CTA-pair slab kernel when the filter fits two SMs but not one (2: also for small problems)
-static int g_slab_pair = 0;      // fvt_set_option("slab_pair", 0|1|2): CTA-pair slab kernel (cta_group::2) for stationary-filter layers;
-                                 // 2 = pair kernel with register stores instead of the staged TMA store (A/B runs)
-static int g_disable_slab = 0;   // fvt_set_option("disable_slab", 1): force the generic im2col kernel (A/B runs, tests)
 static std::mutex g_mu;
+
+// ------------------------------------------------------------------------------------------------ handle
+// One handle per (host thread, device) — the analogue of the reference's one executor per context (train.py:54).  It owns
+// the tuning switches (fvt_set_option), nothing else: every buffer, the split-K and weight-gradient workspaces included,
+// is passed in by the caller per call, and no pointer is kept past a call.
+#define FVT_OPTIONS(X)                                                                                                          \
+  X(disable_b_stationary, 0)  /* 1: K1 always streams the weights */                                                             \
+  X(disable_wgrad_slab, 0)    /* 1: K3 (im2col) for every weight gradient */                                                     \
+  X(debug_flags, 0)           /* OR-ed into the conv kernels' flags (kDbgNoStore | kDbgNoEpilogue: timing experiments) */        \
+  X(slab_box_rows, 0)         /* rows per slab TMA box (0 = whole slab in one box) */                                            \
+  X(slab_prefetch, 2)         /* L2 prefetch distance of the slab kernels in tiles (0 = off) */                                  \
+  X(ring_prefetch, 4)         /* K1t L2 prefetch distance in frames (0 = off) */                                                 \
+  X(disable_frame_ring, 0)    /* 1: temporal convs go through K1 (im2col) instead of K1t */                                      \
+  X(slab_single_stage, 1)     /* 0: keep two input stages even with a shallow weight ring */                                     \
+  X(disable_temporal_is, 0)   /* 1: no input-stationary temporal kernel (K1i) */                                                 \
+  X(disable_tis_tma_store, 1) /* 0 turns the TMA-store epilogue of K1i ON.  Measured SLOWER than the register stores it          \
+                                 replaces (conv2_x 144->64 at batch 48: 399 -> 422 us, with residual 562 -> 641 us) */           \
+  X(disable_split_k, 0)       /* 1: K1 never splits the reduction */                                                             \
+  X(slab_epi_warps, 8)        /* 8|16 epilogue warps of the slab kernel.  16 measured SLOWER (conv2_x 1x3x3 at batch 48:         \
+                                 756 -> 996 us): the stores are request-throughput-bound, not latency-bound */                   \
+  X(wgrad_no_store, 0)        /* experiments only: the weight-gradient epilogue reads TMEM and stores nothing */                 \
+  X(unit_input_stationary, 1) /* fused (2+1)D unit: temporal conv as one N = 192 MMA chain per mid frame                         \
+                                 (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame */                     \
+  X(igemm_pair, 1)            /* 0|1|2: generic im2col convolution on CTA pairs (K1p) for the wide streamed-weight layers */     \
+  X(slab_pair_auto, 1)        /* 0|1|2: CTA-pair slab kernel when the filter fits two SMs but not one (2: also small problems) */ \
+  X(slab_pair, 0)             /* 0|1|2: CTA-pair slab kernel for single-SM-stationary layers; 2 = register stores */             \
+  X(disable_slab, 0)          /* 1: force the generic im2col kernel (A/B runs, tests) */                                          \
+  X(disable_dgrad_direct, 0)  /* 1: strided data gradients go through fvt_zero_insert instead of the parity sub-convolutions */
+
+struct Options {
+#define FVT_OPT_FIELD(name, def) int name = def;
+  FVT_OPTIONS(FVT_OPT_FIELD)
+#undef FVT_OPT_FIELD
+};
+
+}  // namespace fvt
+
+struct fvt_handle_s {
+  uint32_t magic;
+  int device;
+  const fvt::DeviceInfo* di;
+  fvt::Options opt;
+};
+
+namespace fvt {
+constexpr uint32_t kHandleMagic = 0x46565442u;   // "FVTB"
+
+
 
 static int resolve_driver(DeviceInfo& di) {
   cudaDriverEntryPointQueryResult qres;
@@ -126,6 +148,20 @@ const DeviceInfo* current_device_info(int* status) {
   return device_info(dev, status);
 }
 int sm_count_of(const DeviceInfo* di) { return di->sm_count; }
+
+// Validates a handle and that its device is the calling thread's current device; returns the device facts.
+const DeviceInfo* handle_device(fvt_handle_t h, int* status) {
+  if (h == nullptr || h->magic != kHandleMagic) { *status = set_error(FVT_ERR_BAD_HANDLE, "invalid handle (fvt_create first)"); return nullptr; }
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { *status = set_error(FVT_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+  if (dev != h->device) {
+    *status = set_error(FVT_ERR_BAD_HANDLE, "handle belongs to device %d but the current device is %d (one handle per thread and device)", h->device, dev);
+    return nullptr;
+  }
+  *status = 0;
+  return h->di;
+}
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -231,13 +267,88 @@ pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ multi-tensor packing
+// The training step re-packs the bf16 operand copies of ALL conv weights after every optimiser step (69 forward-layout +
+// 68 data-gradient-layout tensors).  One launch per tensor cost 1.4 ms of kernel time per step (137 launches of 4-15 us
+// for 0.76 GB of traffic); here ONE launch walks a device table of (tensor, layout) entries.  Sources are the fp32
+// masters in the (O, kT, kH, kW, I) storage of engine.FlatParams (FVT_CONV_W_OHWI).
+//   kind 0, forward layout:        out[o][tap][ci]          = w[o][tap][ci]      (o < rows, ci < k_store; zero padded)
+//   kind 1, data-gradient layout:  out[r][taps-1-tap][k]    = w[k][tap][r]       (r < rows, k < k_store; zero padded)
+//   kind 2, parity sub-filter of a STRIDED convolution's data gradient (see fvt_conv3d_fwd_ex): out[r][u][k] = w[k][tap(u)][r],
+//           u = (ut, uh, uw) over sub[3], source tap per axis = tap_a - tap_s*u over the src_k[3] filter
+constexpr int kPackFwdRows = 8;          // output rows per CTA (kind 0)
+constexpr int kPackTileR = 32, kPackTileK = 64;   // (r, k) tile per CTA (kind 1)
+
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const fvt_pack_entry* __restrict__ table, int n_entries) {
+  __shared__ float tile[kPackTileK][kPackTileR + 1];
+  // entry of this CTA: last entry with block0 <= blockIdx.x
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].block0 <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const fvt_pack_entry e = table[lo];
+  const unsigned local = blockIdx.x - e.block0;
+  const float* __restrict__ w = e.w;
+  __nv_bfloat16* __restrict__ out = static_cast<__nv_bfloat16*>(e.out);
+  if (e.kind == 0) {
+    const int row_len = e.taps * e.k_store;
+    const int o0 = static_cast<int>(local) * kPackFwdRows;
+    const int total = kPackFwdRows * row_len;
+    for (int i = threadIdx.x * 2; i < total; i += blockDim.x * 2) {          // two channels per thread: 4-byte stores
+      const int rr = i / row_len, j = i - rr * row_len;
+      const int o = o0 + rr;
+      if (o >= e.rows) break;
+      const int tap = j / e.k_store, ci = j - tap * e.k_store;               // k_store is even, i is even: ci, ci+1 share a tap
+      float v0 = 0.f, v1 = 0.f;
+      if (o < e.cout_real) {
+        const float* src = w + (static_cast<size_t>(o) * e.taps + tap) * e.cin_real;
+        if (ci < e.cin_real) v0 = __ldg(src + ci);
+        if (ci + 1 < e.cin_real) v1 = __ldg(src + ci + 1);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(out + static_cast<size_t>(o) * row_len + j) = __floats2bfloat162_rn(v0, v1);
+    }
+  } else {
+    const int r_tiles = (e.rows + kPackTileR - 1) / kPackTileR;
+    const int k_tiles = (e.k_store + kPackTileK - 1) / kPackTileK;
+    // `u` = tap of the PACKED filter (e.taps of them: sub[0]*sub[1]*sub[2] for kind 2), `tap` = the source tap it copies
+    const int u = static_cast<int>(local) / (r_tiles * k_tiles);
+    const int rem = static_cast<int>(local) - u * (r_tiles * k_tiles);
+    const int r0 = (rem / k_tiles) * kPackTileR, k0 = (rem % k_tiles) * kPackTileK;
+    int tap = e.taps - 1 - u, src_taps = e.taps;                   // kind 1: the whole filter, reversed
+    if (e.kind == 2) {
+      const int uw = u % e.sub[2], uh = (u / e.sub[2]) % e.sub[1], ut = u / (e.sub[2] * e.sub[1]);
+      const int kt_ = e.tap_a[0] - e.tap_s[0] * ut, kh_ = e.tap_a[1] - e.tap_s[1] * uh, kw_ = e.tap_a[2] - e.tap_s[2] * uw;
+      tap = (kt_ * e.src_k[1] + kh_) * e.src_k[2] + kw_;
+      src_taps = e.src_k[0] * e.src_k[1] * e.src_k[2];
+    }
+    // here cout_real / cin_real are the FORWARD filter counts: k runs over forward output channels, r over forward inputs
+    for (int i = threadIdx.x; i < kPackTileK * kPackTileR; i += blockDim.x) {
+      const int kk = i / kPackTileR, rr = i - kk * kPackTileR;
+      const int k = k0 + kk, r = r0 + rr;
+      tile[kk][rr] = (k < e.cout_real && r < e.cin_real) ? __ldg(w + (static_cast<size_t>(k) * src_taps + tap) * e.cin_real + r) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kPackTileR * (kPackTileK / 2); i += blockDim.x) {
+      const int rr = i / (kPackTileK / 2), kk = 2 * (i - rr * (kPackTileK / 2));
+      const int r = r0 + rr, k = k0 + kk;
+      if (r < e.rows && k < e.k_store)
+        *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(r) * e.taps + u) * e.k_store + k) =
+            __floats2bfloat162_rn(tile[kk][rr], tile[kk + 1][rr]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ tensor maps
-static int encode_x_map(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, CUtensorMap* map) {
+static int encode_x_map(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, CUtensorMap* map, const int32_t* pad_hi = nullptr) {
   const cuuint64_t dims[5] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->t, (cuuint64_t)d->n};
   const cuuint64_t strides[4] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w,
                                  (cuuint64_t)d->cin * 2 * d->w * d->h, (cuuint64_t)d->cin * 2 * d->w * d->h * d->t};
   const int lower[3] = {-d->pw, -d->ph, -d->pt};
-  const int upper[3] = {d->pw - (d->kw - 1), d->ph - (d->kh - 1), d->pt - (d->kt - 1)};
+  // high padding defaults to the low padding (symmetric); fvt_conv3d_fwd_ex may give it per axis (t, h, w)
+  const int upper[3] = {(pad_hi ? pad_hi[2] : d->pw) - (d->kw - 1), (pad_hi ? pad_hi[1] : d->ph) - (d->kh - 1),
+                        (pad_hi ? pad_hi[0] : d->pt) - (d->kt - 1)};
   const cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->st, 1};
   CUresult r = di->encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, lower,
                                  upper, kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -263,21 +374,23 @@ static int encode_w_map(const DeviceInfo* di, const void* w, int k_total, int ro
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ wgrad workspace reduction
-static float* g_wgrad_ws[16] = {nullptr};      // fvt_set_wgrad_workspace: caller-owned scratch per device
-static size_t g_wgrad_ws_bytes[16] = {0};
-
-// dw[i] += sum over the pixel splits of ws[split][i]
+// ------------------------------------------------------------------------------------------------ wgrad split reduction
+// A weight gradient reduces over every output pixel of the batch; to fill the machine that reduction is split over
+// several CTAs per dW tile ("pixel splits").  Round 1 let the splits meet in dW through fp32 atomics (arrival order ->
+// run-to-run differences, and 1.3 ms of L2 read-modify-write per step).  Now every split STORES its partial tile into
+// its own dW-shaped slice of the caller's workspace and one pass adds the slices in split order and overwrites dW:
+// deterministic, and dW needs no zeroing.  With a single split the kernel stores straight into dW.
+// dw[i] = sum over k < splits of ws[k][i]   (fixed order)
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long elems, int splits) {
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long elems, int splits, int vec4) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  if ((elems & 3) == 0) {
+  if (vec4) {
     const long long n4 = elems >> 2;
     const float4* w4 = reinterpret_cast<const float4*>(ws);
     float4* d4 = reinterpret_cast<float4*>(dw);
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      float4 a = d4[i];
-      for (int k = 0; k < splits; ++k) {
+      float4 a = __ldg(w4 + i);
+      for (int k = 1; k < splits; ++k) {
         const float4 b = __ldg(w4 + k * n4 + i);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
       }
@@ -285,41 +398,38 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long l
     }
   } else {
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) {
-      float a = dw[i];
-      for (int k = 0; k < splits; ++k) a += __ldg(ws + k * elems + i);
+      float a = __ldg(ws + i);
+      for (int k = 1; k < splits; ++k) a += __ldg(ws + k * elems + i);
       dw[i] = a;
     }
   }
 }
 
-// Chooses the workspace path for a K3s launch: fills p->ws / p->ws_split_stride when the registered scratch holds
-// `splits` dW-shaped slices.  Returns the slice size in elements (0: atomics).
-static long long wgrad_pick_workspace(WgradSlabParams* p, const float* dw, int cout_real, int cin_real) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const long long elems = (long long)cout_real * cin_real * p->taps;
-  if (dev < 0 || dev >= 16 || g_wgrad_ws[dev] == nullptr || p->splits < 2 || g_wgrad_no_atomics) return 0;
-  if ((size_t)p->splits * (size_t)elems * sizeof(float) > g_wgrad_ws_bytes[dev]) return 0;
-  if ((((uintptr_t)dw) & 15) != 0) return 0;
-  p->ws = g_wgrad_ws[dev];
-  p->ws_split_stride = elems;
-  return elems;
+// Largest number of pixel splits (<= wanted) whose dW-shaped slices fit the caller's workspace; 1 = no workspace needed.
+static int wgrad_fit_splits(int wanted, long long elems, const void* ws, size_t ws_bytes) {
+  if (wanted < 2) return 1;
+  if (ws == nullptr || (((uintptr_t)ws) & 15) != 0) return 1;
+  const size_t slice = (size_t)elems * sizeof(float);
+  size_t fit = slice > 0 ? ws_bytes / slice : 0;
+  if (fit < 2) return 1;
+  return fit < (size_t)wanted ? (int)fit : wanted;
 }
 
-static int wgrad_reduce(const WgradSlabParams& p, long long elems, cudaStream_t stream) {
-  long long work = (elems & 3) == 0 ? elems >> 2 : elems;
+static int wgrad_reduce(const float* ws, float* dw, long long elems, int splits, cudaStream_t stream) {
+  const int vec4 = ((elems & 3) == 0 && (((uintptr_t)dw) & 15) == 0) ? 1 : 0;
+  long long work = vec4 ? elems >> 2 : elems;
   int blocks = (int)((work + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, p.dw, elems, p.splits);
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, dw, elems, splits, vec4);
   return check_launch("wgrad_reduce_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ K3s temporal launch
 // kt x 1 x 1 stride-1 convs: same kernel, temporal mode (see WgradSlabParams).  Returns 1 / 0 / < 0 like try_wgrad_slab.
-static int try_wgrad_temporal(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
-                              int cout_real, int cin_real, cudaStream_t stream) {
-  if (g_disable_wgrad_slab) return 0;
+static int try_wgrad_temporal(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
+                              int cout_real, int cin_real, void* ws, size_t ws_bytes, cudaStream_t stream, size_t* plan_bytes = nullptr) {
+  if (o.disable_wgrad_slab) return 0;
   if (!(d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 && d->ph == 0 &&
         d->pw == 0 && 2 * d->pt == d->kt - 1))
     return 0;
@@ -363,10 +473,14 @@ static int try_wgrad_temporal(const DeviceInfo* di, const fvt_conv_desc* d, cons
   int splits = di->sm_count / items;
   if (splits < 1) splits = 1;
   if (splits > p.num_tiles) splits = p.num_tiles;
+  const long long dw_elems = (long long)cout_real * cin_real * p.taps;
+  if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)dw_elems * sizeof(float) : 0; return 1; }
+  splits = wgrad_fit_splits(splits, dw_elems, ws, ws_bytes);
   p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
   p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw; p.dbg_no_atomics = g_wgrad_no_atomics; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
+  p.dw = dw; p.dbg_no_store = o.wgrad_no_store; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
+  p.ws = p.splits > 1 ? (float*)ws : nullptr; p.ws_split_stride = dw_elems;
 
   CUtensorMap tmx, tmdy;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -387,28 +501,19 @@ static int try_wgrad_temporal(const DeviceInfo* di, const fvt_conv_desc* d, cons
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad temporal dy) failed (CUresult %d)", (int)r);
   }
-  static bool attr_set[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_wgrad_slab_kernel): %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
-  }
   const int smem_bytes = p.stages * p.stage_bytes + kAux;
-  const long long ws_elems = wgrad_pick_workspace(&p, dw, cout_real, cin_real);
   conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
   if (int e = check_launch("conv_wgrad_slab_kernel(temporal)")) return e;
-  if (ws_elems > 0)
-    if (int e = wgrad_reduce(p, ws_elems, stream)) return e;
+  if (p.splits > 1 && !o.wgrad_no_store)
+    if (int e = wgrad_reduce(p.ws, dw, dw_elems, p.splits, stream)) return e;
   return 1;
 }
 
 // ------------------------------------------------------------------------------------------------ K3s launch
 // Returns 1 when the slab weight-gradient kernel took the call, 0 when the shape is not eligible, < 0 on error.
-static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
-                          int cout_real, int cin_real, cudaStream_t stream) {
-  if (g_disable_wgrad_slab) return 0;
+static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
+                          int cout_real, int cin_real, void* ws, size_t ws_bytes, cudaStream_t stream, size_t* plan_bytes = nullptr) {
+  if (o.disable_wgrad_slab) return 0;
   if (!(d->kt == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && (d->kh > 1 || d->kw > 1) &&
         2 * d->ph == d->kh - 1 && 2 * d->pw == d->kw - 1 && d->cin % 64 == 0 && d->w + 2 * d->pw <= 128))
     return 0;
@@ -466,13 +571,8 @@ static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const vo
       const double bytes = (double)ncb_max * p.slab_tx_bytes + (double)p.dy_tx_bytes * n_tile / 64.0;
       const double per_tile = mma_clk > bytes / 64.0 ? mma_clk : bytes / 64.0;
       const int waves = (items * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
-      const double epi = (double)mt * n_tile * 40.0;            // atomics of one accumulator block
-      // every CTA of the launch flushes mt*128*n_tile fp32 reductions, and the L2 atomic units retire only ~150 of them per
-      // clock GPU-wide (measured: the 69 weight gradients of a step take 3.9 ms with, 2.6 ms without the reductions), so
-      // the flush is a launch-wide cost that grows with the number of pixel splits
-      const double ctas = (double)items * ((p.num_tiles + tps - 1) / tps);
-      const double glob = g_wgrad_atomic_rate > 0 ? ctas * mt * 128.0 * n_tile / (double)g_wgrad_atomic_rate : 0.0;
-      const double flush = waves * epi > glob ? waves * epi : glob;
+      const double epi = (double)mt * n_tile * 12.0;            // plain stores of one accumulator block
+      const double flush = waves * epi;
       const double est = waves * (tps * per_tile + 3000.0) + flush;
       if (est < best) { best = est; best_nt = nt; best_mt = mt; }
     }
@@ -498,10 +598,14 @@ static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const vo
   int splits = di->sm_count / items;
   if (splits < 1) splits = 1;
   if (splits > p.num_tiles) splits = p.num_tiles;
+  const long long dw_elems = (long long)cout_real * cin_real * p.taps;
+  if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)dw_elems * sizeof(float) : 0; return 1; }
+  splits = wgrad_fit_splits(splits, dw_elems, ws, ws_bytes);
   p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
   p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw; p.dbg_no_atomics = g_wgrad_no_atomics; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
+  p.dw = dw; p.dbg_no_store = o.wgrad_no_store; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
+  p.ws = p.splits > 1 ? (float*)ws : nullptr; p.ws_split_stride = dw_elems;
 
   CUtensorMap tmx, tmdy;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -523,20 +627,11 @@ static int try_wgrad_slab(const DeviceInfo* di, const fvt_conv_desc* d, const vo
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad slab dy) failed (CUresult %d)", (int)r);
   }
-  static bool attr_set[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_wgrad_slab_kernel): %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
-  }
   const int smem_bytes = p.stages * p.stage_bytes + kAux;
-  const long long ws_elems = wgrad_pick_workspace(&p, dw, cout_real, cin_real);
   conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
   if (int e = check_launch("conv_wgrad_slab_kernel")) return e;
-  if (ws_elems > 0)
-    if (int e = wgrad_reduce(p, ws_elems, stream)) return e;
+  if (p.splits > 1 && !o.wgrad_no_store)
+    if (int e = wgrad_reduce(p.ws, dw, dw_elems, p.splits, stream)) return e;
   return 1;
 }
 
@@ -546,29 +641,90 @@ using namespace fvt;
 
 extern "C" {
 
-int fvt_version(void) { return 101; }
+int fvt_version(void) { return 200; }
 
-int fvt_set_option(const char* name, int value) {
-  if (name != nullptr && strcmp(name, "disable_slab") == 0) { g_disable_slab = value; return 0; }
-  if (name != nullptr && strcmp(name, "disable_tis_tma_store") == 0) { g_disable_tis_tma_store = value; return 0; }
-  if (name != nullptr && strcmp(name, "wgrad_atomic_rate") == 0) { g_wgrad_atomic_rate = value; return 0; }
-  if (name != nullptr && strcmp(name, "wgrad_no_atomics") == 0) { g_wgrad_no_atomics = value; return 0; }
-  if (name != nullptr && strcmp(name, "slab_pair") == 0) { g_slab_pair = value; return 0; }
-  if (name != nullptr && strcmp(name, "slab_pair_auto") == 0) { g_slab_pair_auto = value; return 0; }
-  if (name != nullptr && strcmp(name, "igemm_pair") == 0) { g_igemm_pair = value; return 0; }
-  if (name != nullptr && strcmp(name, "unit_input_stationary") == 0) { g_unit_is = value; return 0; }
-  if (name != nullptr && strcmp(name, "slab_epi_warps") == 0) { g_slab_epi_warps = value == 16 ? 16 : 8; return 0; }
-  if (name != nullptr && strcmp(name, "disable_b_stationary") == 0) { g_disable_bstat = value; return 0; }
-  if (name != nullptr && strcmp(name, "ring_prefetch") == 0) { g_ring_prefetch = value; return 0; }
-  if (name != nullptr && strcmp(name, "disable_frame_ring") == 0) { g_disable_ring = value; return 0; }
-  if (name != nullptr && strcmp(name, "slab_single_stage") == 0) { g_slab_single_stage = value; return 0; }
-  if (name != nullptr && strcmp(name, "disable_temporal_is") == 0) { g_disable_tis = value; return 0; }
-  if (name != nullptr && strcmp(name, "disable_split_k") == 0) { g_disable_splitk = value; return 0; }
-  if (name != nullptr && strcmp(name, "slab_box_rows") == 0) { g_slab_box_rows = value; return 0; }
-  if (name != nullptr && strcmp(name, "slab_prefetch") == 0) { g_slab_prefetch = value; return 0; }
-  if (name != nullptr && strcmp(name, "debug_flags") == 0) { g_debug_flags = value & (kDbgNoStore | kDbgNoEpilogue); return 0; }
-  if (name != nullptr && strcmp(name, "disable_wgrad_slab") == 0) { g_disable_wgrad_slab = value; return 0; }
-  return set_error(FVT_ERR_BAD_DESC, "unknown option");
+// Opt-in to > 48 KB of dynamic shared memory is a per-device, per-kernel attribute: set once when the first handle of a
+// device is created (immutable afterwards — not tuning state).
+static int init_kernel_attributes(int device) {
+  static bool done[16] = {false};
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (done[device]) return 0;
+  const int kSmemMax = 227 * 1024;
+  cudaError_t e = cudaSuccess;
+#define FVT_SET_SMEM(k, bytes) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+  FVT_SET_SMEM(conv_igemm_fwd_kernel, kSmemMax);
+  FVT_SET_SMEM(conv_igemm_pair_kernel, kSmemMax);
+  FVT_SET_SMEM(conv_slab_fwd_kernel<8>, kSmemMax);
+  FVT_SET_SMEM(conv_slab_fwd_kernel<16>, kSmemMax);
+  FVT_SET_SMEM(conv_slab_pair_kernel, kSmemMax);
+  FVT_SET_SMEM(conv_temporal_is_kernel, kSmemMax);
+  FVT_SET_SMEM(conv_frame_ring_kernel, kSmemMax);
+  FVT_SET_SMEM(unit2p1_fused_kernel, kSmemMax);
+  FVT_SET_SMEM(unit2p1_fused_is_kernel, kSmemMax);
+  FVT_SET_SMEM(conv_wgrad_kernel, kSmemMax);
+  FVT_SET_SMEM(conv_wgrad_slab_kernel, kSmemMax);
+  FVT_SET_SMEM(pack_weight_fwd_kernel, 96 * 1024);
+  FVT_SET_SMEM(pack_weight_dgrad_kernel, 96 * 1024);
+#undef FVT_SET_SMEM
+  if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(e));
+  done[device] = true;
+  return 0;
+}
+
+int fvt_create(fvt_handle_t* handle, int device) {
+  if (handle == nullptr) return set_error(FVT_ERR_BAD_DESC, "null handle pointer");
+  *handle = nullptr;
+  int st = 0;
+  const DeviceInfo* di = device_info(device, &st);
+  if (di == nullptr) return st;
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) return set_error(FVT_ERR_CUDA, "no current CUDA device");
+  if (cur != device) {
+    if (cudaSetDevice(device) != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  }
+  st = init_kernel_attributes(device);
+  if (cur != device) cudaSetDevice(cur);
+  if (st != 0) return st;
+  fvt_handle_s* h = new (std::nothrow) fvt_handle_s();
+  if (h == nullptr) return set_error(FVT_ERR_CUDA, "out of host memory");
+  h->magic = kHandleMagic; h->device = device; h->di = di;
+  *handle = h;
+  return 0;
+}
+
+int fvt_destroy(fvt_handle_t handle) {
+  if (handle == nullptr) return 0;
+  if (handle->magic != kHandleMagic) return set_error(FVT_ERR_BAD_HANDLE, "invalid handle");
+  handle->magic = 0;
+  delete handle;
+  return 0;
+}
+
+static int* option_slot(Options& o, const char* name) {
+#define FVT_OPT_FIND(n, def) if (strcmp(name, #n) == 0) return &o.n;
+  FVT_OPTIONS(FVT_OPT_FIND)
+#undef FVT_OPT_FIND
+  return nullptr;
+}
+
+int fvt_set_option(fvt_handle_t handle, const char* name, int value) {
+  if (handle == nullptr || handle->magic != kHandleMagic) return set_error(FVT_ERR_BAD_HANDLE, "invalid handle");
+  if (name == nullptr) return set_error(FVT_ERR_BAD_DESC, "null option name");
+  int* slot = option_slot(handle->opt, name);
+  if (slot == nullptr) return set_error(FVT_ERR_BAD_DESC, "unknown option '%s'", name);
+  if (strcmp(name, "debug_flags") == 0) value &= (kDbgNoStore | kDbgNoEpilogue);
+  if (strcmp(name, "slab_epi_warps") == 0) value = value == 16 ? 16 : 8;
+  *slot = value;
+  return 0;
+}
+
+int fvt_get_option(fvt_handle_t handle, const char* name, int* value) {
+  if (handle == nullptr || handle->magic != kHandleMagic) return set_error(FVT_ERR_BAD_HANDLE, "invalid handle");
+  if (name == nullptr || value == nullptr) return set_error(FVT_ERR_BAD_DESC, "null argument");
+  int* slot = option_slot(handle->opt, name);
+  if (slot == nullptr) return set_error(FVT_ERR_BAD_DESC, "unknown option '%s'", name);
+  *value = *slot;
+  return 0;
 }
 
 const char* fvt_last_error(void) { return g_err; }
@@ -579,14 +735,7 @@ int fvt_device_check(int device) {
   return st;
 }
 
-int fvt_set_wgrad_workspace(void* ws, size_t bytes) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return set_error(FVT_ERR_CUDA, "no current CUDA device");
-  if (ws != nullptr && (((uintptr_t)ws) & 15)) return set_error(FVT_ERR_MISALIGNED, "weight-gradient workspace must be 16-byte aligned");
-  g_wgrad_ws[dev] = (float*)ws;
-  g_wgrad_ws_bytes[dev] = ws != nullptr ? bytes : 0;
-  return 0;
-}
+size_t fvt_stats_bytes(int32_t c_store) { return c_store > 0 ? (size_t)c_store * 2 * kDetLimbs * sizeof(unsigned long long) : 0; }
 
 int fvt_conv3d_out_shape(const fvt_conv_desc* d, int32_t* to, int32_t* ho, int32_t* wo) {
   if (int e = validate_conv(d)) return e;
@@ -609,8 +758,10 @@ size_t fvt_conv3d_packed_weight_elems(const fvt_conv_desc* d) {
   return (size_t)weight_rows(d, bn) * d->kt * d->kh * d->kw * d->cin;
 }
 
-int fvt_pack_conv_weight(const fvt_conv_desc* d, const float* w_oidhw, int32_t cout_real, int32_t cin_real,
+int fvt_pack_conv_weight(fvt_handle_t handle, const fvt_conv_desc* d, const float* w_oidhw, int32_t cout_real, int32_t cin_real,
                          void* w_packed, void* stream) {
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
   if (int e = validate_conv(d)) return e;
   if (cout_real <= 0 || cout_real > d->cout || cin_real <= 0 || cin_real > d->cin)
     return set_error(FVT_ERR_BAD_DESC, "real filter counts (%d, %d) exceed stored (%d, %d)", cout_real, cin_real, d->cout, d->cin);
@@ -620,21 +771,16 @@ int fvt_pack_conv_weight(const fvt_conv_desc* d, const float* w_oidhw, int32_t c
   const int taps = d->kt * d->kh * d->kw;
   const size_t smem = sizeof(float) * (size_t)cin_real * taps;
   if (smem > 96 * 1024) return set_error(FVT_ERR_BAD_DESC, "filter row too long to pack (%zu bytes)", smem);
-  static bool attr_set[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev]) {
-    cudaFuncSetAttribute(pack_weight_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set[dev] = true;
-  }
   pack_weight_fwd_kernel<<<rows, 256, smem, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, taps, d->cin,
                                                                     cout_real, cin_real, (d->flags & FVT_CONV_W_OHWI) ? 1 : 0);
   return check_launch("pack_weight_fwd_kernel");
 }
 
-int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int32_t fwd_cout_real, int32_t fwd_cin_real,
-                               void* w_packed, void* stream) {
+int fvt_pack_conv_weight_dgrad(fvt_handle_t handle, const fvt_conv_desc* d, const float* w_oidhw, int32_t fwd_cout_real,
+                               int32_t fwd_cin_real, void* w_packed, void* stream) {
   // `d` describes the data-gradient convolution: d->cin = stored forward Cout, d->cout = stored forward Cin.
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
   if (int e = validate_conv(d)) return e;
   if (fwd_cout_real <= 0 || fwd_cout_real > d->cin || fwd_cin_real <= 0 || fwd_cin_real > d->cout)
     return set_error(FVT_ERR_BAD_DESC, "forward filter counts (%d, %d) exceed the dgrad descriptor (%d, %d)", fwd_cout_real, fwd_cin_real, d->cin, d->cout);
@@ -646,41 +792,78 @@ int fvt_pack_conv_weight_dgrad(const fvt_conv_desc* d, const float* w_oidhw, int
   const dim3 grid((rows + kPackR - 1) / kPackR, (d->cin + kPackK - 1) / kPackK);
   const size_t smem = sizeof(float) * kPackK * (kPackR * taps + 1);
   if (smem > 96 * 1024) return set_error(FVT_ERR_BAD_DESC, "filter has too many taps to pack (%d)", taps);
-  static bool attr_set_d[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set_d[dev]) {
-    cudaFuncSetAttribute(pack_weight_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set_d[dev] = true;
-  }
   pack_weight_dgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w_oidhw, (__nv_bfloat16*)w_packed, rows, taps, d->cin,
                                                                       fwd_cin_real, fwd_cout_real,
                                                                       (d->flags & FVT_CONV_W_OHWI) ? 1 : 0);
   return check_launch("pack_weight_dgrad_kernel");
 }
 
-int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
-                   const float* shift, const void* residual, void* y, float* stats, void* workspace,
-                   size_t workspace_bytes, void* stream) {
-  if (int e = validate_conv(d)) return e;
+uint32_t fvt_pack_entry_blocks(int32_t kind, int32_t taps, int32_t k_store, int32_t rows) {
+  if (taps <= 0 || k_store <= 0 || rows <= 0) return 0;
+  if (kind == 0) return (uint32_t)((rows + kPackFwdRows - 1) / kPackFwdRows);
+  return (uint32_t)(taps * ((rows + kPackTileR - 1) / kPackTileR) * ((k_store + kPackTileK - 1) / kPackTileK));
+}
+
+int fvt_pack_conv_weights_multi(fvt_handle_t handle, const fvt_pack_entry* table_dev, int32_t n_entries, uint32_t total_blocks,
+                                void* stream) {
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
+  if (table_dev == nullptr || n_entries <= 0 || total_blocks == 0) return set_error(FVT_ERR_BAD_DESC, "empty pack table");
+  pack_weights_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(table_dev, n_entries);
+  return check_launch("pack_weights_multi_kernel");
+}
+
+}  // extern "C"
+
+// ext != nullptr (fvt_conv3d_fwd_ex): per-axis high padding and an output lattice map; always the generic kernel K1.
+static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                           const float* shift, const void* residual, void* y, void* stats_acc, void* workspace,
+                           size_t workspace_bytes, void* stream, const fvt_conv_ext* ext) {
+  int st = 0;
+  const DeviceInfo* di = handle_device(handle, &st);
+  if (di == nullptr) return st;
+  const Options& o = handle->opt;
+  unsigned long long* stats = reinterpret_cast<unsigned long long*>(stats_acc);
+  if (ext != nullptr && d != nullptr) {
+    fvt_conv_desc dv = *d;                    // the size check assumes symmetric padding: give it the larger side
+    if (ext->pad_hi[0] > dv.pt) dv.pt = ext->pad_hi[0];
+    if (ext->pad_hi[1] > dv.ph) dv.ph = ext->pad_hi[1];
+    if (ext->pad_hi[2] > dv.pw) dv.pw = ext->pad_hi[2];
+    if (int e = validate_conv(&dv)) return e;
+  } else if (int e = validate_conv(d)) return e;
   if (x == nullptr || w_packed == nullptr || y == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if ((scale == nullptr) != (shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "scale and shift must be given together");
   if ((d->flags & FVT_CONV_RESIDUAL) && residual == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_RESIDUAL without a residual tensor");
   if ((d->flags & FVT_CONV_STATS) && stats == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_STATS without a stats buffer");
+  if ((d->flags & FVT_CONV_STATS) && scale != nullptr)
+    return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_STATS describes the RAW convolution output (training forward): scale/shift must be NULL");
+  if ((d->flags & FVT_CONV_STATS) && (((uintptr_t)stats) & 7)) return set_error(FVT_ERR_MISALIGNED, "stats accumulators must be 8-byte aligned");
   if (((uintptr_t)x | (uintptr_t)w_packed) & 15) return set_error(FVT_ERR_MISALIGNED, "x / w_packed must be 16-byte aligned");
   if (((uintptr_t)y | (uintptr_t)residual) & 31) return set_error(FVT_ERR_MISALIGNED, "y / residual must be 32-byte aligned (256-bit epilogue accesses)");
-  int st = 0;
-  const DeviceInfo* di = current_device_info(&st);
-  if (di == nullptr) return st;
 
   int to, ho, wo;
   conv_out_shape(d, &to, &ho, &wo);
+  if (ext != nullptr) {
+    if (d->flags & FVT_CONV_STATS) return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_fwd_ex: no statistics epilogue");
+    for (int a = 0; a < 3; ++a)
+      if (ext->pad_hi[a] < 0 || ext->pad_hi[a] > 15 || ext->out_stride[a] < 1 || ext->out_offset[a] < 0)
+        return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_fwd_ex: bad pad_hi / out_stride / out_offset");
+    to = (d->t + d->pt + ext->pad_hi[0] - d->kt) / d->st + 1;
+    ho = (d->h + d->ph + ext->pad_hi[1] - d->kh) / d->sh + 1;
+    wo = (d->w + d->pw + ext->pad_hi[2] - d->kw) / d->sw + 1;
+    if (to < 1 || ho < 1 || wo < 1) return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_fwd_ex: empty output");
+    if ((to - 1) * ext->out_stride[0] + ext->out_offset[0] >= ext->out_extent[0] ||
+        (ho - 1) * ext->out_stride[1] + ext->out_offset[1] >= ext->out_extent[1] ||
+        (wo - 1) * ext->out_stride[2] + ext->out_offset[2] >= ext->out_extent[2])
+      return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_fwd_ex: output lattice (%d,%d,%d) leaves the %dx%dx%d tensor", to, ho, wo,
+                       ext->out_extent[0], ext->out_extent[1], ext->out_extent[2]);
+  }
   const int bn = pick_block_n(d);
   const int rows = weight_rows(d, bn);
   const int taps = d->kt * d->kh * d->kw;
 
   // ---- K1s: stride-1 'same' spatial convs with <= 128 input channels load each input row once (conv_slab.cuh)
-  if (!g_disable_slab && d->kt == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && (d->kh > 1 || d->kw > 1) &&
+  if (ext == nullptr && !o.disable_slab && d->kt == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && (d->kh > 1 || d->kw > 1) &&
       2 * d->ph == d->kh - 1 && 2 * d->pw == d->kw - 1 && d->cin <= 192 && d->w + 2 * d->pw <= 128) {
     SlabParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -700,7 +883,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     const int b_slab = bn * 128;
     const int b_all = taps * sp.cin_blocks;
     const bool want_stats = (d->flags & FVT_CONV_STATS) != 0;
-    const int aux = (512 + 2 * rows * 4 + (want_stats ? 2 * bn * 4 : 0) + 255) / 256 * 256;
+    const int aux = (512 + (want_stats ? 8 : 2) * rows * 4 + 255) / 256 * 256;      // statistics: [4 quadrants][2][rows] partials
     const int kSmemMax = 227 * 1024;
     bool ok = useful >= 0.6 && sp.r_in * sp.wp <= slot_rows && sp.r_in <= 256;
     if (ok) {
@@ -708,7 +891,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
         sp.b_stationary = 1;
         sp.b_ring = b_all;
         sp.stages = (kSmemMax - aux - b_all * b_slab) / stage_bytes;
-      } else if (g_slab_single_stage && sp.num_n_tiles == 1 && b_all <= kSlabMaxBRing &&
+      } else if (o.slab_single_stage && sp.num_n_tiles == 1 && b_all <= kSlabMaxBRing &&
                  b_all * b_slab + stage_bytes + aux <= kSmemMax) {
         // the filter fits beside ONE input stage: resident weights + L2-prefetched single-stage input beats re-streaming
         // the whole filter for every tile
@@ -722,7 +905,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
         // A weight slab is consumed in <= 4 MMAs (256-300 clk) but takes > 1000 clk to arrive: a shallow weight ring
         // starves the tensor pipe (measured on the 144 -> 64 data-gradient conv).  Trade the second input stage for
         // ring depth when the ring would be shallower than 5 slabs.
-        if (sp.b_ring < 5 && g_slab_single_stage) {
+        if (sp.b_ring < 5 && o.slab_single_stage) {
           sp.stages = 1;
           sp.b_ring = (kSmemMax - aux - stage_bytes) / b_slab;
         }
@@ -732,7 +915,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       if (sp.stages > kSlabMaxStages) sp.stages = kSlabMaxStages;
     }
     if (ok) {
-      sp.cout_store = d->cout; sp.flags = d->flags | g_debug_flags;
+      sp.cout_store = d->cout; sp.flags = d->flags | o.debug_flags;
       sp.scale = scale; sp.shift = shift; sp.residual = (const __nv_bfloat16*)residual;
       sp.y = (__nv_bfloat16*)y; sp.stats = stats;
       const int smem_bytes = sp.b_ring * b_slab + sp.stages * stage_bytes + aux;
@@ -740,8 +923,8 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)sp.frames};
       const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w, (cuuint64_t)d->cin * 2 * d->w * d->h};
       sp.box_rows = sp.r_in;
-      if (g_slab_box_rows > 0 && g_slab_box_rows < sp.r_in && sp.r_in % g_slab_box_rows == 0) sp.box_rows = g_slab_box_rows;
-      sp.prefetch_dist = g_slab_prefetch > 0 ? g_slab_prefetch : 0;
+      if (o.slab_box_rows > 0 && o.slab_box_rows < sp.r_in && sp.r_in % o.slab_box_rows == 0) sp.box_rows = o.slab_box_rows;
+      sp.prefetch_dist = o.slab_prefetch > 0 ? o.slab_prefetch : 0;
       const cuuint32_t box[4] = {64, (cuuint32_t)sp.wp, (cuuint32_t)sp.box_rows, 1};
       const cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
@@ -755,8 +938,8 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       //      one N tile per cluster, conv2_x data gradient 144 -> 64); "slab_pair" forces it for single-SM-stationary layers.
       const bool pair_shape_ok = bn % 16 == 0 && sp.box_rows == sp.r_in && !(want_stats && scale != nullptr) &&
                                  di->sm_count % 2 == 0 && (di->sm_count / 2) % sp.num_n_tiles == 0;
-      const bool pair_forced = g_slab_pair && sp.b_stationary && sp.num_n_tiles == 1;
-      const bool pair_auto = g_slab_pair_auto && !sp.b_stationary;
+      const bool pair_forced = o.slab_pair && sp.b_stationary && sp.num_n_tiles == 1;
+      const bool pair_auto = o.slab_pair_auto && !sp.b_stationary;
       if (pair_shape_ok && (pair_forced || pair_auto)) {
         SlabPairParams pp;
         memset(&pp, 0, sizeof(pp));
@@ -766,9 +949,9 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
         pp.w_chunks = 1; pp.w_tile = d->w;
         const int num_m_tiles = sp.frames * sp.tiles_per_frame;
         pp.num_pairs = (num_m_tiles + 1) / 2;
-        pp.tma_store = (pair_forced && g_slab_pair == 1 && bn == d->cout) ? 1 : 0;
+        pp.tma_store = (pair_forced && o.slab_pair == 1 && bn == d->cout) ? 1 : 0;
         pp.out_tile_bytes = (sp.r_out * d->w * d->cout * 2 + 1023) / 1024 * 1024;
-        const int aux2 = (512 + 8 * rows + 255) / 256 * 256;
+        const int aux2 = (512 + (want_stats ? 32 : 8) * rows + 255) / 256 * 256;
         const int b_bytes = (b_all * pp.n_half * 128 + 1023) / 1024 * 1024;
         const int out_bytes = pp.tma_store ? 2 * pp.out_tile_bytes : 0;
         int stages2 = (kSmemMax - aux2 - b_bytes - out_bytes) / sp.slab_slot_bytes;      // ring slots of one 64-channel block
@@ -786,14 +969,6 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (ry != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(slab pair y) failed (CUresult %d)", (int)ry);
-          }
-          static bool attr_set_p[16] = {false};
-          int devp = 0;
-          cudaGetDevice(&devp);
-          if (!attr_set_p[devp]) {
-            cudaError_t e = cudaFuncSetAttribute(conv_slab_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-            if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_pair_kernel): %s", cudaGetErrorString(e));
-            attr_set_p[devp] = true;
           }
           const int smem2 = b_bytes + stages2 * sp.slab_slot_bytes + out_bytes + aux2;
           int clusters = di->sm_count / 2;                                                // a multiple of n_tiles (checked above)
@@ -813,19 +988,9 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
           return check_launch("conv_slab_pair_kernel");
         }
       }
-      static bool attr_set_s[16] = {false};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (!attr_set_s[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_slab_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(conv_slab_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_fwd_kernel): %s", cudaGetErrorString(e));
-        attr_set_s[dev] = true;
-      }
       const int m_tiles = sp.frames * sp.tiles_per_frame;
       const int grid = m_tiles < di->sm_count ? m_tiles : di->sm_count;
-      if (g_slab_epi_warps == 16)
+      if (o.slab_epi_warps == 16)
         conv_slab_fwd_kernel<16><<<grid, kSlabThreadsWide, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
       else
         conv_slab_fwd_kernel<8><<<grid, kSlabThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
@@ -836,14 +1001,14 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   // ---- K1s2 (temporal): stride-1 kt x 1 x 1 convs whose filter fits two SMs but not one (conv3_x 288 -> 128 and its data
   //      gradient) on the CTA-pair slab kernel: image rows = frames, image columns = H*W positions, 16 frames x 8 positions per
   //      tile (taps = shifted descriptors, frames outside the clip = TMA zero fill), filter stationary, one N tile per cluster
-  if (g_slab_pair_auto && !g_disable_slab && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 &&
+  if (ext == nullptr && o.slab_pair_auto && !o.disable_slab && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 &&
       d->sw == 1 && d->ph == 0 && d->pw == 0 && 2 * d->pt == d->kt - 1 && d->cin > 64 && bn % 16 == 0 &&
       di->sm_count % 2 == 0 && (di->sm_count / 2) % (rows / bn) == 0 && !((d->flags & FVT_CONV_STATS) && scale != nullptr)) {
     const int kSmemMax = 227 * 1024;
     const int cin_blocks = (d->cin + 63) / 64;
     // would K1i (single SM, every input frame read exactly once) take it?  then leave it there
     const bool tis_fits = rows == bn && d->h * d->w >= 128 &&
-                          d->kt * cin_blocks * bn * 128 + (512 + 16 * bn + 255) / 256 * 256 + 3 * cin_blocks * 128 * 128 <= kSmemMax;
+                          d->kt * cin_blocks * bn * 128 + (512 + 40 * bn + 255) / 256 * 256 + 3 * cin_blocks * 128 * 128 <= kSmemMax;
     int r_out = 16;
     while (r_out > d->t) r_out >>= 1;
     SlabParams sp;
@@ -861,13 +1026,13 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     sp.slab_slot_bytes = (slot_rows * 128 + 1023) / 1024 * 1024;
     sp.slab_tx_bytes = sp.wp * sp.r_in * 128;
     sp.box_rows = sp.r_in;
-    sp.prefetch_dist = g_slab_prefetch > 0 ? g_slab_prefetch : 0;
-    sp.cout_store = d->cout; sp.flags = d->flags | g_debug_flags;
+    sp.prefetch_dist = o.slab_prefetch > 0 ? o.slab_prefetch : 0;
+    sp.cout_store = d->cout; sp.flags = d->flags | o.debug_flags;
     sp.scale = scale; sp.shift = shift; sp.residual = (const __nv_bfloat16*)residual;
     sp.y = (__nv_bfloat16*)y; sp.stats = stats;
     const int b_all = d->kt * cin_blocks;
     const int b_bytes = (b_all * (bn / 2) * 128 + 1023) / 1024 * 1024;
-    const int aux2 = (512 + 8 * rows + 255) / 256 * 256;
+    const int aux2 = (512 + ((d->flags & FVT_CONV_STATS) ? 32 : 8) * rows + 255) / 256 * 256;
     int stages2 = (kSmemMax - aux2 - b_bytes) / sp.slab_slot_bytes;
     if (stages2 > kPairMaxStages) stages2 = kPairMaxStages;
     const double useful = (double)d->t * sp.w / ((double)row_tiles * r_out * w_chunks * w_tile);
@@ -875,7 +1040,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     // the generic kernel is as fast or faster (measured at batch 4: 24.0 vs 24.2 us, data gradient 24.9 vs 27.7 us)
     const long long pair_items = ((long long)sp.frames * sp.tiles_per_frame + 1) / 2 * sp.num_n_tiles;
     if (!tis_fits && b_bytes + aux2 < kSmemMax && stages2 >= 3 && sp.w >= w_tile && useful >= 0.6 &&
-        (pair_items >= 6ll * (di->sm_count / 2) || g_slab_pair_auto == 2)) {
+        (pair_items >= 6ll * (di->sm_count / 2) || o.slab_pair_auto == 2)) {
       sp.stages = stages2; sp.b_ring = b_all;
       SlabPairParams pp;
       memset(&pp, 0, sizeof(pp));
@@ -893,14 +1058,6 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(temporal pair x) failed (CUresult %d)", (int)r);
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, pp.n_half, &tmw2)) return e;
-      static bool attr_set_tp[16] = {false};
-      int devp = 0;
-      cudaGetDevice(&devp);
-      if (!attr_set_tp[devp]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_slab_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_slab_pair_kernel): %s", cudaGetErrorString(e));
-        attr_set_tp[devp] = true;
-      }
       int clusters = di->sm_count / 2;
       if (pp.num_pairs * pp.n_tiles < clusters) clusters = pp.num_pairs * pp.n_tiles;
       cudaLaunchConfig_t cfg;
@@ -921,7 +1078,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
 
   // ---- K1i: stride-1 temporal convs with several channel blocks whose filter fits in shared memory: input-stationary
   //      (each input frame block is loaded once, multiplied by all kt taps into rotating TMEM accumulators)
-  if (!g_disable_tis && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 &&
+  if (ext == nullptr && !o.disable_temporal_is && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 &&
       d->ph == 0 && d->pw == 0 && 2 * d->pt == d->kt - 1 && rows == bn && d->h * d->w >= 128 && d->cin > 64) {
     TemporalIsParams tp;
     memset(&tp, 0, sizeof(tp));
@@ -933,12 +1090,12 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     tp.acc_slots = 512 / bn;
     if (tp.acc_slots > kTisMaxAcc) tp.acc_slots = kTisMaxAcc;
     const int kSmemMax = 227 * 1024;
-    const int aux = (512 + 16 * bn + 255) / 256 * 256;
+    const int aux = (512 + 40 * bn + 255) / 256 * 256;               // scale/shift + [4 quadrants][2][bn] statistics partials
     const int w_bytes = d->kt * tp.cin_blocks * bn * 128;
     const int stage_bytes = tp.cin_blocks * 128 * 128;
     // TMA-store epilogue for one-row-is-one-line outputs (64 channels): two [128 x 128 B] staging tiles, paid for with
     // one pipeline stage (a stage is released as soon as its frame's MMAs are issued, two are enough to stream)
-    tp.tma_store = (!g_disable_tis_tma_store && bn == 64 && d->cout == 64 &&
+    tp.tma_store = (!o.disable_tis_tma_store && bn == 64 && d->cout == 64 &&
                     w_bytes + aux + 2 * kTisOutTileBytes + 2 * stage_bytes <= kSmemMax) ? 1 : 0;
     const int out_bytes = tp.tma_store ? 2 * kTisOutTileBytes : 0;
     int stages = (kSmemMax - aux - w_bytes - out_bytes) / stage_bytes;
@@ -953,7 +1110,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       tp.chunks_per_clip = chunks;
       tp.t_chunk = d->t / chunks;
       tp.num_items = d->n * chunks * tp.blocks_per_frame;
-      tp.cout_store = d->cout; tp.flags = d->flags | g_debug_flags;
+      tp.cout_store = d->cout; tp.flags = d->flags | o.debug_flags;
       tp.scale = scale; tp.shift = shift; tp.residual = (const __nv_bfloat16*)residual;
       tp.y = (__nv_bfloat16*)y; tp.stats = stats;
       CUtensorMap tmx, tmw;
@@ -975,14 +1132,6 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (ry != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(temporal-is y) failed (CUresult %d)", (int)ry);
       }
-      static bool attr_set_t[16] = {false};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (!attr_set_t[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_temporal_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_temporal_is_kernel): %s", cudaGetErrorString(e));
-        attr_set_t[dev] = true;
-      }
       const int smem_bytes = w_bytes + stages * stage_bytes + out_bytes + aux;
       const int grid = tp.num_items < di->sm_count ? tp.num_items : di->sm_count;
       conv_temporal_is_kernel<<<grid, kTisThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, tmy, tp);
@@ -992,7 +1141,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
 
   // ---- K1t: stride-1 temporal convs whose whole filter fits in shared memory walk a 128-pixel block through time and
   //      load every input frame block once (conv_frame_ring.cuh)
-  if (!g_disable_ring && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 &&
+  if (ext == nullptr && !o.disable_frame_ring && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 &&
       d->ph == 0 && d->pw == 0 && 2 * d->pt == d->kt - 1 && rows == bn && d->h * d->w >= 128) {
     FrameRingParams rp;
     memset(&rp, 0, sizeof(rp));
@@ -1002,7 +1151,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     rp.cin_blocks = (d->cin + 63) / 64; rp.cin_k16 = d->cin / 16; rp.k_per_tap = d->cin;
     rp.n_tile = bn;
     const int kSmemMax = 227 * 1024;
-    const int aux = (320 + 16 * bn + 255) / 256 * 256;
+    const int aux = (320 + 40 * bn + 255) / 256 * 256;
     const int w_bytes = d->kt * rp.cin_blocks * bn * 128;
     int slots = (kSmemMax - aux - w_bytes) / kRingBlockBytes;
     if (slots > kRingMaxSlots) slots = kRingMaxSlots;
@@ -1011,7 +1160,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     // 4.6 vs 3.8 TB/s on 64 -> 64) and loses to K1's 8-stage pipeline when only the kt resident frames fit (144 -> 64).
     if (w_bytes + aux < kSmemMax && rp.cin_blocks == 1 && bn <= 64 && slots >= d->kt + 4 && useful >= 0.6) {
       rp.slots = slots;
-      rp.prefetch_frames = g_ring_prefetch;
+      rp.prefetch_frames = o.ring_prefetch;
       // split the T axis so that there are >= 2 work items per SM (each item re-reads kt-1 halo frames)
       int chunks = 1;
       while (chunks * 2 <= d->t && d->t % (chunks * 2) == 0 && d->n * rp.blocks_per_frame * chunks < 2 * di->sm_count &&
@@ -1020,7 +1169,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
       rp.chunks_per_clip = chunks;
       rp.t_chunk = d->t / chunks;
       rp.num_items = d->n * chunks * rp.blocks_per_frame;
-      rp.cout_store = d->cout; rp.flags = d->flags | g_debug_flags;
+      rp.cout_store = d->cout; rp.flags = d->flags | o.debug_flags;
       rp.scale = scale; rp.shift = shift; rp.residual = (const __nv_bfloat16*)residual;
       rp.y = (__nv_bfloat16*)y; rp.stats = stats;
       CUtensorMap tmx, tmw;
@@ -1033,14 +1182,6 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(frame ring x) failed (CUresult %d)", (int)r);
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
-      static bool attr_set_r[16] = {false};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (!attr_set_r[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_frame_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_frame_ring_kernel): %s", cudaGetErrorString(e));
-        attr_set_r[dev] = true;
-      }
       const int smem_bytes = w_bytes + slots * kRingBlockBytes + aux;
       const int grid = rp.num_items < di->sm_count ? rp.num_items : di->sm_count;
       conv_frame_ring_kernel<<<grid, kRingThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, rp);
@@ -1062,21 +1203,28 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   p.num_m_tiles = (p.m_total + kBlockM - 1) / kBlockM;
   p.num_n_tiles = rows / bn;
   p.cout_store = d->cout;
-  p.flags = d->flags | g_debug_flags;
+  p.flags = d->flags | o.debug_flags;
   p.scale = scale; p.shift = shift;
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;
   p.stats = stats;
+  if (ext != nullptr) {
+    p.om_on = 1;
+    p.om_t = ext->out_extent[0]; p.om_h = ext->out_extent[1]; p.om_w = ext->out_extent[2];
+    p.om_st = ext->out_stride[0]; p.om_sh = ext->out_stride[1]; p.om_sw = ext->out_stride[2];
+    p.om_t0 = ext->out_offset[0]; p.om_h0 = ext->out_offset[1]; p.om_w0 = ext->out_offset[2];
+  }
 
   const int b_tile_bytes = bn * kBlockK * 2;
   int stage_bytes = kATileBytes + b_tile_bytes;
-  const int kAuxBytes = 4096 + 2 * kMaxCout * 4;   // barriers + stats partials + staged scale/shift
+  // barriers + staged scale/shift [2][kMaxCout] — or, for the training forward, statistics partials [4 quadrants][2][rows]
+  const int kAuxBytes = 4096 + (((d->flags & FVT_CONV_STATS) && 8 * rows > 2 * kMaxCout) ? 8 * rows * 4 : 2 * kMaxCout * 4);
   const int budget = 227 * 1024 - 1024 - kAuxBytes;
   // Small filters (one N tile, all taps*cin_blocks weight tiles + >= 4 A stages fit): keep the weights resident in
   // shared memory for the CTA's lifetime instead of re-fetching them from L2 with every 128-pixel tile.
   const int b_all_bytes = taps * p.cin_blocks * b_tile_bytes;
   int b_region = 0;
-  if (!g_disable_bstat && p.num_n_tiles == 1 && p.num_m_tiles > di->sm_count && b_all_bytes + 4 * kATileBytes <= budget) {
+  if (!o.disable_b_stationary && p.num_n_tiles == 1 && p.num_m_tiles > di->sm_count && b_all_bytes + 4 * kATileBytes <= budget) {
     p.b_stationary = 1;
     b_region = b_all_bytes;
     stage_bytes = kATileBytes;
@@ -1088,18 +1236,21 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   const int smem_bytes = 1024 + b_region + stages * stage_bytes + kAuxBytes;
 
   // split-K: a small-M convolution (conv4_x/conv5_x at a few clips per GPU) has fewer tiles than SMs and a long
-  // reduction; splitting K over several CTAs fills the machine.  Needs the caller's zeroed fp32 workspace.
+  // reduction; splitting K over several CTAs fills the machine.  Every split stores its fp32 partial tile into its own
+  // [M][Cout] slice of the caller's workspace and the finalize pass adds the slices in split order (deterministic; the
+  // workspace needs no zeroing).  The number of splits is capped by what the workspace holds.
   p.k_splits = 1;
   p.kb_per_split = taps * p.cin_blocks;
   {
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int k_blocks = taps * p.cin_blocks;
-    const size_t need = (size_t)p.m_total * d->cout * sizeof(float);
-    if (!g_disable_splitk && !p.b_stationary && workspace != nullptr && workspace_bytes >= need && ((uintptr_t)workspace & 15) == 0 &&
+    const size_t slice = (size_t)p.m_total * d->cout * sizeof(float);
+    if (ext == nullptr && !o.disable_split_k && !p.b_stationary && workspace != nullptr && workspace_bytes >= 2 * slice && ((uintptr_t)workspace & 15) == 0 &&
         2 * tiles <= di->sm_count && k_blocks >= 8) {
       int splits = di->sm_count / tiles;
       if (splits > k_blocks / 4) splits = k_blocks / 4;
       if (splits > 8) splits = 8;
+      if ((size_t)splits > workspace_bytes / slice) splits = (int)(workspace_bytes / slice);
       if (splits >= 2) {
         p.kb_per_split = (k_blocks + splits - 1) / splits;
         p.k_splits = (k_blocks + p.kb_per_split - 1) / p.kb_per_split;
@@ -1109,7 +1260,7 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   }
 
   CUtensorMap tmx, tmw;
-  if (int e = encode_x_map(di, d, x, &tmx)) return e;
+  if (int e = encode_x_map(di, d, x, &tmx, ext != nullptr ? ext->pad_hi : nullptr)) return e;
 
   // ---- K1p: streamed-weight layers with at least a few rounds of tile pairs run on CTA pairs (cta_group::2, M = 256):
   //      each CTA loads its own im2col tile and HALF of the weight tile, which takes 30-40 % off the per-SM smem fill
@@ -1120,19 +1271,11 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
     if (stages2 > kMaxStages) stages2 = kMaxStages;
     const long long items = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const bool stats_with_affine = (d->flags & FVT_CONV_STATS) && scale != nullptr;
-    if (g_igemm_pair && !p.b_stationary && p.k_splits == 1 && bn >= 128 && di->sm_count % 2 == 0 && stages2 >= 3 &&
-        !stats_with_affine && (items >= 3ll * (di->sm_count / 2) || g_igemm_pair == 2)) {
+    if (ext == nullptr && o.igemm_pair && !p.b_stationary && p.k_splits == 1 && bn >= 128 && di->sm_count % 2 == 0 && stages2 >= 3 &&
+        !stats_with_affine && (items >= 3ll * (di->sm_count / 2) || o.igemm_pair == 2)) {
       ConvKernelParams pp = p;
       pp.stages = stages2;
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, n_half, &tmw)) return e;
-      static bool attr_set_ip[16] = {false};
-      int devp = 0;
-      cudaGetDevice(&devp);
-      if (!attr_set_ip[devp]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_pair_kernel): %s", cudaGetErrorString(e));
-        attr_set_ip[devp] = true;
-      }
       int clusters = di->sm_count / 2;
       if (items < clusters) clusters = (int)items;
       cudaLaunchConfig_t cfg;
@@ -1152,29 +1295,36 @@ int fvt_conv3d_fwd(const fvt_conv_desc* d, const void* x, const void* w_packed, 
   }
   if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
 
-  static bool attr_set[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_fwd_kernel): %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
-  }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < di->sm_count ? tiles : di->sm_count;
   conv_igemm_fwd_kernel<<<grid, kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p);
   if (int e = check_launch("conv_igemm_fwd_kernel")) return e;
   if (p.k_splits > 1)
-    return launch_splitk_finalize(p.ws, scale, shift, (d->flags & FVT_CONV_RESIDUAL) ? residual : nullptr, y, (d->flags & FVT_CONV_STATS) ? stats : nullptr,
-                                  (size_t)p.m_total, d->cout, (d->flags & FVT_CONV_RELU) ? 1 : 0, (cudaStream_t)stream);
+    return launch_splitk_finalize(p.ws, p.k_splits, scale, shift, (d->flags & FVT_CONV_RESIDUAL) ? residual : nullptr, y,
+                                  (d->flags & FVT_CONV_STATS) ? stats : nullptr, (size_t)p.m_total, d->cout,
+                                  (d->flags & FVT_CONV_RELU) ? 1 : 0, (cudaStream_t)stream);
   return 0;
 }
 
 
+extern "C" {
+
+int fvt_conv3d_fwd(fvt_handle_t handle, const fvt_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                   const float* shift, const void* residual, void* y, void* stats_acc, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  return conv3d_fwd_impl(handle, d, x, w_packed, scale, shift, residual, y, stats_acc, workspace, workspace_bytes, stream, nullptr);
+}
+
+int fvt_conv3d_fwd_ex(fvt_handle_t handle, const fvt_conv_desc* d, const fvt_conv_ext* ext, const void* x, const void* w_packed,
+                      const float* scale, const float* shift, const void* residual, void* y, void* stream) {
+  if (ext == nullptr) return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_fwd_ex: null ext");
+  return conv3d_fwd_impl(handle, d, x, w_packed, scale, shift, residual, y, nullptr, nullptr, 0, stream, ext);
+}
+
 // ------------------------------------------------------------------------------------------------ K2f: fused (2+1)D unit
 // Geometry of the fused unit for a (spatial, temporal) descriptor pair; returns 0 and fills *up / *smem_bytes when the
 // pair is eligible, a negative status (error text set) otherwise.
-static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt_conv_desc* dt, UnitFusedParams* up, int* smem_bytes, int* use_is) {
+static int plan_unit2p1(const DeviceInfo* di, const Options& o, const fvt_conv_desc* ds, const fvt_conv_desc* dt, UnitFusedParams* up, int* smem_bytes, int* use_is) {
   if (int e = validate_conv(ds)) return e;
   if (int e = validate_conv(dt)) return e;
   const bool spatial_ok = ds->kt == 1 && (ds->kh & 1) && (ds->kw & 1) && ds->kh * ds->kw > 1 && ds->kh <= 7 && ds->kw <= 7 &&
@@ -1211,7 +1361,7 @@ static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt
   u.n_mid = n_mid; u.n_out = 64;
   u.mid_blocks = (n_mid + 63) / 64; u.mid_k16 = n_mid / 16;
   // input-stationary form: temporal filter as five 32-row blocks per K block (every tap rotation is a contiguous window)
-  *use_is = g_unit_is && n_mid % 48 == 0;
+  *use_is = o.unit_input_stationary && n_mid % 48 == 0;
   const int s_taps = ds->kh * ds->kw;
   if (!*use_is && s_taps != 9) return set_error(FVT_ERR_BAD_DESC, "fused unit: only the input-stationary form (mid a multiple of 48) handles filters other than 3x3");
   const int bt_bytes = *use_is ? u.mid_blocks * 5 * 32 * 128 : (3 * u.mid_blocks * 32 * 128 + 1023) / 1024 * 1024;
@@ -1227,25 +1377,26 @@ static int plan_unit2p1(const DeviceInfo* di, const fvt_conv_desc* ds, const fvt
   return 0;
 }
 
-int fvt_unit2p1_supported(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal) {
+int fvt_unit2p1_supported(fvt_handle_t handle, const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal) {
   int st = 0;
-  const DeviceInfo* di = current_device_info(&st);
+  const DeviceInfo* di = handle_device(handle, &st);
   if (di == nullptr) return st;
   UnitFusedParams u;
   int smem = 0, use_is = 0;
-  return plan_unit2p1(di, d_spatial, d_temporal, &u, &smem, &use_is) == 0 ? 1 : 0;
+  return plan_unit2p1(di, handle->opt, d_spatial, d_temporal, &u, &smem, &use_is) == 0 ? 1 : 0;
 }
 
-int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal, const void* x,
+int fvt_unit2p1_fwd(fvt_handle_t handle, const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_temporal, const void* x,
                     const void* w_spatial_packed, const float* scale_mid, const float* shift_mid,
                     const void* w_temporal_packed, const float* scale_out, const float* shift_out,
                     const void* residual, void* y, void* stream) {
   int st = 0;
-  const DeviceInfo* di = current_device_info(&st);
+  const DeviceInfo* di = handle_device(handle, &st);
   if (di == nullptr) return st;
+  const Options& o = handle->opt;
   UnitFusedParams u;
   int smem_bytes = 0, use_is = 0;
-  if (int e = plan_unit2p1(di, d_spatial, d_temporal, &u, &smem_bytes, &use_is)) return e;
+  if (int e = plan_unit2p1(di, o, d_spatial, d_temporal, &u, &smem_bytes, &use_is)) return e;
   if (x == nullptr || w_spatial_packed == nullptr || w_temporal_packed == nullptr || y == nullptr)
     return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (scale_mid == nullptr || shift_mid == nullptr || scale_out == nullptr || shift_out == nullptr)
@@ -1255,7 +1406,7 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
   if (((uintptr_t)x | (uintptr_t)w_spatial_packed | (uintptr_t)w_temporal_packed) & 15)
     return set_error(FVT_ERR_MISALIGNED, "x / packed weights must be 16-byte aligned");
   if (((uintptr_t)y | (uintptr_t)residual) & 31) return set_error(FVT_ERR_MISALIGNED, "y / residual must be 32-byte aligned (256-bit epilogue accesses)");
-  u.flags = (has_res ? kConvResidual : 0) | g_debug_flags;
+  u.flags = (has_res ? kConvResidual : 0) | o.debug_flags;
   u.scale_mid = scale_mid; u.shift_mid = shift_mid; u.scale_out = scale_out; u.shift_out = shift_out;
   u.residual = (const __nv_bfloat16*)residual; u.y = (__nv_bfloat16*)y;
 
@@ -1272,15 +1423,6 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
   if (int e = encode_w_map(di, w_spatial_packed, u.kh * u.kw * 64, u.n_mid, u.n_mid / 2, &tmws)) return e;
   if (int e = encode_w_map(di, w_temporal_packed, 3 * u.n_mid, 64, 32, &tmwt)) return e;
 
-  static bool attr_set_u[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set_u[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(unit2p1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(unit2p1_fused_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(unit2p1_fused_kernel): %s", cudaGetErrorString(e));
-    attr_set_u[dev] = true;
-  }
   // every cluster takes an equal share of the output frames; tiny problems keep whole units (a split costs a halo frame per side)
   int clusters = di->sm_count / 2;
   if (u.total_steps < 8ll * clusters) clusters = u.num_units < clusters ? u.num_units : clusters;
@@ -1300,19 +1442,25 @@ int fvt_unit2p1_fwd(const fvt_conv_desc* d_spatial, const fvt_conv_desc* d_tempo
   return check_launch("unit2p1_fused_kernel");
 }
 
-int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
-                     int32_t cin_real, void* stream) {
+}  // extern "C"
+
+// plan_bytes != nullptr: dry run — reports the workspace the launch would like (bytes) and launches nothing.
+static int conv3d_wgrad_impl(fvt_handle_t handle, const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
+                             int32_t cin_real, void* workspace, size_t workspace_bytes, void* stream, size_t* plan_bytes) {
+  int st = 0;
+  const DeviceInfo* di = handle_device(handle, &st);
+  if (di == nullptr) return st;
+  const Options& o = handle->opt;
   if (int e = validate_conv(d)) return e;
-  if (x == nullptr || dy == nullptr || dw == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (cout_real <= 0 || cout_real > d->cout || cin_real <= 0 || cin_real > d->cin)
     return set_error(FVT_ERR_BAD_DESC, "real filter counts exceed stored");
-  if (((uintptr_t)x | (uintptr_t)dy) & 15) return set_error(FVT_ERR_MISALIGNED, "tensor pointers must be 16-byte aligned");
-  int st = 0;
-  const DeviceInfo* di = current_device_info(&st);
-  if (di == nullptr) return st;
+  if (plan_bytes == nullptr) {
+    if (x == nullptr || dy == nullptr || dw == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
+    if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) return set_error(FVT_ERR_MISALIGNED, "tensor pointers must be 16-byte aligned");
+  }
   {
-    int r = try_wgrad_slab(di, d, x, dy, dw, cout_real, cin_real, (cudaStream_t)stream);
-    if (r == 0) r = try_wgrad_temporal(di, d, x, dy, dw, cout_real, cin_real, (cudaStream_t)stream);
+    int r = try_wgrad_slab(di, o, d, x, dy, dw, cout_real, cin_real, workspace, workspace_bytes, (cudaStream_t)stream, plan_bytes);
+    if (r == 0) r = try_wgrad_temporal(di, o, d, x, dy, dw, cout_real, cin_real, workspace, workspace_bytes, (cudaStream_t)stream, plan_bytes);
     if (r != 0) return r < 0 ? r : 0;
   }
   int to, ho, wo;
@@ -1328,7 +1476,7 @@ int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, floa
   p.taps = d->kt * d->kh * d->kw;
   p.cin_blocks = (d->cin + 63) / 64;
   p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw; p.dbg_no_atomics = g_wgrad_no_atomics; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
+  p.dw = dw; p.dbg_no_store = o.wgrad_no_store; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
   fvt_conv_desc tmp = *d;
   tmp.block_n = 0;
   if (d->cin % 64 != 0 && d->cout % 64 == 0) {
@@ -1348,8 +1496,12 @@ int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, floa
   int splits = (2 * di->sm_count + items - 1) / items;
   if (splits > p.kblocks_total) splits = p.kblocks_total;
   if (splits < 1) splits = 1;
+  const long long dw_elems = (long long)cout_real * cin_real * p.taps;
+  if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)dw_elems * sizeof(float) : 0; return 0; }
+  splits = wgrad_fit_splits(splits, dw_elems, workspace, workspace_bytes);
   p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
   p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.ws = p.splits > 1 ? (float*)workspace : nullptr; p.ws_split_stride = dw_elems;
   const int stage_bytes = (2 + p.n_loads) * kSlabBytes;
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > kWgMaxStages) stages = kWgMaxStages;
@@ -1383,17 +1535,43 @@ int fvt_conv3d_wgrad(const fvt_conv_desc* d, const void* x, const void* dy, floa
     if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeIm2col(dy, wgrad) failed (CUresult %d)", (int)r);
     if (di->driver_version <= 13010 && (size_t)d->cout * 2 * wo * ho * to * d->n < 131072) reinterpret_cast<uint64_t*>(&tmdy)[1] &= ~(1ull << 21);
   }
-  static bool attr_set[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return set_error(FVT_ERR_CUDA, "cudaFuncSetAttribute(conv_wgrad_kernel): %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
-  }
   const int grid = items * p.splits;
   conv_wgrad_kernel<<<grid, kWgradThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmdy, p);
-  return check_launch("conv_wgrad_kernel");
+  if (int e = check_launch("conv_wgrad_kernel")) return e;
+  if (p.splits > 1 && !o.wgrad_no_store) return wgrad_reduce(p.ws, dw, dw_elems, p.splits, (cudaStream_t)stream);
+  return 0;
+}
+
+extern "C" {
+
+int fvt_conv3d_wgrad(fvt_handle_t handle, const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
+                     int32_t cin_real, void* workspace, size_t workspace_bytes, void* stream) {
+  return conv3d_wgrad_impl(handle, d, x, dy, dw, cout_real, cin_real, workspace, workspace_bytes, stream, nullptr);
+}
+
+size_t fvt_conv3d_workspace_bytes(fvt_handle_t handle, const fvt_conv_desc* d, int32_t op, int32_t cout_real, int32_t cin_real) {
+  int st = 0;
+  const DeviceInfo* di = handle_device(handle, &st);
+  if (di == nullptr || validate_conv(d)) return 0;
+  if (op == FVT_OP_WGRAD) {
+    size_t bytes = 0;
+    if (conv3d_wgrad_impl(handle, d, nullptr, nullptr, nullptr, cout_real > 0 ? cout_real : d->cout, cin_real > 0 ? cin_real : d->cin,
+                          nullptr, 0, nullptr, &bytes) != 0)
+      return 0;
+    return bytes;
+  }
+  // forward / data gradient: split-K of small-M convolutions on the generic kernel (upper bound: specialised kernels never split)
+  int to, ho, wo;
+  conv_out_shape(d, &to, &ho, &wo);
+  const int bn = pick_block_n(d);
+  const long long m_total = (long long)d->n * to * ho * wo;
+  const int tiles = (int)((m_total + kBlockM - 1) / kBlockM) * (weight_rows(d, bn) / bn);
+  const int k_blocks = d->kt * d->kh * d->kw * ((d->cin + kBlockK - 1) / kBlockK);
+  if (handle->opt.disable_split_k || 2 * tiles > di->sm_count || k_blocks < 8) return 0;
+  int splits = di->sm_count / tiles;
+  if (splits > k_blocks / 4) splits = k_blocks / 4;
+  if (splits > 8) splits = 8;
+  return splits >= 2 ? (size_t)splits * (size_t)m_total * d->cout * sizeof(float) : 0;
 }
 
 }  // extern "C"

@@ -89,7 +89,7 @@ using namespace fvt;
 
 extern "C" {
 
-static int stem_unfold_launch(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+static int stem_unfold_launch(fvt_handle_t handle, const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
                               int32_t sw, int32_t pw, int32_t cu, int hpair, void* stream) {
   if (x_ncdhw == nullptr || u == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (n <= 0 || t <= 0 || h <= 0 || w <= 0 || kw_taps <= 0 || sw <= 0 || pw < 0)
@@ -97,7 +97,7 @@ static int stem_unfold_launch(const float* x_ncdhw, void* u, int32_t n, int32_t 
   if (cu != 32 || kw_taps * 3 > cu) return set_error(FVT_ERR_BAD_DESC, "stem unfold supports cu=32 with 3*kw_taps <= 32");
   if (hpair && (h & 1)) return set_error(FVT_ERR_BAD_DESC, "row-paired stem unfold needs an even height (got %d)", h);
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   const int wo = (w + 2 * pw - kw_taps) / sw + 1;
   const size_t total = static_cast<size_t>(n) * t * h * wo;
   size_t blocks = (total + 255) / 256;
@@ -107,23 +107,23 @@ static int stem_unfold_launch(const float* x_ncdhw, void* u, int32_t n, int32_t 
   return check_launch("stem_unfold_kernel");
 }
 
-int fvt_stem_unfold(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+int fvt_stem_unfold(fvt_handle_t handle, const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
                     int32_t sw, int32_t pw, int32_t cu, void* stream) {
-  return stem_unfold_launch(x_ncdhw, u, n, t, h, w, kw_taps, sw, pw, cu, 0, stream);
+  return stem_unfold_launch(handle, x_ncdhw, u, n, t, h, w, kw_taps, sw, pw, cu, 0, stream);
 }
 
-int fvt_stem_unfold_hpair(const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
+int fvt_stem_unfold_hpair(fvt_handle_t handle, const float* x_ncdhw, void* u, int32_t n, int32_t t, int32_t h, int32_t w, int32_t kw_taps,
                           int32_t sw, int32_t pw, int32_t cu, void* stream) {
-  return stem_unfold_launch(x_ncdhw, u, n, t, h, w, kw_taps, sw, pw, cu, 1, stream);
+  return stem_unfold_launch(handle, x_ncdhw, u, n, t, h, w, kw_taps, sw, pw, cu, 1, stream);
 }
 
-int fvt_pool_fc_fwd(const void* x, int32_t n, int32_t positions, int32_t c, int32_t c_real, const float* w,
+int fvt_pool_fc_fwd(fvt_handle_t handle, const void* x, int32_t n, int32_t positions, int32_t c, int32_t c_real, const float* w,
                     const float* b, int32_t num_class, float* pooled, float* logits, void* stream) {
   if (x == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (n <= 0 || positions <= 0 || c <= 0 || c_real <= 0 || c_real > c) return set_error(FVT_ERR_BAD_DESC, "bad pool/fc extent");
   if (logits != nullptr && (w == nullptr || num_class <= 0)) return set_error(FVT_ERR_BAD_DESC, "logits requested without weights");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   pool_fc_kernel<<<n, 512, c * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, positions, c, c_real, w, b,
                                                                        num_class, pooled, logits);
   return check_launch("pool_fc_kernel");

@@ -22,6 +22,7 @@
 
 #include "../../include/fvt_b200.h"
 #include "host_common.h"
+#include "det_sum.cuh"
 
 namespace fvt {
 
@@ -46,9 +47,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------ K5
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const unsigned long long* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, int c_store, int c_real, float inv_rows, float eps,
+                                   float* __restrict__ running_var, int c_store, int c_real, double inv_rows, float eps,
                                    float momentum, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,8 +58,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
     scale[c] = 0.f; shift[c] = 0.f; mean_out[c] = 0.f; invstd_out[c] = 0.f;
     return;
   }
-  const double m = static_cast<double>(stats[c]) * inv_rows;
-  double v = static_cast<double>(stats[c_store + c]) * inv_rows - m * m;
+  const double m = det_read(stats + static_cast<size_t>(c) * kDetLimbs) * inv_rows;
+  double v = det_read(stats + static_cast<size_t>(c_store + c) * kDetLimbs) * inv_rows - m * m;
   if (v < 0.0) v = 0.0;
   const float inv_std = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
   const float g = gamma[c];
@@ -97,10 +98,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // same arithmetic as bn_finalize_kernel — and CTA 0 also publishes scale/shift/mean/inv_std for the backward pass and
 // updates the running statistics, so the forward pass needs no separate finalize launch.
 struct BnFinalizeArgs {
-  const float* stats; const float* gamma; const float* beta;
+  const unsigned long long* stats; const float* gamma; const float* beta;
   float* running_mean; float* running_var;
   float* scale_out; float* shift_out; float* mean_out; float* invstd_out;
-  int c_real; float inv_rows, eps, momentum;
+  int c_real; double inv_rows; float eps, momentum;
 };
 
 template <int kResMode>
@@ -114,8 +115,8 @@ bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, 
     if (fin.stats != nullptr) {
       float sc = 0.f, sh = 0.f, mf = 0.f, inv_std = 0.f, vf = 0.f;
       if (ch < fin.c_real) {                         // pad channels: identity-zero so they stay exactly 0
-        const double m = static_cast<double>(fin.stats[ch]) * fin.inv_rows;
-        double v = static_cast<double>(fin.stats[c_store + ch]) * fin.inv_rows - m * m;
+        const double m = det_read(fin.stats + static_cast<size_t>(ch) * kDetLimbs) * fin.inv_rows;
+        double v = det_read(fin.stats + static_cast<size_t>(c_store + ch) * kDetLimbs) * fin.inv_rows - m * m;
         if (v < 0.0) v = 0.0;
         inv_std = static_cast<float>(1.0 / sqrt(v + static_cast<double>(fin.eps)));
         const float g = fin.gamma[ch];
@@ -183,14 +184,14 @@ bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, 
 }
 
 // ------------------------------------------------------------------------------------------------ K7a
-// sums[0..C) += sum dz*xhat (dgamma), sums[C..2C) += sum dz (dbeta);  xhat = (raw - mean)*inv_std
+// acc[0..C) += sum dz*(raw - mean)  (dgamma = inv_std * that), acc[C..2C) += sum dz (dbeta) — exact accumulators
 // kMask: 0 no mask, 1 mask tensor (dz = dact * [mask > 0]), 2 ReLU mask recomputed from raw: [raw*scale + shift > 0]
 template <int kMask>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
-                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ mean,
                      const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
-                     float* __restrict__ sums, size_t rows, int cvec, int c_store) {
+                     unsigned long long* __restrict__ acc, size_t rows, int cvec, int c_store) {
   extern __shared__ float sred[];                    // [3][C] constants, then [blockDim.x][16] fold area
   float* cst = sred;
   float* fold = sred + 3 * c_store;
@@ -251,33 +252,37 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ da
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mine[i] = dg[i]; mine[8 + i] = db[i]; }
   __syncthreads();
-  // fold the tpr row-subsets of each channel vector, then one atomic per channel per CTA
+  // fold the tpr row-subsets of each channel vector in a fixed order, then one exact add per channel per CTA
   for (int o = threadIdx.x; o < cvec * 16; o += blockDim.x) {
     const int v = o / 16, k = o % 16;
     float s = 0.f;
     for (int t = 0; t < tpr; ++t) s += fold[(t * cvec + v) * 16 + k];
     const int ch = v * 8 + (k & 7);
-    if (k < 8) s *= invstd[ch];                      // sum dz*(x - mean) -> sum dz*xhat
-    atomicAdd(sums + (k < 8 ? 0 : c_store) + ch, s);
+    det_add(acc + static_cast<size_t>((k < 8 ? 0 : c_store) + ch) * kDetLimbs, s);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ K7b
 // draw = gamma*inv_std*(dz - dbeta/M - xhat*dgamma/M); optionally also writes dz (masked dact) for the shortcut path.
+// Also publishes sums = [dgamma | dbeta] as plain floats (CTA 0).
 template <int kMask, bool kDz>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dact, const uint4* __restrict__ mask,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
-                    const float* __restrict__ sums, uint4* __restrict__ draw, uint4* __restrict__ dz_out, size_t rows,
-                    int cvec, int c_store, int c_real, float inv_rows) {
+                    const unsigned long long* __restrict__ acc, float* __restrict__ sums, uint4* __restrict__ draw,
+                    uint4* __restrict__ dz_out, size_t rows, int cvec, int c_store, int c_real, float inv_rows) {
   extern __shared__ float cst[];      // [6][C]: a = gamma*inv_std, a*dbeta/M, a*inv_std*dgamma/M, mean, relu scale, relu shift
   for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
     const float is = invstd[ch];
     const float a = (ch < c_real ? gamma[ch] : 0.f) * is;
+    // exact sums -> one rounding each: dgamma = inv_std * sum dz*(raw - mean), dbeta = sum dz
+    const float dgamma = static_cast<float>(det_read(acc + static_cast<size_t>(ch) * kDetLimbs)) * is;
+    const float dbeta = static_cast<float>(det_read(acc + static_cast<size_t>(c_store + ch) * kDetLimbs));
+    if (blockIdx.x == 0) { sums[ch] = dgamma; sums[c_store + ch] = dbeta; }
     cst[ch] = a;
-    cst[c_store + ch] = a * sums[c_store + ch] * inv_rows;
-    cst[2 * c_store + ch] = a * is * sums[ch] * inv_rows;
+    cst[c_store + ch] = a * dbeta * inv_rows;
+    cst[2 * c_store + ch] = a * is * dgamma * inv_rows;
     cst[3 * c_store + ch] = mean[ch];
     if (kMask == 2) { cst[4 * c_store + ch] = relu_scale[ch]; cst[5 * c_store + ch] = relu_shift[ch]; }
   }
@@ -365,7 +370,7 @@ zero_insert_kernel(const uint4* __restrict__ dy, uint4* __restrict__ up, int n, 
 
 // ------------------------------------------------------------------------------------------------ head backward
 // dlogits [n, K] fp32, pooled [n, C] fp32 (saved by the forward), w [K, C] fp32:
-//   dw[k, c] += sum_n dlogits[n,k]*pooled[n,c];  db[k] += sum_n dlogits[n,k];
+//   dw[k, c] = sum_n dlogits[n,k]*pooled[n,c];  db[k] = sum_n dlogits[n,k];   (overwritten: grad_req='write')
 //   dx[n, p, c] = (sum_k dlogits[n,k]*w[k,c]) / positions      (bf16, broadcast over the pooled positions)
 __global__ void pool_fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled,
                                    const float* __restrict__ w, int n, int num_class, int c, int positions,
@@ -387,12 +392,12 @@ __global__ void pool_fc_bwd_kernel(const float* __restrict__ dlogits, const floa
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
       float s = 0.f;
       for (int in = 0; in < n; ++in) s = fmaf(dlogits[in * num_class + k], pooled[static_cast<size_t>(in) * c + ch], s);
-      dw[static_cast<size_t>(k) * c + ch] += s;
+      dw[static_cast<size_t>(k) * c + ch] = s;
     }
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int in = 0; in < n; ++in) s += dlogits[in * num_class + k];
-      db[k] += s;
+      db[k] = s;
     }
   }
 }
@@ -422,13 +427,13 @@ sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tensors, const unsigned 
 }
 
 // ------------------------------------------------------------------------------------------------ split-K finalize
-// ws [rows, C] fp32 holds the summed partial tiles of a split-K convolution (conv_igemm.cuh).  This pass is the
-// convolution's epilogue: y = bf16( relu?( ws*scale + shift  + residual ) ), optional per-channel (sum, sum^2) of the
-// bf16-rounded raw output for training BatchNorm; it also writes zeros back so the workspace is clean for the next call.
+// ws [splits][rows, C] fp32 holds the partial tiles of a split-K convolution (conv_igemm.cuh), one slice per split.  This
+// pass is the convolution's epilogue: y = bf16( relu?( (sum of the slices in split order)*scale + shift + residual ) ),
+// optional per-channel (sum, sum^2) of the bf16-rounded raw output for training BatchNorm (exact accumulators).
 __global__ void __launch_bounds__(256)
-splitk_finalize_kernel(float4* __restrict__ ws, const float* __restrict__ scale, const float* __restrict__ shift,
-                       const uint4* __restrict__ res, uint4* __restrict__ y, float* __restrict__ stats, size_t rows, int cvec,
-                       int c_store, int relu) {
+splitk_finalize_kernel(const float4* __restrict__ ws, int splits, size_t slice_vec4, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const uint4* __restrict__ res, uint4* __restrict__ y,
+                       unsigned long long* __restrict__ stats, size_t rows, int cvec, int c_store, int relu) {
   extern __shared__ float sred[];                    // [blockDim.x][16] (statistics only)
   const int tpr = blockDim.x / cvec;
   const int cv = threadIdx.x % cvec;
@@ -443,9 +448,12 @@ splitk_finalize_kernel(float4* __restrict__ ws, const float* __restrict__ scale,
   if (rsub < tpr) {
     for (size_t r = static_cast<size_t>(blockIdx.x) * tpr + rsub; r < rows; r += static_cast<size_t>(gridDim.x) * tpr) {
       const size_t idx = r * cvec + cv;
-      const float4 a = ws[2 * idx], b = ws[2 * idx + 1];
-      ws[2 * idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-      ws[2 * idx + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a = __ldg(ws + 2 * idx), b = __ldg(ws + 2 * idx + 1);
+      for (int k = 1; k < splits; ++k) {
+        const float4 a2 = __ldg(ws + k * slice_vec4 + 2 * idx), b2 = __ldg(ws + k * slice_vec4 + 2 * idx + 1);
+        a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+        b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+      }
       float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
       if (stats != nullptr) {
 #pragma unroll
@@ -478,9 +486,21 @@ splitk_finalize_kernel(float4* __restrict__ ws, const float* __restrict__ scale,
       const int v = o / 16, k = o % 16;
       float s = 0.f;
       for (int t = 0; t < tpr; ++t) s += sred[(t * cvec + v) * 16 + k];
-      atomicAdd(stats + (k < 8 ? 0 : c_store) + v * 8 + (k & 7), s);
+      det_add(stats + static_cast<size_t>((k < 8 ? 0 : c_store) + v * 8 + (k & 7)) * kDetLimbs, s);
     }
   }
+}
+
+// n plain floats <-> n exact accumulators (fvt_stats_encode / fvt_stats_decode)
+__global__ void stats_encode_kernel(const float* __restrict__ v, unsigned long long* __restrict__ acc, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < kDetLimbs; ++k) acc[static_cast<size_t>(i) * kDetLimbs + k] = 0ull;
+  det_add(acc + static_cast<size_t>(i) * kDetLimbs, v[i]);
+}
+__global__ void stats_decode_kernel(const unsigned long long* __restrict__ acc, float* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = static_cast<float>(det_read(acc + static_cast<size_t>(i) * kDetLimbs));
 }
 
 static int rows_launch(size_t rows, int cvec, int* blocks, int* threads) {
@@ -497,15 +517,16 @@ static int rows_launch(size_t rows, int cvec, int* blocks, int* threads) {
   return 0;
 }
 
-int launch_splitk_finalize(float* ws, const float* scale, const float* shift, const void* residual, void* y, float* stats,
-                           size_t rows, int c_store, int relu, cudaStream_t stream) {
+int launch_splitk_finalize(const float* ws, int splits, const float* scale, const float* shift, const void* residual, void* y,
+                           unsigned long long* stats, size_t rows, int c_store, int relu, cudaStream_t stream) {
   int blocks, threads;
   if (c_store % 8 || rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "split-K finalize: bad channel count");
   // one row per thread per iteration here: rows_launch sized the grid for kUnroll rows per iteration
   size_t b = (rows + (threads / (c_store / 8)) - 1) / (threads / (c_store / 8));
   if (b > 148 * 8) b = 148 * 8;
   splitk_finalize_kernel<<<static_cast<int>(b), threads, stats ? threads * 16 * sizeof(float) : 0, stream>>>(
-      reinterpret_cast<float4*>(ws), scale, shift, (const uint4*)residual, (uint4*)y, stats, rows, c_store / 8, c_store, relu);
+      reinterpret_cast<const float4*>(ws), splits, rows * static_cast<size_t>(c_store) / 4, scale, shift, (const uint4*)residual,
+      (uint4*)y, stats, rows, c_store / 8, c_store, relu);
   return check_launch("splitk_finalize_kernel");
 }
 
@@ -527,26 +548,43 @@ static int launch_bn_apply(const void* raw, const float* scale, const float* shi
 
 extern "C" {
 
-int fvt_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+int fvt_stats_encode(fvt_handle_t handle, const float* values, void* stats_acc, int32_t n, void* stream) {
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
+  if (!values || !stats_acc || n <= 0) return set_error(FVT_ERR_BAD_DESC, "bad fvt_stats_encode arguments");
+  stats_encode_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(values, (unsigned long long*)stats_acc, n);
+  return check_launch("stats_encode_kernel");
+}
+
+int fvt_stats_decode(fvt_handle_t handle, const void* stats_acc, float* values, int32_t n, void* stream) {
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
+  if (!values || !stats_acc || n <= 0) return set_error(FVT_ERR_BAD_DESC, "bad fvt_stats_decode arguments");
+  stats_decode_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)stats_acc, values, n);
+  return check_launch("stats_decode_kernel");
+}
+
+int fvt_bn_finalize(fvt_handle_t handle, const void* stats_acc, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, int32_t c_store, int32_t c_real, int64_t rows, float eps, float momentum,
                     float* scale, float* shift, float* mean, float* invstd, void* stream) {
-  if (!stats || !gamma || !beta || !scale || !shift || !mean || !invstd) return set_error(FVT_ERR_BAD_DESC, "null pointer");
-  if (c_store <= 0 || c_real <= 0 || c_real > c_store || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_finalize extent");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
+  if (!stats_acc || !gamma || !beta || !scale || !shift || !mean || !invstd) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  if (c_store <= 0 || c_real <= 0 || c_real > c_store || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_finalize extent");
   bn_finalize_kernel<<<(c_store + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      stats, gamma, beta, running_mean, running_var, c_store, c_real, 1.0f / static_cast<float>(rows), eps, momentum,
-      scale, shift, mean, invstd);
+      (const unsigned long long*)stats_acc, gamma, beta, running_mean, running_var, c_store, c_real, 1.0 / static_cast<double>(rows), eps,
+      momentum, scale, shift, mean, invstd);
   return check_launch("bn_finalize_kernel");
 }
 
-int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const void* res, const float* res_scale,
-                 const float* res_shift, void* out, int64_t rows, int32_t c_store, int32_t relu, void* stream) {
+int fvt_bn_apply(fvt_handle_t handle, const void* raw, const float* scale, const float* shift, const void* res,
+                 const float* res_scale, const float* res_shift, void* out, int64_t rows, int32_t c_store, int32_t relu,
+                 void* stream) {
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
   if (!raw || !scale || !shift || !out) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   if (c_store <= 0 || c_store % 8 || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_apply extent");
   if ((res_scale == nullptr) != (res_shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "res_scale/res_shift must come together");
-  int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
   int blocks, threads;
   if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
   BnFinalizeArgs fin;
@@ -555,48 +593,56 @@ int fvt_bn_apply(const void* raw, const float* scale, const float* shift, const 
                          (cudaStream_t)stream);
 }
 
-int fvt_bn_finalize_apply(const float* stats, const float* gamma, const float* beta, float* running_mean,
+int fvt_bn_finalize_apply(fvt_handle_t handle, const void* stats_acc, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, int32_t c_store, int32_t c_real, int64_t rows, float eps, float momentum,
                           float* scale, float* shift, float* mean, float* invstd, const void* raw, const void* res,
                           const float* res_scale, const float* res_shift, void* out, int32_t relu, void* stream) {
-  if (!stats || !gamma || !beta || !scale || !shift || !mean || !invstd || !raw || !out) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
+  if (!stats_acc || !gamma || !beta || !scale || !shift || !mean || !invstd || !raw || !out) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   if (c_store <= 0 || c_store % 8 || c_real <= 0 || c_real > c_store || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_finalize_apply extent");
   if ((res_scale == nullptr) != (res_shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "res_scale/res_shift must come together");
   if ((running_mean == nullptr) != (running_var == nullptr)) return set_error(FVT_ERR_BAD_DESC, "running_mean/running_var must come together");
-  int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
   int blocks, threads;
   if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
   BnFinalizeArgs fin;
-  fin.stats = stats; fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
+  fin.stats = (const unsigned long long*)stats_acc; fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
   fin.scale_out = scale; fin.shift_out = shift; fin.mean_out = mean; fin.invstd_out = invstd;
-  fin.c_real = c_real; fin.inv_rows = 1.0f / static_cast<float>(rows); fin.eps = eps; fin.momentum = momentum;
+  fin.c_real = c_real; fin.inv_rows = 1.0 / static_cast<double>(rows); fin.eps = eps; fin.momentum = momentum;
   return launch_bn_apply(raw, nullptr, nullptr, res, res_scale, res_shift, out, rows, c_store, relu, fin, blocks, threads,
                          (cudaStream_t)stream);
 }
 
-int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const float* mean, const float* invstd,
-                    const float* gamma, const float* relu_scale, const float* relu_shift, float* sums, void* draw,
-                    void* dz_out, int64_t rows, int32_t c_store, int32_t c_real, void* stream) {
+int fvt_bn_backward(fvt_handle_t handle, const void* raw, const void* dact, const void* mask, const float* mean,
+                    const float* invstd, const float* gamma, const float* relu_scale, const float* relu_shift, float* sums,
+                    void* sums_acc, void* draw, void* dz_out, int64_t rows, int32_t c_store, int32_t c_real, int32_t dz_in,
+                    void* stream) {
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
   if ((relu_scale == nullptr) != (relu_shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "relu_scale/relu_shift must come together");
   if (mask != nullptr && relu_scale != nullptr) return set_error(FVT_ERR_BAD_DESC, "give either a mask tensor or relu_scale/relu_shift");
-  if (!raw || !dact || !mean || !invstd || !gamma || !sums || !draw) return set_error(FVT_ERR_BAD_DESC, "null pointer");
+  if (!raw || !dact || !mean || !invstd || !gamma || !sums || !sums_acc || !draw) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   if (c_store <= 0 || c_store % 8 || rows <= 0 || c_real > c_store) return set_error(FVT_ERR_BAD_DESC, "bad bn_backward extent");
-  int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (((uintptr_t)sums_acc) & 7) return set_error(FVT_ERR_MISALIGNED, "sums_acc must be 8-byte aligned");
+  if (dz_in && (mask != nullptr || dz_out != nullptr)) return set_error(FVT_ERR_BAD_DESC, "dz_in: dact already is dz (no mask tensor, no dz_out)");
   int blocks, threads;
   if (rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "channel count too large");
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c_store, (cudaStream_t)stream);
-  const int mask_mode = mask != nullptr ? 1 : (relu_scale != nullptr ? 2 : 0);
-  const size_t smem_r = sizeof(float) * (3 * c_store + threads * 16);
+  unsigned long long* acc = (unsigned long long*)sums_acc;
+  int mask_mode = mask != nullptr ? 1 : (relu_scale != nullptr ? 2 : 0);
+  if (!dz_in) {
+    cudaMemsetAsync(acc, 0, fvt_stats_bytes(c_store), (cudaStream_t)stream);
+    const size_t smem_r = sizeof(float) * (3 * c_store + threads * 16);
 #define FVT_BN_RED(M) bn_bwd_reduce_kernel<M><<<blocks, threads, smem_r, (cudaStream_t)stream>>>( \
-      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, relu_scale, relu_shift, sums, rows, c_store / 8, c_store)
-  if (mask_mode == 0) FVT_BN_RED(0); else if (mask_mode == 1) FVT_BN_RED(1); else FVT_BN_RED(2);
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, relu_scale, relu_shift, acc, rows, c_store / 8, c_store)
+    if (mask_mode == 0) FVT_BN_RED(0); else if (mask_mode == 1) FVT_BN_RED(1); else FVT_BN_RED(2);
 #undef FVT_BN_RED
-  if (int e = check_launch("bn_bwd_reduce_kernel")) return e;
+    if (int e = check_launch("bn_bwd_reduce_kernel")) return e;
+  } else {
+    mask_mode = 0;                                   // the producer already applied the ReLU mask
+  }
   const size_t smem_a = sizeof(float) * 6 * c_store;
 #define FVT_BN_APP(M, D) bn_bwd_apply_kernel<M, D><<<blocks, threads, smem_a, (cudaStream_t)stream>>>( \
-      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, relu_scale, relu_shift, sums, \
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, relu_scale, relu_shift, acc, sums, \
       (uint4*)draw, (uint4*)dz_out, rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows))
   if (dz_out != nullptr) {
     if (mask_mode == 0) FVT_BN_APP(0, true); else if (mask_mode == 1) FVT_BN_APP(1, true); else FVT_BN_APP(2, true);
@@ -607,12 +653,12 @@ int fvt_bn_backward(const void* raw, const void* dact, const void* mask, const f
   return check_launch("bn_bwd_apply_kernel");
 }
 
-int fvt_zero_insert(const void* dy, void* up, int32_t n, int32_t t, int32_t h, int32_t w, int32_t to, int32_t ho,
+int fvt_zero_insert(fvt_handle_t handle, const void* dy, void* up, int32_t n, int32_t t, int32_t h, int32_t w, int32_t to, int32_t ho,
                     int32_t wo, int32_t st_, int32_t sh, int32_t sw, int32_t c_store, void* stream) {
   if (!dy || !up) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   if (c_store <= 0 || c_store % 8) return set_error(FVT_ERR_BAD_DESC, "bad channel count");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   const size_t total = static_cast<size_t>(n) * t * h * w * (c_store / 8);
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -621,22 +667,22 @@ int fvt_zero_insert(const void* dy, void* up, int32_t n, int32_t t, int32_t h, i
   return check_launch("zero_insert_kernel");
 }
 
-int fvt_pool_fc_bwd(const float* dlogits, const float* pooled, const float* w, int32_t n, int32_t num_class,
+int fvt_pool_fc_bwd(fvt_handle_t handle, const float* dlogits, const float* pooled, const float* w, int32_t n, int32_t num_class,
                     int32_t c, int32_t positions, float* dw, float* db, void* dx, int32_t c_store, void* stream) {
   if (!dlogits || !pooled || !w || !dw || !db || !dx) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   pool_fc_bwd_kernel<<<n + num_class, 256, 0, (cudaStream_t)stream>>>(dlogits, pooled, w, n, num_class, c, positions, dw, db,
                                                                       (__nv_bfloat16*)dx, c_store);
   return check_launch("pool_fc_bwd_kernel");
 }
 
-int fvt_sgd_momentum_multi(const void* tensor_table, const uint32_t* chunk_tensor, const uint32_t* chunk_offset,
+int fvt_sgd_momentum_multi(fvt_handle_t handle, const void* tensor_table, const uint32_t* chunk_tensor, const uint32_t* chunk_offset,
                            int32_t num_chunks, uint32_t chunk_elems, float lr, float momentum, float rescale,
                            void* stream) {
   if (!tensor_table || !chunk_tensor || !chunk_offset || num_chunks <= 0) return set_error(FVT_ERR_BAD_DESC, "bad sgd table");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   sgd_momentum_multi_kernel<<<num_chunks, 256, 0, (cudaStream_t)stream>>>((const SgdTensor*)tensor_table, chunk_tensor,
                                                                           chunk_offset, lr, momentum, rescale, chunk_elems);
   return check_launch("sgd_momentum_multi_kernel");

@@ -110,7 +110,7 @@ using namespace fvt;
 
 extern "C" {
 
-int fvt_conv3d_fwd_f32(const fvt_conv_desc* d, const float* x, const float* w_thwio, const float* scale, const float* shift,
+int fvt_conv3d_fwd_f32(fvt_handle_t handle, const fvt_conv_desc* d, const float* x, const float* w_thwio, const float* scale, const float* shift,
                        const float* residual, float* y, void* stream) {
   if (d == nullptr || x == nullptr || w_thwio == nullptr || y == nullptr) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   if (d->n <= 0 || d->t <= 0 || d->h <= 0 || d->w <= 0 || d->cin <= 0 || d->cout <= 0 || d->kt < 1 || d->kh < 1 || d->kw < 1 ||
@@ -119,7 +119,7 @@ int fvt_conv3d_fwd_f32(const fvt_conv_desc* d, const float* x, const float* w_th
   if ((d->flags & FVT_CONV_RESIDUAL) && residual == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_RESIDUAL without a residual tensor");
   if (d->flags & FVT_CONV_STATS) return set_error(FVT_ERR_BAD_DESC, "the fp32 path is inference-only (no statistics)");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   const int to = (d->t + 2 * d->pt - d->kt) / d->st + 1, ho = (d->h + 2 * d->ph - d->kh) / d->sh + 1,
             wo = (d->w + 2 * d->pw - d->kw) / d->sw + 1;
   if (to <= 0 || ho <= 0 || wo <= 0) return set_error(FVT_ERR_BAD_DESC, "filter larger than padded input");
@@ -132,13 +132,13 @@ int fvt_conv3d_fwd_f32(const fvt_conv_desc* d, const float* x, const float* w_th
   return check_launch("conv3d_f32_kernel");
 }
 
-int fvt_pool_fc_fwd_f32(const float* x, int32_t n, int32_t positions, int32_t c, const float* w, const float* b,
+int fvt_pool_fc_fwd_f32(fvt_handle_t handle, const float* x, int32_t n, int32_t positions, int32_t c, const float* w, const float* b,
                         int32_t num_class, float* pooled, float* logits, void* stream) {
   if (x == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (n <= 0 || positions <= 0 || c <= 0) return set_error(FVT_ERR_BAD_DESC, "bad pool/fc extent");
   if (logits != nullptr && (w == nullptr || num_class <= 0)) return set_error(FVT_ERR_BAD_DESC, "logits requested without weights");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   pool_fc_f32_kernel<<<n, 512, c * sizeof(float), (cudaStream_t)stream>>>(x, positions, c, w, b, num_class, pooled, logits);
   return check_launch("pool_fc_f32_kernel");
 }

@@ -20,6 +20,7 @@
 #pragma once
 #include "ptx.cuh"
 #include "epilogue.cuh"
+#include "det_sum.cuh"
 
 namespace fvt {
 
@@ -45,16 +46,35 @@ struct ConvKernelParams {
   int cout_store;         // channel pitch of Y / residual (elements)
   int flags;
   int stages;
-  int k_splits;           // > 1: split-K — item = (tile, split); partial sums are added into `ws` (fp32), no epilogue math
+  int k_splits;           // > 1: split-K — item = (tile, split); partial tiles are stored into ws[split] (fp32), no epilogue math
   int kb_per_split;
-  float* ws;              // [m_total][cout_store] fp32, zero on entry (split-K only)
+  float* ws;              // [k_splits][m_total][cout_store] fp32 (split-K only)
   int b_stationary;       // 1: all taps*cin_blocks weight tiles are loaded once and stay in shared memory
   const float* scale;     // [cout_store] or nullptr (identity)
   const float* shift;     // [cout_store] or nullptr
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
-  float* stats;           // [2][cout_store]: sum, sum of squares (atomically accumulated) or nullptr
+  unsigned long long* stats;   // [2][cout_store] exact accumulators (det_sum.cuh): sum, sum of squares; or nullptr
+  // Output lattice map (fvt_conv3d_fwd_ex): GEMM row (n, ot, oh, ow) is stored at (n, ot*om_st + om_t0, oh*om_sh + om_h0,
+  // ow*om_sw + om_w0) of a [N, om_t, om_h, om_w, cout_store] tensor (residual read at the same place).  om_on = 0: dense.
+  int om_on;
+  int om_t, om_h, om_w;
+  int om_st, om_sh, om_sw;
+  int om_t0, om_h0, om_w0;
 };
+
+// Row of Y (in pixels) a GEMM row is stored at; < 0 for rows beyond the problem.
+__device__ __forceinline__ long long conv_out_row(const ConvKernelParams& p, int row) {
+  if (row >= p.m_total) return -1ll;
+  if (!p.om_on) return static_cast<long long>(row);
+  int m = row;
+  const int ow = m % p.wo;  m /= p.wo;
+  const int oh = m % p.ho;  m /= p.ho;
+  const int ot = m % p.to;
+  const int on = m / p.to;
+  return ((static_cast<long long>(on) * p.om_t + (ot * p.om_st + p.om_t0)) * p.om_h + (oh * p.om_sh + p.om_h0)) * p.om_w +
+         (ow * p.om_sw + p.om_w0);
+}
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
@@ -83,8 +103,9 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2]
   uint64_t* b_full_bar = acc_empty_bar + 2;        // [1] stationary weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full_bar + 2);   // keeps the float4 arrays below 16-byte aligned
-  float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);   // [2][256] per-CTA channel partials
-  float* affine_smem = stat_smem + 512;                          // [2][kMaxCout] scale, shift
+  // [2][kMaxCout] scale, shift — or, for the training forward (statistics, no folded affine), [4 quadrants][2][n_pad]
+  // per-CTA channel partials (the host sizes the region: conv_aux_bytes)
+  float* affine_smem = reinterpret_cast<float*>(tmem_slot + 4);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_x);
@@ -114,10 +135,12 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     }
   }
   // Training forward (statistics, no folded affine): the per-channel sums of ALL tiles of this CTA accumulate in the
-  // otherwise unused affine area and reach global memory once, after the tile loop (no per-tile barriers/atomics).
+  // otherwise unused affine area, one [2][n_pad] block per TMEM lane quadrant, and reach global memory once, after the
+  // tile loop (no per-tile barriers, no floating-point atomics: see det_sum.cuh).
   const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr && p.k_splits == 1;
+  const int n_pad = p.num_n_tiles * p.block_n;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 2 * kMaxCout; i += kConvThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * n_pad; i += kConvThreads) affine_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -273,7 +296,6 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     const int grp = (warp - 4) >> 2;            // 0 or 1
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool do_stats = (p.flags & kConvStats) != 0;
     const bool has_affine = p.scale != nullptr;
     const int et = threadIdx.x - 128;           // 0..255
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
@@ -284,22 +306,23 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.m_total;
       if (p.k_splits > 1) {
-        // split-K: add this item's fp32 partial tile into the workspace (vector reductions, 16 bytes each); the
-        // epilogue math runs in splitk_finalize_kernel once all splits have landed
+        // split-K: store this item's fp32 partial tile into its split's slice of the workspace (16-byte stores); the
+        // epilogue math runs in splitk_finalize_kernel, which adds the slices in split order
         ptx::mbar_wait(ptx::smem_u32(&acc_full_bar[acc]), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
-        float* wrow = p.ws + static_cast<size_t>(row_ok ? row : 0) * p.cout_store + n0;
+        const int split = item - tile * p.k_splits;
+        float* wrow = p.ws + (static_cast<size_t>(split) * p.m_total + (row_ok ? row : 0)) * p.cout_store + n0;
         for (int c = grp * 16; c < p.block_n; c += 32) {
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(taddr + c, v);
           ptx::tmem_ld_wait();
           if (row_ok && n0 + c < p.cout_store) {
+            float4* dst = reinterpret_cast<float4*>(wrow + c);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c + 4 * i), "f"(__uint_as_float(v[4 * i])),
-                           "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
-                           : "memory");
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
           }
         }
         ptx::tc_fence_before();
@@ -308,49 +331,33 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      if (do_stats && !acc_stats) {
-        for (int i = et; i < 512; i += kEpilogueThreads) stat_smem[i] = 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
+      const long long out_row = conv_out_row(p, row);
       {
         EpilogueArgs pre;
         pre.block_n = p.block_n; pre.cout_store = p.cout_store; pre.flags = p.flags; pre.residual = p.residual;
-        epilogue_prefetch_residual(pre, n0, row_ok ? static_cast<long long>(row) : -1ll, grp);
+        epilogue_prefetch_residual(pre, n0, out_row, grp);
       }
       ptx::mbar_wait(ptx::smem_u32(&acc_full_bar[acc]), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
       {
         EpilogueArgs ea;
-        ea.block_n = p.block_n; ea.cout_store = p.cout_store; ea.flags = p.flags;
+        ea.block_n = p.block_n; ea.cout_store = p.cout_store; ea.flags = acc_stats ? p.flags : (p.flags & ~kConvStats);
         ea.scale_smem = has_affine ? affine_smem : nullptr; ea.shift_smem = affine_smem + kMaxCout;
         ea.residual = p.residual; ea.y = p.y;
-        ea.stat_smem = acc_stats ? affine_smem + n0 : stat_smem; ea.stat_stride = acc_stats ? kMaxCout : 256;
+        ea.stat_smem = affine_smem + q * 2 * n_pad + n0; ea.stat_stride = n_pad;
         ea.stat_mask = stat_mask_below(static_cast<long long>(m_blk) * kBlockM + q * 32, lane, p.m_total);
-        epilogue_chunks(ea, taddr, n0, row_ok ? static_cast<long long>(row) : -1ll, grp, lane);
+        epilogue_chunks(ea, taddr, n0, out_row, grp, lane);
       }
       // release the accumulator stage (all of this warp's TMEM reads have completed: wait::ld above)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty_bar[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (do_stats && !acc_stats) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = et; i < p.block_n; i += kEpilogueThreads) {
-          if (n0 + i < p.cout_store) {
-            atomicAdd(p.stats + n0 + i, stat_smem[i]);
-            atomicAdd(p.stats + p.cout_store + n0 + i, stat_smem[256 + i]);
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
     }
     if (acc_stats && blockIdx.x < num_tiles) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < p.cout_store; i += kEpilogueThreads) {
-        atomicAdd(p.stats + i, affine_smem[i]);
-        atomicAdd(p.stats + p.cout_store + i, affine_smem[kMaxCout + i]);
-      }
+      flush_quadrant_stats(affine_smem, n_pad, p.cout_store, p.stats, et, kEpilogueThreads);
     }
   }
 

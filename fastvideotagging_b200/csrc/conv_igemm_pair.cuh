@@ -62,8 +62,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   uint64_t* acc_full_bar = bars + 2 * kMaxStages;  // [2] multicast commit
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2] leader: 16 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
-  float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);   // [2][256] per-CTA channel partials
-  float* affine_smem = stat_smem + 512;                          // [2][kMaxCout] scale, shift
+  // [2][kMaxCout] scale, shift — or [4 quadrants][2][n_pad] per-CTA statistics partials (training forward), as in K1
+  float* affine_smem = reinterpret_cast<float*>(tmem_slot + 4);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_x);
@@ -89,8 +89,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
   }
   const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr;
+  const int n_pad = p.num_n_tiles * p.block_n;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 2 * kMaxCout; i += kConvThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * n_pad; i += kConvThreads) affine_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   pair::cluster_sync_all();
@@ -205,10 +206,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       const long long row = static_cast<long long>(m_blk) * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.m_total;
       EpilogueArgs ea;
-      ea.block_n = p.block_n; ea.cout_store = p.cout_store; ea.flags = p.flags;
+      ea.block_n = p.block_n; ea.cout_store = p.cout_store; ea.flags = acc_stats ? p.flags : (p.flags & ~kConvStats);
       ea.scale_smem = has_affine ? affine_smem : nullptr; ea.shift_smem = affine_smem + kMaxCout;
       ea.residual = p.residual; ea.y = p.y;
-      ea.stat_smem = affine_smem + n0; ea.stat_stride = kMaxCout;       // statistics only without a folded affine (acc_stats)
+      ea.stat_smem = affine_smem + q * 2 * n_pad + n0; ea.stat_stride = n_pad;   // statistics only without a folded affine (acc_stats)
       ea.stat_mask = stat_mask_below(static_cast<long long>(m_blk) * kBlockM + q * 32, lane, p.m_total);
       epilogue_prefetch_residual(ea, n0, row_ok ? row : -1ll, grp);
       ptx::mbar_wait(ptx::smem_u32(&acc_full_bar[acc]), acc_phase);
@@ -222,10 +223,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
     if (acc_stats && item0 < num_items) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < p.cout_store; i += kEpilogueThreads) {
-        atomicAdd(p.stats + i, affine_smem[i]);
-        atomicAdd(p.stats + p.cout_store + i, affine_smem[kMaxCout + i]);
-      }
+      flush_quadrant_stats(affine_smem, n_pad, p.cout_store, p.stats, et, kEpilogueThreads);
     }
   }
 

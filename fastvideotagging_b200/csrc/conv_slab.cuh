@@ -19,6 +19,7 @@
 #pragma once
 #include "ptx.cuh"
 #include "epilogue.cuh"
+#include "det_sum.cuh"
 
 namespace fvt {
 
@@ -49,7 +50,7 @@ struct SlabParams {
   const float* shift;
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
-  float* stats;
+  unsigned long long* stats;   // [2][cout_store] exact accumulators (det_sum.cuh)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -90,9 +91,10 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   uint64_t* acc_full = b_empty + kSlabMaxBRing;                        // [2]
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* affine_smem = reinterpret_cast<float*>(tmem_slot + 4);        // scale[n_total], shift[n_total]
+  // scale[n_total], shift[n_total] — or, with kConvStats (training forward, no folded affine), the per-CTA statistics
+  // partials [4 quadrants][2][n_total] (the host sizes the region accordingly)
+  float* affine_smem = reinterpret_cast<float*>(tmem_slot + 4);
   const int n_total = p.n_tile * p.num_n_tiles;
-  float* stat_smem = affine_smem + 2 * n_total;                        // [2][n_tile] (only touched with kConvStats)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_x);
@@ -123,11 +125,11 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       affine_smem[n_total + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
     }
   }
-  // training forward (statistics, no folded affine): sums of all tiles of this CTA accumulate in the unused affine area
-  // [2][n_total] and are flushed to global memory once after the tile loop
+  // training forward (statistics, no folded affine): sums of all tiles of this CTA accumulate in the unused affine area,
+  // one [2][n_total] block per TMEM lane quadrant, and are flushed to global memory once after the tile loop
   const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 2 * n_total; i += kThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * n_total; i += kThreads) affine_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -298,14 +300,13 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int et = threadIdx.x - 128;
-    const bool do_stats = (p.flags & kConvStats) != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     EpilogueArgs ea;
     ea.ngrp = kEpiWarps / 4;
-    ea.block_n = p.n_tile; ea.cout_store = p.cout_store; ea.flags = p.flags;
+    ea.block_n = p.n_tile; ea.cout_store = p.cout_store; ea.flags = acc_stats ? p.flags : (p.flags & ~kConvStats);
     ea.scale_smem = p.scale != nullptr ? affine_smem : nullptr; ea.shift_smem = affine_smem + n_total;
-    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem; ea.stat_stride = p.n_tile;
+    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = affine_smem; ea.stat_stride = n_total;
     const int r = q * 32 + lane;                 // GEMM row = padded position m' inside the tile
     const int hl = r / p.wp, wl = r - hl * p.wp;
     // rows whose statistics this thread gathers (16x256b fragment: q*32 + lane/4 + 8j): tile-invariant (hl, wl)
@@ -332,11 +333,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const long long out_row = ok ? (static_cast<long long>(frame) * p.h + h0 + hl) * p.w + wl : -1ll;
       for (int nt = 0; nt < p.num_n_tiles; ++nt) {
         const int n0 = nt * p.n_tile;
-        if (do_stats && !acc_stats) {
-          for (int i = et; i < 2 * p.n_tile; i += kEpiThreads) stat_smem[i] = 0.f;
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        }
-        if (acc_stats) { ea.stat_smem = affine_smem + n0; ea.stat_stride = n_total; }
+        ea.stat_smem = affine_smem + q * 2 * n_total + n0;
         epilogue_prefetch_residual(ea, n0, out_row, grp);
         ptx::mbar_wait(ptx::smem_u32(&acc_full[acc]), acc_phase);
         ptx::tc_fence_after();
@@ -346,24 +343,11 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc_empty[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (do_stats && !acc_stats) {
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          for (int i = et; i < p.n_tile; i += kEpiThreads) {
-            if (n0 + i < p.cout_store) {
-              atomicAdd(p.stats + n0 + i, stat_smem[i]);
-              atomicAdd(p.stats + p.cout_store + n0 + i, stat_smem[p.n_tile + i]);
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        }
       }
     }
     if (acc_stats && static_cast<int>(blockIdx.x) < num_m_tiles) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      for (int i = et; i < n_total && i < p.cout_store; i += kEpiThreads) {
-        atomicAdd(p.stats + i, affine_smem[i]);
-        atomicAdd(p.stats + p.cout_store + i, affine_smem[n_total + i]);
-      }
+      flush_quadrant_stats(affine_smem, n_total, p.cout_store, p.stats, et, kEpiThreads);
     }
   }
 

@@ -16,6 +16,7 @@
 #pragma once
 #include "ptx.cuh"
 #include "epilogue.cuh"
+#include "det_sum.cuh"
 #include "conv_slab.cuh"
 
 namespace fvt {
@@ -40,7 +41,7 @@ struct TemporalIsParams {
   const float* shift;
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
-  float* stats;
+  unsigned long long* stats;   // [2][cout_store] exact accumulators (det_sum.cuh)
 };
 
 constexpr int kTisOutTileBytes = 128 * 128;     // [128 positions x 64 channels] bf16 staging tile (TMA-store epilogue)
@@ -68,7 +69,7 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   uint64_t* w_full = acc_empty + kTisMaxAcc;                   // [1] + 1 pad
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 2);
   float* affine_smem = reinterpret_cast<float*>(tmem_slot + 4);   // scale[n_tile], shift[n_tile]
-  float* stat_smem = affine_smem + 2 * p.n_tile;                   // [2][n_tile]
+  float* stat_smem = affine_smem + 2 * p.n_tile;                   // [4 quadrants][2][n_tile] per-CTA partials
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_x);
@@ -99,7 +100,7 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   }
   // per-channel statistics accumulate in shared memory over ALL tiles of this CTA; one flush after the tile loop
   if (p.flags & kConvStats)
-    for (int i = threadIdx.x; i < 2 * p.n_tile; i += blockDim.x) stat_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * p.n_tile; i += blockDim.x) stat_smem[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -205,13 +206,12 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int et = threadIdx.x - 128;
-    const bool do_stats = (p.flags & kConvStats) != 0;
     int slot = 0;
     uint32_t par = 0;
     EpilogueArgs ea;
     ea.block_n = p.n_tile; ea.cout_store = p.cout_store; ea.flags = p.flags;
     ea.scale_smem = p.scale != nullptr ? affine_smem : nullptr; ea.shift_smem = affine_smem + p.n_tile;
-    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem; ea.stat_stride = p.n_tile;
+    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_smem + q * 2 * p.n_tile; ea.stat_stride = p.n_tile;
     const int r = q * 32 + lane;
     int obuf = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -257,10 +257,8 @@ conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   ptx::tc_fence_before();
   __syncthreads();
   if ((p.flags & kConvStats) && static_cast<int>(blockIdx.x) < p.num_items) {
-    for (int i = threadIdx.x; i < p.n_tile && i < p.cout_store; i += blockDim.x) {
-      atomicAdd(p.stats + i, stat_smem[i]);
-      atomicAdd(p.stats + p.cout_store + i, stat_smem[p.n_tile + i]);
-    }
+    flush_quadrant_stats(stat_smem, p.n_tile, p.cout_store, p.stats, static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x), 0,
+                         p.n_tile < p.cout_store ? p.n_tile : p.cout_store);
   }
   if (warp == 2) {
     ptx::tc_fence_after();

@@ -41,7 +41,11 @@ struct WgradParams {
   int stages;
   float* dw;
   int w_ohwi;            // dw layout (O, taps, I) instead of (O, I, taps)
-  int dbg_no_atomics;    // experiments only: epilogue reads TMEM, adds nothing
+  int dbg_no_store;      // experiments only: epilogue reads TMEM, stores nothing
+  // split reduction as in conv_wgrad_slab.cuh: splits > 1 store into ws[split][...] (reduced in split order by the host's
+  // wgrad_reduce pass), a single split stores straight into dw; no atomics
+  float* ws;
+  long long ws_split_stride;
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -190,26 +194,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         ptx::tmem_ld_32x32b_x16(taddr + c, v);
         ptx::tmem_ld_wait();
         const int nbase = nt * p.n_tile + c;
-        if (row_ok && !p.dbg_no_atomics && p.mode == 1 && p.w_ohwi && (p.cin_real & 3) == 0 && nbase + 16 <= p.cin_real) {
+        float* dst0 = p.ws != nullptr ? p.ws + static_cast<size_t>(split) * p.ws_split_stride : p.dw;
+        if (row_ok && !p.dbg_no_store && p.mode == 1 && p.w_ohwi && (p.cin_real & 3) == 0 && nbase + 16 <= p.cin_real) {
           // (O, taps, I) layout, input channels along N: this thread's 16 columns are 16 consecutive floats
-          float* dst = p.dw + (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + nbase;
+          float4* dst = reinterpret_cast<float4*>(dst0 + (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + nbase);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(__uint_as_float(v[4 * i])),
-                         "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
-                         : "memory");
-        } else if (row_ok && !p.dbg_no_atomics) {
+            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                 __uint_as_float(v[4 * i + 3]));
+        } else if (row_ok && !p.dbg_no_store) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int nidx = nbase + j;
             if (p.mode == 0) {
               if (nidx < p.cout_real)
-                atomicAdd(p.dw + (p.w_ohwi ? (static_cast<size_t>(nidx) * p.taps + tap) * p.cin_real + ci
-                                           : (static_cast<size_t>(nidx) * p.cin_real + ci) * p.taps + tap), __uint_as_float(v[j]));
+                dst0[p.w_ohwi ? (static_cast<size_t>(nidx) * p.taps + tap) * p.cin_real + ci
+                              : (static_cast<size_t>(nidx) * p.cin_real + ci) * p.taps + tap] = __uint_as_float(v[j]);
             } else {
               if (nidx < p.cin_real)
-                atomicAdd(p.dw + (p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + nidx
-                                           : (static_cast<size_t>(co) * p.cin_real + nidx) * p.taps + tap), __uint_as_float(v[j]));
+                dst0[p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + nidx
+                              : (static_cast<size_t>(co) * p.cin_real + nidx) * p.taps + tap] = __uint_as_float(v[j]);
             }
           }
         }

@@ -13,8 +13,8 @@
 //     descriptor's leading-dimension byte offset is simply the distance between the two shifted views
 //     (tools/experiments/mn_stack.cu verifies this on hardware);
 //   * keeps up to 512 TMEM columns of fp32 accumulators (several 128-row M tiles x one N tile) for its whole pixel
-//     range, so X and dY are read once per CTA and the epilogue runs once: atomics into the fp32 (O, I, kT, kH, kW)
-//     gradient (pixel splits of the same block meet there).
+//     range, so X and dY are read once per CTA and the epilogue runs once: plain stores of the fp32 tile into dW (one
+//     pixel split) or into this split's slice of the workspace (reduced in split order afterwards: deterministic).
 //
 // Warp roles (192 threads): warp0 TMA producer, warp1 MMA issuer (+ TMEM alloc), warps 2-5 epilogue.
 // Replaces cuDNN backward-filter for the Conv3D(1,3,3) layers at reference model/R2Plus1.py:27-31, net.py:40-42.
@@ -47,10 +47,11 @@ struct WgradSlabParams {
   int hw, t_frames, blocks_per_frame, kt, pt, chunks_per_tap;
   float* dw;
   int w_ohwi;                  // dw layout (O, taps, I) instead of (O, I, taps)
-  int dbg_no_atomics;          // experiments only (fvt_set_option("wgrad_no_atomics")): epilogue reads TMEM, adds nothing
-  // Workspace reduction (fvt_set_wgrad_workspace): every pixel split STORES its partial gradient into its own dW-shaped
-  // slice ws[split][...] (full 128-byte lines, no read-modify-write in L2) and one reduce pass adds the slices into dw.
-  float* ws;                   // nullptr: fp32 atomics straight into dw
+  int dbg_no_store;            // experiments only (fvt_set_option("wgrad_no_store")): epilogue reads TMEM, stores nothing
+  // Split reduction: with splits > 1 every pixel split STORES its partial gradient into its own dW-shaped slice
+  // ws[split][...] of the caller's workspace (full 128-byte lines, no read-modify-write in L2) and one reduce pass adds
+  // the slices in split order and overwrites dw; with a single split the tile is stored straight into dw.  No atomics.
+  float* ws;                   // nullptr: one split, store into dw
   long long ws_split_stride;   // elements of one slice (= cout_real * cin_real * taps)
 };
 
@@ -214,16 +215,15 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         uint32_t v[16];
         ptx::tmem_ld_32x32b_x16(taddr + c, v);
         ptx::tmem_ld_wait();
-        if (row_ok && !p.dbg_no_atomics) {
-          float* slice = p.ws != nullptr ? p.ws + static_cast<size_t>(split) * p.ws_split_stride : nullptr;
+        if (row_ok && !p.dbg_no_store) {
+          float* dst = p.ws != nullptr ? p.ws + static_cast<size_t>(split) * p.ws_split_stride : p.dw;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = nt * p.n_tile + c + j;
             if (co < p.cout_real) {
               const size_t idx = p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + ci
                                           : (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap;
-              if (slice != nullptr) slice[idx] = __uint_as_float(v[j]);       // a warp writes 32 consecutive floats (OHWI)
-              else atomicAdd(p.dw + idx, __uint_as_float(v[j]));
+              dst[idx] = __uint_as_float(v[j]);                               // a warp writes 32 consecutive floats (OHWI)
             }
           }
         }

@@ -30,7 +30,11 @@ struct EpilogueArgs {
   const float* shift_smem;
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
-  float* stat_smem;                 // [2][stat_stride] per-CTA partial sums (kConvStats)
+  // kConvStats: per-CTA partial sums of THIS warp's TMEM lane quadrant, [2][stat_stride] floats (sum, sum of squares).
+  // Every (quadrant, channel) slot is written by exactly one warp (a quadrant's 16-column chunks are dealt to its warps
+  // statically), tiles are processed in a fixed order, so the partials are bit-reproducible; the kernels combine the
+  // four quadrants in a fixed order and add the result exactly (det_sum.cuh).
+  float* stat_smem;
   int stat_stride;
   int ngrp = 2;                     // epilogue warps per TMEM lane quadrant: warp `grp` takes chunks grp, grp+ngrp, ...
   // TMA-store epilogue (N tile == 64 channels == one 128-byte row): instead of 32-byte global stores from every thread
@@ -165,7 +169,7 @@ __device__ __forceinline__ void epilogue_chunks_impl(const EpilogueArgs& p, uint
       // lane bit 4: quantity (sum / sum^2); bits 3,2: which of this thread's four columns; bits 1,0: column pair
       const int kcol = ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
       const int col = 2 * (lane & 3) + (kcol & 1) + ((kcol & 2) ? 8 : 0);
-      atomicAdd(&stat_smem[((lane & 16) ? p.stat_stride : 0) + c + col], a8[0]);
+      stat_smem[((lane & 16) ? p.stat_stride : 0) + c + col] += a8[0];      // this warp owns the slot: no atomic
     }
     if (has_affine) {
       const float4* sc4 = reinterpret_cast<const float4*>(p.scale_smem + ch0);

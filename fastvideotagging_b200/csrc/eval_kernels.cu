@@ -150,10 +150,10 @@ using namespace fvt;
 
 extern "C" {
 
-int fvt_clip_stats_u8(const uint8_t* clips_nthwc, int64_t pixels, uint64_t* sums6, void* stream) {
+int fvt_clip_stats_u8(fvt_handle_t handle, const uint8_t* clips_nthwc, int64_t pixels, uint64_t* sums6, void* stream) {
   if (!clips_nthwc || !sums6 || pixels <= 0) return set_error(FVT_ERR_BAD_DESC, "bad clip_stats arguments");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   cudaMemsetAsync(sums6, 0, 6 * sizeof(uint64_t), (cudaStream_t)stream);
   size_t blocks = (static_cast<size_t>(pixels) + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -162,12 +162,12 @@ int fvt_clip_stats_u8(const uint8_t* clips_nthwc, int64_t pixels, uint64_t* sums
   return check_launch("clip_stats_u8_kernel");
 }
 
-int fvt_clip_normalize_u8(const uint8_t* clips_nthwc, const uint8_t* flip, float* out_ncdhw, int32_t n, int32_t t, int32_t h,
+int fvt_clip_normalize_u8(fvt_handle_t handle, const uint8_t* clips_nthwc, const uint8_t* flip, float* out_ncdhw, int32_t n, int32_t t, int32_t h,
                           int32_t w, float scale, const float mean[3], const float inv_std[3], void* stream) {
   if (!clips_nthwc || !out_ncdhw || !mean || !inv_std || n <= 0 || t <= 0 || h <= 0 || w <= 0)
     return set_error(FVT_ERR_BAD_DESC, "bad clip_normalize arguments");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   const size_t total = static_cast<size_t>(n) * t * h * w;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -176,30 +176,30 @@ int fvt_clip_normalize_u8(const uint8_t* clips_nthwc, const uint8_t* flip, float
   return check_launch("clip_normalize_u8_kernel");
 }
 
-int fvt_softmax_accumulate(const float* logits, float* acc, int32_t rows, int32_t num_class, void* stream) {
+int fvt_softmax_accumulate(fvt_handle_t handle, const float* logits, float* acc, int32_t rows, int32_t num_class, void* stream) {
   if (!logits || !acc || rows <= 0 || num_class <= 0) return set_error(FVT_ERR_BAD_DESC, "bad softmax_accumulate arguments");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   softmax_accumulate_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, acc, rows, num_class);
   return check_launch("softmax_accumulate_kernel");
 }
 
-int fvt_argmax_correct(const float* acc, const int32_t* labels, int32_t rows, int32_t num_class, int32_t* pred,
+int fvt_argmax_correct(fvt_handle_t handle, const float* acc, const int32_t* labels, int32_t rows, int32_t num_class, int32_t* pred,
                        uint64_t* correct, void* stream) {
   if (!acc || rows <= 0 || num_class <= 0 || (labels && !correct)) return set_error(FVT_ERR_BAD_DESC, "bad argmax_correct arguments");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   argmax_correct_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(acc, labels, rows, num_class, pred,
                                                                           reinterpret_cast<unsigned long long*>(correct));
   return check_launch("argmax_correct_kernel");
 }
 
-int fvt_topk_iou(const float* scores, const float* target, int32_t rows, int32_t num_class, int32_t k_max, uint64_t* inter,
+int fvt_topk_iou(fvt_handle_t handle, const float* scores, const float* target, int32_t rows, int32_t num_class, int32_t k_max, uint64_t* inter,
                  uint64_t* uni, void* stream) {
   if (!scores || !target || !inter || !uni || rows <= 0 || num_class <= 0 || k_max < 1 || k_max > 4)
     return set_error(FVT_ERR_BAD_DESC, "bad topk_iou arguments (k_max in [1, 4])");
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   topk_iou_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(scores, target, rows, num_class, k_max,
                                                                     reinterpret_cast<unsigned long long*>(inter),
                                                                     reinterpret_cast<unsigned long long*>(uni));

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "../../include/fvt_b200.h"
+
 namespace fvt {
 
 struct DeviceInfo;
@@ -12,10 +14,13 @@ int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
 // sm_100 check + driver entry points for the current device; nullptr (and *status < 0) when unusable.
 const DeviceInfo* current_device_info(int* status);
+// Validates `h` (fvt_create) and that its device is the calling thread's current device; nullptr (and *status < 0) otherwise.
+const DeviceInfo* handle_device(fvt_handle_t h, int* status);
 const DeviceInfo* device_info(int device, int* status);
 int sm_count_of(const DeviceInfo* di);
-// Epilogue pass of a split-K convolution (bn_kernels.cu): ws fp32 -> y bf16 (+ stats), leaves ws zeroed.
-int launch_splitk_finalize(float* ws, const float* scale, const float* shift, const void* residual, void* y, float* stats,
-                           size_t rows, int c_store, int relu, cudaStream_t stream);
+// Epilogue pass of a split-K convolution (bn_kernels.cu): sum of the `splits` fp32 slices ws[split][rows][c_store], in split
+// order -> y bf16 (+ exact per-channel statistics of the bf16-rounded raw output).
+int launch_splitk_finalize(const float* ws, int splits, const float* scale, const float* shift, const void* residual, void* y,
+                           unsigned long long* stats, size_t rows, int c_store, int relu, cudaStream_t stream);
 
 }  // namespace fvt

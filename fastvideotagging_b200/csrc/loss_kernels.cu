@@ -305,7 +305,9 @@ softmax_kernel(const float* __restrict__ logits, const float* __restrict__ label
   for (int k = threadIdx.x; k < C; k += blockDim.x) se += expf(x[k] - mx);
   const float sum = block_sum(se, red);
   const float lab = label[b];
-  const int li = static_cast<int>(lab);
+  // MXNet's `pick` (SoftmaxCrossEntropyLoss) clips the class index into [0, C-1]; a NaN label picks class 0
+  int li = lab == lab ? static_cast<int>(fminf(fmaxf(lab, -1.f), static_cast<float>(C))) : 0;
+  if (mode == 0) li = li < 0 ? 0 : (li >= C ? C - 1 : li);
   const bool ignored = (mode == 1) && (lab == -1.f);
   for (int k = threadIdx.x; k < C; k += blockDim.x) {
     const float p = expf(x[k] - mx) / sum;
@@ -319,11 +321,11 @@ softmax_kernel(const float* __restrict__ logits, const float* __restrict__ label
 
 using namespace fvt;
 
-static int loss_common_check(const void* pred, const void* target, int batch, int C) {
+static int loss_common_check(fvt_handle_t handle, const void* pred, const void* target, int batch, int C) {
   if (pred == nullptr || target == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer");
   if (batch <= 0 || C <= 0 || C > kMaxClass) return set_error(FVT_ERR_BAD_DESC, "batch=%d num_class=%d out of range (num_class <= %d)", batch, C, kMaxClass);
   int st = 0;
-  if (current_device_info(&st) == nullptr) return st;
+  if (handle_device(handle, &st) == nullptr) return st;
   return 0;
 }
 
@@ -331,9 +333,9 @@ extern "C" {
 
 size_t fvt_loss_workspace_bytes(int32_t batch) { return (static_cast<size_t>(batch) + 4) * sizeof(float); }
 
-int fvt_lsep_fwd_bwd(const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t mode,
+int fvt_lsep_fwd_bwd(fvt_handle_t handle, const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t mode,
                      float* loss, float* grad, void* workspace, void* stream) {
-  if (int e = loss_common_check(pred, target, batch, num_class)) return e;
+  if (int e = loss_common_check(handle, pred, target, batch, num_class)) return e;
   if (loss == nullptr || grad == nullptr || workspace == nullptr) return set_error(FVT_ERR_BAD_DESC, "null output pointer");
   if (mode != 0 && mode != 1) return set_error(FVT_ERR_BAD_DESC, "lsep mode must be 0 (LsepLoss) or 1 (LSEP_funcLoss as written)");
   float* ws = static_cast<float*>(workspace);
@@ -343,10 +345,10 @@ int fvt_lsep_fwd_bwd(const float* pred, const float* target, int32_t batch, int3
   return check_launch("lsep_kernel");
 }
 
-int fvt_warp_fwd_bwd(const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t label_size,
+int fvt_warp_fwd_bwd(fvt_handle_t handle, const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t label_size,
                      int32_t max_trials, int32_t mode, uint64_t seed, uint64_t sample_offset, const float* rank_in,
                      float* rank_out, int32_t* trials_out, float* loss, float* grad, void* workspace, void* stream) {
-  if (int e = loss_common_check(pred, target, batch, num_class)) return e;
+  if (int e = loss_common_check(handle, pred, target, batch, num_class)) return e;
   if (loss == nullptr || grad == nullptr || workspace == nullptr) return set_error(FVT_ERR_BAD_DESC, "null output pointer");
   if (mode != 0 && mode != 1) return set_error(FVT_ERR_BAD_DESC, "warp mode must be 0 (WarpLoss) or 1 (WARP_funcLoss)");
   if (max_trials < 1) return set_error(FVT_ERR_BAD_DESC, "max_trials must be >= 1");
@@ -362,17 +364,17 @@ int fvt_warp_fwd_bwd(const float* pred, const float* target, int32_t batch, int3
   return check_launch("warp_kernel");
 }
 
-int fvt_bce_fwd_bwd(const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t from_sigmoid,
+int fvt_bce_fwd_bwd(fvt_handle_t handle, const float* pred, const float* target, int32_t batch, int32_t num_class, int32_t from_sigmoid,
                     float* loss, float* grad, void* stream) {
-  if (int e = loss_common_check(pred, target, batch, num_class)) return e;
+  if (int e = loss_common_check(handle, pred, target, batch, num_class)) return e;
   if (loss == nullptr) return set_error(FVT_ERR_BAD_DESC, "null output pointer");
   bce_kernel<<<batch, kLossThreads, 0, (cudaStream_t)stream>>>(pred, target, num_class, from_sigmoid, loss, grad);
   return check_launch("bce_kernel");
 }
 
-int fvt_softmax_fwd_bwd(const float* logits, const float* label, int32_t batch, int32_t num_class, int32_t mode,
+int fvt_softmax_fwd_bwd(fvt_handle_t handle, const float* logits, const float* label, int32_t batch, int32_t num_class, int32_t mode,
                         float* out, float* grad, void* stream) {
-  if (int e = loss_common_check(logits, label, batch, num_class)) return e;
+  if (int e = loss_common_check(handle, logits, label, batch, num_class)) return e;
   if (out == nullptr) return set_error(FVT_ERR_BAD_DESC, "null output pointer");
   if (mode != 0 && mode != 1) return set_error(FVT_ERR_BAD_DESC, "softmax mode must be 0 (SoftmaxCrossEntropyLoss) or 1 (SoftmaxOutput)");
   softmax_kernel<<<batch, kLossThreads, 0, (cudaStream_t)stream>>>(logits, label, num_class, mode, out, grad);

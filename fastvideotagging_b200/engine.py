@@ -437,7 +437,7 @@ class FlatParams:
 class _TLayer:
     __slots__ = ("spec", "fwd", "dgr", "w_name", "cin_real", "cout_real", "cin_s", "cout_s", "rows", "in_shape",
                  "out_shape", "src", "raw", "act", "stats", "scale", "shift", "mean", "invstd", "wp", "wpd", "w_eq",
-                 "strided", "need_dgrad")
+                 "strided", "need_dgrad", "dplan")
 
 
 class TrainPlan:
@@ -453,11 +453,10 @@ class TrainPlan:
         self.device = device
         self.eps, self.momentum = eps, momentum
         self.n, self.t, self.h, self.w = n, t, h, w
-        # FVT_WGRAD_WS=1: the pixel splits of a slab weight gradient are reduced through a scratch buffer (plain stores +
-        # one reduce pass, fixed order -> bit-reproducible gradients) instead of fp32 atomics.  Measured no faster inside
-        # the step (11.68 vs 11.53 ms: the atomics overlap the data-gradient chain on the side stream), so off by default.
-        # All weight gradients run on ONE stream, so one buffer per device is enough.
-        self._wgrad_ws = ops.wgrad_workspace(device, enable=os.environ.get("FVT_WGRAD_WS", "0") == "1")
+        # The whole step is deterministic: weight gradients reduce their pixel splits through workspace slices in a fixed
+        # order (ops.wgrad_workspace, one per stream), BatchNorm sums use exact accumulators, split-K uses slices.  Every
+        # gradient slot is OVERWRITTEN by backward() (MXNet grad_req='write'), so the gradient buffer is never zeroed.
+        self.fwd_generation = 0          # bumped by every training forward: backward() refuses a stale forward
         self.num_class = num_class
         self.bufs = {}
         self.layers = {}
@@ -493,6 +492,7 @@ class TrainPlan:
             for nm in ("scale", "shift", "mean", "invstd"):
                 setattr(L, nm, buf(spec.name + ":" + nm, (L.cout_s,), torch.float32))
             L.wp = L.wpd = L.w_eq = None
+            L.dplan = None
             self.layers[spec.name] = L
             return L
 
@@ -518,8 +518,8 @@ class TrainPlan:
             for L in (a, b, c, d):
                 max_elems = max(max_elems, L.raw.numel(), L.in_shape[0] * L.in_shape[1] * L.in_shape[2] * L.in_shape[3] * L.in_shape[4])
         self.final_name, self.final_shape = cur_name, cur_shape
-        # per-channel (sum, sum^2) accumulators of every conv in ONE buffer: a single memset per step
-        self.stats_all = torch.zeros(sum(2 * L.cout_s for L in self.layers.values()), dtype=torch.float32, device=device)
+        # per-channel (sum, sum^2) exact accumulators of every conv in ONE buffer: a single memset per step
+        self.stats_all = ops.stats_buffer(sum(L.cout_s for L in self.layers.values()), device)
         off = 0
         for L in self.layers.values():
             L.stats = self.stats_all[off:off + 2 * L.cout_s]
@@ -537,6 +537,7 @@ class TrainPlan:
             buf(nm, (max_elems,))
         buf("up", (up_elems,))
         self.pooled = None
+        self._dweq = None                # gradient of the stem's equivalent filter (re-mapped into conv1_middle_weight's slot)
         self.launches_fwd = self.launches_bwd = 0
         # CUDA graphs: the ~700 launches of a step are captured once (forward graph, backward graph) and replayed, so
         # the step is not paced by Python/ctypes launch overhead.  FVT_CUDA_GRAPHS=0 runs every launch eagerly.
@@ -551,12 +552,23 @@ class TrainPlan:
         # layers, and every weight gradient runs beside the data-gradient chain it does not feed.  At batch 4 the
         # conv4_x / conv5_x launches fill 14-49 of the 148 SMs, so the two branches genuinely overlap.
         self.side = torch.cuda.Stream(device=device) if os.environ.get("FVT_SIDE_STREAM", "1") != "0" else None
-        self._packed_ev = {}
+        self._packed_ev = None
+        self._pack_f = self._pack_d = None
+        self.dgrad_direct = os.environ.get("FVT_DGRAD_DIRECT", "1") != "0"
         self._busy = {}                  # scratch buffer name -> event recorded after its last reader on the side stream
         self._draw_i = 0
         # timing experiments only (tools/gpu_train_ablate.py): FVT_SKIP=wgrad,dgrad,bnbwd leaves those launches out, which
         # shows each family's marginal cost inside the replayed graph (results are garbage then)
         self._skip = set(filter(None, os.environ.get("FVT_SKIP", "").split(",")))
+
+    def set_hooks(self, grad_hook, finish_hook):
+        """Attach (or change) the gradient-reduction hooks.  They are baked into the captured backward graph, so a change
+        drops the graphs (re-captured on the next steps)."""
+        if grad_hook is self.grad_hook and finish_hook is self.finish_hook:
+            return
+        self.grad_hook, self.finish_hook = grad_hook, finish_hook
+        self._fwd_graph = self._bwd_graph = None
+        self._warm_fwd = self._warm_bwd = 0
 
     # ------------------------------------------------------------------ weights
     def _w(self, L):
@@ -565,43 +577,56 @@ class TrainPlan:
     def _w_raw(self, L):
         return self.flat.raw(self.flat.w, L.w_name)
 
-    def _pack_fwd(self, L):
-        if L is self.stem0:       # the stem filter is re-expressed over the W-unfolded input (a tiny tensor: torch ops)
-            L.wp = ops.pack_conv_weight(L.fwd, self.stem.weight(self._w(L)), out=L.wp)
-        else:
-            L.wp = ops.pack_conv_weight(L.fwd, self._w_raw(L), out=L.wp, ohwi=True)
+    def _build_pack_tables(self):
+        """Operand copies of all conv weights in TWO launches (forward layouts, then data-gradient layouts) instead of 137
+        (ops.PackTable); the stem's equivalent filter (a 45 x 64 x 5 tensor re-expressed over the W-unfolded input) keeps
+        its own small path."""
+        self._pack_f, self._pack_d = ops.PackTable(self.device), ops.PackTable(self.device)
+        for L in self.layers.values():
+            if L is self.stem0:
+                continue
+            L.wp = self._pack_f.add_fwd(L.fwd, self._w_raw(L))
+        for L in reversed(list(self.layers.values())):
+            if not L.need_dgrad:
+                continue
+            if L.strided and self.dgrad_direct:
+                # data gradient of a strided convolution: one stride-1 sub-convolution of dY per parity class of dX
+                # (ops.DgradPlan) instead of zero-insert + a full convolution over the input extent
+                L.dplan = ops.DgradPlan(L.fwd, self._w_raw(L), self._pack_d)
+            else:
+                L.wpd = self._pack_d.add_dgrad(L.dgr, self._w_raw(L))
 
     def refresh_weights(self, version):
         """Re-pack bf16 operand copies of the fp32 master weights (forward and data-gradient layouts).  With the side
-        stream the packing launches form a branch parallel to the forward pass: forward-layout copies in layer order
-        (each conv waits for its own copy only, `_wait_packed`), then the data-gradient copies, joined by
-        `_join_side()` at the end of the forward pass."""
-        self._packed_ev = {}
+        stream the packing launches form a branch parallel to the forward pass: the forward-layout copies (the stem's
+        first, then everything else in one launch; the first conv after the stem waits for it, `_wait_packed`), then the
+        data-gradient copies, joined by `_join_side()` at the end of the forward pass."""
+        self._packed_ev = None
         if version == self.weights_version:
             return
+        if self._pack_f is None:
+            self._build_pack_tables()
         main = torch.cuda.current_stream(self.device)
+        L0 = self.stem0
         if self.side is None:
-            for L in self.layers.values():
-                self._pack_fwd(L)                                             # packed buffers are allocated once
-                if L.need_dgrad:
-                    L.wpd = ops.pack_conv_weight_dgrad(L.dgr, self._w_raw(L), out=L.wpd, ohwi=True)
+            L0.wp = ops.pack_conv_weight(L0.fwd, self.stem.weight(self._w(L0)), out=L0.wp)
+            self._pack_f.run()
+            self._pack_d.run()
         else:
             self.side.wait_stream(main)
+            L0.wp = ops.pack_conv_weight(L0.fwd, self.stem.weight(self._w(L0)), out=L0.wp)     # tiny: on the main stream
             with torch.cuda.stream(self.side):
-                for L in self.layers.values():
-                    self._pack_fwd(L)
-                    ev = torch.cuda.Event()
-                    ev.record(self.side)
-                    self._packed_ev[L.spec.name] = ev
-                for L in reversed(list(self.layers.values())):
-                    if L.need_dgrad:
-                        L.wpd = ops.pack_conv_weight_dgrad(L.dgr, self._w_raw(L), out=L.wpd, ohwi=True)
+                self._pack_f.run()
+                self._packed_ev = torch.cuda.Event()
+                self._packed_ev.record(self.side)
+                self._pack_d.run()
         self.weights_version = version
 
     def _wait_packed(self, L):
-        ev = self._packed_ev.pop(L.spec.name, None)
-        if ev is not None:
-            torch.cuda.current_stream(self.device).wait_event(ev)
+        if L is self.stem0 or self._packed_ev is None:
+            return
+        torch.cuda.current_stream(self.device).wait_event(self._packed_ev)
+        self._packed_ev = None
 
     def _join_side(self):
         if self.side is not None:
@@ -627,12 +652,12 @@ class TrainPlan:
             ops.bn_finalize_apply(*args, L.raw, L.act, True, **apply)
 
     def forward(self, x, weights_version):
-        """Training-mode forward: re-pack bf16 operand copies if the weights changed, zero the gradient buffer
-        (grad_req='write'), run the network.  Returns fp32 logits (N, num_class)."""
+        """Training-mode forward: re-pack bf16 operand copies if the weights changed, run the network.  Returns fp32
+        logits (N, num_class)."""
         assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w)
+        self.fwd_generation += 1
         if not self.use_graphs:
             self.refresh_weights(weights_version)
-            self.flat.g.zero_()
             out = self._forward_body(x.contiguous())
             self._join_side()
             return out
@@ -641,7 +666,6 @@ class TrainPlan:
             if self._warm_fwd < 1:                      # first call: eager (one-time initialisation inside the library)
                 self._warm_fwd += 1
                 self.refresh_weights(weights_version)
-                self.flat.g.zero_()
                 out = self._forward_body(self.x_static)
                 self._join_side()
                 return out
@@ -649,7 +673,6 @@ class TrainPlan:
             with torch.cuda.graph(graph):
                 self.weights_version = -1               # the graph always re-packs: weights change every step
                 self.refresh_weights(0)
-                self.flat.g.zero_()
                 self._logits_static = self._forward_body(self.x_static)
                 self._join_side()
             self._fwd_graph = graph
@@ -733,15 +756,18 @@ class TrainPlan:
             return
         if L is self.stem0:
             k = self.stem.kernel
-            dweq = torch.zeros((45, self.stem.cin_real, k[0], k[1], k[2]), dtype=torch.float32, device=self.device)
-            ops.conv3d_wgrad(L.fwd, x_in, draw, dweq, 45, self.stem.cin_real)
-            self.flat.view(self.flat.g, L.w_name).add_(self.stem.weight_grad(dweq))
+            if self._dweq is None:
+                self._dweq = torch.zeros((45, self.stem.cin_real, k[0], k[1], k[2]), dtype=torch.float32, device=self.device)
+            ops.conv3d_wgrad(L.fwd, x_in, draw, self._dweq, 45, self.stem.cin_real)
+            self.flat.view(self.flat.g, L.w_name).copy_(self.stem.weight_grad(self._dweq))
         else:
             ops.conv3d_wgrad(L.fwd, x_in, draw, self.flat.raw(self.flat.g, L.w_name), L.cout_real, L.cin_real, ohwi=True)
 
     def _dgrad(self, L, draw, out, residual=None):
         if "dgrad" in self._skip:
             return out
+        if L.dplan is not None:
+            return L.dplan.run(draw, out, residual)
         src = draw
         if L.strided:
             src = ops.zero_insert(draw, L.fwd, out=self._view("up", (L.fwd.n, L.fwd.t, L.fwd.h, L.fwd.w, L.cout_s)))
@@ -753,7 +779,7 @@ class TrainPlan:
         return out
 
     def backward(self, dlogits):
-        """dlogits: (N, num_class) fp32.  Accumulates into flat.g (zeroed by forward())."""
+        """dlogits: (N, num_class) fp32.  Overwrites every slot of flat.g (grad_req='write')."""
         if not self.use_graphs:
             return self._backward_body(dlogits.contiguous())
         self.dlogits_static.copy_(dlogits)

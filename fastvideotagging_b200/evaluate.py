@@ -30,14 +30,14 @@ class MultiClipAccumulator:
         rows = logits.shape[0]
         assert logits.shape[1] == self.num_class and 0 <= row0 and row0 + rows <= self.n_rows
         dst = self.acc[row0:row0 + rows]
-        check(_lib.load().fvt_softmax_accumulate(_ptr(logits), _ptr(dst), rows, self.num_class, _stream()))
+        check(_lib.load().fvt_softmax_accumulate(_lib.handle(), _ptr(logits), _ptr(dst), rows, self.num_class, _stream()))
 
     def predictions(self, labels=None):
         """-> (pred (n_rows,) int32, accuracy or None).  One device->host read for the accuracy, none without labels."""
         pred = torch.empty(self.n_rows, dtype=torch.int32, device=self.acc.device)
         correct = torch.zeros(1, dtype=torch.int64, device=self.acc.device)
         lab = labels.to(self.acc.device, torch.int32).contiguous() if labels is not None else None
-        check(_lib.load().fvt_argmax_correct(_ptr(self.acc), _ptr(lab), self.n_rows, self.num_class, _ptr(pred), _ptr(correct), _stream()))
+        check(_lib.load().fvt_argmax_correct(_lib.handle(), _ptr(self.acc), _ptr(lab), self.n_rows, self.num_class, _ptr(pred), _ptr(correct), _stream()))
         return pred, (correct.item() / float(self.n_rows) if labels is not None else None)
 
 
@@ -53,7 +53,7 @@ class TopkIoU:
         require_cuda(y_hat, "y_hat")
         y_hat = y_hat.float().contiguous()
         y = y.to(y_hat.device, torch.float32).contiguous()
-        check(_lib.load().fvt_topk_iou(_ptr(y_hat), _ptr(y), y_hat.shape[0], y_hat.shape[1], self.k, _ptr(self.inter),
+        check(_lib.load().fvt_topk_iou(_lib.handle(), _ptr(y_hat), _ptr(y), y_hat.shape[0], y_hat.shape[1], self.k, _ptr(self.inter),
                                        _ptr(self.union), _stream()))
 
     def value(self):
@@ -82,16 +82,16 @@ def normalize_clips(clips_u8, flip=None, mode="batch"):
     if mode == "batch":
         sums = torch.empty(6, dtype=torch.int64, device=clips_u8.device)
         pixels = n * t * h * w
-        check(lib.fvt_clip_stats_u8(_ptr(clips_u8), pixels, _ptr(sums), _stream()))
+        check(lib.fvt_clip_stats_u8(_lib.handle(), _ptr(clips_u8), pixels, _ptr(sums), _stream()))
         s = sums.cpu().double()
         mean = s[:3] / pixels
         std = torch.sqrt(torch.clamp(s[3:] / pixels - mean * mean, min=0.0))
         inv = 1.0 / (std + 1e-3)
-        check(lib.fvt_clip_normalize_u8(_ptr(clips_u8), _ptr(flip_t), _ptr(out), n, t, h, w, ctypes.c_float(1.0),
+        check(lib.fvt_clip_normalize_u8(_lib.handle(), _ptr(clips_u8), _ptr(flip_t), _ptr(out), n, t, h, w, ctypes.c_float(1.0),
                                         f3(*mean.tolist()), f3(*inv.tolist()), _stream()))
         return out, mean.float(), std.float()
     if mode == "imagenet":
-        check(lib.fvt_clip_normalize_u8(_ptr(clips_u8), _ptr(flip_t), _ptr(out), n, t, h, w, ctypes.c_float(1.0 / 255.0),
+        check(lib.fvt_clip_normalize_u8(_lib.handle(), _ptr(clips_u8), _ptr(flip_t), _ptr(out), n, t, h, w, ctypes.c_float(1.0 / 255.0),
                                         f3(*IMAGENET_MEAN), f3(*[1.0 / v for v in IMAGENET_STD]), _stream()))
         return out
     raise ValueError("mode must be 'batch' or 'imagenet'")

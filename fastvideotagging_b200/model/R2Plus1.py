@@ -42,11 +42,22 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, x, net, anchor):
         plan = net._train_plan(x)
         ctx.plan = plan
-        return plan.forward(x, net._weights_version)      # also zeroes the gradient buffer (grad_req='write')
+        out = plan.forward(x, net._weights_signature())
+        # Activations, BatchNorm statistics and the pooled features live in plan-owned buffers that the next same-shape
+        # forward overwrites: remember which forward this graph node belongs to.
+        ctx.generation = plan.fwd_generation
+        net._plans.clear()          # a training forward moves the running statistics: folded-BN inference plans are stale
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
-        ctx.plan.backward(dlogits.float())
+        plan = ctx.plan
+        if ctx.generation != plan.fwd_generation:
+            raise RuntimeError(
+                "backward() of a training forward whose saved activations were overwritten by a later forward of the same "
+                "shape on this network (forward #%d, current #%d).  Run forward -> backward per batch shard (the one-process-"
+                "per-GPU form of train_simple_r3d.py:116-123), or use different networks per shard." % (ctx.generation, plan.fwd_generation))
+        plan.backward(dlogits.float())       # every gradient slot is overwritten (MXNet grad_req='write')
         return None, None, None
 
 
@@ -218,17 +229,37 @@ class R2Plus2D(torch.nn.Module):
         self._weights_version += 1
         self._plans.clear()
 
+    def _weights_signature(self):
+        """Changes whenever any parameter or running statistic changes: the module's own counter (bumped by Trainer.step,
+        load_param_dict, initialize — they write through raw pointers) plus torch's in-place version counters, so that a
+        torch.optim step, load_state_dict or any other in-place edit also invalidates packed weights and folded plans."""
+        if self._flat is not None:
+            v = self._flat.w._version          # the parameters are views of one buffer: one shared counter
+        else:
+            v = sum(getattr(self, n)._version for n in self._param_names)
+        return (self._weights_version, v, sum(getattr(self, n)._version for n in self._aux_names))
+
+    def zero_grad(self, set_to_none=False):
+        """The .grad tensors are views of the flat gradient buffer (what the NCCL buckets and the fused SGD launch read):
+        they are zeroed in place, never detached."""
+        if self._flat is not None:
+            self._flat.g.zero_()
+        else:
+            super().zero_grad(set_to_none=set_to_none)
+
     def _attach_trainer(self, trainer):
         self._trainer = trainer
         for plan in self._train_plans.values():
-            plan.grad_hook = trainer.on_grads_ready
-            plan.finish_hook = trainer.allreduce_grads
+            plan.set_hooks(trainer.on_grads_ready, trainer.allreduce_grads)
 
     def _ensure_flat(self, device):
         """Move every trainable tensor into one flat fp32 buffer (engine.FlatParams); the nn.Parameters become views
         of it and their .grad views of the flat gradient buffer."""
         if self._flat is not None and self._flat.w.device == device:
             return self._flat
+        if self._flat is not None:
+            raise RuntimeError("this network already trains on %s; one process per GPU: build one network per device "
+                               "(torch.distributed), do not move a training network between devices" % self._flat.w.device)
         flat = engine.FlatParams(self.model_depth, self.num_class, device)
         with torch.no_grad():
             for name in self._param_names:
@@ -255,13 +286,16 @@ class R2Plus2D(torch.nn.Module):
             plan = engine.TrainPlan(flat, aux, self.model_depth, self.num_class, self.pool, self.bn_eps, n, t, h, w,
                                     x.device, momentum=self.bn_momentum)
             if self._trainer is not None:
-                plan.grad_hook = self._trainer.on_grads_ready
-                plan.finish_hook = self._trainer.allreduce_grads
+                plan.set_hooks(self._trainer.on_grads_ready, self._trainer.allreduce_grads)
             self._train_plans[key] = plan
         return plan
 
     # ------------------------------------------------------------------ forward
     def _inference_plan(self, x):
+        sig = self._weights_signature()
+        if sig != getattr(self, "_plans_sig", None):       # parameters edited in place behind our back: re-fold / re-pack
+            self._plans.clear()
+            self._plans_sig = sig
         key = (tuple(x.shape), x.device.index)
         plan = self._plans.get(key)
         if plan is None:

@@ -89,7 +89,7 @@ class Conv3D(torch.nn.Module):
         # training mode: batch statistics (biased variance), running-stat update with the MXNet convention
         d = ops.conv_desc(n, t, h, w, cs, cout_s, self.kernel, self.strides, self.padding, FVT_CONV_STATS)
         wp = ops.pack_conv_weight(d, self.weight)
-        stats = torch.zeros(2 * cout_s, dtype=torch.float32, device=x.device)
+        stats = ops.stats_buffer(cout_s, x.device)
         raw = ops.conv3d_fwd(d, x, wp, stats=stats)
         rows = raw.numel() // cout_s
         scale, shift, mean, invstd = (torch.empty(cout_s, dtype=torch.float32, device=x.device) for _ in range(4))

@@ -35,7 +35,7 @@ class _LsepFn(torch.autograd.Function):
         b, c = p.shape
         loss = torch.empty(1, dtype=torch.float32, device=p.device)
         grad = torch.empty_like(p)
-        _lib.check(lib.fvt_lsep_fwd_bwd(_ptr(p), _ptr(t), b, c, mode, _ptr(loss), _ptr(grad), _ptr(_workspace(b, p.device)), _stream()))
+        _lib.check(lib.fvt_lsep_fwd_bwd(_lib.handle(), _ptr(p), _ptr(t), b, c, mode, _ptr(loss), _ptr(grad), _ptr(_workspace(b, p.device)), _stream()))
         ctx.save_for_backward(grad)
         return loss
 
@@ -80,7 +80,7 @@ class _WarpFn(torch.autograd.Function):
         grad = torch.empty_like(p)
         rank = torch.empty_like(p)
         trials = torch.empty((b, c), dtype=torch.int32, device=p.device)
-        _lib.check(lib.fvt_warp_fwd_bwd(_ptr(p), _ptr(t), b, c, label_size, max_trials, mode,
+        _lib.check(lib.fvt_warp_fwd_bwd(_lib.handle(), _ptr(p), _ptr(t), b, c, label_size, max_trials, mode,
                                         ctypes.c_uint64(seed), ctypes.c_uint64(sample_offset), _ptr(rank_in),
                                         _ptr(rank), _ptr(trials), _ptr(loss), _ptr(grad),
                                         _ptr(_workspace(b, p.device)), _stream()))
@@ -143,7 +143,7 @@ class _BceFn(torch.autograd.Function):
         b, c = p.shape
         loss = torch.empty(b, dtype=torch.float32, device=p.device)
         grad = torch.empty_like(p)
-        _lib.check(lib.fvt_bce_fwd_bwd(_ptr(p), _ptr(t), b, c, int(from_sigmoid), _ptr(loss), _ptr(grad), _stream()))
+        _lib.check(lib.fvt_bce_fwd_bwd(_lib.handle(), _ptr(p), _ptr(t), b, c, int(from_sigmoid), _ptr(loss), _ptr(grad), _stream()))
         ctx.save_for_backward(grad)
         return loss
 
@@ -175,7 +175,7 @@ class _SoftmaxFn(torch.autograd.Function):
         b, c = x.shape
         out = torch.empty((b,) if mode == 0 else (b, c), dtype=torch.float32, device=x.device)
         grad = torch.empty_like(x)
-        _lib.check(lib.fvt_softmax_fwd_bwd(_ptr(x), _ptr(lab), b, c, mode, _ptr(out), _ptr(grad), _stream()))
+        _lib.check(lib.fvt_softmax_fwd_bwd(_lib.handle(), _ptr(x), _ptr(lab), b, c, mode, _ptr(out), _ptr(grad), _stream()))
         ctx.save_for_backward(grad)
         ctx.mode = mode
         return out

@@ -4,7 +4,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, FVT_CONV_RELU, FVT_CONV_RESIDUAL, FVT_CONV_STATS, FVT_CONV_W_OHWI, check
+from ._lib import ConvDesc, ConvExt, FVT_CONV_RELU, FVT_CONV_RESIDUAL, FVT_CONV_STATS, FVT_CONV_W_OHWI, check
 
 
 def pad16(c):
@@ -17,6 +17,47 @@ def _ptr(t):
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _h(t=None):
+    """The calling thread's library handle for the device `t` lives on (the current device when t is None).  The
+    library refuses a handle whose device is not the current one, so a tensor on another device is an error here, not
+    a launch on the wrong GPU."""
+    return _lib.handle(t.device.index if (t is not None and t.is_cuda) else None)
+
+
+set_option = _lib.set_option
+get_option = _lib.get_option
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# exact per-channel accumulators (fvt_stats_bytes): 4 int64 limbs per value
+# ---------------------------------------------------------------------------------------------------------------------
+STAT_LIMBS = 4
+
+
+def stats_buffer(c_store, device):
+    """Zeroed [2][c_store] accumulators for fvt_conv3d_fwd(FVT_CONV_STATS) / fvt_bn_finalize: int64 (2*c_store, 4)."""
+    return torch.zeros((2 * c_store, STAT_LIMBS), dtype=torch.int64, device=device)
+
+
+def stats_encode(values):
+    """float tensor (n,) -> accumulators (n, 4) holding exactly those values (tests / interop)."""
+    lib = _lib.load()
+    v = values.detach().to(torch.float32).contiguous()
+    out = torch.empty((v.numel(), STAT_LIMBS), dtype=torch.int64, device=v.device)
+    check(lib.fvt_stats_encode(_h(v), _ptr(v), _ptr(out), v.numel(), _stream()))
+    return out
+
+
+def stats_decode(acc):
+    """accumulators (n, 4) -> float32 tensor (n,)."""
+    lib = _lib.load()
+    assert acc.dtype == torch.int64 and acc.is_contiguous()
+    n = acc.numel() // STAT_LIMBS
+    out = torch.empty(n, dtype=torch.float32, device=acc.device)
+    check(lib.fvt_stats_decode(_h(acc), _ptr(acc), _ptr(out), n, _stream()))
+    return out
 
 
 def require_cuda(t, name):
@@ -56,21 +97,23 @@ def pack_conv_weight(desc, w_oidhw, out=None, ohwi=False):
     assert out.numel() == elems and out.dtype == torch.bfloat16
     d = _with_ohwi(desc) if ohwi else desc
     cout, cin = (w.shape[0], w.shape[4]) if ohwi else (w.shape[0], w.shape[1])
-    check(lib.fvt_pack_conv_weight(ctypes.byref(d), _ptr(w), cout, cin, _ptr(out), _stream()))
+    check(lib.fvt_pack_conv_weight(_h(w), ctypes.byref(d), _ptr(w), cout, cin, _ptr(out), _stream()))
     return out
 
 
 _WORKSPACE = {}
-WORKSPACE_BYTES = 64 << 20
+WORKSPACE_BYTES = 128 << 20
 
 
-def workspace(device):
-    """Per-device zeroed fp32 scratch handed to fvt_conv3d_fwd (split-K of small-M convolutions).  The library keeps it
-    zeroed, so it is allocated and cleared exactly once."""
-    key = (device.type, device.index)
+def workspace(device, stream=None):
+    """Caller-owned fp32 scratch handed to fvt_conv3d_fwd (split-K slices of small-M convolutions), one per (device,
+    stream): launches that share a workspace must be stream-ordered.  Contents are irrelevant between calls."""
+    if stream is None:
+        stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device.type, device.index, int(stream))
     ws = _WORKSPACE.get(key)
     if ws is None:
-        ws = torch.zeros(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
+        ws = torch.empty(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
         _WORKSPACE[key] = ws
     return ws
 
@@ -85,15 +128,88 @@ def conv3d_fwd(desc, x, w_packed, scale=None, shift=None, residual=None, out=Non
     if out is None:
         out = torch.empty((desc.n, to, ho, wo, desc.cout), dtype=torch.bfloat16, device=x.device)
     ws = workspace(x.device)
-    check(lib.fvt_conv3d_fwd(ctypes.byref(desc), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(residual),
+    if stats is not None:
+        assert stats.dtype == torch.int64 and stats.numel() == 2 * desc.cout * STAT_LIMBS, "stats: ops.stats_buffer(cout)"
+    check(lib.fvt_conv3d_fwd(_h(x), ctypes.byref(desc), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(residual),
                              _ptr(out), _ptr(stats), _ptr(ws), ws.numel() * 4, _stream()))
     return out
+
+
+def conv3d_fwd_ex(desc, ext, x, w_packed, out, scale=None, shift=None, residual=None):
+    """fvt_conv3d_fwd_ex: `desc` with per-axis high padding and the result written onto a lattice of `out` (see the header;
+    the building block of strided data gradients).  out: (N, T, H, W, cout) bf16, partially written."""
+    lib = _lib.load()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
+    assert tuple(x.shape) == (desc.n, desc.t, desc.h, desc.w, desc.cin), (tuple(x.shape), desc.key())
+    assert tuple(out.shape) == (desc.n, ext.out_extent[0], ext.out_extent[1], ext.out_extent[2], desc.cout), tuple(out.shape)
+    check(lib.fvt_conv3d_fwd_ex(_h(x), ctypes.byref(desc), ctypes.byref(ext), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift),
+                                _ptr(residual), _ptr(out), _stream()))
+    return out
+
+
+class DgradPlan:
+    """Data gradient of a STRIDED convolution as one stride-1 sub-convolution of dY per parity class of dX (header:
+    fvt_conv3d_fwd_ex).  fwd: the forward descriptor (stored channel counts); w_ohwi: its fp32 master (O, kT, kH, kW, I);
+    the sub-filters are registered in `pack_table` (re-packed with the other operand copies).
+    run(dy, out, residual=None): out (N, T, H, W, cin) bf16 <- dgrad (+ residual)."""
+
+    def __init__(self, fwd, w_ohwi, pack_table):
+        self.fwd = fwd
+        to, ho, wo = conv_out_shape(fwd)
+        x_ext, o_ext = (fwd.t, fwd.h, fwd.w), (to, ho, wo)
+        k, s, p = (fwd.kt, fwd.kh, fwd.kw), (fwd.st, fwd.sh, fwd.sw), (fwd.pt, fwd.ph, fwd.pw)
+        self.classes = []
+        self.needs_clear = False
+        for par_t in range(s[0]):
+            for par_h in range(s[1]):
+                for par_w in range(s[2]):
+                    par = (par_t, par_h, par_w)
+                    sub_k, tap_a, pad_hi, empty = [], [], [], False
+                    for a in range(3):
+                        count = (x_ext[a] - par[a] + s[a] - 1) // s[a]             # dX positions of this class on the axis
+                        es = [(par[a] + p[a] - kk) // s[a] for kk in range(k[a]) if (par[a] + p[a] - kk) % s[a] == 0]
+                        if count <= 0 or not es:
+                            empty = True
+                            break
+                        if min(es) < 0:
+                            raise NotImplementedError("padding >= stride*... is not used by the reference's convolutions")
+                        # dY[j + e] for e = 0 .. max(es) (taps that do not exist for some e in between have zero weight:
+                        # the tap map skips nothing here because es is contiguous for k <= s + 1 ... checked below)
+                        if sorted(es) != list(range(0, max(es) + 1)):
+                            raise NotImplementedError("non-contiguous parity taps")
+                        sub_k.append(max(es) + 1)
+                        tap_a.append(par[a] + p[a])
+                        pad_hi.append(count - o_ext[a] + sub_k[-1] - 1)
+                        if pad_hi[-1] < 0:
+                            raise NotImplementedError("parity class smaller than dY")
+                    if empty:
+                        self.needs_clear = True
+                        continue
+                    sub = ConvDesc(fwd.n, to, ho, wo, fwd.cout, fwd.cin, sub_k[0], sub_k[1], sub_k[2], 1, 1, 1, 0, 0, 0, 0, 0)
+                    ext = ConvExt((ctypes.c_int32 * 3)(*pad_hi), (ctypes.c_int32 * 3)(*x_ext), (ctypes.c_int32 * 3)(*s),
+                                  (ctypes.c_int32 * 3)(*par))
+                    wp = pack_table.add_dgrad_sub(sub, w_ohwi, tap_a, s)
+                    self.classes.append((sub, ext, wp))
+
+    def run(self, dy, out, residual=None):
+        if self.needs_clear:
+            if residual is not None:
+                out.copy_(residual)              # classes no filter tap reaches carry the residual alone
+            else:
+                out.zero_()
+        for sub, ext, wp in self.classes:
+            d = sub
+            if residual is not None:
+                d = ConvDesc(*sub.key())
+                d.flags = FVT_CONV_RESIDUAL
+            conv3d_fwd_ex(d, ext, dy, wp, out, residual=residual)
+        return out
 
 
 def unit2p1_supported(d_spatial, d_temporal):
     """True when the (1x3x3, 3x1x1) descriptor pair can run as ONE fused launch (fvt_unit2p1_fwd) on this device."""
     lib = _lib.load()
-    return check(lib.fvt_unit2p1_supported(ctypes.byref(d_spatial), ctypes.byref(d_temporal))) == 1
+    return check(lib.fvt_unit2p1_supported(_h(), ctypes.byref(d_spatial), ctypes.byref(d_temporal))) == 1
 
 
 def unit2p1_fwd(d_spatial, d_temporal, x, w_spatial, scale_mid, shift_mid, w_temporal, scale_out, shift_out,
@@ -107,7 +223,7 @@ def unit2p1_fwd(d_spatial, d_temporal, x, w_spatial, scale_mid, shift_mid, w_tem
     if out is None:
         out = torch.empty((d_temporal.n, d_temporal.t, d_temporal.h, d_temporal.w, d_temporal.cout), dtype=torch.bfloat16,
                           device=x.device)
-    check(lib.fvt_unit2p1_fwd(ctypes.byref(d_spatial), ctypes.byref(d_temporal), _ptr(x), _ptr(w_spatial), _ptr(scale_mid),
+    check(lib.fvt_unit2p1_fwd(_h(x), ctypes.byref(d_spatial), ctypes.byref(d_temporal), _ptr(x), _ptr(w_spatial), _ptr(scale_mid),
                               _ptr(shift_mid), _ptr(w_temporal), _ptr(scale_out), _ptr(shift_out), _ptr(residual),
                               _ptr(out), _stream()))
     return out
@@ -122,7 +238,7 @@ def stem_unfold(x_ncdhw, kw_taps=7, sw=2, pw=3, cu=32, out=None):
     wo = (w + 2 * pw - kw_taps) // sw + 1
     if out is None:
         out = torch.empty((n, t, h, wo, cu), dtype=torch.bfloat16, device=x_ncdhw.device)
-    check(lib.fvt_stem_unfold(_ptr(x_ncdhw), _ptr(out), n, t, h, w, kw_taps, sw, pw, cu, _stream()))
+    check(lib.fvt_stem_unfold(_h(x_ncdhw), _ptr(x_ncdhw), _ptr(out), n, t, h, w, kw_taps, sw, pw, cu, _stream()))
     return out
 
 
@@ -135,7 +251,7 @@ def stem_unfold_hpair(x_ncdhw, kw_taps=7, sw=2, pw=3, cu=32, out=None):
     wo = (w + 2 * pw - kw_taps) // sw + 1
     if out is None:
         out = torch.empty((n, t, h // 2, wo, 2 * cu), dtype=torch.bfloat16, device=x_ncdhw.device)
-    check(lib.fvt_stem_unfold_hpair(_ptr(x_ncdhw), _ptr(out), n, t, h, w, kw_taps, sw, pw, cu, _stream()))
+    check(lib.fvt_stem_unfold_hpair(_h(x_ncdhw), _ptr(x_ncdhw), _ptr(out), n, t, h, w, kw_taps, sw, pw, cu, _stream()))
     return out
 
 
@@ -149,7 +265,7 @@ def pool_fc_fwd(x, c_real, weight, bias, want_pooled=False):
     num_class = weight.shape[0] if weight is not None else 0
     logits = torch.empty((n, num_class), dtype=torch.float32, device=x.device) if weight is not None else None
     pooled = torch.empty((n, c_real), dtype=torch.float32, device=x.device) if want_pooled else None
-    check(lib.fvt_pool_fc_fwd(_ptr(x), n, positions, c, c_real, _ptr(weight), _ptr(bias), num_class, _ptr(pooled),
+    check(lib.fvt_pool_fc_fwd(_h(x), _ptr(x), n, positions, c, c_real, _ptr(weight), _ptr(bias), num_class, _ptr(pooled),
                               _ptr(logits), _stream()))
     return (logits, pooled) if want_pooled else logits
 
@@ -158,24 +274,26 @@ def pool_fc_fwd(x, c_real, weight, bias, want_pooled=False):
 # training ops
 # ---------------------------------------------------------------------------------------------------------------------
 _WGRAD_WS = {}
-WGRAD_WS_BYTES = 160 << 20
+WGRAD_WS_BYTES = 192 << 20
 
 
-def wgrad_workspace(device, enable=True):
-    """Registers (once per device) the scratch the slab weight-gradient kernels reduce their pixel splits through
-    (fvt_set_wgrad_workspace) — plain stores + one reduce pass instead of fp32 atomics.  enable=False withdraws it."""
-    lib = _lib.load()
-    key = (device.type, device.index)
-    with torch.cuda.device(device):
-        if not enable:
-            check(lib.fvt_set_wgrad_workspace(None, 0))
-            return None
-        ws = _WGRAD_WS.get(key)
-        if ws is None:
-            ws = torch.empty(WGRAD_WS_BYTES // 4, dtype=torch.float32, device=device)
-            _WGRAD_WS[key] = ws
-        check(lib.fvt_set_wgrad_workspace(_ptr(ws), ws.numel() * 4))
+def wgrad_workspace(device, stream=None):
+    """Caller-owned scratch for fvt_conv3d_wgrad (dW-shaped slices of the pixel splits, reduced in split order), one per
+    (device, stream)."""
+    if stream is None:
+        stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device.type, device.index, int(stream))
+    ws = _WGRAD_WS.get(key)
+    if ws is None:
+        ws = torch.empty(WGRAD_WS_BYTES // 4, dtype=torch.float32, device=device)
+        _WGRAD_WS[key] = ws
     return ws
+
+
+def conv_workspace_bytes(desc, op="fwd", cout_real=0, cin_real=0):
+    """fvt_conv3d_workspace_bytes: what a fwd / wgrad call with this descriptor would like."""
+    lib = _lib.load()
+    return lib.fvt_conv3d_workspace_bytes(_h(), ctypes.byref(desc), 1 if op == "wgrad" else 0, cout_real, cin_real)
 
 
 def dgrad_desc(fwd, block_n=0, flags=0):
@@ -194,8 +312,64 @@ def pack_conv_weight_dgrad(ddesc, w_oidhw, out=None, ohwi=False):
     assert out.numel() == elems and out.dtype == torch.bfloat16
     d = _with_ohwi(ddesc) if ohwi else ddesc
     cout, cin = (w.shape[0], w.shape[4]) if ohwi else (w.shape[0], w.shape[1])
-    check(lib.fvt_pack_conv_weight_dgrad(ctypes.byref(d), _ptr(w), cout, cin, _ptr(out), _stream()))
+    check(lib.fvt_pack_conv_weight_dgrad(_h(w), ctypes.byref(d), _ptr(w), cout, cin, _ptr(out), _stream()))
     return out
+
+
+class PackTable:
+    """Device table for fvt_pack_conv_weights_multi: every (tensor, layout) operand copy of a training step in one launch.
+    add_fwd / add_dgrad register fp32 masters stored (O, kT, kH, kW, I) and allocate the packed bf16 buffers."""
+
+    _DTYPE = [("w", "<u8"), ("out", "<u8"), ("kind", "<i4"), ("taps", "<i4"), ("k_store", "<i4"), ("rows", "<i4"),
+              ("cout_real", "<i4"), ("cin_real", "<i4"), ("block0", "<u4"), ("nblocks", "<u4"),
+              ("sub", "<i4", (3,)), ("src_k", "<i4", (3,)), ("tap_a", "<i4", (3,)), ("tap_s", "<i4", (3,))]
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.total_blocks = 0
+        self._dev = None
+        self._keep = []
+
+    def _add(self, kind, desc, w_ohwi, cout_real, cin_real, sub=(0, 0, 0), src_k=(0, 0, 0), tap_a=(0, 0, 0), tap_s=(0, 0, 0)):
+        lib = _lib.load()
+        assert w_ohwi.dtype == torch.float32 and w_ohwi.is_contiguous() and w_ohwi.is_cuda
+        elems = lib.fvt_conv3d_packed_weight_elems(ctypes.byref(desc))
+        taps = desc.kt * desc.kh * desc.kw
+        rows = elems // (taps * desc.cin)
+        out = torch.empty(elems, dtype=torch.bfloat16, device=self.device)
+        nb = lib.fvt_pack_entry_blocks(kind, taps, desc.cin, rows)
+        self.rows.append((w_ohwi.data_ptr(), out.data_ptr(), kind, taps, desc.cin, rows, cout_real, cin_real, self.total_blocks, nb,
+                          tuple(sub), tuple(src_k), tuple(tap_a), tuple(tap_s)))
+        self.total_blocks += nb
+        self._keep.append((w_ohwi, out))
+        self._dev = None
+        return out
+
+    def add_fwd(self, desc, w_ohwi):
+        """Forward-layout copy for `desc` of a master (O, kT, kH, kW, I)."""
+        return self._add(0, desc, w_ohwi, w_ohwi.shape[0], w_ohwi.shape[4])
+
+    def add_dgrad(self, ddesc, w_ohwi):
+        """Data-gradient-layout copy for the dgrad descriptor `ddesc` of the FORWARD master (O, kT, kH, kW, I)."""
+        return self._add(1, ddesc, w_ohwi, w_ohwi.shape[0], w_ohwi.shape[4])
+
+    def add_dgrad_sub(self, sub_desc, w_ohwi, tap_a, tap_s):
+        """One parity sub-filter of a strided convolution's data gradient (fvt_pack_entry kind 2): `sub_desc` is the
+        stride-1 convolution over dY (its kt/kh/kw = sub-filter extent), source tap per axis = tap_a - tap_s*u."""
+        return self._add(2, sub_desc, w_ohwi, w_ohwi.shape[0], w_ohwi.shape[4], sub=(sub_desc.kt, sub_desc.kh, sub_desc.kw),
+                         src_k=tuple(w_ohwi.shape[1:4]), tap_a=tap_a, tap_s=tap_s)
+
+    def run(self):
+        import numpy as np
+        if not self.rows:
+            return
+        if self._dev is None:
+            arr = np.array(self.rows, dtype=np.dtype(self._DTYPE))
+            assert arr.dtype.itemsize == 96
+            self._dev = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
+        lib = _lib.load()
+        check(lib.fvt_pack_conv_weights_multi(_h(self._dev), _ptr(self._dev), len(self.rows), self.total_blocks, _stream()))
 
 
 def zero_insert(dy, fwd, out=None):
@@ -204,22 +378,26 @@ def zero_insert(dy, fwd, out=None):
     n, to, ho, wo, c = dy.shape
     if out is None:
         out = torch.empty((n, fwd.t, fwd.h, fwd.w, c), dtype=torch.bfloat16, device=dy.device)
-    check(lib.fvt_zero_insert(_ptr(dy), _ptr(out), n, fwd.t, fwd.h, fwd.w, to, ho, wo, fwd.st, fwd.sh, fwd.sw, c, _stream()))
+    check(lib.fvt_zero_insert(_h(dy), _ptr(dy), _ptr(out), n, fwd.t, fwd.h, fwd.w, to, ho, wo, fwd.st, fwd.sh, fwd.sw, c, _stream()))
     return out
 
 
-def conv3d_wgrad(fwd, x, dy, dw, cout_real, cin_real, ohwi=False):
-    """dw (fp32, (cout_real, cin_real, kT, kH, kW); ohwi=True: (cout_real, kT, kH, kW, cin_real)) += wgrad(x, dy)."""
+def conv3d_wgrad(fwd, x, dy, dw, cout_real, cin_real, ohwi=False, ws="auto"):
+    """dw (fp32, (cout_real, cin_real, kT, kH, kW); ohwi=True: (cout_real, kT, kH, kW, cin_real)) = wgrad(x, dy)
+    (overwritten: MXNet grad_req='write'; deterministic — pixel splits meet through workspace slices, not atomics)."""
     lib = _lib.load()
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     d = _with_ohwi(fwd) if ohwi else fwd
-    check(lib.fvt_conv3d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), cout_real, cin_real, _stream()))
+    if isinstance(ws, str):
+        ws = wgrad_workspace(x.device)                       # ws=None: no workspace (one pixel split per dW tile)
+    check(lib.fvt_conv3d_wgrad(_h(x), ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), cout_real, cin_real, _ptr(ws),
+                               ws.numel() * 4 if ws is not None else 0, _stream()))
     return dw
 
 
 def bn_finalize(stats, gamma, beta, running_mean, running_var, c_store, rows, eps, momentum, scale, shift, mean, invstd):
     lib = _lib.load()
-    check(lib.fvt_bn_finalize(_ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), c_store,
+    check(lib.fvt_bn_finalize(_h(stats), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), c_store,
                               gamma.numel(), rows, eps, momentum, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _stream()))
 
 
@@ -227,7 +405,7 @@ def bn_apply(raw, scale, shift, out, relu, res=None, res_scale=None, res_shift=N
     lib = _lib.load()
     c = raw.shape[-1]
     rows = raw.numel() // c
-    check(lib.fvt_bn_apply(_ptr(raw), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out),
+    check(lib.fvt_bn_apply(_h(raw), _ptr(raw), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out),
                            rows, c, int(relu), _stream()))
     return out
 
@@ -236,21 +414,40 @@ def bn_finalize_apply(stats, gamma, beta, running_mean, running_var, c_store, ro
                       raw, out, relu, res=None, res_scale=None, res_shift=None):
     """bn_finalize + bn_apply in one launch (training forward)."""
     lib = _lib.load()
-    check(lib.fvt_bn_finalize_apply(_ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), c_store,
+    check(lib.fvt_bn_finalize_apply(_h(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), c_store,
                                     gamma.numel(), rows, eps, momentum, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
                                     _ptr(raw), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out), int(relu), _stream()))
     return out
 
 
-def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None, relu_scale=None, relu_shift=None):
+_BN_ACC = {}
+
+
+def _bn_acc(c, device):
+    """Scratch accumulators behind fvt_bn_backward's `sums` (zeroed inside the call), one per (device, stream)."""
+    key = (device.index, int(torch.cuda.current_stream(device).cuda_stream))
+    acc = _BN_ACC.get(key)
+    if acc is None or acc.shape[0] < 2 * c:
+        acc = torch.zeros((2 * max(c, 2048), STAT_LIMBS), dtype=torch.int64, device=device)
+        _BN_ACC[key] = acc
+    return acc
+
+
+def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None, relu_scale=None, relu_shift=None, sums_acc=None,
+                dz_in=False):
     """mask: tensor whose sign gates the gradient (ReLU after a residual add), or None; relu_scale/relu_shift: the
-    forward scale/shift of this BatchNorm when the ReLU follows it directly (mask recomputed from raw)."""
+    forward scale/shift of this BatchNorm when the ReLU follows it directly (mask recomputed from raw).
+    dz_in=True: `dact` already is dz and `sums_acc` already holds [sum dz*(raw-mean), sum dz] (produced by the data
+    gradient convolution's epilogue): only the apply pass runs."""
     lib = _lib.load()
     c = raw.shape[-1]
     rows = raw.numel() // c
-    check(lib.fvt_bn_backward(_ptr(raw), _ptr(dact), _ptr(mask), _ptr(mean), _ptr(invstd), _ptr(gamma),
-                              _ptr(relu_scale), _ptr(relu_shift), _ptr(sums), _ptr(draw), _ptr(dz_out), rows, c,
-                              gamma.numel(), _stream()))
+    if sums_acc is None:
+        assert not dz_in
+        sums_acc = _bn_acc(c, raw.device)
+    check(lib.fvt_bn_backward(_h(raw), _ptr(raw), _ptr(dact), _ptr(mask), _ptr(mean), _ptr(invstd), _ptr(gamma),
+                              _ptr(relu_scale), _ptr(relu_shift), _ptr(sums), _ptr(sums_acc), _ptr(draw), _ptr(dz_out), rows, c,
+                              gamma.numel(), int(dz_in), _stream()))
     return draw
 
 
@@ -260,7 +457,7 @@ def pool_fc_bwd(dlogits, pooled, weight, dw, db, dx):
     c = pooled.shape[1]
     c_store = dx.shape[-1]
     positions = dx.numel() // (n * c_store)
-    check(lib.fvt_pool_fc_bwd(_ptr(dlogits), _ptr(pooled), _ptr(weight), n, k, c, positions, _ptr(dw), _ptr(db), _ptr(dx),
+    check(lib.fvt_pool_fc_bwd(_h(dlogits), _ptr(dlogits), _ptr(pooled), _ptr(weight), n, k, c, positions, _ptr(dw), _ptr(db), _ptr(dx),
                               c_store, _stream()))
 
 
@@ -274,7 +471,7 @@ def conv3d_fwd_f32(desc, x, w_thwio, scale=None, shift=None, residual=None, out=
                   (desc.w + 2 * desc.pw - desc.kw) // desc.sw + 1)
     if out is None:
         out = torch.empty((desc.n, to, ho, wo, desc.cout), dtype=torch.float32, device=x.device)
-    check(lib.fvt_conv3d_fwd_f32(ctypes.byref(desc), _ptr(x), _ptr(w_thwio), _ptr(scale), _ptr(shift), _ptr(residual),
+    check(lib.fvt_conv3d_fwd_f32(_h(x), ctypes.byref(desc), _ptr(x), _ptr(w_thwio), _ptr(scale), _ptr(shift), _ptr(residual),
                                  _ptr(out), _stream()))
     return out
 
@@ -287,6 +484,6 @@ def pool_fc_fwd_f32(x, weight, bias, want_pooled=False):
     positions = x.numel() // (n * c)
     logits = torch.empty((n, weight.shape[0]), dtype=torch.float32, device=x.device)
     pooled = torch.empty((n, c), dtype=torch.float32, device=x.device) if want_pooled else None
-    check(lib.fvt_pool_fc_fwd_f32(_ptr(x), n, positions, c, _ptr(weight), _ptr(bias), weight.shape[0], _ptr(pooled),
+    check(lib.fvt_pool_fc_fwd_f32(_h(x), _ptr(x), n, positions, c, _ptr(weight), _ptr(bias), weight.shape[0], _ptr(pooled),
                                   _ptr(logits), _stream()))
     return (logits, pooled) if want_pooled else logits

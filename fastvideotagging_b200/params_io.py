@@ -189,7 +189,7 @@ def load_any(fname):
             raise ParamsFormatError("%s holds unnamed arrays; a parameter file needs names" % fname)
         return out
     import torch
-    return {k: (v.numpy() if hasattr(v, "numpy") else np.asarray(v)) for k, v in torch.load(fname, map_location="cpu").items()}
+    return {k: (v.numpy() if hasattr(v, "numpy") else np.asarray(v)) for k, v in torch.load(fname, map_location="cpu", weights_only=True).items()}
 
 
 def split_checkpoint(params):

@@ -39,8 +39,13 @@ class Trainer:
         self._table = None
         self._handles = []
         self._pending = None
-        self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._table_key = None
         net._attach_trainer(self)
+
+    @property
+    def _distributed(self):
+        """Evaluated lazily: the process group may be initialised after the Trainer is built."""
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     # ---- gluon API
     @property
@@ -103,10 +108,12 @@ class Trainer:
         if net._flat is None:
             raise RuntimeError("Trainer.step() before any training-mode forward/backward")
         self.allreduce_grads()
-        if self._table is None:
+        key = (net._flat.w.data_ptr(), net._flat.g.data_ptr(), net._flat.m.data_ptr())
+        if self._table is None or key != self._table_key:       # the table caches raw addresses of the flat buffers
             self._build_table()
+            self._table_key = key
         lib = _lib.load()
-        _lib.check(lib.fvt_sgd_momentum_multi(_ptr(self._table), _ptr(self._chunk_t), _ptr(self._chunk_o), self._nchunks,
+        _lib.check(lib.fvt_sgd_momentum_multi(_lib.handle(), _ptr(self._table), _ptr(self._chunk_t), _ptr(self._chunk_o), self._nchunks,
                                               _CHUNK, ctypes.c_float(self._lr), ctypes.c_float(self.momentum),
                                               ctypes.c_float(1.0 / float(batch_size)), _stream()))
         net._weights_changed()

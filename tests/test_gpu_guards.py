@@ -40,7 +40,7 @@ def test_batchnorm_passes_stay_in_bounds(cuda_device):
         raw[:, :c_real] = torch.randn(rows, c_real, generator=gen)
         raw = raw.to(torch.bfloat16).to(cuda_device)
         rf = raw.float()
-        stats = torch.cat([rf.sum(0), (rf * rf).sum(0)]).contiguous()
+        stats = ops.stats_encode(torch.cat([rf.sum(0), (rf * rf).sum(0)]).contiguous())
         gamma = torch.ones(c_real, device=cuda_device)
         beta = torch.zeros(c_real, device=cuda_device)
         rm, rv = torch.zeros(c_real, device=cuda_device), torch.ones(c_real, device=cuda_device)
@@ -109,11 +109,11 @@ def test_weight_gradients_and_tma_store_stay_in_bounds(cuda_device, lib):
     d = ops.conv_desc(n, t, h, w, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU)
     wp = ops.pack_conv_weight(d, wt)
     big, y = _guarded((n, t, h, w, 64), torch.bfloat16, cuda_device)
-    assert lib.fvt_set_option(b"disable_tis_tma_store", 0) == 0
+    assert ops.set_option("disable_tis_tma_store", 0) == 0
     try:
         ops.conv3d_fwd(d, x, wp, out=y)
         torch.cuda.synchronize()
     finally:
-        lib.fvt_set_option(b"disable_tis_tma_store", 1)
+        ops.set_option("disable_tis_tma_store", 1)
     _check(big, "K1i TMA store")
     assert (y.float() != -123.0).any()

@@ -163,11 +163,11 @@ def test_inference_graph_replay_matches_eager(cuda_device):
     x = torch.from_numpy(_clips(2, 8, 112, 112)).to(cuda_device)
     # split-K of the small-M layers adds fp32 partials with reductions whose order varies from run to run (1e-4 of the
     # logits): off here, so that "replay == eager" can be checked bit for bit
-    assert lib.fvt_set_option(b"disable_split_k", 1) == 0
+    assert ops.set_option("disable_split_k", 1) == 0
     try:
         _graph_replay_checks(net, x, cuda_device)
     finally:
-        lib.fvt_set_option(b"disable_split_k", 0)
+        ops.set_option("disable_split_k", 0)
 
 
 def _graph_replay_checks(net, x, cuda_device):

@@ -44,11 +44,11 @@ def test_slab_and_im2col_kernels_agree(cuda_device, lib):
     d = ops.conv_desc(2, 4, 28, 28, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), ops.FVT_CONV_RELU)
     wp = ops.pack_conv_weight(d, w)
     y_slab = ops.conv3d_fwd(d, x, wp)
-    assert lib.fvt_set_option(b"disable_slab", 1) == 0
+    assert ops.set_option("disable_slab", 1) == 0
     try:
         y_gen = ops.conv3d_fwd(d, x, wp)
     finally:
-        lib.fvt_set_option(b"disable_slab", 0)
+        ops.set_option("disable_slab", 0)
     torch.cuda.synchronize()
     diff = (y_slab.float() - y_gen.float()).abs().max().item()
     assert diff <= 2 ** -7 * y_gen.float().abs().max().item()
@@ -64,11 +64,11 @@ def test_stationary_and_streamed_weights_agree(cuda_device, lib):
     d = ops.conv_desc(2, 8, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU)
     wp = ops.pack_conv_weight(d, w)
     y_stat = ops.conv3d_fwd(d, x, wp)
-    assert lib.fvt_set_option(b"disable_b_stationary", 1) == 0
+    assert ops.set_option("disable_b_stationary", 1) == 0
     try:
         y_str = ops.conv3d_fwd(d, x, wp)
     finally:
-        lib.fvt_set_option(b"disable_b_stationary", 0)
+        ops.set_option("disable_b_stationary", 0)
     torch.cuda.synchronize()
     assert torch.equal(y_stat, y_str)
 
@@ -88,29 +88,38 @@ def test_frame_ring_and_im2col_kernels_agree(cuda_device, lib, shape):
     w = torch.randn(cout, cin, 3, 1, 1, device=cuda_device) / (3 * cin) ** 0.5
     sc = (torch.rand(cout, device=cuda_device) + 0.5)
     sh = torch.randn(cout, device=cuda_device) * 0.1
-    d = ops.conv_desc(n, t, h, w_, cin, cout, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL | ops.FVT_CONV_STATS)
+    d = ops.conv_desc(n, t, h, w_, cin, cout, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
+    d_st = ops.conv_desc(n, t, h, w_, cin, cout, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_STATS)     # raw output + statistics
     wp = ops.pack_conv_weight(d, w)
-    st_ring = torch.zeros(2 * cout, device=cuda_device)
-    y_ring = ops.conv3d_fwd(d, x, wp, sc, sh, res, stats=st_ring)
-    assert lib.fvt_set_option(b"disable_frame_ring", 1) == 0 and lib.fvt_set_option(b"disable_temporal_is", 1) == 0
+    st_ring = ops.stats_buffer(cout, cuda_device)
+    y_ring = ops.conv3d_fwd(d, x, wp, sc, sh, res)
+    r_ring = ops.conv3d_fwd(d_st, x, wp, stats=st_ring)
+    assert ops.set_option("disable_frame_ring", 1) == 0 and ops.set_option("disable_temporal_is", 1) == 0
     try:
-        st_gen = torch.zeros(2 * cout, device=cuda_device)
-        y_gen = ops.conv3d_fwd(d, x, wp, sc, sh, res, stats=st_gen)
+        st_gen = ops.stats_buffer(cout, cuda_device)
+        y_gen = ops.conv3d_fwd(d, x, wp, sc, sh, res)
+        r_gen = ops.conv3d_fwd(d_st, x, wp, stats=st_gen)
     finally:
-        lib.fvt_set_option(b"disable_frame_ring", 0)
-        lib.fvt_set_option(b"disable_temporal_is", 0)
+        ops.set_option("disable_frame_ring", 0)
+        ops.set_option("disable_temporal_is", 0)
     torch.cuda.synchronize()
     scale = y_gen.float().abs().max().item()
     assert (y_ring.float() - y_gen.float()).abs().max().item() <= 2 ** -7 * scale
+    assert (r_ring.float() - r_gen.float()).abs().max().item() <= 2 ** -7 * r_gen.float().abs().max().item()
+    st_ring, st_gen = ops.stats_decode(st_ring), ops.stats_decode(st_gen)
     assert (st_ring - st_gen).abs().max().item() <= 1e-3 * st_gen.abs().max().item()
+    # the statistics are those of the stored (bf16-rounded) raw output
+    rf = r_ring.float().reshape(-1, cout)
+    ref = torch.cat([rf.sum(0), (rf * rf).sum(0)])
+    assert (st_ring - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("shape", [(2, 4, 7, 7, 512, 1152, (1, 3, 3), (0, 1, 1)), (4, 4, 7, 7, 1152, 512, (3, 1, 1), (1, 0, 0)),
                                    (1, 8, 14, 14, 576, 256, (3, 1, 1), (1, 0, 0)), (1, 3, 5, 9, 256, 80, (1, 3, 3), (0, 1, 1))])
 def test_split_k_matches_single_pass(cuda_device, lib, shape):
-    """Small-M convolutions split their reduction over several CTAs (fp32 partials in the caller's workspace + one
-    finalize pass).  Same result as the single-pass kernel up to fp32 summation order, for both epilogue flavours; the
-    workspace is left zeroed."""
+    """Small-M convolutions split their reduction over several CTAs (fp32 partial tiles in per-split slices of the
+    caller's workspace + one finalize pass that adds the slices in split order).  Same result as the single-pass kernel up
+    to fp32 summation order, for both epilogue flavours; the workspace may hold garbage on entry; two runs agree bit for bit."""
     import torch
     from fastvideotagging_b200 import ops
     n, t, h, w_, cin, cout, k, pad = shape
@@ -122,19 +131,22 @@ def test_split_k_matches_single_pass(cuda_device, lib, shape):
     sh = torch.randn(cout, device=cuda_device) * 0.1
     outs = {}
     for split in (1, 0):
-        assert lib.fvt_set_option(b"disable_split_k", 0 if split else 1) == 0
+        assert ops.set_option("disable_split_k", 0 if split else 1) == 0
         try:
             d1 = ops.conv_desc(n, t, h, w_, cin, cout, k, (1, 1, 1), pad, ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
             wp = ops.pack_conv_weight(d1, w)
             y1 = ops.conv3d_fwd(d1, x, wp, sc, sh, res)
             d2 = ops.conv_desc(n, t, h, w_, cin, cout, k, (1, 1, 1), pad, ops.FVT_CONV_STATS)
-            st = torch.zeros(2 * cout, device=cuda_device)
+            ops.workspace(cuda_device).fill_(float("nan"))          # contents are irrelevant on entry
+            st = ops.stats_buffer(cout, cuda_device)
             y2 = ops.conv3d_fwd(d2, x, wp, stats=st)
+            st_b = ops.stats_buffer(cout, cuda_device)
+            y2_b = ops.conv3d_fwd(d2, x, wp, stats=st_b)
             torch.cuda.synchronize()
-            outs[split] = (y1.float(), y2.float(), st.clone())
+            assert torch.equal(y2, y2_b) and torch.equal(st, st_b)      # deterministic, statistics included
+            outs[split] = (y1.float(), y2.float(), ops.stats_decode(st))
         finally:
-            lib.fvt_set_option(b"disable_split_k", 0)
-    assert float(ops.workspace(cuda_device).abs().max()) == 0.0
+            ops.set_option("disable_split_k", 0)
     for a, b in zip(outs[1][:2], outs[0][:2]):
         assert (a - b).abs().max().item() <= 2 ** -7 * b.abs().max().item()
     assert (outs[1][2] - outs[0][2]).abs().max().item() <= 2e-3 * outs[0][2].abs().max().item()
@@ -151,12 +163,12 @@ def test_wgrad_slab_and_im2col_kernels_agree(cuda_device, lib):
         d = ops.conv_desc(n, t, h, w_, cin, cout, (1, 3, 3), (1, 1, 1), (0, 1, 1))
         dw_slab = torch.zeros(cout, cin, 1, 3, 3, device=cuda_device)
         ops.conv3d_wgrad(d, x, dy, dw_slab, cout, cin)
-        assert lib.fvt_set_option(b"disable_wgrad_slab", 1) == 0
+        assert ops.set_option("disable_wgrad_slab", 1) == 0
         try:
             dw_gen = torch.zeros_like(dw_slab)
             ops.conv3d_wgrad(d, x, dy, dw_gen, cout, cin)
         finally:
-            lib.fvt_set_option(b"disable_wgrad_slab", 0)
+            ops.set_option("disable_wgrad_slab", 0)
         torch.cuda.synchronize()
         scale = dw_gen.abs().max().item()
         assert (dw_slab - dw_gen).abs().max().item() <= 2e-4 * scale + 1e-4, (h, cin, cout)
@@ -175,12 +187,12 @@ def test_wgrad_temporal_slab_and_im2col_kernels_agree(cuda_device, lib, shape):
     cin_r = cin - 3 if cin == 48 else cin                     # stem-like: 45 real channels in 48 stored
     dw_slab = torch.zeros(cout, cin_r, 3, 1, 1, device=cuda_device)
     ops.conv3d_wgrad(d, x, dy, dw_slab, cout, cin_r)
-    assert lib.fvt_set_option(b"disable_wgrad_slab", 1) == 0
+    assert ops.set_option("disable_wgrad_slab", 1) == 0
     try:
         dw_gen = torch.zeros_like(dw_slab)
         ops.conv3d_wgrad(d, x, dy, dw_gen, cout, cin_r)
     finally:
-        lib.fvt_set_option(b"disable_wgrad_slab", 0)
+        ops.set_option("disable_wgrad_slab", 0)
     torch.cuda.synchronize()
     scale = dw_gen.abs().max().item()
     assert (dw_slab - dw_gen).abs().max().item() <= 2e-4 * scale + 1e-4
@@ -210,7 +222,7 @@ def test_bn_finalize_apply_matches_the_two_pass_form(cuda_device, lib, rows, c_r
     raw[:, :c_real] = torch.randn(rows, c_real, generator=gen) * 2 + 0.5
     raw = raw.to(torch.bfloat16).to(cuda_device)
     rf = raw.float()
-    stats = torch.cat([rf.sum(0), (rf * rf).sum(0)]).contiguous()
+    stats = ops.stats_encode(torch.cat([rf.sum(0), (rf * rf).sum(0)]).contiguous())
     gamma = (0.5 + torch.rand(c_real, generator=gen)).to(cuda_device)
     beta = torch.randn(c_real, generator=gen).to(cuda_device)
     res = torch.randn(rows, cs, generator=gen).to(torch.bfloat16).to(cuda_device) if res_mode else None
@@ -290,11 +302,11 @@ def test_temporal_is_tma_store_epilogue_matches_register_stores(cuda_device, lib
         d = ops.conv_desc(n, t, h, w, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), ops.FVT_CONV_RELU | ops.FVT_CONV_RESIDUAL)
         wp = ops.pack_conv_weight(d, wt)
         a = ops.conv3d_fwd(d, x, wp, sc, sh, res).clone()
-        assert lib.fvt_set_option(b"disable_tis_tma_store", 0) == 0
+        assert ops.set_option("disable_tis_tma_store", 0) == 0
         try:
             b = ops.conv3d_fwd(d, x, wp, sc, sh, res).clone()
         finally:
-            lib.fvt_set_option(b"disable_tis_tma_store", 1)
+            ops.set_option("disable_tis_tma_store", 1)
         torch.cuda.synchronize()
         assert torch.equal(a, b)
         assert a.float().abs().max().item() > 0
@@ -324,18 +336,18 @@ def test_cta_pair_slab_kernel_matches_single_cta(cuda_device, lib, shape):
     def run_all():
         a = ops.conv3d_fwd(d_plain, x, wp).clone()
         b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
-        st = torch.zeros(2 * cout, device=cuda_device)
+        st = ops.stats_buffer(cout, cuda_device)
         c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
         torch.cuda.synchronize()
-        return a, b, c, st.clone()
+        return a, b, c, ops.stats_decode(st)
 
     out = {}
     try:
         for mode in (0, 1, 2):
-            assert lib.fvt_set_option(b"slab_pair", mode) == 0
+            assert ops.set_option("slab_pair", mode) == 0
             out[mode] = run_all()
     finally:
-        lib.fvt_set_option(b"slab_pair", 0)
+        ops.set_option("slab_pair", 0)
     for mode in (1, 2):
         for i in range(3):
             assert torch.equal(out[0][i], out[mode][i]), (mode, i)
@@ -391,12 +403,12 @@ def test_fused_unit_matches_two_launches(cuda_device, lib, shape, input_stationa
     y_mid = ops.conv3d_fwd(d_s, x, wp_s, sc_m, sh_m)
     y_two = ops.conv3d_fwd(d_t, y_mid, wp_t, sc_o, sh_o, res)
     y_fused = torch.full_like(y_two, float("nan"))
-    assert lib.fvt_set_option(b"unit_input_stationary", input_stationary) == 0
+    assert ops.set_option("unit_input_stationary", input_stationary) == 0
     try:
         ops.unit2p1_fwd(d_s, d_t, x, wp_s, sc_m, sh_m, wp_t, sc_o, sh_o, res, out=y_fused)
         torch.cuda.synchronize()
     finally:
-        lib.fvt_set_option(b"unit_input_stationary", 1)
+        ops.set_option("unit_input_stationary", 1)
     a, b = y_fused.float(), y_two.float()
     assert torch.isfinite(a).all()
     tol = 2 ** -7 * b.abs() + 2 ** -7 * 1e-2 * b.abs().max()
@@ -454,18 +466,18 @@ def test_cta_pair_auto_matches_streamed_single_cta(cuda_device, lib, shape):
     def run_all():
         a = ops.conv3d_fwd(d_plain, x, wp).clone()
         b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
-        st = torch.zeros(2 * cout, device=cuda_device)
+        st = ops.stats_buffer(cout, cuda_device)
         c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
         torch.cuda.synchronize()
-        return a, b, c, st.clone()
+        return a, b, c, ops.stats_decode(st)
 
     out = {}
     try:
         for mode in (0, 1):
-            assert lib.fvt_set_option(b"slab_pair_auto", mode) == 0
+            assert ops.set_option("slab_pair_auto", mode) == 0
             out[mode] = run_all()
     finally:
-        lib.fvt_set_option(b"slab_pair_auto", 1)
+        ops.set_option("slab_pair_auto", 1)
     for i in range(3):
         a, b = out[1][i].float(), out[0][i].float()
         assert torch.isfinite(a).all()
@@ -504,18 +516,18 @@ def test_cta_pair_temporal_matches_im2col(cuda_device, lib, shape):
     def run_all():
         a = ops.conv3d_fwd(d_plain, x, wp).clone()
         b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
-        st = torch.zeros(2 * cout, device=cuda_device)
+        st = ops.stats_buffer(cout, cuda_device)
         c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
         torch.cuda.synchronize()
-        return a, b, c, st.clone()
+        return a, b, c, ops.stats_decode(st)
 
     out = {}
     try:
         for mode in (0, 2):                      # 2: the pair kernel even below the problem size where it pays off
-            assert lib.fvt_set_option(b"slab_pair_auto", mode) == 0
+            assert ops.set_option("slab_pair_auto", mode) == 0
             out[mode] = run_all()
     finally:
-        lib.fvt_set_option(b"slab_pair_auto", 1)
+        ops.set_option("slab_pair_auto", 1)
     for i in range(3):
         a, b = out[2][i].float(), out[0][i].float()
         assert torch.isfinite(a).all()
@@ -553,20 +565,20 @@ def test_cta_pair_im2col_matches_single_cta(cuda_device, lib, shape):
     def run_all():
         a = ops.conv3d_fwd(d_plain, x, wp).clone()
         b = ops.conv3d_fwd(d_full, x, wp, sc, sh, res).clone()
-        st = torch.zeros(2 * cout, device=cuda_device)
+        st = ops.stats_buffer(cout, cuda_device)
         c = ops.conv3d_fwd(d_stat, x, wp, stats=st).clone()
         torch.cuda.synchronize()
-        return a, b, c, st.clone()
+        return a, b, c, ops.stats_decode(st)
 
     out = {}
     try:
-        assert lib.fvt_set_option(b"disable_split_k", 1) == 0          # same single-pass reduction on both sides
+        assert ops.set_option("disable_split_k", 1) == 0          # same single-pass reduction on both sides
         for mode in (0, 2):                                              # 2: the pair kernel whatever the problem size
-            assert lib.fvt_set_option(b"igemm_pair", mode) == 0
+            assert ops.set_option("igemm_pair", mode) == 0
             out[mode] = run_all()
     finally:
-        lib.fvt_set_option(b"igemm_pair", 1)
-        lib.fvt_set_option(b"disable_split_k", 0)
+        ops.set_option("igemm_pair", 1)
+        ops.set_option("disable_split_k", 0)
     for i in range(3):
         assert torch.equal(out[0][i], out[2][i]), i
     ref = out[0][3]
@@ -578,10 +590,10 @@ def test_cta_pair_im2col_matches_single_cta(cuda_device, lib, shape):
                                    (2, 8, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1)),     # conv3_x 1x3x3
                                    (2, 8, 56, 56, 144, 64, (3, 1, 1), (1, 0, 0)),      # conv2_x 3x1x1 (temporal mode)
                                    (2, 4, 28, 28, 288, 128, (3, 1, 1), (1, 0, 0))])    # conv3_x 3x1x1
-def test_wgrad_workspace_reduction_matches_atomics(cuda_device, lib, shape):
-    """Slab weight gradients with the pixel splits reduced through the workspace (plain stores + one reduce pass,
-    fvt_set_wgrad_workspace) == the same kernel with fp32 atomics into dw, up to fp32 summation order; the workspace
-    form is deterministic (two runs bit-identical) and accumulates into dw like the atomics do."""
+def test_wgrad_split_reduction_is_deterministic_and_overwrites(cuda_device, lib, shape):
+    """Weight gradients reduce their pixel splits through per-split slices of the caller's workspace, added in split
+    order: two runs are bit-identical, dw is OVERWRITTEN (grad_req='write', whatever it held), garbage in the workspace
+    is harmless, and the result equals the single-split launch (no workspace) up to fp32 summation order."""
     import torch
     from fastvideotagging_b200 import ops
     n, t, h, w, cin, cout, k, p = shape
@@ -590,23 +602,99 @@ def test_wgrad_workspace_reduction_matches_atomics(cuda_device, lib, shape):
     dy = (torch.randn(n, t, h, w, cout, generator=gen) * 0.1).to(torch.bfloat16).to(cuda_device)
     d = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, 0)
     taps = k[0] * k[1] * k[2]
+    want = ops.conv_workspace_bytes(ops._with_ohwi(d), "wgrad", cout, cin)
+    assert want > 0 and want % (cout * cin * taps * 4) == 0          # whole dW-shaped slices, >= 2 of them
 
-    def run(ws_on, base):
-        ops.wgrad_workspace(cuda_device, enable=ws_on)
+    def run(ws, base):
         dw = torch.full((cout, taps, cin), base, dtype=torch.float32, device=cuda_device)
-        ops.conv3d_wgrad(d, x, dy, dw, cout, cin, ohwi=True)
+        ops.conv3d_wgrad(d, x, dy, dw, cout, cin, ohwi=True, ws=ws)
         torch.cuda.synchronize()
         return dw
 
-    try:
-        ref = run(False, 0.0)
-        a = run(True, 0.0)
-        b = run(True, 0.0)
-        c = run(True, 1.5)                   # accumulates on top of what dw holds
-    finally:
-        ops.wgrad_workspace(cuda_device, enable=False)       # the library default: no workspace, atomics
+    ops.wgrad_workspace(cuda_device).fill_(float("nan"))
+    ref = run(None, 0.0)                     # no workspace: one split per dW tile
+    a = run("auto", 0.0)
+    b = run("auto", 1.5)                     # overwritten, not accumulated
     assert torch.equal(a, b)
     scale = ref.abs().max().item()
-    assert scale > 0
+    assert scale > 0 and torch.isfinite(a).all()
     assert (a - ref).abs().max().item() <= 1e-5 * scale + 1e-6
-    assert (c - 1.5 - a).abs().max().item() <= 1e-5 * scale + 1e-5
+
+
+def test_multi_tensor_pack_matches_single_launch_packs(cuda_device, lib):
+    """fvt_pack_conv_weights_multi (all operand copies of a step in one launch) == fvt_pack_conv_weight /
+    fvt_pack_conv_weight_dgrad per tensor, bit for bit, for the layer shapes of the network (padded channel counts,
+    several N tiles, 1 / 3 / 9 taps)."""
+    import torch
+    from fastvideotagging_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(64, 144, (1, 3, 3), (0, 1, 1)), (144, 64, (3, 1, 1), (1, 0, 0)), (64, 230, (1, 3, 3), (0, 1, 1)),
+              (230, 128, (3, 1, 1), (1, 0, 0)), (45, 64, (3, 1, 1), (1, 0, 0)), (256, 921, (1, 3, 3), (0, 1, 1)),
+              (921, 512, (3, 1, 1), (1, 0, 0)), (64, 128, (1, 1, 1), (0, 0, 0)), (512, 1152, (1, 3, 3), (0, 1, 1))]
+    tf, td = ops.PackTable(cuda_device), ops.PackTable(cuda_device)
+    cases = []
+    for cin, cout, k, p in shapes:
+        w = torch.randn(cout, k[0], k[1], k[2], cin, generator=gen).to(cuda_device)            # (O, kT, kH, kW, I) master
+        d = ops.conv_desc(2, 4, 14, 14, ops.pad16(cin), ops.pad16(cout), k, (1, 1, 1), p)
+        dd = ops.dgrad_desc(d)
+        cases.append((d, dd, w, tf.add_fwd(d, w), td.add_dgrad(dd, w)))
+    tf.run()
+    td.run()
+    for d, dd, w, got_f, got_d in cases:
+        ref_f = ops.pack_conv_weight(d, w, ohwi=True)
+        ref_d = ops.pack_conv_weight_dgrad(dd, w, ohwi=True)
+        torch.cuda.synchronize()
+        assert torch.equal(got_f.view(torch.int16), ref_f.view(torch.int16)), d.key()
+        assert torch.equal(got_d.view(torch.int16), ref_d.view(torch.int16)), dd.key()
+
+
+@pytest.mark.parametrize("case", [
+    (2, 8, 28, 28, 64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # first conv of conv3_x: 1x3x3 / s(1,2,2)
+    (2, 8, 14, 14, 230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0)),     # its temporal conv: 3x1x1 / s(2,1,1)
+    (2, 8, 28, 28, 64, 128, (1, 1, 1), (2, 2, 2), (0, 0, 0)),      # projection shortcut: 1x1x1 / s(2,2,2)
+    (1, 2, 14, 14, 256, 921, (1, 3, 3), (1, 2, 2), (0, 1, 1)),     # conv5_x first conv at T/4 = 2 -> dY has one frame pair
+    (1, 2, 7, 7, 921, 512, (3, 1, 1), (2, 1, 1), (1, 0, 0)),       # dY temporal extent 1
+    (1, 4, 9, 11, 32, 48, (3, 3, 3), (2, 2, 2), (1, 1, 1)),        # odd extents, full 3x3x3 / s2 (ECO-style)
+])
+def test_strided_dgrad_parity_classes_match_zero_insert_and_autograd(cuda_device, lib, case):
+    """Data gradient of a strided convolution as per-parity-class sub-convolutions of dY (fvt_conv3d_fwd_ex + pack kind 2)
+    == torch autograd on the same bf16 operands (fp32 accumulate) at 1e-2 of max, and == the zero-insert route up to
+    fp32 summation order; with a residual the classes add it at their lattice positions."""
+    import torch
+    import torch.nn.functional as F
+    from fastvideotagging_b200 import ops
+    n, t, h, w, cin, cout, k, s, p = case
+    gen = torch.Generator().manual_seed(cin * 7 + cout)
+    cin_s, cout_s = ops.pad16(cin), ops.pad16(cout)
+    fwd = ops.conv_desc(n, t, h, w, cin_s, cout_s, k, s, p)
+    to, ho, wo = ops.conv_out_shape(fwd)
+    wm = (torch.randn(cout, k[0], k[1], k[2], cin, generator=gen) / (cin * k[0] * k[1] * k[2]) ** 0.5).to(cuda_device)   # (O,kT,kH,kW,I)
+    dy = torch.zeros(n, to, ho, wo, cout_s)
+    dy[..., :cout] = torch.randn(n, to, ho, wo, cout, generator=gen)
+    dy = dy.to(torch.bfloat16).to(cuda_device)
+    res = torch.zeros(n, t, h, w, cin_s)
+    res[..., :cin] = torch.randn(n, t, h, w, cin, generator=gen)
+    res = res.to(torch.bfloat16).to(cuda_device)
+    table = ops.PackTable(cuda_device)
+    plan = ops.DgradPlan(fwd, wm, table)
+    table.run()
+    got = plan.run(dy, torch.full((n, t, h, w, cin_s), float("nan"), dtype=torch.bfloat16, device=cuda_device))
+    got_res = plan.run(dy, torch.full((n, t, h, w, cin_s), float("nan"), dtype=torch.bfloat16, device=cuda_device), residual=res)
+    # reference 1: autograd of the forward convolution on the bf16-rounded operands
+    w_ref = wm.to(torch.bfloat16).float().permute(0, 4, 1, 2, 3).contiguous()            # (O, I, kT, kH, kW)
+    x0 = torch.zeros(n, cin, t, h, w, device=cuda_device, requires_grad=True)
+    y = F.conv3d(x0, w_ref, stride=s, padding=p)
+    y.backward(dy[..., :cout].float().permute(0, 4, 1, 2, 3))
+    ref = x0.grad.permute(0, 2, 3, 4, 1)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert scale > 0
+    assert (got[..., :cin].float() - ref).abs().max().item() <= 1e-2 * scale
+    assert got[..., cin:].abs().max().item() == 0 if cin_s > cin else True
+    assert (got_res[..., :cin].float() - (ref + res[..., :cin].float())).abs().max().item() <= 1e-2 * (scale + res.float().abs().max().item())
+    # reference 2: the zero-insert route of round 1
+    dd = ops.dgrad_desc(fwd)
+    wpd = ops.pack_conv_weight_dgrad(dd, wm, ohwi=True)
+    old = ops.conv3d_fwd(dd, ops.zero_insert(dy, fwd), wpd)
+    torch.cuda.synchronize()
+    assert (got.float() - old.float()).abs().max().item() <= 2 ** -7 * scale

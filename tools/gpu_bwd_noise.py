@@ -8,7 +8,7 @@ from fastvideotagging_b200.model import R2Plus2D, SigmoidBinaryCrossEntropyLoss
 from fastvideotagging_b200 import _lib
 for kv in os.environ.get("FVT_DBG_OPTS", "").split(","):
     if kv:
-        k, v = kv.split("="); assert _lib.load().fvt_set_option(k.encode(), int(v)) == 0
+        k, v = kv.split("="); assert ops.set_option(k, int(v)) == 0
 dev = torch.device("cuda:0")
 depth, n, t, hw = 34, 4, 32, 112
 params = orc.randomize_bn(orc.init_params(depth, 101, seed=0), seed=1)

@@ -8,7 +8,7 @@ dev = torch.device("cuda:0")
 from fastvideotagging_b200 import _lib
 for kv in os.environ.get("FVT_DBG_OPTS", "").split(","):
     if kv:
-        k, v = kv.split("="); assert _lib.load().fvt_set_option(k.encode(), int(v)) == 0
+        k, v = kv.split("="); assert ops.set_option(k, int(v)) == 0
 depth, n, t, hw, eps, num_class = 10, 4, 8, 64, 10.0, 101
 pool = (t // 8, hw // 16, hw // 16)
 params = orc.randomize_bn(orc.init_params(depth, num_class, seed=0), seed=1)

@@ -8,7 +8,7 @@ lib = _lib.load()
 dev = torch.device("cuda:0")
 for kv in os.environ.get("FVT_DBG_OPTS", "").split(","):
     if kv:
-        k_, v_ = kv.split("="); assert lib.fvt_set_option(k_.encode(), int(v_)) == 0
+        k_, v_ = kv.split("="); assert ops.set_option(k_, int(v_)) == 0
 CASES = [
     ("conv2 spatial 64->144 b48", 48, 32, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1), False),
     ("conv2 temporal 144->64 b48", 48, 32, 56, 56, 144, 64, (3, 1, 1), (1, 0, 0), False),
@@ -34,7 +34,7 @@ def timeit(fn, reps=5):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps * 1e3
 if len(sys.argv) > 1:
-    lib.fvt_set_option(b"ring_prefetch", int(sys.argv[1]))
+    ops.set_option("ring_prefetch", int(sys.argv[1]))
     CASES = [c for c in CASES if "temporal" in c[0]]
 for name, n, t, h, w, cin, cout, k, p, res in CASES:
     x = (torch.randn(n, t, h, w, cin, device=dev) * 0.5).to(torch.bfloat16)
@@ -47,9 +47,9 @@ for name, n, t, h, w, cin, cout, k, p, res in CASES:
     r = torch.randn_like(y) if res else None
     out = []
     for dbg in (0, 256, 512):
-        lib.fvt_set_option(b"debug_flags", dbg)
+        ops.set_option("debug_flags", dbg)
         out.append(timeit(lambda: ops.conv3d_fwd(d, x, wp, sc, sh, r, out=y)))
-    lib.fvt_set_option(b"debug_flags", 0)
+    ops.set_option("debug_flags", 0)
     st = torch.zeros(2 * cout, device=dev)
     ds = ops.conv_desc(n, t, h, w, cin, cout, k, (1, 1, 1), p, ops.FVT_CONV_STATS)
     out.append(timeit(lambda: ops.conv3d_fwd(ds, x, wp, out=y, stats=st)))

@@ -41,15 +41,15 @@ for case in CASES:
     gflop = 2.0 * n * t * h * w * cout * cin * taps / 1e9
     line = "%-34s" % name
     for mode in (0, 1):
-        lib.fvt_set_option(b"slab_pair_auto", mode)
+        ops.set_option("slab_pair_auto", mode)
         fn = (lambda: ops.conv3d_fwd(d, x, wp, out=y, stats=st)) if stats else (lambda: ops.conv3d_fwd(d, x, wp, sc, sh, out=y))
         us = timeit(fn)
         line += " | %s %7.1f us (%5.0f TF/s)" % ("pair  " if mode else "single", us, gflop / us * 1e3)
         for dl, bits in (("no-epi", 512),):
-            lib.fvt_set_option(b"debug_flags", bits)
+            ops.set_option("debug_flags", bits)
             line += " %s %7.1f" % (dl, timeit(fn))
-            lib.fvt_set_option(b"debug_flags", 0)
-    lib.fvt_set_option(b"slab_pair_auto", 1)
+            ops.set_option("debug_flags", 0)
+    ops.set_option("slab_pair_auto", 1)
     print(line, flush=True)
 
 # ---- K1p: generic im2col convolution on CTA pairs (wide streamed-weight layers)
@@ -72,10 +72,10 @@ for name, n, t, hh, cin, cout, kern, strd, pad in (("conv4 spatial 256->576 b48"
     gflop = 2.0 * n * to * ho * wo * cout * cin * taps / 1e9
     line = "%-38s" % name
     for mode in (0, 2):
-        lib.fvt_set_option(b"igemm_pair", mode)
+        ops.set_option("igemm_pair", mode)
         us = timeit(lambda: ops.conv3d_fwd(d, x, wp, sc, sh, out=y))
         line += " | %s %7.1f us (%5.0f TF/s)" % ("pair  " if mode else "single", us, gflop / us * 1e3)
-    lib.fvt_set_option(b"igemm_pair", 1)
+    ops.set_option("igemm_pair", 1)
     print(line, flush=True)
 
 # ---- layers whose filter is stationary on ONE SM (conv2_x 1x3x3 64 -> 144, the row-paired stem): single CTA vs forced pair
@@ -96,9 +96,9 @@ for name, n, t, cin, cout, kern, pad in (("conv2 spatial 64->144 b48", 48, 32, 6
     st = torch.zeros(2 * cout, device=dev)
     line = "%-40s" % name
     for mode in (0, 2, 1):
-        lib.fvt_set_option(b"slab_pair", mode)
+        ops.set_option("slab_pair", mode)
         a = timeit(lambda: ops.conv3d_fwd(d_inf, x, wp, sc, sh, out=y))
         b = timeit(lambda: ops.conv3d_fwd(d_trn, x, wp, out=y, stats=st))
         line += " | pair=%d inference %7.1f train(stats) %7.1f" % (mode, a, b)
-    lib.fvt_set_option(b"slab_pair", 0)
+    ops.set_option("slab_pair", 0)
     print(line, flush=True)

@@ -40,7 +40,7 @@ def run_case(name, n, t, h, w, cin, cout, k, s, p, relu=False, res=False, affine
         yref = yref.relu()
     xd = x.to(dev); wd = wt.to(dev)
     wp = ops.pack_conv_weight(d, wd)
-    st = torch.zeros(2 * cout_s, device=dev) if stats else None
+    st = ops.stats_buffer(cout_s, dev) if stats else None
     t0 = time.time()
     y = ops.conv3d_fwd(d, xd, wp, scale.to(dev) if affine else None, shift.to(dev) if affine else None,
                        r.to(dev) if res else None, stats=st)
@@ -58,7 +58,7 @@ def run_case(name, n, t, h, w, cin, cout, k, s, p, relu=False, res=False, affine
     if stats:
         rawb = raw.to(torch.bfloat16).float()
         s1 = rawb.sum(dim=(0, 1, 2, 3)); s2 = (rawb * rawb).sum(dim=(0, 1, 2, 3))
-        g = st.cpu()
+        g = ops.stats_decode(st).cpu()
         e1 = (g[:cout] - s1).abs().max().item() / (s1.abs().max().item() + 1e-6)
         e2 = (g[cout_s:cout_s + cout] - s2).abs().max().item() / (s2.abs().max().item() + 1e-6)
         sok = e1 < 2e-2 and e2 < 2e-2

@@ -5,7 +5,7 @@ import torch
 from fastvideotagging_b200 import ops, _lib
 lib = _lib.load()
 dev = torch.device("cuda:0")
-if len(sys.argv) > 1: lib.fvt_set_option(b"ring_prefetch", int(sys.argv[1]))
+if len(sys.argv) > 1: ops.set_option("ring_prefetch", int(sys.argv[1]))
 def timeit(fn, reps=5):
     fn(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -22,8 +22,8 @@ for (n, t, h, w, cin, cout) in [(48, 32, 56, 56, 144, 64), (48, 32, 56, 56, 128,
     y = torch.empty(n, t, h, w, cout, device=dev, dtype=torch.bfloat16)
     res = []
     for ring in (1, 0):
-        lib.fvt_set_option(b"disable_frame_ring", 0 if ring else 1)
+        ops.set_option("disable_frame_ring", 0 if ring else 1)
         res.append(timeit(lambda: ops.conv3d_fwd(d, x, wp, out=y)))
-    lib.fvt_set_option(b"disable_frame_ring", 0)
+    ops.set_option("disable_frame_ring", 0)
     gb = (x.numel() + y.numel()) * 2 / 1e9
     print("n=%d cin=%d cout=%d: ring %7.1f us (%.2f TB/s) | im2col %7.1f us (%.2f TB/s)" % (n, cin, cout, res[0], gb / res[0] * 1e3, res[1], gb / res[1] * 1e3), flush=True)

@@ -27,10 +27,10 @@ for name, n, t, h, w, cin, cout in CASES:
     line = "%-28s" % name
     for pf in (0, 1, 2, 4):
         for br in (0, 1, 2):
-            lib.fvt_set_option(b"slab_prefetch", pf); lib.fvt_set_option(b"slab_box_rows", br)
+            ops.set_option("slab_prefetch", pf); ops.set_option("slab_box_rows", br)
             y = torch.empty(n, t, h, w, cout, device=dev, dtype=torch.bfloat16)
             us = timeit(lambda: ops.conv3d_fwd(d, x, wp, out=y))
             if y0 is None: y0 = y.clone()
             line += " | pf%d br%d %6.1f%s" % (pf, br, us, "" if torch.equal(y, y0) else " MISMATCH")
     print(line, flush=True)
-lib.fvt_set_option(b"slab_prefetch", 2); lib.fvt_set_option(b"slab_box_rows", 0)
+ops.set_option("slab_prefetch", 2); ops.set_option("slab_box_rows", 0)

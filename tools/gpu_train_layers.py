@@ -17,7 +17,7 @@ dev = torch.device("cuda:0")
 from fastvideotagging_b200 import _lib
 for kv in os.environ.get("FVT_DBG_OPTS", "").split(","):
     if kv:
-        k_, v_ = kv.split("="); assert _lib.load().fvt_set_option(k_.encode(), int(v_)) == 0
+        k_, v_ = kv.split("="); assert ops.set_option(k_, int(v_)) == 0
 net = R2Plus2D(NUM_CLASS, MODEL_DEPTH, final_spatial_kernel=HW // 16, final_temporal_kernel=T // 8).to(dev)
 net.load_param_dict(oracle_params()); net.train()
 xt = torch.from_numpy(synthetic_clips(tb, seed=7)).to(dev)

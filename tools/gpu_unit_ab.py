@@ -45,14 +45,14 @@ for name, n, t, residual in (("conv2_x unit b48", 48, 32, False), ("conv2_x unit
     t2 = timeit(two)
     line = "%-26s two launches %7.1f us (%5.0f TF/s)" % (name, t2, gflop / t2 * 1e3)
     for label, opt in (("fused IS", 1), ("fused OS", 0)):
-        lib.fvt_set_option(b"unit_input_stationary", opt)
+        ops.set_option("unit_input_stationary", opt)
         y_f.fill_(float("nan"))
         tf = timeit(fused)
         diff = (y_f.float() - y_two.float()).abs().max().item()
         line += " | %s %7.1f us (%5.0f TF/s) diff %.3g" % (label, tf, gflop / tf * 1e3, diff)
         for dl, bits in (("no-store", 256), ("no-epi", 512)):
-            lib.fvt_set_option(b"debug_flags", bits)
+            ops.set_option("debug_flags", bits)
             line += " %s %7.1f" % (dl, timeit(fused))
-            lib.fvt_set_option(b"debug_flags", 0)
-    lib.fvt_set_option(b"unit_input_stationary", 1)
+            ops.set_option("debug_flags", 0)
+    ops.set_option("unit_input_stationary", 1)
     print(line, flush=True)
