@@ -91,6 +91,7 @@ def load():
         "fvt_pack_conv_weights_multi": (ctypes.c_int, [hp, vp, i32, ctypes.c_uint32, vp]),
         "fvt_conv3d_wgrad": (ctypes.c_int, [hp, dp, vp, vp, fp, i32, i32, vp, ctypes.c_size_t, vp]),
         "fvt_zero_insert": (ctypes.c_int, [hp, vp, vp] + [i32] * 11 + [vp]),
+        "fvt_bn_fold_multi": (ctypes.c_int, [hp, vp, i32, vp]),
         "fvt_bn_finalize": (ctypes.c_int, [hp, vp, fp, fp, fp, fp, i32, i32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                            fp, fp, fp, fp, vp]),
         "fvt_bn_apply": (ctypes.c_int, [hp, vp, fp, fp, vp, fp, fp, vp, ctypes.c_int64, i32, i32, vp]),
@@ -103,6 +104,8 @@ def load():
         "fvt_clip_stats_u8": (ctypes.c_int, [hp, vp, ctypes.c_int64, vp, vp]),
         "fvt_clip_normalize_u8": (ctypes.c_int, [hp, vp, vp, fp, i32, i32, i32, i32, ctypes.c_float,
                                                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]),
+        "fvt_clip_unfold_u8": (ctypes.c_int, [hp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, ctypes.c_float,
+                                              ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, vp]),
         "fvt_softmax_accumulate": (ctypes.c_int, [hp, fp, fp, i32, i32, vp]),
         "fvt_argmax_correct": (ctypes.c_int, [hp, fp, vp, i32, i32, vp, vp, vp]),
         "fvt_topk_iou": (ctypes.c_int, [hp, fp, fp, i32, i32, i32, vp, vp, vp]),

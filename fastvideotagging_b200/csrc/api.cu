@@ -170,7 +170,9 @@ int check_launch(const char* what) {
 }
 
 // ------------------------------------------------------------------------------------------------ conv helpers
-static int validate_conv(const fvt_conv_desc* d) {
+// check_extent = false: channel / filter / stride / padding ranges only (weight packing does not care whether the filter
+// fits the padded input: fvt_conv3d_fwd_ex gives the high padding separately)
+static int validate_conv(const fvt_conv_desc* d, bool check_extent = true) {
   if (d == nullptr) return set_error(FVT_ERR_BAD_DESC, "null conv descriptor");
   if (d->n <= 0 || d->t <= 0 || d->h <= 0 || d->w <= 0) return set_error(FVT_ERR_BAD_DESC, "non-positive input extent");
   if (d->cin <= 0 || d->cin % 16) return set_error(FVT_ERR_BAD_DESC, "cin=%d must be a positive multiple of 16", d->cin);
@@ -180,7 +182,8 @@ static int validate_conv(const fvt_conv_desc* d) {
   if (d->st < 1 || d->sh < 1 || d->sw < 1 || d->st > 8 || d->sh > 8 || d->sw > 8) return set_error(FVT_ERR_BAD_DESC, "stride must be in [1, 8]");
   if (d->pt < 0 || d->ph < 0 || d->pw < 0 || d->pt > 15 || d->ph > 15 || d->pw > 15) return set_error(FVT_ERR_BAD_DESC, "padding must be in [0, 15]");
   if (d->pt - (d->kt - 1) < -16 || d->ph - (d->kh - 1) < -16 || d->pw - (d->kw - 1) < -16) return set_error(FVT_ERR_BAD_DESC, "filter/padding outside the im2col corner range");
-  if (d->t + 2 * d->pt < d->kt || d->h + 2 * d->ph < d->kh || d->w + 2 * d->pw < d->kw) return set_error(FVT_ERR_BAD_DESC, "filter larger than padded input");
+  if (check_extent && (d->t + 2 * d->pt < d->kt || d->h + 2 * d->ph < d->kh || d->w + 2 * d->pw < d->kw))
+    return set_error(FVT_ERR_BAD_DESC, "filter larger than padded input");
   if (d->block_n != 0 && (d->block_n % 16 || d->block_n < 16 || d->block_n > 256)) return set_error(FVT_ERR_BAD_DESC, "block_n=%d must be a multiple of 16 in [16, 256]", d->block_n);
   return 0;
 }
@@ -450,16 +453,41 @@ static int try_wgrad_temporal(const DeviceInfo* di, const Options& o, const fvt_
   p.slab_tx_bytes = 128 * 128;
   p.dy_tx_bytes = 128 * 128;
   const int kSmemMax = 227 * 1024, kAux = 1024;
-  // N tile: whole Cout when it fits 256 columns, else equal parts; M tiles per CTA limited by 512 TMEM columns
+  // N tile: whole Cout when it fits 256 columns, else equal parts; M tiles per CTA limited by 512 TMEM columns and by two
+  // pipeline stages in shared memory.  (M tiles per CTA, pixel splits) minimise the estimated time of the slowest CTA plus,
+  // with several splits, the slice reduction (one more launch and (splits + 1) dW-sized passes).
   int nt = (d->cout + 255) / 256;
   int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
   int acc_stride = (n_tile + 31) / 32 * 32;
-  int mt = 512 / acc_stride;
-  if (mt > kWgsMaxMt) mt = kWgsMaxMt;
+  int mt_max = 512 / acc_stride;
+  if (mt_max > kWgsMaxMt) mt_max = kWgsMaxMt;
   const int mt_total = (p.cin_blocks + 1) / 2;
-  if (mt > mt_total) mt = mt_total;
-  // keep >= 2 stages in shared memory
-  while (mt > 1 && 2 * ((2 * mt) * p.slab_slot_bytes + ((n_tile + 63) / 64) * 128 * 128) + kAux > kSmemMax) --mt;
+  if (mt_max > mt_total) mt_max = mt_total;
+  while (mt_max > 1 && 2 * ((2 * mt_max) * p.slab_slot_bytes + ((n_tile + 63) / 64) * 128 * 128) + kAux > kSmemMax) --mt_max;
+  const long long dw_elems = (long long)cout_real * cin_real * p.taps;
+  double best = 1e30;
+  int mt = mt_max, splits = 1;
+  for (int m = 1; m <= mt_max; ++m) {
+    const int chunks = (mt_total + m - 1) / m * d->kt;
+    const int items_m = chunks * nt;
+    int max_splits = di->sm_count / items_m;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > p.num_tiles) max_splits = p.num_tiles;
+    const int ncb = 2 * m < p.cin_blocks ? 2 * m : p.cin_blocks;
+    const double mma_clk = (double)m * p.ksteps * (n_tile > 128 ? n_tile / 2.0 : 64.0);
+    const double bytes = (double)(ncb + (n_tile + 63) / 64) * 128.0 * 128.0;
+    const double per_tile = mma_clk > bytes / 64.0 ? mma_clk : bytes / 64.0;
+    const double epi = (double)m * n_tile * 12.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int sp = pass == 0 ? 1 : max_splits;
+      if (pass == 1 && max_splits == 1) break;
+      const int tps = (p.num_tiles + sp - 1) / sp;
+      const int waves = (items_m * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
+      double est = waves * (tps * per_tile + 3000.0 + epi);
+      if (sp > 1) est += 9000.0 + (double)(sp + 1) * (double)dw_elems * 4.0 / 2500.0;
+      if (est < best) { best = est; mt = m; splits = sp; }
+    }
+  }
   p.n_tiles = nt; p.n_tile = n_tile; p.acc_stride = acc_stride; p.n_blocks = (n_tile + 63) / 64;
   p.mt_per_cta = mt;
   p.chunks_per_tap = (mt_total + mt - 1) / mt;
@@ -470,10 +498,6 @@ static int try_wgrad_temporal(const DeviceInfo* di, const Options& o, const fvt_
   if (p.stages < 2) return 0;
   if (p.stages > kWgsMaxStages) p.stages = kWgsMaxStages;
   const int items = p.m_chunks * p.n_tiles;
-  int splits = di->sm_count / items;
-  if (splits < 1) splits = 1;
-  if (splits > p.num_tiles) splits = p.num_tiles;
-  const long long dw_elems = (long long)cout_real * cin_real * p.taps;
   if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)dw_elems * sizeof(float) : 0; return 1; }
   splits = wgrad_fit_splits(splits, dw_elems, ws, ws_bytes);
   p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
@@ -542,7 +566,8 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
 
   // ---- pick (N tile, M tiles per CTA): minimise the estimated time of the slowest CTA
   double best = 1e30;
-  int best_nt = 0, best_mt = 0;
+  int best_nt = 0, best_mt = 0, best_splits = 1;
+  const long long dw_elems_est = (long long)cout_real * cin_real * p.taps;
   for (int nt = 1; nt <= 8; ++nt) {
     const int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
     if (n_tile > 256) continue;
@@ -563,18 +588,24 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
       const int stage_bytes = ncb_max * p.slab_slot_bytes + n_blocks * 128 * 128;
       if (2 * stage_bytes + kAux > kSmemMax) continue;
       const int items = m_chunks * nt;
-      int splits = di->sm_count / items;
-      if (splits < 1) splits = 1;
-      if (splits > p.num_tiles) splits = p.num_tiles;
-      const int tps = (p.num_tiles + splits - 1) / splits;
-      const double mma_clk = (double)mt * p.ksteps * (n_tile / 2.0);
+      int max_splits = di->sm_count / items;
+      if (max_splits < 1) max_splits = 1;
+      if (max_splits > p.num_tiles) max_splits = p.num_tiles;
+      const double mma_clk = (double)mt * p.ksteps * (n_tile > 128 ? n_tile / 2.0 : 64.0);     // a UMMA costs max(64, N/2) clk
       const double bytes = (double)ncb_max * p.slab_tx_bytes + (double)p.dy_tx_bytes * n_tile / 64.0;
       const double per_tile = mma_clk > bytes / 64.0 ? mma_clk : bytes / 64.0;
-      const int waves = (items * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
       const double epi = (double)mt * n_tile * 12.0;            // plain stores of one accumulator block
-      const double flush = waves * epi;
-      const double est = waves * (tps * per_tile + 3000.0) + flush;
-      if (est < best) { best = est; best_nt = nt; best_mt = mt; }
+      // one pixel split per dW tile stores straight into dW; several splits pay one more launch (~5 us) and
+      // (splits + 1) dW-sized passes through L2/HBM for the slice reduction
+      for (int pass = 0; pass < 2; ++pass) {
+        const int splits = pass == 0 ? 1 : max_splits;
+        if (pass == 1 && max_splits == 1) break;
+        const int tps = (p.num_tiles + splits - 1) / splits;
+        const int waves = (items * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
+        double est = waves * (tps * per_tile + 3000.0 + epi);
+        if (splits > 1) est += 9000.0 + (double)(splits + 1) * (double)dw_elems_est * 4.0 / 2500.0;
+        if (est < best) { best = est; best_nt = nt; best_mt = mt; best_splits = splits; }
+      }
     }
   }
   if (best_nt == 0) return 0;
@@ -595,9 +626,7 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
   p.stages = (kSmemMax - kAux) / p.stage_bytes;
   if (p.stages > kWgsMaxStages) p.stages = kWgsMaxStages;
   const int items = p.m_chunks * p.n_tiles;
-  int splits = di->sm_count / items;
-  if (splits < 1) splits = 1;
-  if (splits > p.num_tiles) splits = p.num_tiles;
+  int splits = best_splits;
   const long long dw_elems = (long long)cout_real * cin_real * p.taps;
   if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)dw_elems * sizeof(float) : 0; return 1; }
   splits = wgrad_fit_splits(splits, dw_elems, ws, ws_bytes);
@@ -748,12 +777,12 @@ int fvt_conv3d_out_shape(const fvt_conv_desc* d, int32_t* to, int32_t* ho, int32
 }
 
 int fvt_conv3d_block_n(const fvt_conv_desc* d) {
-  if (int e = validate_conv(d)) return e;
+  if (int e = validate_conv(d, false)) return e;
   return pick_block_n(d);
 }
 
 size_t fvt_conv3d_packed_weight_elems(const fvt_conv_desc* d) {
-  if (validate_conv(d)) return 0;
+  if (validate_conv(d, false)) return 0;
   const int bn = pick_block_n(d);
   return (size_t)weight_rows(d, bn) * d->kt * d->kh * d->kw * d->cin;
 }
@@ -858,8 +887,9 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_fwd_ex: output lattice (%d,%d,%d) leaves the %dx%dx%d tensor", to, ho, wo,
                        ext->out_extent[0], ext->out_extent[1], ext->out_extent[2]);
   }
-  const int bn = pick_block_n(d);
-  const int rows = weight_rows(d, bn);
+  const int bn0 = pick_block_n(d);
+  const int rows = weight_rows(d, bn0);
+  const int bn = bn0;            // the specialised kernels below use the default N tile
   const int taps = d->kt * d->kh * d->kw;
 
   // ---- K1s: stride-1 'same' spatial convs with <= 128 input channels load each input row once (conv_slab.cuh)
@@ -1192,6 +1222,20 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
   p.m_total = d->n * to * ho * wo;
+  // Small-M layers (conv4_x / conv5_x at a few clips per GPU: fewer M x N tiles than SMs): first narrow the N tile — the
+  // packed weights are plain K-major rows, so any tile width that divides the packed row count reads the same buffer —
+  // until the tiles fill one wave.  That is one launch, deterministic, and needs no workspace; split-K (below) is kept
+  // for the cases where even 64-column tiles leave the reduction long.
+  int bn_g = bn0;
+  if (d->block_n == 0) {
+    const int m_tiles = (p.m_total + kBlockM - 1) / kBlockM;
+    if (m_tiles * (rows / bn0) < di->sm_count) {
+      for (int cand = 64; cand < bn0; cand += 16) {
+        if (rows % cand) continue;
+        if (m_tiles * (rows / cand) <= di->sm_count) { bn_g = cand; break; }
+      }
+    }
+  }
   p.to = to; p.ho = ho; p.wo = wo;
   p.st = d->st; p.sh = d->sh; p.sw = d->sw;
   p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
@@ -1199,9 +1243,9 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
   p.cin_k16 = d->cin / 16;
   p.cin_blocks = (d->cin + kBlockK - 1) / kBlockK;
   p.k_per_tap = d->cin;
-  p.block_n = bn;
+  p.block_n = bn_g;
   p.num_m_tiles = (p.m_total + kBlockM - 1) / kBlockM;
-  p.num_n_tiles = rows / bn;
+  p.num_n_tiles = rows / bn_g;
   p.cout_store = d->cout;
   p.flags = d->flags | o.debug_flags;
   p.scale = scale; p.shift = shift;
@@ -1215,7 +1259,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     p.om_t0 = ext->out_offset[0]; p.om_h0 = ext->out_offset[1]; p.om_w0 = ext->out_offset[2];
   }
 
-  const int b_tile_bytes = bn * kBlockK * 2;
+  const int b_tile_bytes = bn_g * kBlockK * 2;
   int stage_bytes = kATileBytes + b_tile_bytes;
   // barriers + staged scale/shift [2][kMaxCout] — or, for the training forward, statistics partials [4 quadrants][2][rows]
   const int kAuxBytes = 4096 + (((d->flags & FVT_CONV_STATS) && 8 * rows > 2 * kMaxCout) ? 8 * rows * 4 : 2 * kMaxCout * 4);
@@ -1248,7 +1292,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     if (ext == nullptr && !o.disable_split_k && !p.b_stationary && workspace != nullptr && workspace_bytes >= 2 * slice && ((uintptr_t)workspace & 15) == 0 &&
         2 * tiles <= di->sm_count && k_blocks >= 8) {
       int splits = di->sm_count / tiles;
-      if (splits > k_blocks / 4) splits = k_blocks / 4;
+      if (splits > k_blocks / 32) splits = k_blocks / 32;      // a split must keep >= 32 k-blocks, else the finalize pass costs more than it saves
       if (splits > 8) splits = 8;
       if ((size_t)splits > workspace_bytes / slice) splits = (int)(workspace_bytes / slice);
       if (splits >= 2) {
@@ -1265,13 +1309,13 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
   // ---- K1p: streamed-weight layers with at least a few rounds of tile pairs run on CTA pairs (cta_group::2, M = 256):
   //      each CTA loads its own im2col tile and HALF of the weight tile, which takes 30-40 % off the per-SM smem fill
   {
-    const int n_half = bn / 2;
+    const int n_half = bn_g / 2;
     const int stage2 = kATileBytes + (n_half * kBlockK * 2 + 1023) / 1024 * 1024;
     int stages2 = budget / stage2;
     if (stages2 > kMaxStages) stages2 = kMaxStages;
     const long long items = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const bool stats_with_affine = (d->flags & FVT_CONV_STATS) && scale != nullptr;
-    if (ext == nullptr && o.igemm_pair && !p.b_stationary && p.k_splits == 1 && bn >= 128 && di->sm_count % 2 == 0 && stages2 >= 3 &&
+    if (ext == nullptr && o.igemm_pair && !p.b_stationary && p.k_splits == 1 && bn_g >= 128 && di->sm_count % 2 == 0 && stages2 >= 3 &&
         !stats_with_affine && (items >= 3ll * (di->sm_count / 2) || o.igemm_pair == 2)) {
       ConvKernelParams pp = p;
       pp.stages = stages2;
@@ -1293,7 +1337,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       return check_launch("conv_igemm_pair_kernel");
     }
   }
-  if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
+  if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn_g, &tmw)) return e;
 
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < di->sm_count ? tiles : di->sm_count;
@@ -1569,7 +1613,7 @@ size_t fvt_conv3d_workspace_bytes(fvt_handle_t handle, const fvt_conv_desc* d, i
   const int k_blocks = d->kt * d->kh * d->kw * ((d->cin + kBlockK - 1) / kBlockK);
   if (handle->opt.disable_split_k || 2 * tiles > di->sm_count || k_blocks < 8) return 0;
   int splits = di->sm_count / tiles;
-  if (splits > k_blocks / 4) splits = k_blocks / 4;
+  if (splits > k_blocks / 32) splits = k_blocks / 32;
   if (splits > 8) splits = 8;
   return splits >= 2 ? (size_t)splits * (size_t)m_total * d->cout * sizeof(float) : 0;
 }

@@ -7,6 +7,7 @@
 //   N3  softmax_accumulate / argmax_correct  multi-clip softmax averaging + accuracy (validation.py:39-66)
 //       topk_iou                             top-k (k <= 4) intersection / union counts (train_simple_r3d.py:169-197)
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 #include "../../include/fvt_b200.h"
@@ -40,6 +41,11 @@ clip_stats_u8_kernel(const uint8_t* __restrict__ clips, size_t pixels, unsigned 
   }
 }
 
+// One normalised pixel value, the same two roundings wherever it is computed: fma(v, scale, -mean), then * inv_std.
+__device__ __forceinline__ float norm_px(unsigned v, float scale, float m, float inv) {
+  return __fmul_rn(__fmaf_rn(static_cast<float>(v), scale, -m), inv);
+}
+
 // out[n, c, t, h, w] = (in[n, t, h, w', c] * scale - mean[c]) * inv_std[c],  w' = flip[n] ? W-1-w : w
 __global__ void __launch_bounds__(256)
 clip_normalize_u8_kernel(const uint8_t* __restrict__ clips, const uint8_t* __restrict__ flip, float* __restrict__ out, int n,
@@ -55,9 +61,53 @@ clip_normalize_u8_kernel(const uint8_t* __restrict__ clips, const uint8_t* __res
     const int sw = (flip != nullptr && flip[in_]) ? w - 1 - ow : ow;
     const uint8_t* src = clips + ((in_ * plane + row * w + sw) * 3);
     float* dst = out + in_ * 3 * plane + r;
-    dst[0] = (src[0] * scale - m0) * i0;
-    dst[plane] = (src[1] * scale - m1) * i1;
-    dst[2 * plane] = (src[2] * scale - m2) * i2;
+    dst[0] = norm_px(src[0], scale, m0, i0);
+    dst[plane] = norm_px(src[1], scale, m1, i1);
+    dst[2 * plane] = norm_px(src[2], scale, m2, i2);
+  }
+}
+
+// N2 as SURVEY 8f specifies it: decoded uint8 frames -> (crop, flip, per-channel normalise) -> the W-unfolded NDHWC bf16
+// STEM INPUT, in one HBM-bound pass (no fp32 NCDHW tensor in between; the host ships 1 byte per value instead of 4):
+//   u[n, t, h, ow, kw*3 + c] = norm(frame[n, t, y0 + h, x0 + w'(ow*sw - pw + kw), c])   (zero outside the crop)
+// with w'(j) = flip[n] ? W-1-j : j; hpair != 0 interleaves the rows 2*h2, 2*h2+1 per pixel exactly like
+// stem_unfold_kernel (aux_kernels.cu), whose output this reproduces bit for bit.  One thread per output pixel: 21 byte
+// reads (neighbouring threads overlap: L1), one 64-byte store.
+template <int CU>
+__global__ void __launch_bounds__(256)
+clip_unfold_u8_kernel(const uint8_t* __restrict__ clips, const uint8_t* __restrict__ flip, const int* __restrict__ crop_yx,
+                      __nv_bfloat16* __restrict__ u, int n, int t, int hs, int ws, int h, int w, int wo, int kw_taps, int sw,
+                      int pw, int hpair, float scale, float m0, float m1, float m2, float i0, float i1, float i2) {
+  const size_t total = static_cast<size_t>(n) * t * h * wo;
+  const float mm[3] = {m0, m1, m2}, ii[3] = {i0, i1, i2};
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ow = static_cast<int>(i % wo);
+    size_t r = i / wo;
+    const int ih = static_cast<int>(r % h);  r /= h;
+    const int it = static_cast<int>(r % t);
+    const int in = static_cast<int>(r / t);
+    const int y0 = crop_yx != nullptr ? crop_yx[2 * in] : 0, x0 = crop_yx != nullptr ? crop_yx[2 * in + 1] : 0;
+    const bool fl = flip != nullptr && flip[in] != 0;
+    const uint8_t* row = clips + ((static_cast<size_t>(in) * t + it) * hs + (y0 + ih)) * static_cast<size_t>(ws) * 3;
+    __align__(16) __nv_bfloat16 vals[CU];
+#pragma unroll
+    for (int k = 0; k < CU; ++k) vals[k] = __float2bfloat16_rn(0.f);
+    const int w0 = ow * sw - pw;
+    for (int k = 0; k < kw_taps; ++k) {
+      const int iw = w0 + k;
+      if (iw >= 0 && iw < w) {
+        const uint8_t* px = row + static_cast<size_t>(x0 + (fl ? w - 1 - iw : iw)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vals[k * 3 + c] = __float2bfloat16_rn(norm_px(px[c], scale, mm[c], ii[c]));
+      }
+    }
+    size_t o = i;
+    if (hpair) o = ((((static_cast<size_t>(in) * t + it) * (h >> 1) + (ih >> 1)) * wo + ow) << 1) + (ih & 1);
+    uint4* dst = reinterpret_cast<uint4*>(u + o * CU);
+    const uint4* src = reinterpret_cast<const uint4*>(vals);
+#pragma unroll
+    for (int k = 0; k < CU / 8; ++k) dst[k] = src[k];
   }
 }
 
@@ -174,6 +224,27 @@ int fvt_clip_normalize_u8(fvt_handle_t handle, const uint8_t* clips_nthwc, const
   clip_normalize_u8_kernel<<<static_cast<int>(blocks), 256, 0, (cudaStream_t)stream>>>(
       clips_nthwc, flip, out_ncdhw, n, t, h, w, scale, mean[0], mean[1], mean[2], inv_std[0], inv_std[1], inv_std[2]);
   return check_launch("clip_normalize_u8_kernel");
+}
+
+int fvt_clip_unfold_u8(fvt_handle_t handle, const uint8_t* clips_nthwc, const uint8_t* flip, const int32_t* crop_yx, void* u, int32_t n,
+                       int32_t t, int32_t hs, int32_t ws, int32_t h, int32_t w, float scale, const float mean[3],
+                       const float inv_std[3], int32_t kw_taps, int32_t sw, int32_t pw, int32_t cu, int32_t hpair, void* stream) {
+  if (!clips_nthwc || !u || !mean || !inv_std || n <= 0 || t <= 0 || h <= 0 || w <= 0 || hs < h || ws < w)
+    return set_error(FVT_ERR_BAD_DESC, "bad clip_unfold arguments (frames %dx%d, crop %dx%d)", hs, ws, h, w);
+  if (cu != 32 || kw_taps <= 0 || kw_taps * 3 > cu || sw <= 0 || pw < 0) return set_error(FVT_ERR_BAD_DESC, "clip unfold supports cu=32 with 3*kw_taps <= 32");
+  if (hpair && (h & 1)) return set_error(FVT_ERR_BAD_DESC, "row-paired unfold needs an even height (got %d)", h);
+  if (crop_yx == nullptr && (hs != h || ws != w)) return set_error(FVT_ERR_BAD_DESC, "frames larger than the crop need crop offsets");
+  if (((uintptr_t)u) & 15) return set_error(FVT_ERR_MISALIGNED, "u must be 16-byte aligned");
+  int st = 0;
+  if (handle_device(handle, &st) == nullptr) return st;
+  const int wo = (w + 2 * pw - kw_taps) / sw + 1;
+  const size_t total = static_cast<size_t>(n) * t * h * wo;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  clip_unfold_u8_kernel<32><<<static_cast<int>(blocks), 256, 0, (cudaStream_t)stream>>>(
+      clips_nthwc, flip, crop_yx, (__nv_bfloat16*)u, n, t, hs, ws, h, w, wo, kw_taps, sw, pw, hpair, scale, mean[0], mean[1], mean[2],
+      inv_std[0], inv_std[1], inv_std[2]);
+  return check_launch("clip_unfold_u8_kernel");
 }
 
 int fvt_softmax_accumulate(fvt_handle_t handle, const float* logits, float* acc, int32_t rows, int32_t num_class, void* stream) {

@@ -42,7 +42,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Wait with a watchdog: a protocol bug traps (kernel error) instead of hanging the GPU.
+// Wait with a watchdog: a protocol bug traps (kernel error) instead of hanging the GPU.  The limit is far above any
+// legitimate wait — 2^36 clocks, ~35 s at 2 GHz: a wait stretched by GPU time-slicing / MPS, cuda-gdb or ncu kernel replay
+// must not trip it (a trap is a sticky context error that kills the process and its captured graphs).  Build with
+// -DFVT_MBAR_WATCHDOG_CLOCKS=0 to compile the watchdog out, or another value to change the limit.
+#ifndef FVT_MBAR_WATCHDOG_CLOCKS
+#define FVT_MBAR_WATCHDOG_CLOCKS (1ll << 36)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   long long t0 = 0;
@@ -58,10 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) break;
-    if ((++spins & 0x3ff) == 0) {
+    if (FVT_MBAR_WATCHDOG_CLOCKS > 0 && (++spins & 0x3ff) == 0) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();   // ~2 s at 2 GHz
+      else if (now - t0 > FVT_MBAR_WATCHDOG_CLOCKS) __trap();
     }
   }
 }

@@ -101,17 +101,6 @@ def parameter_shapes(model_depth, num_class):
     return params, aux
 
 
-def fold_bn(gamma, beta, mean, var, eps, c_store):
-    """Eval-mode BatchNorm as y = x*scale + shift; pad channels get (0, 0) so they stay exactly zero."""
-    scale = gamma.float() / torch.sqrt(var.float() + eps)
-    shift = beta.float() - mean.float() * scale
-    s = torch.zeros(c_store, dtype=torch.float32, device=gamma.device)
-    b = torch.zeros(c_store, dtype=torch.float32, device=gamma.device)
-    s[: scale.numel()] = scale
-    b[: shift.numel()] = shift
-    return s, b
-
-
 def stem_equivalent_weight(w):
     """(45, 3, 1, 7, 7) stem filter -> (45, 21, 1, 7, 1) filter over the W-unfolded input:
     w_eq[o, kw*3+ci, 0, kh, 0] = w[o, ci, 0, kh, kw]."""
@@ -139,7 +128,13 @@ class StemGeometry:
         wo = (w + 2 * 3 - 7) // 2 + 1
         return (n, t, h // 2, wo, 64) if self.hpair else (n, t, h, wo, STEM_UNFOLD_CH)
 
-    def unfold(self, x, out):
+    def unfold(self, x, out, norm=None):
+        """x: the reference's (N, 3, T, H, W) fp32 clip batch, or decoded uint8 frames (N, T, H, W, 3) with
+        norm = (scale, mean[3], inv_std[3]) — normalised on the fly (ops.clip_unfold_u8: SURVEY 8f N2)."""
+        if x.dtype == torch.uint8:
+            if norm is None:
+                raise ValueError("uint8 clips need the normalisation constants: R2Plus2D.set_input_normalization(...)")
+            return ops.clip_unfold_u8(x, out, norm[0], norm[1], norm[2], self.hpair)
         return ops.stem_unfold_hpair(x, out=out) if self.hpair else ops.stem_unfold(x, out=out)
 
     def weight(self, w):
@@ -164,7 +159,7 @@ class StemGeometry:
 
 
 class _Layer:
-    __slots__ = ("spec", "desc", "w_packed", "scale", "shift", "out_shape", "src", "dst", "res")
+    __slots__ = ("spec", "desc", "w_packed", "scale", "shift", "out_shape", "src", "dst", "res", "is_stem")
 
 
 class InferencePlan:
@@ -177,6 +172,9 @@ class InferencePlan:
         self.pool = pool
         self.layers = []
         self.launches = 0
+        self.eps = eps
+        self.stale = False               # set when the weights moved: refresh() re-packs / re-folds IN PLACE (graphs stay valid)
+        self._fold = ops.BnFoldTable(device)
         bufs = {}
 
         def new_buf(key, shape):
@@ -203,9 +201,12 @@ class InferencePlan:
             to, ho, wo = ops.conv_out_shape(L.desc)
             L.out_shape = (nn_, to, ho, wo, cout_s)
             wt = w_override if w_override is not None else params[spec.name + "_weight"]
+            L.is_stem = w_override is not None
             L.w_packed = ops.pack_conv_weight(L.desc, wt)
-            L.scale, L.shift = fold_bn(params[spec.bn + "_gamma"], params[spec.bn + "_beta"],
-                                       aux[spec.bn + "_moving_mean"], aux[spec.bn + "_moving_var"], eps, cout_s)
+            # eval-mode BatchNorm folded into the conv epilogue: all layers in one launch (fvt_bn_fold_multi), re-run in place
+            # by refresh() when the weights / running statistics move
+            L.scale, L.shift = self._fold.add(params[spec.bn + "_gamma"], params[spec.bn + "_beta"],
+                                              aux[spec.bn + "_moving_mean"], aux[spec.bn + "_moving_var"], eps, cout_s)
             L.src = src
             L.dst = new_buf(dst_key, L.out_shape)
             L.res = res
@@ -237,6 +238,8 @@ class InferencePlan:
             cur, shp = add_layer(main[3], sc_, c, "x1" if flip else "x0", res)
         self.final = cur
         self.bufs = bufs
+        self._fold.run()
+        self._ptrs = self._param_ptrs(params, aux)
         self.fc_w = params["final_fc_weight"].detach().float().contiguous()
         self.fc_b = params["final_fc_bias"].detach().float().contiguous()
         tp, hp, wp = shp[1] - pool[0] + 1, shp[2] - pool[1] + 1, shp[3] - pool[2] + 1
@@ -256,6 +259,27 @@ class InferencePlan:
         self.launches = 1 + len(self.layers) - len(self.fused) + 1
         self.use_graphs = os.environ.get("FVT_INFER_GRAPHS", "1") != "0"
         self._graphs, self._seen = {}, {}
+        self.input_norm = None           # (scale, mean[3], inv_std[3]) for uint8 clips (R2Plus2D.set_input_normalization)
+
+    @staticmethod
+    def _param_ptrs(params, aux):
+        return tuple(t.data_ptr() for t in list(params.values()) + list(aux.values()))
+
+    def refresh(self, params, aux):
+        """The weights or running statistics changed (optimiser step, load): re-pack the bf16 operand copies and re-fold the
+        BatchNorms INTO THE EXISTING BUFFERS — 69 pack launches + one fold launch, no allocation, and the captured forward
+        graphs (which hold those buffers' addresses) stay valid.  Returns False when the parameter storage itself moved
+        (first training forward re-homes the parameters into the flat buffer; .to(device)): the caller rebuilds the plan."""
+        if self._param_ptrs(params, aux) != self._ptrs:
+            return False
+        for L in self.layers:
+            w = params[L.spec.name + "_weight"]
+            ops.pack_conv_weight(L.desc, self.stem.weight(w.detach()) if L.is_stem else w, out=L.w_packed)
+        self._fold.run()
+        self.fc_w.copy_(params["final_fc_weight"].detach())
+        self.fc_b.copy_(params["final_fc_bias"].detach())
+        self.stale = False
+        return True
 
     def _view(self, ref):
         key, shape = ref
@@ -270,7 +294,8 @@ class InferencePlan:
         The ~64 launches of a forward are captured into a CUDA graph per input buffer (keyed by the clip tensor's
         address, captured the third time the same buffer is seen, at most 4 graphs) and replayed: the launches then run
         back to back (12.32 -> 12.1 ms/step at batch 48).  FVT_INFER_GRAPHS=0 keeps every launch eager."""
-        assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w), (tuple(x.shape), (self.n, 3, self.t, self.h, self.w))
+        want = (self.n, self.t, self.h, self.w, 3) if x.dtype == torch.uint8 else (self.n, 3, self.t, self.h, self.w)
+        assert tuple(x.shape) == want, (tuple(x.shape), want)
         x = x.contiguous()
         if not self.use_graphs or torch.cuda.is_current_stream_capturing():
             return self._forward_body(x, want_features, want_map)
@@ -294,7 +319,7 @@ class InferencePlan:
         return tuple(o.clone() for o in out) if isinstance(out, tuple) else out.clone()
 
     def _forward_body(self, x, want_features=False, want_map=False):
-        self.stem.unfold(x, self._view(self.unfold))
+        self.stem.unfold(x, self._view(self.unfold), self.input_norm)
         skip = False
         for i, L in enumerate(self.layers):
             if skip:
@@ -533,7 +558,10 @@ class TrainPlan:
         for L in self.layers.values():
             if L.strided and L.need_dgrad:
                 up_elems = max(up_elems, L.fwd.n * L.fwd.t * L.fwd.h * L.fwd.w * L.cout_s)
-        for nm in ("gA", "gB", "draw0", "draw1", "draw2", "gmask", "gshort", "draw_s"):
+        # raw-gradient scratch buffers rotate so that a weight gradient still reading one on the side stream never sees it
+        # overwritten; more of them let the data-gradient chain run further ahead of the weight gradients
+        self._n_draw = max(3, int(os.environ.get("FVT_DRAW_BUFS", "6")))
+        for nm in ["gA", "gB", "gmask", "gshort", "draw_s"] + ["draw%d" % i for i in range(self._n_draw)]:
             buf(nm, (max_elems,))
         buf("up", (up_elems,))
         self.pooled = None
@@ -548,6 +576,7 @@ class TrainPlan:
         self._logits_static = None
         self._warm_fwd = self._warm_bwd = 0
         self.finish_hook = None          # callable(): wait for gradient reductions launched by grad_hook
+        self.input_norm = None           # (scale, mean[3], inv_std[3]) for uint8 clips
         # Second stream (a parallel branch of the captured graphs): weight re-packing runs beside the first forward
         # layers, and every weight gradient runs beside the data-gradient chain it does not feed.  At batch 4 the
         # conv4_x / conv5_x launches fill 14-49 of the 148 SMs, so the two branches genuinely overlap.
@@ -654,7 +683,12 @@ class TrainPlan:
     def forward(self, x, weights_version):
         """Training-mode forward: re-pack bf16 operand copies if the weights changed, run the network.  Returns fp32
         logits (N, num_class)."""
-        assert tuple(x.shape) == (self.n, 3, self.t, self.h, self.w)
+        want = (self.n, self.t, self.h, self.w, 3) if x.dtype == torch.uint8 else (self.n, 3, self.t, self.h, self.w)
+        assert tuple(x.shape) == want, (tuple(x.shape), want)
+        if x.dtype != self.x_static.dtype:           # the captured graphs read one static input buffer: re-capture for the other form
+            self.x_static = torch.empty(want, dtype=x.dtype, device=self.device)
+            self._fwd_graph = None
+            self._warm_fwd = 0
         self.fwd_generation += 1
         if not self.use_graphs:
             self.refresh_weights(weights_version)
@@ -679,9 +713,23 @@ class TrainPlan:
         self._fwd_graph.replay()
         return self._logits_static.clone()
 
-    def _forward_body(self, x):
+    def forward_map(self, x, weights_version):
+        """Training-mode forward of the TRUNK only (eager launches): returns the conv5_x output (N, T/8, H/16, W/16, 512)
+        bf16 — the input of heads other than pool + Dense (multi-task scene/action heads).  The buffer is
+        plan-owned: backward_map() must run before the next forward of this shape."""
+        self.fwd_generation += 1
+        self.refresh_weights(weights_version)
+        self._forward_body(x.contiguous(), head=False)
+        self._join_side()
+        return self.bufs[self.final_name]
+
+    def backward_map(self, dmap):
+        """Backward of forward_map(): dmap is the gradient w.r.t. the conv5_x output, bf16, same shape."""
+        self._backward_body(None, dmap=dmap.contiguous())
+
+    def _forward_body(self, x, head=True):
         self.stats_all.zero_()
-        self.stem.unfold(x, self.unfold)
+        self.stem.unfold(x, self.unfold, self.input_norm)
         B = self.bufs
         for L in (self.stem0, self.stem1):
             self._conv_bn(L, B[L.src], apply={})
@@ -694,6 +742,8 @@ class TrainPlan:
                 self._conv_bn(d, B[d.src], apply=dict(res=sc.raw, res_scale=sc.scale, res_shift=sc.shift))
             else:
                 self._conv_bn(d, B[d.src], apply=dict(res=xin))
+        if not head:
+            return None
         logits, self.pooled = ops.pool_fc_fwd(B[self.final_name], 512, self.flat.view(self.flat.w, "final_fc_weight"),
                                               self.flat.view(self.flat.w, "final_fc_bias"), want_pooled=True)
         return logits
@@ -731,7 +781,7 @@ class TrainPlan:
         never sees it overwritten); waits for that buffer's last side-stream reader."""
         if key is None:
             key = "draw%d" % self._draw_i
-            self._draw_i = (self._draw_i + 1) % 3
+            self._draw_i = (self._draw_i + 1) % self._n_draw
         ev = self._busy.pop(key, None)
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
@@ -795,13 +845,17 @@ class TrainPlan:
             self._bwd_graph = graph
         self._bwd_graph.replay()
 
-    def _backward_body(self, dlogits):
+    def _backward_body(self, dlogits, dmap=None):
         B = self.bufs
         fl = self.flat
-        final = B[self.final_name]
         g_cur = self._view("gA", self.final_shape)
-        ops.pool_fc_bwd(dlogits, self.pooled, fl.view(fl.w, "final_fc_weight"), fl.view(fl.g, "final_fc_weight"),
-                        fl.view(fl.g, "final_fc_bias"), g_cur)
+        if dmap is not None:                       # the trunk's own pool + Dense head is not part of this graph
+            g_cur.copy_(dmap)
+            fl.view(fl.g, "final_fc_weight").zero_()
+            fl.view(fl.g, "final_fc_bias").zero_()
+        else:
+            ops.pool_fc_bwd(dlogits, self.pooled, fl.view(fl.w, "final_fc_weight"), fl.view(fl.g, "final_fc_weight"),
+                            fl.view(fl.g, "final_fc_bias"), g_cur)
         self._ready("final_fc_weight", "final_fc_bias")
         cur_key = "gA"
         for comp, xin_name, xin_shape, a, b, c, d, sc in reversed(self.blocks):

@@ -64,6 +64,22 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
+def batch_statistics(clips_u8):
+    """Per-channel mean and population std over a whole uint8 clip batch (N, T, H, W, 3), exact integer sums on the device
+    (videos_reader.py:93-94).  Returns (mean[3], std[3]) as python floats, for R2Plus2D.set_input_normalization(mean, std,
+    scale=1.0, std_eps=1e-3)."""
+    require_cuda(clips_u8, "clips")
+    assert clips_u8.dtype == torch.uint8 and clips_u8.dim() == 5 and clips_u8.shape[-1] == 3 and clips_u8.is_contiguous()
+    lib = _lib.load()
+    sums = torch.empty(6, dtype=torch.int64, device=clips_u8.device)
+    pixels = clips_u8.numel() // 3
+    check(lib.fvt_clip_stats_u8(_lib.handle(), _ptr(clips_u8), pixels, _ptr(sums), _stream()))
+    s = sums.cpu().double()
+    mean = s[:3] / pixels
+    std = torch.sqrt(torch.clamp(s[3:] / pixels - mean * mean, min=0.0))
+    return mean.tolist(), std.tolist()
+
+
 def normalize_clips(clips_u8, flip=None, mode="batch"):
     """clips_u8: (N, T, H, W, 3) uint8 CUDA tensor of decoded, cropped frames -> (N, 3, T, H, W) fp32, the layout and
     values the reference feeds the network.

@@ -46,7 +46,8 @@ class _TrainStep(torch.autograd.Function):
         # Activations, BatchNorm statistics and the pooled features live in plan-owned buffers that the next same-shape
         # forward overwrites: remember which forward this graph node belongs to.
         ctx.generation = plan.fwd_generation
-        net._plans.clear()          # a training forward moves the running statistics: folded-BN inference plans are stale
+        for p in net._plans.values():   # a training forward moves the running statistics: folded-BN inference plans are stale
+            p.stale = True
         return out
 
     @staticmethod
@@ -58,6 +59,28 @@ class _TrainStep(torch.autograd.Function):
                 "shape on this network (forward #%d, current #%d).  Run forward -> backward per batch shard (the one-process-"
                 "per-GPU form of train_simple_r3d.py:116-123), or use different networks per shard." % (ctx.generation, plan.fwd_generation))
         plan.backward(dlogits.float())       # every gradient slot is overwritten (MXNet grad_req='write')
+        return None, None, None
+
+
+class _TrunkStep(torch.autograd.Function):
+    """Training-mode forward/backward of the trunk alone: x -> conv5_x output (N, T/8, H/16, W/16, 512) bf16."""
+
+    @staticmethod
+    def forward(ctx, x, net, anchor):
+        plan = net._train_plan(x)
+        ctx.plan = plan
+        fmap = plan.forward_map(x, net._weights_signature())
+        ctx.generation = plan.fwd_generation
+        for p in net._plans.values():
+            p.stale = True
+        return fmap.clone()
+
+    @staticmethod
+    def backward(ctx, dmap):
+        plan = ctx.plan
+        if ctx.generation != plan.fwd_generation:
+            raise RuntimeError("backward() of a trunk forward whose saved activations were overwritten by a later forward")
+        plan.backward_map(dmap.to(torch.bfloat16))
         return None, None, None
 
 
@@ -105,6 +128,7 @@ class R2Plus2D(torch.nn.Module):
         self._trainer = None
         self._grad_anchor = None
         self.bn_momentum = BN_MOMENTUM
+        self._input_norm = None
 
     # ------------------------------------------------------------------ reference helpers
     @staticmethod
@@ -225,9 +249,11 @@ class R2Plus2D(torch.nn.Module):
         self._plans.clear()
 
     def _weights_changed(self):
-        """Optimiser hook: bf16 operand copies are re-packed lazily, folded-BN inference plans are dropped."""
+        """Optimiser hook: the training plan re-packs its operand copies lazily; inference plans are marked stale and
+        re-pack / re-fold in place at their next use (their buffers and captured graphs are kept)."""
         self._weights_version += 1
-        self._plans.clear()
+        for plan in self._plans.values():
+            plan.stale = True
 
     def _weights_signature(self):
         """Changes whenever any parameter or running statistic changes: the module's own counter (bumped by Trainer.step,
@@ -276,34 +302,61 @@ class R2Plus2D(torch.nn.Module):
         self._train_plans.clear()
         return flat
 
+    @staticmethod
+    def _clip_dims(x):
+        """(N, T, H, W) of a clip batch in either accepted form: the reference's (N, 3, T, H, W) fp32, or decoded uint8
+        frames (N, T, H, W, 3)."""
+        if x.dtype == torch.uint8:
+            if x.dim() != 5 or x.shape[-1] != 3:
+                raise ValueError("uint8 clips must be (N, T, H, W, 3) decoded frames")
+            return x.shape[0], x.shape[1], x.shape[2], x.shape[3]
+        if x.dim() != 5 or x.shape[1] != 3:
+            raise ValueError("clips must be (N, 3, T, H, W)")
+        return x.shape[0], x.shape[2], x.shape[3], x.shape[4]
+
+    def set_input_normalization(self, mean, std, scale=1.0 / 255.0, std_eps=0.0):
+        """Constants for uint8 clip batches (N, T, H, W, 3): value = (v*scale - mean[c]) / (std[c] + std_eps), applied
+        inside the stem's input transform (one pass from bytes to the stem operand).  ImageNet statistics with
+        scale = 1/255 is data/ucf101.py:124-128; the per-batch statistics of videos_reader.py:93-97 are
+        evaluate.batch_statistics(clips) with scale = 1, std_eps = 1e-3."""
+        self._input_norm = (float(scale), tuple(float(v) for v in mean), tuple(1.0 / (float(v) + std_eps) for v in std))
+        for plan in list(self._plans.values()) + list(self._train_plans.values()):
+            plan.input_norm = self._input_norm
+
     def _train_plan(self, x):
         flat = self._ensure_flat(x.device)
-        key = (tuple(x.shape), x.device.index)
+        n, t, h, w = self._clip_dims(x)
+        key = ((n, t, h, w), x.device.index)
         plan = self._train_plans.get(key)
         if plan is None:
-            n, _, t, h, w = x.shape
             aux = {k: getattr(self, k) for k in self._aux_names}
             plan = engine.TrainPlan(flat, aux, self.model_depth, self.num_class, self.pool, self.bn_eps, n, t, h, w,
                                     x.device, momentum=self.bn_momentum)
             if self._trainer is not None:
                 plan.set_hooks(self._trainer.on_grads_ready, self._trainer.allreduce_grads)
+            plan.input_norm = self._input_norm
             self._train_plans[key] = plan
         return plan
 
     # ------------------------------------------------------------------ forward
     def _inference_plan(self, x):
         sig = self._weights_signature()
-        if sig != getattr(self, "_plans_sig", None):       # parameters edited in place behind our back: re-fold / re-pack
-            self._plans.clear()
+        if sig != getattr(self, "_plans_sig", None):       # parameters changed (also in place, behind our back): re-fold / re-pack
+            for p in self._plans.values():
+                p.stale = True
             self._plans_sig = sig
-        key = (tuple(x.shape), x.device.index)
+        n, t, h, w = self._clip_dims(x)
+        key = ((n, t, h, w), x.device.index)
         plan = self._plans.get(key)
+        params = {k: getattr(self, k) for k in self._param_names}
+        aux = {k: getattr(self, k) for k in self._aux_names}
+        if plan is not None and getattr(plan, "stale", False):
+            if not (hasattr(plan, "refresh") and plan.refresh(params, aux)):
+                plan = None                                # parameter storage moved: rebuild
         if plan is None:
-            n, _, t, h, w = x.shape
-            params = {k: getattr(self, k) for k in self._param_names}
-            aux = {k: getattr(self, k) for k in self._aux_names}
             cls = engine.InferencePlanF32 if self.precision == "fp32" else engine.InferencePlan
             plan = cls(params, aux, self.model_depth, self.num_class, self.pool, self.bn_eps, n, t, h, w, x.device)
+            plan.input_norm = self._input_norm
             self._plans[key] = plan
         return plan
 
@@ -321,9 +374,13 @@ class R2Plus2D(torch.nn.Module):
 
     def conv5_features(self, x):
         """conv5_x output in the kernels' layout, (N, T/8, H/16, W/16, 512) bf16 — the input of the multi-task heads
-        (reference multi_taskR3d.py:246-251 runs the same trunk)."""
+        (reference multi_taskR3d.py:246-251 runs the same trunk).  In training mode with gradients enabled the result is
+        an autograd node: its backward runs the trunk's full backward pass (batch-statistics BatchNorm, all weight
+        gradients into the flat gradient buffer)."""
         if not x.is_cuda:
             raise RuntimeError("R2Plus2D runs on sm_100a only: move the clip batch to a CUDA device (no CPU fallback)")
+        if self.training and torch.is_grad_enabled():
+            return _TrunkStep.apply(x, self, self._ensure_anchor(x.device))
         return self._inference_plan(x).forward(x, want_map=True)
 
     def extract_features(self, x):

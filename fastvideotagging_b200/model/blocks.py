@@ -9,8 +9,10 @@ the composable pieces a reference user can also instantiate on their own:
 
 Every convolution / BatchNorm / ReLU / add goes through the same C-ABI kernels (ops.conv3d_fwd with the BatchNorm
 folded into the epilogue in eval mode; conv + statistics -> bn_finalize -> bn_apply in training mode).  Inputs and
-outputs are the reference's NCDHW fp32 tensors on a CUDA device; inside, activations are NDHWC bf16.  These modules are
-forward-only (feature extraction / inference / batch-statistics forward); training runs through R2Plus2D + Trainer.
+outputs are the reference's NCDHW fp32 tensors on a CUDA device; inside, activations are NDHWC bf16.  In training mode
+(module.train() with gradients enabled) every Conv3D -> BatchNorm (-> +residual) (-> ReLU) group is ONE autograd node
+(`_ConvBnFn`) whose backward runs the BatchNorm-backward, weight-gradient and data-gradient kernels — eager launches, for
+the heads and stand-alone blocks; the full network trains through R2Plus2D's captured plans.
 """
 import torch
 
@@ -40,6 +42,99 @@ def to_ndhwc(x, c_store=None):
 
 def to_ncdhw(y, c):
     return y[..., :c].permute(0, 4, 1, 2, 3).float().contiguous()
+
+
+class _ToNdhwc(torch.autograd.Function):
+    """Layout change at a block's boundary that gradients pass through: (N,C,T,H,W) fp32 <-> (N,T,H,W,C_store) bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return to_ndhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_ncdhw(g, ctx.c)
+
+
+class _FromNdhwc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, c):
+        ctx.cs = y.shape[-1]
+        return to_ncdhw(y, c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_ndhwc(g, ctx.cs), None
+
+
+def _to_ndhwc(x):
+    return _ToNdhwc.apply(x) if (x.requires_grad and torch.is_grad_enabled()) else to_ndhwc(x)
+
+
+def _from_ndhwc(y, c):
+    return _FromNdhwc.apply(y, c) if (y.requires_grad and torch.is_grad_enabled()) else to_ncdhw(y, c)
+
+
+class _ConvBnFn(torch.autograd.Function):
+    """Training-mode Conv3D -> BatchNorm(batch statistics) [-> + residual] [-> ReLU] on NDHWC bf16 activations:
+    forward  K1(+statistics) -> bn_finalize (MXNet running-stat update) -> bn_apply;
+    backward bn_backward (ReLU mask recomputed from raw, or taken from the block output when a residual joined)
+             -> conv3d_wgrad -> data gradient (fvt_conv3d_fwd with the transposed filter; parity sub-convolutions when strided).
+    A conv bias in front of a batch-statistics BatchNorm cancels in the output (the batch mean absorbs it): it only shifts the
+    running mean and its gradient is exactly zero."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, residual, conv, bn, relu):
+        n, t, h, w, cs = x.shape
+        cout, cout_s = conv.channels, pad16(conv.channels)
+        d = ops.conv_desc(n, t, h, w, cs, cout_s, conv.kernel, conv.strides, conv.padding, FVT_CONV_STATS)
+        wp = ops.pack_conv_weight(d, weight.detach())
+        stats = ops.stats_buffer(cout_s, x.device)
+        raw = ops.conv3d_fwd(d, x, wp, stats=stats)
+        rows = raw.numel() // cout_s
+        scale, shift, mean, invstd = (torch.empty(cout_s, dtype=torch.float32, device=x.device) for _ in range(4))
+        ops.bn_finalize(stats, gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, cout_s, rows, bn.eps, bn.momentum,
+                        scale, shift, mean, invstd)
+        if bias is not None:
+            bn.running_mean.add_((1.0 - bn.momentum) * bias.detach())
+        out = torch.empty_like(raw)
+        ops.bn_apply(raw, scale, shift, out, relu, res=residual)
+        ctx.conv, ctx.d, ctx.relu, ctx.has_res, ctx.has_bias = conv, d, relu, residual is not None, bias is not None
+        ctx.save_for_backward(x, raw, out if (relu and residual is not None) else None, scale, shift, mean, invstd, gamma.detach(), weight.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, raw, out, scale, shift, mean, invstd, gamma, weight = ctx.saved_tensors
+        conv, d = ctx.conv, ctx.d
+        cout, cout_s, cin = conv.channels, raw.shape[-1], conv.in_channels
+        dout = dout.contiguous()
+        sums = torch.empty(2 * cout_s, dtype=torch.float32, device=raw.device)
+        draw = torch.empty_like(raw)
+        dres = None
+        if ctx.has_res:
+            dres = torch.empty_like(raw)
+            ops.bn_backward(raw, dout, out if ctx.relu else None, mean, invstd, gamma, sums, draw, dz_out=dres)
+        elif ctx.relu:
+            ops.bn_backward(raw, dout, None, mean, invstd, gamma, sums, draw, relu_scale=scale, relu_shift=shift)
+        else:
+            ops.bn_backward(raw, dout, None, mean, invstd, gamma, sums, draw)
+        dw = torch.empty_like(weight)
+        ops.conv3d_wgrad(d, x, draw, dw, cout, cin)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if conv.strides != (1, 1, 1):
+                table = ops.PackTable(x.device)
+                plan = ops.DgradPlan(d, weight.permute(0, 2, 3, 4, 1).contiguous(), table)
+                table.run()
+                plan.run(draw, dx)
+            else:
+                dd = ops.dgrad_desc(d)
+                ops.conv3d_fwd(dd, draw, ops.pack_conv_weight_dgrad(dd, weight), out=dx)
+        dbias = torch.zeros(cout, dtype=torch.float32, device=raw.device) if ctx.has_bias else None
+        return dx, dw, dbias, sums[:cout].clone(), sums[cout_s:cout_s + cout].clone(), dres, None, None, None
 
 
 class Conv3D(torch.nn.Module):
@@ -84,20 +179,8 @@ class Conv3D(torch.nn.Module):
                     shift = shift + scale * b
             self._eval_cache = (ver, (d, wp, scale, shift))
             return ops.conv3d_fwd(d, x, wp, scale, shift, residual)
-        if self.bias is not None:
-            raise NotImplementedError("training-mode Conv3D with a bias: train through R2Plus2D (bias-free trunk)")
-        # training mode: batch statistics (biased variance), running-stat update with the MXNet convention
-        d = ops.conv_desc(n, t, h, w, cs, cout_s, self.kernel, self.strides, self.padding, FVT_CONV_STATS)
-        wp = ops.pack_conv_weight(d, self.weight)
-        stats = ops.stats_buffer(cout_s, x.device)
-        raw = ops.conv3d_fwd(d, x, wp, stats=stats)
-        rows = raw.numel() // cout_s
-        scale, shift, mean, invstd = (torch.empty(cout_s, dtype=torch.float32, device=x.device) for _ in range(4))
-        ops.bn_finalize(stats, bn.gamma, bn.beta, bn.running_mean, bn.running_var, cout_s, rows, bn.eps, bn.momentum,
-                        scale, shift, mean, invstd)
-        out = torch.empty_like(raw)
-        ops.bn_apply(raw, scale, shift, out, relu, res=residual)
-        return out
+        # training mode: batch statistics (biased variance), running-stat update with the MXNet convention; one autograd node
+        return _ConvBnFn.apply(x, self.weight, self.bias, bn.gamma, bn.beta, residual, self, bn, relu)
 
 
 class BatchNorm(torch.nn.Module):
@@ -141,7 +224,7 @@ class SpatialTemporalConv(torch.nn.Module):
 
     def forward(self, x):
         _require_cuda(x)
-        return to_ncdhw(self.run(to_ndhwc(x), training=self.training and torch.is_grad_enabled()), self.out_filter)
+        return _from_ndhwc(self.run(_to_ndhwc(x), training=self.training and torch.is_grad_enabled()), self.out_filter)
 
 
 def get_spatial_temporal_conv(in_filters, out_filter, stride, use_bias=False):
@@ -181,7 +264,7 @@ class R3DBlock(torch.nn.Module):
 
     def forward(self, x):
         _require_cuda(x)
-        return to_ncdhw(self.run(to_ndhwc(x), training=self.training and torch.is_grad_enabled()), self.num_filter)
+        return _from_ndhwc(self.run(_to_ndhwc(x), training=self.training and torch.is_grad_enabled()), self.num_filter)
 
 
 class _Stem(torch.nn.Module):

@@ -1,4 +1,7 @@
-"""Other heads on the same convolution kernels, eval-mode forward on K1:
+"""Other heads on the same convolution kernels: eval-mode forward on K1, and training-mode forward +
+backward (module.train() with gradients enabled) through the same BatchNorm / weight-gradient / data-gradient kernels the
+trunk trains with (blocks._ConvBnFn per Conv3D -> BatchNorm -> ReLU group; the trunk's own backward through
+R2Plus2D.conv5_features):
 
 * `R2Plus2D_MT` — the multi-task scene/action network, reference model/multi_taskR3d.py:93-185 (ctor), :246-267
   (forward): the R(2+1)D trunk, then
@@ -40,6 +43,60 @@ class _Dense(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros(units))
 
 
+class _PoolFcFn(torch.autograd.Function):
+    """AvgPool3D (global) + Dense on an NDHWC bf16 map: fvt_pool_fc_fwd / fvt_pool_fc_bwd (the trunk's own head kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, c_real):
+        logits, pooled = ops.pool_fc_fwd(x, c_real, weight.detach().float().contiguous(), bias.detach().float().contiguous(), want_pooled=True)
+        ctx.save_for_backward(pooled, weight.detach().float().contiguous())
+        ctx.shape = tuple(x.shape)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        pooled, w = ctx.saved_tensors
+        dw, db = torch.empty_like(w), torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
+        dx = torch.empty(ctx.shape, dtype=torch.bfloat16, device=w.device)
+        ops.pool_fc_bwd(dlogits.float().contiguous(), pooled, w, dw, db, dx)
+        return dx, dw, db, None
+
+
+class _FlattenDenseFn(torch.autograd.Function):
+    """flatten (NCDHW order, multi_taskR3d.py:254) + Dense as ONE convolution whose window is the whole (T', H', W') map:
+    forward fvt_conv3d_fwd, backward the weight-gradient kernel and the data gradient (a convolution of dY, padded by k-1)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        n, ts, hs, ws, cs = x.shape
+        units = weight.shape[0]
+        up = pad16(units)
+        d = ops.conv_desc(n, ts, hs, ws, cs, up, (ts, hs, ws), (1, 1, 1), (0, 0, 0), 0)
+        w5 = weight.detach().float().reshape(units, -1, ts, hs, ws).contiguous()
+        one = torch.zeros(up, dtype=torch.float32, device=x.device)
+        one[:units] = 1.0
+        b = torch.zeros_like(one)
+        b[:units] = bias.detach().float()
+        y = ops.conv3d_fwd(d, x, ops.pack_conv_weight(d, w5), one, b)
+        ctx.save_for_backward(x, w5)
+        ctx.d, ctx.units = d, units
+        return y.reshape(n, -1)[:, :units].float()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w5 = ctx.saved_tensors
+        d, units = ctx.d, ctx.units
+        n, ts, hs, ws, cs = x.shape
+        up = pad16(units)
+        dyp = torch.zeros((n, 1, 1, 1, up), dtype=torch.bfloat16, device=x.device)
+        dyp[:, 0, 0, 0, :units] = dy.to(torch.bfloat16)
+        dw5 = torch.empty_like(w5)
+        ops.conv3d_wgrad(d, x, dyp, dw5, units, w5.shape[1])
+        dd = ops.conv_desc(n, 1, 1, 1, up, cs, (ts, hs, ws), (1, 1, 1), (ts - 1, hs - 1, ws - 1), 0)
+        dx = ops.conv3d_fwd(dd, dyp, ops.pack_conv_weight_dgrad(dd, w5))
+        return dx, dw5.reshape(units, -1), dy.float().sum(0)
+
+
 class R2Plus2D_MT(torch.nn.Module):
     """forward(x) -> (scene, action), reference multi_taskR3d.py:246-267.  `trunk` is an R2Plus2D whose pooled/dense
     tail is unused; its parameters carry the same canonical names."""
@@ -58,10 +115,31 @@ class R2Plus2D_MT(torch.nn.Module):
         self.pool = (final_temporal_kernel, final_spatial_kernel, final_spatial_kernel)
         self.num_scenes, self.num_actions = num_scenes, num_actions
 
+    dropout = 0.3          # nn.Dropout(0.3) on the scene branch (multi_taskR3d.py:173)
+
+    def _forward_train(self, x):
+        """multi_taskR3d.py:246-267 inside autograd.record(): batch-statistics BatchNorm in the trunk and both heads, Dropout
+        active; backward() fills the trunk's flat gradient buffer and the head parameters' .grad."""
+        self.trunk.train()
+        feat = self.trunk.conv5_features(x)                                   # autograd node: the trunk's full backward
+        s = self.scene_conv.run(feat, self.scene_bn, relu=True, training=True)
+        if tuple(s.shape[1:4]) != self.scene_map:
+            raise ValueError("scene feature map is %s but the Dense layer was sized for %s" % (tuple(s.shape[1:4]), self.scene_map))
+        if self.dropout > 0:                                                  # MXNet Dropout: keep with p = 1 - rate, scale kept values by 1/p
+            keep = (torch.rand(s.shape, device=s.device) >= self.dropout).to(s.dtype) / (1.0 - self.dropout)
+            s = s * keep
+        scene = _FlattenDenseFn.apply(s, self.scene_output.weight, self.scene_output.bias)
+        a = self.action_conv.run(feat, self.action_bn, relu=True, training=True)
+        tp, hp, wpool = a.shape[1] - self.pool[0] + 1, a.shape[2] - self.pool[1] + 1, a.shape[3] - self.pool[2] + 1
+        if (tp, hp, wpool) != (1, 1, 1):
+            raise ValueError("AvgPool3D%s over a %s map: only a global pool is supported" % (self.pool, tuple(a.shape[1:4])))
+        action = _PoolFcFn.apply(a, self.action_output.weight, self.action_output.bias, 512)
+        return scene, action
+
     def forward(self, x):
         _require_cuda(x)
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("R2Plus2D_MT is forward/eval only here; the trunk trains through R2Plus2D + Trainer")
+            return self._forward_train(x)
         feat = self.trunk.conv5_features(x)                                   # (N, T/8, H/16, W/16, 512) bf16
         # ---- scene branch
         s = self.scene_conv.run(feat, self.scene_bn, relu=True)
@@ -101,10 +179,10 @@ class _Basic3D(torch.nn.Module):
             self.down = Conv3D(cin, cout, (3, 3, 3), st, (1, 1, 1))
             self.down_bn = BatchNorm(cout)
 
-    def run(self, x):
-        y = self.conv1.run(x, self.bn1, relu=True)
-        sc = self.down.run(x, self.down_bn, relu=False) if self.project else x
-        return self.conv2.run(y, self.bn2, relu=True, residual=sc)
+    def run(self, x, training=False):
+        y = self.conv1.run(x, self.bn1, relu=True, training=training)
+        sc = self.down.run(x, self.down_bn, relu=False, training=training) if self.project else x
+        return self.conv2.run(y, self.bn2, relu=True, residual=sc, training=training)
 
 
 class ECOLite3DHead(torch.nn.Module):
@@ -121,9 +199,11 @@ class ECOLite3DHead(torch.nn.Module):
 
     def forward(self, x):
         _require_cuda(x)
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("ECOLite3DHead is forward/eval only")
         y = x if (x.dim() == 5 and x.dtype == torch.bfloat16) else to_ndhwc(x)     # NDHWC bf16 is accepted as is
+        if self.training and torch.is_grad_enabled():
+            for blk in self.blocks:                                               # batch-statistics BatchNorm, autograd nodes
+                y = blk.run(y, training=True)
+            return _PoolFcFn.apply(y, self.dense.weight, self.dense.bias, 512)
         for blk in self.blocks:
             y = blk.run(y)
         return ops.pool_fc_fwd(y, 512, self.dense.weight.detach().float().contiguous(), self.dense.bias.detach().float().contiguous())

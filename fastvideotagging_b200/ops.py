@@ -147,49 +147,61 @@ def conv3d_fwd_ex(desc, ext, x, w_packed, out, scale=None, shift=None, residual=
     return out
 
 
+def dgrad_parity_classes(x_ext, k, s, p):
+    """Pure index arithmetic behind DgradPlan.  For a convolution with input extent x_ext, filter k, stride s, padding p
+    (3-tuples over t, h, w): the data gradient splits into one STRIDE-1 convolution of dY per parity class `par` of dX,
+        dX[s*j + par] = sum_e dY[j + e] * w[par + p - s*e],   e = e_lo .. e_hi  (the e with 0 <= par + p - s*e < k).
+    Returns (dY extent, [(par, sub_k, tap_a, pad_lo, pad_hi)]) with sub-filter tap u = e - e_lo copying source tap
+    tap_a - s*u, low padding pad_lo = -e_lo, high padding such that the output has the class's extent.  Classes no filter
+    tap reaches are left out (dX is zero there)."""
+    o_ext = tuple((x_ext[a] + 2 * p[a] - k[a]) // s[a] + 1 for a in range(3))
+    out = []
+    for par_t in range(s[0]):
+        for par_h in range(s[1]):
+            for par_w in range(s[2]):
+                par = (par_t, par_h, par_w)
+                sub_k, tap_a, pad_lo, pad_hi, empty = [], [], [], [], False
+                for a in range(3):
+                    count = (x_ext[a] - par[a] + s[a] - 1) // s[a]             # dX positions of this class on the axis
+                    es = sorted((par[a] + p[a] - kk) // s[a] for kk in range(k[a]) if (par[a] + p[a] - kk) % s[a] == 0)
+                    if count <= 0 or not es:
+                        empty = True
+                        break
+                    if es != list(range(es[0], es[-1] + 1)):
+                        raise NotImplementedError("non-contiguous parity taps")
+                    if es[0] > 0:
+                        raise NotImplementedError("padding beyond the filter's reach is not used by the reference's convolutions")
+                    sub_k.append(es[-1] - es[0] + 1)
+                    pad_lo.append(-es[0])
+                    tap_a.append(par[a] + p[a] - s[a] * es[0])
+                    pad_hi.append(count - o_ext[a] + sub_k[-1] - 1 - pad_lo[-1])
+                    if pad_hi[-1] < 0:
+                        raise NotImplementedError("parity class smaller than dY")
+                if not empty:
+                    out.append((par, tuple(sub_k), tuple(tap_a), tuple(pad_lo), tuple(pad_hi)))
+    return o_ext, out
+
+
 class DgradPlan:
     """Data gradient of a STRIDED convolution as one stride-1 sub-convolution of dY per parity class of dX (header:
-    fvt_conv3d_fwd_ex).  fwd: the forward descriptor (stored channel counts); w_ohwi: its fp32 master (O, kT, kH, kW, I);
-    the sub-filters are registered in `pack_table` (re-packed with the other operand copies).
-    run(dy, out, residual=None): out (N, T, H, W, cin) bf16 <- dgrad (+ residual)."""
+    fvt_conv3d_fwd_ex; index arithmetic: dgrad_parity_classes).  fwd: the forward descriptor (stored channel counts);
+    w_ohwi: its fp32 master (O, kT, kH, kW, I); the sub-filters are registered in `pack_table` (re-packed with the other
+    operand copies).  run(dy, out, residual=None): out (N, T, H, W, cin) bf16 <- dgrad (+ residual)."""
 
     def __init__(self, fwd, w_ohwi, pack_table):
         self.fwd = fwd
-        to, ho, wo = conv_out_shape(fwd)
-        x_ext, o_ext = (fwd.t, fwd.h, fwd.w), (to, ho, wo)
-        k, s, p = (fwd.kt, fwd.kh, fwd.kw), (fwd.st, fwd.sh, fwd.sw), (fwd.pt, fwd.ph, fwd.pw)
+        x_ext, s = (fwd.t, fwd.h, fwd.w), (fwd.st, fwd.sh, fwd.sw)
+        o_ext, cls = dgrad_parity_classes(x_ext, (fwd.kt, fwd.kh, fwd.kw), s, (fwd.pt, fwd.ph, fwd.pw))
+        assert o_ext == conv_out_shape(fwd)
+        self.needs_clear = len(cls) < s[0] * s[1] * s[2]
         self.classes = []
-        self.needs_clear = False
-        for par_t in range(s[0]):
-            for par_h in range(s[1]):
-                for par_w in range(s[2]):
-                    par = (par_t, par_h, par_w)
-                    sub_k, tap_a, pad_hi, empty = [], [], [], False
-                    for a in range(3):
-                        count = (x_ext[a] - par[a] + s[a] - 1) // s[a]             # dX positions of this class on the axis
-                        es = [(par[a] + p[a] - kk) // s[a] for kk in range(k[a]) if (par[a] + p[a] - kk) % s[a] == 0]
-                        if count <= 0 or not es:
-                            empty = True
-                            break
-                        if min(es) < 0:
-                            raise NotImplementedError("padding >= stride*... is not used by the reference's convolutions")
-                        # dY[j + e] for e = 0 .. max(es) (taps that do not exist for some e in between have zero weight:
-                        # the tap map skips nothing here because es is contiguous for k <= s + 1 ... checked below)
-                        if sorted(es) != list(range(0, max(es) + 1)):
-                            raise NotImplementedError("non-contiguous parity taps")
-                        sub_k.append(max(es) + 1)
-                        tap_a.append(par[a] + p[a])
-                        pad_hi.append(count - o_ext[a] + sub_k[-1] - 1)
-                        if pad_hi[-1] < 0:
-                            raise NotImplementedError("parity class smaller than dY")
-                    if empty:
-                        self.needs_clear = True
-                        continue
-                    sub = ConvDesc(fwd.n, to, ho, wo, fwd.cout, fwd.cin, sub_k[0], sub_k[1], sub_k[2], 1, 1, 1, 0, 0, 0, 0, 0)
-                    ext = ConvExt((ctypes.c_int32 * 3)(*pad_hi), (ctypes.c_int32 * 3)(*x_ext), (ctypes.c_int32 * 3)(*s),
-                                  (ctypes.c_int32 * 3)(*par))
-                    wp = pack_table.add_dgrad_sub(sub, w_ohwi, tap_a, s)
-                    self.classes.append((sub, ext, wp))
+        for par, sub_k, tap_a, pad_lo, pad_hi in cls:
+            sub = ConvDesc(fwd.n, o_ext[0], o_ext[1], o_ext[2], fwd.cout, fwd.cin, sub_k[0], sub_k[1], sub_k[2], 1, 1, 1,
+                           pad_lo[0], pad_lo[1], pad_lo[2], 0, 0)
+            ext = ConvExt((ctypes.c_int32 * 3)(*pad_hi), (ctypes.c_int32 * 3)(*x_ext), (ctypes.c_int32 * 3)(*s),
+                          (ctypes.c_int32 * 3)(*par))
+            wp = pack_table.add_dgrad_sub(sub, w_ohwi, tap_a, s)
+            self.classes.append((sub, ext, wp))
 
     def run(self, dy, out, residual=None):
         if self.needs_clear:
@@ -255,6 +267,24 @@ def stem_unfold_hpair(x_ncdhw, kw_taps=7, sw=2, pw=3, cu=32, out=None):
     return out
 
 
+def clip_unfold_u8(clips_u8, out, scale, mean, inv_std, hpair, flip=None, crop_yx=None, crop_hw=None, kw_taps=7, sw=2, pw=3, cu=32):
+    """Decoded uint8 frames (N, T, Hs, Ws, 3) -> crop / flip / normalise -> the W-unfolded bf16 stem input, one pass
+    (fvt_clip_unfold_u8).  out: the tensor stem_unfold / stem_unfold_hpair would write.  scale, mean[3], inv_std[3]:
+    value = (v*scale - mean[c]) * inv_std[c].  crop_yx: (N, 2) int32 device tensor of (y0, x0); crop_hw: (h, w)."""
+    lib = _lib.load()
+    require_cuda(clips_u8, "clips")
+    assert clips_u8.dtype == torch.uint8 and clips_u8.dim() == 5 and clips_u8.shape[-1] == 3 and clips_u8.is_contiguous()
+    n, t, hs, ws, _ = clips_u8.shape
+    h, w = crop_hw if crop_hw is not None else (hs, ws)
+    f3 = ctypes.c_float * 3
+    flip_t = flip.to(clips_u8.device, torch.uint8).contiguous() if flip is not None else None
+    crop_t = crop_yx.to(clips_u8.device, torch.int32).contiguous() if crop_yx is not None else None
+    check(lib.fvt_clip_unfold_u8(_h(clips_u8), _ptr(clips_u8), _ptr(flip_t), _ptr(crop_t), _ptr(out), n, t, hs, ws, h, w,
+                                 ctypes.c_float(scale), f3(*[float(v) for v in mean]), f3(*[float(v) for v in inv_std]),
+                                 kw_taps, sw, pw, cu, int(bool(hpair)), _stream()))
+    return out
+
+
 def pool_fc_fwd(x, c_real, weight, bias, want_pooled=False):
     """x: (N, T, H, W, C) bf16 -> logits (N, num_class) fp32 [and pooled (N, c_real) fp32]."""
     lib = _lib.load()
@@ -316,6 +346,38 @@ def pack_conv_weight_dgrad(ddesc, w_oidhw, out=None, ohwi=False):
     return out
 
 
+class BnFoldTable:
+    """Device table for fvt_bn_fold_multi: eval-mode BatchNorm of every layer folded into (scale, shift) in one launch."""
+
+    _DTYPE = [("gamma", "<u8"), ("beta", "<u8"), ("mean", "<u8"), ("var", "<u8"), ("scale", "<u8"), ("shift", "<u8"),
+              ("c_real", "<i4"), ("c_store", "<i4"), ("eps", "<f4"), ("reserved", "<i4")]
+
+    def __init__(self, device):
+        self.device, self.rows, self._keep, self._dev = device, [], [], None
+
+    def add(self, gamma, beta, mean, var, eps, c_store):
+        """Registers one BatchNorm; returns the (scale, shift) tensors of c_store floats the launch fills."""
+        ts = [t.detach() for t in (gamma, beta, mean, var)]
+        for t in ts:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda, "BatchNorm tensors must be contiguous fp32 CUDA tensors"
+        scale = torch.empty(c_store, dtype=torch.float32, device=self.device)
+        shift = torch.empty(c_store, dtype=torch.float32, device=self.device)
+        self.rows.append(tuple(t.data_ptr() for t in ts) + (scale.data_ptr(), shift.data_ptr(), ts[0].numel(), c_store, float(eps), 0))
+        self._keep.append((ts, scale, shift))
+        self._dev = None
+        return scale, shift
+
+    def run(self):
+        import numpy as np
+        if not self.rows:
+            return
+        if self._dev is None:
+            arr = np.array(self.rows, dtype=np.dtype(self._DTYPE))
+            assert arr.dtype.itemsize == 64
+            self._dev = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
+        check(_lib.load().fvt_bn_fold_multi(_h(self._dev), _ptr(self._dev), len(self.rows), _stream()))
+
+
 class PackTable:
     """Device table for fvt_pack_conv_weights_multi: every (tensor, layout) operand copy of a training step in one launch.
     add_fwd / add_dgrad register fp32 masters stored (O, kT, kH, kW, I) and allocate the packed bf16 buffers."""
@@ -335,6 +397,8 @@ class PackTable:
         lib = _lib.load()
         assert w_ohwi.dtype == torch.float32 and w_ohwi.is_contiguous() and w_ohwi.is_cuda
         elems = lib.fvt_conv3d_packed_weight_elems(ctypes.byref(desc))
+        if elems == 0:
+            check(-1)
         taps = desc.kt * desc.kh * desc.kw
         rows = elems // (taps * desc.cin)
         out = torch.empty(elems, dtype=torch.bfloat16, device=self.device)

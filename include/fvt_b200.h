@@ -235,6 +235,22 @@ int fvt_zero_insert(fvt_handle_t handle, const void* dy, void* up, int32_t n, in
                     int32_t wo, int32_t st, int32_t sh, int32_t sw, int32_t c_store, void* stream);
 
 /* ---- training: BatchNorm (K5-K7), MXNet semantics (A4) ---------------------------------------------------------- */
+/* Eval-mode BatchNorm folded into the producing convolution's epilogue, for every layer of a network in one launch:
+ * scale[c] = gamma[c]/sqrt(var[c] + eps), shift[c] = beta[c] - mean[c]*scale[c] for c < c_real, (0, 0) for the pad channels
+ * up to c_store (they stay exactly zero).  table_dev: DEVICE array of n_entries fvt_bn_fold_entry (device pointers).
+ * (nn.BatchNorm in inference mode, model/R2Plus1.py:32,59,62,71,105,112; running statistics in the MXNet convention.) */
+typedef struct fvt_bn_fold_entry {
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* var;
+  float* scale;
+  float* shift;
+  int32_t c_real, c_store;
+  float eps;
+  int32_t reserved;
+} fvt_bn_fold_entry;
+int fvt_bn_fold_multi(fvt_handle_t handle, const fvt_bn_fold_entry* table_dev, int32_t n_entries, void* stream);
 /* stats_acc = [sum(c_store), sum^2(c_store)] exact accumulators from fvt_conv3d_fwd(FVT_CONV_STATS) over `rows` pixels ->
  * mean, inv_std = 1/sqrt(biased_var + eps), scale = gamma*inv_std, shift = beta - mean*scale;
  * running = momentum*running + (1-momentum)*batch (biased variance) when running_mean != NULL. */
@@ -312,6 +328,14 @@ int fvt_softmax_fwd_bwd(fvt_handle_t handle, const float* logits, const float* l
 int fvt_clip_stats_u8(fvt_handle_t handle, const uint8_t* clips_nthwc, int64_t pixels, uint64_t* sums6, void* stream);
 int fvt_clip_normalize_u8(fvt_handle_t handle, const uint8_t* clips_nthwc, const uint8_t* flip, float* out_ncdhw, int32_t n, int32_t t, int32_t h,
                           int32_t w, float scale, const float mean[3], const float inv_std[3], void* stream);
+/* N2 fused into the stem's input transform: decoded uint8 frames (N, T, Hs, Ws, 3) -> crop (h x w at crop_yx[n] = (y0, x0);
+ * NULL: frames are already h x w) -> flip -> (v*scale - mean[c]) * inv_std[c] -> the W-unfolded NDHWC bf16 stem input of
+ * fvt_stem_unfold (hpair = 0) / fvt_stem_unfold_hpair (hpair = 1), bit for bit what fvt_clip_normalize_u8 followed by
+ * those produces, in ONE pass and without the fp32 NCDHW tensor.  crop_yx is a DEVICE int32[n][2]; mean / inv_std are
+ * HOST arrays.  (videos_reader.py:44-49,58,69-76,93-97; data/ucf101.py:124-128.) */
+int fvt_clip_unfold_u8(fvt_handle_t handle, const uint8_t* clips_nthwc, const uint8_t* flip, const int32_t* crop_yx, void* u, int32_t n,
+                       int32_t t, int32_t hs, int32_t ws, int32_t h, int32_t w, float scale, const float mean[3],
+                       const float inv_std[3], int32_t kw_taps, int32_t sw, int32_t pw, int32_t cu, int32_t hpair, void* stream);
 /* N3, evaluation tail.  acc[rows, C] += softmax(logits[rows, C]) (validation.py:49-51);
  * pred[row] = argmax acc[row] (first maximum), *correct += number of rows with pred == labels (validation.py:61-63). */
 int fvt_softmax_accumulate(fvt_handle_t handle, const float* logits, float* acc, int32_t rows, int32_t num_class, void* stream);

@@ -29,8 +29,11 @@ def test_conv_forward_epilogues(cuda_device):
     assert m.run_case("affine+res+relu", *base, True, True, True)
     assert m.run_case("stats", *base, False, False, False, True)
     assert m.run_case("block_n=64", *base, block_n=64)
-    assert m.run_case("multi-tile persistent", 8, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, True, True)
-    assert m.run_case("ragged M tail", 1, 3, 7, 9, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, False, True, True)
+    # FVT_CONV_STATS describes the RAW output (training forward): it comes without affine / residual / ReLU
+    assert m.run_case("multi-tile persistent", 8, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, True)
+    assert m.run_case("multi-tile persistent, stats", 8, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, False, False, True)
+    assert m.run_case("ragged M tail", 1, 3, 7, 9, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, False, True)
+    assert m.run_case("ragged M tail, stats", 1, 3, 7, 9, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, False, False, True)
 
 
 def test_slab_and_im2col_kernels_agree(cuda_device, lib):
@@ -437,7 +440,7 @@ def test_fused_unit_rejects_other_geometries(cuda_device, lib):
     assert not ops.unit2p1_supported(d_s2, d_t2)
     import ctypes
     with pytest.raises(_lib.FvtError):          # the C entry point itself refuses (bad descriptor pair), nothing is launched
-        _lib.check(lib.fvt_unit2p1_fwd(ctypes.byref(d_s), ctypes.byref(d_t), *([None] * 10)))
+        _lib.check(lib.fvt_unit2p1_fwd(_lib.handle(), ctypes.byref(d_s), ctypes.byref(d_t), *([None] * 10)))
 
 
 @pytest.mark.parametrize("shape", [(2, 4, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1)),     # conv3_x 1x3x3: two N tiles, two channel blocks
@@ -618,7 +621,7 @@ def test_wgrad_split_reduction_is_deterministic_and_overwrites(cuda_device, lib,
     assert torch.equal(a, b)
     scale = ref.abs().max().item()
     assert scale > 0 and torch.isfinite(a).all()
-    assert (a - ref).abs().max().item() <= 1e-5 * scale + 1e-6
+    assert (a - ref).abs().max().item() <= 1e-3 * scale          # fp32 sums over 1e5 pixels in two different orders
 
 
 def test_multi_tensor_pack_matches_single_launch_packs(cuda_device, lib):
@@ -655,6 +658,7 @@ def test_multi_tensor_pack_matches_single_launch_packs(cuda_device, lib):
     (1, 2, 14, 14, 256, 921, (1, 3, 3), (1, 2, 2), (0, 1, 1)),     # conv5_x first conv at T/4 = 2 -> dY has one frame pair
     (1, 2, 7, 7, 921, 512, (3, 1, 1), (2, 1, 1), (1, 0, 0)),       # dY temporal extent 1
     (1, 4, 9, 11, 32, 48, (3, 3, 3), (2, 2, 2), (1, 1, 1)),        # odd extents, full 3x3x3 / s2 (ECO-style)
+    (2, 2, 7, 7, 512, 256, (1, 3, 3), (1, 2, 2), (0, 0, 0)),       # multi-task scene conv: stride 2 WITHOUT padding (low padding in the sub-convolution)
 ])
 def test_strided_dgrad_parity_classes_match_zero_insert_and_autograd(cuda_device, lib, case):
     """Data gradient of a strided convolution as per-parity-class sub-convolutions of dY (fvt_conv3d_fwd_ex + pack kind 2)

@@ -167,14 +167,20 @@ def test_full_size_backward_is_linear_in_the_head_gradient(cuda_device):
     d1 = (torch.randn(4, 101, generator=gen) * 1e-2).to(cuda_device)
     d2 = (torch.randn(4, 101, generator=gen) * 1e-2).to(cuda_device)
 
+    used = torch.zeros_like(plan.flat.g, dtype=torch.bool)
+    for name, (off, numel, shape, store) in plan.flat.slots.items():
+        used[off:off + store] = True
+
     def grads(d):
         plan.flat.g.fill_(float("nan"))             # every slot is overwritten by backward (grad_req='write')
         plan._backward_body(d.contiguous())
         torch.cuda.synchronize()
-        return plan.flat.g.clone()
+        g = plan.flat.g.clone()
+        assert torch.isfinite(g[used]).all(), "a gradient slot was left unwritten (or is not finite)"
+        g[~used] = 0.0                              # the 16-byte alignment gaps between slots are nobody's
+        return g
 
     g1, g2, g12, g1s, g1b = grads(d1), grads(d2), grads(d1 + d2), grads(2.0 * d1), grads(d1)
-    assert torch.isfinite(g12).all()
     # per weight tensor: relative L2 error (BatchNorm beta/gamma gradients of ~1e-9 magnitude are rounding noise and only
     # enter the whole-buffer figure)
     def rel_l2(a, b):
@@ -189,11 +195,7 @@ def test_full_size_backward_is_linear_in_the_head_gradient(cuda_device):
         worst_add = max(worst_add, rel_l2(g12[sl], g1[sl] + g2[sl]))
     all_scale, all_add = rel_l2(g1s, 2.0 * g1), rel_l2(g12, g1 + g2)
     print("linearity rel-L2: scale worst %.3e all %.3e | additivity worst %.3e all %.3e" % (worst_scale, all_scale, worst_add, all_add))
-    used = torch.zeros_like(g1, dtype=torch.bool)
-    for name, (off, numel, shape, store) in plan.flat.slots.items():
-        used[off:off + store] = True
-    assert torch.isfinite(g1[used]).all()                  # no slot was left unwritten
-    assert torch.equal(g1b[used], g1[used]), "the same backward twice must give the same bits"
+    assert torch.equal(g1b, g1), "the same backward twice must give the same bits"
     # x2 is exact in bf16 and in fp32, and the reduction orders are fixed
     assert all_scale <= 1e-6 and worst_scale <= 1e-6, (worst_scale, all_scale)
     assert worst_add < 1e-1 and all_add < 5e-2, (worst_add, all_add)

@@ -120,3 +120,34 @@ def test_lr_schedulers_follow_mxnet_semantics():
     assert [p.shape[0] for p in parts] == [2, 2, 2] and parts[2][0, 0].item() == 8
     with pytest.raises(ValueError):
         split_and_load(torch.zeros(5, 2), [None, None])
+
+
+def test_strided_dgrad_parity_classes_are_the_data_gradient():
+    """ops.dgrad_parity_classes (the index arithmetic behind the direct strided data gradient, fvt_conv3d_fwd_ex): composing the
+    per-class stride-1 sub-convolutions of dY reproduces torch autograd's conv3d input gradient exactly (fp64), for every
+    strided convolution geometry of the network, the multi-task scene conv (stride 2 without padding) and a 3x3x3/s2 stage
+    with odd extents."""
+    import torch
+    import torch.nn.functional as F
+    from fastvideotagging_b200 import ops
+    cases = [((8, 28, 28), (1, 3, 3), (1, 2, 2), (0, 1, 1)), ((8, 14, 14), (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+             ((8, 28, 28), (1, 1, 1), (2, 2, 2), (0, 0, 0)), ((2, 7, 7), (1, 3, 3), (1, 2, 2), (0, 0, 0)),
+             ((4, 9, 11), (3, 3, 3), (2, 2, 2), (1, 1, 1)), ((2, 1, 1), (3, 1, 1), (2, 1, 1), (1, 0, 0))]
+    gen = torch.Generator().manual_seed(0)
+    for x_ext, k, s, p in cases:
+        cin, cout = 3, 4
+        w = torch.randn(cout, cin, *k, dtype=torch.float64, generator=gen)
+        o_ext, cls = ops.dgrad_parity_classes(x_ext, k, s, p)
+        dy = torch.randn(1, cout, *o_ext, dtype=torch.float64, generator=gen)
+        x0 = torch.zeros(1, cin, *x_ext, dtype=torch.float64, requires_grad=True)
+        F.conv3d(x0, w, stride=s, padding=p).backward(dy)
+        dx = torch.zeros(1, cin, *x_ext, dtype=torch.float64)
+        for par, sub_k, tap_a, pad_lo, pad_hi in cls:
+            g = torch.zeros(cin, cout, *sub_k, dtype=torch.float64)
+            for ut in range(sub_k[0]):
+                for uh in range(sub_k[1]):
+                    for uw in range(sub_k[2]):
+                        g[:, :, ut, uh, uw] = w[:, :, tap_a[0] - s[0] * ut, tap_a[1] - s[1] * uh, tap_a[2] - s[2] * uw].t()
+            dyp = F.pad(dy, (pad_lo[2], pad_hi[2], pad_lo[1], pad_hi[1], pad_lo[0], pad_hi[0]))
+            dx[:, :, par[0]::s[0], par[1]::s[1], par[2]::s[2]] = F.conv3d(dyp, g)
+        assert float((dx - x0.grad).abs().max()) < 1e-12, (x_ext, k, s, p)
