@@ -15,6 +15,7 @@ FVT_CONV_RELU = 1
 FVT_CONV_RESIDUAL = 2
 FVT_CONV_STATS = 4
 FVT_CONV_W_OHWI = 8
+FVT_CONV_BN_BWD = 16
 
 
 class FvtError(RuntimeError):

@@ -864,7 +864,15 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
   if ((scale == nullptr) != (shift == nullptr)) return set_error(FVT_ERR_BAD_DESC, "scale and shift must be given together");
   if ((d->flags & FVT_CONV_RESIDUAL) && residual == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_RESIDUAL without a residual tensor");
   if ((d->flags & FVT_CONV_STATS) && stats == nullptr) return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_STATS without a stats buffer");
-  if ((d->flags & FVT_CONV_STATS) && scale != nullptr)
+  const bool bnbwd = (d->flags & FVT_CONV_BN_BWD) != 0;
+  if (bnbwd) {
+    // data gradient fused with the consumer BatchNorm's backward sums: residual = that layer's raw conv output, scale/shift =
+    // its forward BatchNorm constants (ReLU mask), stats_acc = [sum dz*raw, sum dz]
+    if ((d->flags & (FVT_CONV_STATS | FVT_CONV_RESIDUAL | FVT_CONV_RELU)) != (FVT_CONV_STATS | FVT_CONV_RESIDUAL))
+      return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_BN_BWD goes with FVT_CONV_STATS | FVT_CONV_RESIDUAL and without FVT_CONV_RELU");
+    if (scale == nullptr || residual == nullptr || ext != nullptr)
+      return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_BN_BWD needs scale/shift (the BatchNorm's forward constants) and residual (its raw input); not with fvt_conv3d_fwd_ex");
+  } else if ((d->flags & FVT_CONV_STATS) && scale != nullptr)
     return set_error(FVT_ERR_BAD_DESC, "FVT_CONV_STATS describes the RAW convolution output (training forward): scale/shift must be NULL");
   if ((d->flags & FVT_CONV_STATS) && (((uintptr_t)stats) & 7)) return set_error(FVT_ERR_MISALIGNED, "stats accumulators must be 8-byte aligned");
   if (((uintptr_t)x | (uintptr_t)w_packed) & 15) return set_error(FVT_ERR_MISALIGNED, "x / w_packed must be 16-byte aligned");
@@ -913,7 +921,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     const int b_slab = bn * 128;
     const int b_all = taps * sp.cin_blocks;
     const bool want_stats = (d->flags & FVT_CONV_STATS) != 0;
-    const int aux = (512 + (want_stats ? 8 : 2) * rows * 4 + 255) / 256 * 256;      // statistics: [4 quadrants][2][rows] partials
+    const int aux = (512 + (bnbwd ? 10 : want_stats ? 8 : 2) * rows * 4 + 255) / 256 * 256;      // statistics: [4 quadrants][2][rows] partials (after scale/shift with FVT_CONV_BN_BWD)
     const int kSmemMax = 227 * 1024;
     bool ok = useful >= 0.6 && sp.r_in * sp.wp <= slot_rows && sp.r_in <= 256;
     if (ok) {
@@ -966,7 +974,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       //      holds half of the filter rows, which frees shared memory for the staged TMA-store epilogue
       //      Default ("slab_pair_auto") for the layers whose filter does not fit one SM but fits two (conv3_x 128 -> 288 with
       //      one N tile per cluster, conv2_x data gradient 144 -> 64); "slab_pair" forces it for single-SM-stationary layers.
-      const bool pair_shape_ok = bn % 16 == 0 && sp.box_rows == sp.r_in && !(want_stats && scale != nullptr) &&
+      const bool pair_shape_ok = bn % 16 == 0 && sp.box_rows == sp.r_in && !(want_stats && scale != nullptr && !bnbwd) &&
                                  di->sm_count % 2 == 0 && (di->sm_count / 2) % sp.num_n_tiles == 0;
       const bool pair_forced = o.slab_pair && sp.b_stationary && sp.num_n_tiles == 1;
       const bool pair_auto = o.slab_pair_auto && !sp.b_stationary;
@@ -981,7 +989,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
         pp.num_pairs = (num_m_tiles + 1) / 2;
         pp.tma_store = (pair_forced && o.slab_pair == 1 && bn == d->cout) ? 1 : 0;
         pp.out_tile_bytes = (sp.r_out * d->w * d->cout * 2 + 1023) / 1024 * 1024;
-        const int aux2 = (512 + (want_stats ? 32 : 8) * rows + 255) / 256 * 256;
+        const int aux2 = (512 + (bnbwd ? 40 : want_stats ? 32 : 8) * rows + 255) / 256 * 256;
         const int b_bytes = (b_all * pp.n_half * 128 + 1023) / 1024 * 1024;
         const int out_bytes = pp.tma_store ? 2 * pp.out_tile_bytes : 0;
         int stages2 = (kSmemMax - aux2 - b_bytes - out_bytes) / sp.slab_slot_bytes;      // ring slots of one 64-channel block
@@ -1033,7 +1041,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
   //      tile (taps = shifted descriptors, frames outside the clip = TMA zero fill), filter stationary, one N tile per cluster
   if (ext == nullptr && o.slab_pair_auto && !o.disable_slab && d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 &&
       d->sw == 1 && d->ph == 0 && d->pw == 0 && 2 * d->pt == d->kt - 1 && d->cin > 64 && bn % 16 == 0 &&
-      di->sm_count % 2 == 0 && (di->sm_count / 2) % (rows / bn) == 0 && !((d->flags & FVT_CONV_STATS) && scale != nullptr)) {
+      di->sm_count % 2 == 0 && (di->sm_count / 2) % (rows / bn) == 0 && !((d->flags & FVT_CONV_STATS) && scale != nullptr && !bnbwd)) {
     const int kSmemMax = 227 * 1024;
     const int cin_blocks = (d->cin + 63) / 64;
     // would K1i (single SM, every input frame read exactly once) take it?  then leave it there
@@ -1062,7 +1070,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     sp.y = (__nv_bfloat16*)y; sp.stats = stats;
     const int b_all = d->kt * cin_blocks;
     const int b_bytes = (b_all * (bn / 2) * 128 + 1023) / 1024 * 1024;
-    const int aux2 = (512 + ((d->flags & FVT_CONV_STATS) ? 32 : 8) * rows + 255) / 256 * 256;
+    const int aux2 = (512 + (bnbwd ? 40 : (d->flags & FVT_CONV_STATS) ? 32 : 8) * rows + 255) / 256 * 256;
     int stages2 = (kSmemMax - aux2 - b_bytes) / sp.slab_slot_bytes;
     if (stages2 > kPairMaxStages) stages2 = kPairMaxStages;
     const double useful = (double)d->t * sp.w / ((double)row_tiles * r_out * w_chunks * w_tile);
@@ -1125,7 +1133,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     const int stage_bytes = tp.cin_blocks * 128 * 128;
     // TMA-store epilogue for one-row-is-one-line outputs (64 channels): two [128 x 128 B] staging tiles, paid for with
     // one pipeline stage (a stage is released as soon as its frame's MMAs are issued, two are enough to stream)
-    tp.tma_store = (!o.disable_tis_tma_store && bn == 64 && d->cout == 64 &&
+    tp.tma_store = (!o.disable_tis_tma_store && !bnbwd && bn == 64 && d->cout == 64 &&
                     w_bytes + aux + 2 * kTisOutTileBytes + 2 * stage_bytes <= kSmemMax) ? 1 : 0;
     const int out_bytes = tp.tma_store ? 2 * kTisOutTileBytes : 0;
     int stages = (kSmemMax - aux - w_bytes - out_bytes) / stage_bytes;
@@ -1262,7 +1270,8 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
   const int b_tile_bytes = bn_g * kBlockK * 2;
   int stage_bytes = kATileBytes + b_tile_bytes;
   // barriers + staged scale/shift [2][kMaxCout] — or, for the training forward, statistics partials [4 quadrants][2][rows]
-  const int kAuxBytes = 4096 + (((d->flags & FVT_CONV_STATS) && 8 * rows > 2 * kMaxCout) ? 8 * rows * 4 : 2 * kMaxCout * 4);
+  const int kAuxBytes = bnbwd ? 4096 + 2 * kMaxCout * 4 + 8 * rows * 4
+                              : 4096 + (((d->flags & FVT_CONV_STATS) && 8 * rows > 2 * kMaxCout) ? 8 * rows * 4 : 2 * kMaxCout * 4);
   const int budget = 227 * 1024 - 1024 - kAuxBytes;
   // Small filters (one N tile, all taps*cin_blocks weight tiles + >= 4 A stages fit): keep the weights resident in
   // shared memory for the CTA's lifetime instead of re-fetching them from L2 with every 128-pixel tile.
@@ -1289,7 +1298,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int k_blocks = taps * p.cin_blocks;
     const size_t slice = (size_t)p.m_total * d->cout * sizeof(float);
-    if (ext == nullptr && !o.disable_split_k && !p.b_stationary && workspace != nullptr && workspace_bytes >= 2 * slice && ((uintptr_t)workspace & 15) == 0 &&
+    if (ext == nullptr && !bnbwd && !o.disable_split_k && !p.b_stationary && workspace != nullptr && workspace_bytes >= 2 * slice && ((uintptr_t)workspace & 15) == 0 &&
         2 * tiles <= di->sm_count && k_blocks >= 8) {
       int splits = di->sm_count / tiles;
       if (splits > k_blocks / 32) splits = k_blocks / 32;      // a split must keep >= 32 k-blocks, else the finalize pass costs more than it saves
@@ -1314,7 +1323,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     int stages2 = budget / stage2;
     if (stages2 > kMaxStages) stages2 = kMaxStages;
     const long long items = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
-    const bool stats_with_affine = (d->flags & FVT_CONV_STATS) && scale != nullptr;
+    const bool stats_with_affine = (d->flags & FVT_CONV_STATS) && scale != nullptr && !bnbwd;
     if (ext == nullptr && o.igemm_pair && !p.b_stationary && p.k_splits == 1 && bn_g >= 128 && di->sm_count % 2 == 0 && stages2 >= 3 &&
         !stats_with_affine && (items >= 3ll * (di->sm_count / 2) || o.igemm_pair == 2)) {
       ConvKernelParams pp = p;

@@ -271,14 +271,18 @@ bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dac
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
                     const unsigned long long* __restrict__ acc, float* __restrict__ sums, uint4* __restrict__ draw,
-                    uint4* __restrict__ dz_out, size_t rows, int cvec, int c_store, int c_real, float inv_rows) {
+                    uint4* __restrict__ dz_out, size_t rows, int cvec, int c_store, int c_real, float inv_rows, int acc_raw) {
   extern __shared__ float cst[];      // [6][C]: a = gamma*inv_std, a*dbeta/M, a*inv_std*dgamma/M, mean, relu scale, relu shift
   for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
     const float is = invstd[ch];
     const float a = (ch < c_real ? gamma[ch] : 0.f) * is;
-    // exact sums -> one rounding each: dgamma = inv_std * sum dz*(raw - mean), dbeta = sum dz
-    const float dgamma = static_cast<float>(det_read(acc + static_cast<size_t>(ch) * kDetLimbs)) * is;
-    const float dbeta = static_cast<float>(det_read(acc + static_cast<size_t>(c_store + ch) * kDetLimbs));
+    // exact sums -> one rounding each: dgamma = inv_std * sum dz*(raw - mean), dbeta = sum dz.  acc_raw: the first sum was
+    // accumulated as sum dz*raw by the fused data-gradient epilogue; the mean term is taken out here, in double
+    const double s_dz = det_read(acc + static_cast<size_t>(c_store + ch) * kDetLimbs);
+    double s_dzx = det_read(acc + static_cast<size_t>(ch) * kDetLimbs);
+    if (acc_raw) s_dzx -= static_cast<double>(mean[ch]) * s_dz;
+    const float dgamma = static_cast<float>(s_dzx) * is;
+    const float dbeta = static_cast<float>(s_dz);
     if (blockIdx.x == 0) { sums[ch] = dgamma; sums[c_store + ch] = dbeta; }
     cst[ch] = a;
     cst[c_store + ch] = a * dbeta * inv_rows;
@@ -672,7 +676,7 @@ int fvt_bn_backward(fvt_handle_t handle, const void* raw, const void* dact, cons
   const size_t smem_a = sizeof(float) * 6 * c_store;
 #define FVT_BN_APP(M, D) bn_bwd_apply_kernel<M, D><<<blocks, threads, smem_a, (cudaStream_t)stream>>>( \
       (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, relu_scale, relu_shift, acc, sums, \
-      (uint4*)draw, (uint4*)dz_out, rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows))
+      (uint4*)draw, (uint4*)dz_out, rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows), dz_in == 2 ? 1 : 0)
   if (dz_out != nullptr) {
     if (mask_mode == 0) FVT_BN_APP(0, true); else if (mask_mode == 1) FVT_BN_APP(1, true); else FVT_BN_APP(2, true);
   } else {

@@ -137,10 +137,14 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
   // Training forward (statistics, no folded affine): the per-channel sums of ALL tiles of this CTA accumulate in the
   // otherwise unused affine area, one [2][n_pad] block per TMEM lane quadrant, and reach global memory once, after the
   // tile loop (no per-tile barriers, no floating-point atomics: see det_sum.cuh).
-  const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr && p.k_splits == 1;
+  // (kConvBnBwd — data gradient fused with the consumer BatchNorm's backward sums — needs BOTH the staged scale/shift and
+  // the partials: they then follow the affine area)
+  const bool bnbwd = (p.flags & kConvBnBwd) != 0;
+  const bool acc_stats = (p.flags & kConvStats) != 0 && (p.scale == nullptr || bnbwd) && p.k_splits == 1;
   const int n_pad = p.num_n_tiles * p.block_n;
+  float* stat_base = bnbwd ? affine_smem + 2 * kMaxCout : affine_smem;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 8 * n_pad; i += kConvThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * n_pad; i += kConvThreads) stat_base[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -345,7 +349,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         ea.block_n = p.block_n; ea.cout_store = p.cout_store; ea.flags = acc_stats ? p.flags : (p.flags & ~kConvStats);
         ea.scale_smem = has_affine ? affine_smem : nullptr; ea.shift_smem = affine_smem + kMaxCout;
         ea.residual = p.residual; ea.y = p.y;
-        ea.stat_smem = affine_smem + q * 2 * n_pad + n0; ea.stat_stride = n_pad;
+        ea.stat_smem = stat_base + q * 2 * n_pad + n0; ea.stat_stride = n_pad;
         ea.stat_mask = stat_mask_below(static_cast<long long>(m_blk) * kBlockM + q * 32, lane, p.m_total);
         epilogue_chunks(ea, taddr, n0, out_row, grp, lane);
       }
@@ -357,7 +361,7 @@ conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     }
     if (acc_stats && blockIdx.x < num_tiles) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      flush_quadrant_stats(affine_smem, n_pad, p.cout_store, p.stats, et, kEpilogueThreads);
+      flush_quadrant_stats(stat_base, n_pad, p.cout_store, p.stats, et, kEpilogueThreads);
     }
   }
 

@@ -88,10 +88,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       affine_smem[kMaxCout + i] = i < p.cout_store ? __ldg(p.shift + i) : 0.f;
     }
   }
-  const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr;
+  const bool bnbwd = (p.flags & kConvBnBwd) != 0;
+  const bool acc_stats = (p.flags & kConvStats) != 0 && (p.scale == nullptr || bnbwd);
   const int n_pad = p.num_n_tiles * p.block_n;
+  float* stat_base = bnbwd ? affine_smem + 2 * kMaxCout : affine_smem;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 8 * n_pad; i += kConvThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * n_pad; i += kConvThreads) stat_base[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   pair::cluster_sync_all();
@@ -209,7 +211,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       ea.block_n = p.block_n; ea.cout_store = p.cout_store; ea.flags = acc_stats ? p.flags : (p.flags & ~kConvStats);
       ea.scale_smem = has_affine ? affine_smem : nullptr; ea.shift_smem = affine_smem + kMaxCout;
       ea.residual = p.residual; ea.y = p.y;
-      ea.stat_smem = affine_smem + q * 2 * n_pad + n0; ea.stat_stride = n_pad;   // statistics only without a folded affine (acc_stats)
+      ea.stat_smem = stat_base + q * 2 * n_pad + n0; ea.stat_stride = n_pad;   // statistics only without a folded affine (acc_stats)
       ea.stat_mask = stat_mask_below(static_cast<long long>(m_blk) * kBlockM + q * 32, lane, p.m_total);
       epilogue_prefetch_residual(ea, n0, row_ok ? row : -1ll, grp);
       ptx::mbar_wait(ptx::smem_u32(&acc_full_bar[acc]), acc_phase);
@@ -223,7 +225,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
     if (acc_stats && item0 < num_items) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      flush_quadrant_stats(affine_smem, n_pad, p.cout_store, p.stats, et, kEpilogueThreads);
+      flush_quadrant_stats(stat_base, n_pad, p.cout_store, p.stats, et, kEpilogueThreads);
     }
   }
 

@@ -127,9 +127,12 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
   // training forward (statistics, no folded affine): sums of all tiles of this CTA accumulate in the unused affine area,
   // one [2][n_total] block per TMEM lane quadrant, and are flushed to global memory once after the tile loop
-  const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr;
+  // (kConvBnBwd needs the staged scale/shift AND the partials: they then follow the affine area)
+  const bool bnbwd = (p.flags & kConvBnBwd) != 0;
+  const bool acc_stats = (p.flags & kConvStats) != 0 && (p.scale == nullptr || bnbwd);
+  float* stat_base = bnbwd ? affine_smem + 2 * n_total : affine_smem;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 8 * n_total; i += kThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * n_total; i += kThreads) stat_base[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -333,7 +336,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const long long out_row = ok ? (static_cast<long long>(frame) * p.h + h0 + hl) * p.w + wl : -1ll;
       for (int nt = 0; nt < p.num_n_tiles; ++nt) {
         const int n0 = nt * p.n_tile;
-        ea.stat_smem = affine_smem + q * 2 * n_total + n0;
+        ea.stat_smem = stat_base + q * 2 * n_total + n0;
         epilogue_prefetch_residual(ea, n0, out_row, grp);
         ptx::mbar_wait(ptx::smem_u32(&acc_full[acc]), acc_phase);
         ptx::tc_fence_after();
@@ -347,7 +350,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
     if (acc_stats && static_cast<int>(blockIdx.x) < num_m_tiles) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      flush_quadrant_stats(affine_smem, n_total, p.cout_store, p.stats, et, kEpiThreads);
+      flush_quadrant_stats(stat_base, n_total, p.cout_store, p.stats, et, kEpiThreads);
     }
   }
 

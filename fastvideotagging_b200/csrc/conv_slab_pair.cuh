@@ -181,9 +181,11 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     }
   }
   // statistics accumulate in the affine area, [4 quadrants][2][n_total] (sized by the host when FVT_CONV_STATS is set)
-  const bool acc_stats = (p.flags & kConvStats) != 0 && p.scale == nullptr;
+  const bool bnbwd = (p.flags & kConvBnBwd) != 0;               // staged scale/shift AND partials: the partials follow the affine area
+  const bool acc_stats = (p.flags & kConvStats) != 0 && (p.scale == nullptr || bnbwd);
+  float* stat_base = bnbwd ? affine_smem + 2 * n_total : affine_smem;
   if (acc_stats)
-    for (int i = threadIdx.x; i < 8 * n_total; i += kPairThreads) affine_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * n_total; i += kPairThreads) stat_base[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   pair::cluster_sync_all();                    // barriers of both CTAs are initialised before anything arrives remotely
@@ -304,7 +306,7 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     EpilogueArgs ea;
     ea.block_n = p.n_tile; ea.cout_store = p.cout_store; ea.flags = acc_stats ? p.flags : (p.flags & ~kConvStats);
     ea.scale_smem = p.scale != nullptr ? affine_smem : nullptr; ea.shift_smem = affine_smem + n_total;
-    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = affine_smem + q * 2 * n_total + n0; ea.stat_stride = n_total;
+    ea.residual = p.residual; ea.y = p.y; ea.stat_smem = stat_base + q * 2 * n_total + n0; ea.stat_stride = n_total;
     const int r = q * 32 + lane;                 // GEMM row = padded position inside the tile
     const int hl = r / p.wp, wl = r - hl * p.wp;
     int shl[4], swl[4];
@@ -364,7 +366,7 @@ conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (pp.tma_store && et == 0) ptx::tma_store_wait<0>();
     if (acc_stats && pair0 < pp.num_pairs) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      flush_quadrant_stats(affine_smem, n_total, p.cout_store, p.stats, et, 256, n0,
+      flush_quadrant_stats(stat_base, n_total, p.cout_store, p.stats, et, 256, n0,
                            n0 + p.n_tile < p.cout_store ? n0 + p.n_tile : p.cout_store);
     }
   }

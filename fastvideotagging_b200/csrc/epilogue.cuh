@@ -11,6 +11,7 @@ enum ConvFlags : int {
   kConvRelu = 1,
   kConvResidual = 2,
   kConvStats = 4,
+  kConvBnBwd = 16,       // data-gradient epilogue fused with the consumer BatchNorm's backward reduction (see epilogue_chunks_bnbwd)
   kDbgNoStore = 256,     // experiments only (fvt_set_option("debug_flags")): skip the global stores
   kDbgNoEpilogue = 512,  // experiments only: epilogue does the barrier handshakes but touches no data
 };
@@ -213,11 +214,89 @@ __device__ __forceinline__ void epilogue_chunks_impl(const EpilogueArgs& p, uint
   }
 }
 
+// Data-gradient epilogue fused with the first pass of the BatchNorm backward it feeds (kConvBnBwd).  The convolution
+// computes dact = d(loss)/d(activation) of a layer whose activation was relu(raw*scale + shift) (BatchNorm + ReLU on the raw
+// conv output `raw`).  Instead of storing dact and letting bn_bwd_reduce read dact and raw again, the epilogue
+//   * reads this thread's row of `raw` (through p.residual, like a residual operand),
+//   * masks: dz = (raw*scale + shift > 0) ? dact : 0  (scale / shift staged in shared memory like the folded affine),
+//   * stores dz (bf16) and accumulates the per-channel sums of the STORED values: sum dz*raw and sum dz (quantities 0 and 1 of
+//     the statistics partials; bn_bwd_apply turns them into dgamma = inv_std*(sum dz*raw - mean*sum dz) and dbeta = sum dz).
+// One accumulator row per thread, so a column sum is a reduction over the warp's 32 lanes: recursive halving over the 32
+// values (16 columns x 2 quantities) leaves lane L with the sum of value L after 16 + 8 + 4 + 2 + 1 = 31 shuffles.
+__device__ __forceinline__ void epilogue_chunks_bnbwd(const EpilogueArgs& p, uint32_t taddr, int n0, long long out_row, int grp,
+                                                      int lane) {
+  const bool row_ok = out_row >= 0;
+  const int n_chunks = p.block_n >> 4;
+  float* stat_smem = p.stat_smem;
+  __nv_bfloat16* yrow = p.y + static_cast<size_t>(row_ok ? out_row : 0) * p.cout_store;
+  const __nv_bfloat16* rrow = p.residual + static_cast<size_t>(row_ok ? out_row : 0) * p.cout_store;
+  uint32_t v[16], vn[16];
+  uint32_t rr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int ci = grp;
+  if (ci < n_chunks) {
+    ptx::tmem_ld_32x32b_x16(taddr + ci * 16, vn);
+    if (row_ok && n0 + ci * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + ci * 16, rn);
+  }
+  const int ngrp = p.ngrp;
+  for (; ci < n_chunks; ci += ngrp) {
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = vn[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rr[i] = rn[i];
+    const int c = ci * 16;
+    const int ch0 = n0 + c;
+    const int cnext = ci + ngrp;
+    if (cnext < n_chunks) {
+      ptx::tmem_ld_32x32b_x16(taddr + cnext * 16, vn);
+      if (row_ok && n0 + cnext * 16 < p.cout_store) ptx::ld_global_nc_256(rrow + n0 + cnext * 16, rn);
+    }
+    if (ch0 >= p.cout_store) continue;           // N tail (weights zero-padded to a whole tile)
+    float vals[32];
+    uint32_t o[8];
+    {
+      const float4* sc4 = reinterpret_cast<const float4*>(p.scale_smem + ch0);
+      const float4* sh4 = reinterpret_cast<const float4*>(p.shift_smem + ch0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = sc4[i], b = sh4[i];
+        const float as[4] = {a.x, a.y, a.z, a.w}, bs[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          const int e = 4 * i + j;
+          const float r0 = bf16_lo(rr[e >> 1]), r1 = bf16_hi(rr[e >> 1]);
+          const float g0 = (row_ok && fmaf(r0, as[j], bs[j]) > 0.f) ? __uint_as_float(v[e]) : 0.f;
+          const float g1 = (row_ok && fmaf(r1, as[j + 1], bs[j + 1]) > 0.f) ? __uint_as_float(v[e + 1]) : 0.f;
+          const uint32_t pk = pack_bf16x2(g0, g1);
+          o[e >> 1] = pk;
+          const float q0 = bf16_lo(pk), q1 = bf16_hi(pk);        // the stored values
+          vals[e] = q0 * r0;      vals[e + 1] = q1 * r1;
+          vals[16 + e] = q0;      vals[16 + e + 1] = q1;
+        }
+      }
+    }
+    if (row_ok && !(p.flags & kDbgNoStore)) ptx::st_global_256(yrow + ch0, o);
+    // recursive halving over lane bits 4..0: lane L ends with the warp's sum of vals[L]
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+      const bool up = (lane & half) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float send = up ? vals[i] : vals[i + half];
+        const float keep = up ? vals[i + half] : vals[i];
+        vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+      }
+    }
+    stat_smem[((lane & 16) ? p.stat_stride : 0) + c + (lane & 15)] += vals[0];      // this warp owns the slot: no atomic
+  }
+}
+
 // Two instantiations: the statistics variant (training forward) carries the extra TMEM fragments and shuffles; the
 // inference variant must not pay for them in registers or scheduling.
 __device__ __forceinline__ void epilogue_chunks(const EpilogueArgs& p, uint32_t taddr, int n0, long long out_row,
                                                 int grp, int lane) {
-  if (p.flags & kConvStats) epilogue_chunks_impl<true>(p, taddr, n0, out_row, grp, lane);
+  if (p.flags & kConvBnBwd) epilogue_chunks_bnbwd(p, taddr, n0, out_row, grp, lane);
+  else if (p.flags & kConvStats) epilogue_chunks_impl<true>(p, taddr, n0, out_row, grp, lane);
   else epilogue_chunks_impl<false>(p, taddr, n0, out_row, grp, lane);
 }
 

@@ -462,7 +462,7 @@ class FlatParams:
 class _TLayer:
     __slots__ = ("spec", "fwd", "dgr", "w_name", "cin_real", "cout_real", "cin_s", "cout_s", "rows", "in_shape",
                  "out_shape", "src", "raw", "act", "stats", "scale", "shift", "mean", "invstd", "wp", "wpd", "w_eq",
-                 "strided", "need_dgrad", "dplan")
+                 "strided", "need_dgrad", "dplan", "bnacc", "dgr_bn")
 
 
 class TrainPlan:
@@ -518,6 +518,7 @@ class TrainPlan:
                 setattr(L, nm, buf(spec.name + ":" + nm, (L.cout_s,), torch.float32))
             L.wp = L.wpd = L.w_eq = None
             L.dplan = None
+            L.bnacc = L.dgr_bn = None
             self.layers[spec.name] = L
             return L
 
@@ -545,9 +546,13 @@ class TrainPlan:
         self.final_name, self.final_shape = cur_name, cur_shape
         # per-channel (sum, sum^2) exact accumulators of every conv in ONE buffer: a single memset per step
         self.stats_all = ops.stats_buffer(sum(L.cout_s for L in self.layers.values()), device)
+        # exact accumulators of the BatchNorm backward sums that the fused data-gradient epilogues fill (FVT_CONV_BN_BWD)
+        self.fuse_bnbwd = os.environ.get("FVT_FUSE_BNBWD", "1") != "0"
+        self.bnacc_all = ops.stats_buffer(sum(L.cout_s for L in self.layers.values()), device)
         off = 0
         for L in self.layers.values():
             L.stats = self.stats_all[off:off + 2 * L.cout_s]
+            L.bnacc = self.bnacc_all[off:off + 2 * L.cout_s]
             off += 2 * L.cout_s
         tp, hp, wp = cur_shape[1] - pool[0] + 1, cur_shape[2] - pool[1] + 1, cur_shape[3] - pool[2] + 1
         if (tp, hp, wp) != (1, 1, 1):
@@ -589,6 +594,24 @@ class TrainPlan:
         # timing experiments only (tools/gpu_train_ablate.py): FVT_SKIP=wgrad,dgrad,bnbwd leaves those launches out, which
         # shows each family's marginal cost inside the replayed graph (results are garbage then)
         self._skip = set(filter(None, os.environ.get("FVT_SKIP", "").split(",")))
+        # timing experiments only (tools/gpu_train_stages.py): FVT_STAGE_EVENTS=1 records an external timing event on the
+        # main stream after the stem and after every residual block, inside the captured graphs too, so the replayed step
+        # can be read as a per-stage timeline
+        self._marks = {} if os.environ.get("FVT_STAGE_EVENTS", "0") == "1" else None
+
+    def _mark(self, label):
+        if self._marks is None:
+            return
+        ev = self._marks.get(label)
+        if ev is None:
+            ev = self._marks[label] = torch.cuda.Event(enable_timing=True, external=True)
+        ev.record(torch.cuda.current_stream(self.device))
+
+    def stage_times(self):
+        """[(label, ms since the previous mark)] of the last executed step (FVT_STAGE_EVENTS=1; synchronises)."""
+        torch.cuda.synchronize(self.device)
+        labels = list(self._marks)
+        return [(b, self._marks[a].elapsed_time(self._marks[b])) for a, b in zip(labels, labels[1:])]
 
     def set_hooks(self, grad_hook, finish_hook):
         """Attach (or change) the gradient-reduction hooks.  They are baked into the captured backward graph, so a change
@@ -728,11 +751,13 @@ class TrainPlan:
         self._backward_body(None, dmap=dmap.contiguous())
 
     def _forward_body(self, x, head=True):
+        self._mark("fwd:start")
         self.stats_all.zero_()
         self.stem.unfold(x, self.unfold, self.input_norm)
         B = self.bufs
         for L in (self.stem0, self.stem1):
             self._conv_bn(L, B[L.src], apply={})
+        self._mark("fwd:stem")
         for comp, xin_name, xin_shape, a, b, c, d, sc in self.blocks:
             xin = B[xin_name]
             for L in (a, b, c):
@@ -742,10 +767,12 @@ class TrainPlan:
                 self._conv_bn(d, B[d.src], apply=dict(res=sc.raw, res_scale=sc.scale, res_shift=sc.shift))
             else:
                 self._conv_bn(d, B[d.src], apply=dict(res=xin))
+            self._mark("fwd:block%s" % comp)
         if not head:
             return None
         logits, self.pooled = ops.pool_fc_fwd(B[self.final_name], 512, self.flat.view(self.flat.w, "final_fc_weight"),
                                               self.flat.view(self.flat.w, "final_fc_bias"), want_pooled=True)
+        self._mark("fwd:head")
         return logits
 
     # ------------------------------------------------------------------ backward
@@ -763,6 +790,9 @@ class TrainPlan:
         self.grad_hook(lo, hi)
 
     def _bn_bwd(self, L, dact, mask, draw, dz_out=None):
+        """mask: True = ReLU directly after this BatchNorm (mask recomputed from raw); a tensor = ReLU after a residual join
+        (mask by that tensor's sign); None = no ReLU; "fused" = `dact` already is the masked gradient and L.bnacc holds
+        [sum dz*raw, sum dz], both written by the data-gradient convolution's epilogue (_dgrad(fuse_bn=L))."""
         if "bnbwd" in self._skip:
             return
         gname, bname, _, _ = self._bn_names(L)
@@ -770,7 +800,10 @@ class TrainPlan:
         off_g, off_b = self.flat.slots[gname][0], self.flat.slots[bname][0]
         assert off_b == off_g + L.cout_s, "gamma/beta slots must be adjacent"
         sums2 = self.flat.g[off_g:off_g + 2 * L.cout_s]
-        if mask is True:          # ReLU directly after this BatchNorm: recompute the mask from raw (one read less)
+        if isinstance(mask, str):
+            ops.bn_backward(L.raw, dact, None, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, None,
+                            sums_acc=L.bnacc, dz_in=2)
+        elif mask is True:        # ReLU directly after this BatchNorm: recompute the mask from raw (one read less)
             ops.bn_backward(L.raw, dact, None, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, dz_out,
                             relu_scale=L.scale, relu_shift=L.shift)
         else:
@@ -813,8 +846,23 @@ class TrainPlan:
         else:
             ops.conv3d_wgrad(L.fwd, x_in, draw, self.flat.raw(self.flat.g, L.w_name), L.cout_real, L.cin_real, ohwi=True)
 
-    def _dgrad(self, L, draw, out, residual=None):
+    def _can_fuse_bn(self, L):
+        """The data gradient of L feeds exactly one BatchNorm backward whose ReLU mask comes from its own raw output: fusable
+        unless L is strided (its data gradient runs as parity sub-convolutions onto a lattice)."""
+        return self.fuse_bnbwd and L.dplan is None and not L.strided and "dgrad" not in self._skip and "bnbwd" not in self._skip
+
+    def _dgrad(self, L, draw, out, residual=None, fuse_bn=None):
+        """Data gradient of L.  fuse_bn = the producer layer P of L's input (act_P = relu(bn(raw_P))): the epilogue masks with
+        P's ReLU and accumulates P's BatchNorm backward sums (FVT_CONV_BN_BWD), `out` then holds dz and _bn_bwd(P, out,
+        "fused", ...) runs its apply pass only."""
         if "dgrad" in self._skip:
+            return out
+        if fuse_bn is not None:
+            P = fuse_bn
+            if L.dgr_bn is None:
+                L.dgr_bn = ops.ConvDesc(*L.dgr.key())
+                L.dgr_bn.flags = ops.FVT_CONV_STATS | ops.FVT_CONV_BN_BWD | ops.FVT_CONV_RESIDUAL
+            ops.conv3d_fwd(L.dgr_bn, draw, L.wpd, scale=P.scale, shift=P.shift, residual=P.raw, out=out, stats=P.bnacc)
             return out
         if L.dplan is not None:
             return L.dplan.run(draw, out, residual)
@@ -849,6 +897,9 @@ class TrainPlan:
         B = self.bufs
         fl = self.flat
         g_cur = self._view("gA", self.final_shape)
+        self._mark("bwd:start")
+        if self.fuse_bnbwd:
+            self.bnacc_all.zero_()                 # one memset for every fused BatchNorm backward of the step
         if dmap is not None:                       # the trunk's own pool + Dense head is not part of this graph
             g_cur.copy_(dmap)
             fl.view(fl.g, "final_fc_weight").zero_()
@@ -857,6 +908,7 @@ class TrainPlan:
             ops.pool_fc_bwd(dlogits, self.pooled, fl.view(fl.w, "final_fc_weight"), fl.view(fl.g, "final_fc_weight"),
                             fl.view(fl.g, "final_fc_bias"), g_cur)
         self._ready("final_fc_weight", "final_fc_bias")
+        self._mark("bwd:head")
         cur_key = "gA"
         for comp, xin_name, xin_shape, a, b, c, d, sc in reversed(self.blocks):
             xin = B[xin_name]
@@ -872,17 +924,22 @@ class TrainPlan:
             else:
                 gshort = gmask
             self._wgrad(d, c.act, draw_d)
-            gc = self._dgrad(d, draw_d, self._view(other, c.out_shape))
+            # (data gradient -> the BatchNorm backward it feeds) pairs: the ReLU mask and the per-channel sums are taken in
+            # the convolution's epilogue where possible, so the BatchNorm backward is one pass instead of two
+            f = self._can_fuse_bn(d)
+            gc = self._dgrad(d, draw_d, self._view(other, c.out_shape), fuse_bn=c if f else None)
             draw_c = self._draw(c.out_shape)
-            self._bn_bwd(c, gc, True, draw_c)
+            self._bn_bwd(c, gc, "fused" if f else True, draw_c)
             self._wgrad(c, b.act, draw_c)
-            gb = self._dgrad(c, draw_c, self._view(cur_key, b.out_shape))
+            f = self._can_fuse_bn(c)
+            gb = self._dgrad(c, draw_c, self._view(cur_key, b.out_shape), fuse_bn=b if f else None)
             draw_b = self._draw(b.out_shape)
-            self._bn_bwd(b, gb, True, draw_b)
+            self._bn_bwd(b, gb, "fused" if f else True, draw_b)
             self._wgrad(b, a.act, draw_b)
-            ga = self._dgrad(b, draw_b, self._view(other, a.out_shape))
+            f = self._can_fuse_bn(b)
+            ga = self._dgrad(b, draw_b, self._view(other, a.out_shape), fuse_bn=a if f else None)
             draw_a = self._draw(a.out_shape)
-            self._bn_bwd(a, ga, True, draw_a)
+            self._bn_bwd(a, ga, "fused" if f else True, draw_a)
             self._wgrad(a, xin, draw_a)
             g_cur = self._dgrad(a, draw_a, self._view(cur_key, xin_shape), residual=gshort)
             names = []
@@ -891,18 +948,22 @@ class TrainPlan:
             if self.grad_hook is not None:
                 self._join_side()                 # the block's weight gradients must be final before they are reduced
             self._ready(*names)
+            self._mark("bwd:block%s" % comp)
         # stem
         other = "gB" if cur_key == "gA" else "gA"
         draw1 = self._draw(self.stem1.out_shape)
         self._bn_bwd(self.stem1, g_cur, True, draw1)
         self._wgrad(self.stem1, self.stem0.act, draw1)
-        g0 = self._dgrad(self.stem1, draw1, self._view(other, self.stem0.out_shape))
+        f = self._can_fuse_bn(self.stem1)
+        g0 = self._dgrad(self.stem1, draw1, self._view(other, self.stem0.out_shape), fuse_bn=self.stem0 if f else None)
         draw0 = self._draw(self.stem0.out_shape)
-        self._bn_bwd(self.stem0, g0, True, draw0)
+        self._bn_bwd(self.stem0, g0, "fused" if f else True, draw0)
         self._wgrad(self.stem0, self.unfold, draw0)
         names = []
         for L in (self.stem0, self.stem1):
             names += [L.w_name, L.spec.bn + "_gamma", L.spec.bn + "_beta"]
+        self._mark("bwd:stem")
         self._join_side()
         self._busy.clear()
         self._ready(*names)
+        self._mark("bwd:joined")

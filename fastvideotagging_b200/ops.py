@@ -4,7 +4,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, ConvExt, FVT_CONV_RELU, FVT_CONV_RESIDUAL, FVT_CONV_STATS, FVT_CONV_W_OHWI, check
+from ._lib import ConvDesc, ConvExt, FVT_CONV_RELU, FVT_CONV_RESIDUAL, FVT_CONV_STATS, FVT_CONV_W_OHWI, FVT_CONV_BN_BWD, check
 
 
 def pad16(c):
@@ -501,8 +501,8 @@ def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None, r
                 dz_in=False):
     """mask: tensor whose sign gates the gradient (ReLU after a residual add), or None; relu_scale/relu_shift: the
     forward scale/shift of this BatchNorm when the ReLU follows it directly (mask recomputed from raw).
-    dz_in=True: `dact` already is dz and `sums_acc` already holds [sum dz*(raw-mean), sum dz] (produced by the data
-    gradient convolution's epilogue): only the apply pass runs."""
+    dz_in=2: `dact` already is dz and `sums_acc` already holds [sum dz*raw, sum dz] — written by the data-gradient
+    convolution's epilogue (FVT_CONV_BN_BWD) — so only the apply pass runs (dz_in=1: the same with sum dz*(raw-mean))."""
     lib = _lib.load()
     c = raw.shape[-1]
     rows = raw.numel() // c
@@ -511,7 +511,7 @@ def bn_backward(raw, dact, mask, mean, invstd, gamma, sums, draw, dz_out=None, r
         sums_acc = _bn_acc(c, raw.device)
     check(lib.fvt_bn_backward(_h(raw), _ptr(raw), _ptr(dact), _ptr(mask), _ptr(mean), _ptr(invstd), _ptr(gamma),
                               _ptr(relu_scale), _ptr(relu_shift), _ptr(sums), _ptr(sums_acc), _ptr(draw), _ptr(dz_out), rows, c,
-                              gamma.numel(), int(dz_in), _stream()))
+                              gamma.numel(), int(dz_in), _stream()))        # dz_in: 0 two passes, 1 / 2 apply only (see the header)
     return draw
 
 

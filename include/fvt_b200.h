@@ -47,6 +47,13 @@ typedef struct fvt_handle_s* fvt_handle_t;
 #define FVT_CONV_RELU 1      /* y = max(y, 0)                       (Activation 'relu', R2Plus1.py:33,60,81)   */
 #define FVT_CONV_RESIDUAL 2  /* y += residual before the ReLU       (nd.relu(y+x), R2Plus1.py:81; net.py:100)   */
 #define FVT_CONV_STATS 4     /* accumulate per-channel sum, sum^2 of the raw conv output (training BatchNorm) */
+#define FVT_CONV_BN_BWD 16   /* fvt_conv3d_fwd as a DATA GRADIENT fused with the first pass of the BatchNorm backward it feeds.  The
+                              * convolution's output is dact = d(loss)/d(act) of a layer with act = relu(raw*scale + shift);
+                              * with this flag (plus FVT_CONV_STATS | FVT_CONV_RESIDUAL) `residual` is that layer's RAW conv
+                              * output and scale/shift its forward BatchNorm constants: the epilogue stores
+                              * dz = dact * [raw*scale + shift > 0] instead of dact and accumulates stats_acc =
+                              * [sum dz*raw (cout), sum dz (cout)] of the stored values.  fvt_bn_backward(dz_in = 2) finishes
+                              * the BatchNorm backward with one pass instead of two.                                     */
 #define FVT_CONV_W_OHWI 8    /* fvt_pack_conv_weight[_dgrad] / fvt_conv3d_wgrad only: the fp32 weight (gradient) tensor is
                               * laid out (O, kT, kH, kW, I) instead of the reference's (O, I, kT, kH, kW).  With input
                               * channels innermost a warp of the weight-gradient epilogue adds 32 consecutive floats
@@ -275,8 +282,10 @@ int fvt_bn_finalize_apply(fvt_handle_t handle, const void* stats_acc, const floa
  * sums = [dgamma(c_store), dbeta(c_store)] (overwritten);  sums_acc: scratch of fvt_stats_bytes(c_store) bytes (the exact
  * accumulators behind `sums`; zeroed inside, contents irrelevant on entry);
  * draw = gamma*inv_std*(dz - dbeta/rows - xhat*dgamma/rows);  dz_out (optional) receives dz.
- * dz_in != 0: `dact` already IS dz and sums_acc already holds [sum dz*(raw-mean), sum dz] — both produced by the data
- * gradient convolution that wrote dact (fvt_conv3d_dgrad_bn) — so only the apply pass runs. */
+ * dz_in = 2: `dact` already IS dz and sums_acc already holds [sum dz*raw, sum dz] — both produced by the data gradient
+ * convolution that wrote dact (fvt_conv3d_fwd with FVT_CONV_BN_BWD) — so only the apply pass runs
+ * (dgamma = inv_std*(sum dz*raw - mean*sum dz), formed in double from the exact sums).  dz_in = 1: the same with
+ * sums_acc = [sum dz*(raw-mean), sum dz]. */
 int fvt_bn_backward(fvt_handle_t handle, const void* raw, const void* dact, const void* mask, const float* mean,
                     const float* invstd, const float* gamma, const float* relu_scale, const float* relu_shift, float* sums,
                     void* sums_acc, void* draw, void* dz_out, int64_t rows, int32_t c_store, int32_t c_real, int32_t dz_in,

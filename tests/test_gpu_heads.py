@@ -93,9 +93,11 @@ def test_eco_lite_3d_head_matches_torch_restatement(cuda_device, n, t):
     assert abs(ECOLite3DHead.conv_gflop_per_clip(16, 28) - 83.24) < 0.01
 
 
-def _ref_group(x, w, b, gamma, beta, res, stride, pad, relu, eps=1e-5):
+def _ref_group(x, w, b, gamma, beta, res, stride, pad, relu, eps=1e-5, relu_mask=None):
     """torch-CPU fp32 restatement of Conv3D (+bias) -> BatchNorm(batch statistics, biased variance) (+ residual) (-> ReLU)
-    on bf16-rounded operands, with the raw conv output rounded to bf16 as the kernels store it (straight-through)."""
+    on bf16-rounded operands, with the raw conv output rounded to bf16 as the kernels store it (straight-through).
+    relu_mask (teacher forcing): the ReLU passes exactly the positions the kernel's output passed — a pre-activation within
+    rounding of zero may fall on either side, which changes the output by nothing but single gradient entries by O(|x||dy|)."""
     import torch.nn.functional as F
     raw = F.conv3d(x, w, None, stride=stride, padding=pad)
     raw = raw + (raw.to(torch.bfloat16).float() - raw).detach()
@@ -106,6 +108,8 @@ def _ref_group(x, w, b, gamma, beta, res, stride, pad, relu, eps=1e-5):
     y = (raw - mean) / torch.sqrt(var + eps) * gamma.reshape(1, -1, 1, 1, 1) + beta.reshape(1, -1, 1, 1, 1)
     if res is not None:
         y = y + res
+    if relu and relu_mask is not None:
+        return y * relu_mask
     return torch.relu(y) if relu else y
 
 
@@ -146,8 +150,12 @@ def test_training_mode_conv_bn_group_matches_torch_autograd(cuda_device, case):
     br = conv.bias.detach().cpu().clone().requires_grad_(True) if use_bias else None
     gr, btr = bn.gamma.detach().cpu().clone().requires_grad_(True), bn.beta.detach().cpu().clone().requires_grad_(True)
     rr = res.clone().requires_grad_(True) if with_res else None
-    ref = _ref_group(xr, wr, br, gr, btr, rr, s, p, relu)
+    kmask = (to_ncdhw(out.detach(), cout).cpu() > 0).float() if relu else None
+    ref = _ref_group(xr, wr, br, gr, btr, rr, s, p, relu, relu_mask=kmask)
     ref.backward(dout)
+    with torch.no_grad():          # the forced mask differs from the reference's own ReLU only where the pre-activation is ~0
+        ref_free = _ref_group(xr, wr, br, gr, btr, rr, s, p, relu)
+        assert (ref_free - ref).abs().max().item() <= 1e-2 * ref_free.abs().max().item()
 
     def close(what, got, want, tol=1e-2):
         scale = want.abs().max().item()

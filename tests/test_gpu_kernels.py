@@ -699,6 +699,84 @@ def test_strided_dgrad_parity_classes_match_zero_insert_and_autograd(cuda_device
     # reference 2: the zero-insert route of round 1
     dd = ops.dgrad_desc(fwd)
     wpd = ops.pack_conv_weight_dgrad(dd, wm, ohwi=True)
-    old = ops.conv3d_fwd(dd, ops.zero_insert(dy, fwd), wpd)
-    torch.cuda.synchronize()
-    assert (got.float() - old.float()).abs().max().item() <= 2 ** -7 * scale
+    if all(2 * pp == kk - 1 for pp, kk in zip(p, k)):      # the zero-insert route only exists for 'same'-padded filters
+        old = ops.conv3d_fwd(dd, ops.zero_insert(dy, fwd), wpd)
+        torch.cuda.synchronize()
+        assert (got.float() - old.float()).abs().max().item() <= 2 ** -7 * scale
+
+
+@pytest.mark.parametrize("case", [
+    ("conv2_x temporal dgrad 64->144 (K1i)", 2, 8, 56, 56, 144, 64, (3, 1, 1), (1, 0, 0)),
+    ("conv2_x spatial dgrad 144->64 (K1s2)", 2, 8, 56, 56, 64, 144, (1, 3, 3), (0, 1, 1)),
+    ("conv3_x spatial dgrad 288->128", 2, 4, 28, 28, 128, 288, (1, 3, 3), (0, 1, 1)),
+    ("conv3_x temporal dgrad 128->288 (pair)", 4, 16, 28, 28, 288, 128, (3, 1, 1), (1, 0, 0)),
+    ("conv4_x spatial dgrad 576->256 (K1)", 2, 4, 14, 14, 256, 576, (1, 3, 3), (0, 1, 1)),
+    ("conv5_x temporal dgrad 512->1152 (K1, narrow N)", 2, 2, 7, 7, 1152, 512, (3, 1, 1), (1, 0, 0)),
+    ("stem temporal dgrad 64->45 (K1t)", 2, 8, 56, 56, 45, 64, (3, 1, 1), (1, 0, 0)),
+])
+def test_fused_dgrad_bn_backward_matches_the_two_pass_form(cuda_device, lib, case):
+    """FVT_CONV_BN_BWD: the data-gradient convolution masks with the consumer BatchNorm's ReLU and accumulates its backward
+    sums in the epilogue; fvt_bn_backward(dz_in=2) then needs one pass.  Against the unfused sequence (dgrad -> two-pass
+    BatchNorm backward) on the same inputs: dz bit-identical, dgamma/dbeta to fp32 summation order, d(raw) to one bf16
+    rounding; twice the same bits.  One case per kernel the training plan dispatches data gradients to."""
+    import torch
+    from fastvideotagging_b200 import ops
+    name, n, t, h, w, cin, cout, k, p = case        # forward conv cin -> cout; its data gradient maps cout -> cin
+    gen = torch.Generator().manual_seed(cin + 3 * cout)
+    cin_s, cout_s = ops.pad16(cin), ops.pad16(cout)
+    fwd = ops.conv_desc(n, t, h, w, cin_s, cout_s, k, (1, 1, 1), p)
+    dd = ops.dgrad_desc(fwd)
+    wm = (torch.randn(cout, k[0], k[1], k[2], cin, generator=gen) / (cout * k[0] * k[1] * k[2]) ** 0.5).to(cuda_device)
+    wpd = ops.pack_conv_weight_dgrad(dd, wm, ohwi=True)
+    dy = torch.zeros(n, t, h, w, cout_s)
+    dy[..., :cout] = torch.randn(n, t, h, w, cout, generator=gen)
+    dy = dy.to(torch.bfloat16).to(cuda_device)
+    # the consumer BatchNorm (of the layer that produced this conv's input): raw, batch statistics, forward constants
+    raw = torch.zeros(n, t, h, w, cin_s)
+    raw[..., :cin] = torch.randn(n, t, h, w, cin, generator=gen) * 1.3 + 0.2
+    raw = raw.to(torch.bfloat16).to(cuda_device)
+    rows = n * t * h * w
+    rf = raw.float().reshape(rows, cin_s)
+    gamma = (0.5 + torch.rand(cin, generator=gen)).to(cuda_device)
+    beta = (0.3 * torch.randn(cin, generator=gen)).to(cuda_device)
+    mean = torch.zeros(cin_s, device=cuda_device)
+    invstd = torch.zeros(cin_s, device=cuda_device)
+    mean[:cin] = rf[:, :cin].mean(0)
+    invstd[:cin] = 1.0 / torch.sqrt(rf[:, :cin].var(0, unbiased=False) + 1e-5)
+    scale = torch.zeros(cin_s, device=cuda_device)
+    shift = torch.zeros(cin_s, device=cuda_device)
+    scale[:cin] = gamma * invstd[:cin]
+    shift[:cin] = beta - mean[:cin] * scale[:cin]
+    # ---- unfused: dgrad, then the two-pass BatchNorm backward with the mask recomputed from raw
+    assert ops.set_option("disable_split_k", 1) == 0      # the fused form never splits K: same summation order on both sides
+    try:
+        dact = ops.conv3d_fwd(dd, dy, wpd)
+    finally:
+        ops.set_option("disable_split_k", 0)
+    sums_a = torch.empty(2 * cin_s, device=cuda_device)
+    draw_a = torch.empty_like(raw)
+    dz_a = torch.empty_like(raw)
+    ops.bn_backward(raw, dact, None, mean, invstd, gamma, sums_a, draw_a, relu_scale=scale, relu_shift=shift)
+    pre = rf * scale + shift
+    dz_ref = torch.where(pre > 0, dact.float().reshape(rows, cin_s), torch.zeros_like(pre)).to(torch.bfloat16)
+    # ---- fused
+    def fused():
+        d2 = ops.ConvDesc(*dd.key())
+        d2.flags = ops.FVT_CONV_STATS | ops.FVT_CONV_BN_BWD | ops.FVT_CONV_RESIDUAL
+        acc = ops.stats_buffer(cin_s, cuda_device)
+        dz = ops.conv3d_fwd(d2, dy, wpd, scale=scale, shift=shift, residual=raw, stats=acc)
+        sums = torch.empty(2 * cin_s, device=cuda_device)
+        draw = torch.empty_like(raw)
+        ops.bn_backward(raw, dz, None, mean, invstd, gamma, sums, draw, sums_acc=acc, dz_in=2)
+        torch.cuda.synchronize()
+        return dz, sums, draw
+    dz_b, sums_b, draw_b = fused()
+    dz_c, sums_c, draw_c = fused()
+    assert torch.equal(dz_b, dz_c) and torch.equal(sums_b, sums_c) and torch.equal(draw_b, draw_c), name
+    assert torch.equal(dz_b.reshape(rows, cin_s).view(torch.int16), dz_ref.view(torch.int16)), name
+    sg, sb = sums_a[:cin].abs().max().item(), sums_a[cin_s:cin_s + cin].abs().max().item()
+    assert (sums_b[:cin] - sums_a[:cin]).abs().max().item() <= 1e-3 * sg + 1e-4, name
+    assert (sums_b[cin_s:cin_s + cin] - sums_a[cin_s:cin_s + cin]).abs().max().item() <= 1e-4 * sb + 1e-5, name
+    scale_d = draw_a.float().abs().max().item()
+    assert (draw_b.float() - draw_a.float()).abs().max().item() <= 2 ** -6 * scale_d, name
+    assert float(draw_b[..., cin:].float().abs().max()) == 0.0 if cin_s > cin else True
