@@ -91,6 +91,10 @@ def load():
         "fvt_pack_entry_blocks": (ctypes.c_uint32, [i32, i32, i32, i32]),
         "fvt_pack_conv_weights_multi": (ctypes.c_int, [hp, vp, i32, ctypes.c_uint32, vp]),
         "fvt_conv3d_wgrad": (ctypes.c_int, [hp, dp, vp, vp, fp, i32, i32, vp, ctypes.c_size_t, vp]),
+        "fvt_conv3d_wgrad_group_plan": (ctypes.c_int, [hp, i32, dp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ip, ip,
+                                                       vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                                                       ctypes.POINTER(ctypes.c_size_t), ip]),
+        "fvt_conv3d_wgrad_group_run": (ctypes.c_int, [hp, vp, vp, vp]),
         "fvt_zero_insert": (ctypes.c_int, [hp, vp, vp] + [i32] * 11 + [vp]),
         "fvt_bn_fold_multi": (ctypes.c_int, [hp, vp, i32, vp]),
         "fvt_bn_finalize": (ctypes.c_int, [hp, vp, fp, fp, fp, fp, i32, i32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,

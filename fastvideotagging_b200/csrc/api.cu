@@ -8,6 +8,8 @@
 #include <mutex>
 #include <new>
 #include <unordered_map>
+#include <vector>
+#include <algorithm>
 
 #include "../../include/fvt_b200.h"
 #include "conv_igemm.cuh"
@@ -76,6 +78,8 @@ static std::mutex g_mu;
   X(slab_epi_warps, 8)        /* 8|16 epilogue warps of the slab kernel.  16 measured SLOWER (conv2_x 1x3x3 at batch 48:         \
                                  756 -> 996 us): the stores are request-throughput-bound, not latency-bound */                   \
   X(wgrad_no_store, 0)        /* experiments only: the weight-gradient epilogue reads TMEM and stores nothing */                 \
+  X(wgrad_no_flat, 0)         /* 1: temporal weight gradients tile every frame on its own (round-1 tiling) instead of the        \
+                                 flattened T*H*W positions of a clip */                                                          \
   X(unit_input_stationary, 1) /* fused (2+1)D unit: temporal conv as one N = 192 MMA chain per mid frame                         \
                                  (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame */                     \
   X(igemm_pair, 1)            /* 0|1|2: generic im2col convolution on CTA pairs (K1p) for the wide streamed-weight layers */     \
@@ -408,6 +412,31 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long l
   }
 }
 
+// Small dW, many splits (1x1x1 shortcuts, the stem: a few thousand weights cut into up to 296 pixel splits): one thread
+// per element would walk all slices serially (measured 26-64 us for 8-32 blocks).  Here 8 threads share an element:
+// thread j adds the slices k = j, j+8, ... and the eight partial sums are combined in lane order through shared memory
+// (fixed order: deterministic).  blockDim = (32 elements, 8 split lanes).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_wide_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long elems, int splits) {
+  __shared__ float part[8][33];
+  const int ex = threadIdx.x & 31, j = threadIdx.x >> 5;
+  for (long long base = static_cast<long long>(blockIdx.x) * 32; base < elems; base += static_cast<long long>(gridDim.x) * 32) {
+    const long long i = base + ex;
+    float a = 0.f;
+    if (i < elems)
+      for (int k = j; k < splits; k += 8) a += __ldg(ws + k * elems + i);
+    part[j][ex] = a;
+    __syncthreads();
+    if (j == 0 && i < elems) {
+      float r = part[0][ex];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) r += part[q][ex];
+      dw[i] = r;
+    }
+    __syncthreads();
+  }
+}
+
 // Largest number of pixel splits (<= wanted) whose dW-shaped slices fit the caller's workspace; 1 = no workspace needed.
 static int wgrad_fit_splits(int wanted, long long elems, const void* ws, size_t ws_bytes) {
   if (wanted < 2) return 1;
@@ -419,6 +448,12 @@ static int wgrad_fit_splits(int wanted, long long elems, const void* ws, size_t 
 }
 
 static int wgrad_reduce(const float* ws, float* dw, long long elems, int splits, cudaStream_t stream) {
+  if (splits >= 16 && elems <= 148ll * 256 * 4) {        // few elements, many slices: spread the slices over threads too
+    int blocks = (int)((elems + 31) / 32);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_wide_kernel<<<blocks, 256, 0, stream>>>(ws, dw, elems, splits);
+    return check_launch("wgrad_reduce_wide_kernel");
+  }
   const int vec4 = ((elems & 3) == 0 && (((uintptr_t)dw) & 15) == 0) ? 1 : 0;
   long long work = vec4 ? elems >> 2 : elems;
   int blocks = (int)((work + 255) / 256);
@@ -428,22 +463,68 @@ static int wgrad_reduce(const float* ws, float* dw, long long elems, int splits,
   return check_launch("wgrad_reduce_kernel");
 }
 
-// ------------------------------------------------------------------------------------------------ K3s temporal launch
-// kt x 1 x 1 stride-1 convs: same kernel, temporal mode (see WgradSlabParams).  Returns 1 / 0 / < 0 like try_wgrad_slab.
-static int try_wgrad_temporal(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
-                              int cout_real, int cin_real, void* ws, size_t ws_bytes, cudaStream_t stream, size_t* plan_bytes = nullptr) {
+// ------------------------------------------------------------------------------------------------ K3s planning
+// A plan = the kernel parameters of one layer (tile shape, pipeline, work items) without pointers.  Two cost models:
+//   stand-alone (grouped = false): the layer must fill the machine alone -> (M tiles per CTA, N tile, pixel splits) minimise
+//     the estimated time of the slowest CTA plus, with several splits, the slice reduction;
+//   grouped (grouped = true): the machine is filled by the items of all layers of the group -> the tile shape minimises the
+//     layer's total SM time (items x time per item, i.e. the operand traffic it re-reads); pixel splits are chosen by the
+//     group planner afterwards (wgs_set_splits).
+struct WgsPlan {
+  WgradSlabParams p;
+  int items;                // (M chunk, N tile) work items per pixel split
+  int splits_wanted;        // stand-alone model's choice
+  long long dw_elems;
+  double item_clk;          // estimated clocks of one item over the whole pixel range (splits = 1), without the fixed part
+  double fixed_clk;         // per-CTA prologue + epilogue estimate
+};
+
+constexpr double kWgsFeedAlone = 64.0;     // bytes / clk one SM can pull into shared memory when the planner sizes a lone launch
+constexpr double kWgsFeedGroup = 44.0;     // ... when all SMs pull at once (the L2 delivers ~6300 B/clk chip-wide)
+
+static void wgs_finish_common(WgsPlan* pl, const fvt_conv_desc* d, const Options& o, int cout_real, int cin_real) {
+  WgradSlabParams& p = pl->p;
+  p.cin_real = cin_real; p.cout_real = cout_real;
+  p.dbg_no_store = o.wgrad_no_store; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
+  pl->dw_elems = (long long)cout_real * cin_real * p.taps;
+  p.ws_split_stride = pl->dw_elems;
+  pl->items = p.m_chunks * p.n_tiles;
+}
+
+// Pixel splits actually used (<= wanted, limited by the tile count); ws = this layer's slice area or nullptr.
+static void wgs_set_splits(WgsPlan* pl, int splits, float* dw, float* ws) {
+  WgradSlabParams& p = pl->p;
+  if (splits < 1) splits = 1;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
+  p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.dw = dw;
+  p.ws = p.splits > 1 ? ws : nullptr;
+}
+
+// kt x 1 x 1 stride-1 convs: temporal mode (see WgradSlabParams).  Returns 1 eligible / 0 not.
+static int wgs_plan_temporal(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, int cout_real, int cin_real, bool grouped,
+                             WgsPlan* pl) {
   if (o.disable_wgrad_slab) return 0;
   if (!(d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 && d->ph == 0 &&
         d->pw == 0 && 2 * d->pt == d->kt - 1))
     return 0;
   const int hw = d->h * d->w;
-  if (hw < 96) return 0;                                   // a 128-position tile would be mostly padding
-  WgradSlabParams p;
+  // tiles of 128 consecutive positions of a clip (flattened T*H*W) unless frames already are whole tiles
+  const bool flat = (hw % 128) != 0 && !o.wgrad_no_flat;
+  if (!flat && hw < 96) return 0;
+  if (flat && (long long)d->t * hw < 96) return 0;
+  WgradSlabParams& p = pl->p;
   memset(&p, 0, sizeof(p));
   p.temporal = 1;
-  p.hw = hw; p.t_frames = d->t; p.kt = d->kt; p.pt = d->pt;
-  p.blocks_per_frame = (hw + 127) / 128;
-  p.num_tiles = d->n * d->t * p.blocks_per_frame;
+  p.kt = d->kt; p.pt = d->pt;
+  if (flat) {
+    p.hw = d->t * hw; p.t_frames = 1; p.tap_frames = 0; p.tap_pos = hw;
+  } else {
+    p.hw = hw; p.t_frames = d->t; p.tap_frames = 1; p.tap_pos = 0;
+  }
+  p.blocks_per_frame = (p.hw + 127) / 128;
+  p.num_tiles = d->n * p.t_frames * p.blocks_per_frame;
   p.tiles_per_frame = 1; p.r_out = 1;                      // unused by the temporal producer
   p.ksteps = 8;
   p.taps = d->kt; p.kw = 1; p.kh = 1; p.wp = 0;
@@ -453,95 +534,75 @@ static int try_wgrad_temporal(const DeviceInfo* di, const Options& o, const fvt_
   p.slab_tx_bytes = 128 * 128;
   p.dy_tx_bytes = 128 * 128;
   const int kSmemMax = 227 * 1024, kAux = 1024;
-  // N tile: whole Cout when it fits 256 columns, else equal parts; M tiles per CTA limited by 512 TMEM columns and by two
-  // pipeline stages in shared memory.  (M tiles per CTA, pixel splits) minimise the estimated time of the slowest CTA plus,
-  // with several splits, the slice reduction (one more launch and (splits + 1) dW-sized passes).
-  int nt = (d->cout + 255) / 256;
-  int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
-  int acc_stride = (n_tile + 31) / 32 * 32;
-  int mt_max = 512 / acc_stride;
-  if (mt_max > kWgsMaxMt) mt_max = kWgsMaxMt;
   const int mt_total = (p.cin_blocks + 1) / 2;
-  if (mt_max > mt_total) mt_max = mt_total;
-  while (mt_max > 1 && 2 * ((2 * mt_max) * p.slab_slot_bytes + ((n_tile + 63) / 64) * 128 * 128) + kAux > kSmemMax) --mt_max;
   const long long dw_elems = (long long)cout_real * cin_real * p.taps;
   double best = 1e30;
-  int mt = mt_max, splits = 1;
-  for (int m = 1; m <= mt_max; ++m) {
-    const int chunks = (mt_total + m - 1) / m * d->kt;
-    const int items_m = chunks * nt;
-    int max_splits = di->sm_count / items_m;
-    if (max_splits < 1) max_splits = 1;
-    if (max_splits > p.num_tiles) max_splits = p.num_tiles;
-    const int ncb = 2 * m < p.cin_blocks ? 2 * m : p.cin_blocks;
-    const double mma_clk = (double)m * p.ksteps * (n_tile > 128 ? n_tile / 2.0 : 64.0);
-    const double bytes = (double)(ncb + (n_tile + 63) / 64) * 128.0 * 128.0;
-    const double per_tile = mma_clk > bytes / 64.0 ? mma_clk : bytes / 64.0;
-    const double epi = (double)m * n_tile * 12.0;
-    for (int pass = 0; pass < 2; ++pass) {
-      const int sp = pass == 0 ? 1 : max_splits;
-      if (pass == 1 && max_splits == 1) break;
-      const int tps = (p.num_tiles + sp - 1) / sp;
-      const int waves = (items_m * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
-      double est = waves * (tps * per_tile + 3000.0 + epi);
-      if (sp > 1) est += 9000.0 + (double)(sp + 1) * (double)dw_elems * 4.0 / 2500.0;
-      if (est < best) { best = est; mt = m; splits = sp; }
+  int best_nt = 0, best_mt = 0, best_splits = 1;
+  double best_item = 0, best_fixed = 0;
+  for (int nt = (d->cout + 255) / 256; nt <= (grouped ? 4 : (d->cout + 255) / 256); ++nt) {
+    const int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
+    if (nt > 1 && n_tile * (nt - 1) >= d->cout) continue;
+    const int acc_stride = (n_tile + 31) / 32 * 32;
+    const int n_blocks = (n_tile + 63) / 64;
+    int mt_max = 512 / acc_stride;
+    if (mt_max > kWgsMaxMt) mt_max = kWgsMaxMt;
+    if (mt_max > mt_total) mt_max = mt_total;
+    for (int m = 1; m <= mt_max; ++m) {
+      const int ncb = 2 * m < p.cin_blocks ? 2 * m : p.cin_blocks;
+      if (2 * (ncb * p.slab_slot_bytes + n_blocks * 128 * 128) + kAux > kSmemMax) continue;
+      const int chunks = (mt_total + m - 1) / m * d->kt;
+      const int items_m = chunks * nt;
+      const double mma_clk = (double)m * p.ksteps * (n_tile > 128 ? n_tile / 2.0 : 64.0);
+      const double bytes = (double)(ncb + n_blocks) * 128.0 * 128.0;
+      const double feed = grouped ? kWgsFeedGroup : kWgsFeedAlone;
+      const double per_tile = mma_clk > bytes / feed ? mma_clk : bytes / feed;
+      const double epi = (double)m * n_tile * 12.0;
+      if (grouped) {
+        const double est = items_m * (p.num_tiles * per_tile + 3000.0 + epi);
+        if (est < best) { best = est; best_nt = nt; best_mt = m; best_splits = 1; best_item = p.num_tiles * per_tile; best_fixed = 3000.0 + epi; }
+        continue;
+      }
+      int max_splits = di->sm_count / items_m;
+      if (max_splits < 1) max_splits = 1;
+      if (max_splits > p.num_tiles) max_splits = p.num_tiles;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int sp = pass == 0 ? 1 : max_splits;
+        if (pass == 1 && max_splits == 1) break;
+        const int tps = (p.num_tiles + sp - 1) / sp;
+        const int waves = (items_m * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
+        double est = waves * (tps * per_tile + 3000.0 + epi);
+        if (sp > 1) est += 9000.0 + (double)(sp + 1) * (double)dw_elems * 4.0 / 2500.0;
+        if (est < best) { best = est; best_nt = nt; best_mt = m; best_splits = sp; best_item = p.num_tiles * per_tile; best_fixed = 3000.0 + epi; }
+      }
     }
   }
-  p.n_tiles = nt; p.n_tile = n_tile; p.acc_stride = acc_stride; p.n_blocks = (n_tile + 63) / 64;
-  p.mt_per_cta = mt;
-  p.chunks_per_tap = (mt_total + mt - 1) / mt;
+  if (best_nt == 0) return 0;
+  p.n_tiles = best_nt;
+  p.n_tile = ((d->cout + best_nt - 1) / best_nt + 15) / 16 * 16;
+  p.acc_stride = (p.n_tile + 31) / 32 * 32;
+  p.n_blocks = (p.n_tile + 63) / 64;
+  p.mt_per_cta = best_mt;
+  p.chunks_per_tap = (mt_total + best_mt - 1) / best_mt;
   p.m_chunks = p.chunks_per_tap * d->kt;
-  p.ncb_max = 2 * mt < p.cin_blocks ? 2 * mt : p.cin_blocks;
+  p.ncb_max = 2 * best_mt < p.cin_blocks ? 2 * best_mt : p.cin_blocks;
   p.stage_bytes = p.ncb_max * p.slab_slot_bytes + p.n_blocks * 128 * 128;
   p.stages = (kSmemMax - kAux) / p.stage_bytes;
   if (p.stages < 2) return 0;
   if (p.stages > kWgsMaxStages) p.stages = kWgsMaxStages;
-  const int items = p.m_chunks * p.n_tiles;
-  if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)dw_elems * sizeof(float) : 0; return 1; }
-  splits = wgrad_fit_splits(splits, dw_elems, ws, ws_bytes);
-  p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
-  p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw; p.dbg_no_store = o.wgrad_no_store; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
-  p.ws = p.splits > 1 ? (float*)ws : nullptr; p.ws_split_stride = dw_elems;
-
-  CUtensorMap tmx, tmdy;
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const cuuint32_t box[4] = {64, 128, 1, 1};
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)hw, (cuuint64_t)d->t, (cuuint64_t)d->n};
-    const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * hw, (cuuint64_t)d->cin * 2 * hw * d->t};
-    CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad temporal x) failed (CUresult %d)", (int)r);
-  }
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)hw, (cuuint64_t)d->t, (cuuint64_t)d->n};
-    const cuuint64_t strides[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * hw, (cuuint64_t)d->cout * 2 * hw * d->t};
-    CUresult r = di->encode_tiled(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad temporal dy) failed (CUresult %d)", (int)r);
-  }
-  const int smem_bytes = p.stages * p.stage_bytes + kAux;
-  conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
-  if (int e = check_launch("conv_wgrad_slab_kernel(temporal)")) return e;
-  if (p.splits > 1 && !o.wgrad_no_store)
-    if (int e = wgrad_reduce(p.ws, dw, dw_elems, p.splits, stream)) return e;
+  pl->splits_wanted = best_splits;
+  pl->item_clk = best_item; pl->fixed_clk = best_fixed;
+  wgs_finish_common(pl, d, o, cout_real, cin_real);
   return 1;
 }
 
-// ------------------------------------------------------------------------------------------------ K3s launch
-// Returns 1 when the slab weight-gradient kernel took the call, 0 when the shape is not eligible, < 0 on error.
-static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
-                          int cout_real, int cin_real, void* ws, size_t ws_bytes, cudaStream_t stream, size_t* plan_bytes = nullptr) {
+// stride-1 'same' 1 x kh x kw convs.  Returns 1 eligible / 0 not.
+static int wgs_plan_spatial(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, int cout_real, int cin_real, bool grouped,
+                            WgsPlan* pl) {
   if (o.disable_wgrad_slab) return 0;
   if (!(d->kt == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && (d->kh > 1 || d->kw > 1) &&
         2 * d->ph == d->kh - 1 && 2 * d->pw == d->kw - 1 && d->cin % 64 == 0 && d->w + 2 * d->pw <= 128))
     return 0;
-  WgradSlabParams p;
+  WgradSlabParams& p = pl->p;
   memset(&p, 0, sizeof(p));
   p.frames = d->n * d->t; p.h = d->h; p.w = d->w; p.wp = d->w + 2 * d->pw;
   p.ph = d->ph; p.pw = d->pw; p.kh = d->kh; p.kw = d->kw;
@@ -564,9 +625,9 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
   const int kSmemMax = 227 * 1024, kAux = 1024;
   const int mt_total = (p.groups + 1) / 2;
 
-  // ---- pick (N tile, M tiles per CTA): minimise the estimated time of the slowest CTA
   double best = 1e30;
   int best_nt = 0, best_mt = 0, best_splits = 1;
+  double best_item = 0, best_fixed = 0;
   const long long dw_elems_est = (long long)cout_real * cin_real * p.taps;
   for (int nt = 1; nt <= 8; ++nt) {
     const int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
@@ -588,13 +649,19 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
       const int stage_bytes = ncb_max * p.slab_slot_bytes + n_blocks * 128 * 128;
       if (2 * stage_bytes + kAux > kSmemMax) continue;
       const int items = m_chunks * nt;
+      const double mma_clk = (double)mt * p.ksteps * (n_tile > 128 ? n_tile / 2.0 : 64.0);     // a UMMA costs max(64, N/2) clk
+      const double bytes = (double)ncb_max * p.slab_tx_bytes + (double)p.dy_tx_bytes * n_blocks;
+      const double feed = grouped ? kWgsFeedGroup : kWgsFeedAlone;
+      const double per_tile = mma_clk > bytes / feed ? mma_clk : bytes / feed;
+      const double epi = (double)mt * n_tile * 12.0;            // plain stores of one accumulator block
+      if (grouped) {
+        const double est = items * (p.num_tiles * per_tile + 3000.0 + epi);
+        if (est < best) { best = est; best_nt = nt; best_mt = mt; best_splits = 1; best_item = p.num_tiles * per_tile; best_fixed = 3000.0 + epi; }
+        continue;
+      }
       int max_splits = di->sm_count / items;
       if (max_splits < 1) max_splits = 1;
       if (max_splits > p.num_tiles) max_splits = p.num_tiles;
-      const double mma_clk = (double)mt * p.ksteps * (n_tile > 128 ? n_tile / 2.0 : 64.0);     // a UMMA costs max(64, N/2) clk
-      const double bytes = (double)ncb_max * p.slab_tx_bytes + (double)p.dy_tx_bytes * n_tile / 64.0;
-      const double per_tile = mma_clk > bytes / 64.0 ? mma_clk : bytes / 64.0;
-      const double epi = (double)mt * n_tile * 12.0;            // plain stores of one accumulator block
       // one pixel split per dW tile stores straight into dW; several splits pay one more launch (~5 us) and
       // (splits + 1) dW-sized passes through L2/HBM for the slice reduction
       for (int pass = 0; pass < 2; ++pass) {
@@ -604,7 +671,7 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
         const int waves = (items * ((p.num_tiles + tps - 1) / tps) + di->sm_count - 1) / di->sm_count;
         double est = waves * (tps * per_tile + 3000.0 + epi);
         if (splits > 1) est += 9000.0 + (double)(splits + 1) * (double)dw_elems_est * 4.0 / 2500.0;
-        if (est < best) { best = est; best_nt = nt; best_mt = mt; best_splits = splits; }
+        if (est < best) { best = est; best_nt = nt; best_mt = mt; best_splits = splits; best_item = p.num_tiles * per_tile; best_fixed = 3000.0 + epi; }
       }
     }
   }
@@ -625,24 +692,48 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
   p.stage_bytes = p.ncb_max * p.slab_slot_bytes + p.n_blocks * 128 * 128;
   p.stages = (kSmemMax - kAux) / p.stage_bytes;
   if (p.stages > kWgsMaxStages) p.stages = kWgsMaxStages;
-  const int items = p.m_chunks * p.n_tiles;
-  int splits = best_splits;
-  const long long dw_elems = (long long)cout_real * cin_real * p.taps;
-  if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)dw_elems * sizeof(float) : 0; return 1; }
-  splits = wgrad_fit_splits(splits, dw_elems, ws, ws_bytes);
-  p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
-  p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.cin_real = cin_real; p.cout_real = cout_real;
-  p.dw = dw; p.dbg_no_store = o.wgrad_no_store; p.w_ohwi = (d->flags & FVT_CONV_W_OHWI) ? 1 : 0;
-  p.ws = p.splits > 1 ? (float*)ws : nullptr; p.ws_split_stride = dw_elems;
+  pl->splits_wanted = best_splits;
+  pl->item_clk = best_item; pl->fixed_clk = best_fixed;
+  wgs_finish_common(pl, d, o, cout_real, cin_real);
+  return 1;
+}
 
-  CUtensorMap tmx, tmdy;
+static int wgs_plan(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, int cout_real, int cin_real, bool grouped, WgsPlan* pl) {
+  int r = wgs_plan_spatial(di, o, d, cout_real, cin_real, grouped, pl);
+  if (r == 0) r = wgs_plan_temporal(di, o, d, cout_real, cin_real, grouped, pl);
+  return r;
+}
+
+// Tensor maps of a planned layer (X and dY in the tiling the plan's mode expects).
+static int wgs_encode_maps(const DeviceInfo* di, const fvt_conv_desc* d, const WgradSlabParams& p, const void* x, const void* dy,
+                           CUtensorMap* tmx, CUtensorMap* tmdy) {
   const cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (p.temporal) {
+    const cuuint32_t box[4] = {64, 128, 1, 1};
+    const cuuint64_t hw = (cuuint64_t)p.hw, tf = (cuuint64_t)p.t_frames;
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)d->cin, hw, tf, (cuuint64_t)d->n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * hw, (cuuint64_t)d->cin * 2 * hw * tf};
+      CUresult r = di->encode_tiled(tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad temporal x) failed (CUresult %d)", (int)r);
+    }
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)d->cout, hw, tf, (cuuint64_t)d->n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * hw, (cuuint64_t)d->cout * 2 * hw * tf};
+      CUresult r = di->encode_tiled(tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad temporal dy) failed (CUresult %d)", (int)r);
+    }
+    return 0;
+  }
   {
     const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)p.frames};
     const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w, (cuuint64_t)d->cin * 2 * d->w * d->h};
     const cuuint32_t box[4] = {64, (cuuint32_t)p.wp, (cuuint32_t)p.r_in, 1};
-    CUresult r = di->encode_tiled(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+    CUresult r = di->encode_tiled(tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad slab x) failed (CUresult %d)", (int)r);
@@ -651,16 +742,31 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
     const cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)p.frames};
     const cuuint64_t strides[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->cout * 2 * d->w, (cuuint64_t)d->cout * 2 * d->w * d->h};
     const cuuint32_t box[4] = {64, (cuuint32_t)p.wp, (cuuint32_t)p.r_out, 1};
-    CUresult r = di->encode_tiled(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+    CUresult r = di->encode_tiled(tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FVT_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad slab dy) failed (CUresult %d)", (int)r);
   }
-  const int smem_bytes = p.stages * p.stage_bytes + kAux;
-  conv_wgrad_slab_kernel<<<items * p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, p);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K3s launch (one layer)
+// Returns 1 when the slab weight-gradient kernel took the call, 0 when the shape is not eligible, < 0 on error.
+static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, const void* x, const void* dy, float* dw,
+                          int cout_real, int cin_real, void* ws, size_t ws_bytes, cudaStream_t stream, size_t* plan_bytes = nullptr) {
+  WgsPlan pl;
+  if (wgs_plan(di, o, d, cout_real, cin_real, false, &pl) != 1) return 0;
+  int splits = pl.splits_wanted;
+  if (plan_bytes != nullptr) { *plan_bytes = splits > 1 ? (size_t)splits * (size_t)pl.dw_elems * sizeof(float) : 0; return 1; }
+  splits = wgrad_fit_splits(splits, pl.dw_elems, ws, ws_bytes);
+  wgs_set_splits(&pl, splits, dw, (float*)ws);
+  CUtensorMap tmx, tmdy;
+  if (int e = wgs_encode_maps(di, d, pl.p, x, dy, &tmx, &tmdy)) return e;
+  const int smem_bytes = pl.p.stages * pl.p.stage_bytes + 1024;
+  conv_wgrad_slab_kernel<<<pl.items * pl.p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, pl.p);
   if (int e = check_launch("conv_wgrad_slab_kernel")) return e;
-  if (p.splits > 1 && !o.wgrad_no_store)
-    if (int e = wgrad_reduce(p.ws, dw, dw_elems, p.splits, stream)) return e;
+  if (pl.p.splits > 1 && !o.wgrad_no_store)
+    if (int e = wgrad_reduce(pl.p.ws, dw, pl.dw_elems, pl.p.splits, stream)) return e;
   return 1;
 }
 
@@ -692,6 +798,7 @@ static int init_kernel_attributes(int device) {
   FVT_SET_SMEM(unit2p1_fused_is_kernel, kSmemMax);
   FVT_SET_SMEM(conv_wgrad_kernel, kSmemMax);
   FVT_SET_SMEM(conv_wgrad_slab_kernel, kSmemMax);
+  FVT_SET_SMEM(conv_wgrad_group_kernel, kSmemMax);
   FVT_SET_SMEM(pack_weight_fwd_kernel, 96 * 1024);
   FVT_SET_SMEM(pack_weight_dgrad_kernel, 96 * 1024);
 #undef FVT_SET_SMEM
@@ -1512,8 +1619,7 @@ static int conv3d_wgrad_impl(fvt_handle_t handle, const fvt_conv_desc* d, const 
     if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) return set_error(FVT_ERR_MISALIGNED, "tensor pointers must be 16-byte aligned");
   }
   {
-    int r = try_wgrad_slab(di, o, d, x, dy, dw, cout_real, cin_real, workspace, workspace_bytes, (cudaStream_t)stream, plan_bytes);
-    if (r == 0) r = try_wgrad_temporal(di, o, d, x, dy, dw, cout_real, cin_real, workspace, workspace_bytes, (cudaStream_t)stream, plan_bytes);
+    const int r = try_wgrad_slab(di, o, d, x, dy, dw, cout_real, cin_real, workspace, workspace_bytes, (cudaStream_t)stream, plan_bytes);
     if (r != 0) return r < 0 ? r : 0;
   }
   int to, ho, wo;
@@ -1600,6 +1706,130 @@ extern "C" {
 int fvt_conv3d_wgrad(fvt_handle_t handle, const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
                      int32_t cin_real, void* workspace, size_t workspace_bytes, void* stream) {
   return conv3d_wgrad_impl(handle, d, x, dy, dw, cout_real, cin_real, workspace, workspace_bytes, stream, nullptr);
+}
+
+// ---- grouped weight gradients (conv_wgrad_slab.cuh: conv_wgrad_group_kernel) ----
+// Table = header | entries (tensor maps + parameters per layer) | CTA map | reduce map; built on the host, uploaded by the
+// caller once per set of buffers (pointers are baked into the tensor maps), then launched any number of times.
+struct WgradGroupHeader {
+  uint32_t magic;
+  int32_t n_entries, grid, red_blocks, smem_bytes, device;
+  int64_t entries_off, cta_map_off, red_map_off, total_bytes, ws_bytes;
+  int64_t pad[8];
+};
+static_assert(sizeof(WgradGroupHeader) == 128, "header keeps the entries 128-byte aligned");
+constexpr uint32_t kWgradGroupMagic = 0x46564747u;   // "FVGG"
+
+int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_desc* descs, const void* const* x, const void* const* dy,
+                                float* const* dw, const int32_t* cout_real, const int32_t* cin_real, void* workspace,
+                                size_t workspace_bytes, void* host_table, size_t host_table_bytes, size_t* table_bytes,
+                                size_t* workspace_bytes_needed, int32_t* in_group) {
+  int st = 0;
+  const DeviceInfo* di = handle_device(handle, &st);
+  if (di == nullptr) return st;
+  const Options& o = handle->opt;
+  if (n <= 0 || n > 4096 || descs == nullptr || cout_real == nullptr || cin_real == nullptr || in_group == nullptr || table_bytes == nullptr ||
+      workspace_bytes_needed == nullptr)
+    return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_plan: bad arguments");
+  std::vector<WgsPlan> plans((size_t)n);
+  std::vector<int> member;
+  double work = 0.0;
+  for (int l = 0; l < n; ++l) {
+    in_group[l] = 0;
+    if (validate_conv(&descs[l])) return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_plan: descriptor %d is invalid", l);
+    if (cout_real[l] <= 0 || cout_real[l] > descs[l].cout || cin_real[l] <= 0 || cin_real[l] > descs[l].cin)
+      return set_error(FVT_ERR_BAD_DESC, "real filter counts exceed stored");
+    if (wgs_plan(di, o, &descs[l], cout_real[l], cin_real[l], true, &plans[l]) != 1) continue;
+    in_group[l] = 1;
+    member.push_back(l);
+    work += plans[l].items * (plans[l].item_clk + plans[l].fixed_clk);
+  }
+  // pixel splits: an item should not run much longer than half of an SM's share of the whole group (the grid is
+  // list-scheduled onto the SMs, longest items first), nor be cut below ~20k clocks (prologue + epilogue dominate there)
+  const double share = work / di->sm_count;
+  double max_item = share * 0.5;
+  if (max_item < 20000.0) max_item = 20000.0;
+  size_t ws_need = 0;
+  long long grid = 0, red_blocks = 0;
+  std::vector<int> splits((size_t)n, 1);
+  std::vector<size_t> ws_off((size_t)n, 0);
+  for (int l : member) {
+    WgsPlan& pl = plans[l];
+    int sp = (int)((pl.item_clk + max_item - 1.0) / max_item);
+    if (sp < 1) sp = 1;
+    wgs_set_splits(&pl, sp, nullptr, nullptr);
+    splits[l] = pl.p.splits;
+    if (splits[l] > 1) {
+      ws_off[l] = ws_need;
+      ws_need += ((size_t)splits[l] * (size_t)pl.dw_elems * sizeof(float) + 255) / 256 * 256;
+      red_blocks += (pl.dw_elems + kWgrChunk - 1) / kWgrChunk;
+    }
+    grid += (long long)pl.items * splits[l];
+  }
+  const size_t entries_off = sizeof(WgradGroupHeader);
+  const size_t cta_off = entries_off + member.size() * sizeof(WgradGroupEntry);
+  const size_t red_off = (cta_off + (size_t)grid * sizeof(int2) + 127) / 128 * 128;
+  const size_t total = (red_off + (size_t)red_blocks * sizeof(int2) + 127) / 128 * 128;
+  *table_bytes = member.empty() ? 0 : total;
+  *workspace_bytes_needed = ws_need;
+  if (host_table == nullptr || member.empty()) return 0;
+  if (host_table_bytes < total) return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_plan: host_table holds %zu bytes, %zu needed", host_table_bytes, total);
+  if (x == nullptr || dy == nullptr || dw == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer array");
+  if (ws_need > 0 && (workspace == nullptr || workspace_bytes < ws_need || (((uintptr_t)workspace) & 15) != 0))
+    return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_plan: the group needs %zu bytes of 16-byte aligned workspace", ws_need);
+  uint8_t* base = static_cast<uint8_t*>(host_table);
+  memset(base, 0, total);
+  WgradGroupHeader* h = reinterpret_cast<WgradGroupHeader*>(base);
+  WgradGroupEntry* ent = reinterpret_cast<WgradGroupEntry*>(base + entries_off);
+  int2* cta_map = reinterpret_cast<int2*>(base + cta_off);
+  int2* red_map = reinterpret_cast<int2*>(base + red_off);
+  struct Cta { double clk; int entry, item; };
+  std::vector<Cta> ctas;
+  ctas.reserve((size_t)grid);
+  int smem_max = 0;
+  long long rb = 0;
+  for (size_t e = 0; e < member.size(); ++e) {
+    const int l = member[e];
+    WgsPlan& pl = plans[l];
+    if (x[l] == nullptr || dy[l] == nullptr || dw[l] == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer (layer %d)", l);
+    if (((uintptr_t)x[l] | (uintptr_t)dy[l] | (uintptr_t)dw[l]) & 15) return set_error(FVT_ERR_MISALIGNED, "tensor pointers must be 16-byte aligned (layer %d)", l);
+    wgs_set_splits(&pl, splits[l], dw[l], reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + ws_off[l]));
+    if (int err = wgs_encode_maps(di, &descs[l], pl.p, x[l], dy[l], &ent[e].tmx, &ent[e].tmdy)) return err;
+    ent[e].p = pl.p;
+    const int smem = pl.p.stages * pl.p.stage_bytes + 1024;
+    if (smem > smem_max) smem_max = smem;
+    const double clk = pl.item_clk / pl.p.splits + pl.fixed_clk;
+    for (int i = 0; i < pl.items * pl.p.splits; ++i) ctas.push_back({clk, (int)e, i});
+    if (pl.p.splits > 1)
+      for (long long c = 0; c < (pl.dw_elems + kWgrChunk - 1) / kWgrChunk; ++c) red_map[rb++] = make_int2((int)e, (int)c);
+  }
+  std::stable_sort(ctas.begin(), ctas.end(), [](const Cta& a, const Cta& b) { return a.clk > b.clk; });
+  for (size_t i = 0; i < ctas.size(); ++i) cta_map[i] = make_int2(ctas[i].entry, ctas[i].item);
+  h->magic = kWgradGroupMagic;
+  h->n_entries = (int)member.size(); h->grid = (int)grid; h->red_blocks = (int)red_blocks; h->smem_bytes = smem_max; h->device = handle->device;
+  h->entries_off = (int64_t)entries_off; h->cta_map_off = (int64_t)cta_off; h->red_map_off = (int64_t)red_off;
+  h->total_bytes = (int64_t)total; h->ws_bytes = (int64_t)ws_need;
+  return 0;
+}
+
+int fvt_conv3d_wgrad_group_run(fvt_handle_t handle, const void* host_table, const void* device_table, void* stream) {
+  int st = 0;
+  const DeviceInfo* di = handle_device(handle, &st);
+  if (di == nullptr) return st;
+  if (host_table == nullptr || device_table == nullptr || (((uintptr_t)device_table) & 127) != 0)
+    return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_run: host_table / 128-byte aligned device_table required");
+  const WgradGroupHeader* h = static_cast<const WgradGroupHeader*>(host_table);
+  if (h->magic != kWgradGroupMagic || h->device != handle->device || h->grid <= 0)
+    return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_run: not a table planned by fvt_conv3d_wgrad_group_plan for this device");
+  const uint8_t* dev = static_cast<const uint8_t*>(device_table);
+  const WgradGroupEntry* ent = reinterpret_cast<const WgradGroupEntry*>(dev + h->entries_off);
+  conv_wgrad_group_kernel<<<h->grid, kWgsThreads, h->smem_bytes, (cudaStream_t)stream>>>(ent, reinterpret_cast<const int2*>(dev + h->cta_map_off));
+  if (int e = check_launch("conv_wgrad_group_kernel")) return e;
+  if (h->red_blocks > 0 && !handle->opt.wgrad_no_store) {
+    wgrad_group_reduce_kernel<<<h->red_blocks, 256, 0, (cudaStream_t)stream>>>(ent, reinterpret_cast<const int2*>(dev + h->red_map_off));
+    if (int e = check_launch("wgrad_group_reduce_kernel")) return e;
+  }
+  return 0;
 }
 
 size_t fvt_conv3d_workspace_bytes(fvt_handle_t handle, const fvt_conv_desc* d, int32_t op, int32_t cout_real, int32_t cin_real) {

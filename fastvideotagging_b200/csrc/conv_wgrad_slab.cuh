@@ -45,6 +45,11 @@ struct WgradSlabParams {
   // 64-channel blocks); the tap's input frame blocks are plain [128 x 64] TMA boxes (no shifted views: shift = 0)
   int temporal;
   int hw, t_frames, blocks_per_frame, kt, pt, chunks_per_tap;
+  // where the input of filter tap k sits relative to an output tile: (k - pt) * tap_frames frames and (k - pt) * tap_pos
+  // positions further.  Per-frame tiles: (1, 0), maps {C, H*W, T, N}.  Flattened tiles (a tile = 128 consecutive positions of
+  // a clip's T*H*W, no padding at frame ends): (0, H*W), maps {C, T*H*W, 1, N} — positions outside the clip come back as
+  // zeros, which is exactly the temporal zero padding.
+  int tap_frames, tap_pos;
   float* dw;
   int w_ohwi;                  // dw layout (O, taps, I) instead of (O, I, taps)
   int dbg_no_store;            // experiments only (fvt_set_option("wgrad_no_store")): epilogue reads TMEM, stores nothing
@@ -55,10 +60,12 @@ struct WgradSlabParams {
   long long ws_split_stride;   // elements of one slice (= cout_real * cin_real * taps)
 };
 
-__global__ void __launch_bounds__(kWgsThreads, 1)
-conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
-                       const WgradSlabParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+// One work item (pixel split, M chunk, N tile) of one layer.  `global_maps`: the tensor maps live in global memory (a
+// group table written by the host) instead of the kernel's parameter space.
+__device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, const CUtensorMap* tmap_dy_p, const WgradSlabParams& p,
+                                                int item, uint8_t* smem, bool global_maps) {
+  const CUtensorMap& tmap_x = *tmap_x_p;
+  const CUtensorMap& tmap_dy = *tmap_dy_p;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
@@ -70,7 +77,6 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   // ---- work item: (pixel split, M chunk, N tile)
-  int item = blockIdx.x;
   const int nt = item % p.n_tiles;     item /= p.n_tiles;
   const int chunk = item % p.m_chunks; item /= p.m_chunks;
   const int split = item;
@@ -97,6 +103,10 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     ptx::fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
+    if (global_maps) {            // descriptors written by the host into global memory: make them visible to the TMA unit
+      ptx::fence_tensormap_acquire(&tmap_x);
+      ptx::fence_tensormap_acquire(&tmap_dy);
+    }
     ptx::prefetch_tensormap(&tmap_x);
     ptx::prefetch_tensormap(&tmap_dy);
     for (int s = 0; s < p.stages; ++s) {
@@ -141,7 +151,8 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
           const int nt_ = tile / p.blocks_per_frame;
           const int t = nt_ % p.t_frames, n = nt_ / p.t_frames;
           for (int c = 0; c < ncb; ++c)
-            tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, b * 128, t + tap_t - p.pt, n);
+            tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, b * 128 + (tap_t - p.pt) * p.tap_pos,
+                        t + (tap_t - p.pt) * p.tap_frames, n);
           for (int j = 0; j < p.n_blocks; ++j)
             tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, b * 128, t, n);
         }
@@ -235,6 +246,77 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+__global__ void __launch_bounds__(kWgsThreads, 1)
+conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                       const WgradSlabParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  wgrad_slab_body(&tmap_x, &tmap_dy, p, blockIdx.x, smem, false);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Grouped launch: the weight gradients of SEVERAL layers in one grid.  The small-feature-map stages (conv4_x / conv5_x
+// at a few clips per GPU: 784 - 6272 output positions per layer against 0.3 - 5 M weights) cannot fill 148 SMs per layer
+// without cutting the pixel range into many splits, and every split re-reads both operands and adds a dW-sized slice to
+// the reduction; launched one by one each layer also pays its own launch, pipeline fill, epilogue and reduce pass
+// (measured 35 - 55 us per layer against 2 - 12 us of tensor work).  A weight gradient feeds nothing but the optimiser,
+// so the training plan defers the layers of a stage and runs them together: the (M chunk, N tile) items of all layers
+// fill the machine with few or no pixel splits.  One table entry per layer (its tensor maps + parameters), one
+// (entry, item) pair per CTA, longest items first.
+struct __align__(128) WgradGroupEntry {
+  CUtensorMap tmx, tmdy;
+  WgradSlabParams p;
+};
+
+__global__ void __launch_bounds__(kWgsThreads, 1)
+conv_wgrad_group_kernel(const WgradGroupEntry* __restrict__ entries, const int2* __restrict__ cta_map) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int2 m = cta_map[blockIdx.x];
+  const WgradGroupEntry* e = entries + m.x;
+  // the parameters move into the CTA's auxiliary area (behind the barriers): every role reads them many times
+  const int stages = e->p.stages, stage_bytes = e->p.stage_bytes;
+  WgradSlabParams* sp = reinterpret_cast<WgradSlabParams*>(smem + stages * stage_bytes + 256);
+  static_assert(sizeof(WgradSlabParams) <= 768 && sizeof(WgradSlabParams) % 4 == 0, "parameter copy must fit the aux area");
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(WgradSlabParams) / 4); i += kWgsThreads)
+    reinterpret_cast<int*>(sp)[i] = reinterpret_cast<const int*>(&e->p)[i];
+  __syncthreads();
+  wgrad_slab_body(&e->tmx, &e->tmdy, *sp, m.y, smem, true);
+}
+
+// Slice reduction of every split layer of a group in one launch: block -> (entry, 4096-float chunk of its dW);
+// dw[i] = sum over k < splits of ws[k][i] in split order (deterministic).
+constexpr int kWgrChunk = 4096;
+__global__ void __launch_bounds__(256)
+wgrad_group_reduce_kernel(const WgradGroupEntry* __restrict__ entries, const int2* __restrict__ red_map) {
+  const int2 m = red_map[blockIdx.x];
+  const WgradSlabParams& p = entries[m.x].p;
+  const long long elems = p.ws_split_stride;
+  const long long lo = static_cast<long long>(m.y) * kWgrChunk;
+  long long hi = lo + kWgrChunk;
+  if (hi > elems) hi = elems;
+  const float* ws = p.ws;
+  float* dw = p.dw;
+  const int splits = p.splits;
+  if ((elems & 3) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+    const long long n4 = elems >> 2;
+    const float4* w4 = reinterpret_cast<const float4*>(ws);
+    float4* d4 = reinterpret_cast<float4*>(dw);
+    for (long long i = (lo >> 2) + threadIdx.x; i < (hi >> 2); i += 256) {
+      float4 a = __ldg(w4 + i);
+      for (int k = 1; k < splits; ++k) {
+        const float4 b = __ldg(w4 + k * n4 + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      d4[i] = a;
+    }
+  } else {
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+      float a = __ldg(ws + i);
+      for (int k = 1; k < splits; ++k) a += __ldg(ws + k * elems + i);
+      dw[i] = a;
+    }
   }
 }
 

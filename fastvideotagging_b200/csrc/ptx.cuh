@@ -73,6 +73,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------- TMA
+// A tensor map that lives in global memory (written by the host, not a kernel parameter): acquire it for the TMA unit's
+// descriptor fetch before the first use by this CTA.
+__device__ __forceinline__ void fence_tensormap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

@@ -214,6 +214,7 @@ class InferencePlan:
             return L.dst, L.out_shape
 
         # ---- stem: unfold + (1,7,1)/s(1,2,1) conv on K1, then the 3x1x1 temporal conv
+        self._stage_of = {}              # block index -> stage key (the stage's output width)
         s_sp, s_tm = stem_specs()
         self.stem = StemGeometry(h)
         ushape = self.stem.unfold_shape(n, t, h, w)
@@ -462,7 +463,7 @@ class FlatParams:
 class _TLayer:
     __slots__ = ("spec", "fwd", "dgr", "w_name", "cin_real", "cout_real", "cin_s", "cout_s", "rows", "in_shape",
                  "out_shape", "src", "raw", "act", "stats", "scale", "shift", "mean", "invstd", "wp", "wpd", "w_eq",
-                 "strided", "need_dgrad", "dplan", "bnacc", "dgr_bn")
+                 "strided", "need_dgrad", "dplan", "bnacc", "dgr_bn", "draw_own", "group")
 
 
 class TrainPlan:
@@ -519,9 +520,11 @@ class TrainPlan:
             L.wp = L.wpd = L.w_eq = None
             L.dplan = None
             L.bnacc = L.dgr_bn = None
+            L.draw_own = L.group = None
             self.layers[spec.name] = L
             return L
 
+        self._stage_of = {}              # block index -> stage key (the stage's output width)
         s_sp, s_tm = stem_specs()
         self.stem = StemGeometry(h)
         ushape = self.stem.unfold_shape(n, t, h, w)
@@ -540,6 +543,7 @@ class TrainPlan:
             d = make(main[3], c.out_shape, main[2].name + ":act")
             sc = make(short, cur_shape, cur_name) if short is not None else None
             self.blocks.append((comp, cur_name, cur_shape, a, b, c, d, sc))
+            self._stage_of[comp] = cout
             cur_name, cur_shape = main[3].name + ":act", d.out_shape     # block output lives in d.act
             for L in (a, b, c, d):
                 max_elems = max(max_elems, L.raw.numel(), L.in_shape[0] * L.in_shape[1] * L.in_shape[2] * L.in_shape[3] * L.in_shape[4])
@@ -548,6 +552,10 @@ class TrainPlan:
         self.stats_all = ops.stats_buffer(sum(L.cout_s for L in self.layers.values()), device)
         # exact accumulators of the BatchNorm backward sums that the fused data-gradient epilogues fill (FVT_CONV_BN_BWD)
         self.fuse_bnbwd = os.environ.get("FVT_FUSE_BNBWD", "1") != "0"
+        # Measured (batch 4): the fused epilogue pays where launches dominate (conv3_x .. conv5_x); on the large-M layers
+        # (stem, conv2_x: 401408 positions) its per-row reads and 31 shuffles per 16 columns make a short-K data gradient
+        # epilogue-bound (conv2_x 64 -> 144 temporal: 41 -> 122 us, more than the reduce pass it saves)
+        self.fuse_bnbwd_rows = int(os.environ.get("FVT_FUSE_BNBWD_ROWS", "200000"))
         self.bnacc_all = ops.stats_buffer(sum(L.cout_s for L in self.layers.values()), device)
         off = 0
         for L in self.layers.values():
@@ -569,6 +577,26 @@ class TrainPlan:
         for nm in ["gA", "gB", "gmask", "gshort", "draw_s"] + ["draw%d" % i for i in range(self._n_draw)]:
             buf(nm, (max_elems,))
         buf("up", (up_elems,))
+        # Deferred, grouped weight gradients (ops.WgradGroup): in the small-feature-map stages a single layer cannot fill the
+        # machine (conv4_x / conv5_x at batch 4: 35-55 us per layer against 2-12 us of tensor work, and every launch
+        # occupies all SMs, so the data-gradient chain waits behind it).  A weight gradient feeds nothing but the optimiser:
+        # the stride-1 layers of such a stage keep their raw gradient in a buffer of their own and ONE launch at the end of
+        # the stage's backward computes all of them.  FVT_WGRAD_GROUP=0: every layer launches its own (round-1 behaviour);
+        # FVT_WGRAD_GROUP_ROWS: largest output-position count per layer that is still deferred.
+        self._groups = {}                # stage key -> [layers]  (ops.WgradGroup built on first use: needs flat.g)
+        self._group_obj = {}
+        if os.environ.get("FVT_WGRAD_GROUP", "1") != "0":
+            max_rows = int(os.environ.get("FVT_WGRAD_GROUP_ROWS", "65536"))
+            for comp, xin_name, xin_shape, a, b, c, d, sc in self.blocks:
+                cand = [L for L in (a, b, c, d) if L.rows <= max_rows and not L.strided]
+                if not cand:
+                    continue
+                ok = ops.wgrad_group_eligible([L.fwd for L in cand], [L.cout_real for L in cand], [L.cin_real for L in cand], device)
+                for L, e in zip(cand, ok):
+                    if e:
+                        L.group = self._stage_of[comp]
+                        L.draw_own = buf(L.spec.name + ":draw", L.out_shape)
+                        self._groups.setdefault(L.group, []).append(L)
         self.pooled = None
         self._dweq = None                # gradient of the stem's equivalent filter (re-mapped into conv1_middle_weight's slot)
         self.launches_fwd = self.launches_bwd = 0
@@ -809,9 +837,14 @@ class TrainPlan:
         else:
             ops.bn_backward(L.raw, dact, mask, L.mean, L.invstd, self.flat.view(self.flat.w, gname), sums2, draw, dz_out)
 
-    def _draw(self, shape, key=None):
+    def _draw(self, shape, key=None, own=None):
         """Next raw-gradient scratch buffer (three rotate, so a weight gradient still reading one on the side stream
-        never sees it overwritten); waits for that buffer's last side-stream reader."""
+        never sees it overwritten); waits for that buffer's last side-stream reader.  own: a layer whose weight gradient is
+        deferred to its stage's grouped launch keeps its raw gradient in a buffer of its own."""
+        if own is not None and own.draw_own is not None:
+            v = own.draw_own
+            v._fvt_key = None
+            return v
         if key is None:
             key = "draw%d" % self._draw_i
             self._draw_i = (self._draw_i + 1) % self._n_draw
@@ -824,6 +857,9 @@ class TrainPlan:
 
     def _wgrad(self, L, x_in, draw):
         """Weight gradient of L; on the side stream when there is one (it feeds nothing but the gradient buffer)."""
+        if L.group is not None:           # deferred: computed by the stage's grouped launch (_run_group)
+            assert draw is L.draw_own
+            return
         if self.side is None:
             return self._wgrad_now(L, x_in, draw)
         main = torch.cuda.current_stream(self.device)
@@ -833,6 +869,25 @@ class TrainPlan:
             ev = torch.cuda.Event()
             ev.record(self.side)
         self._busy[draw._fvt_key] = ev
+
+    def _run_group(self, key):
+        """The deferred weight gradients of a stage in one launch (ops.WgradGroup), on the side stream when there is one."""
+        layers = self._groups.get(key)
+        if not layers or "wgrad" in self._skip:
+            return
+        g = self._group_obj.get(key)
+        if g is None or g.grad_ptr != self.flat.g.data_ptr():
+            B = self.bufs
+            g = ops.WgradGroup([(L.fwd, B[L.src], L.draw_own, self.flat.raw(self.flat.g, L.w_name), L.cout_real, L.cin_real)
+                                for L in layers], self.device)
+            assert all(g.in_group)
+            g.grad_ptr = self.flat.g.data_ptr()
+            self._group_obj[key] = g
+        if self.side is None:
+            return g.run()
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            g.run()
 
     def _wgrad_now(self, L, x_in, draw):
         if "wgrad" in self._skip:
@@ -849,7 +904,8 @@ class TrainPlan:
     def _can_fuse_bn(self, L):
         """The data gradient of L feeds exactly one BatchNorm backward whose ReLU mask comes from its own raw output: fusable
         unless L is strided (its data gradient runs as parity sub-convolutions onto a lattice)."""
-        return self.fuse_bnbwd and L.dplan is None and not L.strided and "dgrad" not in self._skip and "bnbwd" not in self._skip
+        return (self.fuse_bnbwd and L.dplan is None and not L.strided and L.rows <= self.fuse_bnbwd_rows and
+                "dgrad" not in self._skip and "bnbwd" not in self._skip)
 
     def _dgrad(self, L, draw, out, residual=None, fuse_bn=None):
         """Data gradient of L.  fuse_bn = the producer layer P of L's input (act_P = relu(bn(raw_P))): the epilogue masks with
@@ -910,11 +966,13 @@ class TrainPlan:
         self._ready("final_fc_weight", "final_fc_bias")
         self._mark("bwd:head")
         cur_key = "gA"
-        for comp, xin_name, xin_shape, a, b, c, d, sc in reversed(self.blocks):
+        pending = []                                  # parameter names of a deferred stage's blocks, reduced after its group
+        rblocks = list(reversed(self.blocks))
+        for bi, (comp, xin_name, xin_shape, a, b, c, d, sc) in enumerate(rblocks):
             xin = B[xin_name]
             other = "gB" if cur_key == "gA" else "gA"
             gmask = self._view("gmask", d.out_shape)
-            draw_d = self._draw(d.out_shape)
+            draw_d = self._draw(d.out_shape, own=d)
             self._bn_bwd(d, g_cur, d.act, draw_d, dz_out=gmask)           # out = relu(bn2 + shortcut): mask by out > 0
             if sc is not None:
                 draw_s = self._draw(sc.out_shape, key="draw_s")
@@ -928,26 +986,38 @@ class TrainPlan:
             # the convolution's epilogue where possible, so the BatchNorm backward is one pass instead of two
             f = self._can_fuse_bn(d)
             gc = self._dgrad(d, draw_d, self._view(other, c.out_shape), fuse_bn=c if f else None)
-            draw_c = self._draw(c.out_shape)
+            draw_c = self._draw(c.out_shape, own=c)
             self._bn_bwd(c, gc, "fused" if f else True, draw_c)
             self._wgrad(c, b.act, draw_c)
             f = self._can_fuse_bn(c)
             gb = self._dgrad(c, draw_c, self._view(cur_key, b.out_shape), fuse_bn=b if f else None)
-            draw_b = self._draw(b.out_shape)
+            draw_b = self._draw(b.out_shape, own=b)
             self._bn_bwd(b, gb, "fused" if f else True, draw_b)
             self._wgrad(b, a.act, draw_b)
             f = self._can_fuse_bn(b)
             ga = self._dgrad(b, draw_b, self._view(other, a.out_shape), fuse_bn=a if f else None)
-            draw_a = self._draw(a.out_shape)
+            draw_a = self._draw(a.out_shape, own=a)
             self._bn_bwd(a, ga, "fused" if f else True, draw_a)
             self._wgrad(a, xin, draw_a)
             g_cur = self._dgrad(a, draw_a, self._view(cur_key, xin_shape), residual=gshort)
             names = []
             for L in (a, b, c, d) + ((sc,) if sc is not None else ()):
                 names += [L.w_name, L.spec.bn + "_gamma", L.spec.bn + "_beta"]
-            if self.grad_hook is not None:
-                self._join_side()                 # the block's weight gradients must be final before they are reduced
-            self._ready(*names)
+            stage = self._stage_of[comp]
+            stage_ends = bi + 1 == len(rblocks) or self._stage_of[rblocks[bi + 1][0]] != stage
+            if stage in self._groups:
+                pending.append(names)
+                if stage_ends:
+                    self._run_group(stage)
+                    if self.grad_hook is not None:
+                        self._join_side()
+                    for nm in pending:
+                        self._ready(*nm)
+                    pending = []
+            else:
+                if self.grad_hook is not None:
+                    self._join_side()             # the block's weight gradients must be final before they are reduced
+                self._ready(*names)
             self._mark("bwd:block%s" % comp)
         # stem
         other = "gB" if cur_key == "gA" else "gA"

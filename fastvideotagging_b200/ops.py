@@ -459,6 +459,71 @@ def conv3d_wgrad(fwd, x, dy, dw, cout_real, cin_real, ohwi=False, ws="auto"):
     return dw
 
 
+def wgrad_group_eligible(descs, cout_real, cin_real, device):
+    """Which of these layers a grouped weight-gradient launch would take (fvt_conv3d_wgrad_group_plan without buffers)."""
+    lib = _lib.load()
+    n = len(descs)
+    arr = (ConvDesc * n)(*[_with_ohwi(d) for d in descs])
+    co = (ctypes.c_int32 * n)(*cout_real)
+    ci = (ctypes.c_int32 * n)(*cin_real)
+    member = (ctypes.c_int32 * n)()
+    tb, wb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    check(lib.fvt_conv3d_wgrad_group_plan(_lib.handle(device.index), n, arr, None, None, None, co, ci, None, 0, None, 0,
+                                          ctypes.byref(tb), ctypes.byref(wb), member))
+    return [bool(m) for m in member]
+
+
+class WgradGroup:
+    """Weight gradients of several layers as ONE launch (fvt_conv3d_wgrad_group_plan / _run).  layers: list of
+    (fwd_desc, x, dy, dw, cout_real, cin_real) with dw in the (O, kT, kH, kW, I) layout; all tensors are kept by reference
+    (their pointers are baked into the launch table).  Layers the grouped kernel does not take (strided, 1x1x1) are listed
+    in `.rest` — run() launches them one by one behind the group."""
+
+    def __init__(self, layers, device):
+        lib = _lib.load()
+        n = len(layers)
+        self.layers = layers
+        self.device = device
+        descs = (ConvDesc * n)(*[_with_ohwi(L[0]) for L in layers])
+        self._descs = descs
+        vp = ctypes.c_void_p
+        xs = (vp * n)(*[L[1].data_ptr() for L in layers])
+        dys = (vp * n)(*[L[2].data_ptr() for L in layers])
+        dws = (vp * n)(*[L[3].data_ptr() for L in layers])
+        for L in layers:
+            assert L[3].dtype == torch.float32 and L[3].is_contiguous()
+        co = (ctypes.c_int32 * n)(*[L[4] for L in layers])
+        ci = (ctypes.c_int32 * n)(*[L[5] for L in layers])
+        member = (ctypes.c_int32 * n)()
+        tb, wb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        h = _lib.handle(device.index)
+        check(lib.fvt_conv3d_wgrad_group_plan(h, n, descs, xs, dys, dws, co, ci, None, 0, None, 0, ctypes.byref(tb), ctypes.byref(wb), member))
+        self.in_group = [bool(m) for m in member]
+        self.rest = [L for L, m in zip(layers, self.in_group) if not m]
+        self.table_bytes, self.ws_bytes = tb.value, wb.value
+        self.ws = torch.empty(max(wb.value, 16) // 4, dtype=torch.float32, device=device) if wb.value else None
+        self.host = self.dev = None
+        if tb.value:
+            self.host = (ctypes.c_uint8 * tb.value)()
+            check(lib.fvt_conv3d_wgrad_group_plan(h, n, descs, xs, dys, dws, co, ci, _ptr(self.ws), wb.value, self.host, tb.value,
+                                                  ctypes.byref(tb), ctypes.byref(wb), member))
+            raw = torch.frombuffer(self.host, dtype=torch.uint8).clone()
+            pad = torch.empty(tb.value + 128, dtype=torch.uint8, device=device)
+            off = (-pad.data_ptr()) % 128
+            self.dev = pad[off:off + tb.value]
+            self.dev.copy_(raw)
+            self._pad = pad
+            hdr = torch.frombuffer(self.host, dtype=torch.int32, count=6)
+            self.grid, self.red_blocks = int(hdr[2]), int(hdr[3])
+
+    def run(self):
+        lib = _lib.load()
+        if self.dev is not None:
+            check(lib.fvt_conv3d_wgrad_group_run(_lib.handle(self.device.index), self.host, _ptr(self.dev), _stream()))
+        for fwd, x, dy, dw, co, ci in self.rest:
+            conv3d_wgrad(fwd, x, dy, dw, co, ci, ohwi=True)
+
+
 def bn_finalize(stats, gamma, beta, running_mean, running_var, c_store, rows, eps, momentum, scale, shift, mean, invstd):
     lib = _lib.load()
     check(lib.fvt_bn_finalize(_h(stats), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), c_store,

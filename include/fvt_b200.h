@@ -237,6 +237,23 @@ int fvt_pack_conv_weights_multi(fvt_handle_t handle, const fvt_pack_entry* table
  * single split per dW tile: correct, slower on large-M layers.  fvt_conv3d_workspace_bytes(.., FVT_OP_WGRAD, ..). */
 int fvt_conv3d_wgrad(fvt_handle_t handle, const fvt_conv_desc* d, const void* x, const void* dy, float* dw, int32_t cout_real,
                      int32_t cin_real, void* workspace, size_t workspace_bytes, void* stream);
+/* Weight gradients of SEVERAL layers in one launch (the analogue of cuDNN backward-filter called once per Conv3D of a
+ * residual stage, reference model/R2Plus1.py:73-82 under autograd, train_simple_r3d.py:118-125).  A weight gradient feeds
+ * nothing but the optimiser, so a training loop may defer the layers of a stage and run them together: the small-feature-
+ * map stages (conv4_x / conv5_x at a few clips per GPU) cannot fill the machine one layer at a time.
+ * fvt_conv3d_wgrad_group_plan: descs[l] / x[l] / dy[l] / dw[l] / cout_real[l] / cin_real[l] as for fvt_conv3d_wgrad
+ * (FVT_CONV_W_OHWI per descriptor).  in_group[l] (out) = 1 when layer l is part of the grouped launch, 0 when the caller
+ * must run fvt_conv3d_wgrad for it (strided and 1x1x1 layers).  *table_bytes / *workspace_bytes_needed (out): sizes of the
+ * launch table and of the slice workspace the group wants (0: no layer is split).  With host_table == NULL only the
+ * sizes and in_group are computed (x / dy / dw may be NULL).  Otherwise host_table (>= *table_bytes) is filled; the
+ * caller copies it to 128-byte aligned device memory once and passes both copies to fvt_conv3d_wgrad_group_run.  The
+ * table bakes in the tensor pointers and the workspace pointer: re-plan when any of them changes.  Deterministic
+ * (pixel splits meet through workspace slices added in split order); every dw is overwritten. */
+int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_desc* descs, const void* const* x, const void* const* dy,
+                                float* const* dw, const int32_t* cout_real, const int32_t* cin_real, void* workspace,
+                                size_t workspace_bytes, void* host_table, size_t host_table_bytes, size_t* table_bytes,
+                                size_t* workspace_bytes_needed, int32_t* in_group);
+int fvt_conv3d_wgrad_group_run(fvt_handle_t handle, const void* host_table, const void* device_table, void* stream);
 /* up[n, to*st, ho*sh, wo*sw, :] = dy[n, to, ho, wo, :], zero elsewhere (up has the conv input's T,H,W). */
 int fvt_zero_insert(fvt_handle_t handle, const void* dy, void* up, int32_t n, int32_t t, int32_t h, int32_t w, int32_t to, int32_t ho,
                     int32_t wo, int32_t st, int32_t sh, int32_t sw, int32_t c_store, void* stream);

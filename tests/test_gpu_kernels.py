@@ -780,3 +780,57 @@ def test_fused_dgrad_bn_backward_matches_the_two_pass_form(cuda_device, lib, cas
     scale_d = draw_a.float().abs().max().item()
     assert (draw_b.float() - draw_a.float()).abs().max().item() <= 2 ** -6 * scale_d, name
     assert float(draw_b[..., cin:].float().abs().max()) == 0.0 if cin_s > cin else True
+
+
+def test_grouped_wgrad_matches_single_launches(cuda_device, lib):
+    """fvt_conv3d_wgrad_group_plan/_run: the weight gradients of several layers in one grid (conv4_x / conv5_x shapes of
+    the training plan, spatial and temporal, plus layers the group does not take) == the one-layer launches up to fp32
+    summation order (the group uses fewer pixel splits), == torch autograd on the same bf16 operands at 1e-2 of max; twice
+    the same bits."""
+    import torch
+    import torch.nn.functional as F
+    from fastvideotagging_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    shapes = [  # n, t, h, w, cin, cout, k, stride, pad
+        (2, 4, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1)),      # conv4_x spatial
+        (2, 4, 14, 14, 576, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # conv4_x temporal (flattened T*H*W tiles)
+        (2, 2, 7, 7, 512, 1152, (1, 3, 3), (1, 1, 1), (0, 1, 1)),       # conv5_x spatial
+        (2, 2, 7, 7, 1152, 512, (3, 1, 1), (1, 1, 1), (1, 0, 0)),       # conv5_x temporal: 49-position frames
+        (2, 8, 28, 28, 288, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # conv3_x temporal: long pixel range -> split + slice reduction
+        (2, 4, 14, 14, 256, 921, (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # strided: not in the group (run behind it)
+        (2, 4, 14, 14, 230, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # channel counts with padding (230 -> 240 stored)
+    ]
+    layers, refs = [], []
+    for n, t, h, w, cin, cout, k, s, p in shapes:
+        cin_s, cout_s = ops.pad16(cin), ops.pad16(cout)
+        fwd = ops.conv_desc(n, t, h, w, cin_s, cout_s, k, s, p)
+        to, ho, wo = ops.conv_out_shape(fwd)
+        x = torch.zeros(n, t, h, w, cin_s)
+        x[..., :cin] = torch.randn(n, t, h, w, cin, generator=gen)
+        dy = torch.zeros(n, to, ho, wo, cout_s)
+        dy[..., :cout] = torch.randn(n, to, ho, wo, cout, generator=gen)
+        x, dy = x.to(torch.bfloat16).to(cuda_device), dy.to(torch.bfloat16).to(cuda_device)
+        dw = torch.full((cout, k[0], k[1], k[2], cin), float("nan"), device=cuda_device)
+        layers.append((fwd, x, dy, dw, cout, cin))
+        single = ops.conv3d_wgrad(fwd, x, dy, torch.empty_like(dw), cout, cin, ohwi=True)
+        w0 = torch.zeros(cout, cin, *k, device=cuda_device, requires_grad=True)
+        y = F.conv3d(x[..., :cin].float().permute(0, 4, 1, 2, 3), w0, stride=s, padding=p)
+        y.backward(dy[..., :cout].float().permute(0, 4, 1, 2, 3))
+        refs.append((single, w0.grad.permute(0, 2, 3, 4, 1)))
+    group = ops.WgradGroup(layers, cuda_device)
+    assert group.in_group == [True, True, True, True, True, False, True]
+    assert group.red_blocks > 0                      # at least the conv3_x layer is split
+    group.run()
+    torch.cuda.synchronize()
+    first = [L[3].clone() for L in layers]
+    for (fwd, x, dy, dw, cout, cin), (single, ref) in zip(layers, refs):
+        scale = ref.abs().max().item()
+        assert torch.isfinite(dw).all()
+        assert (dw - ref).abs().max().item() <= 1e-2 * scale
+        assert (dw - single).abs().max().item() <= 1e-4 * scale
+    for L in layers:
+        L[3].fill_(float("nan"))
+    group.run()
+    torch.cuda.synchronize()
+    for L, f in zip(layers, first):
+        assert torch.equal(L[3], f)
