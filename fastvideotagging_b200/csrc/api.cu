@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <new>
@@ -506,22 +507,26 @@ static void wgs_set_splits(WgsPlan* pl, int splits, float* dw, float* ws) {
 static int wgs_plan_temporal(const DeviceInfo* di, const Options& o, const fvt_conv_desc* d, int cout_real, int cin_real, bool grouped,
                              WgsPlan* pl) {
   if (o.disable_wgrad_slab) return 0;
-  if (!(d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st == 1 && d->sh == 1 && d->sw == 1 && d->ph == 0 &&
+  if (!(d->kh == 1 && d->kw == 1 && d->kt > 1 && (d->kt & 1) && d->st >= 1 && d->sh == 1 && d->sw == 1 && d->ph == 0 &&
         d->pw == 0 && 2 * d->pt == d->kt - 1))
     return 0;
   const int hw = d->h * d->w;
-  // tiles of 128 consecutive positions of a clip (flattened T*H*W) unless frames already are whole tiles
-  const bool flat = (hw % 128) != 0 && !o.wgrad_no_flat;
-  if (!flat && hw < 96) return 0;
+  const int t_out = (d->t + 2 * d->pt - d->kt) / d->st + 1;
+  // tiles of 128 consecutive positions of a clip (flattened T*H*W) unless frames already are whole tiles; a temporally
+  // strided convolution (the first 3x1x1 of conv3_x .. conv5_x) keeps per-frame tiles: output frame t reads input frames
+  // t*st + tap - pt
+  const bool flat = (hw % 128) != 0 && !o.wgrad_no_flat && d->st == 1;
+  if (!flat && hw < (d->st == 1 ? 96 : 40)) return 0;
   if (flat && (long long)d->t * hw < 96) return 0;
   WgradSlabParams& p = pl->p;
   memset(&p, 0, sizeof(p));
   p.temporal = 1;
   p.kt = d->kt; p.pt = d->pt;
+  p.t_stride = d->st;
   if (flat) {
     p.hw = d->t * hw; p.t_frames = 1; p.tap_frames = 0; p.tap_pos = hw;
   } else {
-    p.hw = hw; p.t_frames = d->t; p.tap_frames = 1; p.tap_pos = 0;
+    p.hw = hw; p.t_frames = t_out; p.tap_frames = 1; p.tap_pos = 0;
   }
   p.blocks_per_frame = (p.hw + 127) / 128;
   p.num_tiles = d->n * p.t_frames * p.blocks_per_frame;
@@ -712,8 +717,9 @@ static int wgs_encode_maps(const DeviceInfo* di, const fvt_conv_desc* d, const W
     const cuuint32_t box[4] = {64, 128, 1, 1};
     const cuuint64_t hw = (cuuint64_t)p.hw, tf = (cuuint64_t)p.t_frames;
     {
-      const cuuint64_t dims[4] = {(cuuint64_t)d->cin, hw, tf, (cuuint64_t)d->n};
-      const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * hw, (cuuint64_t)d->cin * 2 * hw * tf};
+      const cuuint64_t tfx = p.tap_frames ? (cuuint64_t)d->t : 1;            // input frames (!= output frames when strided)
+      const cuuint64_t dims[4] = {(cuuint64_t)d->cin, hw, tfx, (cuuint64_t)d->n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * hw, (cuuint64_t)d->cin * 2 * hw * tfx};
       CUresult r = di->encode_tiled(tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1652,7 +1658,9 @@ static int conv3d_wgrad_impl(fvt_handle_t handle, const fvt_conv_desc* d, const 
   p.m_tiles = (p.m_groups + 1) / 2;
   p.kblocks_total = (p.m_total + kWgPix - 1) / kWgPix;
   const int items = p.m_tiles * p.n_tiles * (p.mode == 1 ? p.taps : 1);
-  int splits = (2 * di->sm_count + items - 1) / items;
+  // pixel splits: one wave of CTAs (every CTA pays ~8 us of launch + prologue + epilogue + slice store, and every split adds
+  // a dW-sized slice to the reduction; round 1 aimed at two waves, which the small strided layers paid for twice)
+  int splits = items <= di->sm_count ? di->sm_count / items : 1;
   if (splits > p.kblocks_total) splits = p.kblocks_total;
   if (splits < 1) splits = 1;
   const long long dw_elems = (long long)cout_real * cin_real * p.taps;
@@ -1799,6 +1807,10 @@ int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_d
     const int smem = pl.p.stages * pl.p.stage_bytes + 1024;
     if (smem > smem_max) smem_max = smem;
     const double clk = pl.item_clk / pl.p.splits + pl.fixed_clk;
+    if (getenv("FVT_WGRAD_DEBUG") != nullptr)
+      fprintf(stderr, "[fvt wgrad group] layer %d %s cin %d cout %d tiles %d: n_tile %d x%d, mt %d, chunks %d, splits %d -> %d CTAs, stages %d x %d B, "
+              "est %.0f clk/CTA (share %.0f)\n", l, pl.p.temporal ? "temporal" : "spatial", descs[l].cin, descs[l].cout, pl.p.num_tiles, pl.p.n_tile,
+              pl.p.n_tiles, pl.p.mt_per_cta, pl.p.m_chunks, pl.p.splits, pl.items * pl.p.splits, pl.p.stages, pl.p.stage_bytes, clk, share);
     for (int i = 0; i < pl.items * pl.p.splits; ++i) ctas.push_back({clk, (int)e, i});
     if (pl.p.splits > 1)
       for (long long c = 0; c < (pl.dw_elems + kWgrChunk - 1) / kWgrChunk; ++c) red_map[rb++] = make_int2((int)e, (int)c);

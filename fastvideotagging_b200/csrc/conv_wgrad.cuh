@@ -19,7 +19,7 @@
 
 namespace fvt {
 
-constexpr int kWgradThreads = 256;      // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kWgradThreads = 256;      // warp0 + warp3 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
 constexpr int kWgPix = 64;              // pixels per k-block
 constexpr int kSlabBytes = kWgPix * 128;   // one [64 px x 64 ch] slab
 constexpr int kWgMaxStages = 6;
@@ -98,7 +98,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 3) {
+    // Two producer warps: a TMA box costs its issuing thread ~275 clk whatever its size (profiles/r01_tma_rate_microbench.log),
+    // and a 64-pixel k-block needs up to six 8 KB boxes — one thread made the loop issue-bound.  Warp 0 posts the stage's
+    // byte count and loads the M side, warp 3 loads the N side; both complete on the stage's full barrier.
     {
       int stage = 0;
       uint32_t phase = 0;
@@ -114,30 +117,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
         uint8_t* base = smem + stage * stage_bytes;
         if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(fb, tx_bytes);
-        // ---- M side
-        for (int g = 0; g < m_valid_groups; ++g) {
-          const uint32_t dst = ptx::smem_u32(base + g * kSlabBytes);
-          if (p.mode == 0) {
-            const int grp = g0 + g;
-            const int tap = grp / p.cin_blocks, cb = grp - tap * p.cin_blocks;
-            const int dw_ = tap % p.kw, dh_ = (tap / p.kw) % p.kh, dt_ = tap / (p.kw * p.kh);
-            ptx::tma_load_im2col_5d(dst, &tmap_x, fb, cb * 64, cw, ch, cd, on, (uint16_t)dw_, (uint16_t)dh_, (uint16_t)dt_);
+          if (warp == 0) {
+            ptx::mbar_arrive_expect_tx(fb, tx_bytes);
+            // ---- M side
+            for (int g = 0; g < m_valid_groups; ++g) {
+              const uint32_t dst = ptx::smem_u32(base + g * kSlabBytes);
+              if (p.mode == 0) {
+                const int grp = g0 + g;
+                const int tap = grp / p.cin_blocks, cb = grp - tap * p.cin_blocks;
+                const int dw_ = tap % p.kw, dh_ = (tap / p.kw) % p.kh, dt_ = tap / (p.kw * p.kh);
+                ptx::tma_load_im2col_5d(dst, &tmap_x, fb, cb * 64, cw, ch, cd, on, (uint16_t)dw_, (uint16_t)dh_, (uint16_t)dt_);
+              } else {
+                ptx::tma_load_im2col_5d(dst, &tmap_dy, fb, (g0 + g) * 64, ow, oh, ot, on, 0, 0, 0);
+              }
+            }
           } else {
-            ptx::tma_load_im2col_5d(dst, &tmap_dy, fb, (g0 + g) * 64, ow, oh, ot, on, 0, 0, 0);
+            // ---- N side
+            for (int j = 0; j < p.n_loads; ++j) {
+              const uint32_t dst = ptx::smem_u32(base + (2 + j) * kSlabBytes);
+              const int c0 = nt * p.n_tile + j * 64;
+              if (p.mode == 0) {
+                ptx::tma_load_im2col_5d(dst, &tmap_dy, fb, c0, ow, oh, ot, on, 0, 0, 0);
+              } else {
+                const int dw_ = tap1 % p.kw, dh_ = (tap1 / p.kw) % p.kh, dt_ = tap1 / (p.kw * p.kh);
+                ptx::tma_load_im2col_5d(dst, &tmap_x, fb, c0, cw, ch, cd, on, (uint16_t)dw_, (uint16_t)dh_, (uint16_t)dt_);
+              }
+            }
           }
-        }
-        // ---- N side
-        for (int j = 0; j < p.n_loads; ++j) {
-          const uint32_t dst = ptx::smem_u32(base + (2 + j) * kSlabBytes);
-          const int c0 = nt * p.n_tile + j * 64;
-          if (p.mode == 0) {
-            ptx::tma_load_im2col_5d(dst, &tmap_dy, fb, c0, ow, oh, ot, on, 0, 0, 0);
-          } else {
-            const int dw_ = tap1 % p.kw, dh_ = (tap1 / p.kw) % p.kh, dt_ = tap1 / (p.kw * p.kh);
-            ptx::tma_load_im2col_5d(dst, &tmap_x, fb, c0, cw, ch, cd, on, (uint16_t)dw_, (uint16_t)dh_, (uint16_t)dt_);
-          }
-        }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }

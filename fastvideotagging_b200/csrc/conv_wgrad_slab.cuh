@@ -50,6 +50,7 @@ struct WgradSlabParams {
   // a clip's T*H*W, no padding at frame ends): (0, H*W), maps {C, T*H*W, 1, N} — positions outside the clip come back as
   // zeros, which is exactly the temporal zero padding.
   int tap_frames, tap_pos;
+  int t_stride;                // temporal stride of the convolution (per-frame tiles only): input frame = t * t_stride + ...
   float* dw;
   int w_ohwi;                  // dw layout (O, taps, I) instead of (O, I, taps)
   int dbg_no_store;            // experiments only (fvt_set_option("wgrad_no_store")): epilogue reads TMEM, stores nothing
@@ -62,8 +63,12 @@ struct WgradSlabParams {
 
 // One work item (pixel split, M chunk, N tile) of one layer.  `global_maps`: the tensor maps live in global memory (a
 // group table written by the host) instead of the kernel's parameter space.
-__device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, const CUtensorMap* tmap_dy_p, const WgradSlabParams& p,
+__device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, const CUtensorMap* tmap_dy_p, const WgradSlabParams& p_in,
                                                 int item, uint8_t* smem, bool global_maps) {
+  // A private copy: in the grouped kernel the parameters sit in shared memory behind a generic reference, and every global
+  // store of the epilogue (which may alias anything, as far as the compiler knows) forced the fields it uses to be re-read
+  // — a ~50-clock dependent chain per store (measured: conv5_x group 275 us, 85 us with the stores compiled out).
+  const WgradSlabParams p = p_in;
   const CUtensorMap& tmap_x = *tmap_x_p;
   const CUtensorMap& tmap_dy = *tmap_dy_p;
   const int warp = threadIdx.x >> 5;
@@ -152,7 +157,7 @@ __device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, con
           const int t = nt_ % p.t_frames, n = nt_ / p.t_frames;
           for (int c = 0; c < ncb; ++c)
             tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, b * 128 + (tap_t - p.pt) * p.tap_pos,
-                        t + (tap_t - p.pt) * p.tap_frames, n);
+                        t * p.t_stride + (tap_t - p.pt) * p.tap_frames, n);
           for (int j = 0; j < p.n_blocks; ++j)
             tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, b * 128, t, n);
         }

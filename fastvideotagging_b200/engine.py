@@ -588,7 +588,7 @@ class TrainPlan:
         if os.environ.get("FVT_WGRAD_GROUP", "1") != "0":
             max_rows = int(os.environ.get("FVT_WGRAD_GROUP_ROWS", "65536"))
             for comp, xin_name, xin_shape, a, b, c, d, sc in self.blocks:
-                cand = [L for L in (a, b, c, d) if L.rows <= max_rows and not L.strided]
+                cand = [L for L in (a, b, c, d) if L.rows <= max_rows]
                 if not cand:
                     continue
                 ok = ops.wgrad_group_eligible([L.fwd for L in cand], [L.cout_real for L in cand], [L.cin_real for L in cand], device)

@@ -15,6 +15,9 @@ STAGES = {  # stage: (units, t, hw, c, mid)
     "conv5_x": (5, 4, 7, 512, 1152),
 }
 only = os.environ.get("FVT_ONLY", "")
+for kv in os.environ.get("FVT_DBG_OPTS", "").split(","):
+    if kv:
+        k_, v_ = kv.split("="); assert ops.set_option(k_, int(v_)) == 0
 for stage, (units, t, hw, c, mid) in STAGES.items():
     if only and only not in stage:
         continue
@@ -40,7 +43,7 @@ for stage, (units, t, hw, c, mid) in STAGES.items():
     t1 = timeit(single) if reps > 1 else 0.0
     ref = [L[3].clone() for L in layers]
     t2 = timeit(group.run) if reps > 1 else (group.run(), 0.0)[1]
-    err = max(((L[3] - r).abs().max() / r.abs().max()).item() for L, r in zip(layers, ref))
+    err = max(((L[3] - r).abs().max() / r.abs().max()).item() for L, r in zip(layers, ref)) if reps > 1 else 0.0
     fl = sum(2.0 * N * t * hw * hw * L[4] * L[5] * L[0].kt * L[0].kh * L[0].kw for L in layers)
     print("%s: %d layers  one by one %8.1f us   grouped %8.1f us (grid %d, reduce blocks %d, workspace %.1f MB)  tensor roofline %6.1f us  max rel diff %.2e"
           % (stage, len(layers), t1, t2, group.grid, group.red_blocks, group.ws_bytes / 1e6, fl / 1382.8e12 * 1e6, err), flush=True)
