@@ -150,6 +150,9 @@ def handle(device_index=None):
         out = ctypes.c_void_p()
         check(lib.fvt_create(ctypes.byref(out), int(device_index)))
         h = ctypes.c_void_p(out.value)
+        # FVT_PDL=1: programmatic dependent launch for every hot-path kernel of this handle (csrc/pdl.cuh)
+        if os.environ.get("FVT_PDL", "0") == "1":
+            check(lib.fvt_set_option(h, b"pdl", 1))
         with _handles_lock:
             _handles[key] = h
     return h

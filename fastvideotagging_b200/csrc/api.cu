@@ -24,6 +24,7 @@
 #include "conv_frame_ring.cuh"
 #include "conv_temporal_is.cuh"
 #include "det_sum.cuh"
+#include "pdl.cuh"
 #include "host_common.h"
 
 namespace fvt {
@@ -87,7 +88,8 @@ static std::mutex g_mu;
   X(slab_pair_auto, 1)        /* 0|1|2: CTA-pair slab kernel when the filter fits two SMs but not one (2: also small problems) */ \
   X(slab_pair, 0)             /* 0|1|2: CTA-pair slab kernel for single-SM-stationary layers; 2 = register stores */             \
   X(disable_slab, 0)          /* 1: force the generic im2col kernel (A/B runs, tests) */                                          \
-  X(disable_dgrad_direct, 0)  /* 1: strided data gradients go through fvt_zero_insert instead of the parity sub-convolutions */
+  X(disable_dgrad_direct, 0)  /* 1: strided data gradients go through fvt_zero_insert instead of the parity sub-convolutions */ \
+  X(pdl, 0)                   /* 1: programmatic dependent launch for the kernels of the hot path (pdl.cuh) */
 
 struct Options {
 #define FVT_OPT_FIELD(name, def) int name = def;
@@ -106,6 +108,7 @@ struct fvt_handle_s {
 
 namespace fvt {
 constexpr uint32_t kHandleMagic = 0x46565442u;   // "FVTB"
+bool handle_pdl(fvt_handle_t h) { return h != nullptr && h->opt.pdl != 0; }
 
 
 
@@ -289,6 +292,7 @@ constexpr int kPackTileR = 32, kPackTileK = 64;   // (r, k) tile per CTA (kind 1
 
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const fvt_pack_entry* __restrict__ table, int n_entries) {
+  fvt_pdl_entry();
   __shared__ float tile[kPackTileK][kPackTileR + 1];
   // entry of this CTA: last entry with block0 <= blockIdx.x
   int lo = 0, hi = n_entries - 1;
@@ -391,6 +395,7 @@ static int encode_w_map(const DeviceInfo* di, const void* w, int k_total, int ro
 // dw[i] = sum over k < splits of ws[k][i]   (fixed order)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long elems, int splits, int vec4) {
+  fvt_pdl_entry();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   if (vec4) {
     const long long n4 = elems >> 2;
@@ -419,6 +424,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long l
 // (fixed order: deterministic).  blockDim = (32 elements, 8 split lanes).
 __global__ void __launch_bounds__(256)
 wgrad_reduce_wide_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long elems, int splits) {
+  fvt_pdl_entry();
   __shared__ float part[8][33];
   const int ex = threadIdx.x & 31, j = threadIdx.x >> 5;
   for (long long base = static_cast<long long>(blockIdx.x) * 32; base < elems; base += static_cast<long long>(gridDim.x) * 32) {
@@ -448,11 +454,11 @@ static int wgrad_fit_splits(int wanted, long long elems, const void* ws, size_t 
   return fit < (size_t)wanted ? (int)fit : wanted;
 }
 
-static int wgrad_reduce(const float* ws, float* dw, long long elems, int splits, cudaStream_t stream) {
+static int wgrad_reduce(const float* ws, float* dw, long long elems, int splits, cudaStream_t stream, bool pdl) {
   if (splits >= 16 && elems <= 148ll * 256 * 4) {        // few elements, many slices: spread the slices over threads too
     int blocks = (int)((elems + 31) / 32);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wgrad_reduce_wide_kernel<<<blocks, 256, 0, stream>>>(ws, dw, elems, splits);
+    fvt::launch(wgrad_reduce_wide_kernel, blocks, 256, 0, stream, 1, pdl, ws, dw, elems, splits);
     return check_launch("wgrad_reduce_wide_kernel");
   }
   const int vec4 = ((elems & 3) == 0 && (((uintptr_t)dw) & 15) == 0) ? 1 : 0;
@@ -460,7 +466,7 @@ static int wgrad_reduce(const float* ws, float* dw, long long elems, int splits,
   int blocks = (int)((work + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, dw, elems, splits, vec4);
+  fvt::launch(wgrad_reduce_kernel, blocks, 256, 0, stream, 1, pdl, ws, dw, elems, splits, vec4);
   return check_launch("wgrad_reduce_kernel");
 }
 
@@ -769,10 +775,10 @@ static int try_wgrad_slab(const DeviceInfo* di, const Options& o, const fvt_conv
   CUtensorMap tmx, tmdy;
   if (int e = wgs_encode_maps(di, d, pl.p, x, dy, &tmx, &tmdy)) return e;
   const int smem_bytes = pl.p.stages * pl.p.stage_bytes + 1024;
-  conv_wgrad_slab_kernel<<<pl.items * pl.p.splits, kWgsThreads, smem_bytes, stream>>>(tmx, tmdy, pl.p);
+  fvt::launch(conv_wgrad_slab_kernel, pl.items * pl.p.splits, kWgsThreads, smem_bytes, stream, 1, o.pdl != 0, tmx, tmdy, pl.p);
   if (int e = check_launch("conv_wgrad_slab_kernel")) return e;
   if (pl.p.splits > 1 && !o.wgrad_no_store)
-    if (int e = wgrad_reduce(pl.p.ws, dw, pl.dw_elems, pl.p.splits, stream)) return e;
+    if (int e = wgrad_reduce(pl.p.ws, dw, pl.dw_elems, pl.p.splits, stream, o.pdl != 0)) return e;
   return 1;
 }
 
@@ -951,7 +957,7 @@ int fvt_pack_conv_weights_multi(fvt_handle_t handle, const fvt_pack_entry* table
   int st = 0;
   if (handle_device(handle, &st) == nullptr) return st;
   if (table_dev == nullptr || n_entries <= 0 || total_blocks == 0) return set_error(FVT_ERR_BAD_DESC, "empty pack table");
-  pack_weights_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(table_dev, n_entries);
+  fvt::launch(pack_weights_multi_kernel, (int)total_blocks, 256, 0, (cudaStream_t)stream, 1, handle->opt.pdl != 0, table_dev, n_entries);
   return check_launch("pack_weights_multi_kernel");
 }
 
@@ -1130,10 +1136,12 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
           cfg.blockDim = dim3(kPairThreads);
           cfg.dynamicSmemBytes = smem2;
           cfg.stream = (cudaStream_t)stream;
-          cudaLaunchAttribute attr[1];
+          cudaLaunchAttribute attr[2];
           attr[0].id = cudaLaunchAttributeClusterDimension;
           attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-          cfg.attrs = attr; cfg.numAttrs = 1;
+          attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[1].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr; cfg.numAttrs = o.pdl ? 2 : 1;
           cudaError_t le = cudaLaunchKernelEx(&cfg, conv_slab_pair_kernel, tmx, tmw2, tmy, pp);
           if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "conv_slab_pair_kernel launch: %s", cudaGetErrorString(le));
           return check_launch("conv_slab_pair_kernel");
@@ -1142,9 +1150,9 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       const int m_tiles = sp.frames * sp.tiles_per_frame;
       const int grid = m_tiles < di->sm_count ? m_tiles : di->sm_count;
       if (o.slab_epi_warps == 16)
-        conv_slab_fwd_kernel<16><<<grid, kSlabThreadsWide, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
+        fvt::launch(conv_slab_fwd_kernel<16>, grid, kSlabThreadsWide, smem_bytes, (cudaStream_t)stream, 1, o.pdl != 0, tmx, tmw, sp);
       else
-        conv_slab_fwd_kernel<8><<<grid, kSlabThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, sp);
+        fvt::launch(conv_slab_fwd_kernel<8>, grid, kSlabThreads, smem_bytes, (cudaStream_t)stream, 1, o.pdl != 0, tmx, tmw, sp);
       return check_launch("conv_slab_fwd_kernel");
     }
   }
@@ -1217,10 +1225,12 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       cfg.blockDim = dim3(kPairThreads);
       cfg.dynamicSmemBytes = b_bytes + stages2 * sp.slab_slot_bytes + aux2;
       cfg.stream = (cudaStream_t)stream;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = o.pdl ? 2 : 1;
       cudaError_t le = cudaLaunchKernelEx(&cfg, conv_slab_pair_kernel, tmx, tmw2, tmx, pp);
       if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "conv_slab_pair_kernel(temporal) launch: %s", cudaGetErrorString(le));
       return check_launch("conv_slab_pair_kernel(temporal)");
@@ -1285,7 +1295,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       }
       const int smem_bytes = w_bytes + stages * stage_bytes + out_bytes + aux;
       const int grid = tp.num_items < di->sm_count ? tp.num_items : di->sm_count;
-      conv_temporal_is_kernel<<<grid, kTisThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, tmy, tp);
+      fvt::launch(conv_temporal_is_kernel, grid, kTisThreads, smem_bytes, (cudaStream_t)stream, 1, o.pdl != 0, tmx, tmw, tmy, tp);
       return check_launch("conv_temporal_is_kernel");
     }
   }
@@ -1335,7 +1345,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, bn, &tmw)) return e;
       const int smem_bytes = w_bytes + slots * kRingBlockBytes + aux;
       const int grid = rp.num_items < di->sm_count ? rp.num_items : di->sm_count;
-      conv_frame_ring_kernel<<<grid, kRingThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, rp);
+      fvt::launch(conv_frame_ring_kernel, grid, kRingThreads, smem_bytes, (cudaStream_t)stream, 1, o.pdl != 0, tmx, tmw, rp);
       return check_launch("conv_frame_ring_kernel");
     }
   }
@@ -1450,10 +1460,12 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
       cfg.blockDim = dim3(kConvThreads);
       cfg.dynamicSmemBytes = stages2 * stage2 + kAuxBytes;
       cfg.stream = (cudaStream_t)stream;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = o.pdl ? 2 : 1;
       cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel, tmx, tmw, pp);
       if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "conv_igemm_pair_kernel launch: %s", cudaGetErrorString(le));
       return check_launch("conv_igemm_pair_kernel");
@@ -1463,12 +1475,12 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
 
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < di->sm_count ? tiles : di->sm_count;
-  conv_igemm_fwd_kernel<<<grid, kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p);
+  fvt::launch(conv_igemm_fwd_kernel, grid, kConvThreads, smem_bytes, (cudaStream_t)stream, 1, o.pdl != 0, tmx, tmw, p);
   if (int e = check_launch("conv_igemm_fwd_kernel")) return e;
   if (p.k_splits > 1)
     return launch_splitk_finalize(p.ws, p.k_splits, scale, shift, (d->flags & FVT_CONV_RESIDUAL) ? residual : nullptr, y,
                                   (d->flags & FVT_CONV_STATS) ? stats : nullptr, (size_t)p.m_total, d->cout,
-                                  (d->flags & FVT_CONV_RELU) ? 1 : 0, (cudaStream_t)stream);
+                                  (d->flags & FVT_CONV_RELU) ? 1 : 0, (cudaStream_t)stream, o.pdl != 0);
   return 0;
 }
 
@@ -1598,10 +1610,12 @@ int fvt_unit2p1_fwd(fvt_handle_t handle, const fvt_conv_desc* d_spatial, const f
   cfg.blockDim = dim3(use_is ? kUnitIsThreads : kUnitThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = handle->opt.pdl ? 2 : 1;
   cudaError_t le = use_is ? cudaLaunchKernelEx(&cfg, unit2p1_fused_is_kernel, tmx, tmws, tmwt, u)
                           : cudaLaunchKernelEx(&cfg, unit2p1_fused_kernel, tmx, tmws, tmwt, u);
   if (le != cudaSuccess) return set_error(FVT_ERR_CUDA, "unit2p1_fused_kernel launch: %s", cudaGetErrorString(le));
@@ -1703,9 +1717,9 @@ static int conv3d_wgrad_impl(fvt_handle_t handle, const fvt_conv_desc* d, const 
     if (di->driver_version <= 13010 && (size_t)d->cout * 2 * wo * ho * to * d->n < 131072) reinterpret_cast<uint64_t*>(&tmdy)[1] &= ~(1ull << 21);
   }
   const int grid = items * p.splits;
-  conv_wgrad_kernel<<<grid, kWgradThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmdy, p);
+  fvt::launch(conv_wgrad_kernel, grid, kWgradThreads, smem_bytes, (cudaStream_t)stream, 1, o.pdl != 0, tmx, tmdy, p);
   if (int e = check_launch("conv_wgrad_kernel")) return e;
-  if (p.splits > 1 && !o.wgrad_no_store) return wgrad_reduce(p.ws, dw, dw_elems, p.splits, (cudaStream_t)stream);
+  if (p.splits > 1 && !o.wgrad_no_store) return wgrad_reduce(p.ws, dw, dw_elems, p.splits, (cudaStream_t)stream, o.pdl != 0);
   return 0;
 }
 
@@ -1835,10 +1849,12 @@ int fvt_conv3d_wgrad_group_run(fvt_handle_t handle, const void* host_table, cons
     return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_run: not a table planned by fvt_conv3d_wgrad_group_plan for this device");
   const uint8_t* dev = static_cast<const uint8_t*>(device_table);
   const WgradGroupEntry* ent = reinterpret_cast<const WgradGroupEntry*>(dev + h->entries_off);
-  conv_wgrad_group_kernel<<<h->grid, kWgsThreads, h->smem_bytes, (cudaStream_t)stream>>>(ent, reinterpret_cast<const int2*>(dev + h->cta_map_off));
+  fvt::launch(conv_wgrad_group_kernel, h->grid, kWgsThreads, h->smem_bytes, (cudaStream_t)stream, 1, handle->opt.pdl != 0, ent,
+              reinterpret_cast<const int2*>(dev + h->cta_map_off));
   if (int e = check_launch("conv_wgrad_group_kernel")) return e;
   if (h->red_blocks > 0 && !handle->opt.wgrad_no_store) {
-    wgrad_group_reduce_kernel<<<h->red_blocks, 256, 0, (cudaStream_t)stream>>>(ent, reinterpret_cast<const int2*>(dev + h->red_map_off));
+    fvt::launch(wgrad_group_reduce_kernel, h->red_blocks, 256, 0, (cudaStream_t)stream, 1, handle->opt.pdl != 0, ent,
+                reinterpret_cast<const int2*>(dev + h->red_map_off));
     if (int e = check_launch("wgrad_group_reduce_kernel")) return e;
   }
   return 0;

@@ -5,6 +5,7 @@
 
 #include "../../include/fvt_b200.h"
 #include "host_common.h"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -19,6 +20,7 @@ namespace fvt {
 template <int CU>
 __global__ void stem_unfold_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ u, int n, int t, int h,
                                    int w, int wo, int kw_taps, int sw, int pw, int hpair) {
+  fvt_pdl_entry();
   const size_t total = static_cast<size_t>(n) * t * h * wo;
   const size_t plane = static_cast<size_t>(h) * w;           // one (n, c, t) frame
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -59,6 +61,7 @@ __global__ void stem_unfold_kernel(const float* __restrict__ x, __nv_bfloat16* _
 __global__ void pool_fc_kernel(const __nv_bfloat16* __restrict__ x, int positions, int c, int c_real,
                                const float* __restrict__ w, const float* __restrict__ b, int num_class,
                                float* __restrict__ pooled, float* __restrict__ logits) {
+  fvt_pdl_entry();
   extern __shared__ float sp[];   // [c]
   const int n = blockIdx.x;
   const __nv_bfloat16* xn = x + static_cast<size_t>(n) * positions * c;
@@ -102,8 +105,8 @@ static int stem_unfold_launch(fvt_handle_t handle, const float* x_ncdhw, void* u
   const size_t total = static_cast<size_t>(n) * t * h * wo;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  stem_unfold_kernel<32><<<static_cast<int>(blocks), 256, 0, (cudaStream_t)stream>>>(
-      x_ncdhw, (__nv_bfloat16*)u, n, t, h, w, wo, kw_taps, sw, pw, hpair);
+  fvt::launch(stem_unfold_kernel<32>, static_cast<int>(blocks), 256, 0, (cudaStream_t)stream, 1, handle_pdl(handle),
+              x_ncdhw, (__nv_bfloat16*)u, n, t, h, w, wo, kw_taps, sw, pw, hpair);
   return check_launch("stem_unfold_kernel");
 }
 
@@ -124,8 +127,8 @@ int fvt_pool_fc_fwd(fvt_handle_t handle, const void* x, int32_t n, int32_t posit
   if (logits != nullptr && (w == nullptr || num_class <= 0)) return set_error(FVT_ERR_BAD_DESC, "logits requested without weights");
   int st = 0;
   if (handle_device(handle, &st) == nullptr) return st;
-  pool_fc_kernel<<<n, 512, c * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, positions, c, c_real, w, b,
-                                                                       num_class, pooled, logits);
+  fvt::launch(pool_fc_kernel, n, 512, c * sizeof(float), (cudaStream_t)stream, 1, handle_pdl(handle), (const __nv_bfloat16*)x, positions,
+              c, c_real, w, b, num_class, pooled, logits);
   return check_launch("pool_fc_kernel");
 }
 

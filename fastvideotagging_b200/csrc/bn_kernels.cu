@@ -23,6 +23,7 @@
 #include "../../include/fvt_b200.h"
 #include "host_common.h"
 #include "det_sum.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -52,6 +53,7 @@ __global__ void bn_finalize_kernel(const unsigned long long* __restrict__ stats,
                                    float* __restrict__ running_var, int c_store, int c_real, double inv_rows, float eps,
                                    float momentum, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  fvt_pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= c_store) return;
   if (c >= c_real) {                      // pad channels: identity-zero so they stay exactly 0
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                 const uint4* __restrict__ res, const float* __restrict__ res_scale, const float* __restrict__ res_shift,
                 uint4* __restrict__ out, size_t rows, int cvec, int relu, const BnFinalizeArgs fin) {
+  fvt_pdl_entry();
   extern __shared__ float cst[];                     // [4][C]: scale, shift, res_scale, res_shift
   const int c_store = cvec * 8;
   for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
@@ -192,6 +195,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ da
                      const float* __restrict__ mean,
                      const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
                      unsigned long long* __restrict__ acc, size_t rows, int cvec, int c_store) {
+  fvt_pdl_entry();
   extern __shared__ float sred[];                    // [3][C] constants, then [blockDim.x][16] fold area
   float* cst = sred;
   float* fold = sred + 3 * c_store;
@@ -272,6 +276,7 @@ bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dac
                     const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
                     const unsigned long long* __restrict__ acc, float* __restrict__ sums, uint4* __restrict__ draw,
                     uint4* __restrict__ dz_out, size_t rows, int cvec, int c_store, int c_real, float inv_rows, int acc_raw) {
+  fvt_pdl_entry();
   extern __shared__ float cst[];      // [6][C]: a = gamma*inv_std, a*dbeta/M, a*inv_std*dgamma/M, mean, relu scale, relu shift
   for (int ch = threadIdx.x; ch < c_store; ch += blockDim.x) {
     const float is = invstd[ch];
@@ -353,6 +358,7 @@ bn_bwd_apply_kernel(const uint4* __restrict__ raw, const uint4* __restrict__ dac
 __global__ void __launch_bounds__(256)
 zero_insert_kernel(const uint4* __restrict__ dy, uint4* __restrict__ up, int n, int t, int h, int w, int to, int ho,
                    int wo, int st, int sh, int sw, int cvec) {
+  fvt_pdl_entry();
   const size_t total = static_cast<size_t>(n) * t * h * w * cvec;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -380,6 +386,7 @@ __global__ void pool_fc_bwd_kernel(const float* __restrict__ dlogits, const floa
                                    const float* __restrict__ w, int n, int num_class, int c, int positions,
                                    float* __restrict__ dw, float* __restrict__ db, __nv_bfloat16* __restrict__ dx,
                                    int c_store) {
+  fvt_pdl_entry();
   // grid.x = n (dx part) + num_class (dw/db part)
   if (blockIdx.x < n) {
     const int in = blockIdx.x;
@@ -416,6 +423,7 @@ __global__ void __launch_bounds__(256)
 sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tensors, const unsigned int* __restrict__ chunk_tensor,
                           const unsigned int* __restrict__ chunk_offset, float lr, float momentum, float rescale,
                           unsigned int chunk_elems) {
+  fvt_pdl_entry();
   const SgdTensor t = tensors[chunk_tensor[blockIdx.x]];
   const unsigned long long start = static_cast<unsigned long long>(chunk_offset[blockIdx.x]) * chunk_elems;
   unsigned long long end = start + chunk_elems;
@@ -438,6 +446,7 @@ __global__ void __launch_bounds__(256)
 splitk_finalize_kernel(const float4* __restrict__ ws, int splits, size_t slice_vec4, const float* __restrict__ scale,
                        const float* __restrict__ shift, const uint4* __restrict__ res, uint4* __restrict__ y,
                        unsigned long long* __restrict__ stats, size_t rows, int cvec, int c_store, int relu) {
+  fvt_pdl_entry();
   extern __shared__ float sred[];                    // [blockDim.x][16] (statistics only)
   const int tpr = blockDim.x / cvec;
   const int cv = threadIdx.x % cvec;
@@ -540,15 +549,15 @@ static int rows_launch(size_t rows, int cvec, int* blocks, int* threads) {
 }
 
 int launch_splitk_finalize(const float* ws, int splits, const float* scale, const float* shift, const void* residual, void* y,
-                           unsigned long long* stats, size_t rows, int c_store, int relu, cudaStream_t stream) {
+                           unsigned long long* stats, size_t rows, int c_store, int relu, cudaStream_t stream, bool pdl) {
   int blocks, threads;
   if (c_store % 8 || rows_launch(rows, c_store / 8, &blocks, &threads)) return set_error(FVT_ERR_BAD_DESC, "split-K finalize: bad channel count");
   // one row per thread per iteration here: rows_launch sized the grid for kUnroll rows per iteration
   size_t b = (rows + (threads / (c_store / 8)) - 1) / (threads / (c_store / 8));
   if (b > 148 * 8) b = 148 * 8;
-  splitk_finalize_kernel<<<static_cast<int>(b), threads, stats ? threads * 16 * sizeof(float) : 0, stream>>>(
-      reinterpret_cast<const float4*>(ws), splits, rows * static_cast<size_t>(c_store) / 4, scale, shift, (const uint4*)residual,
-      (uint4*)y, stats, rows, c_store / 8, c_store, relu);
+  fvt::launch(splitk_finalize_kernel, static_cast<int>(b), threads, stats ? threads * 16 * sizeof(float) : 0, stream, 1, pdl,
+              reinterpret_cast<const float4*>(ws), splits, rows * static_cast<size_t>(c_store) / 4, scale, shift, (const uint4*)residual,
+              (uint4*)y, stats, rows, c_store / 8, c_store, relu);
   return check_launch("splitk_finalize_kernel");
 }
 
@@ -558,11 +567,11 @@ using namespace fvt;
 
 static int launch_bn_apply(const void* raw, const float* scale, const float* shift, const void* res, const float* res_scale,
                            const float* res_shift, void* out, int64_t rows, int c_store, int relu, const BnFinalizeArgs& fin,
-                           int blocks, int threads, cudaStream_t stream) {
+                           int blocks, int threads, cudaStream_t stream, bool pdl) {
   const int res_mode = res == nullptr ? 0 : (res_scale ? 2 : 1);
   const size_t smem = sizeof(float) * 4 * c_store;
-#define FVT_BN_APPLY(M) bn_apply_kernel<M><<<blocks, threads, smem, stream>>>( \
-      (const uint4*)raw, scale, shift, (const uint4*)res, res_scale, res_shift, (uint4*)out, rows, c_store / 8, relu, fin)
+#define FVT_BN_APPLY(M) fvt::launch(bn_apply_kernel<M>, blocks, threads, smem, stream, 1, pdl, \
+      (const uint4*)raw, scale, shift, (const uint4*)res, res_scale, res_shift, (uint4*)out, (size_t)rows, c_store / 8, relu, fin)
   if (res_mode == 0) FVT_BN_APPLY(0); else if (res_mode == 1) FVT_BN_APPLY(1); else FVT_BN_APPLY(2);
 #undef FVT_BN_APPLY
   return check_launch("bn_apply_kernel");
@@ -601,9 +610,9 @@ int fvt_bn_finalize(fvt_handle_t handle, const void* stats_acc, const float* gam
   if (handle_device(handle, &st) == nullptr) return st;
   if (!stats_acc || !gamma || !beta || !scale || !shift || !mean || !invstd) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   if (c_store <= 0 || c_real <= 0 || c_real > c_store || rows <= 0) return set_error(FVT_ERR_BAD_DESC, "bad bn_finalize extent");
-  bn_finalize_kernel<<<(c_store + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      (const unsigned long long*)stats_acc, gamma, beta, running_mean, running_var, c_store, c_real, 1.0 / static_cast<double>(rows), eps,
-      momentum, scale, shift, mean, invstd);
+  fvt::launch(bn_finalize_kernel, (c_store + 127) / 128, 128, 0, (cudaStream_t)stream, 1, handle_pdl(handle),
+              (const unsigned long long*)stats_acc, gamma, beta, running_mean, running_var, c_store, c_real, 1.0 / static_cast<double>(rows), eps,
+              momentum, scale, shift, mean, invstd);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -620,7 +629,7 @@ int fvt_bn_apply(fvt_handle_t handle, const void* raw, const float* scale, const
   BnFinalizeArgs fin;
   memset(&fin, 0, sizeof(fin));
   return launch_bn_apply(raw, scale, shift, res, res_scale, res_shift, out, rows, c_store, relu, fin, blocks, threads,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, handle_pdl(handle));
 }
 
 int fvt_bn_finalize_apply(fvt_handle_t handle, const void* stats_acc, const float* gamma, const float* beta, float* running_mean,
@@ -640,7 +649,7 @@ int fvt_bn_finalize_apply(fvt_handle_t handle, const void* stats_acc, const floa
   fin.scale_out = scale; fin.shift_out = shift; fin.mean_out = mean; fin.invstd_out = invstd;
   fin.c_real = c_real; fin.inv_rows = 1.0 / static_cast<double>(rows); fin.eps = eps; fin.momentum = momentum;
   return launch_bn_apply(raw, nullptr, nullptr, res, res_scale, res_shift, out, rows, c_store, relu, fin, blocks, threads,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, handle_pdl(handle));
 }
 
 int fvt_bn_backward(fvt_handle_t handle, const void* raw, const void* dact, const void* mask, const float* mean,
@@ -665,8 +674,8 @@ int fvt_bn_backward(fvt_handle_t handle, const void* raw, const void* dact, cons
     // every CTA ends with one exact add per channel and quantity into the SAME 2*C accumulators: keep the grid at what is
     // resident anyway (3 CTAs per SM) — 1184 CTAs queued 1184 same-address reductions per channel at the L2 (+4.5 us per launch)
     const int rblocks = blocks < 148 * 3 ? blocks : 148 * 3;
-#define FVT_BN_RED(M) bn_bwd_reduce_kernel<M><<<rblocks, threads, smem_r, (cudaStream_t)stream>>>( \
-      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, relu_scale, relu_shift, acc, rows, c_store / 8, c_store)
+#define FVT_BN_RED(M) fvt::launch(bn_bwd_reduce_kernel<M>, rblocks, threads, smem_r, (cudaStream_t)stream, 1, handle_pdl(handle), \
+      (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, relu_scale, relu_shift, acc, (size_t)rows, c_store / 8, c_store)
     if (mask_mode == 0) FVT_BN_RED(0); else if (mask_mode == 1) FVT_BN_RED(1); else FVT_BN_RED(2);
 #undef FVT_BN_RED
     if (int e = check_launch("bn_bwd_reduce_kernel")) return e;
@@ -674,9 +683,9 @@ int fvt_bn_backward(fvt_handle_t handle, const void* raw, const void* dact, cons
     mask_mode = 0;                                   // the producer already applied the ReLU mask
   }
   const size_t smem_a = sizeof(float) * 6 * c_store;
-#define FVT_BN_APP(M, D) bn_bwd_apply_kernel<M, D><<<blocks, threads, smem_a, (cudaStream_t)stream>>>( \
+#define FVT_BN_APP(M, D) fvt::launch(bn_bwd_apply_kernel<M, D>, blocks, threads, smem_a, (cudaStream_t)stream, 1, handle_pdl(handle), \
       (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, invstd, gamma, relu_scale, relu_shift, acc, sums, \
-      (uint4*)draw, (uint4*)dz_out, rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows), dz_in == 2 ? 1 : 0)
+      (uint4*)draw, (uint4*)dz_out, (size_t)rows, c_store / 8, c_store, c_real, 1.0f / static_cast<float>(rows), dz_in == 2 ? 1 : 0)
   if (dz_out != nullptr) {
     if (mask_mode == 0) FVT_BN_APP(0, true); else if (mask_mode == 1) FVT_BN_APP(1, true); else FVT_BN_APP(2, true);
   } else {
@@ -695,8 +704,8 @@ int fvt_zero_insert(fvt_handle_t handle, const void* dy, void* up, int32_t n, in
   const size_t total = static_cast<size_t>(n) * t * h * w * (c_store / 8);
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  zero_insert_kernel<<<static_cast<int>(blocks), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)up, n, t, h, w, to, ho,
-                                                                                 wo, st_, sh, sw, c_store / 8);
+  fvt::launch(zero_insert_kernel, static_cast<int>(blocks), 256, 0, (cudaStream_t)stream, 1, handle_pdl(handle), (const uint4*)dy,
+              (uint4*)up, n, t, h, w, to, ho, wo, st_, sh, sw, c_store / 8);
   return check_launch("zero_insert_kernel");
 }
 
@@ -705,8 +714,8 @@ int fvt_pool_fc_bwd(fvt_handle_t handle, const float* dlogits, const float* pool
   if (!dlogits || !pooled || !w || !dw || !db || !dx) return set_error(FVT_ERR_BAD_DESC, "null pointer");
   int st = 0;
   if (handle_device(handle, &st) == nullptr) return st;
-  pool_fc_bwd_kernel<<<n + num_class, 256, 0, (cudaStream_t)stream>>>(dlogits, pooled, w, n, num_class, c, positions, dw, db,
-                                                                      (__nv_bfloat16*)dx, c_store);
+  fvt::launch(pool_fc_bwd_kernel, n + num_class, 256, 0, (cudaStream_t)stream, 1, handle_pdl(handle), dlogits, pooled, w, n, num_class,
+              c, positions, dw, db, (__nv_bfloat16*)dx, c_store);
   return check_launch("pool_fc_bwd_kernel");
 }
 
@@ -716,8 +725,8 @@ int fvt_sgd_momentum_multi(fvt_handle_t handle, const void* tensor_table, const 
   if (!tensor_table || !chunk_tensor || !chunk_offset || num_chunks <= 0) return set_error(FVT_ERR_BAD_DESC, "bad sgd table");
   int st = 0;
   if (handle_device(handle, &st) == nullptr) return st;
-  sgd_momentum_multi_kernel<<<num_chunks, 256, 0, (cudaStream_t)stream>>>((const SgdTensor*)tensor_table, chunk_tensor,
-                                                                          chunk_offset, lr, momentum, rescale, chunk_elems);
+  fvt::launch(sgd_momentum_multi_kernel, num_chunks, 256, 0, (cudaStream_t)stream, 1, handle_pdl(handle), (const SgdTensor*)tensor_table,
+              chunk_tensor, chunk_offset, lr, momentum, rescale, chunk_elems);
   return check_launch("sgd_momentum_multi_kernel");
 }
 

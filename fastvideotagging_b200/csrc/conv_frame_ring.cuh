@@ -21,6 +21,7 @@
 #include "epilogue.cuh"
 #include "det_sum.cuh"
 #include "conv_slab.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -49,6 +50,7 @@ struct FrameRingParams {
 __global__ void __launch_bounds__(kRingThreads, 1)
 conv_frame_ring_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        const FrameRingParams p) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

@@ -21,6 +21,7 @@
 #include "ptx.cuh"
 #include "epilogue.cuh"
 #include "det_sum.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                       const __grid_constant__ CUtensorMap tmap_w,
                       const ConvKernelParams p) {
+  fvt_pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -17,6 +17,7 @@
 #pragma once
 #include "conv_igemm.cuh"
 #include "conv_slab_pair.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -42,6 +43,7 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        const ConvKernelParams p) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5;

@@ -20,6 +20,7 @@
 #include "ptx.cuh"
 #include "epilogue.cuh"
 #include "det_sum.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -71,6 +72,7 @@ template <int kEpiWarps>
 __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1)
 conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const SlabParams p) {
+  fvt_pdl_entry();
   constexpr int kThreads = 128 + 32 * kEpiWarps;
   constexpr int kEpiThreads = 32 * kEpiWarps;
   extern __shared__ __align__(1024) uint8_t smem[];

@@ -38,6 +38,7 @@
 #include "epilogue.cuh"
 #include "det_sum.cuh"
 #include "conv_slab.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -127,6 +128,7 @@ __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* tmap, 
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_slab_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ CUtensorMap tmap_y, const SlabPairParams pp) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   const SlabParams& p = pp.s;
   const int warp = threadIdx.x >> 5;

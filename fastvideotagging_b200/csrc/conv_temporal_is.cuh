@@ -18,6 +18,7 @@
 #include "epilogue.cuh"
 #include "det_sum.cuh"
 #include "conv_slab.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -49,6 +50,7 @@ constexpr int kTisOutTileBytes = 128 * 128;     // [128 positions x 64 channels]
 __global__ void __launch_bounds__(kTisThreads, 1)
 conv_temporal_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_y, const TemporalIsParams p) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

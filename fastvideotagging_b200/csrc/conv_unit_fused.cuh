@@ -30,6 +30,7 @@
 #include "epilogue.cuh"
 #include "conv_slab.cuh"
 #include "conv_slab_pair.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -102,6 +103,7 @@ struct Segments {
 __global__ void __launch_bounds__(kUnitThreads, 1)
 unit2p1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_ws,
                      const __grid_constant__ CUtensorMap tmap_wt, const UnitFusedParams p) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

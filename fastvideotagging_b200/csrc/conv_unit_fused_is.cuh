@@ -24,6 +24,7 @@
 // Replaces the Conv3D / BatchNorm / Activation / add chain of reference model/R2Plus1.py:27-38,59-62,76-81.
 #pragma once
 #include "conv_unit_fused.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -42,6 +43,7 @@ constexpr int kUnitIsDCol0 = 320;          // first TMEM column of the 192-colum
 __global__ void __launch_bounds__(kUnitIsThreads, 1)
 unit2p1_fused_is_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_ws,
                         const __grid_constant__ CUtensorMap tmap_wt, const UnitFusedParams p) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

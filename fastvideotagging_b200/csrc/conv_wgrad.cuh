@@ -16,6 +16,7 @@
 // Replaces the cuDNN backward-filter calls MXNet issues for the Conv3D layers of model/R2Plus1.py / net.py.
 #pragma once
 #include "ptx.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -51,6 +52,7 @@ struct WgradParams {
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                   const WgradParams p) {
+  fvt_pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;

@@ -21,6 +21,7 @@
 #pragma once
 #include "ptx.cuh"
 #include "conv_slab.cuh"
+#include "pdl.cuh"
 
 namespace fvt {
 
@@ -257,6 +258,7 @@ __device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, con
 __global__ void __launch_bounds__(kWgsThreads, 1)
 conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                        const WgradSlabParams p) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   wgrad_slab_body(&tmap_x, &tmap_dy, p, blockIdx.x, smem, false);
 }
@@ -277,6 +279,7 @@ struct __align__(128) WgradGroupEntry {
 
 __global__ void __launch_bounds__(kWgsThreads, 1)
 conv_wgrad_group_kernel(const WgradGroupEntry* __restrict__ entries, const int2* __restrict__ cta_map) {
+  fvt_pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int2 m = cta_map[blockIdx.x];
   const WgradGroupEntry* e = entries + m.x;
@@ -295,6 +298,7 @@ conv_wgrad_group_kernel(const WgradGroupEntry* __restrict__ entries, const int2*
 constexpr int kWgrChunk = 4096;
 __global__ void __launch_bounds__(256)
 wgrad_group_reduce_kernel(const WgradGroupEntry* __restrict__ entries, const int2* __restrict__ red_map) {
+  fvt_pdl_entry();
   const int2 m = red_map[blockIdx.x];
   const WgradSlabParams& p = entries[m.x].p;
   const long long elems = p.ws_split_stride;

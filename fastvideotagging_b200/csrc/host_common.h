@@ -17,10 +17,12 @@ const DeviceInfo* current_device_info(int* status);
 // Validates `h` (fvt_create) and that its device is the calling thread's current device; nullptr (and *status < 0) otherwise.
 const DeviceInfo* handle_device(fvt_handle_t h, int* status);
 const DeviceInfo* device_info(int device, int* status);
+// The handle's "pdl" option (programmatic dependent launch, pdl.cuh).
+bool handle_pdl(fvt_handle_t h);
 int sm_count_of(const DeviceInfo* di);
 // Epilogue pass of a split-K convolution (bn_kernels.cu): sum of the `splits` fp32 slices ws[split][rows][c_store], in split
 // order -> y bf16 (+ exact per-channel statistics of the bf16-rounded raw output).
 int launch_splitk_finalize(const float* ws, int splits, const float* scale, const float* shift, const void* residual, void* y,
-                           unsigned long long* stats, size_t rows, int c_store, int relu, cudaStream_t stream);
+                           unsigned long long* stats, size_t rows, int c_store, int relu, cudaStream_t stream, bool pdl);
 
 }  // namespace fvt
