@@ -1829,7 +1829,22 @@ int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_d
     if (pl.p.splits > 1)
       for (long long c = 0; c < (pl.dw_elems + kWgrChunk - 1) / kWgrChunk; ++c) red_map[rb++] = make_int2((int)e, (int)c);
   }
-  std::stable_sort(ctas.begin(), ctas.end(), [](const Cta& a, const Cta& b) { return a.clk > b.clk; });
+  // CTA order.  Layers whose operands fit the 126 MB L2 several at a time: longest items first, the classic list-scheduling
+  // order (conv4_x, 22 layers: 254 us against 273 us layer after layer).  Large layers (conv2_x at batch 4: 167 MB of
+  // operands each): layer after layer, so that the CTAs running at the same time read the same tensors — longest-first
+  // interleaves all layers and every operand tile then comes from HBM several times (ncu on 12 conv2_x layers: 3.7 GB of
+  // DRAM reads for 2.0 GB of operands; 906 -> 826 us).
+  size_t operand_bytes = 0;                                        // of the largest layer
+  for (int l : member) {
+    int to, ho, wo;
+    conv_out_shape(&descs[l], &to, &ho, &wo);
+    const size_t b = 2 * ((size_t)descs[l].n * descs[l].t * descs[l].h * descs[l].w * descs[l].cin + (size_t)descs[l].n * to * ho * wo * descs[l].cout);
+    if (b > operand_bytes) operand_bytes = b;
+  }
+  const char* order_env = getenv("FVT_WGRAD_GROUP_ORDER");          // experiments: 1 = longest first, 2 = layer after layer
+  const int order = order_env != nullptr ? atoi(order_env) : 0;
+  if (order == 1 || (order == 0 && operand_bytes <= (size_t)64 << 20))
+    std::stable_sort(ctas.begin(), ctas.end(), [](const Cta& a, const Cta& b) { return a.clk > b.clk; });
   for (size_t i = 0; i < ctas.size(); ++i) cta_map[i] = make_int2(ctas[i].entry, ctas[i].item);
   h->magic = kWgradGroupMagic;
   h->n_entries = (int)member.size(); h->grid = (int)grid; h->red_blocks = (int)red_blocks; h->smem_bytes = smem_max; h->device = handle->device;

@@ -311,7 +311,7 @@ class InferencePlan:
                 return self._forward_body(x, want_features, want_map)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with _capture(graph):
                 out = self._forward_body(x, want_features, want_map)
             entry = (graph, out, x)                  # the clip tensor is kept alive: the graph reads its address
             self._graphs[key] = entry
@@ -460,6 +460,29 @@ class FlatParams:
         return buf[off:off + store]
 
 
+import contextlib
+import gc
+
+
+@contextlib.contextmanager
+def _capture(graph):
+    """torch.cuda.graph(graph) with Python's cyclic garbage collector held off for the duration of the capture.  The
+    capture runs in CUDA's global capture mode, where e.g. destroying another plan's graphs, streams or events is "not
+    permitted while a stream is capturing" and invalidates the capture; torch collects garbage once on entry, but a
+    capture of several hundred launches allocates enough Python objects to trigger further collections — which then
+    finalise whatever cyclic garbage an earlier network left behind (seen as a flaky cudaErrorStreamCaptureInvalidated
+    when two networks are trained one after the other in one process)."""
+    was = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was:
+            gc.enable()
+
+
 class _TLayer:
     __slots__ = ("spec", "fwd", "dgr", "w_name", "cin_real", "cout_real", "cin_s", "cout_s", "rows", "in_shape",
                  "out_shape", "src", "raw", "act", "stats", "scale", "shift", "mean", "invstd", "wp", "wpd", "w_eq",
@@ -586,7 +609,7 @@ class TrainPlan:
         self._groups = {}                # stage key -> [layers]  (ops.WgradGroup built on first use: needs flat.g)
         self._group_obj = {}
         if os.environ.get("FVT_WGRAD_GROUP", "1") != "0":
-            max_rows = int(os.environ.get("FVT_WGRAD_GROUP_ROWS", "65536"))
+            max_rows = int(os.environ.get("FVT_WGRAD_GROUP_ROWS", "500000"))
             for comp, xin_name, xin_shape, a, b, c, d, sc in self.blocks:
                 cand = [L for L in (a, b, c, d) if L.rows <= max_rows]
                 if not cand:
@@ -755,7 +778,7 @@ class TrainPlan:
                 self._join_side()
                 return out
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with _capture(graph):
                 self.weights_version = -1               # the graph always re-packs: weights change every step
                 self.refresh_weights(0)
                 self._logits_static = self._forward_body(self.x_static)
@@ -942,7 +965,7 @@ class TrainPlan:
                 self._warm_bwd += 1
                 return self._backward_body(self.dlogits_static)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with _capture(graph):
                 self._backward_body(self.dlogits_static)
                 if self.finish_hook is not None:        # gradient all-reduces launched during capture join here
                     self.finish_hook()
