@@ -1448,7 +1448,8 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     const long long items = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const bool stats_with_affine = (d->flags & FVT_CONV_STATS) && scale != nullptr && !bnbwd;
     if (ext == nullptr && o.igemm_pair && !p.b_stationary && p.k_splits == 1 && bn_g >= 128 && di->sm_count % 2 == 0 && stages2 >= 3 &&
-        !stats_with_affine && (items >= 3ll * (di->sm_count / 2) || o.igemm_pair == 2)) {
+        !stats_with_affine && (items >= 2ll * (di->sm_count / 2) || o.igemm_pair == 2)) {     // measured: two rounds of pairs pay (conv3_x 288->128
+                                                                                              // data gradient at batch 4: 42 -> 36 us), one does not (conv4_x forward +13 %)
       ConvKernelParams pp = p;
       pp.stages = stages2;
       if (int e = encode_w_map(di, w_packed, taps * d->cin, rows, n_half, &tmw)) return e;
