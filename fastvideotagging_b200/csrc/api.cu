@@ -82,6 +82,7 @@ static std::mutex g_mu;
   X(wgrad_no_store, 0)        /* experiments only: the weight-gradient epilogue reads TMEM and stores nothing */                 \
   X(wgrad_no_flat, 0)         /* 1: temporal weight gradients tile every frame on its own (round-1 tiling) instead of the        \
                                  flattened T*H*W positions of a clip */                                                          \
+  X(wgrad_no_taps_n, 0)       /* 1: temporal weight gradients of <= 64-output-channel layers keep the taps on the M side */      \
   X(unit_input_stationary, 1) /* fused (2+1)D unit: temporal conv as one N = 192 MMA chain per mid frame                         \
                                  (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame */                     \
   X(igemm_pair, 1)            /* 0|1|2: generic im2col convolution on CTA pairs (K1p) for the wide streamed-weight layers */     \
@@ -521,7 +522,10 @@ static int wgs_plan_temporal(const DeviceInfo* di, const Options& o, const fvt_c
   // tiles of 128 consecutive positions of a clip (flattened T*H*W) unless frames already are whole tiles; a temporally
   // strided convolution (the first 3x1x1 of conv3_x .. conv5_x) keeps per-frame tiles: output frame t reads input frames
   // t*st + tap - pt
-  const bool flat = (hw % 128) != 0 && !o.wgrad_no_flat && d->st == 1;
+  // taps on the N side (see WgradSlabParams::taps_on_n): per-frame tiles, <= 64 stored output channels
+  const bool taps_n = !o.wgrad_no_taps_n && d->st == 1 && d->cout <= 64 && d->kt * 64 <= 256 && hw >= 96 &&
+                      (double)hw / (((hw + 127) / 128) * 128.0) >= 0.85;
+  const bool flat = (hw % 128) != 0 && !o.wgrad_no_flat && d->st == 1 && !taps_n;
   if (!flat && hw < (d->st == 1 ? 96 : 40)) return 0;
   if (flat && (long long)d->t * hw < 96) return 0;
   WgradSlabParams& p = pl->p;
@@ -529,6 +533,7 @@ static int wgs_plan_temporal(const DeviceInfo* di, const Options& o, const fvt_c
   p.temporal = 1;
   p.kt = d->kt; p.pt = d->pt;
   p.t_stride = d->st;
+  p.taps_on_n = taps_n ? 1 : 0;
   if (flat) {
     p.hw = d->t * hw; p.t_frames = 1; p.tap_frames = 0; p.tap_pos = hw;
   } else {
@@ -550,8 +555,9 @@ static int wgs_plan_temporal(const DeviceInfo* di, const Options& o, const fvt_c
   double best = 1e30;
   int best_nt = 0, best_mt = 0, best_splits = 1;
   double best_item = 0, best_fixed = 0;
-  for (int nt = (d->cout + 255) / 256; nt <= (grouped ? 4 : (d->cout + 255) / 256); ++nt) {
-    const int n_tile = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
+  const int tap_items = taps_n ? 1 : d->kt;              // work items along the filter taps
+  for (int nt = (d->cout + 255) / 256; nt <= (grouped && !taps_n ? 4 : (d->cout + 255) / 256); ++nt) {
+    const int n_tile = taps_n ? d->kt * 64 : ((d->cout + nt - 1) / nt + 15) / 16 * 16;
     if (nt > 1 && n_tile * (nt - 1) >= d->cout) continue;
     const int acc_stride = (n_tile + 31) / 32 * 32;
     const int n_blocks = (n_tile + 63) / 64;
@@ -561,7 +567,7 @@ static int wgs_plan_temporal(const DeviceInfo* di, const Options& o, const fvt_c
     for (int m = 1; m <= mt_max; ++m) {
       const int ncb = 2 * m < p.cin_blocks ? 2 * m : p.cin_blocks;
       if (2 * (ncb * p.slab_slot_bytes + n_blocks * 128 * 128) + kAux > kSmemMax) continue;
-      const int chunks = (mt_total + m - 1) / m * d->kt;
+      const int chunks = (mt_total + m - 1) / m * tap_items;
       const int items_m = chunks * nt;
       const double mma_clk = (double)m * p.ksteps * (n_tile > 128 ? n_tile / 2.0 : 64.0);
       const double bytes = (double)(ncb + n_blocks) * 128.0 * 128.0;
@@ -589,12 +595,12 @@ static int wgs_plan_temporal(const DeviceInfo* di, const Options& o, const fvt_c
   }
   if (best_nt == 0) return 0;
   p.n_tiles = best_nt;
-  p.n_tile = ((d->cout + best_nt - 1) / best_nt + 15) / 16 * 16;
+  p.n_tile = taps_n ? d->kt * 64 : ((d->cout + best_nt - 1) / best_nt + 15) / 16 * 16;
   p.acc_stride = (p.n_tile + 31) / 32 * 32;
   p.n_blocks = (p.n_tile + 63) / 64;
   p.mt_per_cta = best_mt;
   p.chunks_per_tap = (mt_total + best_mt - 1) / best_mt;
-  p.m_chunks = p.chunks_per_tap * d->kt;
+  p.m_chunks = p.chunks_per_tap * tap_items;
   p.ncb_max = 2 * best_mt < p.cin_blocks ? 2 * best_mt : p.cin_blocks;
   p.stage_bytes = p.ncb_max * p.slab_slot_bytes + p.n_blocks * 128 * 128;
   p.stages = (kSmemMax - kAux) / p.stage_bytes;

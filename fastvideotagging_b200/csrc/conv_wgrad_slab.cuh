@@ -52,6 +52,13 @@ struct WgradSlabParams {
   // zeros, which is exactly the temporal zero padding.
   int tap_frames, tap_pos;
   int t_stride;                // temporal stride of the convolution (per-frame tiles only): input frame = t * t_stride + ...
+  // taps_on_n (temporal, per-frame tiles, stride 1, <= 64 output channels: conv2_x 144 -> 64, the stem's 45 -> 64): the
+  // filter taps move from the M side to the N side.  A tile loads the INPUT frame block once (all channel blocks) and the
+  // kt OUTPUT-gradient frame blocks t+pt, t+pt-1, .. that pair with it, side by side as one N = kt*64 operand (the
+  // descriptor's leading-dimension offset steps from block to block): dW[tap][ci, co] += X[t]^T dY[t + pt - tap].
+  // One N = 192 instruction instead of three N = 64 ones (a tcgen05.mma costs max(64, N/2) clocks), and X — the large
+  // operand — is read once instead of once per tap.
+  int taps_on_n;
   float* dw;
   int w_ohwi;                  // dw layout (O, taps, I) instead of (O, I, taps)
   int dbg_no_store;            // experiments only (fvt_set_option("wgrad_no_store")): epilogue reads TMEM, stores nothing
@@ -87,9 +94,10 @@ __device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, con
   const int chunk = item % p.m_chunks; item /= p.m_chunks;
   const int split = item;
   // spatial: groups g = cb*taps + tap over the whole filter;  temporal: this CTA's tap is fixed, groups = channel blocks
-  const int tap_t = p.temporal ? chunk / p.chunks_per_tap : 0;
+  const int tap_c = (p.temporal && !p.taps_on_n) ? chunk / p.chunks_per_tap : 0;      // the tap this CTA's chunk index encodes
+  const int tap_t = p.taps_on_n ? p.pt : tap_c;                                        // the tap whose input frame it loads
   const int n_groups = p.temporal ? p.cin_blocks : p.groups;
-  const int g_lo = (p.temporal ? chunk - tap_t * p.chunks_per_tap : chunk) * 2 * p.mt_per_cta;
+  const int g_lo = (p.temporal ? chunk - tap_c * p.chunks_per_tap : chunk) * 2 * p.mt_per_cta;
   int g_hi = g_lo + 2 * p.mt_per_cta;
   if (g_hi > n_groups) g_hi = n_groups;
   const int mt_count = (g_hi - g_lo + 1) >> 1;
@@ -132,6 +140,8 @@ __device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, con
   const uint32_t tmem_base = *tmem_slot;
   const int dy_off = p.ncb_max * p.slab_slot_bytes;      // dY blocks follow the X slabs inside a stage
 
+  // (Measured: issuing the dY boxes from a second warp — as the generic kernel K3 now does — changes nothing here: the
+  // boxes are 15-30 KB, the loop is not bound by its issuing thread.)
   if (warp == 0) {
     // ===================================================== producer
     int stage = 0;
@@ -159,8 +169,13 @@ __device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, con
           for (int c = 0; c < ncb; ++c)
             tma_load_4d(base + c * p.slab_slot_bytes, &tmap_x, fb, (cb_lo + c) * 64, b * 128 + (tap_t - p.pt) * p.tap_pos,
                         t * p.t_stride + (tap_t - p.pt) * p.tap_frames, n);
-          for (int j = 0; j < p.n_blocks; ++j)
-            tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, b * 128, t, n);
+          if (p.taps_on_n) {
+            for (int j = 0; j < p.n_blocks; ++j)          // N block j = filter tap j: the output frame that input frame t feeds through it
+              tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, 0, b * 128, t + p.pt - j, n);
+          } else {
+            for (int j = 0; j < p.n_blocks; ++j)
+              tma_load_4d(base + dy_off + j * (128 * 128), &tmap_dy, fb, nt * p.n_tile + j * 64, b * 128, t, n);
+          }
         }
       }
       __syncwarp();
@@ -236,10 +251,12 @@ __device__ __forceinline__ void wgrad_slab_body(const CUtensorMap* tmap_x_p, con
           float* dst = p.ws != nullptr ? p.ws + static_cast<size_t>(split) * p.ws_split_stride : p.dw;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = nt * p.n_tile + c + j;
+            const int col = nt * p.n_tile + c + j;
+            const int co = p.taps_on_n ? (col & 63) : col;
+            const int tp = p.taps_on_n ? (col >> 6) : tap;
             if (co < p.cout_real) {
-              const size_t idx = p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tap) * p.cin_real + ci
-                                          : (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap;
+              const size_t idx = p.w_ohwi ? (static_cast<size_t>(co) * p.taps + tp) * p.cin_real + ci
+                                          : (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tp;
               dst[idx] = __uint_as_float(v[j]);                               // a warp writes 32 consecutive floats (OHWI)
             }
           }

@@ -799,6 +799,8 @@ def test_grouped_wgrad_matches_single_launches(cuda_device, lib):
         (2, 8, 28, 28, 288, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # conv3_x temporal: long pixel range -> split + slice reduction
         (2, 4, 14, 14, 256, 921, (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # strided: not in the group (run behind it)
         (2, 4, 14, 14, 230, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # channel counts with padding (230 -> 240 stored)
+        (2, 6, 28, 28, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),       # conv2_x temporal: taps on the N side (N = 192)
+        (2, 6, 28, 28, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),        # stem temporal: one (padded) channel block, taps on N
     ]
     layers, refs = [], []
     for n, t, h, w, cin, cout, k, s, p in shapes:
@@ -818,7 +820,7 @@ def test_grouped_wgrad_matches_single_launches(cuda_device, lib):
         y.backward(dy[..., :cout].float().permute(0, 4, 1, 2, 3))
         refs.append((single, w0.grad.permute(0, 2, 3, 4, 1)))
     group = ops.WgradGroup(layers, cuda_device)
-    assert group.in_group == [True, True, True, True, True, False, True]
+    assert group.in_group == [True, True, True, True, True, False, True, True, True]
     assert group.red_blocks > 0                      # at least the conv3_x layer is split
     group.run()
     torch.cuda.synchronize()

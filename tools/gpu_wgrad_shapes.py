@@ -30,6 +30,9 @@ SHAPES = [  # name, t, h, w, cin, cout, kernel, stride, pad
     ("shortcut 1x1x1/s2 256->512", 8, 14, 14, 256, 512, (1, 1, 1), (2, 2, 2), (0, 0, 0)),
 ]
 only = os.environ.get("FVT_ONLY", "")
+for kv in os.environ.get("FVT_DBG_OPTS", "").split(","):
+    if kv:
+        k_, v_ = kv.split("="); assert ops.set_option(k_, int(v_)) == 0
 tot = tot_ideal = 0.0
 for name, t, h, w, cin, cout, k, s, p in SHAPES:
     if only and only not in name:
