@@ -673,7 +673,12 @@ int fvt_bn_backward(fvt_handle_t handle, const void* raw, const void* dact, cons
     const size_t smem_r = sizeof(float) * (3 * c_store + threads * 16);
     // every CTA ends with one exact add per channel and quantity into the SAME 2*C accumulators: keep the grid at what is
     // resident anyway (3 CTAs per SM) — 1184 CTAs queued 1184 same-address reductions per channel at the L2 (+4.5 us per launch)
-    const int rblocks = blocks < 148 * 3 ? blocks : 148 * 3;
+    // ... and every CTA ends with 4 integer reductions per channel (2 quantities x 2 limbs): 444 CTAs x 576 channels are a
+    // million same-address reductions queued at the L2 slices (measured inside a replayed graph: 27 us for the reduce pass
+    // of a 7 MB conv4_x tensor, most of it that queue) — wide layers get fewer, longer CTAs (<= ~300k reductions)
+    int rblocks = blocks < 148 * 3 ? blocks : 148 * 3;
+    const int by_channels = 300000 / (4 * c_store);
+    if (rblocks > by_channels) rblocks = by_channels < 74 ? 74 : by_channels;
 #define FVT_BN_RED(M) fvt::launch(bn_bwd_reduce_kernel<M>, rblocks, threads, smem_r, (cudaStream_t)stream, 1, handle_pdl(handle), \
       (const uint4*)raw, (const uint4*)dact, (const uint4*)mask, mean, relu_scale, relu_shift, acc, (size_t)rows, c_store / 8, c_store)
     if (mask_mode == 0) FVT_BN_RED(0); else if (mask_mode == 1) FVT_BN_RED(1); else FVT_BN_RED(2);
