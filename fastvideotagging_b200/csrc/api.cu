@@ -1363,11 +1363,21 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
   // packed weights are plain K-major rows, so any tile width that divides the packed row count reads the same buffer —
   // until the tiles fill one wave.  That is one launch, deterministic, and needs no workspace; split-K (below) is kept
   // for the cases where even 64-column tiles leave the reduction long.
+  // Measured inside a replayed graph (tools/gpu_small_conv_tiles.py): tiles narrower than 128 columns run the MMAs at half
+  // rate (max(64, N/2) clocks each) and re-read the A tile once per N tile, so when the reduction is long enough to split
+  // (a workspace is given, >= 32 k-blocks) the N tile stops at 128 columns and split-K fills the machine instead
+  // (conv5_x 1152 -> 512 data gradient: 32 -> 24 us).
   int bn_g = bn0;
   if (d->block_n == 0) {
     const int m_tiles = (p.m_total + kBlockM - 1) / kBlockM;
+    const int k_blocks_all = taps * ((d->cin + kBlockK - 1) / kBlockK);
+    // (not for the training forward: the split-K finalize pass would also have to produce the BatchNorm statistics, and with
+    // them it costs more than the split saves — conv5_x 512 -> 1152 with statistics: 22 us unsplit, 30 us split)
+    const bool can_split = ext == nullptr && !bnbwd && !(d->flags & FVT_CONV_STATS) && !o.disable_split_k && workspace != nullptr &&
+                           k_blocks_all >= 32;
+    const int cand_lo = can_split ? 128 : 64;
     if (m_tiles * (rows / bn0) < di->sm_count) {
-      for (int cand = 64; cand < bn0; cand += 16) {
+      for (int cand = cand_lo; cand < bn0; cand += 16) {
         if (rows % cand) continue;
         if (m_tiles * (rows / cand) <= di->sm_count) { bn_g = cand; break; }
       }
@@ -1430,7 +1440,7 @@ static int conv3d_fwd_impl(fvt_handle_t handle, const fvt_conv_desc* d, const vo
     if (ext == nullptr && !bnbwd && !o.disable_split_k && !p.b_stationary && workspace != nullptr && workspace_bytes >= 2 * slice && ((uintptr_t)workspace & 15) == 0 &&
         2 * tiles <= di->sm_count && k_blocks >= 8) {
       int splits = di->sm_count / tiles;
-      if (splits > k_blocks / 32) splits = k_blocks / 32;      // a split must keep >= 32 k-blocks, else the finalize pass costs more than it saves
+      if (splits > k_blocks / 16) splits = k_blocks / 16;      // a split must keep >= 16 k-blocks, else the finalize pass costs more than it saves
       if (splits > 8) splits = 8;
       if ((size_t)splits > workspace_bytes / slice) splits = (int)(workspace_bytes / slice);
       if (splits >= 2) {

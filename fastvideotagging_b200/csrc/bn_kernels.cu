@@ -555,6 +555,13 @@ int launch_splitk_finalize(const float* ws, int splits, const float* scale, cons
   // one row per thread per iteration here: rows_launch sized the grid for kUnroll rows per iteration
   size_t b = (rows + (threads / (c_store / 8)) - 1) / (threads / (c_store / 8));
   if (b > 148 * 8) b = 148 * 8;
+  if (stats != nullptr) {
+    // every CTA ends with 4 integer reductions per channel into the same accumulators: one row per CTA meant 784 x 2304 x 2
+    // of them for a conv5_x layer (32 us for a 3.6 MB tensor) — wide layers get fewer CTAs that walk several rows
+    size_t by_channels = 300000 / (4 * static_cast<size_t>(c_store));
+    if (by_channels < 74) by_channels = 74;
+    if (b > by_channels) b = by_channels;
+  }
   fvt::launch(splitk_finalize_kernel, static_cast<int>(b), threads, stats ? threads * 16 * sizeof(float) : 0, stream, 1, pdl,
               reinterpret_cast<const float4*>(ws), splits, rows * static_cast<size_t>(c_store) / 4, scale, shift, (const uint4*)residual,
               (uint4*)y, stats, rows, c_store / 8, c_store, relu);

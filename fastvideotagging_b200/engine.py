@@ -927,8 +927,16 @@ class TrainPlan:
     def _can_fuse_bn(self, L):
         """The data gradient of L feeds exactly one BatchNorm backward whose ReLU mask comes from its own raw output: fusable
         unless L is strided (its data gradient runs as parity sub-convolutions onto a lattice)."""
-        return (self.fuse_bnbwd and L.dplan is None and not L.strided and L.rows <= self.fuse_bnbwd_rows and
-                "dgrad" not in self._skip and "bnbwd" not in self._skip)
+        if not (self.fuse_bnbwd and L.dplan is None and not L.strided and L.rows <= self.fuse_bnbwd_rows and
+                "dgrad" not in self._skip and "bnbwd" not in self._skip):
+            return False
+        # The fused epilogue needs the whole reduction in one CTA: a data gradient with few output tiles and a long
+        # reduction (conv5_x 1152 -> 512: 28 tiles, 162 k-blocks) runs faster split over K with the two-pass BatchNorm
+        # backward behind it (measured inside a replayed graph: 27.7 us against 46.9 us fused)
+        k = L.spec.kernel
+        tiles = ((L.rows + 127) // 128) * ((L.cin_s + 127) // 128)
+        k_blocks = k[0] * k[1] * k[2] * ((L.cout_s + 63) // 64)
+        return not (2 * tiles <= 148 and k_blocks >= 32)
 
     def _dgrad(self, L, draw, out, residual=None, fuse_bn=None):
         """Data gradient of L.  fuse_bn = the producer layer P of L's input (act_P = relu(bn(raw_P))): the epilogue masks with
