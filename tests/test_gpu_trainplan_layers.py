@@ -248,6 +248,25 @@ def _check_config(device, n, t, num_class, seed):
         report.append("%-24s %-13s raw %.1e act %.1e bnbwd %.1e wgrad %.1e dgrad %.1e" % (name, spec.role, e_raw, e_act, e_bn, e_wg, e_dg))
     print("\n".join(report))
     assert len(report) >= 17, "R(2+1)D-34 has 17 distinct conv geometries (incl. the 3 projection shortcuts and the stem)"
+    # ---------------- the plan's GROUPED weight-gradient launches (one per residual stage) at these shapes: every layer's
+    # result equals the single-layer launch checked against the oracle above, up to fp32 summation order (the group uses
+    # fewer pixel splits)
+    assert plan._groups, "the plan defers its stride-1 weight gradients to grouped launches"
+    for key, layers in plan._groups.items():
+        for L in layers:                                  # fresh operands in the plan's own buffers (pad channels are never stored)
+            L.draw_own.normal_()
+            L.draw_own.mul_(0.05)
+            plan.bufs[L.src].normal_()
+        plan._run_group(key)
+        plan._join_side()
+        torch.cuda.synchronize()
+        for L in layers:
+            got = flat.raw(flat.g, L.w_name).detach().clone()
+            single = ops.conv3d_wgrad(L.fwd, plan.bufs[L.src], L.draw_own, torch.empty_like(got), L.cout_real, L.cin_real, ohwi=True)
+            torch.cuda.synchronize()
+            scale = float(single.abs().max())
+            assert scale > 0 and torch.isfinite(got).all(), L.spec.name
+            assert float((got - single).abs().max()) <= 1e-4 * scale, (L.spec.name, "grouped vs single weight gradient")     # fp32 order over up to 401408 positions
     return net, plan, params, x, ref_logits
 
 
