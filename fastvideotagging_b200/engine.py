@@ -609,7 +609,7 @@ class TrainPlan:
         self._groups = {}                # stage key -> [layers]  (ops.WgradGroup built on first use: needs flat.g)
         self._group_obj = {}
         if os.environ.get("FVT_WGRAD_GROUP", "1") != "0":
-            max_rows = int(os.environ.get("FVT_WGRAD_GROUP_ROWS", "500000"))
+            max_rows = int(os.environ.get("FVT_WGRAD_GROUP_ROWS", "1000000"))
             for comp, xin_name, xin_shape, a, b, c, d, sc in self.blocks:
                 cand = [L for L in (a, b, c, d) if L.rows <= max_rows]
                 if not cand:
