@@ -840,6 +840,23 @@ class TrainPlan:
         hi = max(self.flat.slots[n][0] + self.flat.slots[n][3] for n in names)
         self.grad_hook(lo, hi)
 
+    def _ready_from_side(self, name_lists):
+        """Hand finished gradient slices to the reducer FROM the side stream: a block's (or a stage's grouped) weight
+        gradients finish there, and the all-reduce is then ordered behind them without the main stream waiting — it goes
+        on with the next block's data-gradient chain.  (Round 1 joined the side stream into the main stream here; with the
+        grouped launches that serialised 1.6 ms of weight-gradient kernels with the chain whenever a reducer was attached:
+        2 GPUs 9.76 -> 9.43 ms/step, the single-GPU time.)"""
+        if self.grad_hook is None:
+            return
+        if self.side is None:
+            for nm in name_lists:
+                self._ready(*nm)
+            return
+        self.side.wait_stream(torch.cuda.current_stream(self.device))     # BatchNorm parameter gradients come from the main stream
+        with torch.cuda.stream(self.side):
+            for nm in name_lists:
+                self._ready(*nm)
+
     def _bn_bwd(self, L, dact, mask, draw, dz_out=None):
         """mask: True = ReLU directly after this BatchNorm (mask recomputed from raw); a tensor = ReLU after a residual join
         (mask by that tensor's sign); None = no ReLU; "fused" = `dact` already is the masked gradient and L.bnacc holds
@@ -1040,15 +1057,10 @@ class TrainPlan:
                 pending.append(names)
                 if stage_ends:
                     self._run_group(stage)
-                    if self.grad_hook is not None:
-                        self._join_side()
-                    for nm in pending:
-                        self._ready(*nm)
+                    self._ready_from_side(pending)
                     pending = []
             else:
-                if self.grad_hook is not None:
-                    self._join_side()             # the block's weight gradients must be final before they are reduced
-                self._ready(*names)
+                self._ready_from_side([names])
             self._mark("bwd:block%s" % comp)
         # stem
         other = "gB" if cur_key == "gA" else "gA"
