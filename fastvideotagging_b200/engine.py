@@ -637,8 +637,9 @@ class TrainPlan:
         # layers, and every weight gradient runs beside the data-gradient chain it does not feed.  At batch 4 the
         # conv4_x / conv5_x launches fill 14-49 of the 148 SMs, so the two branches genuinely overlap.
         self.side = torch.cuda.Stream(device=device) if os.environ.get("FVT_SIDE_STREAM", "1") != "0" else None
-        self._packed_ev = None
-        self._pack_f = self._pack_d = None
+        self._packed_ev = self._packed_ev_early = None
+        self._pack_f = self._pack_d = self._pack_f_early = None
+        self._early = set()
         self.dgrad_direct = os.environ.get("FVT_DGRAD_DIRECT", "1") != "0"
         self._busy = {}                  # scratch buffer name -> event recorded after its last reader on the side stream
         self._draw_i = 0
@@ -685,10 +686,19 @@ class TrainPlan:
         (ops.PackTable); the stem's equivalent filter (a 45 x 64 x 5 tensor re-expressed over the W-unfolded input) keeps
         its own small path."""
         self._pack_f, self._pack_d = ops.PackTable(self.device), ops.PackTable(self.device)
+        # the stem's temporal conv and the first stage (conv2_x: 1 MB of weights) get a launch of their own, so that the
+        # forward pass does not wait for the 250 MB of conv3_x..conv5_x filters before its second convolution (measured:
+        # the main stream idled ~0.19 ms at the start of every step behind the one-launch pack)
+        self._pack_f_early = ops.PackTable(self.device)
+        first_stage = self._stage_of[self.blocks[0][0]] if self.blocks else None
+        self._early = {self.stem1.spec.name}
+        for comp, _, _, a, b, c, d, sc in self.blocks:
+            if self._stage_of[comp] == first_stage:
+                self._early.update(L.spec.name for L in (a, b, c, d) + ((sc,) if sc is not None else ()))
         for L in self.layers.values():
             if L is self.stem0:
                 continue
-            L.wp = self._pack_f.add_fwd(L.fwd, self._w_raw(L))
+            L.wp = (self._pack_f_early if L.spec.name in self._early else self._pack_f).add_fwd(L.fwd, self._w_raw(L))
         for L in reversed(list(self.layers.values())):
             if not L.need_dgrad:
                 continue
@@ -704,7 +714,7 @@ class TrainPlan:
         stream the packing launches form a branch parallel to the forward pass: the forward-layout copies (the stem's
         first, then everything else in one launch; the first conv after the stem waits for it, `_wait_packed`), then the
         data-gradient copies, joined by `_join_side()` at the end of the forward pass."""
-        self._packed_ev = None
+        self._packed_ev = self._packed_ev_early = None
         if version == self.weights_version:
             return
         if self._pack_f is None:
@@ -713,12 +723,16 @@ class TrainPlan:
         L0 = self.stem0
         if self.side is None:
             L0.wp = ops.pack_conv_weight(L0.fwd, self.stem.weight(self._w(L0)), out=L0.wp)
+            self._pack_f_early.run()
             self._pack_f.run()
             self._pack_d.run()
         else:
             self.side.wait_stream(main)
             L0.wp = ops.pack_conv_weight(L0.fwd, self.stem.weight(self._w(L0)), out=L0.wp)     # tiny: on the main stream
             with torch.cuda.stream(self.side):
+                self._pack_f_early.run()
+                self._packed_ev_early = torch.cuda.Event()
+                self._packed_ev_early.record(self.side)
                 self._pack_f.run()
                 self._packed_ev = torch.cuda.Event()
                 self._packed_ev.record(self.side)
@@ -726,10 +740,16 @@ class TrainPlan:
         self.weights_version = version
 
     def _wait_packed(self, L):
-        if L is self.stem0 or self._packed_ev is None:
+        if L is self.stem0:
             return
-        torch.cuda.current_stream(self.device).wait_event(self._packed_ev)
-        self._packed_ev = None
+        if L.spec.name in self._early:
+            if self._packed_ev_early is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._packed_ev_early)
+                self._packed_ev_early = None
+            return
+        if self._packed_ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._packed_ev)
+            self._packed_ev = None
 
     def _join_side(self):
         if self.side is not None:
