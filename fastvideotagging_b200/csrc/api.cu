@@ -4,7 +4,6 @@
 #include <cuda_bf16.h>
 #include <stdarg.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <new>
@@ -83,6 +82,8 @@ static std::mutex g_mu;
   X(wgrad_no_flat, 0)         /* 1: temporal weight gradients tile every frame on its own (round-1 tiling) instead of the        \
                                  flattened T*H*W positions of a clip */                                                          \
   X(wgrad_no_taps_n, 0)       /* 1: temporal weight gradients of <= 64-output-channel layers keep the taps on the M side */      \
+  X(wgrad_group_order, 0)     /* grouped weight gradients, CTA order: 0 auto, 1 longest items first, 2 layer after layer */      \
+  X(wgrad_group_debug, 0)     /* 1: fvt_conv3d_wgrad_group_plan prints the plan of every layer to stderr */                      \
   X(unit_input_stationary, 1) /* fused (2+1)D unit: temporal conv as one N = 192 MMA chain per mid frame                         \
                                  (conv_unit_fused_is.cuh) instead of three N = 64 chains per output frame */                     \
   X(igemm_pair, 1)            /* 0|1|2: generic im2col convolution on CTA pairs (K1p) for the wide streamed-weight layers */     \
@@ -1838,7 +1839,7 @@ int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_d
     const int smem = pl.p.stages * pl.p.stage_bytes + 1024;
     if (smem > smem_max) smem_max = smem;
     const double clk = pl.item_clk / pl.p.splits + pl.fixed_clk;
-    if (getenv("FVT_WGRAD_DEBUG") != nullptr)
+    if (o.wgrad_group_debug)
       fprintf(stderr, "[fvt wgrad group] layer %d %s cin %d cout %d tiles %d: n_tile %d x%d, mt %d, chunks %d, splits %d -> %d CTAs, stages %d x %d B, "
               "est %.0f clk/CTA (share %.0f)\n", l, pl.p.temporal ? "temporal" : "spatial", descs[l].cin, descs[l].cout, pl.p.num_tiles, pl.p.n_tile,
               pl.p.n_tiles, pl.p.mt_per_cta, pl.p.m_chunks, pl.p.splits, pl.items * pl.p.splits, pl.p.stages, pl.p.stage_bytes, clk, share);
@@ -1858,8 +1859,7 @@ int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_d
     const size_t b = 2 * ((size_t)descs[l].n * descs[l].t * descs[l].h * descs[l].w * descs[l].cin + (size_t)descs[l].n * to * ho * wo * descs[l].cout);
     if (b > operand_bytes) operand_bytes = b;
   }
-  const char* order_env = getenv("FVT_WGRAD_GROUP_ORDER");          // experiments: 1 = longest first, 2 = layer after layer
-  const int order = order_env != nullptr ? atoi(order_env) : 0;
+  const int order = o.wgrad_group_order;                           // experiments: 1 = longest first, 2 = layer after layer
   if (order == 1 || (order == 0 && operand_bytes <= (size_t)64 << 20))
     std::stable_sort(ctas.begin(), ctas.end(), [](const Cta& a, const Cta& b) { return a.clk > b.clk; });
   for (size_t i = 0; i < ctas.size(); ++i) cta_map[i] = make_int2(ctas[i].entry, ctas[i].item);
