@@ -359,6 +359,31 @@ pack_weights_multi_kernel(const fvt_pack_entry* __restrict__ table, int n_entrie
       src_taps = e.src_k[0] * e.src_k[1] * e.src_k[2];
     }
     // here cout_real / cin_real are the FORWARD filter counts: k runs over forward output channels, r over forward inputs
+    if ((e.cin_real & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && blockDim.x == 256) {
+      // 16-byte path: 4 input channels per load (a [64 k x 32 r] tile = 512 float4), 8 output channels per store
+      for (int i = threadIdx.x; i < kPackTileK * (kPackTileR / 4); i += 256) {
+        const int kk = i / (kPackTileR / 4), r4 = (i - kk * (kPackTileR / 4)) * 4;
+        const int k = k0 + kk, r = r0 + r4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < e.cout_real && r < e.cin_real)
+          v = __ldg(reinterpret_cast<const float4*>(w + (static_cast<size_t>(k) * src_taps + tap) * e.cin_real + r));
+        tile[kk][r4] = v.x; tile[kk][r4 + 1] = v.y; tile[kk][r4 + 2] = v.z; tile[kk][r4 + 3] = v.w;
+      }
+      __syncthreads();
+      {
+        const int rr = threadIdx.x >> 3, kk = (threadIdx.x & 7) * 8;          // 32 rows x 8 segments of 8 output channels
+        const int r = r0 + rr, k = k0 + kk;
+        if (r < e.rows && k < e.k_store) {                                     // k_store is a multiple of 16: whole segments
+          uint4 q;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(tile[kk][rr], tile[kk + 1][rr]), t1 = __floats2bfloat162_rn(tile[kk + 2][rr], tile[kk + 3][rr]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(tile[kk + 4][rr], tile[kk + 5][rr]), t3 = __floats2bfloat162_rn(tile[kk + 6][rr], tile[kk + 7][rr]);
+          q.x = *reinterpret_cast<uint32_t*>(&t0); q.y = *reinterpret_cast<uint32_t*>(&t1);
+          q.z = *reinterpret_cast<uint32_t*>(&t2); q.w = *reinterpret_cast<uint32_t*>(&t3);
+          *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * e.taps + u) * e.k_store + k) = q;
+        }
+      }
+      return;
+    }
     for (int i = threadIdx.x; i < kPackTileK * kPackTileR; i += blockDim.x) {
       const int kk = i / kPackTileR, rr = i - kk * kPackTileR;
       const int k = k0 + kk, r = r0 + rr;
