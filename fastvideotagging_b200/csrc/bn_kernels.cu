@@ -429,6 +429,34 @@ sgd_momentum_multi_kernel(const SgdTensor* __restrict__ tensors, const unsigned 
   unsigned long long end = start + chunk_elems;
   if (end > t.numel) end = t.numel;
   const float lrt = lr * t.lr_mult;
+  // 16-byte path (the flat buffers keep every slot 16-byte aligned and chunks start at multiples of 65536 elements): four
+  // elements per thread and access — the scalar loop below ran at 4.8 TB/s over the 1.27 GB the update moves
+  if (((reinterpret_cast<uintptr_t>(t.w) | reinterpret_cast<uintptr_t>(t.g) | reinterpret_cast<uintptr_t>(t.mom)) & 15) == 0 && (start & 3) == 0) {
+    const unsigned long long n4 = (end - start) >> 2;
+    float4* w4 = reinterpret_cast<float4*>(t.w + start);
+    const float4* g4 = reinterpret_cast<const float4*>(t.g + start);
+    float4* m4 = reinterpret_cast<float4*>(t.mom + start);
+    for (unsigned long long i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 w = w4[i];
+      const float4 g = g4[i];
+      float4 m = m4[i];
+      m.x = momentum * m.x - lrt * fmaf(rescale, g.x, t.wd * w.x);
+      m.y = momentum * m.y - lrt * fmaf(rescale, g.y, t.wd * w.y);
+      m.z = momentum * m.z - lrt * fmaf(rescale, g.z, t.wd * w.z);
+      m.w = momentum * m.w - lrt * fmaf(rescale, g.w, t.wd * w.w);
+      w.x += m.x; w.y += m.y; w.z += m.z; w.w += m.w;
+      m4[i] = m;
+      w4[i] = w;
+    }
+    for (unsigned long long i = start + (n4 << 2) + threadIdx.x; i < end; i += blockDim.x) {
+      const float w = t.w[i];
+      const float gp = fmaf(rescale, t.g[i], t.wd * w);
+      const float m = momentum * t.mom[i] - lrt * gp;
+      t.mom[i] = m;
+      t.w[i] = w + m;
+    }
+    return;
+  }
   for (unsigned long long i = start + threadIdx.x; i < end; i += blockDim.x) {
     const float w = t.w[i];
     const float gp = fmaf(rescale, t.g[i], t.wd * w);
