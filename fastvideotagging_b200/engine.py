@@ -493,8 +493,13 @@ class TrainPlan:
     """Shape-specialised training step: forward with batch-statistics BatchNorm (reference semantics inside
     autograd.record(), model/R2Plus1.py:73-82 + A4) and the full backward pass, on the C-ABI kernels.
 
-    forward:   per conv  K1(+stats) -> K5 finalize -> K6 apply(+residual)(+ReLU)
-    backward:  per conv  K7 (reduce + apply) -> K3 wgrad -> K1 dgrad (zero-insert first when strided)
+    forward:   per conv  K1(+stats) -> finalize + apply(+residual)(+ReLU) in one launch; bf16 operand copies of the weights
+               re-packed on the side stream (first stage first)
+    backward:  per conv  BatchNorm backward (one pass when the data gradient that produced its input fused the sums, else
+               reduce + apply) -> data gradient (K1 / K1s2 / K1p; strided layers as parity sub-convolutions);
+               weight gradients: deferred per residual stage into ONE grouped launch (K3g) on the side stream — strided and
+               1x1x1 layers launch their own (K3) — and handed to the gradient reducer from that stream
+    Everything is deterministic (exact BatchNorm sums, slice reductions in split order): two runs give the same bits.
     """
 
     def __init__(self, flat, aux, model_depth, num_class, pool, eps, n, t, h, w, device, momentum=0.9):
