@@ -1082,8 +1082,9 @@ class TrainPlan:
                 pending.append(names)
                 if stage_ends:
                     self._run_group(stage)
-                    self._ready_from_side(pending)
-                    pending = []
+                    if bi + 1 < len(rblocks):             # the last stage's slices go out together with the stem's (below):
+                        self._ready_from_side(pending)    # one small all-reduce at the end of the step instead of two
+                        pending = []
             else:
                 self._ready_from_side([names])
             self._mark("bwd:block%s" % comp)
@@ -1101,7 +1102,7 @@ class TrainPlan:
         for L in (self.stem0, self.stem1):
             names += [L.w_name, L.spec.bn + "_gamma", L.spec.bn + "_beta"]
         self._mark("bwd:stem")
+        self._ready_from_side(pending + [names])          # behind the stem's weight gradients on the side stream
         self._join_side()
         self._busy.clear()
-        self._ready(*names)
         self._mark("bwd:joined")
