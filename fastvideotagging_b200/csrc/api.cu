@@ -1863,7 +1863,10 @@ int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_d
   if (x == nullptr || dy == nullptr || dw == nullptr) return set_error(FVT_ERR_BAD_DESC, "null tensor pointer array");
   if (ws_need > 0 && (workspace == nullptr || workspace_bytes < ws_need || (((uintptr_t)workspace) & 15) != 0))
     return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_plan: the group needs %zu bytes of 16-byte aligned workspace", ws_need);
-  uint8_t* base = static_cast<uint8_t*>(host_table);
+  // The table is assembled in 128-byte aligned scratch (its entries hold CUtensorMaps and are declared 128-byte aligned;
+  // the caller's host buffer may have any alignment) and copied out at the end.
+  std::vector<uint8_t> scratch(total + 128);
+  uint8_t* base = scratch.data() + ((128 - (reinterpret_cast<uintptr_t>(scratch.data()) & 127)) & 127);
   memset(base, 0, total);
   WgradGroupHeader* h = reinterpret_cast<WgradGroupHeader*>(base);
   WgradGroupEntry* ent = reinterpret_cast<WgradGroupEntry*>(base + entries_off);
@@ -1913,6 +1916,7 @@ int fvt_conv3d_wgrad_group_plan(fvt_handle_t handle, int32_t n, const fvt_conv_d
   h->n_entries = (int)member.size(); h->grid = (int)grid; h->red_blocks = (int)red_blocks; h->smem_bytes = smem_max; h->device = handle->device;
   h->entries_off = (int64_t)entries_off; h->cta_map_off = (int64_t)cta_off; h->red_map_off = (int64_t)red_off;
   h->total_bytes = (int64_t)total; h->ws_bytes = (int64_t)ws_need;
+  memcpy(host_table, base, total);
   return 0;
 }
 
@@ -1922,7 +1926,9 @@ int fvt_conv3d_wgrad_group_run(fvt_handle_t handle, const void* host_table, cons
   if (di == nullptr) return st;
   if (host_table == nullptr || device_table == nullptr || (((uintptr_t)device_table) & 127) != 0)
     return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_run: host_table / 128-byte aligned device_table required");
-  const WgradGroupHeader* h = static_cast<const WgradGroupHeader*>(host_table);
+  WgradGroupHeader hdr;
+  memcpy(&hdr, host_table, sizeof(hdr));                     // the caller's host copy may have any alignment
+  const WgradGroupHeader* h = &hdr;
   if (h->magic != kWgradGroupMagic || h->device != handle->device || h->grid <= 0)
     return set_error(FVT_ERR_BAD_DESC, "fvt_conv3d_wgrad_group_run: not a table planned by fvt_conv3d_wgrad_group_plan for this device");
   const uint8_t* dev = static_cast<const uint8_t*>(device_table);
