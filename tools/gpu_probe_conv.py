@@ -48,7 +48,9 @@ def run_case(name, n, t, h, w, cin, cout, k, s, p, relu=False, res=False, affine
     dt = time.time() - t0
     yc = y.float().cpu()
     err = (yc[..., :cout] - yref).abs()
-    tol = 2e-2 + 1e-2 * yref.abs()
+    # north-star tolerance for the bf16 path: 1e-2 relative per element; the absolute floor (values near zero) is 1e-3 of the
+    # tensor's max — the kernel's only roundings are the bf16 store (2^-9 relative) and fp32 summation order
+    tol = 1e-3 * yref.abs().max() + 1e-2 * yref.abs()
     bad = (err > tol)
     padbad = yc[..., cout:].abs().max().item() if cout_s > cout else 0.0
     ok = (not bad.any().item()) and padbad == 0.0
